@@ -1,0 +1,231 @@
+/*
+ * ox_b200.h — C ABI of libox_b200.so: the B200-native batched `mj_step` path
+ * behind oxide_control's `Physics` API.
+ *
+ * Every entry point below replaces one call the reference makes into
+ * `rusty_mujoco` (reference = /root/reference, cited as src/...:line):
+ *
+ *   ox_model_from_xml_path      <- Physics::from_xml        src/physics.rs:12-16  (mj_loadXML + mj_makeData)
+ *   ox_model_from_xml_string    <- Physics::from_xml_string src/physics.rs:18-24  (mj_parseXMLString + mj_compile + mjs_getError)
+ *   ox_batch_create             <- mj_makeData              src/physics.rs:14,22  (batched: nenv copies of mjData, SoA on device)
+ *   ox_batch_step               <- Physics::step            src/physics.rs:44-46  (mj_step)      ** the hot path **
+ *   ox_batch_forward            <- Physics::forward         src/physics.rs:48-50  (mj_forward)
+ *   ox_batch_reset              <- Physics::reset           src/physics.rs:52-54  (mj_resetData, masked)
+ *   ox_model_name2id/id2name    <- object_id / object_name  src/physics.rs:56-62
+ *   ox_batch_set1/get1, set/get <- Actuators::set, time/ctrl/act/qpos/qvel/qacc_warmstart/qfrc_applied/
+ *                                  xfrc_applied getters+setters src/physics.rs:65-171, and data() src/physics.rs:30
+ *
+ * Conventions:
+ *   - every function returns ox_status (0 = OK) unless it returns a size or a pointer;
+ *     ox_last_error_message() returns a thread-local NUL-terminated string owned by the library.
+ *   - "feature absent" (stateless actuator, non-mocap body, no plugin) is OX_ABSENT, which the
+ *     Rust wrapper maps to Option::None exactly as src/physics.rs:96-102,125-131,154-170 do.
+ *   - parse errors map to Error::Mujoco, compile errors to Error::Mjs(msg) (src/error.rs:4-6).
+ *   - divergence (NaN / |x| > mjMAXVAL) is not an error: reference step() is infallible
+ *     (src/physics.rs:44); the env is auto-reset like mj_step does and a per-env flag is raised
+ *     (home of Error::PhysicsDiverged, src/error.rs:7).
+ *   - nothing throws or aborts across this boundary; no torch/STL types in any signature.
+ *   - there is NO CPU fallback: without a CUDA device ox_batch_create fails with OX_ERR_CUDA.
+ */
+#ifndef OX_B200_H
+#define OX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define OX_API
+#else
+#define OX_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t ox_status;
+enum {
+  OX_OK = 0,
+  OX_ERR_PARSE = 1,     /* malformed XML / unknown element or attribute  -> Error::Mujoco */
+  OX_ERR_COMPILE = 2,   /* well-formed but un-compilable model           -> Error::Mjs    */
+  OX_ERR_CUDA = 3,      /* no device / allocation / launch failure                         */
+  OX_ERR_INVALID = 4,   /* bad argument (null handle, index out of range, wrong field)     */
+  OX_ABSENT = 5,        /* optional feature absent                       -> Option::None   */
+  OX_ERR_IO = 6         /* file could not be read                        -> Error::Mujoco */
+};
+
+/* mjtJoint / mjtGeom / mjtObj numeric values of MuJoCo 3.3.2 (rusty_mujoco::bindgen). */
+enum { OX_JNT_FREE = 0, OX_JNT_BALL = 1, OX_JNT_SLIDE = 2, OX_JNT_HINGE = 3 };
+enum { OX_GEOM_PLANE = 0, OX_GEOM_HFIELD = 1, OX_GEOM_SPHERE = 2, OX_GEOM_CAPSULE = 3,
+       OX_GEOM_ELLIPSOID = 4, OX_GEOM_CYLINDER = 5, OX_GEOM_BOX = 6, OX_GEOM_MESH = 7 };
+enum { OX_OBJ_UNKNOWN = 0, OX_OBJ_BODY = 1, OX_OBJ_XBODY = 2, OX_OBJ_JOINT = 3, OX_OBJ_DOF = 4,
+       OX_OBJ_GEOM = 5, OX_OBJ_SITE = 6, OX_OBJ_EQUALITY = 17, OX_OBJ_ACTUATOR = 19,
+       OX_OBJ_SENSOR = 20, OX_OBJ_PLUGIN = 25 };
+enum { OX_INT_EULER = 0, OX_INT_RK4 = 1 };
+enum { OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
+enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
+enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
+/* mjtDisableBit subset */
+enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 << 4,
+       OX_DSBL_PASSIVE = 1 << 5, OX_DSBL_GRAVITY = 1 << 6, OX_DSBL_CLAMPCTRL = 1 << 7,
+       OX_DSBL_WARMSTART = 1 << 8, OX_DSBL_FILTERPARENT = 1 << 9, OX_DSBL_ACTUATION = 1 << 10,
+       OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13 };
+/* mjtSensor subset */
+enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3,
+       OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
+       OX_SENS_ACTUATORFRC = 15, OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26,
+       OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_SUBTREECOM = 34,
+       OX_SENS_SUBTREELINVEL = 35, OX_SENS_CLOCK = 45 };
+
+#define OX_MAXVAL 1e10  /* mjMAXVAL re-exported at src/physics.rs:2 */
+#define OX_MINVAL 1e-15 /* mjMINVAL re-exported at src/physics.rs:2 */
+#define OX_MINIMP 0.0001
+#define OX_MAXIMP 0.9999
+
+/* ---- compiled-model constant tables (host, fp64; mirror of the mjModel fields the path reads) ----
+ * X(name, count_field, width): array of count_field*width entries.                                  */
+#define OX_MODEL_INT_TABLES(X)                                                                      \
+  X(body_parentid, nbody, 1) X(body_rootid, nbody, 1) X(body_weldid, nbody, 1)                     \
+  X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
+  X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
+  X(jnt_limited, njnt, 1)                                                                           \
+  X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1)               \
+  X(geom_type, ngeom, 1) X(geom_bodyid, ngeom, 1) X(geom_contype, ngeom, 1)                        \
+  X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
+  X(site_bodyid, nsite, 1)                                                                          \
+  X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1)   \
+  X(actuator_trnid, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
+  X(actuator_ctrllimited, nu, 1) X(actuator_forcelimited, nu, 1)                                    \
+  X(sensor_type, nsensor, 1) X(sensor_objtype, nsensor, 1) X(sensor_objid, nsensor, 1)             \
+  X(sensor_adr, nsensor, 1) X(sensor_dim, nsensor, 1)
+
+#define OX_MODEL_REAL_TABLES(X)                                                                     \
+  X(qpos0, nq, 1) X(qpos_spring, nq, 1)                                                             \
+  X(body_pos, nbody, 3) X(body_quat, nbody, 4) X(body_ipos, nbody, 3) X(body_iquat, nbody, 4)      \
+  X(body_mass, nbody, 1) X(body_inertia, nbody, 3) X(body_subtreemass, nbody, 1)                   \
+  X(body_invweight0, nbody, 2)                                                                      \
+  X(jnt_pos, njnt, 3) X(jnt_axis, njnt, 3) X(jnt_stiffness, njnt, 1) X(jnt_range, njnt, 2)         \
+  X(jnt_margin, njnt, 1) X(jnt_solref, njnt, 2) X(jnt_solimp, njnt, 5)                             \
+  X(dof_armature, nv, 1) X(dof_damping, nv, 1) X(dof_invweight0, nv, 1)                            \
+  X(geom_size, ngeom, 3) X(geom_pos, ngeom, 3) X(geom_quat, ngeom, 4) X(geom_friction, ngeom, 3)   \
+  X(geom_solmix, ngeom, 1) X(geom_solref, ngeom, 2) X(geom_solimp, ngeom, 5)                       \
+  X(geom_margin, ngeom, 1) X(geom_gap, ngeom, 1)                                                    \
+  X(site_pos, nsite, 3) X(site_quat, nsite, 4)                                                      \
+  X(pair_friction, npair, 5) X(pair_solref, npair, 2) X(pair_solimp, npair, 5)                     \
+  X(pair_margin, npair, 1) X(pair_gap, npair, 1)                                                    \
+  X(actuator_gear, nu, 1) X(actuator_gainprm, nu, 3) X(actuator_biasprm, nu, 3)                    \
+  X(actuator_ctrlrange, nu, 2) X(actuator_forcerange, nu, 2)
+
+typedef struct ox_model_tables {
+  /* sizes */
+  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata;
+  int32_t nconmax;  /* sum of pair_maxcon: capacity of the per-env contact list         */
+  int32_t nefcmax;  /* 2*nlimited + sum of contact rows: capacity of the per-env efc list */
+  /* mjOption subset */
+  int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
+  double timestep, gravity[3], tolerance, ls_tolerance, impratio;
+  /* mjStatistic subset */
+  double meaninertia;
+#define OX_X(name, n, w) const int32_t* name;
+  OX_MODEL_INT_TABLES(OX_X)
+#undef OX_X
+#define OX_X(name, n, w) const double* name;
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+} ox_model_tables;
+
+typedef struct ox_model ox_model; /* immutable after construction; thread-safe to share */
+typedef struct ox_batch ox_batch; /* nenv copies of mjData, SoA on one device, one stream */
+
+/* ---- errors ---- */
+OX_API const char* ox_last_error_message(void);
+OX_API const char* ox_version(void);
+
+/* ---- model (setup side of the boundary) ---- */
+OX_API ox_status ox_model_from_xml_string(const char* xml, ox_model** out);
+OX_API ox_status ox_model_from_xml_path(const char* path, ox_model** out);
+OX_API void ox_model_free(ox_model* m);
+OX_API const ox_model_tables* ox_model_get_tables(const ox_model* m);
+/* name-addressed table access for bindings that cannot see the struct (ctypes, Rust sys crate) */
+OX_API ox_status ox_model_int_table(const ox_model* m, const char* name, const int32_t** ptr, int32_t* count);
+OX_API ox_status ox_model_real_table(const ox_model* m, const char* name, const double** ptr, int32_t* count);
+OX_API int32_t ox_model_size(const ox_model* m, const char* name); /* "nq","nv",...; -1 if unknown */
+OX_API int32_t ox_model_name2id(const ox_model* m, int32_t objtype, const char* name); /* -1 = None */
+OX_API const char* ox_model_id2name(const ox_model* m, int32_t objtype, int32_t id);   /* "" if unnamed, NULL if bad id */
+
+/* ---- batch ---- */
+enum { OX_F32 = 0, OX_F64 = 1 };
+enum { OX_MEM_HOST = 0, OX_MEM_DEVICE = 1 };
+enum { OX_LAYOUT_ENV_MAJOR = 0 /* [env][elem] (AoS, what a Vec<mjData> would give) */,
+       OX_LAYOUT_ELEM_MAJOR = 1 /* [elem][env] (native SoA) */ };
+enum { OX_MODE_FUSED = 0 /* one launch per step */, OX_MODE_STAGED = 1 /* one launch per mj_step stage */ };
+
+typedef struct ox_batch_config {
+  int32_t nenv;
+  int32_t device;        /* CUDA ordinal */
+  int32_t precision;     /* OX_F32 throughput mode | OX_F64 validation mode */
+  int32_t mode;          /* OX_MODE_FUSED | OX_MODE_STAGED */
+  int32_t iterations;    /* solver iteration cap; 0 = model's <option iterations> */
+  int32_t ls_iterations; /* line-search iteration cap; 0 = model's */
+  int32_t use_graph;     /* capture the per-step launch sequence in a CUDA graph */
+  int32_t block_threads; /* 0 = default */
+  int64_t env_id_offset; /* global env id of env 0 (multi-GPU sharding; keys the Philox control stream) */
+  double tolerance;      /* <0 = model's */
+} ox_batch_config;
+
+OX_API void ox_batch_config_default(ox_batch_config* cfg);
+OX_API ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batch** out);
+OX_API void ox_batch_free(ox_batch* b);
+OX_API int32_t ox_batch_nenv(const ox_batch* b);
+OX_API void* ox_batch_stream(const ox_batch* b); /* cudaStream_t */
+
+/* step family: asynchronous on the batch's stream */
+OX_API ox_status ox_batch_step(ox_batch* b, int32_t nsteps);
+OX_API ox_status ox_batch_forward(ox_batch* b);
+OX_API ox_status ox_batch_reset(ox_batch* b, const uint8_t* host_mask_or_null);
+OX_API ox_status ox_batch_sync(ox_batch* b);
+
+/* benchmark control source: fresh ctrl ~ U(-1,1) every step from Philox4x32-10 keyed on
+ * (seed, global env id, step, actuator) generated on device. enable=0 returns to user ctrl. */
+OX_API ox_status ox_batch_ctrl_philox(ox_batch* b, int32_t enable, uint64_t seed);
+OX_API ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step);
+
+/* field ids for bulk / per-env access */
+enum {
+  OX_F_QPOS = 0, OX_F_QVEL, OX_F_CTRL, OX_F_QFRC_APPLIED, OX_F_XFRC_APPLIED, OX_F_QACC_WARMSTART,
+  OX_F_TIME, OX_F_ACT,
+  OX_F_QACC, OX_F_SENSORDATA, OX_F_XPOS, OX_F_XQUAT, OX_F_XMAT, OX_F_XIPOS, OX_F_XIMAT,
+  OX_F_XANCHOR, OX_F_XAXIS, OX_F_GEOM_XPOS, OX_F_GEOM_XMAT, OX_F_SITE_XPOS, OX_F_SITE_XMAT,
+  OX_F_SUBTREE_COM, OX_F_CINERT, OX_F_CDOF, OX_F_QM, OX_F_QLD, OX_F_QLDIAGINV, OX_F_CVEL,
+  OX_F_CDOF_DOT, OX_F_QFRC_BIAS, OX_F_QFRC_PASSIVE, OX_F_ACTUATOR_FORCE, OX_F_QFRC_ACTUATOR,
+  OX_F_QFRC_SMOOTH, OX_F_QACC_SMOOTH, OX_F_QFRC_CONSTRAINT,
+  OX_F_CON_DIST, OX_F_CON_POS, OX_F_CON_FRAME,
+  OX_F_EFC_J, OX_F_EFC_POS, OX_F_EFC_MARGIN, OX_F_EFC_D, OX_F_EFC_AREF, OX_F_EFC_FORCE,
+  OX_F_COUNT_REAL,
+  /* int32 fields */
+  OX_F_NCON = 100, OX_F_NEFC, OX_F_SOLVER_NITER, OX_F_DIVERGED, OX_F_CON_PAIR
+};
+OX_API int32_t ox_batch_field_size(const ox_batch* b, int32_t field); /* elements per env; -1 bad field */
+
+/* bulk I/O: `buf` holds nenv*field_size elements of `dtype` (OX_F32/OX_F64; int fields are int32)
+ * in `layout`, living in `mem`. Stream-ordered; host copies complete before return. */
+OX_API ox_status ox_batch_get(ox_batch* b, int32_t field, void* buf, int32_t dtype, int32_t mem, int32_t layout);
+OX_API ox_status ox_batch_set(ox_batch* b, int32_t field, const void* buf, int32_t dtype, int32_t mem, int32_t layout);
+/* per-env slices, always fp64 at this boundary (reference types are f64 / [f64;N]) */
+OX_API ox_status ox_batch_get1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, double* out);
+OX_API ox_status ox_batch_set1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, const double* in);
+OX_API ox_status ox_batch_get1_int(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, int32_t* out);
+
+/* run statistics accumulated on device since the last call (mean ncon, nefc, solver iterations,
+ * number of divergence auto-resets); out[4]. */
+OX_API ox_status ox_batch_stats(ox_batch* b, double* out4);
+/* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
+OX_API int64_t ox_batch_launch_count(const ox_batch* b);
+/* per-stage device time of one staged forward+integrate (ms), for profiles/: names via ox_stage_name */
+OX_API ox_status ox_batch_stage_times(ox_batch* b, int32_t reps, double* out_ms, int32_t* nstage);
+OX_API const char* ox_stage_name(int32_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OX_B200_H */

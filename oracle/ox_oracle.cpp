@@ -1,0 +1,1314 @@
+/*
+ * ox_oracle.cpp — CPU restatement (fp64, scalar, array-of-structs, one env at a time) of the
+ * arithmetic behind oxide_control's hot path  Physics::step -> rusty_mujoco::mj_step
+ * (reference src/physics.rs:44-46), plus Physics::forward (src/physics.rs:48-50) and
+ * Physics::reset (src/physics.rs:52-54).
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT. Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it. The product path
+ * (oxide_control_b200/csrc) never links, includes or calls anything in this directory.
+ *
+ * PARITY UNPINNED. The arithmetic of the reference path lives in third-party code that is absent
+ * from /root/reference: crate rusty_mujoco "0.1.0" (Cargo.toml:16) -> MuJoCo 3.3.2
+ * (.github/workflows/CI.yml:28). The reference holds no tests, fixtures or golden vectors
+ *  and MuJoCo cannot be built or imported here. This file restates
+ * MuJoCo's published algorithm (stage list and formulas: SURVEY.md Appendix A; decisions where the
+ * documentation leaves room: ORACLE_DECISIONS.md). It is pinned instead by closed-form and
+ * algorithm-independent checks in tests/  and by the golden hook
+ * tools/dump_mujoco_golden.py (output goes to tests/golden/).
+ *
+ * Input model = the ox_model_tables struct of include/ox_b200.h (mirror of the mjModel fields the
+ * path reads). Stage functions are exported individually so the GPU path can be compared stage by stage.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../include/ox_b200.h"
+
+typedef ox_model_tables Model;
+
+struct oxo_data {
+  // state (mjData fields of the same names)
+  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart;
+  double time = 0;
+  // position stage
+  std::vector<double> xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, geom_xpos, geom_xmat, site_xpos, site_xmat;
+  std::vector<double> subtree_com, cinert, cdof, crb, qM, qLD, qLDiagInv;
+  // velocity / actuation / acceleration
+  std::vector<double> cvel, cdof_dot, qfrc_bias, qfrc_passive, actuator_force, qfrc_actuator, qfrc_smooth, qacc_smooth;
+  // contacts
+  int ncon = 0;
+  std::vector<double> con_dist, con_pos, con_frame;
+  std::vector<int> con_pair;
+  // constraints
+  int nefc = 0;
+  std::vector<double> efc_J, efc_pos, efc_margin, efc_D, efc_R, efc_aref, efc_vel, efc_force, efc_diagApprox;
+  std::vector<int> efc_type, efc_id;
+  // solution
+  std::vector<double> qacc, qfrc_constraint;
+  int solver_niter = 0;
+  std::vector<double> sensordata;
+  int diverged = 0;  // number of auto-resets (mj_checkPos/Vel/Acc warnings)
+};
+typedef oxo_data Data;
+
+namespace {
+
+// ---------------------------------------------------------------- small math (mju_* equivalents)
+inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline void cross3(double* r, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+inline double normalize3(double* v) {
+  double n = std::sqrt(dot3(v, v));
+  if (n < OX_MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; } else { double s = 1 / n; v[0] *= s; v[1] *= s; v[2] *= s; }
+  return n;
+}
+inline void normalize4(double* q) {
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < OX_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { double s = 1 / n; for (int i = 0; i < 4; i++) q[i] *= s; }
+}
+inline void mulQuat(double* r, const double* a, const double* b) {
+  double t[4] = {a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                 a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]};
+  std::memcpy(r, t, sizeof t);
+}
+inline void quat2Mat(double* m, const double* q) {
+  double q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  double q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
+  m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+inline void mulMatVec3(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+         z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+inline void rotVecQuat(double* r, const double* v, const double* q) {
+  double m[9];
+  quat2Mat(m, q);
+  mulMatVec3(r, m, v);
+}
+inline void axisAngle2Quat(double* q, const double* axis, double angle) {
+  if (angle == 0) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double s = std::sin(angle * 0.5);
+  q[0] = std::cos(angle * 0.5); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+// quaternion difference as a 3D velocity: qb * quat(res) = qa  (mju_subQuat)
+inline void subQuat(double* res, const double* qa, const double* qb) {
+  double qneg[4] = {qb[0], -qb[1], -qb[2], -qb[3]}, qdif[4];
+  mulQuat(qdif, qneg, qa);
+  double axis[3] = {qdif[1], qdif[2], qdif[3]};
+  double sin_a_2 = normalize3(axis);
+  double speed = 2 * std::atan2(sin_a_2, qdif[0]);
+  if (speed > M_PI) speed -= 2 * M_PI;
+  res[0] = axis[0] * speed; res[1] = axis[1] * speed; res[2] = axis[2] * speed;
+}
+inline void quatIntegrate(double* quat, const double* vel, double scale) {
+  double tmp[3] = {vel[0], vel[1], vel[2]}, qrot[4];
+  double angle = scale * normalize3(tmp);
+  axisAngle2Quat(qrot, tmp, angle);
+  normalize4(quat);
+  mulQuat(quat, quat, qrot);
+}
+// spatial algebra, 6-vectors are [angular; linear]
+inline void crossMotion(double* r, const double* vel, const double* v) {
+  r[0] = -vel[2] * v[1] + vel[1] * v[2];
+  r[1] = vel[2] * v[0] - vel[0] * v[2];
+  r[2] = -vel[1] * v[0] + vel[0] * v[1];
+  r[3] = -vel[2] * v[4] + vel[1] * v[5] - vel[5] * v[1] + vel[4] * v[2];
+  r[4] = vel[2] * v[3] - vel[0] * v[5] + vel[5] * v[0] - vel[3] * v[2];
+  r[5] = -vel[1] * v[3] + vel[0] * v[4] - vel[4] * v[0] + vel[3] * v[1];
+}
+inline void crossForce(double* r, const double* vel, const double* f) {
+  r[0] = -vel[2] * f[1] + vel[1] * f[2] - vel[5] * f[4] + vel[4] * f[5];
+  r[1] = vel[2] * f[0] - vel[0] * f[2] + vel[5] * f[3] - vel[3] * f[5];
+  r[2] = -vel[1] * f[0] + vel[0] * f[1] - vel[4] * f[3] + vel[3] * f[4];
+  r[3] = -vel[2] * f[4] + vel[1] * f[5];
+  r[4] = vel[2] * f[3] - vel[0] * f[5];
+  r[5] = -vel[1] * f[3] + vel[0] * f[4];
+}
+// 10-number com-frame inertia times motion vector
+inline void mulInertVec(double* r, const double* i, const double* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+inline double dot6(const double* a, const double* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+inline bool disabled(const Model* m, int bit) { return (m->disableflags & bit) != 0; }
+
+// ---------------------------------------------------------------- A.1 kinematics
+void kinematics(const Model* m, Data* d) {
+  double* xpos = d->xpos.data();
+  double* xquat = d->xquat.data();
+  double* xmat = d->xmat.data();
+  xpos[0] = xpos[1] = xpos[2] = 0;
+  xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+  for (int k = 0; k < 9; k++) { xmat[k] = (k % 4 == 0); d->ximat[k] = (k % 4 == 0); }
+  d->xipos[0] = d->xipos[1] = d->xipos[2] = 0;
+  for (int i = 1; i < m->nbody; i++) {
+    double pos[3], quat[4];
+    int jntadr = m->body_jntadr[i], jntnum = m->body_jntnum[i];
+    if (jntnum == 1 && m->jnt_type[jntadr] == OX_JNT_FREE) {
+      int qadr = m->jnt_qposadr[jntadr];
+      std::memcpy(pos, &d->qpos[qadr], 3 * sizeof(double));
+      std::memcpy(quat, &d->qpos[qadr + 3], 4 * sizeof(double));
+      normalize4(quat);
+      std::memcpy(&d->xanchor[3 * jntadr], pos, 3 * sizeof(double));
+      std::memcpy(&d->xaxis[3 * jntadr], &m->jnt_axis[3 * jntadr], 3 * sizeof(double));
+    } else {
+      int pid = m->body_parentid[i];
+      mulMatVec3(pos, xmat + 9 * pid, m->body_pos + 3 * i);
+      for (int k = 0; k < 3; k++) pos[k] += xpos[3 * pid + k];
+      mulQuat(quat, xquat + 4 * pid, m->body_quat + 4 * i);
+      for (int j = 0; j < jntnum; j++) {
+        int jid = jntadr + j, qadr = m->jnt_qposadr[jid], jt = m->jnt_type[jid];
+        double anchor[3], axis[3];
+        rotVecQuat(axis, m->jnt_axis + 3 * jid, quat);
+        rotVecQuat(anchor, m->jnt_pos + 3 * jid, quat);
+        for (int k = 0; k < 3; k++) anchor[k] += pos[k];
+        if (jt == OX_JNT_SLIDE) {
+          double dq = d->qpos[qadr] - m->qpos0[qadr];
+          for (int k = 0; k < 3; k++) pos[k] += axis[k] * dq;
+        } else if (jt == OX_JNT_BALL || jt == OX_JNT_HINGE) {
+          double qloc[4];
+          if (jt == OX_JNT_BALL) {
+            std::memcpy(qloc, &d->qpos[qadr], 4 * sizeof(double));
+            normalize4(qloc);
+          } else {
+            axisAngle2Quat(qloc, m->jnt_axis + 3 * jid, d->qpos[qadr] - m->qpos0[qadr]);
+          }
+          mulQuat(quat, quat, qloc);
+          double vec[3];
+          rotVecQuat(vec, m->jnt_pos + 3 * jid, quat);
+          for (int k = 0; k < 3; k++) pos[k] = anchor[k] - vec[k];
+        }
+        std::memcpy(&d->xanchor[3 * jid], anchor, sizeof anchor);
+        std::memcpy(&d->xaxis[3 * jid], axis, sizeof axis);
+      }
+    }
+    normalize4(quat);
+    std::memcpy(xquat + 4 * i, quat, sizeof quat);
+    std::memcpy(xpos + 3 * i, pos, sizeof pos);
+    quat2Mat(xmat + 9 * i, quat);
+  }
+  for (int i = 1; i < m->nbody; i++) {
+    double v[3], q[4];
+    mulMatVec3(v, xmat + 9 * i, m->body_ipos + 3 * i);
+    for (int k = 0; k < 3; k++) d->xipos[3 * i + k] = xpos[3 * i + k] + v[k];
+    mulQuat(q, xquat + 4 * i, m->body_iquat + 4 * i);
+    quat2Mat(&d->ximat[9 * i], q);
+  }
+  for (int g = 0; g < m->ngeom; g++) {
+    int b = m->geom_bodyid[g];
+    double v[3], q[4];
+    mulMatVec3(v, xmat + 9 * b, m->geom_pos + 3 * g);
+    for (int k = 0; k < 3; k++) d->geom_xpos[3 * g + k] = xpos[3 * b + k] + v[k];
+    mulQuat(q, xquat + 4 * b, m->geom_quat + 4 * g);
+    quat2Mat(&d->geom_xmat[9 * g], q);
+  }
+  for (int s = 0; s < m->nsite; s++) {
+    int b = m->site_bodyid[s];
+    double v[3], q[4];
+    mulMatVec3(v, xmat + 9 * b, m->site_pos + 3 * s);
+    for (int k = 0; k < 3; k++) d->site_xpos[3 * s + k] = xpos[3 * b + k] + v[k];
+    mulQuat(q, xquat + 4 * b, m->site_quat + 4 * s);
+    quat2Mat(&d->site_xmat[9 * s], q);
+  }
+}
+
+// ---------------------------------------------------------------- A.2 com-frame quantities
+void comPos(const Model* m, Data* d) {
+  double* sc = d->subtree_com.data();
+  std::fill(d->subtree_com.begin(), d->subtree_com.end(), 0.0);
+  for (int i = m->nbody - 1; i >= 0; i--) {
+    for (int k = 0; k < 3; k++) sc[3 * i + k] += d->xipos[3 * i + k] * m->body_mass[i];
+    if (i) {
+      int j = m->body_parentid[i];
+      for (int k = 0; k < 3; k++) sc[3 * j + k] += sc[3 * i + k];
+    }
+    if (m->body_subtreemass[i] < OX_MINVAL) std::memcpy(sc + 3 * i, &d->xipos[3 * i], 3 * sizeof(double));
+    else for (int k = 0; k < 3; k++) sc[3 * i + k] /= m->body_subtreemass[i];
+  }
+  std::fill(d->cinert.begin(), d->cinert.begin() + 10, 0.0);
+  for (int i = 1; i < m->nbody; i++) {
+    const double* mat = &d->ximat[9 * i];
+    const double* inert = m->body_inertia + 3 * i;
+    double mass = m->body_mass[i], dif[3];
+    for (int k = 0; k < 3; k++) dif[k] = d->xipos[3 * i + k] - sc[3 * m->body_rootid[i] + k];
+    double* res = &d->cinert[10 * i];
+    double tmp[9];  // diag(inert) * mat'
+    tmp[0] = mat[0] * inert[0]; tmp[3] = mat[1] * inert[1]; tmp[6] = mat[2] * inert[2];
+    tmp[1] = mat[3] * inert[0]; tmp[4] = mat[4] * inert[1]; tmp[7] = mat[5] * inert[2];
+    tmp[2] = mat[6] * inert[0]; tmp[5] = mat[7] * inert[1]; tmp[8] = mat[8] * inert[2];
+    res[0] = mat[0] * tmp[0] + mat[1] * tmp[3] + mat[2] * tmp[6];
+    res[1] = mat[3] * tmp[1] + mat[4] * tmp[4] + mat[5] * tmp[7];
+    res[2] = mat[6] * tmp[2] + mat[7] * tmp[5] + mat[8] * tmp[8];
+    res[3] = mat[0] * tmp[1] + mat[1] * tmp[4] + mat[2] * tmp[7];
+    res[4] = mat[0] * tmp[2] + mat[1] * tmp[5] + mat[2] * tmp[8];
+    res[5] = mat[3] * tmp[2] + mat[4] * tmp[5] + mat[5] * tmp[8];
+    res[0] += mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+    res[1] += mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+    res[2] += mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+    res[3] -= mass * dif[0] * dif[1];
+    res[4] -= mass * dif[0] * dif[2];
+    res[5] -= mass * dif[1] * dif[2];
+    res[6] = mass * dif[0]; res[7] = mass * dif[1]; res[8] = mass * dif[2];
+    res[9] = mass;
+  }
+  for (int j = 0; j < m->njnt; j++) {
+    int bi = m->jnt_bodyid[j], da = m->jnt_dofadr[j];
+    double offset[3];
+    for (int k = 0; k < 3; k++) offset[k] = sc[3 * m->body_rootid[bi] + k] - d->xanchor[3 * j + k];
+    double* cdof = d->cdof.data();
+    int skip = 0;
+    switch (m->jnt_type[j]) {
+      case OX_JNT_FREE:
+        std::fill(cdof + 6 * da, cdof + 6 * da + 18, 0.0);
+        for (int i = 0; i < 3; i++) cdof[6 * (da + i) + 3 + i] = 1;
+        skip = 3;
+        // fallthrough
+      case OX_JNT_BALL:
+        for (int i = 0; i < 3; i++) {
+          double axis[3] = {d->xmat[9 * bi + i], d->xmat[9 * bi + i + 3], d->xmat[9 * bi + i + 6]};
+          double* r = cdof + 6 * (da + i + skip);
+          r[0] = axis[0]; r[1] = axis[1]; r[2] = axis[2];
+          cross3(r + 3, axis, offset);
+        }
+        break;
+      case OX_JNT_SLIDE: {
+        double* r = cdof + 6 * da;
+        r[0] = r[1] = r[2] = 0;
+        std::memcpy(r + 3, &d->xaxis[3 * j], 3 * sizeof(double));
+        break;
+      }
+      case OX_JNT_HINGE: {
+        double* r = cdof + 6 * da;
+        std::memcpy(r, &d->xaxis[3 * j], 3 * sizeof(double));
+        cross3(r + 3, &d->xaxis[3 * j], offset);
+        break;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- A.3 composite rigid body
+void crb(const Model* m, Data* d) {
+  d->crb = d->cinert;
+  for (int i = m->nbody - 1; i > 0; i--) {
+    int p = m->body_parentid[i];
+    if (p > 0) for (int k = 0; k < 10; k++) d->crb[10 * p + k] += d->crb[10 * i + k];
+  }
+  std::fill(d->qM.begin(), d->qM.end(), 0.0);
+  for (int i = 0; i < m->nv; i++) {
+    int adr = m->dof_Madr[i];
+    d->qM[adr] = m->dof_armature[i];
+    double buf[6];
+    mulInertVec(buf, &d->crb[10 * m->dof_bodyid[i]], &d->cdof[6 * i]);
+    for (int j = i; j >= 0; j = m->dof_parentid[j]) d->qM[adr++] += dot6(&d->cdof[6 * j], buf);
+  }
+}
+
+// ---------------------------------------------------------------- A.4 sparse L'DL
+void factorLD(const Model* m, double* qLD, double* qLDiagInv) {
+  for (int k = m->nv - 1; k >= 0; k--) {
+    int Madr_kk = m->dof_Madr[k], Madr_ki = Madr_kk + 1, i = m->dof_parentid[k];
+    while (i >= 0) {
+      double tmp = qLD[Madr_ki] / qLD[Madr_kk];
+      // row i holds M(i,i), M(i,parent(i)), ...; row k from Madr_ki holds M(k,i), M(k,parent(i)), ...
+      int n = 1;
+      for (int a = m->dof_parentid[i]; a >= 0; a = m->dof_parentid[a]) n++;
+      for (int c = 0; c < n; c++) qLD[m->dof_Madr[i] + c] -= tmp * qLD[Madr_ki + c];
+      qLD[Madr_ki] = tmp;
+      i = m->dof_parentid[i];
+      Madr_ki++;
+    }
+    qLDiagInv[k] = 1.0 / qLD[Madr_kk];
+  }
+}
+void factorM(const Model* m, Data* d) {
+  d->qLD = d->qM;
+  factorLD(m, d->qLD.data(), d->qLDiagInv.data());
+}
+void solveLD(const Model* m, const double* qLD, const double* qLDiagInv, double* x) {
+  for (int i = m->nv - 1; i >= 0; i--) {
+    int adr = m->dof_Madr[i] + 1;
+    for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j]) x[j] -= qLD[adr++] * x[i];
+  }
+  for (int i = 0; i < m->nv; i++) x[i] *= qLDiagInv[i];
+  for (int i = 0; i < m->nv; i++) {
+    int adr = m->dof_Madr[i] + 1;
+    for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j]) x[i] -= qLD[adr++] * x[j];
+  }
+}
+void mulM(const Model* m, const double* qM, double* res, const double* v) {
+  for (int i = 0; i < m->nv; i++) res[i] = 0;
+  for (int i = 0; i < m->nv; i++) {
+    int adr = m->dof_Madr[i];
+    res[i] += qM[adr] * v[i];
+    int k = 1;
+    for (int j = m->dof_parentid[i]; j >= 0; j = m->dof_parentid[j], k++) {
+      res[i] += qM[adr + k] * v[j];
+      res[j] += qM[adr + k] * v[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- A.5 collision
+struct RawContact { double dist, pos[3], frame[9]; };
+
+int planeSphere(RawContact* con, double margin, const double* pos1, const double* mat1, const double* pos2, double radius) {
+  double normal[3] = {mat1[2], mat1[5], mat1[8]};
+  double tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  double cdist = dot3(tmp, normal);
+  if (cdist > margin + radius) return 0;
+  con->dist = cdist - radius;
+  std::memcpy(con->frame, normal, sizeof normal);
+  con->frame[3] = con->frame[4] = con->frame[5] = 0;
+  for (int k = 0; k < 3; k++) con->pos[k] = pos2[k] + normal[k] * (-con->dist / 2 - radius);
+  return 1;
+}
+int sphereSphere(RawContact* con, double margin, const double* pos1, double r1, const double* pos2, double r2) {
+  double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  double cdist2 = dot3(dif, dif), mind = margin + r1 + r2;
+  if (cdist2 > mind * mind) return 0;
+  con->dist = std::sqrt(cdist2) - r1 - r2;
+  std::memcpy(con->frame, dif, sizeof dif);
+  normalize3(con->frame);
+  con->frame[3] = con->frame[4] = con->frame[5] = 0;
+  for (int k = 0; k < 3; k++) con->pos[k] = pos1[k] + con->frame[k] * (r1 + con->dist / 2);
+  return 1;
+}
+inline double clip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+int collidePair(const Model* m, const Data* d, int p, RawContact* con) {
+  int g1 = m->pair_geom1[p], g2 = m->pair_geom2[p];
+  int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+  const double *pos1 = &d->geom_xpos[3 * g1], *mat1 = &d->geom_xmat[9 * g1], *size1 = m->geom_size + 3 * g1;
+  const double *pos2 = &d->geom_xpos[3 * g2], *mat2 = &d->geom_xmat[9 * g2], *size2 = m->geom_size + 3 * g2;
+  double margin = m->pair_margin[p];
+  if (t1 == OX_GEOM_PLANE && t2 == OX_GEOM_SPHERE) return planeSphere(con, margin, pos1, mat1, pos2, size2[0]);
+  if (t1 == OX_GEOM_PLANE && t2 == OX_GEOM_CAPSULE) {
+    double axis[3] = {mat2[2], mat2[5], mat2[8]}, seg[3], pt[3];
+    for (int k = 0; k < 3; k++) seg[k] = axis[k] * size2[1];
+    for (int k = 0; k < 3; k++) pt[k] = pos2[k] + seg[k];
+    int n1 = planeSphere(con, margin, pos1, mat1, pt, size2[0]);
+    for (int k = 0; k < 3; k++) pt[k] = pos2[k] - seg[k];
+    int n2 = planeSphere(con + n1, margin, pos1, mat1, pt, size2[0]);
+    for (int c = 0; c < n1 + n2; c++) std::memcpy(con[c].frame + 3, axis, sizeof axis);
+    return n1 + n2;
+  }
+  if (t1 == OX_GEOM_PLANE && t2 == OX_GEOM_BOX) {
+    double norm[3] = {mat1[2], mat1[5], mat1[8]};
+    double dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+    double dist = dot3(dif, norm);
+    int cnt = 0;
+    for (int i = 0; i < 8; i++) {
+      double vec[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])};
+      double corner[3];
+      mulMatVec3(corner, mat2, vec);
+      double ldist = dot3(norm, corner);
+      if (dist + ldist > margin || ldist > 0) continue;
+      con[cnt].dist = dist + ldist;
+      std::memcpy(con[cnt].frame, norm, sizeof norm);
+      con[cnt].frame[3] = con[cnt].frame[4] = con[cnt].frame[5] = 0;
+      for (int k = 0; k < 3; k++) con[cnt].pos[k] = corner[k] + pos2[k] + norm[k] * (-con[cnt].dist / 2);
+      if (++cnt >= 4) return 4;
+    }
+    return cnt;
+  }
+  if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_SPHERE) return sphereSphere(con, margin, pos1, size1[0], pos2, size2[0]);
+  if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_CAPSULE) {
+    double axis[3] = {mat2[2], mat2[5], mat2[8]};
+    double vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    double x = clip(dot3(axis, vec), -size2[1], size2[1]);
+    for (int k = 0; k < 3; k++) vec[k] = pos2[k] + axis[k] * x;
+    return sphereSphere(con, margin, pos1, size1[0], vec, size2[0]);
+  }
+  if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {
+    double axis1[3] = {mat1[2] * size1[1], mat1[5] * size1[1], mat1[8] * size1[1]};
+    double axis2[3] = {mat2[2] * size2[1], mat2[5] * size2[1], mat2[8] * size2[1]};
+    double dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+    double ma = dot3(axis1, axis1), mb = -dot3(axis1, axis2), mc = dot3(axis2, axis2);
+    double u = -dot3(axis1, dif), v = dot3(axis2, dif), det = ma * mc - mb * mb;
+    double vec1[3], vec2[3];
+    if (std::fabs(det) >= OX_MINVAL) {
+      double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+      if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+      if (x2 > 1) { x2 = 1; x1 = (u - mb) / ma; } else if (x2 < -1) { x2 = -1; x1 = (u + mb) / ma; }
+      x1 = clip(x1, -1, 1);
+      for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k] * x2; }
+      return sphereSphere(con, margin, vec1, size1[0], vec2, size2[0]);
+    }
+    // parallel axes: up to two contacts
+    int n = 0;
+    double x2 = clip((v - mb) / mc, -1, 1);
+    for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
+    n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+    x2 = clip((v + mb) / mc, -1, 1);
+    for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] - axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
+    n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+    if (n >= 2) return n;
+    double x1 = clip((u - mb) / ma, -1, 1);
+    for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k]; }
+    n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+    if (n >= 2) return n;
+    x1 = clip((u + mb) / ma, -1, 1);
+    for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] - axis2[k]; }
+    n += sphereSphere(con + n, margin, vec1, size1[0], vec2, size2[0]);
+    return n;
+  }
+  return 0;
+}
+
+void makeFrame(double* frame) {
+  normalize3(frame);
+  if (std::sqrt(dot3(frame + 3, frame + 3)) < 0.5) {
+    frame[3] = frame[4] = frame[5] = 0;
+    if (frame[1] < 0.5 && frame[1] > -0.5) frame[4] = 1; else frame[5] = 1;
+  }
+  double t = dot3(frame, frame + 3);
+  for (int k = 0; k < 3; k++) frame[3 + k] -= t * frame[k];
+  normalize3(frame + 3);
+  cross3(frame + 6, frame, frame + 3);
+}
+
+void collision(const Model* m, Data* d) {
+  d->ncon = 0;
+  if (disabled(m, OX_DSBL_CONTACT) || disabled(m, OX_DSBL_CONSTRAINT)) return;
+  for (int p = 0; p < m->npair; p++) {
+    RawContact rc[8];
+    int n = collidePair(m, d, p, rc);
+    for (int c = 0; c < n; c++) {
+      makeFrame(rc[c].frame);
+      int k = d->ncon++;
+      d->con_dist[k] = rc[c].dist;
+      std::memcpy(&d->con_pos[3 * k], rc[c].pos, 3 * sizeof(double));
+      std::memcpy(&d->con_frame[9 * k], rc[c].frame, 9 * sizeof(double));
+      d->con_pair[k] = p;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- A.6 constraint assembly
+// translational Jacobian of a world point attached to `body` (mj_jac, jacp rows only), accumulated with sign
+void addJacP(const Model* m, const Data* d, int body, const double* point, double sign, double* jacp /*3 x nv*/) {
+  int nv = m->nv;
+  double offset[3];
+  for (int k = 0; k < 3; k++) offset[k] = point[k] - d->subtree_com[3 * m->body_rootid[body] + k];
+  while (body && m->body_dofnum[body] == 0) body = m->body_parentid[body];
+  if (!body) return;
+  for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i]) {
+    const double* cd = &d->cdof[6 * i];
+    double tmp[3];
+    cross3(tmp, cd, offset);
+    for (int k = 0; k < 3; k++) jacp[k * nv + i] += sign * (cd[3 + k] + tmp[k]);
+  }
+}
+
+void getImpedance(const double* solimp, double pos, double margin, double* imp) {
+  double dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (dmin == dmax || width <= OX_MINVAL) { *imp = 0.5 * (dmin + dmax); return; }
+  double x = std::fabs(pos - margin) / width;
+  if (x >= 1) { *imp = dmax; return; }
+  if (x <= 0) { *imp = dmin; return; }
+  double y;
+  if (power == 1) y = x;
+  else if (x <= mid) y = std::pow(x, power) / std::pow(mid, power - 1);
+  else y = 1 - std::pow(1 - x, power) / std::pow(1 - mid, power - 1);
+  *imp = dmin + y * (dmax - dmin);
+}
+
+void addRow(const Model* m, Data* d, const double* jrow, double pos, double margin, double diagApprox, const double* solref,
+            const double* solimp, int type, int id) {
+  int r = d->nefc++, nv = m->nv;
+  std::memcpy(&d->efc_J[(size_t)r * nv], jrow, nv * sizeof(double));
+  d->efc_pos[r] = pos;
+  d->efc_margin[r] = margin;
+  d->efc_type[r] = type;
+  d->efc_id[r] = id;
+  d->efc_diagApprox[r] = diagApprox;
+  double imp;
+  getImpedance(solimp, pos, margin, &imp);
+  imp = clip(imp, OX_MINIMP, OX_MAXIMP);
+  d->efc_R[r] = std::max(OX_MINVAL, (1 - imp) * diagApprox / imp);
+  // stiffness / damping of the reference acceleration
+  double dmax = solimp[1], K, Bd;
+  if (solref[0] > 0) {
+    double tc = solref[0], dr = solref[1];
+    if (!disabled(m, OX_DSBL_REFSAFE)) tc = std::max(tc, 2 * m->timestep);
+    K = 1 / std::max(OX_MINVAL, dmax * dmax * tc * tc * dr * dr);
+    Bd = 2 / std::max(OX_MINVAL, dmax * tc);
+  } else {
+    K = -solref[0] / std::max(OX_MINVAL, dmax * dmax);
+    Bd = -solref[1] / std::max(OX_MINVAL, dmax);
+  }
+  double vel = 0;
+  for (int i = 0; i < nv; i++) vel += jrow[i] * d->qvel[i];
+  d->efc_vel[r] = vel;
+  d->efc_aref[r] = -Bd * vel - K * imp * (pos - margin);
+}
+
+void makeConstraint(const Model* m, Data* d) {
+  int nv = m->nv;
+  d->nefc = 0;
+  if (disabled(m, OX_DSBL_CONSTRAINT)) return;
+  std::vector<double> jrow(nv), jacp(3 * nv), jac(3 * nv);
+  // joint limits
+  if (!disabled(m, OX_DSBL_LIMIT))
+    for (int j = 0; j < m->njnt; j++) {
+      if (!m->jnt_limited[j]) continue;
+      int jt = m->jnt_type[j];
+      if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
+      double value = d->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];
+      for (int side = -1; side <= 1; side += 2) {
+        double dist = side * (m->jnt_range[2 * j + (side + 1) / 2] - value);
+        if (dist < margin) {
+          std::fill(jrow.begin(), jrow.end(), 0.0);
+          jrow[m->jnt_dofadr[j]] = -side;
+          addRow(m, d, jrow.data(), dist, margin, m->dof_invweight0[m->jnt_dofadr[j]], m->jnt_solref + 2 * j,
+                 m->jnt_solimp + 5 * j, 0, j);
+        }
+      }
+    }
+  // contacts (pyramidal cone)
+  for (int c = 0; c < d->ncon; c++) {
+    int p = d->con_pair[c];
+    double includemargin = m->pair_margin[p] - m->pair_gap[p];
+    if (d->con_dist[c] >= includemargin) continue;
+    int b1 = m->geom_bodyid[m->pair_geom1[p]], b2 = m->geom_bodyid[m->pair_geom2[p]];
+    std::fill(jacp.begin(), jacp.end(), 0.0);
+    addJacP(m, d, b2, &d->con_pos[3 * c], +1, jacp.data());
+    addJacP(m, d, b1, &d->con_pos[3 * c], -1, jacp.data());
+    const double* frame = &d->con_frame[9 * c];
+    for (int r = 0; r < 3; r++)
+      for (int i = 0; i < nv; i++)
+        jac[r * nv + i] = frame[3 * r] * jacp[i] + frame[3 * r + 1] * jacp[nv + i] + frame[3 * r + 2] * jacp[2 * nv + i];
+    double tran = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+    const double* fri = m->pair_friction + 5 * p;
+    int dim = m->pair_dim[p];
+    if (dim == 1) {
+      addRow(m, d, jac.data(), d->con_dist[c], includemargin, tran, m->pair_solref + 2 * p, m->pair_solimp + 5 * p, 1, c);
+    } else {
+      int first = d->nefc;
+      for (int k = 1; k < dim; k++)
+        for (int s = 0; s < 2; s++) {
+          double sg = s ? -1.0 : 1.0;
+          for (int i = 0; i < nv; i++) jrow[i] = jac[i] + sg * fri[k - 1] * jac[k * nv + i];
+          addRow(m, d, jrow.data(), d->con_dist[c], includemargin, tran + fri[k - 1] * fri[k - 1] * tran, m->pair_solref + 2 * p,
+                 m->pair_solimp + 5 * p, 2, c);
+        }
+      // pyramidal regularisation: every edge gets R = 2 mu^2 R(first edge), mu = friction[0]/sqrt(impratio)
+      double mu = fri[0] * std::sqrt(1 / m->impratio);
+      double Rpy = 2 * mu * mu * d->efc_R[first];
+      for (int r = first; r < d->nefc; r++) d->efc_R[r] = Rpy;
+    }
+  }
+  for (int r = 0; r < d->nefc; r++) d->efc_D[r] = 1 / d->efc_R[r];
+}
+
+// ---------------------------------------------------------------- A.7 velocity
+void comVel(const Model* m, Data* d) {
+  std::fill(d->cvel.begin(), d->cvel.begin() + 6, 0.0);
+  for (int i = 1; i < m->nbody; i++) {
+    int bda = m->body_dofadr[i];
+    double cvel[6], cdofdot[36], tmp[6];
+    std::memcpy(cvel, &d->cvel[6 * m->body_parentid[i]], sizeof cvel);
+    int dofnum = m->body_dofnum[i];
+    for (int j = 0; j < dofnum; j++) {
+      int jt = m->jnt_type[m->dof_jntid[bda + j]];
+      if (jt == OX_JNT_FREE) {
+        std::fill(cdofdot, cdofdot + 18, 0.0);
+        for (int k = 0; k < 3; k++)
+          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + k) + c] * d->qvel[bda + k];
+        j += 3;
+      }
+      if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+        for (int k = 0; k < 3; k++) crossMotion(cdofdot + 6 * (j + k), cvel, &d->cdof[6 * (bda + j + k)]);
+        for (int k = 0; k < 3; k++)
+          for (int c = 0; c < 6; c++) cvel[c] += d->cdof[6 * (bda + j + k) + c] * d->qvel[bda + j + k];
+        j += 2;
+      } else {
+        crossMotion(cdofdot + 6 * j, cvel, &d->cdof[6 * (bda + j)]);
+        for (int c = 0; c < 6; c++) tmp[c] = d->cdof[6 * (bda + j) + c] * d->qvel[bda + j];
+        for (int c = 0; c < 6; c++) cvel[c] += tmp[c];
+      }
+    }
+    std::memcpy(&d->cvel[6 * i], cvel, sizeof cvel);
+    if (dofnum) std::memcpy(&d->cdof_dot[6 * bda], cdofdot, 6 * dofnum * sizeof(double));
+  }
+}
+
+void passive(const Model* m, Data* d) {
+  std::fill(d->qfrc_passive.begin(), d->qfrc_passive.end(), 0.0);
+  if (disabled(m, OX_DSBL_PASSIVE)) return;
+  for (int j = 0; j < m->njnt; j++) {
+    double k = m->jnt_stiffness[j];
+    if (k == 0) continue;
+    int pa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    switch (m->jnt_type[j]) {
+      case OX_JNT_FREE:
+        for (int c = 0; c < 3; c++) d->qfrc_passive[da + c] -= k * (d->qpos[pa + c] - m->qpos_spring[pa + c]);
+        pa += 3; da += 3;
+        // fallthrough
+      case OX_JNT_BALL: {
+        double q[4], dif[3];
+        std::memcpy(q, &d->qpos[pa], sizeof q);
+        normalize4(q);
+        subQuat(dif, q, m->qpos_spring + pa);
+        for (int c = 0; c < 3; c++) d->qfrc_passive[da + c] -= k * dif[c];
+        break;
+      }
+      default: d->qfrc_passive[da] -= k * (d->qpos[pa] - m->qpos_spring[pa]);
+    }
+  }
+  for (int i = 0; i < m->nv; i++) d->qfrc_passive[i] -= m->dof_damping[i] * d->qvel[i];
+}
+
+// ---------------------------------------------------------------- A.8 bias forces (RNE, flg_acc = 0)
+void rne(const Model* m, Data* d) {
+  int nb = m->nbody;
+  std::vector<double> cacc(6 * nb, 0.0), cfrc(6 * nb, 0.0);
+  if (!disabled(m, OX_DSBL_GRAVITY)) for (int k = 0; k < 3; k++) cacc[3 + k] = -m->gravity[k];
+  for (int i = 1; i < nb; i++) {
+    int bda = m->body_dofadr[i];
+    double tmp[6] = {0, 0, 0, 0, 0, 0}, tmp1[6];
+    for (int j = 0; j < m->body_dofnum[i]; j++)
+      for (int c = 0; c < 6; c++) tmp[c] += d->cdof_dot[6 * (bda + j) + c] * d->qvel[bda + j];
+    for (int c = 0; c < 6; c++) cacc[6 * i + c] = cacc[6 * m->body_parentid[i] + c] + tmp[c];
+    mulInertVec(&cfrc[6 * i], &d->cinert[10 * i], &cacc[6 * i]);
+    mulInertVec(tmp, &d->cinert[10 * i], &d->cvel[6 * i]);
+    crossForce(tmp1, &d->cvel[6 * i], tmp);
+    for (int c = 0; c < 6; c++) cfrc[6 * i + c] += tmp1[c];
+  }
+  for (int i = nb - 1; i > 0; i--) {
+    int p = m->body_parentid[i];
+    if (p) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * i + c];
+  }
+  for (int i = 0; i < m->nv; i++) d->qfrc_bias[i] = dot6(&d->cdof[6 * i], &cfrc[6 * m->dof_bodyid[i]]);
+}
+
+// ---------------------------------------------------------------- A.9 actuation
+void actuation(const Model* m, Data* d) {
+  std::fill(d->qfrc_actuator.begin(), d->qfrc_actuator.end(), 0.0);
+  std::fill(d->actuator_force.begin(), d->actuator_force.end(), 0.0);
+  if (disabled(m, OX_DSBL_ACTUATION)) return;
+  for (int i = 0; i < m->nu; i++) {
+    int j = m->actuator_trnid[i], qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    double gear = m->actuator_gear[i];
+    double length = gear * d->qpos[qa], velocity = gear * d->qvel[da];
+    double ctrl = d->ctrl[i];
+    if (m->actuator_ctrllimited[i] && !disabled(m, OX_DSBL_CLAMPCTRL))
+      ctrl = clip(ctrl, m->actuator_ctrlrange[2 * i], m->actuator_ctrlrange[2 * i + 1]);
+    const double* gp = m->actuator_gainprm + 3 * i;
+    const double* bp = m->actuator_biasprm + 3 * i;
+    double gain = gp[0];
+    if (m->actuator_gaintype[i] == OX_GAIN_AFFINE) gain += gp[1] * length + gp[2] * velocity;
+    double bias = 0;
+    if (m->actuator_biastype[i] == OX_BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
+    double force = gain * ctrl + bias;
+    if (m->actuator_forcelimited[i]) force = clip(force, m->actuator_forcerange[2 * i], m->actuator_forcerange[2 * i + 1]);
+    d->actuator_force[i] = force;
+    d->qfrc_actuator[da] += gear * force;
+  }
+}
+
+// ---------------------------------------------------------------- A.10 smooth acceleration
+void fwdAcceleration(const Model* m, Data* d) {
+  int nv = m->nv;
+  for (int i = 0; i < nv; i++)
+    d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_applied[i] + d->qfrc_actuator[i];
+  // Cartesian forces: force at xipos, torque
+  for (int b = 1; b < m->nbody; b++) {
+    const double* f = &d->xfrc_applied[6 * b];
+    if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
+    double offset[3];
+    for (int k = 0; k < 3; k++) offset[k] = d->xipos[3 * b + k] - d->subtree_com[3 * m->body_rootid[b] + k];
+    int body = b;
+    while (body && m->body_dofnum[body] == 0) body = m->body_parentid[body];
+    if (!body) continue;
+    for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i]) {
+      const double* cd = &d->cdof[6 * i];
+      double jp[3];
+      cross3(jp, cd, offset);
+      for (int k = 0; k < 3; k++) jp[k] += cd[3 + k];
+      d->qfrc_smooth[i] += dot3(jp, f) + dot3(cd, f + 3);
+    }
+  }
+  d->qacc_smooth = d->qfrc_smooth;
+  solveLD(m, d->qLD.data(), d->qLDiagInv.data(), d->qacc_smooth.data());
+}
+
+// ---------------------------------------------------------------- A.11 constraint solver (primal: Newton / CG)
+struct Solver {
+  const Model* m;
+  Data* d;
+  int nv, nefc;
+  std::vector<double> Ma, Jaref, grad, Mgrad, search, Mv, Jv, H, gradold, Mgradold;
+  std::vector<char> active;
+  double cost = 0, gauss = 0;
+  double quadGauss[3];
+  std::vector<double> quad;  // nefc x 3
+
+  Solver(const Model* m_, Data* d_) : m(m_), d(d_), nv(m_->nv), nefc(d_->nefc) {
+    Ma.resize(nv); Jaref.resize(nefc); grad.resize(nv); Mgrad.resize(nv); search.resize(nv); Mv.resize(nv); Jv.resize(nefc);
+    H.resize((size_t)nv * nv); gradold.resize(nv); Mgradold.resize(nv); active.resize(nefc); quad.resize(3 * (size_t)nefc);
+  }
+  // efc_force, active set, cost, qfrc_constraint at the current Jaref / Ma / qacc
+  void updateConstraint() {
+    double c = 0;
+    for (int r = 0; r < nefc; r++) {
+      if (Jaref[r] < 0) {
+        active[r] = 1;
+        d->efc_force[r] = -d->efc_D[r] * Jaref[r];
+        c += 0.5 * d->efc_D[r] * Jaref[r] * Jaref[r];
+      } else {
+        active[r] = 0;
+        d->efc_force[r] = 0;
+      }
+    }
+    for (int i = 0; i < nv; i++) {
+      double f = 0;
+      for (int r = 0; r < nefc; r++) f += d->efc_J[(size_t)r * nv + i] * d->efc_force[r];
+      d->qfrc_constraint[i] = f;
+    }
+    gauss = 0;
+    for (int i = 0; i < nv; i++) gauss += 0.5 * (Ma[i] - d->qfrc_smooth[i]) * (d->qacc[i] - d->qacc_smooth[i]);
+    cost = c + gauss;
+  }
+  void updateGradient(bool newton) {
+    for (int i = 0; i < nv; i++) grad[i] = Ma[i] - d->qfrc_smooth[i] - d->qfrc_constraint[i];
+    if (!newton) {
+      Mgrad = grad;
+      solveLD(m, d->qLD.data(), d->qLDiagInv.data(), Mgrad.data());
+      return;
+    }
+    // H = M + J' diag(D active) J, dense, lower triangle; Cholesky; Mgrad = H^-1 grad
+    std::fill(H.begin(), H.end(), 0.0);
+    for (int i = 0; i < nv; i++) {
+      int adr = m->dof_Madr[i];
+      for (int j = i; j >= 0; j = m->dof_parentid[j]) H[(size_t)i * nv + j] = d->qM[adr++];
+    }
+    for (int r = 0; r < nefc; r++) {
+      if (!active[r]) continue;
+      const double* J = &d->efc_J[(size_t)r * nv];
+      double D = d->efc_D[r];
+      for (int i = 0; i < nv; i++) {
+        if (J[i] == 0) continue;
+        double s = D * J[i];
+        for (int j = 0; j <= i; j++) H[(size_t)i * nv + j] += s * J[j];
+      }
+    }
+    for (int j = 0; j < nv; j++) {
+      double s = H[(size_t)j * nv + j];
+      for (int k = 0; k < j; k++) s -= H[(size_t)j * nv + k] * H[(size_t)j * nv + k];
+      s = std::sqrt(std::max(s, OX_MINVAL));
+      H[(size_t)j * nv + j] = s;
+      for (int i = j + 1; i < nv; i++) {
+        double v = H[(size_t)i * nv + j];
+        for (int k = 0; k < j; k++) v -= H[(size_t)i * nv + k] * H[(size_t)j * nv + k];
+        H[(size_t)i * nv + j] = v / s;
+      }
+    }
+    for (int i = 0; i < nv; i++) {
+      double v = grad[i];
+      for (int k = 0; k < i; k++) v -= H[(size_t)i * nv + k] * Mgrad[k];
+      Mgrad[i] = v / H[(size_t)i * nv + i];
+    }
+    for (int i = nv - 1; i >= 0; i--) {
+      double v = Mgrad[i];
+      for (int k = i + 1; k < nv; k++) v -= H[(size_t)k * nv + i] * Mgrad[k];
+      Mgrad[i] = v / H[(size_t)i * nv + i];
+    }
+  }
+  struct Pt { double alpha, cost, d0, d1; };
+  Pt eval(double a) const {
+    Pt p;
+    p.alpha = a;
+    p.cost = a * a * quadGauss[2] + a * quadGauss[1] + quadGauss[0];
+    p.d0 = 2 * a * quadGauss[2] + quadGauss[1];
+    p.d1 = 2 * quadGauss[2];
+    for (int r = 0; r < nefc; r++) {
+      double x = Jaref[r] + a * Jv[r];
+      if (x < 0) {
+        const double* q = &quad[3 * (size_t)r];
+        p.cost += a * a * q[2] + a * q[1] + q[0];
+        p.d0 += 2 * a * q[2] + q[1];
+        p.d1 += 2 * q[2];
+      }
+    }
+    if (p.d1 < OX_MINVAL) p.d1 = OX_MINVAL;
+    return p;
+  }
+  // exact line search on the convex piecewise-quadratic phi(alpha): safeguarded Newton on phi'
+  double lineSearch(int ls_iterations) {
+    double snorm = 0;
+    for (int i = 0; i < nv; i++) snorm += search[i] * search[i];
+    snorm = std::sqrt(snorm);
+    if (snorm < OX_MINVAL) return 0;
+    double gtol = m->tolerance * m->ls_tolerance * snorm * m->meaninertia * std::max(1, nv);
+    mulM(m, d->qM.data(), Mv.data(), search.data());
+    for (int r = 0; r < nefc; r++) {
+      double v = 0;
+      for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * search[i];
+      Jv[r] = v;
+    }
+    quadGauss[0] = gauss;
+    quadGauss[1] = 0;
+    quadGauss[2] = 0;
+    for (int i = 0; i < nv; i++) {
+      quadGauss[1] += search[i] * (Ma[i] - d->qfrc_smooth[i]);
+      quadGauss[2] += 0.5 * search[i] * Mv[i];
+    }
+    for (int r = 0; r < nefc; r++) {
+      double D = d->efc_D[r];
+      quad[3 * (size_t)r] = 0.5 * D * Jaref[r] * Jaref[r];
+      quad[3 * (size_t)r + 1] = D * Jaref[r] * Jv[r];
+      quad[3 * (size_t)r + 2] = 0.5 * D * Jv[r] * Jv[r];
+    }
+    const double eps = 4 * 2.220446049250313e-16;
+    Pt p0 = eval(0);
+    if (!(p0.d0 < 0)) return 0;
+    Pt lo = p0, hi = p0, cur = p0;
+    bool have_hi = false;
+    for (int it = 0; it < ls_iterations; it++) {
+      double a = cur.alpha - cur.d0 / cur.d1;
+      if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = 0.5 * (lo.alpha + hi.alpha);
+      if (std::fabs(a - cur.alpha) <= eps * std::fabs(a)) break;
+      cur = eval(a);
+      if (std::fabs(cur.d0) < gtol) break;
+      if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
+    }
+    return cur.cost <= p0.cost ? cur.alpha : 0;
+  }
+  void solve(bool newton, int maxiter, int ls_iterations) {
+    mulM(m, d->qM.data(), Ma.data(), d->qacc.data());
+    for (int r = 0; r < nefc; r++) {
+      double v = -d->efc_aref[r];
+      for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * d->qacc[i];
+      Jaref[r] = v;
+    }
+    updateConstraint();
+    updateGradient(newton);
+    for (int i = 0; i < nv; i++) search[i] = -Mgrad[i];
+    double scale = 1 / (m->meaninertia * std::max(1, nv));
+    int iter = 0;
+    double gn = 0;
+    for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
+    if (scale * std::sqrt(gn) < m->tolerance) maxiter = 0;
+    while (iter < maxiter) {
+      double alpha = lineSearch(ls_iterations);
+      if (alpha == 0) break;
+      for (int i = 0; i < nv; i++) { d->qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      for (int r = 0; r < nefc; r++) Jaref[r] += alpha * Jv[r];
+      if (!newton) { gradold = grad; Mgradold = Mgrad; }
+      double oldcost = cost;
+      updateConstraint();
+      updateGradient(newton);
+      iter++;
+      double improvement = scale * (oldcost - cost);
+      gn = 0;
+      for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
+      double gradient = scale * std::sqrt(gn);
+      if (improvement < m->tolerance || gradient < m->tolerance) break;
+      if (newton) for (int i = 0; i < nv; i++) search[i] = -Mgrad[i];
+      else {
+        double num = 0, den = 0;
+        for (int i = 0; i < nv; i++) { num += grad[i] * (Mgrad[i] - Mgradold[i]); den += gradold[i] * Mgradold[i]; }
+        double beta = num / std::max(OX_MINVAL, den);
+        if (beta < 0) beta = 0;
+        for (int i = 0; i < nv; i++) search[i] = -Mgrad[i] + beta * search[i];
+      }
+    }
+    d->solver_niter = iter;
+  }
+  // total cost of a candidate acceleration (warm-start selection)
+  double costAt(const double* qacc) {
+    std::vector<double> ma(nv);
+    mulM(m, d->qM.data(), ma.data(), qacc);
+    double c = 0;
+    for (int i = 0; i < nv; i++) c += 0.5 * (ma[i] - d->qfrc_smooth[i]) * (qacc[i] - d->qacc_smooth[i]);
+    for (int r = 0; r < nefc; r++) {
+      double v = -d->efc_aref[r];
+      for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * qacc[i];
+      if (v < 0) c += 0.5 * d->efc_D[r] * v * v;
+    }
+    return c;
+  }
+};
+
+void fwdConstraint(const Model* m, Data* d, int iterations, int ls_iterations) {
+  int nv = m->nv;
+  if (d->nefc == 0) {
+    d->qacc = d->qacc_smooth;
+    d->qacc_warmstart = d->qacc_smooth;
+    std::fill(d->qfrc_constraint.begin(), d->qfrc_constraint.end(), 0.0);
+    d->solver_niter = 0;
+    return;
+  }
+  Solver s(m, d);
+  if (!disabled(m, OX_DSBL_WARMSTART)) {
+    double cw = s.costAt(d->qacc_warmstart.data()), cs = s.costAt(d->qacc_smooth.data());
+    d->qacc = cw > cs ? d->qacc_smooth : d->qacc_warmstart;
+  } else d->qacc = d->qacc_smooth;
+  s.solve(m->solver == OX_SOL_NEWTON, iterations, ls_iterations);
+  for (int i = 0; i < nv; i++) d->qacc_warmstart[i] = d->qacc[i];
+}
+
+// ---------------------------------------------------------------- sensors (N2 subset)
+void subtreeLinvel(const Model* m, const Data* d, std::vector<double>& out) {
+  int nb = m->nbody;
+  out.assign(3 * nb, 0.0);
+  // linear momentum of each body: m * (v_lin at body com); cvel is at subtree_com[root] in world axes
+  for (int b = nb - 1; b > 0; b--) {
+    double dif[3], v[3];
+    for (int k = 0; k < 3; k++) dif[k] = d->xipos[3 * b + k] - d->subtree_com[3 * m->body_rootid[b] + k];
+    cross3(v, &d->cvel[6 * b], dif);
+    for (int k = 0; k < 3; k++) out[3 * b + k] += m->body_mass[b] * (d->cvel[6 * b + 3 + k] + v[k]);
+    int p = m->body_parentid[b];
+    for (int k = 0; k < 3; k++) out[3 * p + k] += out[3 * b + k];
+  }
+  for (int b = 0; b < nb; b++)
+    for (int k = 0; k < 3; k++) out[3 * b + k] /= std::max(OX_MINVAL, m->body_subtreemass[b]);
+}
+
+void objFrame(const Model* m, const Data* d, int objtype, int id, const double** pos, const double** mat, int* body) {
+  switch (objtype) {
+    case OX_OBJ_BODY: *pos = &d->xipos[3 * id]; *mat = &d->ximat[9 * id]; *body = id; break;
+    case OX_OBJ_XBODY: *pos = &d->xpos[3 * id]; *mat = &d->xmat[9 * id]; *body = id; break;
+    case OX_OBJ_GEOM: *pos = &d->geom_xpos[3 * id]; *mat = &d->geom_xmat[9 * id]; *body = m->geom_bodyid[id]; break;
+    default: *pos = &d->site_xpos[3 * id]; *mat = &d->site_xmat[9 * id]; *body = m->site_bodyid[id]; break;
+  }
+}
+void mat2Quat(double* q, const double* m) {
+  double tr = m[0] + m[4] + m[8];
+  if (tr > 0) {
+    double s = std::sqrt(tr + 1.0) * 2;
+    q[0] = 0.25 * s; q[1] = (m[7] - m[5]) / s; q[2] = (m[2] - m[6]) / s; q[3] = (m[3] - m[1]) / s;
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    double s = std::sqrt(1.0 + m[0] - m[4] - m[8]) * 2;
+    q[0] = (m[7] - m[5]) / s; q[1] = 0.25 * s; q[2] = (m[1] + m[3]) / s; q[3] = (m[2] + m[6]) / s;
+  } else if (m[4] > m[8]) {
+    double s = std::sqrt(1.0 + m[4] - m[0] - m[8]) * 2;
+    q[0] = (m[2] - m[6]) / s; q[1] = (m[1] + m[3]) / s; q[2] = 0.25 * s; q[3] = (m[5] + m[7]) / s;
+  } else {
+    double s = std::sqrt(1.0 + m[8] - m[0] - m[4]) * 2;
+    q[0] = (m[3] - m[1]) / s; q[1] = (m[2] + m[6]) / s; q[2] = (m[5] + m[7]) / s; q[3] = 0.25 * s;
+  }
+  normalize4(q);
+}
+
+void sensors(const Model* m, Data* d) {
+  std::vector<double> slv;
+  for (int s = 0; s < m->nsensor; s++) {
+    double* out = &d->sensordata[m->sensor_adr[s]];
+    int id = m->sensor_objid[s], ot = m->sensor_objtype[s];
+    const double *pos, *mat;
+    int body;
+    switch (m->sensor_type[s]) {
+      case OX_SENS_JOINTPOS: out[0] = d->qpos[m->jnt_qposadr[id]]; break;
+      case OX_SENS_JOINTVEL: out[0] = d->qvel[m->jnt_dofadr[id]]; break;
+      case OX_SENS_ACTUATORPOS: out[0] = m->actuator_gear[id] * d->qpos[m->jnt_qposadr[m->actuator_trnid[id]]]; break;
+      case OX_SENS_ACTUATORVEL: out[0] = m->actuator_gear[id] * d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]; break;
+      case OX_SENS_ACTUATORFRC: out[0] = d->actuator_force[id]; break;
+      case OX_SENS_SUBTREECOM: std::memcpy(out, &d->subtree_com[3 * id], 3 * sizeof(double)); break;
+      case OX_SENS_SUBTREELINVEL:
+        if (slv.empty()) subtreeLinvel(m, d, slv);
+        std::memcpy(out, &slv[3 * id], 3 * sizeof(double));
+        break;
+      case OX_SENS_FRAMEPOS: objFrame(m, d, ot, id, &pos, &mat, &body); std::memcpy(out, pos, 3 * sizeof(double)); break;
+      case OX_SENS_FRAMEQUAT: objFrame(m, d, ot, id, &pos, &mat, &body); mat2Quat(out, mat); break;
+      case OX_SENS_FRAMELINVEL: case OX_SENS_FRAMEANGVEL: case OX_SENS_VELOCIMETER: case OX_SENS_GYRO: {
+        // object velocity (mj_objectVelocity): cvel transported from the com frame origin to the object position
+        objFrame(m, d, ot, id, &pos, &mat, &body);
+        const double* cv = &d->cvel[6 * body];
+        double dif[3], lin[3], tmp[3];
+        for (int k = 0; k < 3; k++) dif[k] = pos[k] - d->subtree_com[3 * m->body_rootid[body] + k];
+        cross3(tmp, cv, dif);
+        for (int k = 0; k < 3; k++) lin[k] = cv[3 + k] + tmp[k];
+        int ty = m->sensor_type[s];
+        const double* src = (ty == OX_SENS_FRAMELINVEL || ty == OX_SENS_VELOCIMETER) ? lin : cv;
+        if (ty == OX_SENS_VELOCIMETER || ty == OX_SENS_GYRO) {  // local frame: mat' * v
+          for (int k = 0; k < 3; k++) out[k] = mat[k] * src[0] + mat[3 + k] * src[1] + mat[6 + k] * src[2];
+        } else std::memcpy(out, src, 3 * sizeof(double));
+        break;
+      }
+      case OX_SENS_CLOCK: out[0] = d->time; break;
+      default: break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- forward / integrators / step
+void forwardSkip(const Model* m, Data* d, bool skipsensor) {
+  kinematics(m, d);
+  comPos(m, d);
+  crb(m, d);
+  factorM(m, d);
+  collision(m, d);
+  comVel(m, d);  // (order within the position/velocity stages does not matter for independent outputs)
+  makeConstraint(m, d);
+  passive(m, d);
+  rne(m, d);
+  actuation(m, d);
+  fwdAcceleration(m, d);
+  fwdConstraint(m, d, m->iterations, m->ls_iterations);
+  if (!skipsensor) sensors(m, d);
+}
+
+void integratePos(const Model* m, double* qpos, const double* qvel, double dt) {
+  for (int j = 0; j < m->njnt; j++) {
+    int pa = m->jnt_qposadr[j], va = m->jnt_dofadr[j];
+    switch (m->jnt_type[j]) {
+      case OX_JNT_FREE:
+        for (int i = 0; i < 3; i++) qpos[pa + i] += dt * qvel[va + i];
+        pa += 3; va += 3;
+        // fallthrough
+      case OX_JNT_BALL: quatIntegrate(qpos + pa, qvel + va, dt); break;
+      default: qpos[pa] += dt * qvel[va];
+    }
+  }
+}
+void advance(const Model* m, Data* d, const double* qacc, const double* qvel_override) {
+  for (int i = 0; i < m->nv; i++) d->qvel[i] += m->timestep * qacc[i];
+  integratePos(m, d->qpos.data(), qvel_override ? qvel_override : d->qvel.data(), m->timestep);
+  d->time += m->timestep;
+}
+void euler(const Model* m, Data* d) {
+  int nv = m->nv;
+  bool damping = false;
+  if (!disabled(m, OX_DSBL_EULERDAMP))
+    for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) damping = true;
+  if (!damping) { advance(m, d, d->qacc.data(), nullptr); return; }
+  // implicit-in-velocity joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint.
+  // MuJoCo factors into d->qLD, overwriting the factor of M; so do we.
+  d->qLD = d->qM;
+  for (int i = 0; i < nv; i++) d->qLD[m->dof_Madr[i]] += m->timestep * m->dof_damping[i];
+  factorLD(m, d->qLD.data(), d->qLDiagInv.data());
+  std::vector<double> qacc(nv);
+  for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+  solveLD(m, d->qLD.data(), d->qLDiagInv.data(), qacc.data());
+  advance(m, d, qacc.data(), nullptr);
+}
+void rk4(const Model* m, Data* d) {
+  static const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1}, Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+  int nv = m->nv, nq = m->nq;
+  double h = m->timestep, time = d->time;
+  double C[3], T[3];
+  for (int i = 0; i < 3; i++) { C[i] = A[3 * i] + A[3 * i + 1] + A[3 * i + 2]; T[i] = time + C[i] * h; }
+  std::vector<double> X0q = d->qpos, X0v = d->qvel;
+  std::vector<std::vector<double>> Fv(4), Fa(4);
+  Fv[0] = d->qvel; Fa[0] = d->qacc;
+  std::vector<double> dXv(nv), dXa(nv);
+  for (int i = 1; i < 4; i++) {
+    std::fill(dXv.begin(), dXv.end(), 0.0);
+    std::fill(dXa.begin(), dXa.end(), 0.0);
+    for (int j = 0; j < i; j++) {
+      double a = A[(i - 1) * 3 + j];
+      for (int k = 0; k < nv; k++) { dXv[k] += a * Fv[j][k]; dXa[k] += a * Fa[j][k]; }
+    }
+    d->qpos = X0q;
+    integratePos(m, d->qpos.data(), dXv.data(), h);
+    for (int k = 0; k < nv; k++) d->qvel[k] = X0v[k] + h * dXa[k];
+    d->time = T[i - 1];
+    forwardSkip(m, d, true);
+    Fv[i] = d->qvel; Fa[i] = d->qacc;
+  }
+  std::fill(dXv.begin(), dXv.end(), 0.0);
+  std::fill(dXa.begin(), dXa.end(), 0.0);
+  for (int j = 0; j < 4; j++)
+    for (int k = 0; k < nv; k++) { dXv[k] += Bw[j] * Fv[j][k]; dXa[k] += Bw[j] * Fa[j][k]; }
+  d->time = time;
+  d->qpos = X0q; d->qvel = X0v;
+  (void)nq;
+  advance(m, d, dXa.data(), dXv.data());
+}
+
+bool isBad(double x) { return std::isnan(x) || x > OX_MAXVAL || x < -OX_MAXVAL; }
+
+void resetData(const Model* m, Data* d) {
+  std::memcpy(d->qpos.data(), m->qpos0, m->nq * sizeof(double));
+  auto z = [](std::vector<double>& v) { std::fill(v.begin(), v.end(), 0.0); };
+  z(d->qvel); z(d->ctrl); z(d->qfrc_applied); z(d->xfrc_applied); z(d->qacc_warmstart); z(d->qacc);
+  z(d->xpos); z(d->xquat); z(d->xmat); z(d->xipos); z(d->ximat); z(d->xanchor); z(d->xaxis); z(d->geom_xpos); z(d->geom_xmat);
+  z(d->site_xpos); z(d->site_xmat); z(d->subtree_com); z(d->cinert); z(d->cdof); z(d->qM); z(d->qLD); z(d->qLDiagInv);
+  z(d->cvel); z(d->cdof_dot); z(d->qfrc_bias); z(d->qfrc_passive); z(d->actuator_force); z(d->qfrc_actuator); z(d->qfrc_smooth);
+  z(d->qacc_smooth); z(d->qfrc_constraint); z(d->sensordata); z(d->efc_force);
+  d->time = 0; d->ncon = 0; d->nefc = 0; d->solver_niter = 0;
+}
+
+void step(const Model* m, Data* d) {
+  bool bad = false;
+  for (double x : d->qpos) bad |= isBad(x);
+  for (double x : d->qvel) bad |= isBad(x);
+  if (bad) { resetData(m, d); d->diverged++; }
+  forwardSkip(m, d, false);
+  bad = false;
+  for (double x : d->qacc) bad |= isBad(x);
+  if (bad) { resetData(m, d); d->diverged++; forwardSkip(m, d, false); }
+  if (m->integrator == OX_INT_RK4) rk4(m, d); else euler(m, d);
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 control stream
+inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+inline double ctrl_from_bits(uint32_t x) {  // U(-1,1) on a 2^-23 lattice: exact in fp32 and fp64
+  return (double)(int64_t)(((uint64_t)(x >> 9) * 2 + 1)) * (1.0 / 8388608.0) - 1.0;
+}
+void fillCtrlPhilox(const Model* m, Data* d, uint64_t seed, int64_t genv, int64_t stepno) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int g = 0; g * 4 < m->nu; g++) {
+    uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)stepno, (uint32_t)g}, out[4];
+    philox4x32_10(ctr, key, out);
+    for (int k = 0; k < 4 && g * 4 + k < m->nu; k++) d->ctrl[g * 4 + k] = ctrl_from_bits(out[k]);
+  }
+}
+
+}  // namespace
+
+// ================================================================== exported C interface
+extern "C" {
+#define OXO_API __attribute__((visibility("default")))
+
+OXO_API oxo_data* oxo_make_data(const Model* m) {
+  Data* d = new Data();
+  int nb = m->nbody, nv = m->nv;
+  d->qpos.resize(m->nq); d->qvel.resize(nv); d->ctrl.resize(m->nu); d->qfrc_applied.resize(nv); d->xfrc_applied.resize(6 * nb);
+  d->qacc_warmstart.resize(nv);
+  d->xpos.resize(3 * nb); d->xquat.resize(4 * nb); d->xmat.resize(9 * nb); d->xipos.resize(3 * nb); d->ximat.resize(9 * nb);
+  d->xanchor.resize(3 * m->njnt); d->xaxis.resize(3 * m->njnt); d->geom_xpos.resize(3 * m->ngeom); d->geom_xmat.resize(9 * m->ngeom);
+  d->site_xpos.resize(3 * m->nsite); d->site_xmat.resize(9 * m->nsite);
+  d->subtree_com.resize(3 * nb); d->cinert.resize(10 * nb); d->cdof.resize(6 * nv); d->crb.resize(10 * nb);
+  d->qM.resize(m->nM); d->qLD.resize(m->nM); d->qLDiagInv.resize(nv);
+  d->cvel.resize(6 * nb); d->cdof_dot.resize(6 * nv); d->qfrc_bias.resize(nv); d->qfrc_passive.resize(nv);
+  d->actuator_force.resize(m->nu); d->qfrc_actuator.resize(nv); d->qfrc_smooth.resize(nv); d->qacc_smooth.resize(nv);
+  int nc = std::max(1, m->nconmax), ne = std::max(1, m->nefcmax);
+  d->con_dist.resize(nc); d->con_pos.resize(3 * nc); d->con_frame.resize(9 * nc); d->con_pair.resize(nc);
+  d->efc_J.resize((size_t)ne * std::max(1, nv)); d->efc_pos.resize(ne); d->efc_margin.resize(ne); d->efc_D.resize(ne);
+  d->efc_R.resize(ne); d->efc_aref.resize(ne); d->efc_vel.resize(ne); d->efc_force.resize(ne); d->efc_diagApprox.resize(ne);
+  d->efc_type.resize(ne); d->efc_id.resize(ne);
+  d->qacc.resize(nv); d->qfrc_constraint.resize(nv); d->sensordata.resize(m->nsensordata);
+  resetData(m, d);
+  return d;
+}
+OXO_API void oxo_free_data(oxo_data* d) { delete d; }
+OXO_API void oxo_reset(const Model* m, oxo_data* d) { resetData(m, d); }
+OXO_API void oxo_forward(const Model* m, oxo_data* d) { forwardSkip(m, d, false); }
+OXO_API void oxo_step(const Model* m, oxo_data* d) { step(m, d); }
+OXO_API void oxo_fill_ctrl_philox(const Model* m, oxo_data* d, uint64_t seed, int64_t genv, int64_t stepno) {
+  fillCtrlPhilox(m, d, seed, genv, stepno);
+}
+OXO_API void oxo_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+
+// individual stages, in pipeline order
+OXO_API void oxo_stage(const Model* m, oxo_data* d, const char* name) {
+  std::string s(name);
+  if (s == "kinematics") kinematics(m, d);
+  else if (s == "comPos") comPos(m, d);
+  else if (s == "crb") crb(m, d);
+  else if (s == "factorM") factorM(m, d);
+  else if (s == "collision") collision(m, d);
+  else if (s == "makeConstraint") makeConstraint(m, d);
+  else if (s == "comVel") comVel(m, d);
+  else if (s == "passive") passive(m, d);
+  else if (s == "rne") rne(m, d);
+  else if (s == "actuation") actuation(m, d);
+  else if (s == "fwdAcceleration") fwdAcceleration(m, d);
+  else if (s == "fwdConstraint") fwdConstraint(m, d, m->iterations, m->ls_iterations);
+  else if (s == "sensors") sensors(m, d);
+}
+
+// field access: pointer into the AoS arrays (valid until oxo_free_data)
+OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
+  std::string s(name);
+#define F(f) if (s == #f) { *count = (int32_t)d->f.size(); return d->f.data(); }
+  F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
+  F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
+  F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
+  F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)
+  F(efc_diagApprox) F(qacc) F(qfrc_constraint) F(sensordata)
+#undef F
+  if (s == "time") { *count = 1; return &d->time; }
+  *count = -1;
+  return nullptr;
+}
+OXO_API int32_t oxo_int(oxo_data* d, const char* name) {
+  std::string s(name);
+  if (s == "ncon") return d->ncon;
+  if (s == "nefc") return d->nefc;
+  if (s == "solver_niter") return d->solver_niter;
+  if (s == "diverged") return d->diverged;
+  return -1;
+}
+OXO_API const int32_t* oxo_int_field(oxo_data* d, const char* name, int32_t* count) {
+  std::string s(name);
+  if (s == "con_pair") { *count = d->ncon; return d->con_pair.data(); }
+  if (s == "efc_type") { *count = d->nefc; return d->efc_type.data(); }
+  if (s == "efc_id") { *count = d->nefc; return d->efc_id.data(); }
+  *count = -1;
+  return nullptr;
+}
+
+/* CPU baseline: step `nenv` envs for `nsteps` steps on `nthreads` threads with the same seeded initial
+ * states (given as [nenv][nq], [nenv][nv]) and Philox controls as the GPU run. Returns wall seconds.
+ * Final qpos/qvel are written back so the caller can cross-check against the GPU. */
+OXO_API double oxo_bench(const Model* m, int32_t nenv, int32_t nsteps, int32_t nthreads, uint64_t seed, int64_t env_id_offset,
+                         int64_t step0, double* qpos_io, double* qvel_io, double* stats_out /*4: ncon nefc niter diverged*/) {
+  if (nthreads < 1) nthreads = 1;
+  std::vector<std::thread> th;
+  std::vector<double> st(4 * (size_t)nthreads, 0.0);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t]() {
+      int lo = (int)((int64_t)nenv * t / nthreads), hi = (int)((int64_t)nenv * (t + 1) / nthreads);
+      Data* d = oxo_make_data(m);
+      for (int e = lo; e < hi; e++) {
+        resetData(m, d);
+        std::memcpy(d->qpos.data(), qpos_io + (size_t)e * m->nq, m->nq * sizeof(double));
+        std::memcpy(d->qvel.data(), qvel_io + (size_t)e * m->nv, m->nv * sizeof(double));
+        int div0 = d->diverged;
+        for (int s = 0; s < nsteps; s++) {
+          fillCtrlPhilox(m, d, seed, env_id_offset + e, step0 + s);
+          step(m, d);
+          st[4 * t] += d->ncon; st[4 * t + 1] += d->nefc; st[4 * t + 2] += d->solver_niter;
+        }
+        st[4 * t + 3] += d->diverged - div0;
+        std::memcpy(qpos_io + (size_t)e * m->nq, d->qpos.data(), m->nq * sizeof(double));
+        std::memcpy(qvel_io + (size_t)e * m->nv, d->qvel.data(), m->nv * sizeof(double));
+      }
+      delete d;
+    });
+  for (auto& x : th) x.join();
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (stats_out) {
+    for (int k = 0; k < 4; k++) stats_out[k] = 0;
+    for (int t = 0; t < nthreads; t++) for (int k = 0; k < 4; k++) stats_out[k] += st[4 * t + k];
+    double n = (double)nenv * nsteps;
+    for (int k = 0; k < 3; k++) stats_out[k] /= std::max(1.0, n);
+  }
+  return sec;
+}
+OXO_API int32_t oxo_hardware_threads(void) { return (int32_t)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,572 @@
+// Batch side of the C ABI: SoA arena on one B200, sm_100a kernels for every mj_step stage, launch
+// orchestration (fused / staged, optional CUDA graph), bulk and per-env I/O.
+// Replaces mj_makeData / mj_step / mj_forward / mj_resetData as called by the reference at
+// src/physics.rs:14,22,44-54 for nenv independent copies of one model.
+//
+// There is no CPU fallback in this file: every compute entry point launches CUDA kernels or fails
+// with OX_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ox_internal.h"
+#include "ox_model.h"
+#include "ox_arena.h"
+#include "ox_stages.cuh"
+
+namespace ox {
+
+// ---------------------------------------------------------------- model staging: one TMA bulk copy per CTA
+// (cp.async.bulk global -> shared, completion on an mbarrier; shows up as UBLKCP in SASS)
+__device__ __forceinline__ const unsigned char* stage_model(const unsigned char* __restrict__ gblob, int bytes) {
+  extern __shared__ __align__(128) unsigned char ox_smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ox_smem);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gblob),
+                 "r"(bytes), "r"(mb)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb)
+        : "memory");
+  }
+  return ox_smem;
+}
+
+struct StepArgs {
+  int nsteps;
+  int philox;
+  uint64_t seed;
+  int64_t env_id_offset;
+  const long long* d_step;
+};
+
+enum Stage { ST_CTRL = 0, ST_CHECK, ST_KIN, ST_CRB, ST_COLLIDE, ST_VEL, ST_EFC, ST_ACC, ST_SOLVE, ST_SENSE, ST_INTEGRATE, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"ctrl_rng", "check_pos_vel", "kin_com", "crb_ldl", "collide", "vel_bias",
+                                             "make_efc", "act_smooth_acc", "solve", "sensors_check_acc", "integrate"};
+
+template <typename T>
+__global__ void k_step_fused(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, StepArgs a) {
+  DevModel<T> m{stage_model(gblob, bytes)};
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  Env<T> env(m, b, e);
+  const long long step0 = a.philox ? *a.d_step : 0;
+  for (int s = 0; s < a.nsteps; s++) {
+    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
+    env.step();
+  }
+}
+
+template <typename T>
+__global__ void k_forward_fused(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b) {
+  DevModel<T> m{stage_model(gblob, bytes)};
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  Env<T> env(m, b, e);
+  env.forward(false);
+}
+
+template <typename T, int STAGE>
+__global__ void k_stage(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, StepArgs a) {
+  DevModel<T> m{stage_model(gblob, bytes)};
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  Env<T> env(m, b, e);
+  if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, *a.d_step);
+  if (STAGE == ST_CHECK) {
+    if (env.bad_state()) { env.reset_data(); env.ati(b.diverged, 0) += 1; }
+  }
+  if (STAGE == ST_KIN) { env.kinematics(); env.com_pos(); }
+  if (STAGE == ST_CRB) { env.crb(); env.factor_m(); }
+  if (STAGE == ST_COLLIDE) env.collision();
+  if (STAGE == ST_VEL) { env.com_vel(); env.passive(); env.rne(); }
+  if (STAGE == ST_EFC) env.make_constraint();
+  if (STAGE == ST_ACC) { env.actuation(); env.fwd_acceleration(); }
+  if (STAGE == ST_SOLVE) env.fwd_constraint();
+  if (STAGE == ST_SENSE) {
+    env.sensors();
+    if (env.bad_acc()) { env.reset_data(); env.ati(b.diverged, 0) += 1; env.forward(false); }
+    env.accumulate_stats();
+  }
+  if (STAGE == ST_INTEGRATE) {
+    if (m.h().integrator == OX_INT_RK4) env.rk4(); else env.euler();
+  }
+}
+
+__global__ void k_bump(long long* d_step, int n) { *d_step += n; }
+
+template <typename T>
+__global__ void k_reset(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, const uint8_t* __restrict__ mask) {
+  DevModel<T> m{stage_model(gblob, bytes)};
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.nenv) return;
+  if (mask && !mask[e]) return;
+  Env<T> env(m, b, e);
+  env.reset_data();
+}
+
+// layout / dtype conversion between a user buffer and a native SoA field
+// dir 0: user -> field, 1: field -> user
+template <typename TF, typename TU>
+__global__ void k_pack(TF* __restrict__ field, TU* __restrict__ user, int nenv, int cnt, int stride, int layout, int dir) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nenv * cnt) return;
+  // consecutive threads walk consecutive envs: coalesced on the SoA side
+  const int e = (int)(idx % nenv), i = (int)(idx / nenv);
+  const size_t fi = (size_t)i * stride + e;
+  const size_t ui = layout == OX_LAYOUT_ELEM_MAJOR ? (size_t)i * nenv + e : (size_t)e * cnt + i;
+  if (dir == 0) field[fi] = (TF)user[ui];
+  else user[ui] = (TU)field[fi];
+}
+
+}  // namespace ox
+
+using namespace ox;
+
+struct ox_batch {
+  const ox_model* model = nullptr;
+  ox_batch_config cfg{};
+  int nenv = 0, stride = 0, block = 32, grid = 0;
+  bool f64 = false;
+  cudaStream_t stream = nullptr;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  unsigned char* d_blob = nullptr;
+  int blob_bytes = 0;
+  DevBatch<float> bf{};
+  DevBatch<double> bd{};
+  std::map<int, FieldInfo> fields;
+  long long launches = 0;
+  int philox = 0;
+  uint64_t seed = 0;
+  long long* d_step = nullptr;
+  void* d_tmp = nullptr;  // staging for bulk I/O
+  size_t d_tmp_bytes = 0;
+  void* h_tmp = nullptr;  // pinned staging for per-env I/O
+  size_t h_tmp_bytes = 0;
+  uint8_t* d_mask = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraph_t graph = nullptr;
+};
+
+namespace {
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t err__ = (expr);                                                                        \
+    if (err__ != cudaSuccess) {                                                                        \
+      ox::set_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #expr);           \
+      return OX_ERR_CUDA;                                                                              \
+    }                                                                                                  \
+  } while (0)
+
+template <typename T> DevBatch<T>& dev(ox_batch* b);
+template <> DevBatch<float>& dev<float>(ox_batch* b) { return b->bf; }
+template <> DevBatch<double>& dev<double>(ox_batch* b) { return b->bd; }
+
+StepArgs make_args(ox_batch* b, int nsteps) {
+  StepArgs a;
+  a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset; a.d_step = b->d_step;
+  return a;
+}
+
+template <typename T, int STAGE>
+void launch_stage(ox_batch* b, const StepArgs& a) {
+  k_stage<T, STAGE><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), a);
+  b->launches++;
+}
+
+template <typename T>
+void launch_staged_step(ox_batch* b) {
+  StepArgs a = make_args(b, 1);
+  if (b->philox) launch_stage<T, ST_CTRL>(b, a);
+  launch_stage<T, ST_CHECK>(b, a);
+  launch_stage<T, ST_KIN>(b, a);
+  launch_stage<T, ST_CRB>(b, a);
+  launch_stage<T, ST_COLLIDE>(b, a);
+  launch_stage<T, ST_VEL>(b, a);
+  launch_stage<T, ST_EFC>(b, a);
+  launch_stage<T, ST_ACC>(b, a);
+  launch_stage<T, ST_SOLVE>(b, a);
+  launch_stage<T, ST_SENSE>(b, a);
+  launch_stage<T, ST_INTEGRATE>(b, a);
+  if (b->philox) {
+    k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
+    b->launches++;
+  }
+}
+
+template <typename T>
+ox_status do_step(ox_batch* b, int nsteps) {
+  if (b->cfg.mode == OX_MODE_FUSED) {
+    k_step_fused<T><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), make_args(b, nsteps));
+    b->launches++;
+    if (b->philox) {
+      k_bump<<<1, 1, 0, b->stream>>>(b->d_step, nsteps);
+      b->launches++;
+    }
+  } else if (b->cfg.use_graph) {
+    if (!b->graph_exec) {
+      long long saved = b->launches;
+      CU_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+      launch_staged_step<T>(b);
+      CU_TRY(cudaStreamEndCapture(b->stream, &b->graph));
+      CU_TRY(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
+      b->launches = saved;
+    }
+    const int per = ST_COUNT - 1 + (b->philox ? 2 : 0);
+    for (int s = 0; s < nsteps; s++) {
+      CU_TRY(cudaGraphLaunch(b->graph_exec, b->stream));
+      b->launches += per;
+    }
+  } else {
+    for (int s = 0; s < nsteps; s++) launch_staged_step<T>(b);
+  }
+  CU_TRY(cudaGetLastError());
+  return OX_OK;
+}
+
+void drop_graph(ox_batch* b) {
+  if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+  if (b->graph) { cudaGraphDestroy(b->graph); b->graph = nullptr; }
+}
+
+ox_status ensure_tmp(ox_batch* b, size_t bytes) {
+  if (bytes <= b->d_tmp_bytes) return OX_OK;
+  if (b->d_tmp) { CU_TRY(cudaStreamSynchronize(b->stream)); CU_TRY(cudaFree(b->d_tmp)); b->d_tmp = nullptr; }
+  CU_TRY(cudaMalloc(&b->d_tmp, bytes));
+  b->d_tmp_bytes = bytes;
+  return OX_OK;
+}
+ox_status ensure_htmp(ox_batch* b, size_t bytes) {
+  if (bytes <= b->h_tmp_bytes) return OX_OK;
+  if (b->h_tmp) { CU_TRY(cudaStreamSynchronize(b->stream)); CU_TRY(cudaFreeHost(b->h_tmp)); b->h_tmp = nullptr; }
+  CU_TRY(cudaMallocHost(&b->h_tmp, bytes));
+  b->h_tmp_bytes = bytes;
+  return OX_OK;
+}
+
+template <typename TF, typename TU>
+void launch_pack(ox_batch* b, void* field, void* user, int cnt, int layout, int dir) {
+  const long long n = (long long)b->nenv * cnt;
+  const int threads = 256;
+  const int blocks = (int)((n + threads - 1) / threads);
+  k_pack<TF, TU><<<blocks, threads, 0, b->stream>>>((TF*)field, (TU*)user, b->nenv, cnt, b->stride, layout, dir);
+  b->launches++;
+}
+
+ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int layout, int dir) {
+  if (!b || !buf) { ox::set_error("bulk I/O: null argument"); return OX_ERR_INVALID; }
+  auto it = b->fields.find(field);
+  if (it == b->fields.end()) { ox::set_error("bulk I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
+  const FieldInfo& fi = it->second;
+  if (field == OX_F_ACT) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if (fi.count == 0) return OX_OK;
+  if (layout != OX_LAYOUT_ENV_MAJOR && layout != OX_LAYOUT_ELEM_MAJOR) { ox::set_error("bulk I/O: bad layout"); return OX_ERR_INVALID; }
+  if (!fi.is_int && dtype != OX_F32 && dtype != OX_F64) { ox::set_error("bulk I/O: bad dtype"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const size_t usz = fi.is_int ? 4 : (dtype == OX_F64 ? 8 : 4);
+  const size_t bytes = (size_t)b->nenv * fi.count * usz;
+  void* dbuf = buf;
+  if (mem == OX_MEM_HOST) {
+    ox_status s = ensure_tmp(b, bytes);
+    if (s) return s;
+    dbuf = b->d_tmp;
+    if (dir == 0) CU_TRY(cudaMemcpyAsync(dbuf, buf, bytes, cudaMemcpyHostToDevice, b->stream));
+  } else if (mem != OX_MEM_DEVICE) { ox::set_error("bulk I/O: bad mem"); return OX_ERR_INVALID; }
+  if (fi.is_int) launch_pack<int32_t, int32_t>(b, fi.ptr, dbuf, fi.count, layout, dir);
+  else if (b->f64) {
+    if (dtype == OX_F64) launch_pack<double, double>(b, fi.ptr, dbuf, fi.count, layout, dir);
+    else launch_pack<double, float>(b, fi.ptr, dbuf, fi.count, layout, dir);
+  } else {
+    if (dtype == OX_F64) launch_pack<float, double>(b, fi.ptr, dbuf, fi.count, layout, dir);
+    else launch_pack<float, float>(b, fi.ptr, dbuf, fi.count, layout, dir);
+  }
+  CU_TRY(cudaGetLastError());
+  if (mem == OX_MEM_HOST && dir == 1) {
+    CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+  }
+  return OX_OK;
+}
+
+ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, double* dout, const double* din, int32_t* iout) {
+  if (!b) { ox::set_error("per-env I/O: null batch"); return OX_ERR_INVALID; }
+  auto it = b->fields.find(field);
+  if (it == b->fields.end()) { ox::set_error("per-env I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
+  const FieldInfo& fi = it->second;
+  if (field == OX_F_ACT) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if (env < 0 || env >= b->nenv || offset < 0 || count < 0 || offset + count > fi.count) {
+    ox::set_error("per-env I/O: index out of range");
+    return OX_ERR_INVALID;
+  }
+  if ((iout != nullptr) != fi.is_int) { ox::set_error("per-env I/O: int/real field mismatch"); return OX_ERR_INVALID; }
+  if (count == 0) return OX_OK;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const size_t esz = fi.is_int ? 4 : (b->f64 ? 8 : 4);
+  ox_status s = ensure_htmp(b, (size_t)count * 8);
+  if (s) return s;
+  unsigned char* base = (unsigned char*)fi.ptr + ((size_t)offset * b->stride + env) * esz;
+  const size_t pitch = (size_t)b->stride * esz;
+  if (din) {
+    if (b->f64) for (int i = 0; i < count; i++) ((double*)b->h_tmp)[i] = din[i];
+    else for (int i = 0; i < count; i++) ((float*)b->h_tmp)[i] = (float)din[i];
+    CU_TRY(cudaMemcpy2DAsync(base, pitch, b->h_tmp, esz, esz, count, cudaMemcpyHostToDevice, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+  } else {
+    CU_TRY(cudaMemcpy2DAsync(b->h_tmp, esz, base, pitch, esz, count, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    if (fi.is_int) for (int i = 0; i < count; i++) iout[i] = ((int32_t*)b->h_tmp)[i];
+    else if (b->f64) for (int i = 0; i < count; i++) dout[i] = ((double*)b->h_tmp)[i];
+    else for (int i = 0; i < count; i++) dout[i] = ((float*)b->h_tmp)[i];
+  }
+  return OX_OK;
+}
+
+}  // namespace
+
+template <typename T>
+static ox_status stage_times_impl(ox_batch* b, int reps, double* out_ms) {
+  std::vector<cudaEvent_t> ev(ST_COUNT + 1);
+  for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+  for (int s = 0; s < ST_COUNT; s++) out_ms[s] = 0;
+  StepArgs a = make_args(b, 1);
+  for (int r = 0; r < reps; r++) {
+    CU_TRY(cudaEventRecord(ev[0], b->stream));
+#define RUN(S)                                          \
+  launch_stage<T, S>(b, a);                             \
+  CU_TRY(cudaEventRecord(ev[S + 1], b->stream));
+    RUN(ST_CTRL) RUN(ST_CHECK) RUN(ST_KIN) RUN(ST_CRB) RUN(ST_COLLIDE) RUN(ST_VEL) RUN(ST_EFC) RUN(ST_ACC) RUN(ST_SOLVE)
+    RUN(ST_SENSE) RUN(ST_INTEGRATE)
+#undef RUN
+    k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
+    b->launches++;
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    for (int s = 0; s < ST_COUNT; s++) {
+      float ms = 0;
+      CU_TRY(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+      out_ms[s] += ms;
+    }
+  }
+  for (int s = 0; s < ST_COUNT; s++) out_ms[s] /= std::max(1, reps);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return OX_OK;
+}
+
+extern "C" {
+
+void ox_batch_config_default(ox_batch_config* cfg) {
+  if (!cfg) return;
+  cfg->nenv = 1; cfg->device = 0; cfg->precision = OX_F32; cfg->mode = OX_MODE_FUSED; cfg->iterations = 0; cfg->ls_iterations = 0;
+  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1;
+}
+
+ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batch** out) {
+  if (!m || !cfg || !out) { ox::set_error("ox_batch_create: null argument"); return OX_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->nenv < 1) { ox::set_error("ox_batch_create: nenv must be >= 1"); return OX_ERR_INVALID; }
+  if (cfg->precision != OX_F32 && cfg->precision != OX_F64) { ox::set_error("ox_batch_create: bad precision"); return OX_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    ox::set_error(std::string("no CUDA device available (") + cudaGetErrorString(err) +
+                  "); libox_b200 has no CPU fallback");
+    cudaGetLastError();
+    return OX_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { ox::set_error("ox_batch_create: bad device ordinal"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(cfg->device));
+  std::unique_ptr<ox_batch, void (*)(ox_batch*)> b(new ox_batch(), ox_batch_free);
+  b->model = m;
+  b->cfg = *cfg;
+  b->nenv = cfg->nenv;
+  b->stride = (cfg->nenv + 31) / 32 * 32;
+  b->f64 = cfg->precision == OX_F64;
+  int block = cfg->block_threads;
+  if (block <= 0) {
+    const int warps = (b->nenv + 31) / 32;
+    block = warps <= 4 * 148 ? 32 : (warps <= 8 * 148 ? 64 : 128);
+  }
+  if (block % 32 != 0 || block > 1024) { ox::set_error("ox_batch_create: block_threads must be a multiple of 32, <= 1024"); return OX_ERR_INVALID; }
+  b->block = block;
+  b->grid = (b->nenv + block - 1) / block;
+  CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  const ox_model_tables& t = m->t;
+  std::vector<unsigned char> blob = b->f64 ? build_blob<double>(t, cfg->iterations, cfg->ls_iterations, cfg->tolerance)
+                                           : build_blob<float>(t, cfg->iterations, cfg->ls_iterations, cfg->tolerance);
+  b->blob_bytes = (int)blob.size();
+  if (b->blob_bytes > 200 * 1024) { ox::set_error("model constant tables exceed shared memory (200 KB)"); return OX_ERR_INVALID; }
+  CU_TRY(cudaMalloc(&b->d_blob, blob.size()));
+  CU_TRY(cudaMemcpy(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  b->arena_bytes = b->f64 ? layout_arena<double>(t, b->stride, nullptr, nullptr, nullptr)
+                          : layout_arena<float>(t, b->stride, nullptr, nullptr, nullptr);
+  CU_TRY(cudaMalloc(&b->arena, b->arena_bytes));
+  CU_TRY(cudaMemset(b->arena, 0, b->arena_bytes));
+  if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; }
+  else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; }
+  CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
+  CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));
+  CU_TRY(cudaMalloc(&b->d_mask, b->stride));
+  if (b->blob_bytes > 48 * 1024) {
+#define SETATTR(K) CU_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, b->blob_bytes));
+    SETATTR(k_step_fused<float>) SETATTR(k_step_fused<double>) SETATTR(k_forward_fused<float>) SETATTR(k_forward_fused<double>)
+    SETATTR(k_reset<float>) SETATTR(k_reset<double>)
+#define SETST(S) SETATTR((k_stage<float, S>)) SETATTR((k_stage<double, S>))
+    SETST(ST_CTRL) SETST(ST_CHECK) SETST(ST_KIN) SETST(ST_CRB) SETST(ST_COLLIDE) SETST(ST_VEL) SETST(ST_EFC) SETST(ST_ACC)
+    SETST(ST_SOLVE) SETST(ST_SENSE) SETST(ST_INTEGRATE)
+#undef SETST
+#undef SETATTR
+  }
+  ox_batch* raw = b.release();
+  ox_status s = ox_batch_reset(raw, nullptr);
+  if (s == OX_OK) s = ox_batch_sync(raw);
+  if (s != OX_OK) { ox_batch_free(raw); return s; }
+  raw->launches = 0;
+  *out = raw;
+  return OX_OK;
+}
+
+void ox_batch_free(ox_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->cfg.device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  drop_graph(b);
+  cudaFree(b->arena); cudaFree(b->d_blob); cudaFree(b->d_step); cudaFree(b->d_tmp); cudaFree(b->d_mask);
+  if (b->h_tmp) cudaFreeHost(b->h_tmp);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int32_t ox_batch_nenv(const ox_batch* b) { return b ? b->nenv : -1; }
+void* ox_batch_stream(const ox_batch* b) { return b ? (void*)b->stream : nullptr; }
+int64_t ox_batch_launch_count(const ox_batch* b) { return b ? b->launches : -1; }
+
+ox_status ox_batch_step(ox_batch* b, int32_t nsteps) {
+  if (!b || nsteps < 0) { ox::set_error("ox_batch_step: bad argument"); return OX_ERR_INVALID; }
+  if (nsteps == 0) return OX_OK;
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  return b->f64 ? do_step<double>(b, nsteps) : do_step<float>(b, nsteps);
+}
+
+ox_status ox_batch_forward(ox_batch* b) {
+  if (!b) { ox::set_error("ox_batch_forward: null batch"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  if (b->f64) k_forward_fused<double><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bd);
+  else k_forward_fused<float><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bf);
+  b->launches++;
+  CU_TRY(cudaGetLastError());
+  return OX_OK;
+}
+
+ox_status ox_batch_reset(ox_batch* b, const uint8_t* host_mask) {
+  if (!b) { ox::set_error("ox_batch_reset: null batch"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const uint8_t* dm = nullptr;
+  if (host_mask) {
+    CU_TRY(cudaMemcpyAsync(b->d_mask, host_mask, b->nenv, cudaMemcpyHostToDevice, b->stream));
+    dm = b->d_mask;
+  }
+  if (b->f64) k_reset<double><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bd, dm);
+  else k_reset<float><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bf, dm);
+  b->launches++;
+  CU_TRY(cudaGetLastError());
+  return OX_OK;
+}
+
+ox_status ox_batch_sync(ox_batch* b) {
+  if (!b) { ox::set_error("ox_batch_sync: null batch"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return OX_OK;
+}
+
+ox_status ox_batch_ctrl_philox(ox_batch* b, int32_t enable, uint64_t seed) {
+  if (!b) { ox::set_error("ox_batch_ctrl_philox: null batch"); return OX_ERR_INVALID; }
+  if ((enable != 0) != (b->philox != 0)) drop_graph(b);
+  b->philox = enable ? 1 : 0;
+  if (b->seed != seed) drop_graph(b);
+  b->seed = seed;
+  return OX_OK;
+}
+
+ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step) {
+  if (!b) { ox::set_error("ox_batch_set_step_counter: null batch"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  long long v = step;
+  CU_TRY(cudaMemcpyAsync(b->d_step, &v, sizeof v, cudaMemcpyHostToDevice, b->stream));
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return OX_OK;
+}
+
+int32_t ox_batch_field_size(const ox_batch* b, int32_t field) {
+  if (!b) return -1;
+  auto it = b->fields.find(field);
+  return it == b->fields.end() ? -1 : it->second.count;
+}
+
+ox_status ox_batch_get(ox_batch* b, int32_t field, void* buf, int32_t dtype, int32_t mem, int32_t layout) {
+  return bulk_io(b, field, buf, dtype, mem, layout, 1);
+}
+ox_status ox_batch_set(ox_batch* b, int32_t field, const void* buf, int32_t dtype, int32_t mem, int32_t layout) {
+  return bulk_io(b, field, const_cast<void*>(buf), dtype, mem, layout, 0);
+}
+ox_status ox_batch_get1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, double* out) {
+  if (!out) { ox::set_error("ox_batch_get1: null output"); return OX_ERR_INVALID; }
+  return slice_io(b, field, env, offset, count, out, nullptr, nullptr);
+}
+ox_status ox_batch_set1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, const double* in) {
+  if (!in) { ox::set_error("ox_batch_set1: null input"); return OX_ERR_INVALID; }
+  return slice_io(b, field, env, offset, count, nullptr, in, nullptr);
+}
+ox_status ox_batch_get1_int(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, int32_t* out) {
+  if (!out) { ox::set_error("ox_batch_get1_int: null output"); return OX_ERR_INVALID; }
+  return slice_io(b, field, env, offset, count, nullptr, nullptr, out);
+}
+
+ox_status ox_batch_stats(ox_batch* b, double* out4) {
+  if (!b || !out4) { ox::set_error("ox_batch_stats: null argument"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  std::vector<int32_t> h((size_t)b->nenv);
+  int32_t* ptrs[4] = {b->f64 ? b->bd.acc_ncon : b->bf.acc_ncon, b->f64 ? b->bd.acc_nefc : b->bf.acc_nefc,
+                      b->f64 ? b->bd.acc_niter : b->bf.acc_niter, b->f64 ? b->bd.diverged : b->bf.diverged};
+  for (int k = 0; k < 4; k++) {
+    CU_TRY(cudaMemcpyAsync(h.data(), ptrs[k], (size_t)b->nenv * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    double s = 0;
+    for (int32_t v : h) s += v;
+    out4[k] = s;
+    if (k < 3) CU_TRY(cudaMemsetAsync(ptrs[k], 0, (size_t)b->stride * 4, b->stream));
+  }
+  return OX_OK;
+}
+
+const char* ox_stage_name(int32_t i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : nullptr; }
+
+ox_status ox_batch_stage_times(ox_batch* b, int32_t reps, double* out_ms, int32_t* nstage) {
+  if (!b || !out_ms || !nstage || reps < 1) { ox::set_error("ox_batch_stage_times: bad argument"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  *nstage = ST_COUNT;
+  return b->f64 ? stage_times_impl<double>(b, reps, out_ms) : stage_times_impl<float>(b, reps, out_ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Device-side view of the compiled model ("constant tables") and of the SoA batch arena.
+//
+// Model blob  : [BlobHeader][int tables][real tables in the batch precision], 16-byte padded, built once
+//               per (model, precision) on the host, uploaded once, and staged into shared memory by every
+//               kernel with one TMA bulk copy (cp.async.bulk, see ox_batch.cu: stage_model()).
+// Batch arena : one allocation; every per-env field is stored [element][env] with env fastest
+//               (stride = nenv rounded up to 32) so that a warp of 32 consecutive envs reads/writes
+//               one 128-byte (fp32) or two (fp64) fully coalesced lines per element.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ox_b200.h"
+
+#if defined(__CUDACC__)
+#define OX_HD __host__ __device__ __forceinline__
+#define OX_HDN __host__ __device__
+#else
+#define OX_HD inline
+#define OX_HDN
+#endif
+
+namespace ox {
+
+struct BlobHeader {
+  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata, nconmax, nefcmax;
+  int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
+  int32_t total_bytes, any_damping;
+  double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
+#define OX_X(name, n, w) int32_t off_##name;
+  OX_MODEL_INT_TABLES(OX_X)
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+  int32_t pad_[2];
+};
+
+template <typename T>
+struct DevModel {
+  const unsigned char* base;
+  OX_HD const BlobHeader& h() const { return *reinterpret_cast<const BlobHeader*>(base); }
+#define OX_X(name, n, w) \
+  OX_HD const int32_t* name() const { return reinterpret_cast<const int32_t*>(base + h().off_##name); }
+  OX_MODEL_INT_TABLES(OX_X)
+#undef OX_X
+#define OX_X(name, n, w) \
+  OX_HD const T* name() const { return reinterpret_cast<const T*>(base + h().off_##name); }
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+};
+
+template <typename T>
+inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int iterations, int ls_iterations, double tolerance) {
+  BlobHeader h;
+  std::memset(&h, 0, sizeof h);
+  h.nq = t.nq; h.nv = t.nv; h.nu = t.nu; h.na = t.na; h.nbody = t.nbody; h.njnt = t.njnt; h.ngeom = t.ngeom; h.nsite = t.nsite;
+  h.nM = t.nM; h.npair = t.npair; h.nsensor = t.nsensor; h.nsensordata = t.nsensordata; h.nconmax = t.nconmax; h.nefcmax = t.nefcmax;
+  h.integrator = t.integrator; h.solver = t.solver; h.cone = t.cone;
+  h.iterations = iterations > 0 ? iterations : t.iterations;
+  h.ls_iterations = ls_iterations > 0 ? ls_iterations : t.ls_iterations;
+  h.disableflags = t.disableflags;
+  h.timestep = t.timestep;
+  for (int k = 0; k < 3; k++) h.gravity[k] = t.gravity[k];
+  h.tolerance = tolerance >= 0 ? tolerance : t.tolerance;
+  h.ls_tolerance = t.ls_tolerance; h.impratio = t.impratio; h.meaninertia = t.meaninertia;
+  h.any_damping = 0;
+  for (int i = 0; i < t.nv; i++) if (t.dof_damping[i] > 0) h.any_damping = 1;
+  size_t off = (sizeof(BlobHeader) + 15) / 16 * 16;
+#define OX_X(name, n, w)                                   \
+  h.off_##name = (int32_t)off;                             \
+  off += ((size_t)t.n * (w) * sizeof(int32_t) + 15) / 16 * 16;
+  OX_MODEL_INT_TABLES(OX_X)
+#undef OX_X
+#define OX_X(name, n, w)                                   \
+  h.off_##name = (int32_t)off;                             \
+  off += ((size_t)t.n * (w) * sizeof(T) + 15) / 16 * 16;
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+  h.total_bytes = (int32_t)off;
+  std::vector<unsigned char> blob(off, 0);
+  std::memcpy(blob.data(), &h, sizeof h);
+#define OX_X(name, n, w) \
+  if (t.n * (w) > 0) std::memcpy(blob.data() + h.off_##name, t.name, (size_t)t.n * (w) * sizeof(int32_t));
+  OX_MODEL_INT_TABLES(OX_X)
+#undef OX_X
+#define OX_X(name, n, w)                                                  \
+  {                                                                       \
+    T* dst = reinterpret_cast<T*>(blob.data() + h.off_##name);            \
+    for (long i = 0; i < (long)t.n * (w); i++) dst[i] = (T)t.name[i];     \
+  }
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+  return blob;
+}
+
+// ---- batch arena fields: X(name, elements-per-env) in terms of nq nv nu nb nj ng ns nM ncm nem nsd ----
+#define OX_BATCH_REAL_FIELDS(X)                                                                        \
+  /* state */                                                                                          \
+  X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(xfrc_applied, 6 * nb) X(qacc_warmstart, nv) \
+  X(time, 1)                                                                                           \
+  /* position stage */                                                                                 \
+  X(xpos, 3 * nb) X(xquat, 4 * nb) X(xmat, 9 * nb) X(xipos, 3 * nb) X(ximat, 9 * nb)                   \
+  X(xanchor, 3 * nj) X(xaxis, 3 * nj) X(geom_xpos, 3 * ng) X(geom_xmat, 9 * ng)                        \
+  X(site_xpos, 3 * ns) X(site_xmat, 9 * ns) X(subtree_com, 3 * nb) X(cinert, 10 * nb) X(cdof, 6 * nv)  \
+  X(crb, 10 * nb) X(qM, nM) X(qLD, nM) X(qLDiagInv, nv)                                                \
+  /* velocity / actuation / acceleration */                                                            \
+  X(cvel, 6 * nb) X(cdof_dot, 6 * nv) X(cacc, 6 * nb) X(cfrc, 6 * nb) X(qfrc_bias, nv)                 \
+  X(qfrc_passive, nv) X(actuator_force, nu) X(qfrc_actuator, nv) X(qfrc_smooth, nv) X(qacc_smooth, nv) \
+  /* contacts and constraints */                                                                       \
+  X(con_dist, ncm) X(con_pos, 3 * ncm) X(con_frame, 9 * ncm)                                           \
+  X(efc_J, nem * nv) X(efc_pos, nem) X(efc_margin, nem) X(efc_D, nem) X(efc_aref, nem) X(efc_force, nem) \
+  /* solver */                                                                                         \
+  X(qacc, nv) X(qfrc_constraint, nv) X(s_Ma, nv) X(s_Jaref, nem) X(s_grad, nv) X(s_Mgrad, nv)          \
+  X(s_search, nv) X(s_Mv, nv) X(s_Jv, nem) X(s_H, nv * nv) X(s_gradold, nv) X(s_Mgradold, nv)          \
+  /* integrator scratch */                                                                             \
+  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(i_qacc, nv)                                    \
+  X(sensordata, nsd) X(subtree_linvel, 3 * nb)
+
+#define OX_BATCH_INT_FIELDS(X) \
+  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1)
+
+template <typename T>
+struct DevBatch {
+  int32_t nenv;
+  int32_t stride;  // env stride of every field (nenv rounded up to a multiple of 32)
+#define OX_X(name, cnt) T* name;
+  OX_BATCH_REAL_FIELDS(OX_X)
+#undef OX_X
+#define OX_X(name, cnt) int32_t* name;
+  OX_BATCH_INT_FIELDS(OX_X)
+#undef OX_X
+};
+
+}  // namespace ox

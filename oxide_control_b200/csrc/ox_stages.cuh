@@ -1,0 +1,1372 @@
+// mj_step stage arithmetic for ONE environment of the SoA batch, templated on the real type.
+// One CUDA thread owns one environment (lane = env, so every batch access below is coalesced
+// across the warp); the model tables are uniform across the warp and come from shared memory.
+// Stage list / formulas: SURVEY.md Appendix A (A.1 .. A.12); reference entry Physics::step ->
+// mj_step, src/physics.rs:44-46.
+//
+// The functions are __host__ __device__ only so that tests/native can run the very same code on the
+// CPU against the oracle while no GPU is attached. libox_b200.so never instantiates them on the host.
+#pragma once
+#include <cmath>
+
+#include "ox_blob.h"
+
+namespace ox {
+
+// ---------------------------------------------------------------- scalar helpers
+OX_HD float ox_sqrt(float x) { return sqrtf(x); }
+OX_HD double ox_sqrt(double x) { return sqrt(x); }
+OX_HD float ox_abs(float x) { return fabsf(x); }
+OX_HD double ox_abs(double x) { return fabs(x); }
+OX_HD float ox_pow(float x, float y) { return powf(x, y); }
+OX_HD double ox_pow(double x, double y) { return pow(x, y); }
+OX_HD float ox_atan2(float y, float x) { return atan2f(y, x); }
+OX_HD double ox_atan2(double y, double x) { return atan2(y, x); }
+OX_HD void ox_sincos(float a, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(a, s, c);
+#else
+  *s = sinf(a); *c = cosf(a);
+#endif
+}
+OX_HD void ox_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(a, s, c);
+#else
+  *s = sin(a); *c = cos(a);
+#endif
+}
+template <typename T> OX_HD T ox_max(T a, T b) { return a > b ? a : b; }
+template <typename T> OX_HD T ox_min(T a, T b) { return a < b ? a : b; }
+template <typename T> OX_HD T ox_clip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+template <typename T> OX_HD bool ox_bad(T x) { return !(x <= (T)OX_MAXVAL && x >= (T)-OX_MAXVAL); }  // NaN or too large
+template <typename T> struct Eps;
+template <> struct Eps<float> { static OX_HD float v() { return 4 * 1.1920929e-07f; } };
+template <> struct Eps<double> { static OX_HD double v() { return 4 * 2.220446049250313e-16; } };
+
+// ---------------------------------------------------------------- 3-vectors / quaternions in registers
+template <typename T> OX_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> OX_HD void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> OX_HD T normalize3(T* v) {
+  T n = ox_sqrt(dot3(v, v));
+  if (n < (T)OX_MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; }
+  else { T s = (T)1 / n; v[0] *= s; v[1] *= s; v[2] *= s; }
+  return n;
+}
+template <typename T> OX_HD void normalize4(T* q) {
+  T n = ox_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < (T)OX_MINVAL) { q[0] = 1; q[1] = 0; q[2] = 0; q[3] = 0; }
+  else { T s = (T)1 / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+}
+template <typename T> OX_HD void mul_quat(T* r, const T* a, const T* b) {
+  T w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+template <typename T> OX_HD void quat2mat(T* m, const T* q) {
+  T q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  T q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
+  m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+template <typename T> OX_HD void mat_vec3(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+    z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> OX_HD void rot_vec_quat(T* r, const T* v, const T* q) {
+  T m[9];
+  quat2mat(m, q);
+  mat_vec3(r, m, v);
+}
+template <typename T> OX_HD void axis_angle2quat(T* q, const T* axis, T angle) {
+  if (angle == 0) { q[0] = 1; q[1] = 0; q[2] = 0; q[3] = 0; return; }
+  T s, c;
+  ox_sincos(angle * (T)0.5, &s, &c);
+  q[0] = c; q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+template <typename T> OX_HD void sub_quat(T* res, const T* qa, const T* qb) {
+  T qneg[4] = {qb[0], -qb[1], -qb[2], -qb[3]}, qdif[4];
+  mul_quat(qdif, qneg, qa);
+  T axis[3] = {qdif[1], qdif[2], qdif[3]};
+  T s = normalize3(axis);
+  T speed = 2 * ox_atan2(s, qdif[0]);
+  if (speed > (T)3.14159265358979323846) speed -= (T)(2 * 3.14159265358979323846);
+  res[0] = axis[0] * speed; res[1] = axis[1] * speed; res[2] = axis[2] * speed;
+}
+template <typename T> OX_HD void quat_integrate(T* quat, const T* vel, T scale) {
+  T tmp[3] = {vel[0], vel[1], vel[2]}, qrot[4], out[4];
+  T angle = scale * normalize3(tmp);
+  axis_angle2quat(qrot, tmp, angle);
+  normalize4(quat);
+  mul_quat(out, quat, qrot);
+  quat[0] = out[0]; quat[1] = out[1]; quat[2] = out[2]; quat[3] = out[3];
+}
+template <typename T> OX_HD void mat2quat(T* q, const T* m) {
+  T tr = m[0] + m[4] + m[8];
+  if (tr > 0) {
+    T s = ox_sqrt(tr + (T)1) * 2;
+    q[0] = (T)0.25 * s; q[1] = (m[7] - m[5]) / s; q[2] = (m[2] - m[6]) / s; q[3] = (m[3] - m[1]) / s;
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    T s = ox_sqrt((T)1 + m[0] - m[4] - m[8]) * 2;
+    q[0] = (m[7] - m[5]) / s; q[1] = (T)0.25 * s; q[2] = (m[1] + m[3]) / s; q[3] = (m[2] + m[6]) / s;
+  } else if (m[4] > m[8]) {
+    T s = ox_sqrt((T)1 + m[4] - m[0] - m[8]) * 2;
+    q[0] = (m[2] - m[6]) / s; q[1] = (m[1] + m[3]) / s; q[2] = (T)0.25 * s; q[3] = (m[5] + m[7]) / s;
+  } else {
+    T s = ox_sqrt((T)1 + m[8] - m[0] - m[4]) * 2;
+    q[0] = (m[3] - m[1]) / s; q[1] = (m[2] + m[6]) / s; q[2] = (m[5] + m[7]) / s; q[3] = (T)0.25 * s;
+  }
+  normalize4(q);
+}
+// spatial vectors [angular; linear]
+template <typename T> OX_HD void cross_motion(T* r, const T* vel, const T* v) {
+  r[0] = -vel[2] * v[1] + vel[1] * v[2];
+  r[1] = vel[2] * v[0] - vel[0] * v[2];
+  r[2] = -vel[1] * v[0] + vel[0] * v[1];
+  r[3] = -vel[2] * v[4] + vel[1] * v[5] - vel[5] * v[1] + vel[4] * v[2];
+  r[4] = vel[2] * v[3] - vel[0] * v[5] + vel[5] * v[0] - vel[3] * v[2];
+  r[5] = -vel[1] * v[3] + vel[0] * v[4] - vel[4] * v[0] + vel[3] * v[1];
+}
+template <typename T> OX_HD void cross_force(T* r, const T* vel, const T* f) {
+  r[0] = -vel[2] * f[1] + vel[1] * f[2] - vel[5] * f[4] + vel[4] * f[5];
+  r[1] = vel[2] * f[0] - vel[0] * f[2] + vel[5] * f[3] - vel[3] * f[5];
+  r[2] = -vel[1] * f[0] + vel[0] * f[1] - vel[4] * f[3] + vel[3] * f[4];
+  r[3] = -vel[2] * f[4] + vel[1] * f[5];
+  r[4] = vel[2] * f[3] - vel[0] * f[5];
+  r[5] = -vel[1] * f[3] + vel[0] * f[4];
+}
+template <typename T> OX_HD void mul_inert_vec(T* r, const T* i, const T* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+template <typename T> OX_HD T dot6(const T* a, const T* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// Philox4x32-10 (control stream). KATs in tests/test_philox.py.
+OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ---------------------------------------------------------------- one environment
+template <typename T>
+struct Env {
+  DevModel<T> m;
+  DevBatch<T> b;
+  int e;
+  size_t S;
+
+  OX_HD Env(const DevModel<T>& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(e_), S((size_t)b_.stride) {}
+
+  // element i of a field for this env
+  OX_HD T& at(T* f, int i) const { return f[(size_t)i * S + e]; }
+  OX_HD int32_t& ati(int32_t* f, int i) const { return f[(size_t)i * S + e]; }
+  template <int N> OX_HD void ld(T* dst, const T* f, int first) const {
+#pragma unroll
+    for (int k = 0; k < N; k++) dst[k] = f[(size_t)(first + k) * S + e];
+  }
+  template <int N> OX_HD void st(T* f, int first, const T* src) const {
+#pragma unroll
+    for (int k = 0; k < N; k++) f[(size_t)(first + k) * S + e] = src[k];
+  }
+  template <int N> OX_HD void ldm(T* dst, const T* table, int first) const {  // model table (uniform)
+#pragma unroll
+    for (int k = 0; k < N; k++) dst[k] = table[first + k];
+  }
+  OX_HD bool dis(int bit) const { return (m.h().disableflags & bit) != 0; }
+
+  // ============================================================ A.1 kinematics (+ geoms, sites)
+  OX_HDN void kinematics() const {
+    const BlobHeader& h = m.h();
+    const int nbody = h.nbody, ngeom = h.ngeom, nsite = h.nsite;
+    const int32_t *jnt_type = m.jnt_type(), *jnt_qposadr = m.jnt_qposadr(), *geom_bodyid = m.geom_bodyid(), *site_bodyid = m.site_bodyid();
+    int g = 0, s = 0;
+    for (int i = 0; i < nbody; i++) {
+      T pos[3], quat[4], mat[9];
+      if (i == 0) {
+        pos[0] = pos[1] = pos[2] = 0;
+        quat[0] = 1; quat[1] = quat[2] = quat[3] = 0;
+      } else {
+        const int jntadr = m.body_jntadr()[i], jntnum = m.body_jntnum()[i];
+        if (jntnum == 1 && jnt_type[jntadr] == OX_JNT_FREE) {
+          const int qadr = jnt_qposadr[jntadr];
+          ld<3>(pos, b.qpos, qadr);
+          ld<4>(quat, b.qpos, qadr + 3);
+          normalize4(quat);
+          st<3>(b.xanchor, 3 * jntadr, pos);
+          T ax[3];
+          ldm<3>(ax, m.jnt_axis(), 3 * jntadr);
+          st<3>(b.xaxis, 3 * jntadr, ax);
+        } else {
+          const int pid = m.body_parentid()[i];
+          T ppos[3], pquat[4], pmat[9], bp[3], bq[4];
+          ld<3>(ppos, b.xpos, 3 * pid);
+          ld<4>(pquat, b.xquat, 4 * pid);
+          ld<9>(pmat, b.xmat, 9 * pid);
+          ldm<3>(bp, m.body_pos(), 3 * i);
+          ldm<4>(bq, m.body_quat(), 4 * i);
+          mat_vec3(pos, pmat, bp);
+          pos[0] += ppos[0]; pos[1] += ppos[1]; pos[2] += ppos[2];
+          mul_quat(quat, pquat, bq);
+          for (int j = 0; j < jntnum; j++) {
+            const int jid = jntadr + j, qadr = jnt_qposadr[jid], jt = jnt_type[jid];
+            T jaxis[3], jpos[3], anchor[3], axis[3];
+            ldm<3>(jaxis, m.jnt_axis(), 3 * jid);
+            ldm<3>(jpos, m.jnt_pos(), 3 * jid);
+            rot_vec_quat(axis, jaxis, quat);
+            rot_vec_quat(anchor, jpos, quat);
+            anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+            if (jt == OX_JNT_SLIDE) {
+              T dq = at(b.qpos, qadr) - m.qpos0()[qadr];
+              pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+            } else if (jt == OX_JNT_BALL || jt == OX_JNT_HINGE) {
+              T qloc[4], qn[4], vec[3];
+              if (jt == OX_JNT_BALL) {
+                ld<4>(qloc, b.qpos, qadr);
+                normalize4(qloc);
+              } else {
+                axis_angle2quat(qloc, jaxis, at(b.qpos, qadr) - m.qpos0()[qadr]);
+              }
+              mul_quat(qn, quat, qloc);
+              quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+              rot_vec_quat(vec, jpos, quat);
+              pos[0] = anchor[0] - vec[0]; pos[1] = anchor[1] - vec[1]; pos[2] = anchor[2] - vec[2];
+            }
+            st<3>(b.xanchor, 3 * jid, anchor);
+            st<3>(b.xaxis, 3 * jid, axis);
+          }
+        }
+        normalize4(quat);
+      }
+      quat2mat(mat, quat);
+      st<3>(b.xpos, 3 * i, pos);
+      st<4>(b.xquat, 4 * i, quat);
+      st<9>(b.xmat, 9 * i, mat);
+      {  // inertial frame
+        T ip[3], iq[4], v[3], q[4], im[9];
+        ldm<3>(ip, m.body_ipos(), 3 * i);
+        ldm<4>(iq, m.body_iquat(), 4 * i);
+        mat_vec3(v, mat, ip);
+        v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
+        mul_quat(q, quat, iq);
+        quat2mat(im, q);
+        st<3>(b.xipos, 3 * i, v);
+        st<9>(b.ximat, 9 * i, im);
+      }
+      for (; g < ngeom && geom_bodyid[g] == i; g++) {  // geoms are sorted by body
+        T gp[3], gq[4], v[3], q[4], gm[9];
+        ldm<3>(gp, m.geom_pos(), 3 * g);
+        ldm<4>(gq, m.geom_quat(), 4 * g);
+        mat_vec3(v, mat, gp);
+        v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
+        mul_quat(q, quat, gq);
+        quat2mat(gm, q);
+        st<3>(b.geom_xpos, 3 * g, v);
+        st<9>(b.geom_xmat, 9 * g, gm);
+      }
+      for (; s < nsite && site_bodyid[s] == i; s++) {
+        T sp[3], sq[4], v[3], q[4], sm[9];
+        ldm<3>(sp, m.site_pos(), 3 * s);
+        ldm<4>(sq, m.site_quat(), 4 * s);
+        mat_vec3(v, mat, sp);
+        v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
+        mul_quat(q, quat, sq);
+        quat2mat(sm, q);
+        st<3>(b.site_xpos, 3 * s, v);
+        st<9>(b.site_xmat, 9 * s, sm);
+      }
+    }
+  }
+
+  // ============================================================ A.2 subtree com, cinert, cdof
+  OX_HDN void com_pos() const {
+    const BlobHeader& h = m.h();
+    const int nbody = h.nbody, njnt = h.njnt;
+    const int32_t *parent = m.body_parentid(), *rootid = m.body_rootid();
+    const T *mass = m.body_mass(), *stm = m.body_subtreemass();
+    for (int i = 0; i < 3 * nbody; i++) at(b.subtree_com, i) = 0;
+    for (int i = nbody - 1; i >= 0; i--) {
+      T acc[3], xi[3];
+      ld<3>(acc, b.subtree_com, 3 * i);
+      ld<3>(xi, b.xipos, 3 * i);
+      const T mi = mass[i];
+      acc[0] += xi[0] * mi; acc[1] += xi[1] * mi; acc[2] += xi[2] * mi;
+      if (i) {
+        const int j = parent[i];
+        T pa[3];
+        ld<3>(pa, b.subtree_com, 3 * j);
+        pa[0] += acc[0]; pa[1] += acc[1]; pa[2] += acc[2];
+        st<3>(b.subtree_com, 3 * j, pa);
+      }
+      if (stm[i] < (T)OX_MINVAL) { acc[0] = xi[0]; acc[1] = xi[1]; acc[2] = xi[2]; }
+      else { const T sm = stm[i]; acc[0] /= sm; acc[1] /= sm; acc[2] /= sm; }
+      st<3>(b.subtree_com, 3 * i, acc);
+    }
+    for (int k = 0; k < 10; k++) at(b.cinert, k) = 0;
+    for (int i = 1; i < nbody; i++) {
+      T mat[9], xi[3], sc[3], inert[3], dif[3], res[10], tmp[9];
+      ld<9>(mat, b.ximat, 9 * i);
+      ld<3>(xi, b.xipos, 3 * i);
+      ld<3>(sc, b.subtree_com, 3 * rootid[i]);
+      ldm<3>(inert, m.body_inertia(), 3 * i);
+      const T ms = mass[i];
+      dif[0] = xi[0] - sc[0]; dif[1] = xi[1] - sc[1]; dif[2] = xi[2] - sc[2];
+      tmp[0] = mat[0] * inert[0]; tmp[3] = mat[1] * inert[1]; tmp[6] = mat[2] * inert[2];
+      tmp[1] = mat[3] * inert[0]; tmp[4] = mat[4] * inert[1]; tmp[7] = mat[5] * inert[2];
+      tmp[2] = mat[6] * inert[0]; tmp[5] = mat[7] * inert[1]; tmp[8] = mat[8] * inert[2];
+      res[0] = mat[0] * tmp[0] + mat[1] * tmp[3] + mat[2] * tmp[6];
+      res[1] = mat[3] * tmp[1] + mat[4] * tmp[4] + mat[5] * tmp[7];
+      res[2] = mat[6] * tmp[2] + mat[7] * tmp[5] + mat[8] * tmp[8];
+      res[3] = mat[0] * tmp[1] + mat[1] * tmp[4] + mat[2] * tmp[7];
+      res[4] = mat[0] * tmp[2] + mat[1] * tmp[5] + mat[2] * tmp[8];
+      res[5] = mat[3] * tmp[2] + mat[4] * tmp[5] + mat[5] * tmp[8];
+      res[0] += ms * (dif[1] * dif[1] + dif[2] * dif[2]);
+      res[1] += ms * (dif[0] * dif[0] + dif[2] * dif[2]);
+      res[2] += ms * (dif[0] * dif[0] + dif[1] * dif[1]);
+      res[3] -= ms * dif[0] * dif[1];
+      res[4] -= ms * dif[0] * dif[2];
+      res[5] -= ms * dif[1] * dif[2];
+      res[6] = ms * dif[0]; res[7] = ms * dif[1]; res[8] = ms * dif[2];
+      res[9] = ms;
+      st<10>(b.cinert, 10 * i, res);
+    }
+    const int32_t *jnt_type = m.jnt_type(), *jnt_bodyid = m.jnt_bodyid(), *jnt_dofadr = m.jnt_dofadr();
+    for (int j = 0; j < njnt; j++) {
+      const int bi = jnt_bodyid[j], da = jnt_dofadr[j], jt = jnt_type[j];
+      T sc[3], anchor[3], offset[3];
+      ld<3>(sc, b.subtree_com, 3 * rootid[bi]);
+      ld<3>(anchor, b.xanchor, 3 * j);
+      offset[0] = sc[0] - anchor[0]; offset[1] = sc[1] - anchor[1]; offset[2] = sc[2] - anchor[2];
+      if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+        int skip = 0;
+        if (jt == OX_JNT_FREE) {
+          for (int i = 0; i < 3; i++) {
+            T cd[6] = {0, 0, 0, 0, 0, 0};
+            cd[3 + i] = 1;
+            st<6>(b.cdof, 6 * (da + i), cd);
+          }
+          skip = 3;
+        }
+        T xm[9];
+        ld<9>(xm, b.xmat, 9 * bi);
+        for (int i = 0; i < 3; i++) {
+          T cd[6];
+          cd[0] = xm[i]; cd[1] = xm[i + 3]; cd[2] = xm[i + 6];
+          cross3(cd + 3, cd, offset);
+          st<6>(b.cdof, 6 * (da + i + skip), cd);
+        }
+      } else {
+        T ax[3], cd[6];
+        ld<3>(ax, b.xaxis, 3 * j);
+        if (jt == OX_JNT_SLIDE) {
+          cd[0] = cd[1] = cd[2] = 0;
+          cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2];
+        } else {
+          cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+          cross3(cd + 3, ax, offset);
+        }
+        st<6>(b.cdof, 6 * da, cd);
+      }
+    }
+  }
+
+  // ============================================================ A.3 composite rigid body -> qM
+  OX_HDN void crb() const {
+    const BlobHeader& h = m.h();
+    const int nbody = h.nbody, nv = h.nv;
+    const int32_t *parent = m.body_parentid(), *dof_parent = m.dof_parentid(), *dof_body = m.dof_bodyid(), *Madr = m.dof_Madr();
+    for (int i = 0; i < 10 * nbody; i++) at(b.crb, i) = at(b.cinert, i);
+    for (int i = nbody - 1; i > 0; i--) {
+      const int p = parent[i];
+      if (p > 0) {
+        T a[10], c[10];
+        ld<10>(a, b.crb, 10 * p);
+        ld<10>(c, b.crb, 10 * i);
+#pragma unroll
+        for (int k = 0; k < 10; k++) a[k] += c[k];
+        st<10>(b.crb, 10 * p, a);
+      }
+    }
+    for (int i = 0; i < nv; i++) {
+      T in[10], cd[6], buf[6];
+      ld<10>(in, b.crb, 10 * dof_body[i]);
+      ld<6>(cd, b.cdof, 6 * i);
+      mul_inert_vec(buf, in, cd);
+      int adr = Madr[i];
+      at(b.qM, adr++) = m.dof_armature()[i] + dot6(cd, buf);
+      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) {
+        T cj[6];
+        ld<6>(cj, b.cdof, 6 * j);
+        at(b.qM, adr++) = dot6(cj, buf);
+      }
+    }
+  }
+
+  // ============================================================ A.4 sparse L'DL factor / solve / M*v
+  OX_HDN void factor_ld(T* qLD, T* qLDiagInv) const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nM = h.nM;
+    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    for (int k = nv - 1; k >= 0; k--) {
+      const int Madr_kk = Madr[k];
+      int Madr_ki = Madr_kk + 1, i = dof_parent[k];
+      const T dkk = at(qLD, Madr_kk);
+      while (i >= 0) {
+        const T tmp = at(qLD, Madr_ki) / dkk;
+        const int rowi = Madr[i], n = (i + 1 < nv ? Madr[i + 1] : nM) - rowi;
+        for (int c = 0; c < n; c++) at(qLD, rowi + c) -= tmp * at(qLD, Madr_ki + c);
+        at(qLD, Madr_ki) = tmp;
+        i = dof_parent[i];
+        Madr_ki++;
+      }
+      at(qLDiagInv, k) = (T)1 / dkk;
+    }
+  }
+  OX_HDN void factor_m() const {
+    const int nM = m.h().nM;
+    for (int i = 0; i < nM; i++) at(b.qLD, i) = at(b.qM, i);
+    factor_ld(b.qLD, b.qLDiagInv);
+  }
+  OX_HDN void solve_ld(T* x) const {
+    const int nv = m.h().nv;
+    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    for (int i = nv - 1; i >= 0; i--) {
+      int adr = Madr[i] + 1;
+      const T xi = at(x, i);
+      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) at(x, j) -= at(b.qLD, adr++) * xi;
+    }
+    for (int i = 0; i < nv; i++) at(x, i) *= at(b.qLDiagInv, i);
+    for (int i = 0; i < nv; i++) {
+      int adr = Madr[i] + 1;
+      T xi = at(x, i);
+      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) xi -= at(b.qLD, adr++) * at(x, j);
+      at(x, i) = xi;
+    }
+  }
+  OX_HDN void mul_m(T* res, const T* v) const {
+    const int nv = m.h().nv;
+    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    for (int i = 0; i < nv; i++) at(res, i) = 0;
+    for (int i = 0; i < nv; i++) {
+      int adr = Madr[i];
+      const T vi = v[(size_t)i * S + e];
+      T ri = at(res, i) + at(b.qM, adr++) * vi;
+      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) {
+        const T mij = at(b.qM, adr++);
+        ri += mij * v[(size_t)j * S + e];
+        at(res, j) += mij * vi;
+      }
+      at(res, i) = ri;
+    }
+  }
+
+  // ============================================================ A.7 com velocities
+  OX_HDN void com_vel() const {
+    const BlobHeader& h = m.h();
+    const int nbody = h.nbody;
+    const int32_t *parent = m.body_parentid(), *dofadr = m.body_dofadr(), *dofnum = m.body_dofnum(), *dof_jnt = m.dof_jntid(),
+                  *jnt_type = m.jnt_type();
+    for (int k = 0; k < 6; k++) at(b.cvel, k) = 0;
+    for (int i = 1; i < nbody; i++) {
+      const int bda = dofadr[i], nd = dofnum[i];
+      T cvel[6];
+      ld<6>(cvel, b.cvel, 6 * parent[i]);
+      for (int j = 0; j < nd; j++) {
+        const int jt = jnt_type[dof_jnt[bda + j]];
+        if (jt == OX_JNT_FREE) {
+          for (int k = 0; k < 3; k++) {
+            T z[6] = {0, 0, 0, 0, 0, 0}, cd[6];
+            st<6>(b.cdof_dot, 6 * (bda + k), z);
+            ld<6>(cd, b.cdof, 6 * (bda + k));
+            const T qv = at(b.qvel, bda + k);
+#pragma unroll
+            for (int c = 0; c < 6; c++) cvel[c] += cd[c] * qv;
+          }
+          j += 3;
+        }
+        if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+          T cd[3][6];
+          for (int k = 0; k < 3; k++) {
+            T cdd[6];
+            ld<6>(cd[k], b.cdof, 6 * (bda + j + k));
+            cross_motion(cdd, cvel, cd[k]);
+            st<6>(b.cdof_dot, 6 * (bda + j + k), cdd);
+          }
+          for (int k = 0; k < 3; k++) {
+            const T qv = at(b.qvel, bda + j + k);
+#pragma unroll
+            for (int c = 0; c < 6; c++) cvel[c] += cd[k][c] * qv;
+          }
+          j += 2;
+        } else {
+          T cd[6], cdd[6];
+          ld<6>(cd, b.cdof, 6 * (bda + j));
+          cross_motion(cdd, cvel, cd);
+          st<6>(b.cdof_dot, 6 * (bda + j), cdd);
+          const T qv = at(b.qvel, bda + j);
+#pragma unroll
+          for (int c = 0; c < 6; c++) cvel[c] += cd[c] * qv;
+        }
+      }
+      st<6>(b.cvel, 6 * i, cvel);
+    }
+  }
+
+  // ============================================================ passive forces
+  OX_HDN void passive() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, njnt = h.njnt;
+    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) = 0;
+    if (dis(OX_DSBL_PASSIVE)) return;
+    const int32_t *jnt_type = m.jnt_type(), *qposadr = m.jnt_qposadr(), *jdofadr = m.jnt_dofadr();
+    for (int j = 0; j < njnt; j++) {
+      const T k = m.jnt_stiffness()[j];
+      if (k == 0) continue;
+      int pa = qposadr[j], da = jdofadr[j];
+      const int jt = jnt_type[j];
+      if (jt == OX_JNT_FREE) {
+        for (int c = 0; c < 3; c++) at(b.qfrc_passive, da + c) -= k * (at(b.qpos, pa + c) - m.qpos_spring()[pa + c]);
+        pa += 3; da += 3;
+      }
+      if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+        T q[4], qs[4], dif[3];
+        ld<4>(q, b.qpos, pa);
+        normalize4(q);
+        ldm<4>(qs, m.qpos_spring(), pa);
+        sub_quat(dif, q, qs);
+        for (int c = 0; c < 3; c++) at(b.qfrc_passive, da + c) -= k * dif[c];
+      } else {
+        at(b.qfrc_passive, da) -= k * (at(b.qpos, pa) - m.qpos_spring()[pa]);
+      }
+    }
+    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping()[i] * at(b.qvel, i);
+  }
+
+  // ============================================================ A.8 bias forces (RNE, no acceleration)
+  OX_HDN void rne() const {
+    const BlobHeader& h = m.h();
+    const int nbody = h.nbody, nv = h.nv;
+    const int32_t *parent = m.body_parentid(), *dofadr = m.body_dofadr(), *dofnum = m.body_dofnum(), *dof_body = m.dof_bodyid();
+    {
+      T a0[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0};
+      if (!dis(OX_DSBL_GRAVITY)) { a0[3] = -(T)h.gravity[0]; a0[4] = -(T)h.gravity[1]; a0[5] = -(T)h.gravity[2]; }
+      st<6>(b.cacc, 0, a0);
+      st<6>(b.cfrc, 0, z);
+    }
+    for (int i = 1; i < nbody; i++) {
+      const int bda = dofadr[i], nd = dofnum[i];
+      T cacc[6], in[10], cv[6], f[6], tmp[6], tmp1[6];
+      ld<6>(cacc, b.cacc, 6 * parent[i]);
+      for (int j = 0; j < nd; j++) {
+        T cdd[6];
+        ld<6>(cdd, b.cdof_dot, 6 * (bda + j));
+        const T qv = at(b.qvel, bda + j);
+#pragma unroll
+        for (int c = 0; c < 6; c++) cacc[c] += cdd[c] * qv;
+      }
+      st<6>(b.cacc, 6 * i, cacc);
+      ld<10>(in, b.cinert, 10 * i);
+      ld<6>(cv, b.cvel, 6 * i);
+      mul_inert_vec(f, in, cacc);
+      mul_inert_vec(tmp, in, cv);
+      cross_force(tmp1, cv, tmp);
+#pragma unroll
+      for (int c = 0; c < 6; c++) f[c] += tmp1[c];
+      st<6>(b.cfrc, 6 * i, f);
+    }
+    for (int i = nbody - 1; i > 0; i--) {
+      const int p = parent[i];
+      if (p) {
+        T a[6], c[6];
+        ld<6>(a, b.cfrc, 6 * p);
+        ld<6>(c, b.cfrc, 6 * i);
+#pragma unroll
+        for (int k = 0; k < 6; k++) a[k] += c[k];
+        st<6>(b.cfrc, 6 * p, a);
+      }
+    }
+    for (int i = 0; i < nv; i++) {
+      T cd[6], f[6];
+      ld<6>(cd, b.cdof, 6 * i);
+      ld<6>(f, b.cfrc, 6 * dof_body[i]);
+      at(b.qfrc_bias, i) = dot6(cd, f);
+    }
+  }
+
+  // ============================================================ A.9 actuation (joint transmission)
+  OX_HDN void actuation() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nu = h.nu;
+    for (int i = 0; i < nv; i++) at(b.qfrc_actuator, i) = 0;
+    const bool off = dis(OX_DSBL_ACTUATION);
+    const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
+    for (int i = 0; i < nu; i++) {
+      if (off) { at(b.actuator_force, i) = 0; continue; }
+      const int j = m.actuator_trnid()[i], qa = m.jnt_qposadr()[j], da = m.jnt_dofadr()[j];
+      const T gear = m.actuator_gear()[i];
+      const T length = gear * at(b.qpos, qa), velocity = gear * at(b.qvel, da);
+      T ctrl = at(b.ctrl, i);
+      if (m.actuator_ctrllimited()[i] && clamp) ctrl = ox_clip(ctrl, m.actuator_ctrlrange()[2 * i], m.actuator_ctrlrange()[2 * i + 1]);
+      const T* gp = m.actuator_gainprm() + 3 * i;
+      const T* bp = m.actuator_biasprm() + 3 * i;
+      T gain = gp[0];
+      if (m.actuator_gaintype()[i] == OX_GAIN_AFFINE) gain += gp[1] * length + gp[2] * velocity;
+      T bias = 0;
+      if (m.actuator_biastype()[i] == OX_BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
+      T force = gain * ctrl + bias;
+      if (m.actuator_forcelimited()[i]) force = ox_clip(force, m.actuator_forcerange()[2 * i], m.actuator_forcerange()[2 * i + 1]);
+      at(b.actuator_force, i) = force;
+      at(b.qfrc_actuator, da) += gear * force;
+    }
+  }
+
+  // ============================================================ A.10 smooth acceleration
+  OX_HDN void fwd_acceleration() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nbody = h.nbody;
+    for (int i = 0; i < nv; i++)
+      at(b.qfrc_smooth, i) = at(b.qfrc_passive, i) - at(b.qfrc_bias, i) + at(b.qfrc_applied, i) + at(b.qfrc_actuator, i);
+    const int32_t *dof_parent = m.dof_parentid(), *rootid = m.body_rootid();
+    for (int bd = 1; bd < nbody; bd++) {
+      T f[6];
+      ld<6>(f, b.xfrc_applied, 6 * bd);
+      if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
+      T xi[3], sc[3], offset[3];
+      ld<3>(xi, b.xipos, 3 * bd);
+      ld<3>(sc, b.subtree_com, 3 * rootid[bd]);
+      offset[0] = xi[0] - sc[0]; offset[1] = xi[1] - sc[1]; offset[2] = xi[2] - sc[2];
+      int body = bd;
+      while (body && m.body_dofnum()[body] == 0) body = m.body_parentid()[body];
+      if (!body) continue;
+      for (int i = m.body_dofadr()[body] + m.body_dofnum()[body] - 1; i >= 0; i = dof_parent[i]) {
+        T cd[6], jp[3];
+        ld<6>(cd, b.cdof, 6 * i);
+        cross3(jp, cd, offset);
+        jp[0] += cd[3]; jp[1] += cd[4]; jp[2] += cd[5];
+        at(b.qfrc_smooth, i) += dot3(jp, f) + dot3(cd, f + 3);
+      }
+    }
+    for (int i = 0; i < nv; i++) at(b.qacc_smooth, i) = at(b.qfrc_smooth, i);
+    solve_ld(b.qacc_smooth);
+  }
+
+  // ============================================================ A.5 collision (precompiled pair list)
+  struct Con { T dist, pos[3], frame[9]; };
+
+  static OX_HD int plane_sphere(Con& c, T margin, const T* pos1, const T* n, const T* pos2, T radius) {
+    T tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+    T cdist = dot3(tmp, n);
+    if (cdist > margin + radius) return 0;
+    c.dist = cdist - radius;
+    c.frame[0] = n[0]; c.frame[1] = n[1]; c.frame[2] = n[2];
+    c.frame[3] = 0; c.frame[4] = 0; c.frame[5] = 0;
+    const T s = -c.dist / 2 - radius;
+    c.pos[0] = pos2[0] + n[0] * s; c.pos[1] = pos2[1] + n[1] * s; c.pos[2] = pos2[2] + n[2] * s;
+    return 1;
+  }
+  static OX_HD int sphere_sphere(Con& c, T margin, const T* pos1, T r1, const T* pos2, T r2) {
+    T dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+    T cd2 = dot3(dif, dif), mind = margin + r1 + r2;
+    if (cd2 > mind * mind) return 0;
+    c.dist = ox_sqrt(cd2) - r1 - r2;
+    c.frame[0] = dif[0]; c.frame[1] = dif[1]; c.frame[2] = dif[2];
+    normalize3(c.frame);
+    c.frame[3] = 0; c.frame[4] = 0; c.frame[5] = 0;
+    const T s = r1 + c.dist / 2;
+    c.pos[0] = pos1[0] + c.frame[0] * s; c.pos[1] = pos1[1] + c.frame[1] * s; c.pos[2] = pos1[2] + c.frame[2] * s;
+    return 1;
+  }
+  static OX_HD void make_frame(T* frame) {
+    normalize3(frame);
+    if (ox_sqrt(dot3(frame + 3, frame + 3)) < (T)0.5) {
+      frame[3] = 0; frame[4] = 0; frame[5] = 0;
+      if (frame[1] < (T)0.5 && frame[1] > (T)-0.5) frame[4] = 1; else frame[5] = 1;
+    }
+    const T t = dot3(frame, frame + 3);
+    frame[3] -= t * frame[0]; frame[4] -= t * frame[1]; frame[5] -= t * frame[2];
+    normalize3(frame + 3);
+    cross3(frame + 6, frame, frame + 3);
+  }
+  OX_HD void emit(Con& c, int p, int& ncon) const {
+    make_frame(c.frame);
+    at(b.con_dist, ncon) = c.dist;
+    st<3>(b.con_pos, 3 * ncon, c.pos);
+    st<9>(b.con_frame, 9 * ncon, c.frame);
+    ati(b.con_pair, ncon) = p;
+    ncon++;
+  }
+
+  OX_HDN void collision() const {
+    const BlobHeader& h = m.h();
+    int ncon = 0;
+    if (!(dis(OX_DSBL_CONTACT) || dis(OX_DSBL_CONSTRAINT))) {
+      const int npair = h.npair;
+      const int32_t *pg1 = m.pair_geom1(), *pg2 = m.pair_geom2(), *gtype = m.geom_type();
+      for (int p = 0; p < npair; p++) {
+        const int g1 = pg1[p], g2 = pg2[p], t1 = gtype[g1], t2 = gtype[g2];
+        const T margin = m.pair_margin()[p];
+        const T* size1 = m.geom_size() + 3 * g1;
+        const T* size2 = m.geom_size() + 3 * g2;
+        T pos1[3], pos2[3];
+        ld<3>(pos1, b.geom_xpos, 3 * g1);
+        ld<3>(pos2, b.geom_xpos, 3 * g2);
+        if (t1 == OX_GEOM_PLANE) {
+          T n[3] = {at(b.geom_xmat, 9 * g1 + 2), at(b.geom_xmat, 9 * g1 + 5), at(b.geom_xmat, 9 * g1 + 8)};
+          if (t2 == OX_GEOM_SPHERE) {
+            Con c;
+            if (plane_sphere(c, margin, pos1, n, pos2, size2[0])) emit(c, p, ncon);
+          } else if (t2 == OX_GEOM_CAPSULE) {
+            T axis[3] = {at(b.geom_xmat, 9 * g2 + 2), at(b.geom_xmat, 9 * g2 + 5), at(b.geom_xmat, 9 * g2 + 8)};
+            const T hl = size2[1];
+            for (int sgn = 1; sgn >= -1; sgn -= 2) {
+              T pt[3] = {pos2[0] + sgn * axis[0] * hl, pos2[1] + sgn * axis[1] * hl, pos2[2] + sgn * axis[2] * hl};
+              Con c;
+              if (plane_sphere(c, margin, pos1, n, pt, size2[0])) {
+                c.frame[3] = axis[0]; c.frame[4] = axis[1]; c.frame[5] = axis[2];
+                emit(c, p, ncon);
+              }
+            }
+          } else if (t2 == OX_GEOM_BOX) {
+            T mat2[9];
+            ld<9>(mat2, b.geom_xmat, 9 * g2);
+            T dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+            const T dist = dot3(dif, n);
+            int cnt = 0;
+            for (int i = 0; i < 8 && cnt < 4; i++) {
+              T vec[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])}, corner[3];
+              mat_vec3(corner, mat2, vec);
+              const T ldist = dot3(n, corner);
+              if (dist + ldist > margin || ldist > 0) continue;
+              Con c;
+              c.dist = dist + ldist;
+              c.frame[0] = n[0]; c.frame[1] = n[1]; c.frame[2] = n[2]; c.frame[3] = 0; c.frame[4] = 0; c.frame[5] = 0;
+              const T s = -c.dist / 2;
+              c.pos[0] = corner[0] + pos2[0] + n[0] * s; c.pos[1] = corner[1] + pos2[1] + n[1] * s; c.pos[2] = corner[2] + pos2[2] + n[2] * s;
+              emit(c, p, ncon);
+              cnt++;
+            }
+          }
+        } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_SPHERE) {
+          Con c;
+          if (sphere_sphere(c, margin, pos1, size1[0], pos2, size2[0])) emit(c, p, ncon);
+        } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_CAPSULE) {
+          T axis[3] = {at(b.geom_xmat, 9 * g2 + 2), at(b.geom_xmat, 9 * g2 + 5), at(b.geom_xmat, 9 * g2 + 8)};
+          T vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+          const T x = ox_clip(dot3(axis, vec), -size2[1], size2[1]);
+          vec[0] = pos2[0] + axis[0] * x; vec[1] = pos2[1] + axis[1] * x; vec[2] = pos2[2] + axis[2] * x;
+          Con c;
+          if (sphere_sphere(c, margin, pos1, size1[0], vec, size2[0])) emit(c, p, ncon);
+        } else if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {
+          T axis1[3] = {at(b.geom_xmat, 9 * g1 + 2) * size1[1], at(b.geom_xmat, 9 * g1 + 5) * size1[1], at(b.geom_xmat, 9 * g1 + 8) * size1[1]};
+          T axis2[3] = {at(b.geom_xmat, 9 * g2 + 2) * size2[1], at(b.geom_xmat, 9 * g2 + 5) * size2[1], at(b.geom_xmat, 9 * g2 + 8) * size2[1]};
+          T dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+          const T ma = dot3(axis1, axis1), mb = -dot3(axis1, axis2), mc = dot3(axis2, axis2);
+          const T u = -dot3(axis1, dif), v = dot3(axis2, dif), det = ma * mc - mb * mb;
+          T vec1[3], vec2[3];
+          Con c;
+          if (ox_abs(det) >= (T)OX_MINVAL) {
+            T x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+            if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
+            if (x2 > 1) { x2 = 1; x1 = (u - mb) / ma; } else if (x2 < -1) { x2 = -1; x1 = (u + mb) / ma; }
+            x1 = ox_clip(x1, (T)-1, (T)1);
+            for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k] * x2; }
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) emit(c, p, ncon);
+          } else {
+            int n = 0;
+            T x2 = ox_clip((v - mb) / mc, (T)-1, (T)1);
+            for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            x2 = ox_clip((v + mb) / mc, (T)-1, (T)1);
+            for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] - axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            if (n < 2) {
+              T x1 = ox_clip((u - mb) / ma, (T)-1, (T)1);
+              for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k]; }
+              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            }
+            if (n < 2) {
+              T x1 = ox_clip((u + mb) / ma, (T)-1, (T)1);
+              for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] - axis2[k]; }
+              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            }
+          }
+        }
+      }
+    }
+    ati(b.ncon, 0) = ncon;
+  }
+
+  // ============================================================ A.6 constraint assembly
+  // impedance d(x), reference acceleration aref, regulariser R for one row; returns R
+  OX_HD T row_params(const T* solref, const T* solimp, T pos, T margin, T diagApprox, T vel, T* aref) const {
+    const BlobHeader& h = m.h();
+    const T dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+    T imp;
+    if (dmin == dmax || width <= (T)OX_MINVAL) imp = (T)0.5 * (dmin + dmax);
+    else {
+      const T x = ox_abs(pos - margin) / width;
+      if (x >= 1) imp = dmax;
+      else if (x <= 0) imp = dmin;
+      else {
+        T y;
+        if (power == 1) y = x;
+        else if (x <= mid) y = ox_pow(x, power) / ox_pow(mid, power - 1);
+        else y = 1 - ox_pow(1 - x, power) / ox_pow(1 - mid, power - 1);
+        imp = dmin + y * (dmax - dmin);
+      }
+    }
+    imp = ox_clip(imp, (T)OX_MINIMP, (T)OX_MAXIMP);
+    T K, Bd;
+    if (solref[0] > 0) {
+      T tc = solref[0];
+      const T dr = solref[1];
+      if (!dis(OX_DSBL_REFSAFE)) tc = ox_max(tc, 2 * (T)h.timestep);
+      K = 1 / ox_max((T)OX_MINVAL, dmax * dmax * tc * tc * dr * dr);
+      Bd = 2 / ox_max((T)OX_MINVAL, dmax * tc);
+    } else {
+      K = -solref[0] / ox_max((T)OX_MINVAL, dmax * dmax);
+      Bd = -solref[1] / ox_max((T)OX_MINVAL, dmax);
+    }
+    *aref = -Bd * vel - K * imp * (pos - margin);
+    return ox_max((T)OX_MINVAL, (1 - imp) * diagApprox / imp);
+  }
+
+  OX_HDN void make_constraint() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, njnt = h.njnt;
+    int nefc = 0;
+    if (!dis(OX_DSBL_CONSTRAINT)) {
+      if (!dis(OX_DSBL_LIMIT)) {
+        const int32_t *limited = m.jnt_limited(), *jnt_type = m.jnt_type();
+        for (int j = 0; j < njnt; j++) {
+          if (!limited[j]) continue;
+          const int jt = jnt_type[j];
+          if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
+          const int da = m.jnt_dofadr()[j];
+          const T value = at(b.qpos, m.jnt_qposadr()[j]), margin = m.jnt_margin()[j];
+          for (int side = -1; side <= 1; side += 2) {
+            const T dist = side * (m.jnt_range()[2 * j + (side + 1) / 2] - value);
+            if (dist < margin) {
+              const int r = nefc++;
+              for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
+              at(b.efc_J, r * nv + da) = (T)(-side);
+              const T vel = (T)(-side) * at(b.qvel, da);
+              T aref;
+              const T R = row_params(m.jnt_solref() + 2 * j, m.jnt_solimp() + 5 * j, dist, margin, m.dof_invweight0()[da], vel, &aref);
+              at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
+            }
+          }
+        }
+      }
+      const int ncon = ati(b.ncon, 0);
+      const int32_t *dof_parent = m.dof_parentid(), *rootid = m.body_rootid(), *gbody = m.geom_bodyid();
+      for (int c = 0; c < ncon; c++) {
+        const int p = ati(b.con_pair, c);
+        const T includemargin = m.pair_margin()[p] - m.pair_gap()[p];
+        const T dist = at(b.con_dist, c);
+        if (dist >= includemargin) continue;
+        const int dim = m.pair_dim()[p];
+        const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+        const int r0 = nefc;
+        nefc += nrow;
+        const T* fri = m.pair_friction() + 5 * p;
+        T cpos[3], frame[9];
+        ld<3>(cpos, b.con_pos, 3 * c);
+        ld<9>(frame, b.con_frame, 9 * c);
+        for (int r = r0; r < r0 + nrow; r++)
+          for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
+        T veln = 0, velt[2] = {0, 0};
+        const int bodies[2] = {gbody[m.pair_geom2()[p]], gbody[m.pair_geom1()[p]]};
+        for (int sidx = 0; sidx < 2; sidx++) {
+          const T sign = sidx == 0 ? (T)1 : (T)-1;
+          int body = bodies[sidx];
+          T sc[3], offset[3];
+          ld<3>(sc, b.subtree_com, 3 * rootid[body]);
+          offset[0] = cpos[0] - sc[0]; offset[1] = cpos[1] - sc[1]; offset[2] = cpos[2] - sc[2];
+          while (body && m.body_dofnum()[body] == 0) body = m.body_parentid()[body];
+          if (!body) continue;
+          for (int i = m.body_dofadr()[body] + m.body_dofnum()[body] - 1; i >= 0; i = dof_parent[i]) {
+            T cd[6], jp[3];
+            ld<6>(cd, b.cdof, 6 * i);
+            cross3(jp, cd, offset);
+            jp[0] = sign * (jp[0] + cd[3]); jp[1] = sign * (jp[1] + cd[4]); jp[2] = sign * (jp[2] + cd[5]);
+            const T jn = dot3(frame, jp);
+            const T qv = at(b.qvel, i);
+            veln += jn * qv;
+            if (dim == 1) {
+              at(b.efc_J, r0 * nv + i) += jn;
+            } else {
+              for (int k = 1; k < dim; k++) {
+                const T jt = dot3(frame + 3 * k, jp) * fri[k - 1];
+                velt[k - 1] += jt * qv;
+                at(b.efc_J, (r0 + 2 * (k - 1)) * nv + i) += jn + jt;
+                at(b.efc_J, (r0 + 2 * (k - 1) + 1) * nv + i) += jn - jt;
+              }
+            }
+          }
+        }
+        const T tran = m.body_invweight0()[2 * bodies[1]] + m.body_invweight0()[2 * bodies[0]];
+        const T* solref = m.pair_solref() + 2 * p;
+        const T* solimp = m.pair_solimp() + 5 * p;
+        if (dim == 1) {
+          T aref;
+          const T R = row_params(solref, solimp, dist, includemargin, tran, veln, &aref);
+          at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / R; at(b.efc_aref, r0) = aref;
+        } else {
+          T arefs[4], Rfirst = 0;
+          for (int k = 1; k < dim; k++)
+            for (int s = 0; s < 2; s++) {
+              const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
+              const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
+              if (k == 1 && s == 0) Rfirst = R;
+            }
+          const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
+          const T D = 1 / (2 * mu * mu * Rfirst);
+          for (int r = 0; r < nrow; r++) {
+            at(b.efc_pos, r0 + r) = dist; at(b.efc_margin, r0 + r) = includemargin; at(b.efc_D, r0 + r) = D;
+            at(b.efc_aref, r0 + r) = arefs[r];
+          }
+        }
+      }
+    }
+    ati(b.nefc, 0) = nefc;
+  }
+
+  // ============================================================ A.11 primal solver (Newton / CG)
+  struct LsPt { T alpha, cost, d0, d1; };
+
+  OX_HD LsPt ls_eval(T a, int nefc, T qg0, T qg1, T qg2) const {
+    LsPt p;
+    p.alpha = a;
+    p.cost = a * a * qg2 + a * qg1 + qg0;
+    p.d0 = 2 * a * qg2 + qg1;
+    p.d1 = 2 * qg2;
+    for (int r = 0; r < nefc; r++) {
+      const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
+      const T x = ja + a * jv;
+      if (x < 0) {
+        const T D = at(b.efc_D, r);
+        const T q0 = (T)0.5 * D * ja * ja, q1 = D * ja * jv, q2 = (T)0.5 * D * jv * jv;
+        p.cost += a * a * q2 + a * q1 + q0;
+        p.d0 += 2 * a * q2 + q1;
+        p.d1 += 2 * q2;
+      }
+    }
+    if (p.d1 < (T)OX_MINVAL) p.d1 = (T)OX_MINVAL;
+    return p;
+  }
+
+  // efc_force, qfrc_constraint and total cost at the current (qacc, Ma, Jaref); returns cost, gauss via pointer
+  OX_HD T update_constraint(int nv, int nefc, T* gauss_out) const {
+    T c = 0;
+    for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
+    for (int r = 0; r < nefc; r++) {
+      const T ja = at(b.s_Jaref, r);
+      T f = 0;
+      if (ja < 0) {
+        const T D = at(b.efc_D, r);
+        f = -D * ja;
+        c += (T)0.5 * D * ja * ja;
+        for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, r * nv + i) * f;
+      }
+      at(b.efc_force, r) = f;
+    }
+    T g = 0;
+    for (int i = 0; i < nv; i++) g += (T)0.5 * (at(b.s_Ma, i) - at(b.qfrc_smooth, i)) * (at(b.qacc, i) - at(b.qacc_smooth, i));
+    *gauss_out = g;
+    return c + g;
+  }
+
+  // grad, Mgrad (Newton: H^-1 grad with H = M + J' D_active J; CG: M^-1 grad); returns |grad|
+  OX_HD T update_gradient(int nv, int nefc, bool newton) const {
+    T gn = 0;
+    for (int i = 0; i < nv; i++) {
+      const T g = at(b.s_Ma, i) - at(b.qfrc_smooth, i) - at(b.qfrc_constraint, i);
+      at(b.s_grad, i) = g;
+      gn += g * g;
+    }
+    if (!newton) {
+      for (int i = 0; i < nv; i++) at(b.s_Mgrad, i) = at(b.s_grad, i);
+      solve_ld(b.s_Mgrad);
+      return ox_sqrt(gn);
+    }
+    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    T* H = b.s_H;
+    for (int i = 0; i < nv; i++) {
+      for (int j = 0; j <= i; j++) at(H, i * nv + j) = 0;
+      int adr = Madr[i];
+      for (int j = i; j >= 0; j = dof_parent[j]) at(H, i * nv + j) = at(b.qM, adr++);
+    }
+    for (int r = 0; r < nefc; r++) {
+      if (!(at(b.s_Jaref, r) < 0)) continue;
+      const T D = at(b.efc_D, r);
+      for (int i = 0; i < nv; i++) {
+        const T ji = at(b.efc_J, r * nv + i);
+        if (ji == 0) continue;
+        const T s = D * ji;
+        for (int j = 0; j <= i; j++) at(H, i * nv + j) += s * at(b.efc_J, r * nv + j);
+      }
+    }
+    for (int j = 0; j < nv; j++) {  // Cholesky, lower
+      T s = at(H, j * nv + j);
+      for (int k = 0; k < j; k++) { const T l = at(H, j * nv + k); s -= l * l; }
+      s = ox_sqrt(ox_max(s, (T)OX_MINVAL));
+      at(H, j * nv + j) = s;
+      const T inv = 1 / s;
+      for (int i = j + 1; i < nv; i++) {
+        T v = at(H, i * nv + j);
+        for (int k = 0; k < j; k++) v -= at(H, i * nv + k) * at(H, j * nv + k);
+        at(H, i * nv + j) = v * inv;
+      }
+    }
+    for (int i = 0; i < nv; i++) {
+      T v = at(b.s_grad, i);
+      for (int k = 0; k < i; k++) v -= at(H, i * nv + k) * at(b.s_Mgrad, k);
+      at(b.s_Mgrad, i) = v / at(H, i * nv + i);
+    }
+    for (int i = nv - 1; i >= 0; i--) {
+      T v = at(b.s_Mgrad, i);
+      for (int k = i + 1; k < nv; k++) v -= at(H, k * nv + i) * at(b.s_Mgrad, k);
+      at(b.s_Mgrad, i) = v / at(H, i * nv + i);
+    }
+    return ox_sqrt(gn);
+  }
+
+  OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
+    mul_m(b.s_Mv, qacc);
+    T c = 0;
+    for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (qacc[(size_t)i * S + e] - at(b.qacc_smooth, i));
+    for (int r = 0; r < nefc; r++) {
+      T v = -at(b.efc_aref, r);
+      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * qacc[(size_t)i * S + e];
+      if (v < 0) c += (T)0.5 * at(b.efc_D, r) * v * v;
+    }
+    return c;
+  }
+
+  OX_HDN void fwd_constraint() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nefc = ati(b.nefc, 0);
+    if (nefc == 0) {
+      for (int i = 0; i < nv; i++) {
+        const T a = at(b.qacc_smooth, i);
+        at(b.qacc, i) = a; at(b.qacc_warmstart, i) = a; at(b.qfrc_constraint, i) = 0;
+      }
+      ati(b.solver_niter, 0) = 0;
+      return;
+    }
+    const bool newton = h.solver == OX_SOL_NEWTON;
+    bool use_smooth = true;
+    if (!dis(OX_DSBL_WARMSTART)) {
+      const T cw = cost_at(b.qacc_warmstart, nv, nefc), cs = cost_at(b.qacc_smooth, nv, nefc);
+      use_smooth = cw > cs;
+    }
+    for (int i = 0; i < nv; i++) at(b.qacc, i) = use_smooth ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
+    // initial state
+    mul_m(b.s_Ma, b.qacc);
+    for (int r = 0; r < nefc; r++) {
+      T v = -at(b.efc_aref, r);
+      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.qacc, i);
+      at(b.s_Jaref, r) = v;
+    }
+    T gauss;
+    T cost = update_constraint(nv, nefc, &gauss);
+    T gnorm = update_gradient(nv, nefc, newton);
+    for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
+    const T tol = (T)h.tolerance;
+    const T mscale = (T)h.meaninertia * (T)(nv > 1 ? nv : 1);
+    const T scale = 1 / mscale;
+    int maxiter = h.iterations;
+    if (scale * gnorm < tol) maxiter = 0;
+    int iter = 0;
+    while (iter < maxiter) {
+      // ---- exact line search on the convex piecewise-quadratic phi(alpha)
+      T snorm = 0;
+      for (int i = 0; i < nv; i++) { const T s = at(b.s_search, i); snorm += s * s; }
+      snorm = ox_sqrt(snorm);
+      if (snorm < (T)OX_MINVAL) break;
+      const T gtol = tol * (T)h.ls_tolerance * snorm * mscale;
+      mul_m(b.s_Mv, b.s_search);
+      for (int r = 0; r < nefc; r++) {
+        T v = 0;
+        for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.s_search, i);
+        at(b.s_Jv, r) = v;
+      }
+      T qg1 = 0, qg2 = 0;
+      for (int i = 0; i < nv; i++) {
+        const T s = at(b.s_search, i);
+        qg1 += s * (at(b.s_Ma, i) - at(b.qfrc_smooth, i));
+        qg2 += (T)0.5 * s * at(b.s_Mv, i);
+      }
+      const LsPt p0 = ls_eval(0, nefc, gauss, qg1, qg2);
+      if (!(p0.d0 < 0)) break;
+      LsPt lo = p0, hi = p0, cur = p0;
+      bool have_hi = false;
+      for (int it = 0; it < h.ls_iterations; it++) {
+        T a = cur.alpha - cur.d0 / cur.d1;
+        if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = (T)0.5 * (lo.alpha + hi.alpha);
+        if (ox_abs(a - cur.alpha) <= Eps<T>::v() * ox_abs(a)) break;
+        cur = ls_eval(a, nefc, gauss, qg1, qg2);
+        if (ox_abs(cur.d0) < gtol) break;
+        if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
+      }
+      const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
+      if (alpha == 0) break;
+      // ---- move
+      for (int i = 0; i < nv; i++) {
+        at(b.qacc, i) += alpha * at(b.s_search, i);
+        at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
+        if (!newton) { at(b.s_gradold, i) = at(b.s_grad, i); at(b.s_Mgradold, i) = at(b.s_Mgrad, i); }
+      }
+      for (int r = 0; r < nefc; r++) at(b.s_Jaref, r) += alpha * at(b.s_Jv, r);
+      const T oldcost = cost;
+      cost = update_constraint(nv, nefc, &gauss);
+      gnorm = update_gradient(nv, nefc, newton);
+      iter++;
+      const T improvement = scale * (oldcost - cost), gradient = scale * gnorm;
+      if (improvement < tol || gradient < tol) break;
+      if (newton) {
+        for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
+      } else {
+        T num = 0, den = 0;
+        for (int i = 0; i < nv; i++) {
+          num += at(b.s_grad, i) * (at(b.s_Mgrad, i) - at(b.s_Mgradold, i));
+          den += at(b.s_gradold, i) * at(b.s_Mgradold, i);
+        }
+        T beta = num / ox_max((T)OX_MINVAL, den);
+        if (beta < 0) beta = 0;
+        for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i) + beta * at(b.s_search, i);
+      }
+    }
+    ati(b.solver_niter, 0) = iter;
+    for (int i = 0; i < nv; i++) at(b.qacc_warmstart, i) = at(b.qacc, i);
+  }
+
+  // ============================================================ sensors (N2 subset)
+  OX_HD void obj_frame(int objtype, int id, T* pos, T* mat, int* body) const {
+    if (objtype == OX_OBJ_BODY) { ld<3>(pos, b.xipos, 3 * id); ld<9>(mat, b.ximat, 9 * id); *body = id; }
+    else if (objtype == OX_OBJ_XBODY) { ld<3>(pos, b.xpos, 3 * id); ld<9>(mat, b.xmat, 9 * id); *body = id; }
+    else if (objtype == OX_OBJ_GEOM) { ld<3>(pos, b.geom_xpos, 3 * id); ld<9>(mat, b.geom_xmat, 9 * id); *body = m.geom_bodyid()[id]; }
+    else { ld<3>(pos, b.site_xpos, 3 * id); ld<9>(mat, b.site_xmat, 9 * id); *body = m.site_bodyid()[id]; }
+  }
+  OX_HDN void sensors() const {
+    const BlobHeader& h = m.h();
+    const int ns = h.nsensor, nbody = h.nbody;
+    bool have_slv = false;
+    for (int s = 0; s < ns; s++) {
+      const int adr = m.sensor_adr()[s], id = m.sensor_objid()[s], ot = m.sensor_objtype()[s], ty = m.sensor_type()[s];
+      switch (ty) {
+        case OX_SENS_JOINTPOS: at(b.sensordata, adr) = at(b.qpos, m.jnt_qposadr()[id]); break;
+        case OX_SENS_JOINTVEL: at(b.sensordata, adr) = at(b.qvel, m.jnt_dofadr()[id]); break;
+        case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear()[id] * at(b.qpos, m.jnt_qposadr()[m.actuator_trnid()[id]]); break;
+        case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear()[id] * at(b.qvel, m.jnt_dofadr()[m.actuator_trnid()[id]]); break;
+        case OX_SENS_ACTUATORFRC: at(b.sensordata, adr) = at(b.actuator_force, id); break;
+        case OX_SENS_SUBTREECOM: for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_com, 3 * id + k); break;
+        case OX_SENS_SUBTREELINVEL: {
+          if (!have_slv) {
+            for (int i = 0; i < 3 * nbody; i++) at(b.subtree_linvel, i) = 0;
+            for (int bd = nbody - 1; bd > 0; bd--) {
+              T xi[3], sc[3], cv[6], dif[3], v[3], acc[3], pa[3];
+              ld<3>(xi, b.xipos, 3 * bd);
+              ld<3>(sc, b.subtree_com, 3 * m.body_rootid()[bd]);
+              ld<6>(cv, b.cvel, 6 * bd);
+              dif[0] = xi[0] - sc[0]; dif[1] = xi[1] - sc[1]; dif[2] = xi[2] - sc[2];
+              cross3(v, cv, dif);
+              ld<3>(acc, b.subtree_linvel, 3 * bd);
+              const T ms = m.body_mass()[bd];
+              for (int k = 0; k < 3; k++) acc[k] += ms * (cv[3 + k] + v[k]);
+              st<3>(b.subtree_linvel, 3 * bd, acc);
+              const int p = m.body_parentid()[bd];
+              ld<3>(pa, b.subtree_linvel, 3 * p);
+              for (int k = 0; k < 3; k++) pa[k] += acc[k];
+              st<3>(b.subtree_linvel, 3 * p, pa);
+            }
+            for (int bd = 0; bd < nbody; bd++) {
+              const T inv = 1 / ox_max((T)OX_MINVAL, m.body_subtreemass()[bd]);
+              for (int k = 0; k < 3; k++) at(b.subtree_linvel, 3 * bd + k) *= inv;
+            }
+            have_slv = true;
+          }
+          for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_linvel, 3 * id + k);
+          break;
+        }
+        case OX_SENS_FRAMEPOS: case OX_SENS_FRAMEQUAT: case OX_SENS_FRAMELINVEL: case OX_SENS_FRAMEANGVEL:
+        case OX_SENS_VELOCIMETER: case OX_SENS_GYRO: {
+          T pos[3], mat[9];
+          int body;
+          obj_frame(ot, id, pos, mat, &body);
+          if (ty == OX_SENS_FRAMEPOS) { st<3>(b.sensordata, adr, pos); break; }
+          if (ty == OX_SENS_FRAMEQUAT) { T q[4]; mat2quat(q, mat); st<4>(b.sensordata, adr, q); break; }
+          T cv[6], sc[3], dif[3], tmp[3], lin[3], out[3];
+          ld<6>(cv, b.cvel, 6 * body);
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid()[body]);
+          dif[0] = pos[0] - sc[0]; dif[1] = pos[1] - sc[1]; dif[2] = pos[2] - sc[2];
+          cross3(tmp, cv, dif);
+          lin[0] = cv[3] + tmp[0]; lin[1] = cv[4] + tmp[1]; lin[2] = cv[5] + tmp[2];
+          const T* src = (ty == OX_SENS_FRAMELINVEL || ty == OX_SENS_VELOCIMETER) ? lin : cv;
+          if (ty == OX_SENS_VELOCIMETER || ty == OX_SENS_GYRO) {
+            for (int k = 0; k < 3; k++) out[k] = mat[k] * src[0] + mat[3 + k] * src[1] + mat[6 + k] * src[2];
+          } else { out[0] = src[0]; out[1] = src[1]; out[2] = src[2]; }
+          st<3>(b.sensordata, adr, out);
+          break;
+        }
+        case OX_SENS_CLOCK: at(b.sensordata, adr) = at(b.time, 0); break;
+        default: break;
+      }
+    }
+  }
+
+  // ============================================================ forward (mj_forwardSkip)
+  OX_HD void fwd_position() const { kinematics(); com_pos(); crb(); factor_m(); collision(); }
+  OX_HD void fwd_velocity() const { com_vel(); passive(); rne(); }
+  OX_HDN void forward(bool skipsensor) const {
+    fwd_position();
+    fwd_velocity();
+    make_constraint();
+    actuation();
+    fwd_acceleration();
+    fwd_constraint();
+    if (!skipsensor) sensors();
+  }
+
+  // ============================================================ A.12 integration
+  OX_HD void integrate_pos(T* qpos, const T* qvel, T dt) const {
+    const int njnt = m.h().njnt;
+    const int32_t *jnt_type = m.jnt_type(), *qposadr = m.jnt_qposadr(), *jdofadr = m.jnt_dofadr();
+    for (int j = 0; j < njnt; j++) {
+      int pa = qposadr[j], va = jdofadr[j];
+      const int jt = jnt_type[j];
+      if (jt == OX_JNT_FREE) {
+        for (int i = 0; i < 3; i++) at(qpos, pa + i) += dt * qvel[(size_t)(va + i) * S + e];
+        pa += 3; va += 3;
+      }
+      if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+        T q[4], w[3] = {qvel[(size_t)va * S + e], qvel[(size_t)(va + 1) * S + e], qvel[(size_t)(va + 2) * S + e]};
+        ld<4>(q, qpos, pa);
+        quat_integrate(q, w, dt);
+        st<4>(qpos, pa, q);
+      } else {
+        at(qpos, pa) += dt * qvel[(size_t)va * S + e];
+      }
+    }
+  }
+  OX_HD void advance(const T* qacc, const T* qvel_override) const {
+    const BlobHeader& h = m.h();
+    const T dt = (T)h.timestep;
+    for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * qacc[(size_t)i * S + e];
+    integrate_pos(b.qpos, qvel_override ? qvel_override : b.qvel, dt);
+    at(b.time, 0) += dt;
+  }
+  OX_HDN void euler() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nM = h.nM;
+    if (!h.any_damping || dis(OX_DSBL_EULERDAMP)) { advance(b.qacc, nullptr); return; }
+    // implicit-in-velocity joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint; like MuJoCo
+    // the factor of M in qLD is overwritten by the factor of M + h B.
+    const T dt = (T)h.timestep;
+    for (int i = 0; i < nM; i++) at(b.qLD, i) = at(b.qM, i);
+    for (int i = 0; i < nv; i++) at(b.qLD, m.dof_Madr()[i]) += dt * m.dof_damping()[i];
+    factor_ld(b.qLD, b.qLDiagInv);
+    for (int i = 0; i < nv; i++) at(b.i_qacc, i) = at(b.qfrc_smooth, i) + at(b.qfrc_constraint, i);
+    solve_ld(b.i_qacc);
+    advance(b.i_qacc, nullptr);
+  }
+  // classic RK4; the Butcher matrix has one entry per row, so X_i = X_0 (+) h a_i F_{i-1}
+  OX_HDN void rk4() const {
+    const BlobHeader& h = m.h();
+    const int nv = h.nv, nq = h.nq;
+    const T dt = (T)h.timestep;
+    const T t0 = at(b.time, 0);
+    const T A[3] = {(T)0.5, (T)0.5, (T)1}, Bw[4] = {(T)(1.0 / 6), (T)(1.0 / 3), (T)(1.0 / 3), (T)(1.0 / 6)};
+    for (int i = 0; i < nq; i++) at(b.rk_q0, i) = at(b.qpos, i);
+    for (int i = 0; i < nv; i++) {
+      at(b.rk_v0, i) = at(b.qvel, i);
+      at(b.rk_sv, i) = Bw[0] * at(b.qvel, i);
+      at(b.rk_sa, i) = Bw[0] * at(b.qacc, i);
+    }
+    for (int st_ = 1; st_ < 4; st_++) {
+      const T a = A[st_ - 1];
+      // dX = a * F_{st-1}; F_{st-1} = (current qvel, current qacc)
+      for (int i = 0; i < nv; i++) { at(b.s_gradold, i) = a * at(b.qvel, i); at(b.s_Mgradold, i) = a * at(b.qacc, i); }
+      for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
+      integrate_pos(b.qpos, b.s_gradold, dt);
+      for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i) + dt * at(b.s_Mgradold, i);
+      at(b.time, 0) = t0 + a * dt;
+      forward(true);
+      for (int i = 0; i < nv; i++) {
+        at(b.rk_sv, i) += Bw[st_] * at(b.qvel, i);
+        at(b.rk_sa, i) += Bw[st_] * at(b.qacc, i);
+      }
+    }
+    at(b.time, 0) = t0;
+    for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
+    for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i);
+    advance(b.rk_sa, b.rk_sv);
+  }
+
+  // ============================================================ reset / checks / step
+  OX_HDN void reset_data() const {
+    const BlobHeader& h = m.h();
+    for (int i = 0; i < h.nq; i++) at(b.qpos, i) = m.qpos0()[i];
+    for (int i = 0; i < h.nv; i++) { at(b.qvel, i) = 0; at(b.qfrc_applied, i) = 0; at(b.qacc_warmstart, i) = 0; at(b.qacc, i) = 0; }
+    for (int i = 0; i < h.nu; i++) at(b.ctrl, i) = 0;
+    for (int i = 0; i < 6 * h.nbody; i++) at(b.xfrc_applied, i) = 0;
+    at(b.time, 0) = 0;
+    ati(b.ncon, 0) = 0; ati(b.nefc, 0) = 0; ati(b.solver_niter, 0) = 0;
+  }
+  OX_HD bool bad_state() const {
+    const BlobHeader& h = m.h();
+    bool bad = false;
+    for (int i = 0; i < h.nq; i++) bad |= ox_bad(at(b.qpos, i));
+    for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qvel, i));
+    return bad;
+  }
+  OX_HD bool bad_acc() const {
+    const BlobHeader& h = m.h();
+    bool bad = false;
+    for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qacc, i));
+    return bad;
+  }
+  OX_HD void fill_ctrl_philox(uint64_t seed, int64_t genv, int64_t stepno) const {
+    const int nu = m.h().nu;
+    for (int g = 0; g * 4 < nu; g++) {
+      uint32_t out[4];
+      philox4x32_10((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)stepno, (uint32_t)g, (uint32_t)seed,
+                    (uint32_t)(seed >> 32), out);
+      for (int k = 0; k < 4 && g * 4 + k < nu; k++)
+        at(b.ctrl, g * 4 + k) = (T)(int32_t)((out[k] >> 9) * 2u + 1u) * (T)(1.0 / 8388608.0) - (T)1;
+    }
+  }
+  OX_HD void accumulate_stats() const {
+    ati(b.acc_ncon, 0) += ati(b.ncon, 0);
+    ati(b.acc_nefc, 0) += ati(b.nefc, 0);
+    ati(b.acc_niter, 0) += ati(b.solver_niter, 0);
+  }
+  OX_HDN void step() const {
+    if (bad_state()) { reset_data(); ati(b.diverged, 0) += 1; }
+    forward(false);
+    if (bad_acc()) { reset_data(); ati(b.diverged, 0) += 1; forward(false); }
+    accumulate_stats();
+    if (m.h().integrator == OX_INT_RK4) rk4(); else euler();
+  }
+};
+
+}  // namespace ox

@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Gates: single-step qpos/qvel/qacc relative error <= 1e-9 in fp64 validation mode and
+<= 1e-4 in fp32, with rel = |a-b| / max(1, |b|); bounded divergence over a 100-step horizon.
+The comparator is the restated oracle (oracle/ox_oracle.cpp), not libmujoco - parity is unpinned.
+"""
+import numpy as np
+import pytest
+
+from support import OracleData, SEED, random_state, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = ["pendulum", "cartpole", "acrobot", "cheetah", "humanoid"]
+STAGE_FIELDS = ["xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat", "subtree_com", "cinert",
+                "cdof", "qM", "cvel", "cdof_dot", "qfrc_bias", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth",
+                "qacc_smooth", "qacc", "qfrc_constraint", "sensordata"]
+
+
+def oracle_rollout(model, qpos, qvel, nsteps, warm=0, env_off=0):
+    """Returns per-step (qpos, qvel, qacc) of the oracle, shape [nsteps, nenv, n], plus the final OracleData list."""
+    nenv = qpos.shape[0]
+    out_q, out_v, out_a, ods = [], [], [], []
+    for e in range(nenv):
+        od = OracleData(model)
+        od.field("qpos")[:] = qpos[e]
+        od.field("qvel")[:] = qvel[e]
+        q, v, a = [], [], []
+        for s in range(nsteps):
+            od.fill_ctrl_philox(env_off + e, s)
+            od.step()
+            q.append(od.field("qpos").copy()); v.append(od.field("qvel").copy()); a.append(od.field("qacc").copy())
+        out_q.append(q); out_v.append(v); out_a.append(a); ods.append(od)
+    tr = lambda x: np.transpose(np.array(x), (1, 0, 2))
+    return tr(out_q), tr(out_v), tr(out_a), ods
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+@pytest.mark.parametrize("mode", ["fused", "staged"])
+def test_single_step_fp64(ox, name, mode):
+    model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    nenv = 256
+    qpos, qvel = random_state(model, nenv, seed=11)
+    b = ox.BatchedPhysics(model, nenv, precision="f64", mode=mode)
+    b.set("qpos", qpos); b.set("qvel", qvel)
+    b.ctrl_philox(True, SEED)
+    b.step(1); b.sync()
+    oq, ov, oa, ods = oracle_rollout(model, qpos, qvel, 1)
+    assert rel_err(b.get("qpos"), oq[0]) <= 1e-9
+    assert rel_err(b.get("qvel"), ov[0]) <= 1e-9
+    assert rel_err(b.get("qacc"), oa[0]) <= 1e-9
+    # derived arrays of the forward pass inside the step (pre-integration state), stage by stage
+    for f in STAGE_FIELDS:
+        ref = np.stack([od.field(f) for od in ods])
+        assert rel_err(b.get(f), ref) <= 1e-9, f
+    assert np.array_equal(b.get("ncon")[:, 0], [od.int("ncon") for od in ods])
+    assert np.array_equal(b.get("nefc")[:, 0], [od.int("nefc") for od in ods])
+    assert int(b.diverged().sum()) == 0
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_single_step_fp32(ox, name):
+    model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    nenv = 256
+    qpos, qvel = random_state(model, nenv, seed=12)
+    b = ox.BatchedPhysics(model, nenv, precision="f32")
+    b.set("qpos", qpos); b.set("qvel", qvel)
+    b.ctrl_philox(True, SEED)
+    b.step(1); b.sync()
+    # the oracle starts from the fp32-rounded state the device actually holds
+    q32, v32 = qpos.astype(np.float32).astype(np.float64), qvel.astype(np.float32).astype(np.float64)
+    oq, ov, oa, ods = oracle_rollout(model, q32, v32, 1)
+    assert rel_err(b.get("qpos"), oq[0]) <= 1e-4
+    assert rel_err(b.get("qvel"), ov[0]) <= 1e-4
+    assert rel_err(b.get("qacc"), oa[0]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", CONFIGS)
+def test_horizon_fp64(ox, name):
+    """100 steps: max abs qpos deviation <= 1e-6 (fp64), no divergence flags."""
+    model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    nenv, nsteps = 32, 100
+    qpos, qvel = random_state(model, nenv, seed=13)
+    b = ox.BatchedPhysics(model, nenv, precision="f64")
+    b.set("qpos", qpos); b.set("qvel", qvel)
+    b.ctrl_philox(True, SEED)
+    b.step(nsteps); b.sync()
+    oq, ov, oa, ods = oracle_rollout(model, qpos, qvel, nsteps)
+    assert np.max(np.abs(b.get("qpos") - oq[-1])) <= 1e-6
+    assert np.max(np.abs(b.get("qvel") - ov[-1])) <= 1e-5
+    assert int(b.diverged().sum()) == 0
+    assert abs(float(b.get("time")[0, 0]) - nsteps * model.timestep) < 1e-9
+
+
+@pytest.mark.parametrize("name,bound", [("pendulum", 1e-3), ("cartpole", 1e-2), ("acrobot", 1e-2)])
+def test_horizon_fp32_contact_free(ox, name, bound):
+    model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    nenv, nsteps = 32, 100
+    qpos, qvel = random_state(model, nenv, seed=14)
+    b = ox.BatchedPhysics(model, nenv, precision="f32")
+    b.set("qpos", qpos); b.set("qvel", qvel)
+    b.ctrl_philox(True, SEED)
+    b.step(nsteps); b.sync()
+    oq, ov, oa, ods = oracle_rollout(model, qpos, qvel, nsteps)
+    assert np.max(np.abs(b.get("qpos") - oq[-1])) <= bound
+    assert int(b.diverged().sum()) == 0
+
+
+def test_sharding_is_trajectory_stable(ox):
+    """Global env ids key the control stream: envs [128,256) of a 256-env batch == a 128-env batch at offset 128."""
+    model = ox.Model.from_xml_string(ox.models.CHEETAH)
+    qpos, qvel = random_state(model, 256, seed=15)
+    full = ox.BatchedPhysics(model, 256, precision="f32")
+    full.set("qpos", qpos); full.set("qvel", qvel); full.ctrl_philox(True, SEED); full.step(20); full.sync()
+    half = ox.BatchedPhysics(model, 128, precision="f32", env_id_offset=128)
+    half.set("qpos", qpos[128:]); half.set("qvel", qvel[128:]); half.ctrl_philox(True, SEED); half.step(20); half.sync()
+    assert np.array_equal(full.get("qpos")[128:], half.get("qpos"))
+    assert np.array_equal(full.get("qvel")[128:], half.get("qvel"))
+
+
+def test_fault_injection_autoreset(ox):
+    """A NaN in one env's qvel triggers mj_checkVel-style auto-reset of that env only."""
+    model = ox.Model.from_xml_string(ox.models.CHEETAH)
+    nenv = 64
+    qpos, qvel = random_state(model, nenv, seed=16)
+    ref = ox.BatchedPhysics(model, nenv, precision="f64")
+    ref.set("qpos", qpos); ref.set("qvel", qvel); ref.step(3); ref.sync()
+    bad = qvel.copy()
+    bad[7, 2] = np.nan
+    b = ox.BatchedPhysics(model, nenv, precision="f64")
+    b.set("qpos", qpos); b.set("qvel", bad); b.step(3); b.sync()
+    div = b.diverged()
+    assert div[7] == 1 and div.sum() == 1
+    keep = np.arange(nenv) != 7
+    assert np.array_equal(b.get("qpos")[keep], ref.get("qpos")[keep])
+    assert np.all(np.isfinite(b.get("qpos")))
+    with pytest.raises(ox.PhysicsDiverged):
+        b.check_diverged()
+
+
+def test_single_env_physics_api_pendulum_1000_steps(ox):
+    """BASELINE config[0]: inline-MJCF pendulum stepped 1000 steps through the Physics API (src/physics.rs)."""
+    p = ox.Physics.from_xml_string(ox.models.PENDULUM)
+    hinge = p.object_id(ox.obj.Joint, "hinge")
+    act = p.object_id(ox.obj.Actuator, "torque")
+    assert p.object_name(hinge) == "hinge" and p.object_id(ox.obj.Joint, "nope") is None
+    p.set_qpos(hinge, 0.3, ox.joint.Hinge)
+    od = OracleData(p.model())
+    od.field("qpos")[0] = 0.3
+    for s in range(1000):
+        u = 0.5 * np.sin(0.01 * s)
+        p.actuators().set(act, u)
+        od.field("ctrl")[0] = u
+        p.step(); od.step()
+    assert abs(p.qpos(hinge, ox.joint.Hinge) - od.field("qpos")[0]) <= 1e-9
+    assert abs(p.qvel(hinge) - od.field("qvel")[0]) <= 1e-9
+    assert abs(p.time() - 2.0) < 1e-9
+    assert p.act(act) is None and p.mocap_pos(ox.ObjectId(ox.obj.Body, 1)) is None
+    with pytest.raises(ox.JointTypeNotMatch):
+        p.qpos(hinge, ox.joint.Slide)
+    p.reset()
+    assert p.qpos(hinge) == 0.0 and p.time() == 0.0
+
+
+def test_bulk_io_layouts_and_dtypes(ox):
+    model = ox.Model.from_xml_string(ox.models.CHEETAH)
+    nenv = 100  # not a multiple of 32: exercises the padded stride
+    b = ox.BatchedPhysics(model, nenv, precision="f32")
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(nenv, model.nq))
+    b.set("qpos", q)
+    assert np.array_equal(b.get("qpos", np.float32), q.astype(np.float32))
+    assert np.array_equal(b.get("qpos", np.float64, "elem_major"), q.astype(np.float32).astype(np.float64).T)
+    b.set("qvel", q.T.astype(np.float32).copy(), layout="elem_major")
+    assert np.array_equal(b.get("qvel", np.float32), q.astype(np.float32))
+    b.set1("ctrl", 5, [0.25], offset=2)
+    assert b.get1("ctrl", 5)[2] == 0.25 and b.get1("ctrl", 4)[2] == 0.0
+    mask = np.zeros(nenv, np.uint8); mask[3] = 1
+    b.reset(mask)
+    assert np.array_equal(b.get("qpos")[3], model.qpos0) and np.array_equal(b.get("qpos", np.float32)[4], q[4].astype(np.float32))
