@@ -924,6 +924,8 @@ struct Solver {
       for (int i = 0; i < nv; i++) gn += grad[i] * grad[i];
       double gradient = scale * std::sqrt(gn);
       if (improvement < m->tolerance || gradient < m->tolerance) break;
+      // floating-point floor (ORACLE_DECISIONS.md #7): inert in fp64, kept so oracle and GPU run the same rule
+      if (oldcost - cost <= 8 * 4 * 2.220446049250313e-16 * (std::fabs(oldcost) + std::fabs(cost))) break;
       if (newton) for (int i = 0; i < nv; i++) search[i] = -Mgrad[i];
       else {
         double num = 0, den = 0;

@@ -418,6 +418,14 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   if (b->blob_bytes > 200 * 1024) { ox::set_error("model constant tables exceed shared memory (200 KB)"); return OX_ERR_INVALID; }
   CU_TRY(cudaMalloc(&b->d_blob, blob.size()));
   CU_TRY(cudaMemcpy(b->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  {  // device code indexes every field with 32-bit arithmetic: element * stride + env must fit
+    const long long nem = std::max(1, t.nefcmax), big = std::max<long long>({nem * (long long)t.nv, (long long)t.nv * t.nv,
+                                                                             10LL * t.nbody, 9LL * std::max(1, t.nconmax), 9LL * t.ngeom});
+    if ((big + 1) * (long long)b->stride >= (1LL << 32)) {
+      ox::set_error("ox_batch_create: nenv too large for 32-bit field indexing (largest field x nenv >= 2^32); split the batch");
+      return OX_ERR_INVALID;
+    }
+  }
   b->arena_bytes = b->f64 ? layout_arena<double>(t, b->stride, nullptr, nullptr, nullptr)
                           : layout_arena<float>(t, b->stride, nullptr, nullptr, nullptr);
   CU_TRY(cudaMalloc(&b->arena, b->arena_bytes));

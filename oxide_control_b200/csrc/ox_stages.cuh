@@ -172,20 +172,20 @@ struct Env {
   DevModel<T> m;
   DevBatch<T> b;
   int e;
-  size_t S;
+  uint32_t S;  // env stride; every field index fits 32 bits (checked at batch creation)
 
-  OX_HD Env(const DevModel<T>& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(e_), S((size_t)b_.stride) {}
+  OX_HD Env(const DevModel<T>& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(e_), S((uint32_t)b_.stride) {}
 
   // element i of a field for this env
-  OX_HD T& at(T* f, int i) const { return f[(size_t)i * S + e]; }
-  OX_HD int32_t& ati(int32_t* f, int i) const { return f[(size_t)i * S + e]; }
+  OX_HD T& at(T* f, int i) const { return f[(uint32_t)i * S + (uint32_t)e]; }
+  OX_HD int32_t& ati(int32_t* f, int i) const { return f[(uint32_t)i * S + (uint32_t)e]; }
   template <int N> OX_HD void ld(T* dst, const T* f, int first) const {
 #pragma unroll
-    for (int k = 0; k < N; k++) dst[k] = f[(size_t)(first + k) * S + e];
+    for (int k = 0; k < N; k++) dst[k] = f[(uint32_t)(first + k) * S + (uint32_t)e];
   }
   template <int N> OX_HD void st(T* f, int first, const T* src) const {
 #pragma unroll
-    for (int k = 0; k < N; k++) f[(size_t)(first + k) * S + e] = src[k];
+    for (int k = 0; k < N; k++) f[(uint32_t)(first + k) * S + (uint32_t)e] = src[k];
   }
   template <int N> OX_HD void ldm(T* dst, const T* table, int first) const {  // model table (uniform)
 #pragma unroll
@@ -467,11 +467,11 @@ struct Env {
     for (int i = 0; i < nv; i++) at(res, i) = 0;
     for (int i = 0; i < nv; i++) {
       int adr = Madr[i];
-      const T vi = v[(size_t)i * S + e];
+      const T vi = v[(uint32_t)i * S + (uint32_t)e];
       T ri = at(res, i) + at(b.qM, adr++) * vi;
       for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) {
         const T mij = at(b.qM, adr++);
-        ri += mij * v[(size_t)j * S + e];
+        ri += mij * v[(uint32_t)j * S + (uint32_t)e];
         at(res, j) += mij * vi;
       }
       at(res, i) = ri;
@@ -1053,10 +1053,10 @@ struct Env {
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
     mul_m(b.s_Mv, qacc);
     T c = 0;
-    for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (qacc[(size_t)i * S + e] - at(b.qacc_smooth, i));
+    for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (qacc[(uint32_t)i * S + (uint32_t)e] - at(b.qacc_smooth, i));
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
-      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * qacc[(size_t)i * S + e];
+      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * qacc[(uint32_t)i * S + (uint32_t)e];
       if (v < 0) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
     return c;
@@ -1143,6 +1143,9 @@ struct Env {
       iter++;
       const T improvement = scale * (oldcost - cost), gradient = scale * gnorm;
       if (improvement < tol || gradient < tol) break;
+      // floating-point floor: a decrease below the resolution of the cost itself is round-off, not progress
+      // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
+      if (oldcost - cost <= 8 * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
       if (newton) {
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
       } else {
@@ -1255,23 +1258,23 @@ struct Env {
       int pa = qposadr[j], va = jdofadr[j];
       const int jt = jnt_type[j];
       if (jt == OX_JNT_FREE) {
-        for (int i = 0; i < 3; i++) at(qpos, pa + i) += dt * qvel[(size_t)(va + i) * S + e];
+        for (int i = 0; i < 3; i++) at(qpos, pa + i) += dt * qvel[(uint32_t)(va + i) * S + (uint32_t)e];
         pa += 3; va += 3;
       }
       if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
-        T q[4], w[3] = {qvel[(size_t)va * S + e], qvel[(size_t)(va + 1) * S + e], qvel[(size_t)(va + 2) * S + e]};
+        T q[4], w[3] = {qvel[(uint32_t)va * S + (uint32_t)e], qvel[(uint32_t)(va + 1) * S + (uint32_t)e], qvel[(uint32_t)(va + 2) * S + (uint32_t)e]};
         ld<4>(q, qpos, pa);
         quat_integrate(q, w, dt);
         st<4>(qpos, pa, q);
       } else {
-        at(qpos, pa) += dt * qvel[(size_t)va * S + e];
+        at(qpos, pa) += dt * qvel[(uint32_t)va * S + (uint32_t)e];
       }
     }
   }
   OX_HD void advance(const T* qacc, const T* qvel_override) const {
     const BlobHeader& h = m.h();
     const T dt = (T)h.timestep;
-    for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * qacc[(size_t)i * S + e];
+    for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * qacc[(uint32_t)i * S + (uint32_t)e];
     integrate_pos(b.qpos, qvel_override ? qvel_override : b.qvel, dt);
     at(b.time, 0) += dt;
   }
