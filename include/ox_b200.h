@@ -89,7 +89,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
   X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
   X(jnt_limited, njnt, 1)                                                                           \
-  X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1)               \
+  X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1)               \
   X(geom_type, ngeom, 1) X(geom_bodyid, ngeom, 1) X(geom_contype, ngeom, 1)                        \
   X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
   X(site_bodyid, nsite, 1)                                                                          \
@@ -171,6 +171,8 @@ typedef struct ox_batch_config {
   int32_t block_threads; /* 0 = default */
   int64_t env_id_offset; /* global env id of env 0 (multi-GPU sharding; keys the Philox control stream) */
   double tolerance;      /* <0 = model's */
+  int32_t specialize;    /* 1 (default): use the model-specialised step kernel when one was compiled in (fused mode) */
+  int32_t reserved_;
 } ox_batch_config;
 
 OX_API void ox_batch_config_default(ox_batch_config* cfg);
@@ -221,6 +223,11 @@ OX_API ox_status ox_batch_get1_int(ox_batch* b, int32_t field, int32_t env, int3
 OX_API ox_status ox_batch_stats(ox_batch* b, double* out4);
 /* number of kernel launches issued by this batch so far (bench.py "gpu_launches") */
 OX_API int64_t ox_batch_launch_count(const ox_batch* b);
+/* which step kernel this batch launches: a spec name ("cheetah"), or the generic kernel */
+OX_API const char* ox_batch_kernel_name(const ox_batch* b);
+/* model-specialised kernels compiled into the library (oxide_control_b200/spec_models/*.xml at build time) */
+OX_API int32_t ox_spec_count(void);
+OX_API const char* ox_spec_name(int32_t i);
 /* per-stage device time of one staged forward+integrate (ms), for profiles/: names via ox_stage_name */
 OX_API ox_status ox_batch_stage_times(ox_batch* b, int32_t reps, double* out_ms, int32_t* nstage);
 OX_API const char* ox_stage_name(int32_t i);

@@ -41,7 +41,7 @@ class BatchConfig(C.Structure):
     _fields_ = [
         ("nenv", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32), ("mode", C.c_int32),
         ("iterations", C.c_int32), ("ls_iterations", C.c_int32), ("use_graph", C.c_int32), ("block_threads", C.c_int32),
-        ("env_id_offset", C.c_int64), ("tolerance", C.c_double),
+        ("env_id_offset", C.c_int64), ("tolerance", C.c_double), ("specialize", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -78,6 +78,9 @@ SYMBOLS = {
     "ox_batch_get1_int": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "ox_batch_stats": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "ox_batch_launch_count": (C.c_int64, [_P]),
+    "ox_batch_kernel_name": (C.c_char_p, [_P]),
+    "ox_spec_count": (C.c_int32, []),
+    "ox_spec_name": (C.c_char_p, [C.c_int32]),
     "ox_batch_stage_times": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "ox_stage_name": (C.c_char_p, [C.c_int32]),
 }

@@ -17,6 +17,7 @@
 #include "ox_internal.h"
 #include "ox_model.h"
 #include "ox_arena.h"
+#include "ox_spec.cuh"
 #include "ox_stages.cuh"
 
 namespace ox {
@@ -51,14 +52,6 @@ __device__ __forceinline__ const unsigned char* stage_model(const unsigned char*
   }
   return ox_smem;
 }
-
-struct StepArgs {
-  int nsteps;
-  int philox;
-  uint64_t seed;
-  int64_t env_id_offset;
-  const long long* d_step;
-};
 
 enum Stage { ST_CTRL = 0, ST_CHECK, ST_KIN, ST_CRB, ST_COLLIDE, ST_VEL, ST_EFC, ST_ACC, ST_SOLVE, ST_SENSE, ST_INTEGRATE, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {"ctrl_rng", "check_pos_vel", "kin_com", "crb_ldl", "collide", "vel_bias",
@@ -167,6 +160,8 @@ struct ox_batch {
   uint8_t* d_mask = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   cudaGraph_t graph = nullptr;
+  const ox::SpecEntry* spec = nullptr;  // model-specialised step kernel, when one was compiled in for this model
+  ox::SpecRuntime spec_rt{};
 };
 
 namespace {
@@ -219,7 +214,12 @@ void launch_staged_step(ox_batch* b) {
 template <typename T>
 ox_status do_step(ox_batch* b, int nsteps) {
   if (b->cfg.mode == OX_MODE_FUSED) {
-    k_step_fused<T><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), make_args(b, nsteps));
+    if (b->spec) {
+      if (sizeof(T) == 8) b->spec->launch_f64(b->grid, b->block, b->stream, b->bd, make_args(b, nsteps), b->spec_rt);
+      else b->spec->launch_f32(b->grid, b->block, b->stream, b->bf, make_args(b, nsteps), b->spec_rt);
+    } else {
+      k_step_fused<T><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), make_args(b, nsteps));
+    }
     b->launches++;
     if (b->philox) {
       k_bump<<<1, 1, 0, b->stream>>>(b->d_step, nsteps);
@@ -378,7 +378,7 @@ extern "C" {
 void ox_batch_config_default(ox_batch_config* cfg) {
   if (!cfg) return;
   cfg->nenv = 1; cfg->device = 0; cfg->precision = OX_F32; cfg->mode = OX_MODE_FUSED; cfg->iterations = 0; cfg->ls_iterations = 0;
-  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1;
+  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1; cfg->specialize = 1;
 }
 
 ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batch** out) {
@@ -432,6 +432,12 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   CU_TRY(cudaMemset(b->arena, 0, b->arena_bytes));
   if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; }
   else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; }
+  if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
+    b->spec = ox::find_spec(ox::model_hash(t));
+    b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;
+    b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
+    b->spec_rt.tolerance = cfg->tolerance >= 0 ? cfg->tolerance : t.tolerance;
+  }
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
   CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));
   CU_TRY(cudaMalloc(&b->d_mask, b->stride));
@@ -468,6 +474,13 @@ void ox_batch_free(ox_batch* b) {
 int32_t ox_batch_nenv(const ox_batch* b) { return b ? b->nenv : -1; }
 void* ox_batch_stream(const ox_batch* b) { return b ? (void*)b->stream : nullptr; }
 int64_t ox_batch_launch_count(const ox_batch* b) { return b ? b->launches : -1; }
+const char* ox_batch_kernel_name(const ox_batch* b) {
+  if (!b) return nullptr;
+  if (b->cfg.mode != OX_MODE_FUSED) return "k_stage (generic, one kernel per stage)";
+  return b->spec ? b->spec->name : "k_step_fused (generic)";
+}
+int32_t ox_spec_count(void) { return ox::spec_count(); }
+const char* ox_spec_name(int32_t i) { const ox::SpecEntry* e = ox::spec_at(i); return e ? e->name : nullptr; }
 
 ox_status ox_batch_step(ox_batch* b, int32_t nsteps) {
   if (!b || nsteps < 0) { ox::set_error("ox_batch_step: bad argument"); return OX_ERR_INVALID; }

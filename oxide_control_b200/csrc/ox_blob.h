@@ -33,6 +33,7 @@ struct BlobHeader {
   OX_MODEL_REAL_TABLES(OX_X)
 #undef OX_X
   int32_t pad_[2];
+  OX_HD double grav(int k) const { return gravity[k]; }
 };
 
 template <typename T>
@@ -40,11 +41,11 @@ struct DevModel {
   const unsigned char* base;
   OX_HD const BlobHeader& h() const { return *reinterpret_cast<const BlobHeader*>(base); }
 #define OX_X(name, n, w) \
-  OX_HD const int32_t* name() const { return reinterpret_cast<const int32_t*>(base + h().off_##name); }
+  OX_HD int32_t name(int i) const { return reinterpret_cast<const int32_t*>(base + h().off_##name)[i]; }
   OX_MODEL_INT_TABLES(OX_X)
 #undef OX_X
 #define OX_X(name, n, w) \
-  OX_HD const T* name() const { return reinterpret_cast<const T*>(base + h().off_##name); }
+  OX_HD T name(int i) const { return reinterpret_cast<const T*>(base + h().off_##name)[i]; }
   OX_MODEL_REAL_TABLES(OX_X)
 #undef OX_X
 };

@@ -783,7 +783,7 @@ ox_model* compile_mjcf(const std::string& xml) {
   M->v_jnt_pos.resize(3 * njnt); M->v_jnt_axis.resize(3 * njnt); M->v_jnt_stiffness.resize(njnt);
   M->v_jnt_range.resize(2 * njnt); M->v_jnt_margin.resize(njnt); M->v_jnt_solref.resize(2 * njnt); M->v_jnt_solimp.resize(5 * njnt);
   M->v_qpos0.assign(nq, 0); M->v_qpos_spring.assign(nq, 0);
-  M->v_dof_bodyid.resize(nv); M->v_dof_jntid.resize(nv); M->v_dof_parentid.resize(nv); M->v_dof_Madr.resize(nv);
+  M->v_dof_bodyid.resize(nv); M->v_dof_jntid.resize(nv); M->v_dof_parentid.resize(nv); M->v_dof_Madr.resize(nv); M->v_dof_depth.resize(nv);
   M->v_dof_armature.resize(nv); M->v_dof_damping.resize(nv); M->v_dof_invweight0.assign(nv, 0);
   int nlimited = 0;
   for (int j = 0; j < njnt; j++) {
@@ -832,6 +832,7 @@ ox_model* compile_mjcf(const std::string& xml) {
       M->v_dof_Madr[d] = nM;
       int depth = 1;
       for (int a = par; a >= 0; a = M->v_dof_parentid[a]) depth++;
+      M->v_dof_depth[d] = depth;  // number of dofs on the chain d -> root = length of row d of qM
       nM += depth;
     }
     t.nM = nM;

@@ -1,0 +1,141 @@
+// Model-specialised step: the same stage code as the generic path (ox_stages.cuh), instantiated with
+//   * a generated model policy (ox_specgen -> Spec_<name><T>) whose tables are compile-time constants, so every
+//     loop over bodies / joints / dofs / geoms / pairs unrolls and the tree walks disappear, and
+//   * LOCAL = true storage: every intermediate mjData field is a per-thread array that the unrolled code turns into
+//     registers; only the algorithmic state is read from / written to the SoA batch in HBM.
+// One thread = one environment, one launch = nsteps steps.
+#pragma once
+#include "ox_stages.cuh"
+
+namespace ox {
+
+struct SpecRuntime {  // options that stay runtime so ox_batch_config can override them without a rebuild
+  int iterations, ls_iterations;
+  double tolerance;
+};
+
+struct StepArgs {
+  int nsteps;
+  int philox;
+  uint64_t seed;
+  int64_t env_id_offset;
+  const long long* d_step;
+};
+
+// FNV-1a over everything the generated code depends on
+inline uint64_t model_hash(const ox_model_tables& t) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
+  };
+  const int32_t sizes[] = {t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
+                           t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags};
+  mix(sizes, sizeof sizes);
+  const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia};
+  mix(opts, sizeof opts);
+#define OX_X(name, n, w) mix(t.name, (size_t)t.n * (w) * sizeof(int32_t));
+  OX_MODEL_INT_TABLES(OX_X)
+#undef OX_X
+#define OX_X(name, n, w) mix(t.name, (size_t)t.n * (w) * sizeof(double));
+  OX_MODEL_REAL_TABLES(OX_X)
+#undef OX_X
+  return h;
+}
+
+template <int N> struct AtLeast1 { static constexpr int v = N > 0 ? N : 1; };
+
+// per-thread copy of every batch field, sized by the spec's compile-time dimensions
+template <class S, typename T>
+struct LocalArena {
+  static constexpr int nq = S::Hdr::nq, nv = S::Hdr::nv, nu = S::Hdr::nu, nb = S::Hdr::nbody, nj = S::Hdr::njnt, ng = S::Hdr::ngeom,
+                       ns = S::Hdr::nsite, nM = S::Hdr::nM, ncm = AtLeast1<S::Hdr::nconmax>::v, nem = AtLeast1<S::Hdr::nefcmax>::v,
+                       nsd = S::Hdr::nsensordata;
+#define OX_X(name, cnt) T name[AtLeast1<(cnt)>::v];
+  OX_BATCH_REAL_FIELDS(OX_X)
+#undef OX_X
+#define OX_X(name, cnt) int32_t name[AtLeast1<(cnt)>::v];
+  OX_BATCH_INT_FIELDS(OX_X)
+#undef OX_X
+};
+
+// The whole life of one environment inside one launch: load state, step nsteps times on-chip, store state.
+template <class S, typename T>
+OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) {
+  using H = typename S::Hdr;
+  LocalArena<S, T> la;
+  DevBatch<T> lb;
+  lb.nenv = 1;
+  lb.stride = 1;
+#define OX_X(name, cnt) lb.name = la.name;
+  OX_BATCH_REAL_FIELDS(OX_X)
+  OX_BATCH_INT_FIELDS(OX_X)
+#undef OX_X
+  S m;
+  m.hdr.iterations = rt.iterations;
+  m.hdr.ls_iterations = rt.ls_iterations;
+  m.hdr.tolerance = rt.tolerance;
+  Env<T, S, true> env(m, lb, 0);
+  const uint32_t st = (uint32_t)g.stride, ue = (uint32_t)e;
+#define G(field, i) g.field[(uint32_t)(i) * st + ue]
+  // ---- algorithmic reads: qpos, qvel, ctrl, qacc_warmstart, time (+ applied forces)
+#pragma unroll
+  for (int i = 0; i < H::nq; i++) la.qpos[i] = G(qpos, i);
+#pragma unroll
+  for (int i = 0; i < H::nv; i++) { la.qvel[i] = G(qvel, i); la.qacc_warmstart[i] = G(qacc_warmstart, i); la.qfrc_applied[i] = G(qfrc_applied, i); }
+#pragma unroll
+  for (int i = 0; i < H::nu; i++) la.ctrl[i] = G(ctrl, i);
+#pragma unroll
+  for (int i = 0; i < 6 * H::nbody; i++) la.xfrc_applied[i] = G(xfrc_applied, i);
+  la.time[0] = G(time, 0);
+  la.diverged[0] = G(diverged, 0);
+  la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
+  la.ncon[0] = 0; la.nefc[0] = 0; la.solver_niter[0] = 0;
+#pragma unroll
+  for (int i = 0; i < H::nv; i++) la.qacc[i] = 0;
+  for (int s = 0; s < a.nsteps; s++) {
+    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
+    env.step();
+  }
+  // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
+#pragma unroll
+  for (int i = 0; i < H::nq; i++) G(qpos, i) = la.qpos[i];
+#pragma unroll
+  for (int i = 0; i < H::nv; i++) { G(qvel, i) = la.qvel[i]; G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qacc, i) = la.qacc[i]; }
+  if (a.philox) {
+#pragma unroll
+    for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+  }
+#pragma unroll
+  for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
+  G(time, 0) = la.time[0];
+  G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0]; G(diverged, 0) = la.diverged[0];
+  G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
+#undef G
+}
+
+#if defined(__CUDACC__)
+template <class S, typename T>
+__global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.nenv) return;
+  const long long step0 = a.philox ? *a.d_step : 0;
+  spec_step_env<S, T>(g, e, a, rt, step0);
+}
+#endif
+
+// ---- registry of the specialisations compiled into this library
+struct SpecEntry {
+  uint64_t hash;
+  const char* name;
+  void (*launch_f32)(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt);
+  void (*launch_f64)(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt);
+  void (*host_f32)(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);   // tests/native only
+  void (*host_f64)(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
+};
+void register_spec(const SpecEntry& e);
+const SpecEntry* find_spec(uint64_t hash);
+int spec_count();
+const SpecEntry* spec_at(int i);
+
+}  // namespace ox

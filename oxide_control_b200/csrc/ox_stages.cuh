@@ -166,76 +166,85 @@ OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// model-table load into registers: dst[k] = m.table(first + k)
+#define OX_LDM(N, dst, table, first)                         \
+  _Pragma("unroll") for (int k_ = 0; k_ < (N); k_++) (dst)[k_] = m.table((first) + k_)
+
+// Loops over the model's structure (bodies, joints, dofs, geoms, pairs, chains): fully unrolled when the model policy
+// makes their bounds compile-time constants (LOCAL specialisation), left as loops in the generic kernels.
+#define OX_MLOOP _Pragma("unroll")  // no count: full unroll iff the trip count is a compile-time constant, else none
+
 // ---------------------------------------------------------------- one environment
-template <typename T>
+// M     : model policy. DevModel<T> reads the runtime tables staged in shared memory; a generated Spec_* type
+//         (ox_specgen) answers the same calls with compile-time constants so every model loop unrolls.
+// LOCAL : false = fields live in the SoA batch arena ([element][env], coalesced); true = fields are per-thread
+//         arrays (stride 1), which after unrolling become registers.
+template <typename T, typename M = DevModel<T>, bool LOCAL = false>
 struct Env {
-  DevModel<T> m;
+  M m;
   DevBatch<T> b;
   int e;
   uint32_t S;  // env stride; every field index fits 32 bits (checked at batch creation)
 
-  OX_HD Env(const DevModel<T>& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(e_), S((uint32_t)b_.stride) {}
+  OX_HD Env(const M& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(LOCAL ? 0 : e_), S(LOCAL ? 1u : (uint32_t)b_.stride) {}
 
   // element i of a field for this env
-  OX_HD T& at(T* f, int i) const { return f[(uint32_t)i * S + (uint32_t)e]; }
-  OX_HD int32_t& ati(int32_t* f, int i) const { return f[(uint32_t)i * S + (uint32_t)e]; }
+  OX_HD T& at(T* f, int i) const { return LOCAL ? f[i] : f[(uint32_t)i * S + (uint32_t)e]; }
+  OX_HD const T& at(const T* f, int i) const { return LOCAL ? f[i] : f[(uint32_t)i * S + (uint32_t)e]; }
+  OX_HD int32_t& ati(int32_t* f, int i) const { return LOCAL ? f[i] : f[(uint32_t)i * S + (uint32_t)e]; }
   template <int N> OX_HD void ld(T* dst, const T* f, int first) const {
 #pragma unroll
-    for (int k = 0; k < N; k++) dst[k] = f[(uint32_t)(first + k) * S + (uint32_t)e];
+    for (int k = 0; k < N; k++) dst[k] = at(f, first + k);
   }
   template <int N> OX_HD void st(T* f, int first, const T* src) const {
 #pragma unroll
-    for (int k = 0; k < N; k++) f[(uint32_t)(first + k) * S + (uint32_t)e] = src[k];
-  }
-  template <int N> OX_HD void ldm(T* dst, const T* table, int first) const {  // model table (uniform)
-#pragma unroll
-    for (int k = 0; k < N; k++) dst[k] = table[first + k];
+    for (int k = 0; k < N; k++) at(f, first + k) = src[k];
   }
   OX_HD bool dis(int bit) const { return (m.h().disableflags & bit) != 0; }
 
   // ============================================================ A.1 kinematics (+ geoms, sites)
   OX_HDN void kinematics() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nbody = h.nbody, ngeom = h.ngeom, nsite = h.nsite;
-    const int32_t *jnt_type = m.jnt_type(), *jnt_qposadr = m.jnt_qposadr(), *geom_bodyid = m.geom_bodyid(), *site_bodyid = m.site_bodyid();
-    int g = 0, s = 0;
+    OX_MLOOP
     for (int i = 0; i < nbody; i++) {
       T pos[3], quat[4], mat[9];
       if (i == 0) {
         pos[0] = pos[1] = pos[2] = 0;
         quat[0] = 1; quat[1] = quat[2] = quat[3] = 0;
       } else {
-        const int jntadr = m.body_jntadr()[i], jntnum = m.body_jntnum()[i];
-        if (jntnum == 1 && jnt_type[jntadr] == OX_JNT_FREE) {
-          const int qadr = jnt_qposadr[jntadr];
+        const int jntadr = m.body_jntadr(i), jntnum = m.body_jntnum(i);
+        if (jntnum == 1 && m.jnt_type(jntadr) == OX_JNT_FREE) {
+          const int qadr = m.jnt_qposadr(jntadr);
           ld<3>(pos, b.qpos, qadr);
           ld<4>(quat, b.qpos, qadr + 3);
           normalize4(quat);
           st<3>(b.xanchor, 3 * jntadr, pos);
           T ax[3];
-          ldm<3>(ax, m.jnt_axis(), 3 * jntadr);
+          OX_LDM(3, ax, jnt_axis, 3 * jntadr);
           st<3>(b.xaxis, 3 * jntadr, ax);
         } else {
-          const int pid = m.body_parentid()[i];
+          const int pid = m.body_parentid(i);
           T ppos[3], pquat[4], pmat[9], bp[3], bq[4];
           ld<3>(ppos, b.xpos, 3 * pid);
           ld<4>(pquat, b.xquat, 4 * pid);
           ld<9>(pmat, b.xmat, 9 * pid);
-          ldm<3>(bp, m.body_pos(), 3 * i);
-          ldm<4>(bq, m.body_quat(), 4 * i);
+          OX_LDM(3, bp, body_pos, 3 * i);
+          OX_LDM(4, bq, body_quat, 4 * i);
           mat_vec3(pos, pmat, bp);
           pos[0] += ppos[0]; pos[1] += ppos[1]; pos[2] += ppos[2];
           mul_quat(quat, pquat, bq);
+          OX_MLOOP
           for (int j = 0; j < jntnum; j++) {
-            const int jid = jntadr + j, qadr = jnt_qposadr[jid], jt = jnt_type[jid];
+            const int jid = jntadr + j, qadr = m.jnt_qposadr(jid), jt = m.jnt_type(jid);
             T jaxis[3], jpos[3], anchor[3], axis[3];
-            ldm<3>(jaxis, m.jnt_axis(), 3 * jid);
-            ldm<3>(jpos, m.jnt_pos(), 3 * jid);
+            OX_LDM(3, jaxis, jnt_axis, 3 * jid);
+            OX_LDM(3, jpos, jnt_pos, 3 * jid);
             rot_vec_quat(axis, jaxis, quat);
             rot_vec_quat(anchor, jpos, quat);
             anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
             if (jt == OX_JNT_SLIDE) {
-              T dq = at(b.qpos, qadr) - m.qpos0()[qadr];
+              T dq = at(b.qpos, qadr) - m.qpos0(qadr);
               pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
             } else if (jt == OX_JNT_BALL || jt == OX_JNT_HINGE) {
               T qloc[4], qn[4], vec[3];
@@ -243,7 +252,7 @@ struct Env {
                 ld<4>(qloc, b.qpos, qadr);
                 normalize4(qloc);
               } else {
-                axis_angle2quat(qloc, jaxis, at(b.qpos, qadr) - m.qpos0()[qadr]);
+                axis_angle2quat(qloc, jaxis, at(b.qpos, qadr) - m.qpos0(qadr));
               }
               mul_quat(qn, quat, qloc);
               quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
@@ -262,8 +271,8 @@ struct Env {
       st<9>(b.xmat, 9 * i, mat);
       {  // inertial frame
         T ip[3], iq[4], v[3], q[4], im[9];
-        ldm<3>(ip, m.body_ipos(), 3 * i);
-        ldm<4>(iq, m.body_iquat(), 4 * i);
+        OX_LDM(3, ip, body_ipos, 3 * i);
+        OX_LDM(4, iq, body_iquat, 4 * i);
         mat_vec3(v, mat, ip);
         v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
         mul_quat(q, quat, iq);
@@ -271,10 +280,12 @@ struct Env {
         st<3>(b.xipos, 3 * i, v);
         st<9>(b.ximat, 9 * i, im);
       }
-      for (; g < ngeom && geom_bodyid[g] == i; g++) {  // geoms are sorted by body
+      OX_MLOOP
+      for (int g = 0; g < ngeom; g++) {
+        if (m.geom_bodyid(g) != i) continue;
         T gp[3], gq[4], v[3], q[4], gm[9];
-        ldm<3>(gp, m.geom_pos(), 3 * g);
-        ldm<4>(gq, m.geom_quat(), 4 * g);
+        OX_LDM(3, gp, geom_pos, 3 * g);
+        OX_LDM(4, gq, geom_quat, 4 * g);
         mat_vec3(v, mat, gp);
         v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
         mul_quat(q, quat, gq);
@@ -282,10 +293,12 @@ struct Env {
         st<3>(b.geom_xpos, 3 * g, v);
         st<9>(b.geom_xmat, 9 * g, gm);
       }
-      for (; s < nsite && site_bodyid[s] == i; s++) {
+      OX_MLOOP
+      for (int s = 0; s < nsite; s++) {
+        if (m.site_bodyid(s) != i) continue;
         T sp[3], sq[4], v[3], q[4], sm[9];
-        ldm<3>(sp, m.site_pos(), 3 * s);
-        ldm<4>(sq, m.site_quat(), 4 * s);
+        OX_LDM(3, sp, site_pos, 3 * s);
+        OX_LDM(4, sq, site_quat, 4 * s);
         mat_vec3(v, mat, sp);
         v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
         mul_quat(q, quat, sq);
@@ -298,36 +311,38 @@ struct Env {
 
   // ============================================================ A.2 subtree com, cinert, cdof
   OX_HDN void com_pos() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nbody = h.nbody, njnt = h.njnt;
-    const int32_t *parent = m.body_parentid(), *rootid = m.body_rootid();
-    const T *mass = m.body_mass(), *stm = m.body_subtreemass();
+    OX_MLOOP
     for (int i = 0; i < 3 * nbody; i++) at(b.subtree_com, i) = 0;
+    OX_MLOOP
     for (int i = nbody - 1; i >= 0; i--) {
       T acc[3], xi[3];
       ld<3>(acc, b.subtree_com, 3 * i);
       ld<3>(xi, b.xipos, 3 * i);
-      const T mi = mass[i];
+      const T mi = m.body_mass(i);
       acc[0] += xi[0] * mi; acc[1] += xi[1] * mi; acc[2] += xi[2] * mi;
       if (i) {
-        const int j = parent[i];
+        const int j = m.body_parentid(i);
         T pa[3];
         ld<3>(pa, b.subtree_com, 3 * j);
         pa[0] += acc[0]; pa[1] += acc[1]; pa[2] += acc[2];
         st<3>(b.subtree_com, 3 * j, pa);
       }
-      if (stm[i] < (T)OX_MINVAL) { acc[0] = xi[0]; acc[1] = xi[1]; acc[2] = xi[2]; }
-      else { const T sm = stm[i]; acc[0] /= sm; acc[1] /= sm; acc[2] /= sm; }
+      if (m.body_subtreemass(i) < (T)OX_MINVAL) { acc[0] = xi[0]; acc[1] = xi[1]; acc[2] = xi[2]; }
+      else { const T sm = m.body_subtreemass(i); acc[0] /= sm; acc[1] /= sm; acc[2] /= sm; }
       st<3>(b.subtree_com, 3 * i, acc);
     }
+    OX_MLOOP
     for (int k = 0; k < 10; k++) at(b.cinert, k) = 0;
+    OX_MLOOP
     for (int i = 1; i < nbody; i++) {
       T mat[9], xi[3], sc[3], inert[3], dif[3], res[10], tmp[9];
       ld<9>(mat, b.ximat, 9 * i);
       ld<3>(xi, b.xipos, 3 * i);
-      ld<3>(sc, b.subtree_com, 3 * rootid[i]);
-      ldm<3>(inert, m.body_inertia(), 3 * i);
-      const T ms = mass[i];
+      ld<3>(sc, b.subtree_com, 3 * m.body_rootid(i));
+      OX_LDM(3, inert, body_inertia, 3 * i);
+      const T ms = m.body_mass(i);
       dif[0] = xi[0] - sc[0]; dif[1] = xi[1] - sc[1]; dif[2] = xi[2] - sc[2];
       tmp[0] = mat[0] * inert[0]; tmp[3] = mat[1] * inert[1]; tmp[6] = mat[2] * inert[2];
       tmp[1] = mat[3] * inert[0]; tmp[4] = mat[4] * inert[1]; tmp[7] = mat[5] * inert[2];
@@ -348,16 +363,17 @@ struct Env {
       res[9] = ms;
       st<10>(b.cinert, 10 * i, res);
     }
-    const int32_t *jnt_type = m.jnt_type(), *jnt_bodyid = m.jnt_bodyid(), *jnt_dofadr = m.jnt_dofadr();
+    OX_MLOOP
     for (int j = 0; j < njnt; j++) {
-      const int bi = jnt_bodyid[j], da = jnt_dofadr[j], jt = jnt_type[j];
+      const int bi = m.jnt_bodyid(j), da = m.jnt_dofadr(j), jt = m.jnt_type(j);
       T sc[3], anchor[3], offset[3];
-      ld<3>(sc, b.subtree_com, 3 * rootid[bi]);
+      ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bi));
       ld<3>(anchor, b.xanchor, 3 * j);
       offset[0] = sc[0] - anchor[0]; offset[1] = sc[1] - anchor[1]; offset[2] = sc[2] - anchor[2];
       if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
         int skip = 0;
         if (jt == OX_JNT_FREE) {
+          OX_MLOOP
           for (int i = 0; i < 3; i++) {
             T cd[6] = {0, 0, 0, 0, 0, 0};
             cd[3 + i] = 1;
@@ -367,6 +383,7 @@ struct Env {
         }
         T xm[9];
         ld<9>(xm, b.xmat, 9 * bi);
+        OX_MLOOP
         for (int i = 0; i < 3; i++) {
           T cd[6];
           cd[0] = xm[i]; cd[1] = xm[i + 3]; cd[2] = xm[i + 6];
@@ -390,12 +407,13 @@ struct Env {
 
   // ============================================================ A.3 composite rigid body -> qM
   OX_HDN void crb() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nbody = h.nbody, nv = h.nv;
-    const int32_t *parent = m.body_parentid(), *dof_parent = m.dof_parentid(), *dof_body = m.dof_bodyid(), *Madr = m.dof_Madr();
+    OX_MLOOP
     for (int i = 0; i < 10 * nbody; i++) at(b.crb, i) = at(b.cinert, i);
+    OX_MLOOP
     for (int i = nbody - 1; i > 0; i--) {
-      const int p = parent[i];
+      const int p = m.body_parentid(i);
       if (p > 0) {
         T a[10], c[10];
         ld<10>(a, b.crb, 10 * p);
@@ -405,14 +423,16 @@ struct Env {
         st<10>(b.crb, 10 * p, a);
       }
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
       T in[10], cd[6], buf[6];
-      ld<10>(in, b.crb, 10 * dof_body[i]);
+      ld<10>(in, b.crb, 10 * m.dof_bodyid(i));
       ld<6>(cd, b.cdof, 6 * i);
       mul_inert_vec(buf, in, cd);
-      int adr = Madr[i];
-      at(b.qM, adr++) = m.dof_armature()[i] + dot6(cd, buf);
-      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) {
+      int adr = m.dof_Madr(i);
+      at(b.qM, adr++) = m.dof_armature(i) + dot6(cd, buf);
+      OX_MLOOP
+      for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) {
         T cj[6];
         ld<6>(cj, b.cdof, 6 * j);
         at(b.qM, adr++) = dot6(cj, buf);
@@ -422,19 +442,21 @@ struct Env {
 
   // ============================================================ A.4 sparse L'DL factor / solve / M*v
   OX_HDN void factor_ld(T* qLD, T* qLDiagInv) const {
-    const BlobHeader& h = m.h();
-    const int nv = h.nv, nM = h.nM;
-    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    const auto& h = m.h();
+    const int nv = h.nv;
+    OX_MLOOP
     for (int k = nv - 1; k >= 0; k--) {
-      const int Madr_kk = Madr[k];
-      int Madr_ki = Madr_kk + 1, i = dof_parent[k];
+      const int Madr_kk = m.dof_Madr(k);
+      int Madr_ki = Madr_kk + 1, i = m.dof_parentid(k);
       const T dkk = at(qLD, Madr_kk);
-      while (i >= 0) {
+      OX_MLOOP
+      for (int d_ = 1; d_ < m.dof_depth(k); d_++) {
         const T tmp = at(qLD, Madr_ki) / dkk;
-        const int rowi = Madr[i], n = (i + 1 < nv ? Madr[i + 1] : nM) - rowi;
+        const int rowi = m.dof_Madr(i), n = m.dof_depth(i);
+        OX_MLOOP
         for (int c = 0; c < n; c++) at(qLD, rowi + c) -= tmp * at(qLD, Madr_ki + c);
         at(qLD, Madr_ki) = tmp;
-        i = dof_parent[i];
+        i = m.dof_parentid(i);
         Madr_ki++;
       }
       at(qLDiagInv, k) = (T)1 / dkk;
@@ -442,36 +464,43 @@ struct Env {
   }
   OX_HDN void factor_m() const {
     const int nM = m.h().nM;
+    OX_MLOOP
     for (int i = 0; i < nM; i++) at(b.qLD, i) = at(b.qM, i);
     factor_ld(b.qLD, b.qLDiagInv);
   }
   OX_HDN void solve_ld(T* x) const {
     const int nv = m.h().nv;
-    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    OX_MLOOP
     for (int i = nv - 1; i >= 0; i--) {
-      int adr = Madr[i] + 1;
+      int adr = m.dof_Madr(i) + 1;
       const T xi = at(x, i);
-      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) at(x, j) -= at(b.qLD, adr++) * xi;
+      OX_MLOOP
+      for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) at(x, j) -= at(b.qLD, adr++) * xi;
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(x, i) *= at(b.qLDiagInv, i);
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
-      int adr = Madr[i] + 1;
+      int adr = m.dof_Madr(i) + 1;
       T xi = at(x, i);
-      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) xi -= at(b.qLD, adr++) * at(x, j);
+      OX_MLOOP
+      for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) xi -= at(b.qLD, adr++) * at(x, j);
       at(x, i) = xi;
     }
   }
   OX_HDN void mul_m(T* res, const T* v) const {
     const int nv = m.h().nv;
-    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(res, i) = 0;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
-      int adr = Madr[i];
-      const T vi = v[(uint32_t)i * S + (uint32_t)e];
+      int adr = m.dof_Madr(i);
+      const T vi = at(v, i);
       T ri = at(res, i) + at(b.qM, adr++) * vi;
-      for (int j = dof_parent[i]; j >= 0; j = dof_parent[j]) {
+      OX_MLOOP
+      for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) {
         const T mij = at(b.qM, adr++);
-        ri += mij * v[(uint32_t)j * S + (uint32_t)e];
+        ri += mij * at(v, j);
         at(res, j) += mij * vi;
       }
       at(res, i) = ri;
@@ -480,48 +509,52 @@ struct Env {
 
   // ============================================================ A.7 com velocities
   OX_HDN void com_vel() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nbody = h.nbody;
-    const int32_t *parent = m.body_parentid(), *dofadr = m.body_dofadr(), *dofnum = m.body_dofnum(), *dof_jnt = m.dof_jntid(),
-                  *jnt_type = m.jnt_type();
+    OX_MLOOP
     for (int k = 0; k < 6; k++) at(b.cvel, k) = 0;
+    OX_MLOOP
     for (int i = 1; i < nbody; i++) {
-      const int bda = dofadr[i], nd = dofnum[i];
       T cvel[6];
-      ld<6>(cvel, b.cvel, 6 * parent[i]);
-      for (int j = 0; j < nd; j++) {
-        const int jt = jnt_type[dof_jnt[bda + j]];
-        if (jt == OX_JNT_FREE) {
+      ld<6>(cvel, b.cvel, 6 * m.body_parentid(i));
+      const int jntadr = m.body_jntadr(i), jntnum = m.body_jntnum(i);
+      OX_MLOOP
+      for (int jj = 0; jj < jntnum; jj++) {
+        const int jid = jntadr + jj, jt = m.jnt_type(jid);
+        int da = m.jnt_dofadr(jid);
+        if (jt == OX_JNT_FREE) {  // translational dofs: cdof_dot = 0, velocity added first
+          OX_MLOOP
           for (int k = 0; k < 3; k++) {
             T z[6] = {0, 0, 0, 0, 0, 0}, cd[6];
-            st<6>(b.cdof_dot, 6 * (bda + k), z);
-            ld<6>(cd, b.cdof, 6 * (bda + k));
-            const T qv = at(b.qvel, bda + k);
+            st<6>(b.cdof_dot, 6 * (da + k), z);
+            ld<6>(cd, b.cdof, 6 * (da + k));
+            const T qv = at(b.qvel, da + k);
 #pragma unroll
             for (int c = 0; c < 6; c++) cvel[c] += cd[c] * qv;
           }
-          j += 3;
+          da += 3;
         }
-        if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
+        if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {  // all three cdof_dot with the same incoming velocity
           T cd[3][6];
+          OX_MLOOP
           for (int k = 0; k < 3; k++) {
             T cdd[6];
-            ld<6>(cd[k], b.cdof, 6 * (bda + j + k));
+            ld<6>(cd[k], b.cdof, 6 * (da + k));
             cross_motion(cdd, cvel, cd[k]);
-            st<6>(b.cdof_dot, 6 * (bda + j + k), cdd);
+            st<6>(b.cdof_dot, 6 * (da + k), cdd);
           }
+          OX_MLOOP
           for (int k = 0; k < 3; k++) {
-            const T qv = at(b.qvel, bda + j + k);
+            const T qv = at(b.qvel, da + k);
 #pragma unroll
             for (int c = 0; c < 6; c++) cvel[c] += cd[k][c] * qv;
           }
-          j += 2;
         } else {
           T cd[6], cdd[6];
-          ld<6>(cd, b.cdof, 6 * (bda + j));
+          ld<6>(cd, b.cdof, 6 * da);
           cross_motion(cdd, cvel, cd);
-          st<6>(b.cdof_dot, 6 * (bda + j), cdd);
-          const T qv = at(b.qvel, bda + j);
+          st<6>(b.cdof_dot, 6 * da, cdd);
+          const T qv = at(b.qvel, da);
 #pragma unroll
           for (int c = 0; c < 6; c++) cvel[c] += cd[c] * qv;
         }
@@ -532,49 +565,54 @@ struct Env {
 
   // ============================================================ passive forces
   OX_HDN void passive() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) = 0;
     if (dis(OX_DSBL_PASSIVE)) return;
-    const int32_t *jnt_type = m.jnt_type(), *qposadr = m.jnt_qposadr(), *jdofadr = m.jnt_dofadr();
+    OX_MLOOP
     for (int j = 0; j < njnt; j++) {
-      const T k = m.jnt_stiffness()[j];
+      const T k = m.jnt_stiffness(j);
       if (k == 0) continue;
-      int pa = qposadr[j], da = jdofadr[j];
-      const int jt = jnt_type[j];
+      int pa = m.jnt_qposadr(j), da = m.jnt_dofadr(j);
+      const int jt = m.jnt_type(j);
       if (jt == OX_JNT_FREE) {
-        for (int c = 0; c < 3; c++) at(b.qfrc_passive, da + c) -= k * (at(b.qpos, pa + c) - m.qpos_spring()[pa + c]);
+        OX_MLOOP
+        for (int c = 0; c < 3; c++) at(b.qfrc_passive, da + c) -= k * (at(b.qpos, pa + c) - m.qpos_spring(pa + c));
         pa += 3; da += 3;
       }
       if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
         T q[4], qs[4], dif[3];
         ld<4>(q, b.qpos, pa);
         normalize4(q);
-        ldm<4>(qs, m.qpos_spring(), pa);
+        OX_LDM(4, qs, qpos_spring, pa);
         sub_quat(dif, q, qs);
+        OX_MLOOP
         for (int c = 0; c < 3; c++) at(b.qfrc_passive, da + c) -= k * dif[c];
       } else {
-        at(b.qfrc_passive, da) -= k * (at(b.qpos, pa) - m.qpos_spring()[pa]);
+        at(b.qfrc_passive, da) -= k * (at(b.qpos, pa) - m.qpos_spring(pa));
       }
     }
-    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping()[i] * at(b.qvel, i);
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping(i) * at(b.qvel, i);
   }
 
   // ============================================================ A.8 bias forces (RNE, no acceleration)
   OX_HDN void rne() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nbody = h.nbody, nv = h.nv;
-    const int32_t *parent = m.body_parentid(), *dofadr = m.body_dofadr(), *dofnum = m.body_dofnum(), *dof_body = m.dof_bodyid();
     {
       T a0[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0};
-      if (!dis(OX_DSBL_GRAVITY)) { a0[3] = -(T)h.gravity[0]; a0[4] = -(T)h.gravity[1]; a0[5] = -(T)h.gravity[2]; }
+      if (!dis(OX_DSBL_GRAVITY)) { a0[3] = -(T)h.grav(0); a0[4] = -(T)h.grav(1); a0[5] = -(T)h.grav(2); }
       st<6>(b.cacc, 0, a0);
       st<6>(b.cfrc, 0, z);
     }
+    OX_MLOOP
     for (int i = 1; i < nbody; i++) {
-      const int bda = dofadr[i], nd = dofnum[i];
+      const int bda = m.body_dofadr(i), nd = m.body_dofnum(i);
       T cacc[6], in[10], cv[6], f[6], tmp[6], tmp1[6];
-      ld<6>(cacc, b.cacc, 6 * parent[i]);
+      ld<6>(cacc, b.cacc, 6 * m.body_parentid(i));
+      OX_MLOOP
       for (int j = 0; j < nd; j++) {
         T cdd[6];
         ld<6>(cdd, b.cdof_dot, 6 * (bda + j));
@@ -592,8 +630,9 @@ struct Env {
       for (int c = 0; c < 6; c++) f[c] += tmp1[c];
       st<6>(b.cfrc, 6 * i, f);
     }
+    OX_MLOOP
     for (int i = nbody - 1; i > 0; i--) {
-      const int p = parent[i];
+      const int p = m.body_parentid(i);
       if (p) {
         T a[6], c[6];
         ld<6>(a, b.cfrc, 6 * p);
@@ -603,36 +642,40 @@ struct Env {
         st<6>(b.cfrc, 6 * p, a);
       }
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
       T cd[6], f[6];
       ld<6>(cd, b.cdof, 6 * i);
-      ld<6>(f, b.cfrc, 6 * dof_body[i]);
+      ld<6>(f, b.cfrc, 6 * m.dof_bodyid(i));
       at(b.qfrc_bias, i) = dot6(cd, f);
     }
   }
 
   // ============================================================ A.9 actuation (joint transmission)
   OX_HDN void actuation() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, nu = h.nu;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_actuator, i) = 0;
     const bool off = dis(OX_DSBL_ACTUATION);
     const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
+    OX_MLOOP
     for (int i = 0; i < nu; i++) {
       if (off) { at(b.actuator_force, i) = 0; continue; }
-      const int j = m.actuator_trnid()[i], qa = m.jnt_qposadr()[j], da = m.jnt_dofadr()[j];
-      const T gear = m.actuator_gear()[i];
+      const int j = m.actuator_trnid(i), qa = m.jnt_qposadr(j), da = m.jnt_dofadr(j);
+      const T gear = m.actuator_gear(i);
       const T length = gear * at(b.qpos, qa), velocity = gear * at(b.qvel, da);
       T ctrl = at(b.ctrl, i);
-      if (m.actuator_ctrllimited()[i] && clamp) ctrl = ox_clip(ctrl, m.actuator_ctrlrange()[2 * i], m.actuator_ctrlrange()[2 * i + 1]);
-      const T* gp = m.actuator_gainprm() + 3 * i;
-      const T* bp = m.actuator_biasprm() + 3 * i;
+      if (m.actuator_ctrllimited(i) && clamp) ctrl = ox_clip(ctrl, m.actuator_ctrlrange(2 * i), m.actuator_ctrlrange(2 * i + 1));
+      T gp[3], bp[3];
+      OX_LDM(3, gp, actuator_gainprm, 3 * i);
+      OX_LDM(3, bp, actuator_biasprm, 3 * i);
       T gain = gp[0];
-      if (m.actuator_gaintype()[i] == OX_GAIN_AFFINE) gain += gp[1] * length + gp[2] * velocity;
+      if (m.actuator_gaintype(i) == OX_GAIN_AFFINE) gain += gp[1] * length + gp[2] * velocity;
       T bias = 0;
-      if (m.actuator_biastype()[i] == OX_BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
+      if (m.actuator_biastype(i) == OX_BIAS_AFFINE) bias = bp[0] + bp[1] * length + bp[2] * velocity;
       T force = gain * ctrl + bias;
-      if (m.actuator_forcelimited()[i]) force = ox_clip(force, m.actuator_forcerange()[2 * i], m.actuator_forcerange()[2 * i + 1]);
+      if (m.actuator_forcelimited(i)) force = ox_clip(force, m.actuator_forcerange(2 * i), m.actuator_forcerange(2 * i + 1));
       at(b.actuator_force, i) = force;
       at(b.qfrc_actuator, da) += gear * force;
     }
@@ -640,23 +683,26 @@ struct Env {
 
   // ============================================================ A.10 smooth acceleration
   OX_HDN void fwd_acceleration() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, nbody = h.nbody;
+    OX_MLOOP
     for (int i = 0; i < nv; i++)
       at(b.qfrc_smooth, i) = at(b.qfrc_passive, i) - at(b.qfrc_bias, i) + at(b.qfrc_applied, i) + at(b.qfrc_actuator, i);
-    const int32_t *dof_parent = m.dof_parentid(), *rootid = m.body_rootid();
+    OX_MLOOP
     for (int bd = 1; bd < nbody; bd++) {
       T f[6];
       ld<6>(f, b.xfrc_applied, 6 * bd);
       if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
       T xi[3], sc[3], offset[3];
       ld<3>(xi, b.xipos, 3 * bd);
-      ld<3>(sc, b.subtree_com, 3 * rootid[bd]);
+      ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bd));
       offset[0] = xi[0] - sc[0]; offset[1] = xi[1] - sc[1]; offset[2] = xi[2] - sc[2];
       int body = bd;
-      while (body && m.body_dofnum()[body] == 0) body = m.body_parentid()[body];
+      body = m.body_weldid(body);  // nearest ancestor-or-self that has dofs (0 = static)
       if (!body) continue;
-      for (int i = m.body_dofadr()[body] + m.body_dofnum()[body] - 1; i >= 0; i = dof_parent[i]) {
+      const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+      OX_MLOOP
+      for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
         T cd[6], jp[3];
         ld<6>(cd, b.cdof, 6 * i);
         cross3(jp, cd, offset);
@@ -664,6 +710,7 @@ struct Env {
         at(b.qfrc_smooth, i) += dot3(jp, f) + dot3(cd, f + 3);
       }
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qacc_smooth, i) = at(b.qfrc_smooth, i);
     solve_ld(b.qacc_smooth);
   }
@@ -715,16 +762,17 @@ struct Env {
   }
 
   OX_HDN void collision() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     int ncon = 0;
     if (!(dis(OX_DSBL_CONTACT) || dis(OX_DSBL_CONSTRAINT))) {
       const int npair = h.npair;
-      const int32_t *pg1 = m.pair_geom1(), *pg2 = m.pair_geom2(), *gtype = m.geom_type();
+      OX_MLOOP
       for (int p = 0; p < npair; p++) {
-        const int g1 = pg1[p], g2 = pg2[p], t1 = gtype[g1], t2 = gtype[g2];
-        const T margin = m.pair_margin()[p];
-        const T* size1 = m.geom_size() + 3 * g1;
-        const T* size2 = m.geom_size() + 3 * g2;
+        const int g1 = m.pair_geom1(p), g2 = m.pair_geom2(p), t1 = m.geom_type(g1), t2 = m.geom_type(g2);
+        const T margin = m.pair_margin(p);
+        T size1[3], size2[3];
+        OX_LDM(3, size1, geom_size, 3 * g1);
+        OX_LDM(3, size2, geom_size, 3 * g2);
         T pos1[3], pos2[3];
         ld<3>(pos1, b.geom_xpos, 3 * g1);
         ld<3>(pos2, b.geom_xpos, 3 * g2);
@@ -750,6 +798,7 @@ struct Env {
             T dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
             const T dist = dot3(dif, n);
             int cnt = 0;
+            OX_MLOOP
             for (int i = 0; i < 8 && cnt < 4; i++) {
               T vec[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])}, corner[3];
               mat_vec3(corner, mat2, vec);
@@ -787,23 +836,28 @@ struct Env {
             if (x1 > 1) { x1 = 1; x2 = (v - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (v + mb) / mc; }
             if (x2 > 1) { x2 = 1; x1 = (u - mb) / ma; } else if (x2 < -1) { x2 = -1; x1 = (u + mb) / ma; }
             x1 = ox_clip(x1, (T)-1, (T)1);
+            OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k] * x2; }
             if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) emit(c, p, ncon);
           } else {
             int n = 0;
             T x2 = ox_clip((v - mb) / mc, (T)-1, (T)1);
+            OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
             if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
             x2 = ox_clip((v + mb) / mc, (T)-1, (T)1);
+            OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] - axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
             if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
             if (n < 2) {
               T x1 = ox_clip((u - mb) / ma, (T)-1, (T)1);
+              OX_MLOOP
               for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k]; }
               if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
             }
             if (n < 2) {
               T x1 = ox_clip((u + mb) / ma, (T)-1, (T)1);
+              OX_MLOOP
               for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] - axis2[k]; }
               if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
             }
@@ -817,7 +871,7 @@ struct Env {
   // ============================================================ A.6 constraint assembly
   // impedance d(x), reference acceleration aref, regulariser R for one row; returns R
   OX_HD T row_params(const T* solref, const T* solimp, T pos, T margin, T diagApprox, T vel, T* aref) const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const T dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
     T imp;
     if (dmin == dmax || width <= (T)OX_MINVAL) imp = (T)0.5 * (dmin + dmax);
@@ -850,60 +904,68 @@ struct Env {
   }
 
   OX_HDN void make_constraint() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
     int nefc = 0;
     if (!dis(OX_DSBL_CONSTRAINT)) {
       if (!dis(OX_DSBL_LIMIT)) {
-        const int32_t *limited = m.jnt_limited(), *jnt_type = m.jnt_type();
+        OX_MLOOP
         for (int j = 0; j < njnt; j++) {
-          if (!limited[j]) continue;
-          const int jt = jnt_type[j];
+          if (!m.jnt_limited(j)) continue;
+          const int jt = m.jnt_type(j);
           if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
-          const int da = m.jnt_dofadr()[j];
-          const T value = at(b.qpos, m.jnt_qposadr()[j]), margin = m.jnt_margin()[j];
+          const int da = m.jnt_dofadr(j);
+          const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
+          OX_MLOOP
           for (int side = -1; side <= 1; side += 2) {
-            const T dist = side * (m.jnt_range()[2 * j + (side + 1) / 2] - value);
+            const T dist = side * (m.jnt_range(2 * j + (side + 1) / 2) - value);
             if (dist < margin) {
               const int r = nefc++;
+              OX_MLOOP
               for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
               at(b.efc_J, r * nv + da) = (T)(-side);
               const T vel = (T)(-side) * at(b.qvel, da);
               T aref;
-              const T R = row_params(m.jnt_solref() + 2 * j, m.jnt_solimp() + 5 * j, dist, margin, m.dof_invweight0()[da], vel, &aref);
+              T sr[2], si[5];
+              OX_LDM(2, sr, jnt_solref, 2 * j);
+              OX_LDM(5, si, jnt_solimp, 5 * j);
+              const T R = row_params(sr, si, dist, margin, m.dof_invweight0(da), vel, &aref);
               at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
             }
           }
         }
       }
       const int ncon = ati(b.ncon, 0);
-      const int32_t *dof_parent = m.dof_parentid(), *rootid = m.body_rootid(), *gbody = m.geom_bodyid();
       for (int c = 0; c < ncon; c++) {
         const int p = ati(b.con_pair, c);
-        const T includemargin = m.pair_margin()[p] - m.pair_gap()[p];
+        const T includemargin = m.pair_margin(p) - m.pair_gap(p);
         const T dist = at(b.con_dist, c);
         if (dist >= includemargin) continue;
-        const int dim = m.pair_dim()[p];
+        const int dim = m.pair_dim(p);
         const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
         const int r0 = nefc;
         nefc += nrow;
-        const T* fri = m.pair_friction() + 5 * p;
+        T fri[5];
+        OX_LDM(5, fri, pair_friction, 5 * p);
         T cpos[3], frame[9];
         ld<3>(cpos, b.con_pos, 3 * c);
         ld<9>(frame, b.con_frame, 9 * c);
         for (int r = r0; r < r0 + nrow; r++)
+          OX_MLOOP
           for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
         T veln = 0, velt[2] = {0, 0};
-        const int bodies[2] = {gbody[m.pair_geom2()[p]], gbody[m.pair_geom1()[p]]};
+        const int bodies[2] = {m.geom_bodyid(m.pair_geom2(p)), m.geom_bodyid(m.pair_geom1(p))};
+        OX_MLOOP
         for (int sidx = 0; sidx < 2; sidx++) {
           const T sign = sidx == 0 ? (T)1 : (T)-1;
           int body = bodies[sidx];
           T sc[3], offset[3];
-          ld<3>(sc, b.subtree_com, 3 * rootid[body]);
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
           offset[0] = cpos[0] - sc[0]; offset[1] = cpos[1] - sc[1]; offset[2] = cpos[2] - sc[2];
-          while (body && m.body_dofnum()[body] == 0) body = m.body_parentid()[body];
+          body = m.body_weldid(body);  // nearest ancestor-or-self that has dofs (0 = static)
           if (!body) continue;
-          for (int i = m.body_dofadr()[body] + m.body_dofnum()[body] - 1; i >= 0; i = dof_parent[i]) {
+          const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+      for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
             T cd[6], jp[3];
             ld<6>(cd, b.cdof, 6 * i);
             cross3(jp, cd, offset);
@@ -923,9 +985,10 @@ struct Env {
             }
           }
         }
-        const T tran = m.body_invweight0()[2 * bodies[1]] + m.body_invweight0()[2 * bodies[0]];
-        const T* solref = m.pair_solref() + 2 * p;
-        const T* solimp = m.pair_solimp() + 5 * p;
+        const T tran = m.body_invweight0(2 * bodies[1]) + m.body_invweight0(2 * bodies[0]);
+        T solref[2], solimp[5];
+        OX_LDM(2, solref, pair_solref, 2 * p);
+        OX_LDM(5, solimp, pair_solimp, 5 * p);
         if (dim == 1) {
           T aref;
           const T R = row_params(solref, solimp, dist, includemargin, tran, veln, &aref);
@@ -933,6 +996,7 @@ struct Env {
         } else {
           T arefs[4], Rfirst = 0;
           for (int k = 1; k < dim; k++)
+            OX_MLOOP
             for (int s = 0; s < 2; s++) {
               const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
               const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
@@ -977,6 +1041,7 @@ struct Env {
   // efc_force, qfrc_constraint and total cost at the current (qacc, Ma, Jaref); returns cost, gauss via pointer
   OX_HD T update_constraint(int nv, int nefc, T* gauss_out) const {
     T c = 0;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r);
@@ -985,11 +1050,13 @@ struct Env {
         const T D = at(b.efc_D, r);
         f = -D * ja;
         c += (T)0.5 * D * ja * ja;
+        OX_MLOOP
         for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, r * nv + i) * f;
       }
       at(b.efc_force, r) = f;
     }
     T g = 0;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) g += (T)0.5 * (at(b.s_Ma, i) - at(b.qfrc_smooth, i)) * (at(b.qacc, i) - at(b.qacc_smooth, i));
     *gauss_out = g;
     return c + g;
@@ -998,52 +1065,66 @@ struct Env {
   // grad, Mgrad (Newton: H^-1 grad with H = M + J' D_active J; CG: M^-1 grad); returns |grad|
   OX_HD T update_gradient(int nv, int nefc, bool newton) const {
     T gn = 0;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
       const T g = at(b.s_Ma, i) - at(b.qfrc_smooth, i) - at(b.qfrc_constraint, i);
       at(b.s_grad, i) = g;
       gn += g * g;
     }
     if (!newton) {
+      OX_MLOOP
       for (int i = 0; i < nv; i++) at(b.s_Mgrad, i) = at(b.s_grad, i);
       solve_ld(b.s_Mgrad);
       return ox_sqrt(gn);
     }
-    const int32_t *dof_parent = m.dof_parentid(), *Madr = m.dof_Madr();
     T* H = b.s_H;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
+      OX_MLOOP
       for (int j = 0; j <= i; j++) at(H, i * nv + j) = 0;
-      int adr = Madr[i];
-      for (int j = i; j >= 0; j = dof_parent[j]) at(H, i * nv + j) = at(b.qM, adr++);
+      int adr = m.dof_Madr(i);
+      OX_MLOOP
+      for (int d_ = 0, j = i; d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) at(H, i * nv + j) = at(b.qM, adr++);
     }
     for (int r = 0; r < nefc; r++) {
       if (!(at(b.s_Jaref, r) < 0)) continue;
       const T D = at(b.efc_D, r);
+      OX_MLOOP
       for (int i = 0; i < nv; i++) {
         const T ji = at(b.efc_J, r * nv + i);
         if (ji == 0) continue;
         const T s = D * ji;
+        OX_MLOOP
         for (int j = 0; j <= i; j++) at(H, i * nv + j) += s * at(b.efc_J, r * nv + j);
       }
     }
+    OX_MLOOP
     for (int j = 0; j < nv; j++) {  // Cholesky, lower
       T s = at(H, j * nv + j);
+      OX_MLOOP
       for (int k = 0; k < j; k++) { const T l = at(H, j * nv + k); s -= l * l; }
       s = ox_sqrt(ox_max(s, (T)OX_MINVAL));
       at(H, j * nv + j) = s;
       const T inv = 1 / s;
+      OX_MLOOP
       for (int i = j + 1; i < nv; i++) {
         T v = at(H, i * nv + j);
+        OX_MLOOP
         for (int k = 0; k < j; k++) v -= at(H, i * nv + k) * at(H, j * nv + k);
         at(H, i * nv + j) = v * inv;
       }
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
       T v = at(b.s_grad, i);
+      OX_MLOOP
       for (int k = 0; k < i; k++) v -= at(H, i * nv + k) * at(b.s_Mgrad, k);
       at(b.s_Mgrad, i) = v / at(H, i * nv + i);
     }
+    OX_MLOOP
     for (int i = nv - 1; i >= 0; i--) {
       T v = at(b.s_Mgrad, i);
+      OX_MLOOP
       for (int k = i + 1; k < nv; k++) v -= at(H, k * nv + i) * at(b.s_Mgrad, k);
       at(b.s_Mgrad, i) = v / at(H, i * nv + i);
     }
@@ -1053,19 +1134,22 @@ struct Env {
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
     mul_m(b.s_Mv, qacc);
     T c = 0;
-    for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (qacc[(uint32_t)i * S + (uint32_t)e] - at(b.qacc_smooth, i));
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (at(qacc, i) - at(b.qacc_smooth, i));
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
-      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * qacc[(uint32_t)i * S + (uint32_t)e];
+      OX_MLOOP
+      for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(qacc, i);
       if (v < 0) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
     return c;
   }
 
   OX_HDN void fwd_constraint() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, nefc = ati(b.nefc, 0);
     if (nefc == 0) {
+      OX_MLOOP
       for (int i = 0; i < nv; i++) {
         const T a = at(b.qacc_smooth, i);
         at(b.qacc, i) = a; at(b.qacc_warmstart, i) = a; at(b.qfrc_constraint, i) = 0;
@@ -1079,17 +1163,20 @@ struct Env {
       const T cw = cost_at(b.qacc_warmstart, nv, nefc), cs = cost_at(b.qacc_smooth, nv, nefc);
       use_smooth = cw > cs;
     }
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qacc, i) = use_smooth ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
     // initial state
     mul_m(b.s_Ma, b.qacc);
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
+      OX_MLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.qacc, i);
       at(b.s_Jaref, r) = v;
     }
     T gauss;
     T cost = update_constraint(nv, nefc, &gauss);
     T gnorm = update_gradient(nv, nefc, newton);
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
     const T tol = (T)h.tolerance;
     const T mscale = (T)h.meaninertia * (T)(nv > 1 ? nv : 1);
@@ -1100,6 +1187,7 @@ struct Env {
     while (iter < maxiter) {
       // ---- exact line search on the convex piecewise-quadratic phi(alpha)
       T snorm = 0;
+      OX_MLOOP
       for (int i = 0; i < nv; i++) { const T s = at(b.s_search, i); snorm += s * s; }
       snorm = ox_sqrt(snorm);
       if (snorm < (T)OX_MINVAL) break;
@@ -1107,10 +1195,12 @@ struct Env {
       mul_m(b.s_Mv, b.s_search);
       for (int r = 0; r < nefc; r++) {
         T v = 0;
+        OX_MLOOP
         for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.s_search, i);
         at(b.s_Jv, r) = v;
       }
       T qg1 = 0, qg2 = 0;
+      OX_MLOOP
       for (int i = 0; i < nv; i++) {
         const T s = at(b.s_search, i);
         qg1 += s * (at(b.s_Ma, i) - at(b.qfrc_smooth, i));
@@ -1131,6 +1221,7 @@ struct Env {
       const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
       if (alpha == 0) break;
       // ---- move
+      OX_MLOOP
       for (int i = 0; i < nv; i++) {
         at(b.qacc, i) += alpha * at(b.s_search, i);
         at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
@@ -1147,19 +1238,23 @@ struct Env {
       // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
       if (oldcost - cost <= 8 * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
       if (newton) {
+        OX_MLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
       } else {
         T num = 0, den = 0;
+        OX_MLOOP
         for (int i = 0; i < nv; i++) {
           num += at(b.s_grad, i) * (at(b.s_Mgrad, i) - at(b.s_Mgradold, i));
           den += at(b.s_gradold, i) * at(b.s_Mgradold, i);
         }
         T beta = num / ox_max((T)OX_MINVAL, den);
         if (beta < 0) beta = 0;
+        OX_MLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i) + beta * at(b.s_search, i);
       }
     }
     ati(b.solver_niter, 0) = iter;
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qacc_warmstart, i) = at(b.qacc, i);
   }
 
@@ -1167,47 +1262,55 @@ struct Env {
   OX_HD void obj_frame(int objtype, int id, T* pos, T* mat, int* body) const {
     if (objtype == OX_OBJ_BODY) { ld<3>(pos, b.xipos, 3 * id); ld<9>(mat, b.ximat, 9 * id); *body = id; }
     else if (objtype == OX_OBJ_XBODY) { ld<3>(pos, b.xpos, 3 * id); ld<9>(mat, b.xmat, 9 * id); *body = id; }
-    else if (objtype == OX_OBJ_GEOM) { ld<3>(pos, b.geom_xpos, 3 * id); ld<9>(mat, b.geom_xmat, 9 * id); *body = m.geom_bodyid()[id]; }
-    else { ld<3>(pos, b.site_xpos, 3 * id); ld<9>(mat, b.site_xmat, 9 * id); *body = m.site_bodyid()[id]; }
+    else if (objtype == OX_OBJ_GEOM) { ld<3>(pos, b.geom_xpos, 3 * id); ld<9>(mat, b.geom_xmat, 9 * id); *body = m.geom_bodyid(id); }
+    else { ld<3>(pos, b.site_xpos, 3 * id); ld<9>(mat, b.site_xmat, 9 * id); *body = m.site_bodyid(id); }
   }
   OX_HDN void sensors() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int ns = h.nsensor, nbody = h.nbody;
     bool have_slv = false;
+    OX_MLOOP
     for (int s = 0; s < ns; s++) {
-      const int adr = m.sensor_adr()[s], id = m.sensor_objid()[s], ot = m.sensor_objtype()[s], ty = m.sensor_type()[s];
+      const int adr = m.sensor_adr(s), id = m.sensor_objid(s), ot = m.sensor_objtype(s), ty = m.sensor_type(s);
       switch (ty) {
-        case OX_SENS_JOINTPOS: at(b.sensordata, adr) = at(b.qpos, m.jnt_qposadr()[id]); break;
-        case OX_SENS_JOINTVEL: at(b.sensordata, adr) = at(b.qvel, m.jnt_dofadr()[id]); break;
-        case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear()[id] * at(b.qpos, m.jnt_qposadr()[m.actuator_trnid()[id]]); break;
-        case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear()[id] * at(b.qvel, m.jnt_dofadr()[m.actuator_trnid()[id]]); break;
+        case OX_SENS_JOINTPOS: at(b.sensordata, adr) = at(b.qpos, m.jnt_qposadr(id)); break;
+        case OX_SENS_JOINTVEL: at(b.sensordata, adr) = at(b.qvel, m.jnt_dofadr(id)); break;
+        case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qpos, m.jnt_qposadr(m.actuator_trnid(id))); break;
+        case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qvel, m.jnt_dofadr(m.actuator_trnid(id))); break;
         case OX_SENS_ACTUATORFRC: at(b.sensordata, adr) = at(b.actuator_force, id); break;
         case OX_SENS_SUBTREECOM: for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_com, 3 * id + k); break;
         case OX_SENS_SUBTREELINVEL: {
           if (!have_slv) {
+            OX_MLOOP
             for (int i = 0; i < 3 * nbody; i++) at(b.subtree_linvel, i) = 0;
+            OX_MLOOP
             for (int bd = nbody - 1; bd > 0; bd--) {
               T xi[3], sc[3], cv[6], dif[3], v[3], acc[3], pa[3];
               ld<3>(xi, b.xipos, 3 * bd);
-              ld<3>(sc, b.subtree_com, 3 * m.body_rootid()[bd]);
+              ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bd));
               ld<6>(cv, b.cvel, 6 * bd);
               dif[0] = xi[0] - sc[0]; dif[1] = xi[1] - sc[1]; dif[2] = xi[2] - sc[2];
               cross3(v, cv, dif);
               ld<3>(acc, b.subtree_linvel, 3 * bd);
-              const T ms = m.body_mass()[bd];
+              const T ms = m.body_mass(bd);
+              OX_MLOOP
               for (int k = 0; k < 3; k++) acc[k] += ms * (cv[3 + k] + v[k]);
               st<3>(b.subtree_linvel, 3 * bd, acc);
-              const int p = m.body_parentid()[bd];
+              const int p = m.body_parentid(bd);
               ld<3>(pa, b.subtree_linvel, 3 * p);
+              OX_MLOOP
               for (int k = 0; k < 3; k++) pa[k] += acc[k];
               st<3>(b.subtree_linvel, 3 * p, pa);
             }
+            OX_MLOOP
             for (int bd = 0; bd < nbody; bd++) {
-              const T inv = 1 / ox_max((T)OX_MINVAL, m.body_subtreemass()[bd]);
+              const T inv = 1 / ox_max((T)OX_MINVAL, m.body_subtreemass(bd));
+              OX_MLOOP
               for (int k = 0; k < 3; k++) at(b.subtree_linvel, 3 * bd + k) *= inv;
             }
             have_slv = true;
           }
+          OX_MLOOP
           for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_linvel, 3 * id + k);
           break;
         }
@@ -1220,12 +1323,13 @@ struct Env {
           if (ty == OX_SENS_FRAMEQUAT) { T q[4]; mat2quat(q, mat); st<4>(b.sensordata, adr, q); break; }
           T cv[6], sc[3], dif[3], tmp[3], lin[3], out[3];
           ld<6>(cv, b.cvel, 6 * body);
-          ld<3>(sc, b.subtree_com, 3 * m.body_rootid()[body]);
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
           dif[0] = pos[0] - sc[0]; dif[1] = pos[1] - sc[1]; dif[2] = pos[2] - sc[2];
           cross3(tmp, cv, dif);
           lin[0] = cv[3] + tmp[0]; lin[1] = cv[4] + tmp[1]; lin[2] = cv[5] + tmp[2];
           const T* src = (ty == OX_SENS_FRAMELINVEL || ty == OX_SENS_VELOCIMETER) ? lin : cv;
           if (ty == OX_SENS_VELOCIMETER || ty == OX_SENS_GYRO) {
+            OX_MLOOP
             for (int k = 0; k < 3; k++) out[k] = mat[k] * src[0] + mat[3 + k] * src[1] + mat[6 + k] * src[2];
           } else { out[0] = src[0]; out[1] = src[1]; out[2] = src[2]; }
           st<3>(b.sensordata, adr, out);
@@ -1253,107 +1357,130 @@ struct Env {
   // ============================================================ A.12 integration
   OX_HD void integrate_pos(T* qpos, const T* qvel, T dt) const {
     const int njnt = m.h().njnt;
-    const int32_t *jnt_type = m.jnt_type(), *qposadr = m.jnt_qposadr(), *jdofadr = m.jnt_dofadr();
+    OX_MLOOP
     for (int j = 0; j < njnt; j++) {
-      int pa = qposadr[j], va = jdofadr[j];
-      const int jt = jnt_type[j];
+      int pa = m.jnt_qposadr(j), va = m.jnt_dofadr(j);
+      const int jt = m.jnt_type(j);
       if (jt == OX_JNT_FREE) {
-        for (int i = 0; i < 3; i++) at(qpos, pa + i) += dt * qvel[(uint32_t)(va + i) * S + (uint32_t)e];
+        OX_MLOOP
+        for (int i = 0; i < 3; i++) at(qpos, pa + i) += dt * at(qvel, va + i);
         pa += 3; va += 3;
       }
       if (jt == OX_JNT_FREE || jt == OX_JNT_BALL) {
-        T q[4], w[3] = {qvel[(uint32_t)va * S + (uint32_t)e], qvel[(uint32_t)(va + 1) * S + (uint32_t)e], qvel[(uint32_t)(va + 2) * S + (uint32_t)e]};
+        T q[4], w[3] = {at(qvel, va), at(qvel, va + 1), at(qvel, va + 2)};
         ld<4>(q, qpos, pa);
         quat_integrate(q, w, dt);
         st<4>(qpos, pa, q);
       } else {
-        at(qpos, pa) += dt * qvel[(uint32_t)va * S + (uint32_t)e];
+        at(qpos, pa) += dt * at(qvel, va);
       }
     }
   }
   OX_HD void advance(const T* qacc, const T* qvel_override) const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const T dt = (T)h.timestep;
-    for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * qacc[(uint32_t)i * S + (uint32_t)e];
+    OX_MLOOP
+    for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * at(qacc, i);
     integrate_pos(b.qpos, qvel_override ? qvel_override : b.qvel, dt);
     at(b.time, 0) += dt;
   }
   OX_HDN void euler() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, nM = h.nM;
     if (!h.any_damping || dis(OX_DSBL_EULERDAMP)) { advance(b.qacc, nullptr); return; }
     // implicit-in-velocity joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint; like MuJoCo
     // the factor of M in qLD is overwritten by the factor of M + h B.
     const T dt = (T)h.timestep;
+    OX_MLOOP
     for (int i = 0; i < nM; i++) at(b.qLD, i) = at(b.qM, i);
-    for (int i = 0; i < nv; i++) at(b.qLD, m.dof_Madr()[i]) += dt * m.dof_damping()[i];
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) at(b.qLD, m.dof_Madr(i)) += dt * m.dof_damping(i);
     factor_ld(b.qLD, b.qLDiagInv);
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.i_qacc, i) = at(b.qfrc_smooth, i) + at(b.qfrc_constraint, i);
     solve_ld(b.i_qacc);
     advance(b.i_qacc, nullptr);
   }
   // classic RK4; the Butcher matrix has one entry per row, so X_i = X_0 (+) h a_i F_{i-1}
   OX_HDN void rk4() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     const int nv = h.nv, nq = h.nq;
     const T dt = (T)h.timestep;
     const T t0 = at(b.time, 0);
     const T A[3] = {(T)0.5, (T)0.5, (T)1}, Bw[4] = {(T)(1.0 / 6), (T)(1.0 / 3), (T)(1.0 / 3), (T)(1.0 / 6)};
+    OX_MLOOP
     for (int i = 0; i < nq; i++) at(b.rk_q0, i) = at(b.qpos, i);
+    OX_MLOOP
     for (int i = 0; i < nv; i++) {
       at(b.rk_v0, i) = at(b.qvel, i);
       at(b.rk_sv, i) = Bw[0] * at(b.qvel, i);
       at(b.rk_sa, i) = Bw[0] * at(b.qacc, i);
     }
+    OX_MLOOP
     for (int st_ = 1; st_ < 4; st_++) {
       const T a = A[st_ - 1];
       // dX = a * F_{st-1}; F_{st-1} = (current qvel, current qacc)
+      OX_MLOOP
       for (int i = 0; i < nv; i++) { at(b.s_gradold, i) = a * at(b.qvel, i); at(b.s_Mgradold, i) = a * at(b.qacc, i); }
+      OX_MLOOP
       for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
       integrate_pos(b.qpos, b.s_gradold, dt);
+      OX_MLOOP
       for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i) + dt * at(b.s_Mgradold, i);
       at(b.time, 0) = t0 + a * dt;
       forward(true);
+      OX_MLOOP
       for (int i = 0; i < nv; i++) {
         at(b.rk_sv, i) += Bw[st_] * at(b.qvel, i);
         at(b.rk_sa, i) += Bw[st_] * at(b.qacc, i);
       }
     }
     at(b.time, 0) = t0;
+    OX_MLOOP
     for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
+    OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i);
     advance(b.rk_sa, b.rk_sv);
   }
 
   // ============================================================ reset / checks / step
   OX_HDN void reset_data() const {
-    const BlobHeader& h = m.h();
-    for (int i = 0; i < h.nq; i++) at(b.qpos, i) = m.qpos0()[i];
+    const auto& h = m.h();
+    OX_MLOOP
+    for (int i = 0; i < h.nq; i++) at(b.qpos, i) = m.qpos0(i);
+    OX_MLOOP
     for (int i = 0; i < h.nv; i++) { at(b.qvel, i) = 0; at(b.qfrc_applied, i) = 0; at(b.qacc_warmstart, i) = 0; at(b.qacc, i) = 0; }
+    OX_MLOOP
     for (int i = 0; i < h.nu; i++) at(b.ctrl, i) = 0;
+    OX_MLOOP
     for (int i = 0; i < 6 * h.nbody; i++) at(b.xfrc_applied, i) = 0;
     at(b.time, 0) = 0;
     ati(b.ncon, 0) = 0; ati(b.nefc, 0) = 0; ati(b.solver_niter, 0) = 0;
   }
   OX_HD bool bad_state() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     bool bad = false;
+    OX_MLOOP
     for (int i = 0; i < h.nq; i++) bad |= ox_bad(at(b.qpos, i));
+    OX_MLOOP
     for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qvel, i));
     return bad;
   }
   OX_HD bool bad_acc() const {
-    const BlobHeader& h = m.h();
+    const auto& h = m.h();
     bool bad = false;
+    OX_MLOOP
     for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qacc, i));
     return bad;
   }
   OX_HD void fill_ctrl_philox(uint64_t seed, int64_t genv, int64_t stepno) const {
     const int nu = m.h().nu;
+    OX_MLOOP
     for (int g = 0; g * 4 < nu; g++) {
       uint32_t out[4];
       philox4x32_10((uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)stepno, (uint32_t)g, (uint32_t)seed,
                     (uint32_t)(seed >> 32), out);
+      OX_MLOOP
       for (int k = 0; k < 4 && g * 4 + k < nu; k++)
         at(b.ctrl, g * 4 + k) = (T)(int32_t)((out[k] >> 9) * 2u + 1u) * (T)(1.0 / 8388608.0) - (T)1;
     }

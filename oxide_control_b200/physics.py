@@ -169,7 +169,7 @@ class BatchedPhysics:
 
     def __init__(self, model: Model, nenv: int, *, precision: str = "f32", device: int = 0, mode: str = "fused",
                  iterations: int = 0, ls_iterations: int = 0, tolerance: float = -1.0, use_graph: bool = False,
-                 block_threads: int = 0, env_id_offset: int = 0):
+                 block_threads: int = 0, env_id_offset: int = 0, specialize: bool = True):
         self.model = model
         cfg = A.BatchConfig()
         A.lib().ox_batch_config_default(C.byref(cfg))
@@ -183,6 +183,7 @@ class BatchedPhysics:
         cfg.use_graph = int(use_graph)
         cfg.block_threads = block_threads
         cfg.env_id_offset = env_id_offset
+        cfg.specialize = int(specialize)
         self.precision = precision
         self.nenv = nenv
         self._h = C.c_void_p()
@@ -310,6 +311,9 @@ class BatchedPhysics:
         out = (C.c_double * 4)()
         _check(A.lib().ox_batch_stats(self._h, out))
         return {"sum_ncon": out[0], "sum_nefc": out[1], "sum_niter": out[2], "diverged": out[3]}
+
+    def kernel_name(self) -> str:
+        return A.lib().ox_batch_kernel_name(self._h).decode()
 
     def launch_count(self) -> int:
         return int(A.lib().ox_batch_launch_count(self._h))

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../oxide_control_b200/csrc/ox_arena.h"
+#include "../../oxide_control_b200/csrc/ox_spec.cuh"
 #include "../../oxide_control_b200/csrc/ox_stages.cuh"
 
 using namespace ox;
@@ -19,6 +20,8 @@ struct hc_batch {
   DevBatch<float> bf{};
   DevBatch<double> bd{};
   std::map<int, FieldInfo> fields;
+  uint64_t hash = 0;
+  SpecRuntime rt{};
 };
 
 template <typename T, typename F>
@@ -37,6 +40,10 @@ HC_API hc_batch* hc_create(const ox_model_tables* t, int nenv, int precision, in
   b->nenv = nenv;
   b->stride = (nenv + 31) / 32 * 32;
   b->f64 = precision == OX_F64;
+  b->hash = model_hash(*t);
+  b->rt.iterations = iterations > 0 ? iterations : t->iterations;
+  b->rt.ls_iterations = ls_iterations > 0 ? ls_iterations : t->ls_iterations;
+  b->rt.tolerance = tolerance >= 0 ? tolerance : t->tolerance;
   b->blob = b->f64 ? build_blob<double>(*t, iterations, ls_iterations, tolerance) : build_blob<float>(*t, iterations, ls_iterations, tolerance);
   size_t bytes = b->f64 ? layout_arena<double>(*t, b->stride, nullptr, nullptr, nullptr) : layout_arena<float>(*t, b->stride, nullptr, nullptr, nullptr);
   b->arena.assign(bytes + 256, 0);
@@ -60,6 +67,19 @@ HC_API void hc_step(hc_batch* b, int nsteps, int philox, uint64_t seed, int64_t 
     env.step();
   })
 }
+// the model-specialised step (csrc/ox_spec.cuh + generated spec_<name>.cu) run on the host; returns 0 if no spec matches
+HC_API int hc_step_spec(hc_batch* b, int nsteps, int philox, uint64_t seed, int64_t env_off, int64_t step0) {
+  const SpecEntry* sp = find_spec(b->hash);
+  if (!sp || !sp->host_f32) return 0;
+  StepArgs a;
+  a.nsteps = nsteps; a.philox = philox; a.seed = seed; a.env_id_offset = env_off; a.d_step = nullptr;
+  for (int e = 0; e < b->nenv; e++) {
+    if (b->f64) sp->host_f64(b->bd, e, a, b->rt, step0);
+    else sp->host_f32(b->bf, e, a, b->rt, step0);
+  }
+  return 1;
+}
+HC_API int hc_spec_count() { return spec_count(); }
 // raw SoA access: element i of env e of field id is ptr[i*stride + e]
 HC_API void* hc_field(hc_batch* b, int field, int* count, int* is_int) {
   auto it = b->fields.find(field);

@@ -35,13 +35,21 @@ def oracle_rollout(model, qpos, qvel, nsteps, warm=0, env_off=0):
     return tr(out_q), tr(out_v), tr(out_a), ods
 
 
+MODES = {  # which kernels a batch launches
+    "spec": dict(mode="fused", specialize=True),        # model-specialised fused kernel (csrc/ox_spec.cuh); state + qacc + sensors only
+    "fused": dict(mode="fused", specialize=False),      # generic fused kernel, all mjData arrays written
+    "staged": dict(mode="staged"),                      # generic, one kernel per mj_step stage
+}
+
+
 @pytest.mark.parametrize("name", CONFIGS)
-@pytest.mark.parametrize("mode", ["fused", "staged"])
+@pytest.mark.parametrize("mode", list(MODES))
 def test_single_step_fp64(ox, name, mode):
     model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
     nenv = 256
     qpos, qvel = random_state(model, nenv, seed=11)
-    b = ox.BatchedPhysics(model, nenv, precision="f64", mode=mode)
+    b = ox.BatchedPhysics(model, nenv, precision="f64", **MODES[mode])
+    assert (b.kernel_name() == name) == (mode == "spec")
     b.set("qpos", qpos); b.set("qvel", qvel)
     b.ctrl_philox(True, SEED)
     b.step(1); b.sync()
@@ -49,8 +57,10 @@ def test_single_step_fp64(ox, name, mode):
     assert rel_err(b.get("qpos"), oq[0]) <= 1e-9
     assert rel_err(b.get("qvel"), ov[0]) <= 1e-9
     assert rel_err(b.get("qacc"), oa[0]) <= 1e-9
-    # derived arrays of the forward pass inside the step (pre-integration state), stage by stage
-    for f in STAGE_FIELDS:
+    # derived arrays of the forward pass inside the step (pre-integration state), stage by stage; the specialised kernel
+    # keeps them in registers and writes back only the algorithmic state, qacc, sensordata and the counters
+    fields = ["qacc", "qacc_warmstart", "sensordata", "ctrl", "time"] if mode == "spec" else STAGE_FIELDS
+    for f in fields:
         ref = np.stack([od.field(f) for od in ods])
         assert rel_err(b.get(f), ref) <= 1e-9, f
     assert np.array_equal(b.get("ncon")[:, 0], [od.int("ncon") for od in ods])

@@ -72,3 +72,24 @@ def test_autoreset_on_nan_matches_oracle():
     od.field("qpos")[:] = qpos[2]; od.field("qvel")[:] = qvel[2]
     od.step(); od.step()
     assert od.int("diverged") == 1 and rel_err(hb.get("qpos")[2], od.field("qpos")) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "acrobot", "cheetah", "humanoid"])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_model_specialised_step_is_bit_identical_to_generic(name, prec):
+    """The generated specialisation (ox_specgen + csrc/ox_spec.cuh) runs the same stage code with compile-time tables
+    and per-thread storage; on the host it must reproduce the generic path bit for bit."""
+    import ctypes as C
+    from support import hostcheck_lib
+    L = hostcheck_lib()
+    L.hc_step_spec.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64]
+    m = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    qpos, qvel = random_state(m, 5, seed=31)
+    ha, hb = HostBatch(m, 5, prec), HostBatch(m, 5, prec)
+    for h in (ha, hb):
+        h.set("qpos", qpos); h.set("qvel", qvel)
+    for s in range(0, 40, 4):
+        ha.step(4, True, SEED, 10, s)
+        assert L.hc_step_spec(hb.h, 4, 1, SEED, 10, s) == 1, "no specialisation compiled for this model"
+        for f in ("qpos", "qvel", "qacc", "qacc_warmstart", "time", "sensordata", "ctrl", "ncon", "nefc", "solver_niter", "diverged"):
+            assert np.array_equal(ha.get(f), hb.get(f)), (f, s)
