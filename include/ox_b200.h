@@ -93,7 +93,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(geom_type, ngeom, 1) X(geom_bodyid, ngeom, 1) X(geom_contype, ngeom, 1)                        \
   X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
   X(site_bodyid, nsite, 1)                                                                          \
-  X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1)   \
+  X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1) X(pair_conadr, npair, 1)   \
   X(actuator_trnid, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
   X(actuator_ctrllimited, nu, 1) X(actuator_forcelimited, nu, 1)                                    \
   X(sensor_type, nsensor, 1) X(sensor_objtype, nsensor, 1) X(sensor_objid, nsensor, 1)             \
@@ -172,7 +172,7 @@ typedef struct ox_batch_config {
   int64_t env_id_offset; /* global env id of env 0 (multi-GPU sharding; keys the Philox control stream) */
   double tolerance;      /* <0 = model's */
   int32_t specialize;    /* 1 (default): use the model-specialised step kernel when one was compiled in (fused mode) */
-  int32_t reserved_;
+  int32_t lanes_per_warp; /* active envs per warp, 1..32; 0 = auto (thin warps while the batch cannot fill every SM scheduler) */
 } ox_batch_config;
 
 OX_API void ox_batch_config_default(ox_batch_config* cfg);

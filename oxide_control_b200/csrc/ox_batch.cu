@@ -53,6 +53,18 @@ __device__ __forceinline__ const unsigned char* stage_model(const unsigned char*
   return ox_smem;
 }
 
+// env owned by this thread, or -1. Warps may be deliberately under-filled (b.lanes < 32 active lanes per warp): at small
+// batch sizes the step is latency-bound with far fewer warps than SM sub-partitions (8192 envs = 256 full warps for 592
+// schedulers), so spreading the envs over more, thinner warps uses the idle schedulers and shortens every warp's
+// divergent max-over-lanes critical path.
+template <typename T>
+__device__ __forceinline__ int env_index(const DevBatch<T>& b) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (lane >= b.lanes) return -1;
+  const int e = warp * b.lanes + lane;
+  return e < b.nenv ? e : -1;
+}
+
 enum Stage { ST_CTRL = 0, ST_CHECK, ST_KIN, ST_CRB, ST_COLLIDE, ST_VEL, ST_EFC, ST_ACC, ST_SOLVE, ST_SENSE, ST_INTEGRATE, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {"ctrl_rng", "check_pos_vel", "kin_com", "crb_ldl", "collide", "vel_bias",
                                              "make_efc", "act_smooth_acc", "solve", "sensors_check_acc", "integrate"};
@@ -60,8 +72,8 @@ static const char* kStageNames[ST_COUNT] = {"ctrl_rng", "check_pos_vel", "kin_co
 template <typename T>
 __global__ void k_step_fused(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, StepArgs a) {
   DevModel<T> m{stage_model(gblob, bytes)};
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
+  const int e = env_index(b);
+  if (e < 0) return;
   Env<T> env(m, b, e);
   const long long step0 = a.philox ? *a.d_step : 0;
   for (int s = 0; s < a.nsteps; s++) {
@@ -73,8 +85,8 @@ __global__ void k_step_fused(const unsigned char* __restrict__ gblob, int bytes,
 template <typename T>
 __global__ void k_forward_fused(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b) {
   DevModel<T> m{stage_model(gblob, bytes)};
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
+  const int e = env_index(b);
+  if (e < 0) return;
   Env<T> env(m, b, e);
   env.forward(false);
 }
@@ -82,8 +94,8 @@ __global__ void k_forward_fused(const unsigned char* __restrict__ gblob, int byt
 template <typename T, int STAGE>
 __global__ void k_stage(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, StepArgs a) {
   DevModel<T> m{stage_model(gblob, bytes)};
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
+  const int e = env_index(b);
+  if (e < 0) return;
   Env<T> env(m, b, e);
   if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, *a.d_step);
   if (STAGE == ST_CHECK) {
@@ -111,8 +123,8 @@ __global__ void k_bump(long long* d_step, int n) { *d_step += n; }
 template <typename T>
 __global__ void k_reset(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, const uint8_t* __restrict__ mask) {
   DevModel<T> m{stage_model(gblob, bytes)};
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= b.nenv) return;
+  const int e = env_index(b);
+  if (e < 0) return;
   if (mask && !mask[e]) return;
   Env<T> env(m, b, e);
   env.reset_data();
@@ -139,7 +151,7 @@ using namespace ox;
 struct ox_batch {
   const ox_model* model = nullptr;
   ox_batch_config cfg{};
-  int nenv = 0, stride = 0, block = 32, grid = 0;
+  int nenv = 0, stride = 0, block = 32, grid = 0, lanes = 32;
   bool f64 = false;
   cudaStream_t stream = nullptr;
   unsigned char* arena = nullptr;
@@ -378,7 +390,7 @@ extern "C" {
 void ox_batch_config_default(ox_batch_config* cfg) {
   if (!cfg) return;
   cfg->nenv = 1; cfg->device = 0; cfg->precision = OX_F32; cfg->mode = OX_MODE_FUSED; cfg->iterations = 0; cfg->ls_iterations = 0;
-  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1; cfg->specialize = 1;
+  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1; cfg->specialize = 1; cfg->lanes_per_warp = 0;
 }
 
 ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batch** out) {
@@ -405,11 +417,16 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   int block = cfg->block_threads;
   if (block <= 0) {
     const int warps = (b->nenv + 31) / 32;
-    block = warps <= 4 * 148 ? 32 : (warps <= 8 * 148 ? 64 : 128);
+    block = warps <= 8 * 148 ? 32 : (warps <= 16 * 148 ? 64 : 128);
   }
   if (block % 32 != 0 || block > 1024) { ox::set_error("ox_batch_create: block_threads must be a multiple of 32, <= 1024"); return OX_ERR_INVALID; }
   b->block = block;
-  b->grid = (b->nenv + block - 1) / block;
+  int lanes = cfg->lanes_per_warp;
+  if (lanes <= 0) lanes = 32;  // measured on B200 (profiles/r1_notes.md): thinner warps lose to L1 pressure from per-thread storage
+  if (lanes > 32) { ox::set_error("ox_batch_create: lanes_per_warp must be in 1..32"); return OX_ERR_INVALID; }
+  b->lanes = lanes;
+  const int nwarps = (b->nenv + lanes - 1) / lanes, wpb = block / 32;
+  b->grid = (nwarps + wpb - 1) / wpb;
   CU_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   const ox_model_tables& t = m->t;
   std::vector<unsigned char> blob = b->f64 ? build_blob<double>(t, cfg->iterations, cfg->ls_iterations, cfg->tolerance)
@@ -430,8 +447,8 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
                           : layout_arena<float>(t, b->stride, nullptr, nullptr, nullptr);
   CU_TRY(cudaMalloc(&b->arena, b->arena_bytes));
   CU_TRY(cudaMemset(b->arena, 0, b->arena_bytes));
-  if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; }
-  else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; }
+  if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; b->bd.lanes = b->lanes; }
+  else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; b->bf.lanes = b->lanes; }
   if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
     b->spec = ox::find_spec(ox::model_hash(t));
     b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;

@@ -114,16 +114,17 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   X(qacc, nv) X(qfrc_constraint, nv) X(s_Ma, nv) X(s_Jaref, nem) X(s_grad, nv) X(s_Mgrad, nv)          \
   X(s_search, nv) X(s_Mv, nv) X(s_Jv, nem) X(s_H, nv * nv) X(s_gradold, nv) X(s_Mgradold, nv)          \
   /* integrator scratch */                                                                             \
-  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(i_qacc, nv)                                    \
+  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(rk_t0, 1) X(i_qacc, nv)                                    \
   X(sensordata, nsd) X(subtree_linvel, 3 * nb)
 
 #define OX_BATCH_INT_FIELDS(X) \
-  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1)
+  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(con_active, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1)
 
 template <typename T>
 struct DevBatch {
   int32_t nenv;
   int32_t stride;  // env stride of every field (nenv rounded up to a multiple of 32)
+  int32_t lanes;   // active lanes per warp (32 = full warps)
 #define OX_X(name, cnt) T* name;
   OX_BATCH_REAL_FIELDS(OX_X)
 #undef OX_X

@@ -954,7 +954,7 @@ ox_model* compile_mjcf(const std::string& xml) {
             }
             if (dim != 1 && dim != 3) cfail("contact dimension " + std::to_string(dim) + " (torsional/rolling friction) is outside the supported subset (condim 1 or 3)");
             M->v_pair_geom1.push_back(ga); M->v_pair_geom2.push_back(gb);
-            M->v_pair_dim.push_back(dim); M->v_pair_maxcon.push_back(maxcon);
+            M->v_pair_dim.push_back(dim); M->v_pair_maxcon.push_back(maxcon); M->v_pair_conadr.push_back(nconmax);
             double f5[5] = {fri[0], fri[0], fri[1], fri[2], fri[2]};
             for (double v : f5) M->v_pair_friction.push_back(v);
             for (double v : solref) M->v_pair_solref.push_back(v);

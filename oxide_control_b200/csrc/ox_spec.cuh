@@ -45,29 +45,34 @@ inline uint64_t model_hash(const ox_model_tables& t) {
 
 template <int N> struct AtLeast1 { static constexpr int v = N > 0 ? N : 1; };
 
-// per-thread copy of every batch field, sized by the spec's compile-time dimensions
-template <class S, typename T>
-struct LocalArena {
-  static constexpr int nq = S::Hdr::nq, nv = S::Hdr::nv, nu = S::Hdr::nu, nb = S::Hdr::nbody, nj = S::Hdr::njnt, ng = S::Hdr::ngeom,
-                       ns = S::Hdr::nsite, nM = S::Hdr::nM, ncm = AtLeast1<S::Hdr::nconmax>::v, nem = AtLeast1<S::Hdr::nefcmax>::v,
-                       nsd = S::Hdr::nsensordata;
-#define OX_X(name, cnt) T name[AtLeast1<(cnt)>::v];
-  OX_BATCH_REAL_FIELDS(OX_X)
-#undef OX_X
-#define OX_X(name, cnt) int32_t name[AtLeast1<(cnt)>::v];
-  OX_BATCH_INT_FIELDS(OX_X)
-#undef OX_X
-};
-
 // The whole life of one environment inside one launch: load state, step nsteps times on-chip, store state.
 template <class S, typename T>
 OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) {
   using H = typename S::Hdr;
-  LocalArena<S, T> la;
+  // per-thread copy of every batch field, sized by the spec's compile-time dimensions. One local array per field (not one
+  // struct): each array whose indices all fold to constants after unrolling is promoted to registers independently;
+  // only the runtime-indexed ones (contact / constraint rows and what the contact Jacobian walk reads) stay in local memory.
+  constexpr int nq = H::nq, nv = H::nv, nu = H::nu, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
+                ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata;
+  struct LaView {  // names only; the arrays themselves are the separate locals below
+#define OX_X(name, cnt) T* name;
+    OX_BATCH_REAL_FIELDS(OX_X)
+#undef OX_X
+#define OX_X(name, cnt) int32_t* name;
+    OX_BATCH_INT_FIELDS(OX_X)
+#undef OX_X
+  } la;
+#define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v]; la.name = loc_##name;
+  OX_BATCH_REAL_FIELDS(OX_X)
+#undef OX_X
+#define OX_X(name, cnt) int32_t loc_##name[AtLeast1<(cnt)>::v]; la.name = loc_##name;
+  OX_BATCH_INT_FIELDS(OX_X)
+#undef OX_X
   DevBatch<T> lb;
   lb.nenv = 1;
   lb.stride = 1;
-#define OX_X(name, cnt) lb.name = la.name;
+  lb.lanes = 32;
+#define OX_X(name, cnt) lb.name = loc_##name;
   OX_BATCH_REAL_FIELDS(OX_X)
   OX_BATCH_INT_FIELDS(OX_X)
 #undef OX_X
@@ -117,7 +122,9 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #if defined(__CUDACC__)
 template <class S, typename T>
 __global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (lane >= g.lanes) return;  // deliberately under-filled warps at small batch sizes (see env_index in ox_batch.cu)
+  const int e = warp * g.lanes + lane;
   if (e >= g.nenv) return;
   const long long step0 = a.philox ? *a.d_step : 0;
   spec_step_env<S, T>(g, e, a, rt, step0);

@@ -752,18 +752,27 @@ struct Env {
     normalize3(frame + 3);
     cross3(frame + 6, frame, frame + 3);
   }
-  OX_HD void emit(Con& c, int p, int& ncon) const {
+  // Store one contact. Generic kernels compact (MuJoCo's contact list); the specialised kernels give every narrowphase
+  // test site k of pair p its own slot pair_conadr(p) + k, so that all contact indices are compile-time constants and the
+  // contact arrays live in registers; walking the slots in order visits the contacts in the same order as the compact list.
+  OX_HD void emit(Con& c, int p, int k, int& ncon) const {
     make_frame(c.frame);
-    at(b.con_dist, ncon) = c.dist;
-    st<3>(b.con_pos, 3 * ncon, c.pos);
-    st<9>(b.con_frame, 9 * ncon, c.frame);
-    ati(b.con_pair, ncon) = p;
+    const int idx = LOCAL ? m.pair_conadr(p) + k : ncon;
+    at(b.con_dist, idx) = c.dist;
+    st<3>(b.con_pos, 3 * idx, c.pos);
+    st<9>(b.con_frame, 9 * idx, c.frame);
+    ati(b.con_pair, idx) = p;
+    if (LOCAL) ati(b.con_active, idx) = 1;
     ncon++;
   }
 
   OX_HDN void collision() const {
     const auto& h = m.h();
     int ncon = 0;
+    if (LOCAL) {
+      OX_MLOOP
+      for (int i = 0; i < h.nconmax; i++) ati(b.con_active, i) = 0;
+    }
     if (!(dis(OX_DSBL_CONTACT) || dis(OX_DSBL_CONSTRAINT))) {
       const int npair = h.npair;
       OX_MLOOP
@@ -780,16 +789,17 @@ struct Env {
           T n[3] = {at(b.geom_xmat, 9 * g1 + 2), at(b.geom_xmat, 9 * g1 + 5), at(b.geom_xmat, 9 * g1 + 8)};
           if (t2 == OX_GEOM_SPHERE) {
             Con c;
-            if (plane_sphere(c, margin, pos1, n, pos2, size2[0])) emit(c, p, ncon);
+            if (plane_sphere(c, margin, pos1, n, pos2, size2[0])) emit(c, p, 0, ncon);
           } else if (t2 == OX_GEOM_CAPSULE) {
             T axis[3] = {at(b.geom_xmat, 9 * g2 + 2), at(b.geom_xmat, 9 * g2 + 5), at(b.geom_xmat, 9 * g2 + 8)};
             const T hl = size2[1];
+#pragma unroll
             for (int sgn = 1; sgn >= -1; sgn -= 2) {
               T pt[3] = {pos2[0] + sgn * axis[0] * hl, pos2[1] + sgn * axis[1] * hl, pos2[2] + sgn * axis[2] * hl};
               Con c;
               if (plane_sphere(c, margin, pos1, n, pt, size2[0])) {
                 c.frame[3] = axis[0]; c.frame[4] = axis[1]; c.frame[5] = axis[2];
-                emit(c, p, ncon);
+                emit(c, p, sgn > 0 ? 0 : 1, ncon);
               }
             }
           } else if (t2 == OX_GEOM_BOX) {
@@ -809,20 +819,20 @@ struct Env {
               c.frame[0] = n[0]; c.frame[1] = n[1]; c.frame[2] = n[2]; c.frame[3] = 0; c.frame[4] = 0; c.frame[5] = 0;
               const T s = -c.dist / 2;
               c.pos[0] = corner[0] + pos2[0] + n[0] * s; c.pos[1] = corner[1] + pos2[1] + n[1] * s; c.pos[2] = corner[2] + pos2[2] + n[2] * s;
-              emit(c, p, ncon);
+              if (cnt == 0) emit(c, p, 0, ncon); else if (cnt == 1) emit(c, p, 1, ncon); else if (cnt == 2) emit(c, p, 2, ncon); else emit(c, p, 3, ncon);
               cnt++;
             }
           }
         } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_SPHERE) {
           Con c;
-          if (sphere_sphere(c, margin, pos1, size1[0], pos2, size2[0])) emit(c, p, ncon);
+          if (sphere_sphere(c, margin, pos1, size1[0], pos2, size2[0])) emit(c, p, 0, ncon);
         } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_CAPSULE) {
           T axis[3] = {at(b.geom_xmat, 9 * g2 + 2), at(b.geom_xmat, 9 * g2 + 5), at(b.geom_xmat, 9 * g2 + 8)};
           T vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
           const T x = ox_clip(dot3(axis, vec), -size2[1], size2[1]);
           vec[0] = pos2[0] + axis[0] * x; vec[1] = pos2[1] + axis[1] * x; vec[2] = pos2[2] + axis[2] * x;
           Con c;
-          if (sphere_sphere(c, margin, pos1, size1[0], vec, size2[0])) emit(c, p, ncon);
+          if (sphere_sphere(c, margin, pos1, size1[0], vec, size2[0])) emit(c, p, 0, ncon);
         } else if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {
           T axis1[3] = {at(b.geom_xmat, 9 * g1 + 2) * size1[1], at(b.geom_xmat, 9 * g1 + 5) * size1[1], at(b.geom_xmat, 9 * g1 + 8) * size1[1]};
           T axis2[3] = {at(b.geom_xmat, 9 * g2 + 2) * size2[1], at(b.geom_xmat, 9 * g2 + 5) * size2[1], at(b.geom_xmat, 9 * g2 + 8) * size2[1]};
@@ -838,28 +848,28 @@ struct Env {
             x1 = ox_clip(x1, (T)-1, (T)1);
             OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k] * x2; }
-            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) emit(c, p, ncon);
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) emit(c, p, 0, ncon);
           } else {
             int n = 0;
             T x2 = ox_clip((v - mb) / mc, (T)-1, (T)1);
             OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
-            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { if (n == 0) emit(c, p, 0, ncon); else emit(c, p, 1, ncon); n++; }
             x2 = ox_clip((v + mb) / mc, (T)-1, (T)1);
             OX_MLOOP
             for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] - axis1[k]; vec2[k] = pos2[k] + axis2[k] * x2; }
-            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+            if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { if (n == 0) emit(c, p, 0, ncon); else emit(c, p, 1, ncon); n++; }
             if (n < 2) {
               T x1 = ox_clip((u - mb) / ma, (T)-1, (T)1);
               OX_MLOOP
               for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] + axis2[k]; }
-              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { if (n == 0) emit(c, p, 0, ncon); else emit(c, p, 1, ncon); n++; }
             }
             if (n < 2) {
               T x1 = ox_clip((u + mb) / ma, (T)-1, (T)1);
               OX_MLOOP
               for (int k = 0; k < 3; k++) { vec1[k] = pos1[k] + axis1[k] * x1; vec2[k] = pos2[k] - axis2[k]; }
-              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { emit(c, p, ncon); n++; }
+              if (sphere_sphere(c, margin, vec1, size1[0], vec2, size2[0])) { if (n == 0) emit(c, p, 0, ncon); else emit(c, p, 1, ncon); n++; }
             }
           }
         }
@@ -903,6 +913,90 @@ struct Env {
     return ox_max((T)OX_MINVAL, (1 - imp) * diagApprox / imp);
   }
 
+  // rows of one contact (pyramidal cone or frictionless): Jacobian, impedance, reference acceleration
+  OX_HD void contact_rows(int c, int p, int& nefc) const {
+    const auto& h = m.h();
+    const int nv = h.nv;
+      const T includemargin = m.pair_margin(p) - m.pair_gap(p);
+      const T dist = at(b.con_dist, c);
+      if (dist >= includemargin) return;
+      const int dim = m.pair_dim(p);
+      const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+      const int r0 = nefc;
+      nefc += nrow;
+      T fri[5];
+      OX_LDM(5, fri, pair_friction, 5 * p);
+      T cpos[3], frame[9];
+      ld<3>(cpos, b.con_pos, 3 * c);
+      ld<9>(frame, b.con_frame, 9 * c);
+      OX_MLOOP
+      for (int rr = 0; rr < nrow; rr++) {
+        const int r = r0 + rr;
+        OX_MLOOP
+        for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
+      }
+      T veln = 0, velt[2] = {0, 0};
+      const int bodies[2] = {m.geom_bodyid(m.pair_geom2(p)), m.geom_bodyid(m.pair_geom1(p))};
+      OX_MLOOP
+      for (int sidx = 0; sidx < 2; sidx++) {
+        const T sign = sidx == 0 ? (T)1 : (T)-1;
+        int body = bodies[sidx];
+        T sc[3], offset[3];
+        ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
+        offset[0] = cpos[0] - sc[0]; offset[1] = cpos[1] - sc[1]; offset[2] = cpos[2] - sc[2];
+        body = m.body_weldid(body);  // nearest ancestor-or-self that has dofs (0 = static)
+        if (!body) continue;  // static body: no dofs on this side
+        const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+        OX_MLOOP
+        for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
+          T cd[6], jp[3];
+          ld<6>(cd, b.cdof, 6 * i);
+          cross3(jp, cd, offset);
+          jp[0] = sign * (jp[0] + cd[3]); jp[1] = sign * (jp[1] + cd[4]); jp[2] = sign * (jp[2] + cd[5]);
+          const T jn = dot3(frame, jp);
+          const T qv = at(b.qvel, i);
+          veln += jn * qv;
+          if (dim == 1) {
+            at(b.efc_J, r0 * nv + i) += jn;
+          } else {
+            OX_MLOOP
+            for (int k = 1; k < dim; k++) {
+              const T jt = dot3(frame + 3 * k, jp) * fri[k - 1];
+              velt[k - 1] += jt * qv;
+              at(b.efc_J, (r0 + 2 * (k - 1)) * nv + i) += jn + jt;
+              at(b.efc_J, (r0 + 2 * (k - 1) + 1) * nv + i) += jn - jt;
+            }
+          }
+        }
+      }
+      const T tran = m.body_invweight0(2 * bodies[1]) + m.body_invweight0(2 * bodies[0]);
+      T solref[2], solimp[5];
+      OX_LDM(2, solref, pair_solref, 2 * p);
+      OX_LDM(5, solimp, pair_solimp, 5 * p);
+      if (dim == 1) {
+        T aref;
+        const T R = row_params(solref, solimp, dist, includemargin, tran, veln, &aref);
+        at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / R; at(b.efc_aref, r0) = aref;
+      } else {
+        T arefs[4], Rfirst = 0;
+        OX_MLOOP
+        for (int k = 1; k < dim; k++)
+          OX_MLOOP
+          for (int s = 0; s < 2; s++) {
+            const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
+            const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
+            if (k == 1 && s == 0) Rfirst = R;
+          }
+        const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
+        const T D = 1 / (2 * mu * mu * Rfirst);
+        OX_MLOOP
+        for (int r = 0; r < nrow; r++) {
+          at(b.efc_pos, r0 + r) = dist; at(b.efc_margin, r0 + r) = includemargin; at(b.efc_D, r0 + r) = D;
+          at(b.efc_aref, r0 + r) = arefs[r];
+        }
+      }
+  }
+
   OX_HDN void make_constraint() const {
     const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
@@ -935,80 +1029,18 @@ struct Env {
           }
         }
       }
-      const int ncon = ati(b.ncon, 0);
-      for (int c = 0; c < ncon; c++) {
-        const int p = ati(b.con_pair, c);
-        const T includemargin = m.pair_margin(p) - m.pair_gap(p);
-        const T dist = at(b.con_dist, c);
-        if (dist >= includemargin) continue;
-        const int dim = m.pair_dim(p);
-        const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
-        const int r0 = nefc;
-        nefc += nrow;
-        T fri[5];
-        OX_LDM(5, fri, pair_friction, 5 * p);
-        T cpos[3], frame[9];
-        ld<3>(cpos, b.con_pos, 3 * c);
-        ld<9>(frame, b.con_frame, 9 * c);
-        for (int r = r0; r < r0 + nrow; r++)
-          OX_MLOOP
-          for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
-        T veln = 0, velt[2] = {0, 0};
-        const int bodies[2] = {m.geom_bodyid(m.pair_geom2(p)), m.geom_bodyid(m.pair_geom1(p))};
+      if (LOCAL) {  // static contact slots: every index below is a compile-time constant after unrolling
         OX_MLOOP
-        for (int sidx = 0; sidx < 2; sidx++) {
-          const T sign = sidx == 0 ? (T)1 : (T)-1;
-          int body = bodies[sidx];
-          T sc[3], offset[3];
-          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
-          offset[0] = cpos[0] - sc[0]; offset[1] = cpos[1] - sc[1]; offset[2] = cpos[2] - sc[2];
-          body = m.body_weldid(body);  // nearest ancestor-or-self that has dofs (0 = static)
-          if (!body) continue;
-          const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
-      for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
-            T cd[6], jp[3];
-            ld<6>(cd, b.cdof, 6 * i);
-            cross3(jp, cd, offset);
-            jp[0] = sign * (jp[0] + cd[3]); jp[1] = sign * (jp[1] + cd[4]); jp[2] = sign * (jp[2] + cd[5]);
-            const T jn = dot3(frame, jp);
-            const T qv = at(b.qvel, i);
-            veln += jn * qv;
-            if (dim == 1) {
-              at(b.efc_J, r0 * nv + i) += jn;
-            } else {
-              for (int k = 1; k < dim; k++) {
-                const T jt = dot3(frame + 3 * k, jp) * fri[k - 1];
-                velt[k - 1] += jt * qv;
-                at(b.efc_J, (r0 + 2 * (k - 1)) * nv + i) += jn + jt;
-                at(b.efc_J, (r0 + 2 * (k - 1) + 1) * nv + i) += jn - jt;
-              }
-            }
+        for (int p = 0; p < h.npair; p++) {
+          OX_MLOOP
+          for (int k = 0; k < m.pair_maxcon(p); k++) {
+            const int c = m.pair_conadr(p) + k;
+            if (ati(b.con_active, c)) contact_rows(c, p, nefc);
           }
         }
-        const T tran = m.body_invweight0(2 * bodies[1]) + m.body_invweight0(2 * bodies[0]);
-        T solref[2], solimp[5];
-        OX_LDM(2, solref, pair_solref, 2 * p);
-        OX_LDM(5, solimp, pair_solimp, 5 * p);
-        if (dim == 1) {
-          T aref;
-          const T R = row_params(solref, solimp, dist, includemargin, tran, veln, &aref);
-          at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / R; at(b.efc_aref, r0) = aref;
-        } else {
-          T arefs[4], Rfirst = 0;
-          for (int k = 1; k < dim; k++)
-            OX_MLOOP
-            for (int s = 0; s < 2; s++) {
-              const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
-              const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
-              if (k == 1 && s == 0) Rfirst = R;
-            }
-          const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
-          const T D = 1 / (2 * mu * mu * Rfirst);
-          for (int r = 0; r < nrow; r++) {
-            at(b.efc_pos, r0 + r) = dist; at(b.efc_margin, r0 + r) = includemargin; at(b.efc_D, r0 + r) = D;
-            at(b.efc_aref, r0 + r) = arefs[r];
-          }
-        }
+      } else {
+        const int ncon = ati(b.ncon, 0);
+        for (int c = 0; c < ncon; c++) contact_rows(c, ati(b.con_pair, c), nefc);
       }
     }
     ati(b.nefc, 0) = nefc;
@@ -1089,13 +1121,24 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       if (!(at(b.s_Jaref, r) < 0)) continue;
       const T D = at(b.efc_D, r);
-      OX_MLOOP
-      for (int i = 0; i < nv; i++) {
-        const T ji = at(b.efc_J, r * nv + i);
-        if (ji == 0) continue;
-        const T s = D * ji;
-        OX_MLOOP
-        for (int j = 0; j <= i; j++) at(H, i * nv + j) += s * at(b.efc_J, r * nv + j);
+      if constexpr (LOCAL) {  // the row once into registers, then the rank-1 update on register-resident H
+        constexpr int NV = M::Hdr::nv;
+        T Jr[NV > 0 ? NV : 1];
+#pragma unroll
+        for (int i = 0; i < NV; i++) Jr[i] = at(b.efc_J, r * NV + i);
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          const T s = D * Jr[i];
+#pragma unroll
+          for (int j = 0; j <= i; j++) at(H, i * NV + j) += s * Jr[j];
+        }
+      } else {
+        for (int i = 0; i < nv; i++) {
+          const T ji = at(b.efc_J, r * nv + i);
+          if (ji == 0) continue;
+          const T s = D * ji;
+          for (int j = 0; j <= i; j++) at(H, i * nv + j) += s * at(b.efc_J, r * nv + j);
+        }
       }
     }
     OX_MLOOP
@@ -1160,8 +1203,14 @@ struct Env {
     const bool newton = h.solver == OX_SOL_NEWTON;
     bool use_smooth = true;
     if (!dis(OX_DSBL_WARMSTART)) {
-      const T cw = cost_at(b.qacc_warmstart, nv, nefc), cs = cost_at(b.qacc_smooth, nv, nefc);
-      use_smooth = cw > cs;
+      T cand[2];
+#pragma unroll 1
+      for (int k = 0; k < 2; k++) {  // cost(qacc_warmstart), cost(qacc_smooth) through one evaluation site
+        OX_MLOOP
+        for (int i = 0; i < nv; i++) at(b.qacc, i) = k ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
+        cand[k] = cost_at(b.qacc, nv, nefc);
+      }
+      use_smooth = cand[0] > cand[1];
     }
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qacc, i) = use_smooth ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
@@ -1401,46 +1450,60 @@ struct Env {
     solve_ld(b.i_qacc);
     advance(b.i_qacc, nullptr);
   }
-  // classic RK4; the Butcher matrix has one entry per row, so X_i = X_0 (+) h a_i F_{i-1}
-  OX_HDN void rk4() const {
+  // classic RK4; the Butcher matrix has one entry per row, so X_i = X_0 (+) h a_i F_{i-1}. Split into pieces so that
+  // step() can drive all four forward evaluations through ONE call site (code size: forward() is inlined once).
+  OX_HD void rk4_begin() const {
     const auto& h = m.h();
-    const int nv = h.nv, nq = h.nq;
-    const T dt = (T)h.timestep;
-    const T t0 = at(b.time, 0);
-    const T A[3] = {(T)0.5, (T)0.5, (T)1}, Bw[4] = {(T)(1.0 / 6), (T)(1.0 / 3), (T)(1.0 / 3), (T)(1.0 / 6)};
     OX_MLOOP
-    for (int i = 0; i < nq; i++) at(b.rk_q0, i) = at(b.qpos, i);
+    for (int i = 0; i < h.nq; i++) at(b.rk_q0, i) = at(b.qpos, i);
     OX_MLOOP
-    for (int i = 0; i < nv; i++) {
+    for (int i = 0; i < h.nv; i++) {
       at(b.rk_v0, i) = at(b.qvel, i);
-      at(b.rk_sv, i) = Bw[0] * at(b.qvel, i);
-      at(b.rk_sa, i) = Bw[0] * at(b.qacc, i);
+      at(b.rk_sv, i) = (T)(1.0 / 6) * at(b.qvel, i);
+      at(b.rk_sa, i) = (T)(1.0 / 6) * at(b.qacc, i);
     }
+    at(b.rk_t0, 0) = at(b.time, 0);
+  }
+  OX_HD void rk4_prepare(int st_) const {  // state for stage st_ = 1..3 from F_{st_-1} = (current qvel, current qacc)
+    const auto& h = m.h();
+    const T dt = (T)h.timestep;
+    const T a = st_ == 3 ? (T)1 : (T)0.5;
     OX_MLOOP
-    for (int st_ = 1; st_ < 4; st_++) {
-      const T a = A[st_ - 1];
-      // dX = a * F_{st-1}; F_{st-1} = (current qvel, current qacc)
-      OX_MLOOP
-      for (int i = 0; i < nv; i++) { at(b.s_gradold, i) = a * at(b.qvel, i); at(b.s_Mgradold, i) = a * at(b.qacc, i); }
-      OX_MLOOP
-      for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
-      integrate_pos(b.qpos, b.s_gradold, dt);
-      OX_MLOOP
-      for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i) + dt * at(b.s_Mgradold, i);
-      at(b.time, 0) = t0 + a * dt;
-      forward(true);
-      OX_MLOOP
-      for (int i = 0; i < nv; i++) {
-        at(b.rk_sv, i) += Bw[st_] * at(b.qvel, i);
-        at(b.rk_sa, i) += Bw[st_] * at(b.qacc, i);
-      }
+    for (int i = 0; i < h.nv; i++) { at(b.s_gradold, i) = a * at(b.qvel, i); at(b.s_Mgradold, i) = a * at(b.qacc, i); }
+    OX_MLOOP
+    for (int i = 0; i < h.nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
+    integrate_pos(b.qpos, b.s_gradold, dt);
+    OX_MLOOP
+    for (int i = 0; i < h.nv; i++) at(b.qvel, i) = at(b.rk_v0, i) + dt * at(b.s_Mgradold, i);
+    at(b.time, 0) = at(b.rk_t0, 0) + a * dt;
+  }
+  OX_HD void rk4_accumulate(int st_) const {
+    const auto& h = m.h();
+    const T w = st_ == 3 ? (T)(1.0 / 6) : (T)(1.0 / 3);
+    OX_MLOOP
+    for (int i = 0; i < h.nv; i++) {
+      at(b.rk_sv, i) += w * at(b.qvel, i);
+      at(b.rk_sa, i) += w * at(b.qacc, i);
     }
-    at(b.time, 0) = t0;
+  }
+  OX_HD void rk4_finish() const {
+    const auto& h = m.h();
+    at(b.time, 0) = at(b.rk_t0, 0);
     OX_MLOOP
-    for (int i = 0; i < nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
+    for (int i = 0; i < h.nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
     OX_MLOOP
-    for (int i = 0; i < nv; i++) at(b.qvel, i) = at(b.rk_v0, i);
+    for (int i = 0; i < h.nv; i++) at(b.qvel, i) = at(b.rk_v0, i);
     advance(b.rk_sa, b.rk_sv);
+  }
+  OX_HDN void rk4() const {  // staged mode: stages 2..4 after the forward the step already ran
+    rk4_begin();
+#pragma unroll 1
+    for (int st_ = 1; st_ < 4; st_++) {
+      rk4_prepare(st_);
+      forward(true);
+      rk4_accumulate(st_);
+    }
+    rk4_finish();
   }
 
   // ============================================================ reset / checks / step
@@ -1492,10 +1555,25 @@ struct Env {
   }
   OX_HDN void step() const {
     if (bad_state()) { reset_data(); ati(b.diverged, 0) += 1; }
-    forward(false);
-    if (bad_acc()) { reset_data(); ati(b.diverged, 0) += 1; forward(false); }
-    accumulate_stats();
-    if (m.h().integrator == OX_INT_RK4) rk4(); else euler();
+    const bool rk = m.h().integrator == OX_INT_RK4;
+    int stage = 0;
+    bool retried = false;
+#pragma unroll 1
+    for (;;) {  // the only call site of forward(): first evaluation, its retry after a bad-qacc reset, and RK4 stages 2..4
+      forward(stage > 0);
+      if (stage == 0) {
+        if (!retried && bad_acc()) { reset_data(); ati(b.diverged, 0) += 1; retried = true; continue; }
+        accumulate_stats();
+        if (!rk) break;
+        rk4_begin();
+      } else {
+        rk4_accumulate(stage);
+        if (stage == 3) break;
+      }
+      stage++;
+      rk4_prepare(stage);
+    }
+    if (rk) rk4_finish(); else euler();
   }
 };
 

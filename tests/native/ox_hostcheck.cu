@@ -48,8 +48,8 @@ HC_API hc_batch* hc_create(const ox_model_tables* t, int nenv, int precision, in
   size_t bytes = b->f64 ? layout_arena<double>(*t, b->stride, nullptr, nullptr, nullptr) : layout_arena<float>(*t, b->stride, nullptr, nullptr, nullptr);
   b->arena.assign(bytes + 256, 0);
   unsigned char* base = (unsigned char*)(((uintptr_t)b->arena.data() + 255) / 256 * 256);
-  if (b->f64) { layout_arena<double>(*t, b->stride, base, &b->bd, &b->fields); b->bd.nenv = nenv; b->bd.stride = b->stride; }
-  else { layout_arena<float>(*t, b->stride, base, &b->bf, &b->fields); b->bf.nenv = nenv; b->bf.stride = b->stride; }
+  if (b->f64) { layout_arena<double>(*t, b->stride, base, &b->bd, &b->fields); b->bd.nenv = nenv; b->bd.stride = b->stride; b->bd.lanes = 32; }
+  else { layout_arena<float>(*t, b->stride, base, &b->bf, &b->fields); b->bf.nenv = nenv; b->bf.stride = b->stride; b->bf.lanes = 32; }
   return b;
 }
 HC_API void hc_free(hc_batch* b) { delete b; }

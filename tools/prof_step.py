@@ -26,13 +26,14 @@ ap.add_argument("--ls-iterations", type=int, default=0)
 ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--no-spec", action="store_true")
+ap.add_argument("--lanes", type=int, default=0)
 a = ap.parse_args()
 
 import torch
 from oxide_control_b200 import _abi as A
 model = ox.Model.from_xml_string(ox.models.CONFIGS[a.config]["xml"])
 b = ox.BatchedPhysics(model, a.nenv, precision=a.precision, mode=a.mode, iterations=a.iterations, ls_iterations=a.ls_iterations,
-                      block_threads=a.block, use_graph=a.graph, specialize=not a.no_spec)
+                      block_threads=a.block, use_graph=a.graph, specialize=not a.no_spec, lanes_per_warp=a.lanes)
 q, v = initial_state(model, a.nenv, 0, a.nenv)
 b.set("qpos", q); b.set("qvel", v); b.ctrl_philox(True, 0x0B200)
 b.step(a.warmup); b.sync(); b.stats()
@@ -49,6 +50,6 @@ ms = e0.elapsed_time(e1)
 n = a.launches * a.steps_per_launch
 st = b.stats()
 den = a.nenv * n
-print(f"[{b.kernel_name()}] {a.config} {a.precision} nenv={a.nenv} mode={a.mode} steps/launch={a.steps_per_launch} launches={a.launches} it={a.iterations} ls={a.ls_iterations} block={a.block}: "
+print(f"[{b.kernel_name()}] {a.config} {a.precision} nenv={a.nenv} mode={a.mode} steps/launch={a.steps_per_launch} launches={a.launches} it={a.iterations} ls={a.ls_iterations} block={a.block} lanes={a.lanes}: "
       f"{ms / n:.4f} ms/step  {a.nenv * n / ms * 1e3:.3e} env-steps/s  ncon={st['sum_ncon'] / den:.2f} nefc={st['sum_nefc'] / den:.2f} "
       f"iters={st['sum_niter'] / den:.2f} div={st['diverged']}", flush=True)
