@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--iterations", type=int, default=0)
     ap.add_argument("--ls-iterations", type=int, default=0)
     ap.add_argument("--stage-times", action="store_true", help="also print per-stage device times (staged kernels)")
+    ap.add_argument("--no-spec", action="store_true", help="use the generic fused kernel instead of the model-specialised one")
     return ap.parse_args()
 
 
@@ -207,6 +208,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("OX_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no NCCL version banner)
     import torch
     import torch.distributed as dist
     import oxide_control_b200 as ox
@@ -225,7 +227,7 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     b = ox.BatchedPhysics(model, nenv, precision=precision, device=local_rank, mode=args.mode, env_id_offset=rank * nenv,
-                          block_threads=args.block, iterations=args.iterations, ls_iterations=args.ls_iterations)
+                          block_threads=args.block, iterations=args.iterations, ls_iterations=args.ls_iterations, specialize=not args.no_spec)
     qpos, qvel = initial_state(model, world * nenv, rank * nenv, (rank + 1) * nenv)
     b.set("qpos", qpos)
     b.set("qvel", qvel)
@@ -326,7 +328,7 @@ def main():
     else:
         finite = True
 
-    # ---------------- roofline of the dominant kernel (k_step_fused: the only kernel of a step)
+    # ---------------- roofline of the dominant kernel (the step kernel: the only kernel of a step besides the 1-thread counter bump)
     peaks, peak_src = load_peaks()
     step_ms = dev_ms / K  # this rank's average launch duration
     alg_bytes = algorithmic_bytes_per_env_step(model, real_bytes) * nenv
@@ -343,7 +345,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_source": f"{peak_src} copy bandwidth (burst)", "kernel": f"k_step_fused<{precision}>",
+                "traffic": traffic, "peak_source": f"{peak_src} copy bandwidth (burst)", "kernel": (f"k_step_spec<Spec_{args.config},{precision}>" if b.kernel_name() == args.config else f"{b.kernel_name()} <{precision}>"),
                 "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(model, real_bytes),
                 "fp_model_flops_per_env_step": flops, "fp_achieved_tflops": fp_achieved, "fp_peak_tflops_nominal": fp_peak,
                 "fp_frac": fp_achieved / fp_peak,
@@ -364,7 +366,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": precision, "data": "synthetic",
             "config": {"workload": f"{cfg['label']}: {nenv} envs per GPU, fresh Philox U(-1,1) controls every step, "
-                                   f"{'RK4' if model.integrator == 1 else 'Euler'}, Newton solver, mode={args.mode}",
+                                   f"{'RK4' if model.integrator == 1 else 'Euler'}, Newton solver, mode={args.mode}, kernel={b.kernel_name()}",
                        "envs_per_gpu": nenv, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "none (state resident by design)" if args.no_flush else
                              "L2 flushed (256 MiB memset) between timed steps, outside the per-step event pairs"},

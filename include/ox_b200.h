@@ -89,7 +89,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
   X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
   X(jnt_limited, njnt, 1)                                                                           \
-  X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1)               \
+  X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1) X(dof_Mdense, nvv, 1)               \
   X(geom_type, ngeom, 1) X(geom_bodyid, ngeom, 1) X(geom_contype, ngeom, 1)                        \
   X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
   X(site_bodyid, nsite, 1)                                                                          \
@@ -119,6 +119,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
 typedef struct ox_model_tables {
   /* sizes */
   int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata;
+  int32_t nvv;      /* nv*nv: size of dof_Mdense (index into qM of M(i,j), -1 where M is structurally zero) */
   int32_t nconmax;  /* sum of pair_maxcon: capacity of the per-env contact list         */
   int32_t nefcmax;  /* 2*nlimited + sum of contact rows: capacity of the per-env efc list */
   /* mjOption subset */
@@ -173,6 +174,8 @@ typedef struct ox_batch_config {
   double tolerance;      /* <0 = model's */
   int32_t specialize;    /* 1 (default): use the model-specialised step kernel when one was compiled in (fused mode) */
   int32_t lanes_per_warp; /* active envs per warp, 1..32; 0 = auto (thin warps while the batch cannot fill every SM scheduler) */
+  int32_t coop_solver;   /* staged mode: warp-per-env Newton solver; -1 auto (on when eligible and nv > 12), 0 off, 1 on */
+  int32_t reserved_;
 } ox_batch_config;
 
 OX_API void ox_batch_config_default(ox_batch_config* cfg);

@@ -42,6 +42,7 @@ class BatchConfig(C.Structure):
         ("nenv", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32), ("mode", C.c_int32),
         ("iterations", C.c_int32), ("ls_iterations", C.c_int32), ("use_graph", C.c_int32), ("block_threads", C.c_int32),
         ("env_id_offset", C.c_int64), ("tolerance", C.c_double), ("specialize", C.c_int32), ("lanes_per_warp", C.c_int32),
+        ("coop_solver", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -17,53 +17,11 @@
 #include "ox_internal.h"
 #include "ox_model.h"
 #include "ox_arena.h"
+#include "ox_kernels.cuh"
 #include "ox_spec.cuh"
 #include "ox_stages.cuh"
 
 namespace ox {
-
-// ---------------------------------------------------------------- model staging: one TMA bulk copy per CTA
-// (cp.async.bulk global -> shared, completion on an mbarrier; shows up as UBLKCP in SASS)
-__device__ __forceinline__ const unsigned char* stage_model(const unsigned char* __restrict__ gblob, int bytes) {
-  extern __shared__ __align__(128) unsigned char ox_smem[];
-  __shared__ __align__(8) unsigned long long mbar;
-  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&mbar);
-  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ox_smem);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gblob),
-                 "r"(bytes), "r"(mb)
-                 : "memory");
-  }
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(mb)
-        : "memory");
-  }
-  return ox_smem;
-}
-
-// env owned by this thread, or -1. Warps may be deliberately under-filled (b.lanes < 32 active lanes per warp): at small
-// batch sizes the step is latency-bound with far fewer warps than SM sub-partitions (8192 envs = 256 full warps for 592
-// schedulers), so spreading the envs over more, thinner warps uses the idle schedulers and shortens every warp's
-// divergent max-over-lanes critical path.
-template <typename T>
-__device__ __forceinline__ int env_index(const DevBatch<T>& b) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (lane >= b.lanes) return -1;
-  const int e = warp * b.lanes + lane;
-  return e < b.nenv ? e : -1;
-}
 
 enum Stage { ST_CTRL = 0, ST_CHECK, ST_KIN, ST_CRB, ST_COLLIDE, ST_VEL, ST_EFC, ST_ACC, ST_SOLVE, ST_SENSE, ST_INTEGRATE, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {"ctrl_rng", "check_pos_vel", "kin_com", "crb_ldl", "collide", "vel_bias",
@@ -148,6 +106,12 @@ __global__ void k_pack(TF* __restrict__ field, TU* __restrict__ user, int nenv, 
 
 using namespace ox;
 
+namespace ox {
+cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax);
+cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int nefcmax);
+bool solve_coop_eligible(const ox_model_tables& t);
+}  // namespace ox
+
 struct ox_batch {
   const ox_model* model = nullptr;
   ox_batch_config cfg{};
@@ -172,6 +136,8 @@ struct ox_batch {
   uint8_t* d_mask = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   cudaGraph_t graph = nullptr;
+  bool split = false;  // fused mode: specialised PRE/POST kernels around the warp-cooperative solver
+  bool coop = false;  // staged mode: warp-cooperative Newton solver (ox_solve_coop.cu) instead of the thread-per-env solve stage
   const ox::SpecEntry* spec = nullptr;  // model-specialised step kernel, when one was compiled in for this model
   ox::SpecRuntime spec_rt{};
 };
@@ -214,7 +180,13 @@ void launch_staged_step(ox_batch* b) {
   launch_stage<T, ST_VEL>(b, a);
   launch_stage<T, ST_EFC>(b, a);
   launch_stage<T, ST_ACC>(b, a);
-  launch_stage<T, ST_SOLVE>(b, a);
+  if (b->coop) {
+    if (sizeof(T) == 8) launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
+    else launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
+    b->launches++;
+  } else {
+    launch_stage<T, ST_SOLVE>(b, a);
+  }
   launch_stage<T, ST_SENSE>(b, a);
   launch_stage<T, ST_INTEGRATE>(b, a);
   if (b->philox) {
@@ -226,7 +198,28 @@ void launch_staged_step(ox_batch* b) {
 template <typename T>
 ox_status do_step(ox_batch* b, int nsteps) {
   if (b->cfg.mode == OX_MODE_FUSED) {
-    if (b->spec) {
+    if (b->spec && b->split) {
+      // specialised PRE -> warp-cooperative Newton solve -> specialised POST, one step at a time
+      for (int s = 0; s < nsteps; s++) {
+        const StepArgs a1 = make_args(b, 1);
+        if (sizeof(T) == 8) {
+          b->spec->launch_split_f64[0](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
+          launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
+          b->spec->launch_split_f64[1](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
+        } else {
+          b->spec->launch_split_f32[0](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
+          launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
+          b->spec->launch_split_f32[1](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
+        }
+        b->launches += 3;
+        if (b->philox && s + 1 < nsteps) {
+          k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
+          b->launches++;
+        }
+      }
+      b->launches--;               // the common increment below
+      if (b->philox) nsteps = 1;  // the final bump below advances the counter for the last step
+    } else if (b->spec) {
       if (sizeof(T) == 8) b->spec->launch_f64(b->grid, b->block, b->stream, b->bd, make_args(b, nsteps), b->spec_rt);
       else b->spec->launch_f32(b->grid, b->block, b->stream, b->bf, make_args(b, nsteps), b->spec_rt);
     } else {
@@ -368,7 +361,15 @@ static ox_status stage_times_impl(ox_batch* b, int reps, double* out_ms) {
 #define RUN(S)                                          \
   launch_stage<T, S>(b, a);                             \
   CU_TRY(cudaEventRecord(ev[S + 1], b->stream));
-    RUN(ST_CTRL) RUN(ST_CHECK) RUN(ST_KIN) RUN(ST_CRB) RUN(ST_COLLIDE) RUN(ST_VEL) RUN(ST_EFC) RUN(ST_ACC) RUN(ST_SOLVE)
+    RUN(ST_CTRL) RUN(ST_CHECK) RUN(ST_KIN) RUN(ST_CRB) RUN(ST_COLLIDE) RUN(ST_VEL) RUN(ST_EFC) RUN(ST_ACC)
+    if (b->coop) {
+      if (sizeof(T) == 8) launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
+      else launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
+      b->launches++;
+      CU_TRY(cudaEventRecord(ev[ST_SOLVE + 1], b->stream));
+    } else {
+      RUN(ST_SOLVE)
+    }
     RUN(ST_SENSE) RUN(ST_INTEGRATE)
 #undef RUN
     k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
@@ -390,7 +391,7 @@ extern "C" {
 void ox_batch_config_default(ox_batch_config* cfg) {
   if (!cfg) return;
   cfg->nenv = 1; cfg->device = 0; cfg->precision = OX_F32; cfg->mode = OX_MODE_FUSED; cfg->iterations = 0; cfg->ls_iterations = 0;
-  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1; cfg->specialize = 1; cfg->lanes_per_warp = 0;
+  cfg->use_graph = 0; cfg->block_threads = 0; cfg->env_id_offset = 0; cfg->tolerance = -1; cfg->specialize = 1; cfg->lanes_per_warp = 0; cfg->coop_solver = -1; cfg->reserved_ = 0;
 }
 
 ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batch** out) {
@@ -449,11 +450,18 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   CU_TRY(cudaMemset(b->arena, 0, b->arena_bytes));
   if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; b->bd.lanes = b->lanes; }
   else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; b->bf.lanes = b->lanes; }
+  if (cfg->mode == OX_MODE_STAGED && ox::solve_coop_eligible(t))
+    b->coop = cfg->coop_solver > 0 || (cfg->coop_solver < 0 && t.nv > 12);
+  if (cfg->coop_solver > 0 && !b->coop) {
+    ox::set_error("ox_batch_create: coop_solver needs mode=staged, the Newton solver, nv <= 32");
+    return OX_ERR_INVALID;
+  }
   if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
     b->spec = ox::find_spec(ox::model_hash(t));
     b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;
     b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
     b->spec_rt.tolerance = cfg->tolerance >= 0 ? cfg->tolerance : t.tolerance;
+    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && ox::solve_coop_eligible(t) && t.integrator == OX_INT_EULER;
   }
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
   CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));
@@ -493,7 +501,8 @@ void* ox_batch_stream(const ox_batch* b) { return b ? (void*)b->stream : nullptr
 int64_t ox_batch_launch_count(const ox_batch* b) { return b ? b->launches : -1; }
 const char* ox_batch_kernel_name(const ox_batch* b) {
   if (!b) return nullptr;
-  if (b->cfg.mode != OX_MODE_FUSED) return "k_stage (generic, one kernel per stage)";
+  if (b->cfg.mode != OX_MODE_FUSED) return b->coop ? "k_stage + k_solve_coop (warp-per-env Newton)" : "k_stage (generic, one kernel per stage)";
+  if (b->spec && b->split) { static thread_local std::string nm; nm = std::string(b->spec->name) + " (split: spec PRE + k_solve_coop + spec POST)"; return nm.c_str(); }
   return b->spec ? b->spec->name : "k_step_fused (generic)";
 }
 int32_t ox_spec_count(void) { return ox::spec_count(); }

@@ -24,7 +24,7 @@
 namespace ox {
 
 struct BlobHeader {
-  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata, nconmax, nefcmax;
+  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata, nconmax, nefcmax, nvv, padn_;
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
   int32_t total_bytes, any_damping;
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
@@ -38,6 +38,7 @@ struct BlobHeader {
 
 template <typename T>
 struct DevModel {
+  struct Hdr { static constexpr int nv = 1 << 30, nconmax = 1 << 30; };  // runtime model: no compile-time sizes
   const unsigned char* base;
   OX_HD const BlobHeader& h() const { return *reinterpret_cast<const BlobHeader*>(base); }
 #define OX_X(name, n, w) \
@@ -55,7 +56,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   BlobHeader h;
   std::memset(&h, 0, sizeof h);
   h.nq = t.nq; h.nv = t.nv; h.nu = t.nu; h.na = t.na; h.nbody = t.nbody; h.njnt = t.njnt; h.ngeom = t.ngeom; h.nsite = t.nsite;
-  h.nM = t.nM; h.npair = t.npair; h.nsensor = t.nsensor; h.nsensordata = t.nsensordata; h.nconmax = t.nconmax; h.nefcmax = t.nefcmax;
+  h.nM = t.nM; h.npair = t.npair; h.nsensor = t.nsensor; h.nsensordata = t.nsensordata; h.nconmax = t.nconmax; h.nefcmax = t.nefcmax; h.nvv = t.nvv;
   h.integrator = t.integrator; h.solver = t.solver; h.cone = t.cone;
   h.iterations = iterations > 0 ? iterations : t.iterations;
   h.ls_iterations = ls_iterations > 0 ? ls_iterations : t.ls_iterations;

@@ -836,6 +836,15 @@ ox_model* compile_mjcf(const std::string& xml) {
       nM += depth;
     }
     t.nM = nM;
+    t.nvv = nv * nv;
+    M->v_dof_Mdense.assign((size_t)nv * nv, -1);
+    for (int i = 0; i < nv; i++) {
+      int adr = M->v_dof_Madr[i];
+      for (int j = i; j >= 0; j = M->v_dof_parentid[j], adr++) {
+        M->v_dof_Mdense[(size_t)i * nv + j] = adr;
+        M->v_dof_Mdense[(size_t)j * nv + i] = adr;
+      }
+    }
   }
 
   // ---- geoms, sites ----

@@ -45,8 +45,11 @@ inline uint64_t model_hash(const ox_model_tables& t) {
 
 template <int N> struct AtLeast1 { static constexpr int v = N > 0 ? N : 1; };
 
-// The whole life of one environment inside one launch: load state, step nsteps times on-chip, store state.
-template <class S, typename T>
+// PHASE 0: the whole life of one environment inside one launch: load state, step nsteps times on-chip, store state.
+// PHASE 1 / 2: the same step split around the constraint solve, for models whose solve runs in the warp-cooperative
+// kernel (ox_solve_coop.cu): PRE = checks + forward up to the smooth acceleration and the constraint rows, written to
+// the SoA batch for the solver; POST = bad-qacc check, statistics, integration. Only Euler models are split.
+template <class S, typename T, int PHASE>
 OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) {
   using H = typename S::Hdr;
   // per-thread copy of every batch field, sized by the spec's compile-time dimensions. One local array per field (not one
@@ -87,47 +90,121 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #pragma unroll
   for (int i = 0; i < H::nq; i++) la.qpos[i] = G(qpos, i);
 #pragma unroll
-  for (int i = 0; i < H::nv; i++) { la.qvel[i] = G(qvel, i); la.qacc_warmstart[i] = G(qacc_warmstart, i); la.qfrc_applied[i] = G(qfrc_applied, i); }
-#pragma unroll
-  for (int i = 0; i < H::nu; i++) la.ctrl[i] = G(ctrl, i);
-#pragma unroll
-  for (int i = 0; i < 6 * H::nbody; i++) la.xfrc_applied[i] = G(xfrc_applied, i);
+  for (int i = 0; i < H::nv; i++) la.qvel[i] = G(qvel, i);
   la.time[0] = G(time, 0);
   la.diverged[0] = G(diverged, 0);
-  la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
-  la.ncon[0] = 0; la.nefc[0] = 0; la.solver_niter[0] = 0;
+  auto load_inputs = [&]() {
 #pragma unroll
-  for (int i = 0; i < H::nv; i++) la.qacc[i] = 0;
-  for (int s = 0; s < a.nsteps; s++) {
-    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
-    env.step();
+    for (int i = 0; i < H::nv; i++) { la.qacc_warmstart[i] = G(qacc_warmstart, i); la.qfrc_applied[i] = G(qfrc_applied, i); }
+#pragma unroll
+    for (int i = 0; i < H::nu; i++) la.ctrl[i] = G(ctrl, i);
+#pragma unroll
+    for (int i = 0; i < 6 * H::nbody; i++) la.xfrc_applied[i] = G(xfrc_applied, i);
+  };
+  auto store_state = [&](bool inputs_too) {
+#pragma unroll
+    for (int i = 0; i < H::nq; i++) G(qpos, i) = la.qpos[i];
+#pragma unroll
+    for (int i = 0; i < H::nv; i++) G(qvel, i) = la.qvel[i];
+    G(time, 0) = la.time[0];
+    G(diverged, 0) = la.diverged[0];
+    if (inputs_too) {  // an auto-reset cleared them
+#pragma unroll
+      for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qfrc_applied, i) = la.qfrc_applied[i]; }
+#pragma unroll
+      for (int i = 0; i < 6 * H::nbody; i++) G(xfrc_applied, i) = la.xfrc_applied[i];
+    }
+  };
+  if constexpr (PHASE == 0) {
+    load_inputs();
+    la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
+    la.ncon[0] = 0; la.nefc[0] = 0; la.solver_niter[0] = 0;
+#pragma unroll
+    for (int i = 0; i < H::nv; i++) la.qacc[i] = 0;
+    for (int s = 0; s < a.nsteps; s++) {
+      if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
+      env.step();
+    }
+    // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
+    store_state(false);
+#pragma unroll
+    for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qacc, i) = la.qacc[i]; }
+    if (a.philox) {
+#pragma unroll
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+    }
+#pragma unroll
+    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
+    G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0];
+    G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
+  } else if constexpr (PHASE == 1) {
+    load_inputs();
+    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0);
+    const bool did_reset = env.bad_state();
+    if (did_reset) { env.reset_data(); la.diverged[0] += 1; }
+    env.fwd_position();
+    env.fwd_velocity();
+    env.make_constraint();
+    env.actuation();
+    env.fwd_acceleration();
+    env.sensors();
+    // ---- what the solver and the POST phase need, into the SoA batch
+    if (did_reset) store_state(true);
+    if (a.philox || did_reset) {
+#pragma unroll
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+    }
+#pragma unroll
+    for (int i = 0; i < H::nM; i++) G(qM, i) = la.qM[i];
+#pragma unroll
+    for (int i = 0; i < H::nv; i++) { G(qfrc_smooth, i) = la.qfrc_smooth[i]; G(qacc_smooth, i) = la.qacc_smooth[i]; }
+#pragma unroll
+    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
+    const int nefc = la.nefc[0];
+    G(ncon, 0) = la.ncon[0]; G(nefc, 0) = nefc;
+    for (int r = 0; r < nefc; r++) {
+      G(efc_D, r) = la.efc_D[r]; G(efc_aref, r) = la.efc_aref[r];
+#pragma unroll
+      for (int i = 0; i < H::nv; i++) G(efc_J, r * H::nv + i) = la.efc_J[r * H::nv + i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < H::nv; i++) { la.qacc[i] = G(qacc, i); la.qfrc_constraint[i] = G(qfrc_constraint, i); la.qfrc_smooth[i] = G(qfrc_smooth, i); }
+#pragma unroll
+    for (int i = 0; i < H::nM; i++) la.qM[i] = G(qM, i);
+    la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
+    la.ncon[0] = G(ncon, 0); la.nefc[0] = G(nefc, 0); la.solver_niter[0] = G(solver_niter, 0);
+    const bool redo = env.bad_acc();
+    if (redo) {  // mj_checkAcc: reset and redo the forward (thread-serial solver; this path is rare)
+      load_inputs();
+      env.reset_data();
+      la.diverged[0] += 1;
+      env.forward(false);
+    }
+    env.accumulate_stats();
+    env.euler();
+    store_state(redo);
+    if (redo) {
+#pragma unroll
+      for (int i = 0; i < H::nv; i++) { G(qacc, i) = la.qacc[i]; G(qacc_warmstart, i) = la.qacc_warmstart[i]; }
+#pragma unroll
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+      G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0];
+    }
+    G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
   }
-  // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
-#pragma unroll
-  for (int i = 0; i < H::nq; i++) G(qpos, i) = la.qpos[i];
-#pragma unroll
-  for (int i = 0; i < H::nv; i++) { G(qvel, i) = la.qvel[i]; G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qacc, i) = la.qacc[i]; }
-  if (a.philox) {
-#pragma unroll
-    for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
-  }
-#pragma unroll
-  for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
-  G(time, 0) = la.time[0];
-  G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0]; G(diverged, 0) = la.diverged[0];
-  G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
 #undef G
 }
 
 #if defined(__CUDACC__)
-template <class S, typename T>
+template <class S, typename T, int PHASE>
 __global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (lane >= g.lanes) return;  // deliberately under-filled warps at small batch sizes (see env_index in ox_batch.cu)
+  if (lane >= g.lanes) return;  // deliberately under-filled warps at small batch sizes (see env_index in ox_kernels.cuh)
   const int e = warp * g.lanes + lane;
   if (e >= g.nenv) return;
   const long long step0 = a.philox ? *a.d_step : 0;
-  spec_step_env<S, T>(g, e, a, rt, step0);
+  spec_step_env<S, T, PHASE>(g, e, a, rt, step0);
 }
 #endif
 
@@ -137,8 +214,13 @@ struct SpecEntry {
   const char* name;
   void (*launch_f32)(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt);
   void (*launch_f64)(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt);
+  // split pipeline around the warp-cooperative solver (null when not generated for this model): [0] = PRE, [1] = POST
+  void (*launch_split_f32[2])(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt);
+  void (*launch_split_f64[2])(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt);
   void (*host_f32)(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);   // tests/native only
   void (*host_f64)(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
+  void (*host_split_f32[2])(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
+  void (*host_split_f64[2])(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
 };
 void register_spec(const SpecEntry& e);
 const SpecEntry* find_spec(uint64_t hash);

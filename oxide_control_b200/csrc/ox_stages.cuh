@@ -172,7 +172,9 @@ OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 
 // Loops over the model's structure (bodies, joints, dofs, geoms, pairs, chains): fully unrolled when the model policy
 // makes their bounds compile-time constants (LOCAL specialisation), left as loops in the generic kernels.
-#define OX_MLOOP _Pragma("unroll")  // no count: full unroll iff the trip count is a compile-time constant, else none
+#define OX_MLOOP _Pragma("unroll")
+// loops of the constraint solver over dofs: unrolled only for small specialised models (see Env::UNROLL_NV)
+#define OX_NVLOOP _Pragma("unroll (UNROLL_NV ? 64 : 1)")  // no count: full unroll iff the trip count is a compile-time constant, else none
 
 // ---------------------------------------------------------------- one environment
 // M     : model policy. DevModel<T> reads the runtime tables staged in shared memory; a generated Spec_* type
@@ -181,6 +183,12 @@ OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 //         arrays (stride 1), which after unrolling become registers.
 template <typename T, typename M = DevModel<T>, bool LOCAL = false>
 struct Env {
+  // Specialisation policy by model size: small models (cheetah-class) unroll the solver's O(nv^2)..O(nv^3) loops and use
+  // static contact slots so that H, the vectors and the contact list are registers; large ones (humanoid-class) keep
+  // those as loops over per-thread arrays - fully unrolled they are megabytes of straight-line code that the
+  // instruction cache cannot hold (profiles/r1_notes.md).
+  static constexpr bool UNROLL_NV = LOCAL && (M::Hdr::nv <= 12);
+  static constexpr bool STATIC_CON = LOCAL && (M::Hdr::nconmax <= 24);
   M m;
   DevBatch<T> b;
   int e;
@@ -470,34 +478,34 @@ struct Env {
   }
   OX_HDN void solve_ld(T* x) const {
     const int nv = m.h().nv;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = nv - 1; i >= 0; i--) {
       int adr = m.dof_Madr(i) + 1;
       const T xi = at(x, i);
-      OX_MLOOP
+      OX_NVLOOP
       for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) at(x, j) -= at(b.qLD, adr++) * xi;
     }
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(x, i) *= at(b.qLDiagInv, i);
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       int adr = m.dof_Madr(i) + 1;
       T xi = at(x, i);
-      OX_MLOOP
+      OX_NVLOOP
       for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) xi -= at(b.qLD, adr++) * at(x, j);
       at(x, i) = xi;
     }
   }
   OX_HDN void mul_m(T* res, const T* v) const {
     const int nv = m.h().nv;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(res, i) = 0;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       int adr = m.dof_Madr(i);
       const T vi = at(v, i);
       T ri = at(res, i) + at(b.qM, adr++) * vi;
-      OX_MLOOP
+      OX_NVLOOP
       for (int d_ = 1, j = m.dof_parentid(i); d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) {
         const T mij = at(b.qM, adr++);
         ri += mij * at(v, j);
@@ -757,19 +765,19 @@ struct Env {
   // contact arrays live in registers; walking the slots in order visits the contacts in the same order as the compact list.
   OX_HD void emit(Con& c, int p, int k, int& ncon) const {
     make_frame(c.frame);
-    const int idx = LOCAL ? m.pair_conadr(p) + k : ncon;
+    const int idx = STATIC_CON ? m.pair_conadr(p) + k : ncon;
     at(b.con_dist, idx) = c.dist;
     st<3>(b.con_pos, 3 * idx, c.pos);
     st<9>(b.con_frame, 9 * idx, c.frame);
     ati(b.con_pair, idx) = p;
-    if (LOCAL) ati(b.con_active, idx) = 1;
+    if (STATIC_CON) ati(b.con_active, idx) = 1;
     ncon++;
   }
 
   OX_HDN void collision() const {
     const auto& h = m.h();
     int ncon = 0;
-    if (LOCAL) {
+    if (STATIC_CON) {
       OX_MLOOP
       for (int i = 0; i < h.nconmax; i++) ati(b.con_active, i) = 0;
     }
@@ -1029,7 +1037,7 @@ struct Env {
           }
         }
       }
-      if (LOCAL) {  // static contact slots: every index below is a compile-time constant after unrolling
+      if (STATIC_CON) {  // static contact slots: every index below is a compile-time constant after unrolling
         OX_MLOOP
         for (int p = 0; p < h.npair; p++) {
           OX_MLOOP
@@ -1073,7 +1081,7 @@ struct Env {
   // efc_force, qfrc_constraint and total cost at the current (qacc, Ma, Jaref); returns cost, gauss via pointer
   OX_HD T update_constraint(int nv, int nefc, T* gauss_out) const {
     T c = 0;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r);
@@ -1082,13 +1090,13 @@ struct Env {
         const T D = at(b.efc_D, r);
         f = -D * ja;
         c += (T)0.5 * D * ja * ja;
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, r * nv + i) * f;
       }
       at(b.efc_force, r) = f;
     }
     T g = 0;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) g += (T)0.5 * (at(b.s_Ma, i) - at(b.qfrc_smooth, i)) * (at(b.qacc, i) - at(b.qacc_smooth, i));
     *gauss_out = g;
     return c + g;
@@ -1097,31 +1105,31 @@ struct Env {
   // grad, Mgrad (Newton: H^-1 grad with H = M + J' D_active J; CG: M^-1 grad); returns |grad|
   OX_HD T update_gradient(int nv, int nefc, bool newton) const {
     T gn = 0;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       const T g = at(b.s_Ma, i) - at(b.qfrc_smooth, i) - at(b.qfrc_constraint, i);
       at(b.s_grad, i) = g;
       gn += g * g;
     }
     if (!newton) {
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) at(b.s_Mgrad, i) = at(b.s_grad, i);
       solve_ld(b.s_Mgrad);
       return ox_sqrt(gn);
     }
     T* H = b.s_H;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) {
-      OX_MLOOP
+      OX_NVLOOP
       for (int j = 0; j <= i; j++) at(H, i * nv + j) = 0;
       int adr = m.dof_Madr(i);
-      OX_MLOOP
+      OX_NVLOOP
       for (int d_ = 0, j = i; d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) at(H, i * nv + j) = at(b.qM, adr++);
     }
     for (int r = 0; r < nefc; r++) {
       if (!(at(b.s_Jaref, r) < 0)) continue;
       const T D = at(b.efc_D, r);
-      if constexpr (LOCAL) {  // the row once into registers, then the rank-1 update on register-resident H
+      if constexpr (UNROLL_NV) {  // the row once into registers, then the rank-1 update on register-resident H
         constexpr int NV = M::Hdr::nv;
         T Jr[NV > 0 ? NV : 1];
 #pragma unroll
@@ -1141,33 +1149,33 @@ struct Env {
         }
       }
     }
-    OX_MLOOP
+    OX_NVLOOP
     for (int j = 0; j < nv; j++) {  // Cholesky, lower
       T s = at(H, j * nv + j);
-      OX_MLOOP
+      OX_NVLOOP
       for (int k = 0; k < j; k++) { const T l = at(H, j * nv + k); s -= l * l; }
       s = ox_sqrt(ox_max(s, (T)OX_MINVAL));
       at(H, j * nv + j) = s;
       const T inv = 1 / s;
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = j + 1; i < nv; i++) {
         T v = at(H, i * nv + j);
-        OX_MLOOP
+        OX_NVLOOP
         for (int k = 0; k < j; k++) v -= at(H, i * nv + k) * at(H, j * nv + k);
         at(H, i * nv + j) = v * inv;
       }
     }
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       T v = at(b.s_grad, i);
-      OX_MLOOP
+      OX_NVLOOP
       for (int k = 0; k < i; k++) v -= at(H, i * nv + k) * at(b.s_Mgrad, k);
       at(b.s_Mgrad, i) = v / at(H, i * nv + i);
     }
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = nv - 1; i >= 0; i--) {
       T v = at(b.s_Mgrad, i);
-      OX_MLOOP
+      OX_NVLOOP
       for (int k = i + 1; k < nv; k++) v -= at(H, k * nv + i) * at(b.s_Mgrad, k);
       at(b.s_Mgrad, i) = v / at(H, i * nv + i);
     }
@@ -1177,11 +1185,11 @@ struct Env {
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
     mul_m(b.s_Mv, qacc);
     T c = 0;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (at(qacc, i) - at(b.qacc_smooth, i));
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(qacc, i);
       if (v < 0) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
@@ -1192,7 +1200,7 @@ struct Env {
     const auto& h = m.h();
     const int nv = h.nv, nefc = ati(b.nefc, 0);
     if (nefc == 0) {
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) {
         const T a = at(b.qacc_smooth, i);
         at(b.qacc, i) = a; at(b.qacc_warmstart, i) = a; at(b.qfrc_constraint, i) = 0;
@@ -1206,26 +1214,26 @@ struct Env {
       T cand[2];
 #pragma unroll 1
       for (int k = 0; k < 2; k++) {  // cost(qacc_warmstart), cost(qacc_smooth) through one evaluation site
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.qacc, i) = k ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
         cand[k] = cost_at(b.qacc, nv, nefc);
       }
       use_smooth = cand[0] > cand[1];
     }
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qacc, i) = use_smooth ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
     // initial state
     mul_m(b.s_Ma, b.qacc);
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.qacc, i);
       at(b.s_Jaref, r) = v;
     }
     T gauss;
     T cost = update_constraint(nv, nefc, &gauss);
     T gnorm = update_gradient(nv, nefc, newton);
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
     const T tol = (T)h.tolerance;
     const T mscale = (T)h.meaninertia * (T)(nv > 1 ? nv : 1);
@@ -1236,7 +1244,7 @@ struct Env {
     while (iter < maxiter) {
       // ---- exact line search on the convex piecewise-quadratic phi(alpha)
       T snorm = 0;
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) { const T s = at(b.s_search, i); snorm += s * s; }
       snorm = ox_sqrt(snorm);
       if (snorm < (T)OX_MINVAL) break;
@@ -1244,12 +1252,12 @@ struct Env {
       mul_m(b.s_Mv, b.s_search);
       for (int r = 0; r < nefc; r++) {
         T v = 0;
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.s_search, i);
         at(b.s_Jv, r) = v;
       }
       T qg1 = 0, qg2 = 0;
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) {
         const T s = at(b.s_search, i);
         qg1 += s * (at(b.s_Ma, i) - at(b.qfrc_smooth, i));
@@ -1270,7 +1278,7 @@ struct Env {
       const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
       if (alpha == 0) break;
       // ---- move
-      OX_MLOOP
+      OX_NVLOOP
       for (int i = 0; i < nv; i++) {
         at(b.qacc, i) += alpha * at(b.s_search, i);
         at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
@@ -1287,23 +1295,23 @@ struct Env {
       // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
       if (oldcost - cost <= 8 * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
       if (newton) {
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
       } else {
         T num = 0, den = 0;
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) {
           num += at(b.s_grad, i) * (at(b.s_Mgrad, i) - at(b.s_Mgradold, i));
           den += at(b.s_gradold, i) * at(b.s_Mgradold, i);
         }
         T beta = num / ox_max((T)OX_MINVAL, den);
         if (beta < 0) beta = 0;
-        OX_MLOOP
+        OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i) + beta * at(b.s_search, i);
       }
     }
     ati(b.solver_niter, 0) = iter;
-    OX_MLOOP
+    OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qacc_warmstart, i) = at(b.qacc, i);
   }
 

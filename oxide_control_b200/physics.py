@@ -169,7 +169,7 @@ class BatchedPhysics:
 
     def __init__(self, model: Model, nenv: int, *, precision: str = "f32", device: int = 0, mode: str = "fused",
                  iterations: int = 0, ls_iterations: int = 0, tolerance: float = -1.0, use_graph: bool = False,
-                 block_threads: int = 0, env_id_offset: int = 0, specialize: bool = True, lanes_per_warp: int = 0):
+                 block_threads: int = 0, env_id_offset: int = 0, specialize: bool = True, lanes_per_warp: int = 0, coop_solver: int = -1):
         self.model = model
         cfg = A.BatchConfig()
         A.lib().ox_batch_config_default(C.byref(cfg))
@@ -185,6 +185,7 @@ class BatchedPhysics:
         cfg.env_id_offset = env_id_offset
         cfg.specialize = int(specialize)
         cfg.lanes_per_warp = lanes_per_warp
+        cfg.coop_solver = coop_solver
         self.precision = precision
         self.nenv = nenv
         self._h = C.c_void_p()

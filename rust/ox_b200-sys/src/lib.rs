@@ -21,7 +21,7 @@ pub const OX_ERR_IO: ox_status = 6; // -> Error::Mujoco
 pub struct ox_batch_config {
     pub nenv: i32, pub device: i32, pub precision: i32, pub mode: i32,
     pub iterations: i32, pub ls_iterations: i32, pub use_graph: i32, pub block_threads: i32,
-    pub env_id_offset: i64, pub tolerance: c_double, pub specialize: i32, pub lanes_per_warp: i32,
+    pub env_id_offset: i64, pub tolerance: c_double, pub specialize: i32, pub lanes_per_warp: i32, pub coop_solver: i32, pub reserved_: i32,
 }
 
 pub const OX_F32: i32 = 0; pub const OX_F64: i32 = 1;

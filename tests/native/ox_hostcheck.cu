@@ -79,6 +79,31 @@ HC_API int hc_step_spec(hc_batch* b, int nsteps, int philox, uint64_t seed, int6
   }
   return 1;
 }
+// split pipeline on the host: spec PRE, then the generic thread-serial solver on the arena (the warp-cooperative kernel
+// cannot run on a CPU), then spec POST. Checks the data exchange of the PRE/POST phases.
+HC_API int hc_step_split(hc_batch* b, int nsteps, int philox, uint64_t seed, int64_t env_off, int64_t step0) {
+  const SpecEntry* sp = find_spec(b->hash);
+  if (!sp || !sp->host_split_f32[0]) return 0;
+  StepArgs a;
+  a.nsteps = 1; a.philox = philox; a.seed = seed; a.env_id_offset = env_off; a.d_step = nullptr;
+  for (int s = 0; s < nsteps; s++)
+    for (int e = 0; e < b->nenv; e++) {
+      if (b->f64) {
+        sp->host_split_f64[0](b->bd, e, a, b->rt, step0 + s);
+        DevModel<double> m{b->blob.data()};
+        Env<double> env(m, b->bd, e);
+        env.fwd_constraint();
+        sp->host_split_f64[1](b->bd, e, a, b->rt, step0 + s);
+      } else {
+        sp->host_split_f32[0](b->bf, e, a, b->rt, step0 + s);
+        DevModel<float> m{b->blob.data()};
+        Env<float> env(m, b->bf, e);
+        env.fwd_constraint();
+        sp->host_split_f32[1](b->bf, e, a, b->rt, step0 + s);
+      }
+    }
+  return 1;
+}
 HC_API int hc_spec_count() { return spec_count(); }
 // raw SoA access: element i of env e of field id is ptr[i*stride + e]
 HC_API void* hc_field(hc_batch* b, int field, int* count, int* is_int) {

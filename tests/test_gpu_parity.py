@@ -38,7 +38,8 @@ def oracle_rollout(model, qpos, qvel, nsteps, warm=0, env_off=0):
 MODES = {  # which kernels a batch launches
     "spec": dict(mode="fused", specialize=True),        # model-specialised fused kernel (csrc/ox_spec.cuh); state + qacc + sensors only
     "fused": dict(mode="fused", specialize=False),      # generic fused kernel, all mjData arrays written
-    "staged": dict(mode="staged"),                      # generic, one kernel per mj_step stage
+    "staged": dict(mode="staged", coop_solver=0),       # generic, one kernel per mj_step stage, thread-per-env solver
+    "coop": dict(mode="staged", coop_solver=1),         # staged, solve stage = warp-per-env Newton (csrc/ox_solve_coop.cu)
 }
 
 
@@ -48,8 +49,10 @@ def test_single_step_fp64(ox, name, mode):
     model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
     nenv = 256
     qpos, qvel = random_state(model, nenv, seed=11)
+    if mode == "coop" and name in ("pendulum", "acrobot"):
+        pytest.skip("no constraints in this model: nothing for the cooperative solver to do")
     b = ox.BatchedPhysics(model, nenv, precision="f64", **MODES[mode])
-    assert (b.kernel_name() == name) == (mode == "spec")
+    assert b.kernel_name().startswith(name) == (mode == "spec") and ("k_stage + k_solve_coop" in b.kernel_name()) == (mode == "coop")
     b.set("qpos", qpos); b.set("qvel", qvel)
     b.ctrl_philox(True, SEED)
     b.step(1); b.sync()
@@ -201,3 +204,23 @@ def test_bulk_io_layouts_and_dtypes(ox):
     mask = np.zeros(nenv, np.uint8); mask[3] = 1
     b.reset(mask)
     assert np.array_equal(b.get("qpos")[3], model.qpos0) and np.array_equal(b.get("qpos", np.float32)[4], q[4].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["cheetah", "humanoid"])
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-6), ("f32", 5e-2)])
+def test_coop_solver_horizon(ox, name, precision, tol):
+    """The warp-cooperative solver over a 60-step horizon (contacts come and go) against the oracle / the serial solver."""
+    model = ox.Model.from_xml_string(ox.models.CONFIGS[name]["xml"])
+    nenv, nsteps = 64, 60
+    qpos, qvel = random_state(model, nenv, seed=17)
+    b = ox.BatchedPhysics(model, nenv, precision=precision, mode="staged", coop_solver=1)
+    b.set("qpos", qpos); b.set("qvel", qvel); b.ctrl_philox(True, SEED)
+    b.step(nsteps); b.sync()
+    ref = ox.BatchedPhysics(model, nenv, precision=precision, mode="staged", coop_solver=0)
+    ref.set("qpos", qpos); ref.set("qvel", qvel); ref.ctrl_philox(True, SEED)
+    ref.step(nsteps); ref.sync()
+    assert int(b.diverged().sum()) == 0
+    assert np.max(np.abs(b.get("qpos") - ref.get("qpos"))) <= tol
+    if precision == "f64":
+        oq, ov, oa, ods = oracle_rollout(model, qpos, qvel, nsteps)
+        assert np.max(np.abs(b.get("qpos") - oq[-1])) <= 1e-6

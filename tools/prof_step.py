@@ -27,13 +27,14 @@ ap.add_argument("--block", type=int, default=0)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--no-spec", action="store_true")
 ap.add_argument("--lanes", type=int, default=0)
+ap.add_argument("--coop", type=int, default=-1)
 a = ap.parse_args()
 
 import torch
 from oxide_control_b200 import _abi as A
 model = ox.Model.from_xml_string(ox.models.CONFIGS[a.config]["xml"])
 b = ox.BatchedPhysics(model, a.nenv, precision=a.precision, mode=a.mode, iterations=a.iterations, ls_iterations=a.ls_iterations,
-                      block_threads=a.block, use_graph=a.graph, specialize=not a.no_spec, lanes_per_warp=a.lanes)
+                      block_threads=a.block, use_graph=a.graph, specialize=not a.no_spec, lanes_per_warp=a.lanes, coop_solver=a.coop)
 q, v = initial_state(model, a.nenv, 0, a.nenv)
 b.set("qpos", q); b.set("qvel", v); b.ctrl_philox(True, 0x0B200)
 b.step(a.warmup); b.sync(); b.stats()
