@@ -527,6 +527,7 @@ void getImpedance(const double* solimp, double pos, double margin, double* imp) 
   if (x <= 0) { *imp = dmin; return; }
   double y;
   if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
   else if (x <= mid) y = std::pow(x, power) / std::pow(mid, power - 1);
   else y = 1 - std::pow(1 - x, power) / std::pow(1 - mid, power - 1);
   *imp = dmin + y * (dmax - dmin);

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
       iter++;
       const T improvement = scale * (oldcost - cost), gradient = scale * gnorm;
       if (improvement < tol || gradient < tol) break;
-      if (oldcost - cost <= 8 * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
+      if (oldcost - cost <= OX_FLOOR_MULT * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
     }
     search = -Mgrad;
   }

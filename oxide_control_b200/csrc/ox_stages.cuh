@@ -40,6 +40,10 @@ template <typename T> OX_HD T ox_max(T a, T b) { return a > b ? a : b; }
 template <typename T> OX_HD T ox_min(T a, T b) { return a < b ? a : b; }
 template <typename T> OX_HD T ox_clip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 template <typename T> OX_HD bool ox_bad(T x) { return !(x <= (T)OX_MAXVAL && x >= (T)-OX_MAXVAL); }  // NaN or too large
+// solver floating-point floor (ORACLE_DECISIONS #8): stop when the cost decrease is below FLOOR_MULT * 4 eps * (|old| + |new|)
+#ifndef OX_FLOOR_MULT
+#define OX_FLOOR_MULT 8
+#endif
 template <typename T> struct Eps;
 template <> struct Eps<float> { static OX_HD float v() { return 4 * 1.1920929e-07f; } };
 template <> struct Eps<double> { static OX_HD double v() { return 4 * 2.220446049250313e-16; } };
@@ -900,6 +904,7 @@ struct Env {
       else {
         T y;
         if (power == 1) y = x;
+        else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);  // MuJoCo's default; no pow()
         else if (x <= mid) y = ox_pow(x, power) / ox_pow(mid, power - 1);
         else y = 1 - ox_pow(1 - x, power) / ox_pow(1 - mid, power - 1);
         imp = dmin + y * (dmax - dmin);
@@ -1293,7 +1298,7 @@ struct Env {
       if (improvement < tol || gradient < tol) break;
       // floating-point floor: a decrease below the resolution of the cost itself is round-off, not progress
       // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
-      if (oldcost - cost <= 8 * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
+      if (oldcost - cost <= OX_FLOOR_MULT * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
       if (newton) {
         OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
