@@ -307,8 +307,7 @@ def main():
         def e2e_step(i):
             b.set_ptr("ctrl", ctrl_pool[i % npool].data_ptr(), A.F32, A.MEM_HOST, A.LAYOUT_ENV_MAJOR)
             b.step(1)
-            b.get_ptr("qpos", obs_q.data_ptr(), A.F32, A.MEM_HOST, A.LAYOUT_ENV_MAJOR)
-            b.get_ptr("qvel", obs_v.data_ptr(), A.F32, A.MEM_HOST, A.LAYOUT_ENV_MAJOR)
+            b.get_many_ptr(("qpos", "qvel"), (obs_q.data_ptr(), obs_v.data_ptr()), A.F32, A.MEM_HOST, A.LAYOUT_ENV_MAJOR)
         for i in range(3):
             e2e_step(i)
         barrier()
@@ -322,7 +321,7 @@ def main():
         e2e = {"value": world * nenv * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nenv * nu * 4,
                "d2h_bytes_per_step": nenv * (nq + nv) * 4, "ms_per_step": 1e3 * e2e_s / Ke,
                "timing": "host wall clock around K steps, each = ox_batch_set(ctrl, pinned host) + ox_batch_step(1) + "
-                         "ox_batch_get(qpos, qvel, pinned host); max over ranks"}
+                         "ox_batch_get_many(qpos, qvel -> pinned host, one sync); max over ranks"}
         b.ctrl_philox(True, SEED)
         finite = bool(np.isfinite(obs_q.numpy()).all())
     else:

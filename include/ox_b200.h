@@ -216,6 +216,9 @@ OX_API int32_t ox_batch_field_size(const ox_batch* b, int32_t field); /* element
  * in `layout`, living in `mem`. Stream-ordered; host copies complete before return. */
 OX_API ox_status ox_batch_get(ox_batch* b, int32_t field, void* buf, int32_t dtype, int32_t mem, int32_t layout);
 OX_API ox_status ox_batch_set(ox_batch* b, int32_t field, const void* buf, int32_t dtype, int32_t mem, int32_t layout);
+/* several fields in one call: one stream synchronisation for all the device->host copies (the observation read of an
+ * RL step: qpos + qvel [+ sensordata]). bufs[i] receives field fields[i]; same dtype / mem / layout for all. */
+OX_API ox_status ox_batch_get_many(ox_batch* b, int32_t nfields, const int32_t* fields, void* const* bufs, int32_t dtype, int32_t mem, int32_t layout);
 /* per-env slices, always fp64 at this boundary (reference types are f64 / [f64;N]) */
 OX_API ox_status ox_batch_get1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, double* out);
 OX_API ox_status ox_batch_set1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, const double* in);
@@ -228,7 +231,7 @@ OX_API ox_status ox_batch_stats(ox_batch* b, double* out4);
 OX_API int64_t ox_batch_launch_count(const ox_batch* b);
 /* which step kernel this batch launches: a spec name ("cheetah"), or the generic kernel */
 OX_API const char* ox_batch_kernel_name(const ox_batch* b);
-/* model-specialised kernels compiled into the library (oxide_control_b200/spec_models/*.xml at build time) */
+/* model-specialised kernels compiled into the library (every .xml under oxide_control_b200/spec_models at build time) */
 OX_API int32_t ox_spec_count(void);
 OX_API const char* ox_spec_name(int32_t i);
 /* per-stage device time of one staged forward+integrate (ms), for profiles/: names via ox_stage_name */

@@ -762,11 +762,10 @@ struct Solver {
   std::vector<char> active;
   double cost = 0, gauss = 0;
   double quadGauss[3];
-  std::vector<double> quad;  // nefc x 3
 
   Solver(const Model* m_, Data* d_) : m(m_), d(d_), nv(m_->nv), nefc(d_->nefc) {
     Ma.resize(nv); Jaref.resize(nefc); grad.resize(nv); Mgrad.resize(nv); search.resize(nv); Mv.resize(nv); Jv.resize(nefc);
-    H.resize((size_t)nv * nv); gradold.resize(nv); Mgradold.resize(nv); active.resize(nefc); quad.resize(3 * (size_t)nefc);
+    H.resize((size_t)nv * nv); gradold.resize(nv); Mgradold.resize(nv); active.resize(nefc);
   }
   // efc_force, active set, cost, qfrc_constraint at the current Jaref / Ma / qacc
   void updateConstraint() {
@@ -844,11 +843,11 @@ struct Solver {
     p.d1 = 2 * quadGauss[2];
     for (int r = 0; r < nefc; r++) {
       double x = Jaref[r] + a * Jv[r];
-      if (x < 0) {
-        const double* q = &quad[3 * (size_t)r];
-        p.cost += a * a * q[2] + a * q[1] + q[0];
-        p.d0 += 2 * a * q[2] + q[1];
-        p.d1 += 2 * q[2];
+      if (x < 0) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
+        const double Dx = d->efc_D[r] * x, Dj = d->efc_D[r] * Jv[r];
+        p.cost += 0.5 * Dx * x;
+        p.d0 += Dx * Jv[r];
+        p.d1 += Dj * Jv[r];
       }
     }
     if (p.d1 < OX_MINVAL) p.d1 = OX_MINVAL;
@@ -873,12 +872,6 @@ struct Solver {
     for (int i = 0; i < nv; i++) {
       quadGauss[1] += search[i] * (Ma[i] - d->qfrc_smooth[i]);
       quadGauss[2] += 0.5 * search[i] * Mv[i];
-    }
-    for (int r = 0; r < nefc; r++) {
-      double D = d->efc_D[r];
-      quad[3 * (size_t)r] = 0.5 * D * Jaref[r] * Jaref[r];
-      quad[3 * (size_t)r + 1] = D * Jaref[r] * Jv[r];
-      quad[3 * (size_t)r + 2] = 0.5 * D * Jv[r] * Jv[r];
     }
     const double eps = 4 * 2.220446049250313e-16;
     Pt p0 = eval(0);

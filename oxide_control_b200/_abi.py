@@ -74,6 +74,7 @@ SYMBOLS = {
     "ox_batch_field_size": (C.c_int32, [_P, C.c_int32]),
     "ox_batch_get": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
     "ox_batch_set": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
+    "ox_batch_get_many": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32]),
     "ox_batch_get1": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "ox_batch_set1": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "ox_batch_get1_int": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

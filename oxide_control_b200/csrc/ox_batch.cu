@@ -280,7 +280,7 @@ void launch_pack(ox_batch* b, void* field, void* user, int cnt, int layout, int 
   b->launches++;
 }
 
-ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int layout, int dir) {
+ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int layout, int dir, size_t tmp_off = 0, bool sync = true) {
   if (!b || !buf) { ox::set_error("bulk I/O: null argument"); return OX_ERR_INVALID; }
   auto it = b->fields.find(field);
   if (it == b->fields.end()) { ox::set_error("bulk I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
@@ -294,9 +294,9 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   const size_t bytes = (size_t)b->nenv * fi.count * usz;
   void* dbuf = buf;
   if (mem == OX_MEM_HOST) {
-    ox_status s = ensure_tmp(b, bytes);
+    ox_status s = ensure_tmp(b, tmp_off + bytes);
     if (s) return s;
-    dbuf = b->d_tmp;
+    dbuf = (unsigned char*)b->d_tmp + tmp_off;
     if (dir == 0) CU_TRY(cudaMemcpyAsync(dbuf, buf, bytes, cudaMemcpyHostToDevice, b->stream));
   } else if (mem != OX_MEM_DEVICE) { ox::set_error("bulk I/O: bad mem"); return OX_ERR_INVALID; }
   if (fi.is_int) launch_pack<int32_t, int32_t>(b, fi.ptr, dbuf, fi.count, layout, dir);
@@ -310,7 +310,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   CU_TRY(cudaGetLastError());
   if (mem == OX_MEM_HOST && dir == 1) {
     CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaStreamSynchronize(b->stream));
+    if (sync) CU_TRY(cudaStreamSynchronize(b->stream));
   }
   return OX_OK;
 }
@@ -573,6 +573,25 @@ int32_t ox_batch_field_size(const ox_batch* b, int32_t field) {
 
 ox_status ox_batch_get(ox_batch* b, int32_t field, void* buf, int32_t dtype, int32_t mem, int32_t layout) {
   return bulk_io(b, field, buf, dtype, mem, layout, 1);
+}
+ox_status ox_batch_get_many(ox_batch* b, int32_t nfields, const int32_t* fields, void* const* bufs, int32_t dtype, int32_t mem, int32_t layout) {
+  if (!b || !fields || !bufs || nfields < 1) { ox::set_error("ox_batch_get_many: bad argument"); return OX_ERR_INVALID; }
+  // size the staging buffer once for all fields (a growth between fields would free memory an earlier copy still reads)
+  size_t total = 0;
+  for (int i = 0; i < nfields; i++) {
+    auto it = b->fields.find(fields[i]);
+    if (it == b->fields.end()) { ox::set_error("ox_batch_get_many: unknown field id " + std::to_string(fields[i])); return OX_ERR_INVALID; }
+    total += ((size_t)b->nenv * it->second.count * 8 + 255) / 256 * 256;
+  }
+  if (mem == OX_MEM_HOST) { ox_status s = ensure_tmp(b, total); if (s) return s; }
+  size_t off = 0;
+  for (int i = 0; i < nfields; i++) {
+    ox_status s = bulk_io(b, fields[i], bufs[i], dtype, mem, layout, 1, off, false);
+    if (s) return s;
+    off += ((size_t)b->nenv * b->fields[fields[i]].count * 8 + 255) / 256 * 256;
+  }
+  if (mem == OX_MEM_HOST) CU_TRY(cudaStreamSynchronize(b->stream));
+  return OX_OK;
 }
 ox_status ox_batch_set(ox_batch* b, int32_t field, const void* buf, int32_t dtype, int32_t mem, int32_t layout) {
   return bulk_io(b, field, const_cast<void*>(buf), dtype, mem, layout, 0);

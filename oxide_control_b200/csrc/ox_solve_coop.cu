@@ -161,11 +161,10 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
           const T ja = ROW(rowJar, r), jvr = ROW(rowJv, r);
           const T x = ja + an * jvr;
           if (x < 0) {
-            const T D = ROW(rowD, r);
-            const T q0 = (T)0.5 * D * ja * ja, q1 = D * ja * jvr, q2 = (T)0.5 * D * jvr * jvr;
-            c += an * an * q2 + an * q1 + q0;
-            d0 += 2 * an * q2 + q1;
-            d1 += 2 * q2;
+            const T Dx = ROW(rowD, r) * x, Dj = ROW(rowD, r) * jvr;
+            c += (T)0.5 * Dx * x;
+            d0 += Dx * jvr;
+            d1 += Dj * jvr;
           }
         }
         cur_a = an;

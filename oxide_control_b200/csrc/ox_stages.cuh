@@ -1071,12 +1071,11 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
-      if (x < 0) {
-        const T D = at(b.efc_D, r);
-        const T q0 = (T)0.5 * D * ja * ja, q1 = D * ja * jv, q2 = (T)0.5 * D * jv * jv;
-        p.cost += a * a * q2 + a * q1 + q0;
-        p.d0 += 2 * a * q2 + q1;
-        p.d1 += 2 * q2;
+      if (x < 0) {  // active at alpha: 1/2 D x^2 and its first / second derivative in alpha
+        const T Dx = at(b.efc_D, r) * x, Dj = at(b.efc_D, r) * jv;
+        p.cost += (T)0.5 * Dx * x;
+        p.d0 += Dx * jv;
+        p.d1 += Dj * jv;
       }
     }
     if (p.d1 < (T)OX_MINVAL) p.d1 = (T)OX_MINVAL;

@@ -274,6 +274,13 @@ class BatchedPhysics:
     def get_ptr(self, field: str, ptr: int, dtype_code: int, mem: int, layout: int) -> None:
         _check(A.lib().ox_batch_get(self._h, A.FIELD[field], C.c_void_p(ptr), dtype_code, mem, layout))
 
+    def get_many_ptr(self, fields: Sequence[str], ptrs: Sequence[int], dtype_code: int, mem: int, layout: int) -> None:
+        """Several fields, one stream synchronisation (the observation read of an RL step)."""
+        n = len(fields)
+        ids = (C.c_int32 * n)(*[A.FIELD[f] for f in fields])
+        bufs = (C.c_void_p * n)(*ptrs)
+        _check(A.lib().ox_batch_get_many(self._h, n, ids, bufs, dtype_code, mem, layout))
+
     def set_ptr(self, field: str, ptr: int, dtype_code: int, mem: int, layout: int) -> None:
         _check(A.lib().ox_batch_set(self._h, A.FIELD[field], C.c_void_p(ptr), dtype_code, mem, layout))
 

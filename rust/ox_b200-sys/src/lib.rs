@@ -57,6 +57,7 @@ extern "C" {
     pub fn ox_batch_set_step_counter(b: *mut ox_batch, step: i64) -> ox_status;
     pub fn ox_batch_field_size(b: *const ox_batch, field: i32) -> i32;
     pub fn ox_batch_get(b: *mut ox_batch, field: i32, buf: *mut c_void, dtype: i32, mem: i32, layout: i32) -> ox_status;
+    pub fn ox_batch_get_many(b: *mut ox_batch, nfields: i32, fields: *const i32, bufs: *const *mut c_void, dtype: i32, mem: i32, layout: i32) -> ox_status;
     pub fn ox_batch_set(b: *mut ox_batch, field: i32, buf: *const c_void, dtype: i32, mem: i32, layout: i32) -> ox_status;
     pub fn ox_batch_get1(b: *mut ox_batch, field: i32, env: i32, offset: i32, count: i32, out: *mut c_double) -> ox_status;
     pub fn ox_batch_set1(b: *mut ox_batch, field: i32, env: i32, offset: i32, count: i32, inp: *const c_double) -> ox_status;

@@ -199,6 +199,11 @@ def test_bulk_io_layouts_and_dtypes(ox):
     assert np.array_equal(b.get("qpos", np.float64, "elem_major"), q.astype(np.float32).astype(np.float64).T)
     b.set("qvel", q.T.astype(np.float32).copy(), layout="elem_major")
     assert np.array_equal(b.get("qvel", np.float32), q.astype(np.float32))
+    import torch
+    from oxide_control_b200 import _abi as A
+    oq = torch.empty((nenv, model.nq), dtype=torch.float32).pin_memory(); ov = torch.empty((nenv, model.nv), dtype=torch.float32).pin_memory()
+    b.get_many_ptr(("qpos", "qvel"), (oq.data_ptr(), ov.data_ptr()), A.F32, A.MEM_HOST, A.LAYOUT_ENV_MAJOR)
+    assert np.array_equal(oq.numpy(), b.get("qpos", np.float32)) and np.array_equal(ov.numpy(), b.get("qvel", np.float32))
     b.set1("ctrl", 5, [0.25], offset=2)
     assert b.get1("ctrl", 5)[2] == 0.25 and b.get1("ctrl", 4)[2] == 0.0
     mask = np.zeros(nenv, np.uint8); mask[3] = 1
