@@ -834,13 +834,14 @@ struct Solver {
       Mgrad[i] = v / H[(size_t)i * nv + i];
     }
   }
-  struct Pt { double alpha, cost, d0, d1; };
+  struct Pt { double alpha, cost, d0, d1, s0; };
   Pt eval(double a) const {
     Pt p;
     p.alpha = a;
     p.cost = a * a * quadGauss[2] + a * quadGauss[1] + quadGauss[0];
     p.d0 = 2 * a * quadGauss[2] + quadGauss[1];
     p.d1 = 2 * quadGauss[2];
+    p.s0 = std::fabs(2 * a * quadGauss[2]) + std::fabs(quadGauss[1]);
     for (int r = 0; r < nefc; r++) {
       double x = Jaref[r] + a * Jv[r];
       if (x < 0) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
@@ -848,6 +849,7 @@ struct Solver {
         p.cost += 0.5 * Dx * x;
         p.d0 += Dx * Jv[r];
         p.d1 += Dj * Jv[r];
+        p.s0 += std::fabs(Dx * Jv[r]);
       }
     }
     if (p.d1 < OX_MINVAL) p.d1 = OX_MINVAL;
@@ -883,7 +885,7 @@ struct Solver {
       if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = 0.5 * (lo.alpha + hi.alpha);
       if (std::fabs(a - cur.alpha) <= eps * std::fabs(a)) break;
       cur = eval(a);
-      if (std::fabs(cur.d0) < gtol) break;
+      if (std::fabs(cur.d0) < gtol || std::fabs(cur.d0) <= 8 * eps * cur.s0) break;  // converged, or phi' below its own round-off
       if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
     }
     return cur.cost <= p0.cost ? cur.alpha : 0;

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
           if (have_hi && !(an > lo_a && an < hi_a)) an = (T)0.5 * (lo_a + hi_a);
           if (ox_abs(an - cur_a) <= Eps<T>::v() * ox_abs(an)) break;
         }
-        T c = 0, d0 = 0, d1 = 0;
+        T c = 0, d0 = 0, d1 = 0, s0 = 0;
         for (int r = lane; r < nefc; r += 32) {
           const T ja = ROW(rowJar, r), jvr = ROW(rowJv, r);
           const T x = ja + an * jvr;
@@ -165,18 +165,20 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
             c += (T)0.5 * Dx * x;
             d0 += Dx * jvr;
             d1 += Dj * jvr;
+            s0 += ox_abs(Dx * jvr);
           }
         }
         cur_a = an;
         cur_c = an * an * qg2 + an * qg1 + gauss + wsum(c);
         cur_d0 = 2 * an * qg2 + qg1 + wsum(d0);
         cur_d1 = 2 * qg2 + wsum(d1);
+        const T cur_s0 = ox_abs(2 * an * qg2) + ox_abs(qg1) + wsum(s0);
         if (cur_d1 < (T)OX_MINVAL) cur_d1 = (T)OX_MINVAL;
         if (it < 0) {
           p0c = cur_c; p0d0 = cur_d0;
           if (!(p0d0 < 0)) stop = true;
         } else {
-          if (ox_abs(cur_d0) < gtol) break;
+          if (ox_abs(cur_d0) < gtol || ox_abs(cur_d0) <= 8 * Eps<T>::v() * cur_s0) break;
           if (cur_d0 < 0) lo_a = cur_a; else { hi_a = cur_a; have_hi = true; }
         }
       }

@@ -57,18 +57,10 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   // only the runtime-indexed ones (contact / constraint rows and what the contact Jacobian walk reads) stay in local memory.
   constexpr int nq = H::nq, nv = H::nv, nu = H::nu, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
                 ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata;
-  struct LaView {  // names only; the arrays themselves are the separate locals below
-#define OX_X(name, cnt) T* name;
-    OX_BATCH_REAL_FIELDS(OX_X)
-#undef OX_X
-#define OX_X(name, cnt) int32_t* name;
-    OX_BATCH_INT_FIELDS(OX_X)
-#undef OX_X
-  } la;
-#define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v]; la.name = loc_##name;
+#define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v];
   OX_BATCH_REAL_FIELDS(OX_X)
 #undef OX_X
-#define OX_X(name, cnt) int32_t loc_##name[AtLeast1<(cnt)>::v]; la.name = loc_##name;
+#define OX_X(name, cnt) int32_t loc_##name[AtLeast1<(cnt)>::v];
   OX_BATCH_INT_FIELDS(OX_X)
 #undef OX_X
   DevBatch<T> lb;
@@ -88,39 +80,39 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #define G(field, i) g.field[(uint32_t)(i) * st + ue]
   // ---- algorithmic reads: qpos, qvel, ctrl, qacc_warmstart, time (+ applied forces)
 #pragma unroll
-  for (int i = 0; i < H::nq; i++) la.qpos[i] = G(qpos, i);
+  for (int i = 0; i < H::nq; i++) loc_qpos[i] = G(qpos, i);
 #pragma unroll
-  for (int i = 0; i < H::nv; i++) la.qvel[i] = G(qvel, i);
-  la.time[0] = G(time, 0);
-  la.diverged[0] = G(diverged, 0);
+  for (int i = 0; i < H::nv; i++) loc_qvel[i] = G(qvel, i);
+  loc_time[0] = G(time, 0);
+  loc_diverged[0] = G(diverged, 0);
   auto load_inputs = [&]() {
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) { la.qacc_warmstart[i] = G(qacc_warmstart, i); la.qfrc_applied[i] = G(qfrc_applied, i); }
+    for (int i = 0; i < H::nv; i++) { loc_qacc_warmstart[i] = G(qacc_warmstart, i); loc_qfrc_applied[i] = G(qfrc_applied, i); }
 #pragma unroll
-    for (int i = 0; i < H::nu; i++) la.ctrl[i] = G(ctrl, i);
+    for (int i = 0; i < H::nu; i++) loc_ctrl[i] = G(ctrl, i);
 #pragma unroll
-    for (int i = 0; i < 6 * H::nbody; i++) la.xfrc_applied[i] = G(xfrc_applied, i);
+    for (int i = 0; i < 6 * H::nbody; i++) loc_xfrc_applied[i] = G(xfrc_applied, i);
   };
   auto store_state = [&](bool inputs_too) {
 #pragma unroll
-    for (int i = 0; i < H::nq; i++) G(qpos, i) = la.qpos[i];
+    for (int i = 0; i < H::nq; i++) G(qpos, i) = loc_qpos[i];
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) G(qvel, i) = la.qvel[i];
-    G(time, 0) = la.time[0];
-    G(diverged, 0) = la.diverged[0];
+    for (int i = 0; i < H::nv; i++) G(qvel, i) = loc_qvel[i];
+    G(time, 0) = loc_time[0];
+    G(diverged, 0) = loc_diverged[0];
     if (inputs_too) {  // an auto-reset cleared them
 #pragma unroll
-      for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qfrc_applied, i) = la.qfrc_applied[i]; }
+      for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = loc_qacc_warmstart[i]; G(qfrc_applied, i) = loc_qfrc_applied[i]; }
 #pragma unroll
-      for (int i = 0; i < 6 * H::nbody; i++) G(xfrc_applied, i) = la.xfrc_applied[i];
+      for (int i = 0; i < 6 * H::nbody; i++) G(xfrc_applied, i) = loc_xfrc_applied[i];
     }
   };
   if constexpr (PHASE == 0) {
     load_inputs();
-    la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
-    la.ncon[0] = 0; la.nefc[0] = 0; la.solver_niter[0] = 0;
+    loc_acc_ncon[0] = G(acc_ncon, 0); loc_acc_nefc[0] = G(acc_nefc, 0); loc_acc_niter[0] = G(acc_niter, 0);
+    loc_ncon[0] = 0; loc_nefc[0] = 0; loc_solver_niter[0] = 0;
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) la.qacc[i] = 0;
+    for (int i = 0; i < H::nv; i++) loc_qacc[i] = 0;
     for (int s = 0; s < a.nsteps; s++) {
       if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
       env.step();
@@ -128,20 +120,20 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
     store_state(false);
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = la.qacc_warmstart[i]; G(qacc, i) = la.qacc[i]; }
+    for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = loc_qacc_warmstart[i]; G(qacc, i) = loc_qacc[i]; }
     if (a.philox) {
 #pragma unroll
-      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = loc_ctrl[i];
     }
 #pragma unroll
-    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
-    G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0];
-    G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
+    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = loc_sensordata[i];
+    G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = loc_nefc[0]; G(solver_niter, 0) = loc_solver_niter[0];
+    G(acc_ncon, 0) = loc_acc_ncon[0]; G(acc_nefc, 0) = loc_acc_nefc[0]; G(acc_niter, 0) = loc_acc_niter[0];
   } else if constexpr (PHASE == 1) {
     load_inputs();
     if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0);
     const bool did_reset = env.bad_state();
-    if (did_reset) { env.reset_data(); la.diverged[0] += 1; }
+    if (did_reset) { env.reset_data(); loc_diverged[0] += 1; }
     env.fwd_position();
     env.fwd_velocity();
     env.make_constraint();
@@ -152,33 +144,33 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     if (did_reset) store_state(true);
     if (a.philox || did_reset) {
 #pragma unroll
-      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = loc_ctrl[i];
     }
 #pragma unroll
-    for (int i = 0; i < H::nM; i++) G(qM, i) = la.qM[i];
+    for (int i = 0; i < H::nM; i++) G(qM, i) = loc_qM[i];
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) { G(qfrc_smooth, i) = la.qfrc_smooth[i]; G(qacc_smooth, i) = la.qacc_smooth[i]; }
+    for (int i = 0; i < H::nv; i++) { G(qfrc_smooth, i) = loc_qfrc_smooth[i]; G(qacc_smooth, i) = loc_qacc_smooth[i]; }
 #pragma unroll
-    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = la.sensordata[i];
-    const int nefc = la.nefc[0];
-    G(ncon, 0) = la.ncon[0]; G(nefc, 0) = nefc;
+    for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = loc_sensordata[i];
+    const int nefc = loc_nefc[0];
+    G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = nefc;
     for (int r = 0; r < nefc; r++) {
-      G(efc_D, r) = la.efc_D[r]; G(efc_aref, r) = la.efc_aref[r];
+      G(efc_D, r) = loc_efc_D[r]; G(efc_aref, r) = loc_efc_aref[r]; G(efc_pos, r) = loc_efc_pos[r]; G(efc_margin, r) = loc_efc_margin[r];
 #pragma unroll
-      for (int i = 0; i < H::nv; i++) G(efc_J, r * H::nv + i) = la.efc_J[r * H::nv + i];
+      for (int i = 0; i < H::nv; i++) G(efc_J, r * H::nv + i) = loc_efc_J[r * H::nv + i];
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) { la.qacc[i] = G(qacc, i); la.qfrc_constraint[i] = G(qfrc_constraint, i); la.qfrc_smooth[i] = G(qfrc_smooth, i); }
+    for (int i = 0; i < H::nv; i++) { loc_qacc[i] = G(qacc, i); loc_qfrc_constraint[i] = G(qfrc_constraint, i); loc_qfrc_smooth[i] = G(qfrc_smooth, i); }
 #pragma unroll
-    for (int i = 0; i < H::nM; i++) la.qM[i] = G(qM, i);
-    la.acc_ncon[0] = G(acc_ncon, 0); la.acc_nefc[0] = G(acc_nefc, 0); la.acc_niter[0] = G(acc_niter, 0);
-    la.ncon[0] = G(ncon, 0); la.nefc[0] = G(nefc, 0); la.solver_niter[0] = G(solver_niter, 0);
+    for (int i = 0; i < H::nM; i++) loc_qM[i] = G(qM, i);
+    loc_acc_ncon[0] = G(acc_ncon, 0); loc_acc_nefc[0] = G(acc_nefc, 0); loc_acc_niter[0] = G(acc_niter, 0);
+    loc_ncon[0] = G(ncon, 0); loc_nefc[0] = G(nefc, 0); loc_solver_niter[0] = G(solver_niter, 0);
     const bool redo = env.bad_acc();
     if (redo) {  // mj_checkAcc: reset and redo the forward (thread-serial solver; this path is rare)
       load_inputs();
       env.reset_data();
-      la.diverged[0] += 1;
+      loc_diverged[0] += 1;
       env.forward(false);
     }
     env.accumulate_stats();
@@ -186,12 +178,12 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     store_state(redo);
     if (redo) {
 #pragma unroll
-      for (int i = 0; i < H::nv; i++) { G(qacc, i) = la.qacc[i]; G(qacc_warmstart, i) = la.qacc_warmstart[i]; }
+      for (int i = 0; i < H::nv; i++) { G(qacc, i) = loc_qacc[i]; G(qacc_warmstart, i) = loc_qacc_warmstart[i]; }
 #pragma unroll
-      for (int i = 0; i < H::nu; i++) G(ctrl, i) = la.ctrl[i];
-      G(ncon, 0) = la.ncon[0]; G(nefc, 0) = la.nefc[0]; G(solver_niter, 0) = la.solver_niter[0];
+      for (int i = 0; i < H::nu; i++) G(ctrl, i) = loc_ctrl[i];
+      G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = loc_nefc[0]; G(solver_niter, 0) = loc_solver_niter[0];
     }
-    G(acc_ncon, 0) = la.acc_ncon[0]; G(acc_nefc, 0) = la.acc_nefc[0]; G(acc_niter, 0) = la.acc_niter[0];
+    G(acc_ncon, 0) = loc_acc_ncon[0]; G(acc_nefc, 0) = loc_acc_nefc[0]; G(acc_niter, 0) = loc_acc_niter[0];
   }
 #undef G
 }

@@ -22,16 +22,23 @@ OX_HD float ox_pow(float x, float y) { return powf(x, y); }
 OX_HD double ox_pow(double x, double y) { return pow(x, y); }
 OX_HD float ox_atan2(float y, float x) { return atan2f(y, x); }
 OX_HD double ox_atan2(double y, double x) { return atan2(y, x); }
+// sincos: ONE out-of-line copy per kernel. Inlined, CUDA's sincosf (fast path + Payne-Hanek slow path) is ~1.3 k
+// instructions per call site; with one call per hinge it was 30 % of the specialised cheetah kernel's code
+// (profiles/r1_notes.md), which is instruction-fetch bound.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ void ox_sincos_dev(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __noinline__ void ox_sincos_dev(double a, double* s, double* c) { sincos(a, s, c); }
+#endif
 OX_HD void ox_sincos(float a, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
-  sincosf(a, s, c);
+  ox_sincos_dev(a, s, c);
 #else
   *s = sinf(a); *c = cosf(a);
 #endif
 }
 OX_HD void ox_sincos(double a, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
-  sincos(a, s, c);
+  ox_sincos_dev(a, s, c);
 #else
   *s = sin(a); *c = cos(a);
 #endif
@@ -942,8 +949,9 @@ struct Env {
       T cpos[3], frame[9];
       ld<3>(cpos, b.con_pos, 3 * c);
       ld<9>(frame, b.con_frame, 9 * c);
-      OX_MLOOP
-      for (int rr = 0; rr < nrow; rr++) {
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        if (rr >= nrow) break;
         const int r = r0 + rr;
         OX_MLOOP
         for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
@@ -972,8 +980,9 @@ struct Env {
           if (dim == 1) {
             at(b.efc_J, r0 * nv + i) += jn;
           } else {
-            OX_MLOOP
-            for (int k = 1; k < dim; k++) {
+#pragma unroll
+            for (int k = 1; k < 3; k++) {  // condim <= 3: static bound so that fri / velt stay in registers
+              if (k >= dim) break;
               const T jt = dot3(frame + 3 * k, jp) * fri[k - 1];
               velt[k - 1] += jt * qv;
               at(b.efc_J, (r0 + 2 * (k - 1)) * nv + i) += jn + jt;
@@ -992,18 +1001,20 @@ struct Env {
         at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / R; at(b.efc_aref, r0) = aref;
       } else {
         T arefs[4], Rfirst = 0;
-        OX_MLOOP
-        for (int k = 1; k < dim; k++)
-          OX_MLOOP
+#pragma unroll
+        for (int k = 1; k < 3; k++)
+#pragma unroll
           for (int s = 0; s < 2; s++) {
+            if (k >= dim) continue;
             const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
             const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
             if (k == 1 && s == 0) Rfirst = R;
           }
         const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
         const T D = 1 / (2 * mu * mu * Rfirst);
-        OX_MLOOP
-        for (int r = 0; r < nrow; r++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (r >= nrow) break;
           at(b.efc_pos, r0 + r) = dist; at(b.efc_margin, r0 + r) = includemargin; at(b.efc_D, r0 + r) = D;
           at(b.efc_aref, r0 + r) = arefs[r];
         }
@@ -1060,7 +1071,7 @@ struct Env {
   }
 
   // ============================================================ A.11 primal solver (Newton / CG)
-  struct LsPt { T alpha, cost, d0, d1; };
+  struct LsPt { T alpha, cost, d0, d1, s0; };  // s0 = sum of |terms| of d0: the resolution of the derivative
 
   OX_HD LsPt ls_eval(T a, int nefc, T qg0, T qg1, T qg2) const {
     LsPt p;
@@ -1068,6 +1079,7 @@ struct Env {
     p.cost = a * a * qg2 + a * qg1 + qg0;
     p.d0 = 2 * a * qg2 + qg1;
     p.d1 = 2 * qg2;
+    p.s0 = ox_abs(2 * a * qg2) + ox_abs(qg1);
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
@@ -1076,6 +1088,7 @@ struct Env {
         p.cost += (T)0.5 * Dx * x;
         p.d0 += Dx * jv;
         p.d1 += Dj * jv;
+        p.s0 += ox_abs(Dx * jv);
       }
     }
     if (p.d1 < (T)OX_MINVAL) p.d1 = (T)OX_MINVAL;
@@ -1276,7 +1289,7 @@ struct Env {
         if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = (T)0.5 * (lo.alpha + hi.alpha);
         if (ox_abs(a - cur.alpha) <= Eps<T>::v() * ox_abs(a)) break;
         cur = ls_eval(a, nefc, gauss, qg1, qg2);
-        if (ox_abs(cur.d0) < gtol) break;
+        if (ox_abs(cur.d0) < gtol || ox_abs(cur.d0) <= 8 * Eps<T>::v() * cur.s0) break;  // converged, or phi' below its own round-off
         if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
       }
       const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
