@@ -1,0 +1,87 @@
+"""Feature-coverage models ("zoo"): every joint type, geom/contact primitive, actuator shortcut, sensor and option branch
+the MJCF subset accepts, so that parity tests exercise code paths the five BASELINE models do not."""
+
+ZOO_A = """
+<mujoco model="zoo_a">
+  <compiler angle="radian"/>
+  <option timestep="0.004" impratio="2"/>
+  <default>
+    <geom friction="0.8 0.01 0.001" solref="0.015 1.1" solimp="0.85 0.96 0.002 0.4 3"/>
+  </default>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1" margin="0.01" gap="0.002"/>
+    <body name="boxy" pos="0 0 0.32" euler="0.1 0.2 0.3">
+      <freejoint name="boxroot"/>
+      <geom name="box" type="box" size="0.15 0.1 0.2" density="400"/>
+      <site name="top" pos="0 0 0.2" euler="0 0.3 0"/>
+      <body name="arm" pos="0.15 0 0.1">
+        <joint name="shoulder" type="ball" pos="0 0 0" stiffness="3" damping="0.4"/>
+        <geom name="arm" type="capsule" fromto="0 0 0 0.3 0 0" size="0.04"/>
+        <body name="hand" pos="0.3 0 0">
+          <joint name="wrist" type="hinge" axis="0 1 0" range="-1 1" damping="0.05" armature="0.01" stiffness="1" springref="0.2"/>
+          <joint name="extend" type="slide" axis="1 0 0" range="-0.05 0.1" damping="1" margin="0.01"/>
+          <geom name="hand" type="sphere" pos="0.08 0 0" size="0.06" condim="1"/>
+          <site name="tip" pos="0.14 0 0"/>
+        </body>
+      </body>
+    </body>
+    <body name="ball" pos="0.6 0.1 0.12">
+      <freejoint name="ballroot"/>
+      <geom name="ball" type="sphere" size="0.1" priority="1" friction="0.3 0.02 0.002"/>
+    </body>
+    <body name="rod" pos="-0.5 0 0.06" euler="0 1.5707963 0">
+      <freejoint name="rodroot"/>
+      <geom name="rod" type="capsule" size="0.05 0.2" solmix="3"/>
+      <inertial pos="0 0 0.01" mass="1.5" fullinertia="0.03 0.03 0.004 0.0005 0 0"/>
+    </body>
+  </worldbody>
+  <contact><exclude body1="boxy" body2="hand"/><exclude body1="boxy" body2="ball"/><exclude body1="boxy" body2="rod"/></contact>
+  <actuator>
+    <position name="wrist_pos" joint="wrist" kp="4" kv="0.3" ctrlrange="-1 1"/>
+    <velocity name="extend_vel" joint="extend" kv="2" forcerange="-3 3"/>
+    <general name="wrist_gen" joint="wrist" gear="0.5" gaintype="affine" gainprm="1 0.2 0.1" biastype="affine" biasprm="0.05 -0.3 -0.02"/>
+  </actuator>
+  <sensor>
+    <jointpos joint="wrist"/> <jointvel joint="extend"/>
+    <actuatorpos actuator="wrist_pos"/> <actuatorvel actuator="extend_vel"/> <actuatorfrc actuator="wrist_gen"/>
+    <framepos objtype="site" objname="tip"/> <framequat objtype="site" objname="top"/> <framepos objtype="body" objname="hand"/>
+    <framepos objtype="xbody" objname="arm"/> <framepos objtype="geom" objname="arm"/>
+    <framelinvel objtype="site" objname="tip"/> <frameangvel objtype="body" objname="hand"/>
+    <velocimeter site="tip"/> <gyro site="top"/>
+    <subtreecom body="boxy"/> <subtreelinvel body="boxy"/> <subtreelinvel body="arm"/> <clock/>
+  </sensor>
+</mujoco>
+"""
+
+# CG solver, RK4 with contacts, capsule-capsule and sphere-capsule pairs, frictionless pair, xfrc/qfrc applied in tests
+ZOO_B = """
+<mujoco model="zoo_b">
+  <compiler angle="degree"/>
+  <option timestep="0.003" integrator="RK4" solver="CG" tolerance="1e-10" iterations="200">
+    <flag warmstart="disable"/>
+  </option>
+  <worldbody>
+    <geom type="plane" size="3 3 0.1" condim="1"/>
+    <body name="a" pos="0 0 0.25" euler="0 80 10">
+      <freejoint/>
+      <geom name="ca" type="capsule" size="0.06 0.25"/>
+      <body name="a2" pos="0 0 0.3">
+        <joint name="elbow" type="hinge" axis="1 0 0" range="-60 60" damping="0.02"/>
+        <geom name="ca2" type="capsule" fromto="0 0 0 0 0 0.3" size="0.05"/>
+      </body>
+    </body>
+    <body name="b" pos="0.05 0.1 0.42" euler="70 0 0">
+      <freejoint/>
+      <geom name="cb" type="capsule" size="0.05 0.2" condim="1"/>
+    </body>
+    <body name="s" pos="-0.1 -0.05 0.6">
+      <freejoint/>
+      <geom name="sph" type="sphere" size="0.08"/>
+    </body>
+  </worldbody>
+  <actuator><motor joint="elbow" gear="2" ctrlrange="-1 1"/></actuator>
+  <sensor><subtreelinvel body="a"/><framelinvel objtype="geom" objname="sph"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B}
