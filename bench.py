@@ -322,10 +322,39 @@ def main():
                "d2h_bytes_per_step": nenv * (nq + nv) * 4, "ms_per_step": 1e3 * e2e_s / Ke,
                "timing": "host wall clock around K steps, each = ox_batch_set(ctrl, pinned host) + ox_batch_step(1) + "
                          "ox_batch_get_many(qpos, qvel -> pinned host, one sync); max over ranks"}
-        b.ctrl_philox(True, SEED)
         finite = bool(np.isfinite(obs_q.numpy()).all())
+        # ---------------- N1: the same loop through the on-device Environment / Task layer (ox_env_step): actions in,
+        # observation + reward + discount + finished out, reward / finish / auto-reset evaluated on the GPU
+        import oxide_control_b200 as ox
+        task = ox.TaskSpec(obs=[("qpos", 0, nq), ("qvel", 0, nv)], reward=[("qvel", 0, "linear", 1.0)] + [("ctrl", i, "square", -0.1) for i in range(nu)],
+                           time_limit=1000 * model.timestep, discount=0.99, init_qpos_noise=0.1, init_qvel_noise=0.1, seed=SEED)
+        env = ox.BatchedEnvironment(b, task)
+        obs = torch.empty((nenv, env.obs_dim), dtype=torch.float32).pin_memory()
+        rew = torch.empty(nenv, dtype=torch.float32).pin_memory()
+        dis = torch.empty(nenv, dtype=torch.float32).pin_memory()
+        fin = torch.empty(nenv, dtype=torch.uint8).pin_memory()
+        def env_step(i):
+            env.step_ptr(ctrl_pool[i % npool].data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), fin.data_ptr(), A.F32, A.MEM_HOST)
+        for i in range(3):
+            env_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            env_step(i)
+        b.sync()
+        t1 = time.perf_counter()
+        barrier()
+        env_s = max_over_ranks(t1 - t0)
+        env_line = {"value": world * nenv * Ke / env_s, "unit": UNIT, "h2d_bytes_per_step": nenv * nu * 4,
+                    "d2h_bytes_per_step": nenv * (env.obs_dim * 4 + 4 + 4 + 1), "ms_per_step": 1e3 * env_s / Ke,
+                    "timing": "host wall clock around K x ox_env_step(action pinned host -> obs, reward, discount, finished pinned host); "
+                              "reward, finish test and auto-reset on device; max over ranks"}
+        finite = finite and bool(np.isfinite(obs.numpy()).all())
+        env.close()
+        b.ctrl_philox(True, SEED)
     else:
         finite = True
+        env_line = None
 
     # ---------------- roofline of the dominant kernel (the step kernel: the only kernel of a step besides the 1-thread counter bump)
     peaks, peak_src = load_peaks()
@@ -369,7 +398,7 @@ def main():
                        "envs_per_gpu": nenv, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "none (state resident by design)" if args.no_flush else
                              "L2 flushed (256 MiB memset) between timed steps, outside the per-step event pairs"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "env_step": env_line, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "value_resident_one_launch": value_resident, "ms_per_step_resident": resident_ms / K,
             "mean_ncon": mean_ncon, "mean_nefc": mean_nefc, "mean_solver_iters": mean_iter, "diverged_resets": st[3],
             "finite": finite, "timing": "CUDA events on the library's stream around every step, summed; max over ranks",

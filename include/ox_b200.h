@@ -238,6 +238,59 @@ OX_API const char* ox_spec_name(int32_t i);
 OX_API ox_status ox_batch_stage_times(ox_batch* b, int32_t reps, double* out_ms, int32_t* nstage);
 OX_API const char* ox_stage_name(int32_t i);
 
+/* ---------------------------------------------------------------------------------------------
+ * N1: batched Environment / Task — the direct caller of the step.
+ * Mirrors reference src/lib.rs:8-26 (traits Task / Observation / Action) and :50-88 (Environment::reset / step,
+ * enum TimeStep) for a whole batch, evaluated ON DEVICE so that an RL loop crosses PCIe once per step in each
+ * direction (actions in; observation, reward, discount, finished out). The reference's user-written trait bodies
+ * become a declarative task description, because user code cannot run inside the kernel:
+ *   Observation::generate        -> concatenation of field slices                         (ox_obs_segment)
+ *   Task::get_reward             -> bias + sum_k weight_k * f_k(field element)            (ox_reward_term)
+ *   Task::should_finish_episode  -> any element outside [lo, hi], or time >= time_limit   (ox_finish_cond)
+ *   Task::discount               -> constant
+ *   Task::init_episode           -> mj_resetData, qpos0 + U(-a,a) on hinge/slide coordinates, qvel = U(-b,b);
+ *                                   Philox4x32-10 keyed on (seed; global env id, episode index, word)
+ *   Action::apply                -> ctrl[env][:] = action[env][:]  (Actuators::set for every actuator)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ox_env ox_env;
+typedef struct ox_obs_segment { int32_t field, first, count; } ox_obs_segment;  /* real fields only */
+enum { OX_REWARD_LINEAR = 0 /* w*x */, OX_REWARD_SQUARE = 1 /* w*x^2 */, OX_REWARD_ABS = 2 /* w*|x| */ };
+typedef struct ox_reward_term { int32_t field, index, kind, reserved_; double weight; } ox_reward_term;
+typedef struct ox_finish_cond { int32_t field, index; double lo, hi; } ox_finish_cond; /* finish if x < lo or x > hi */
+typedef struct ox_task_spec {
+  int32_t nobs;     const ox_obs_segment* obs;
+  int32_t nreward;  const ox_reward_term* reward;
+  int32_t nfinish;  const ox_finish_cond* finish;
+  double reward_bias;
+  double time_limit;       /* <= 0: none; otherwise finish once time >= time_limit - timestep/2 */
+  double discount;         /* Task::discount, src/lib.rs:12 */
+  double init_qpos_noise;  /* Task::init_episode, src/lib.rs:13 */
+  double init_qvel_noise;
+  uint64_t seed;
+  int32_t frame_skip;      /* mj_steps per Environment::step (>= 1; the reference does exactly 1, src/lib.rs:65) */
+  int32_t auto_reset;      /* 1: a finished env is re-initialised (init_episode) inside the same call, after its terminal
+                              observation has been written, so the next step starts its next episode */
+} ox_task_spec;
+
+OX_API void ox_task_spec_default(ox_task_spec* spec);
+/* Environment::new(physics, task), src/lib.rs:33-36. The env borrows the batch (which must outlive it). */
+OX_API ox_status ox_env_create(ox_batch* b, const ox_task_spec* spec, ox_env** out);
+OX_API void ox_env_free(ox_env* e);
+OX_API int32_t ox_env_obs_dim(const ox_env* e);
+/* Environment::reset, src/lib.rs:58-61: init_episode on every env, mj_forward (so derived fields / sensordata are
+ * fresh for the first observation), then Observation::generate -> obs[nenv][obs_dim] (env-major, `dtype`, in `mem`). */
+OX_API ox_status ox_env_reset(ox_env* e, void* obs, int32_t dtype, int32_t mem);
+/* Environment::step, src/lib.rs:63-87: apply action[nenv][nu] (NULL = leave ctrl alone, e.g. the Philox stream),
+ * frame_skip x mj_step, observation, reward, finish test. TimeStep::Step{observation,reward,discount} /
+ * TimeStep::Finish{observation,reward} come back as arrays: obs[nenv][obs_dim], reward[nenv], discount[nenv]
+ * (0 for a Finish), finished[nenv] (uint8). Any output pointer may be NULL. All buffers live in `mem`;
+ * host buffers are complete on return. An env that MuJoCo's mj_check* auto-reset during the step also finishes. */
+OX_API ox_status ox_env_step(ox_env* e, const void* action, void* obs, void* reward, void* discount, uint8_t* finished,
+                             int32_t dtype, int32_t mem);
+/* episode bookkeeping since creation: out[0] = finished episodes, out[1] = sum of their returns,
+ * out[2] = sum of their lengths (env steps) */
+OX_API ox_status ox_env_stats(ox_env* e, double* out3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,37 @@ class BatchedPhysics {
   ox_batch* b_ = nullptr;
 };
 
+// N1: Environment<T: Task> over a BatchedPhysics (src/lib.rs:28-88), evaluated on device from a declarative task.
+struct BatchedTimeStep {                               // enum TimeStep<O> for every env (src/lib.rs:50-60)
+  std::vector<double> observation, reward, discount;   // [nenv*obs_dim], [nenv], [nenv] (discount 0 = Finish)
+  std::vector<uint8_t> finished;                       // [nenv]
+};
+class BatchedEnvironment {
+ public:
+  BatchedEnvironment(BatchedPhysics& physics, const ox_task_spec& task) : physics_(physics) { check(ox_env_create(physics.handle(), &task, &e_)); }
+  BatchedEnvironment(const BatchedEnvironment&) = delete;
+  ~BatchedEnvironment() { ox_env_free(e_); }
+  static ox_task_spec default_task() { ox_task_spec t; ox_task_spec_default(&t); return t; }
+  int obs_dim() const { return ox_env_obs_dim(e_); }
+  BatchedPhysics& physics_mut() { return physics_; }                                                              // :45-47
+  std::vector<double> reset() {                                                                                  // :62-65
+    std::vector<double> obs((size_t)nenv() * obs_dim());
+    check(ox_env_reset(e_, obs.data(), OX_F64, OX_MEM_HOST));
+    return obs;
+  }
+  BatchedTimeStep step(const double* action) {                                                                   // :67-87
+    BatchedTimeStep ts;
+    ts.observation.resize((size_t)nenv() * obs_dim()); ts.reward.resize(nenv()); ts.discount.resize(nenv()); ts.finished.resize(nenv());
+    check(ox_env_step(e_, action, ts.observation.data(), ts.reward.data(), ts.discount.data(), ts.finished.data(), OX_F64, OX_MEM_HOST));
+    return ts;
+  }
+  ox_env* handle() { return e_; }
+ private:
+  int nenv() const { return ox_batch_nenv(physics_.handle()); }
+  BatchedPhysics& physics_;
+  ox_env* e_ = nullptr;
+};
+
 class Physics;
 class Actuators {                                  // src/physics.rs:65-79
  public:

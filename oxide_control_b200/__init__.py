@@ -8,6 +8,7 @@ loudly if it has not been built; there is no fallback implementation.
 from . import _abi
 from .physics import (BatchedPhysics, Physics, Model, Actuators, ObjectId, obj, joint, Error, MujocoError, MjsError,
                       NameNotFound, PhysicsDiverged, JointTypeNotMatch, CudaError)
+from .environment import Task, Observation, Action, Environment, TimeStep, TaskSpec, BatchedEnvironment, BatchedTimeStep
 from . import models
 
 _abi.lib()  # fail loudly at import time when the extension is missing
@@ -15,4 +16,5 @@ _abi.lib()  # fail loudly at import time when the extension is missing
 mjMAXVAL = 1e10
 mjMINVAL = 1e-15
 __all__ = ["BatchedPhysics", "Physics", "Model", "Actuators", "ObjectId", "obj", "joint", "Error", "MujocoError", "MjsError",
-           "NameNotFound", "PhysicsDiverged", "JointTypeNotMatch", "CudaError", "models", "mjMAXVAL", "mjMINVAL"]
+           "NameNotFound", "PhysicsDiverged", "JointTypeNotMatch", "CudaError", "models", "mjMAXVAL", "mjMINVAL",
+           "Task", "Observation", "Action", "Environment", "TimeStep", "TaskSpec", "BatchedEnvironment", "BatchedTimeStep"]

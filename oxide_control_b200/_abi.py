@@ -46,6 +46,29 @@ class BatchConfig(C.Structure):
     ]
 
 
+class ObsSegment(C.Structure):
+    _fields_ = [("field", C.c_int32), ("first", C.c_int32), ("count", C.c_int32)]
+
+
+class RewardTerm(C.Structure):
+    _fields_ = [("field", C.c_int32), ("index", C.c_int32), ("kind", C.c_int32), ("reserved_", C.c_int32), ("weight", C.c_double)]
+
+
+class FinishCond(C.Structure):
+    _fields_ = [("field", C.c_int32), ("index", C.c_int32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class TaskSpec(C.Structure):
+    _fields_ = [
+        ("nobs", C.c_int32), ("obs", C.POINTER(ObsSegment)), ("nreward", C.c_int32), ("reward", C.POINTER(RewardTerm)),
+        ("nfinish", C.c_int32), ("finish", C.POINTER(FinishCond)), ("reward_bias", C.c_double), ("time_limit", C.c_double),
+        ("discount", C.c_double), ("init_qpos_noise", C.c_double), ("init_qvel_noise", C.c_double), ("seed", C.c_uint64),
+        ("frame_skip", C.c_int32), ("auto_reset", C.c_int32),
+    ]
+
+
+REWARD_LINEAR, REWARD_SQUARE, REWARD_ABS = range(3)
+
 # every symbol include/ox_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -85,6 +108,13 @@ SYMBOLS = {
     "ox_spec_name": (C.c_char_p, [C.c_int32]),
     "ox_batch_stage_times": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "ox_stage_name": (C.c_char_p, [C.c_int32]),
+    "ox_task_spec_default": (None, [C.POINTER(TaskSpec)]),
+    "ox_env_create": (C.c_int32, [_P, C.POINTER(TaskSpec), C.POINTER(_P)]),
+    "ox_env_free": (None, [_P]),
+    "ox_env_obs_dim": (C.c_int32, [_P]),
+    "ox_env_reset": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
+    "ox_env_step": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32]),
+    "ox_env_stats": (C.c_int32, [_P, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -20,6 +20,7 @@
 #include "ox_kernels.cuh"
 #include "ox_spec.cuh"
 #include "ox_stages.cuh"
+#include "ox_batch_internal.cuh"
 
 namespace ox {
 
@@ -112,46 +113,7 @@ cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int
 bool solve_coop_eligible(const ox_model_tables& t);
 }  // namespace ox
 
-struct ox_batch {
-  const ox_model* model = nullptr;
-  ox_batch_config cfg{};
-  int nenv = 0, stride = 0, block = 32, grid = 0, lanes = 32;
-  bool f64 = false;
-  cudaStream_t stream = nullptr;
-  unsigned char* arena = nullptr;
-  size_t arena_bytes = 0;
-  unsigned char* d_blob = nullptr;
-  int blob_bytes = 0;
-  DevBatch<float> bf{};
-  DevBatch<double> bd{};
-  std::map<int, FieldInfo> fields;
-  long long launches = 0;
-  int philox = 0;
-  uint64_t seed = 0;
-  long long* d_step = nullptr;
-  void* d_tmp = nullptr;  // staging for bulk I/O
-  size_t d_tmp_bytes = 0;
-  void* h_tmp = nullptr;  // pinned staging for per-env I/O
-  size_t h_tmp_bytes = 0;
-  uint8_t* d_mask = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  cudaGraph_t graph = nullptr;
-  bool split = false;  // fused mode: specialised PRE/POST kernels around the warp-cooperative solver
-  bool coop = false;  // staged mode: warp-cooperative Newton solver (ox_solve_coop.cu) instead of the thread-per-env solve stage
-  const ox::SpecEntry* spec = nullptr;  // model-specialised step kernel, when one was compiled in for this model
-  ox::SpecRuntime spec_rt{};
-};
-
 namespace {
-
-#define CU_TRY(expr)                                                                                   \
-  do {                                                                                                 \
-    cudaError_t err__ = (expr);                                                                        \
-    if (err__ != cudaSuccess) {                                                                        \
-      ox::set_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #expr);           \
-      return OX_ERR_CUDA;                                                                              \
-    }                                                                                                  \
-  } while (0)
 
 template <typename T> DevBatch<T>& dev(ox_batch* b);
 template <> DevBatch<float>& dev<float>(ox_batch* b) { return b->bf; }
@@ -476,6 +438,7 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
 #undef SETST
 #undef SETATTR
   }
+  CU_TRY(cudaDeviceSynchronize());  // the uploads / memsets above ran on the legacy stream; the batch's stream is non-blocking
   ox_batch* raw = b.release();
   ox_status s = ox_batch_reset(raw, nullptr);
   if (s == OX_OK) s = ox_batch_sync(raw);

@@ -15,6 +15,19 @@ pub const OX_ERR_IO: ox_status = 6; // -> Error::Mujoco
 
 #[repr(C)] pub struct ox_model { _private: [u8; 0] }
 #[repr(C)] pub struct ox_batch { _private: [u8; 0] }
+#[repr(C)] pub struct ox_env { _private: [u8; 0] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ox_obs_segment { pub field: i32, pub first: i32, pub count: i32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ox_reward_term { pub field: i32, pub index: i32, pub kind: i32, pub reserved_: i32, pub weight: c_double }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ox_finish_cond { pub field: i32, pub index: i32, pub lo: c_double, pub hi: c_double }
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct ox_task_spec {
+    pub nobs: i32, pub obs: *const ox_obs_segment, pub nreward: i32, pub reward: *const ox_reward_term,
+    pub nfinish: i32, pub finish: *const ox_finish_cond, pub reward_bias: c_double, pub time_limit: c_double,
+    pub discount: c_double, pub init_qpos_noise: c_double, pub init_qvel_noise: c_double, pub seed: u64,
+    pub frame_skip: i32, pub auto_reset: i32,
+}
+pub const OX_REWARD_LINEAR: i32 = 0; pub const OX_REWARD_SQUARE: i32 = 1; pub const OX_REWARD_ABS: i32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -69,5 +82,14 @@ extern "C" {
     pub fn ox_spec_name(i: i32) -> *const c_char;
     pub fn ox_batch_stage_times(b: *mut ox_batch, reps: i32, out_ms: *mut c_double, nstage: *mut i32) -> ox_status;
     pub fn ox_stage_name(i: i32) -> *const c_char;
+    // N1: batched Environment / Task (src/lib.rs:8-88)
+    pub fn ox_task_spec_default(spec: *mut ox_task_spec);
+    pub fn ox_env_create(b: *mut ox_batch, spec: *const ox_task_spec, out: *mut *mut ox_env) -> ox_status;
+    pub fn ox_env_free(e: *mut ox_env);
+    pub fn ox_env_obs_dim(e: *const ox_env) -> i32;
+    pub fn ox_env_reset(e: *mut ox_env, obs: *mut c_void, dtype: i32, mem: i32) -> ox_status;
+    pub fn ox_env_step(e: *mut ox_env, action: *const c_void, obs: *mut c_void, reward: *mut c_void, discount: *mut c_void,
+                       finished: *mut u8, dtype: i32, mem: i32) -> ox_status;
+    pub fn ox_env_stats(e: *mut ox_env, out3: *mut c_double) -> ox_status;
 }
 #[allow(unused)] fn _types(_: c_int) {}

@@ -110,3 +110,34 @@ impl Physics {
     pub fn xfrc_applied(&mut self, body: usize) -> [f64; 6] { let mut v = [0.0; 6]; let _ = self.data.get1(sys::OX_F_XFRC_APPLIED, 0, 6 * body, &mut v); v }
     pub fn mocap_pos(&mut self, _body: usize) -> Option<[f64; 3]> { None }          // src/physics.rs:155-157
 }
+
+// ---- N1: Environment<T: Task> for a whole batch, evaluated on device (reference src/lib.rs:28-88) ----
+/// `enum TimeStep<O>` for every env: `finished[e]` selects `Finish` (no discount) or `Step`.
+pub struct BatchedTimeStep<'a> { pub observation: &'a [f32], pub reward: &'a [f32], pub discount: &'a [f32], pub finished: &'a [u8] }
+pub struct BatchedEnvironment<'p> {
+    raw: *mut sys::ox_env, physics: &'p mut BatchedPhysics, obs_dim: usize,
+    obs: Vec<f32>, reward: Vec<f32>, discount: Vec<f32>, finished: Vec<u8>,
+}
+impl<'p> BatchedEnvironment<'p> {
+    /// `Environment::new(physics, task)` (src/lib.rs:33-36); the task is declarative because it runs inside a kernel.
+    pub fn new(physics: &'p mut BatchedPhysics, task: &sys::ox_task_spec) -> Result<Self, Error> {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { sys::ox_env_create(physics.raw, task, &mut raw) })?;
+        let (n, d) = (physics.nenv(), unsafe { sys::ox_env_obs_dim(raw) } as usize);
+        Ok(Self { raw, physics, obs_dim: d, obs: vec![0.0; n * d], reward: vec![0.0; n], discount: vec![0.0; n], finished: vec![0; n] })
+    }
+    pub fn physics_mut(&mut self) -> &mut BatchedPhysics { self.physics }                                   // src/lib.rs:45-47
+    pub fn obs_dim(&self) -> usize { self.obs_dim }
+    /// `Environment::reset` (src/lib.rs:62-65)
+    pub fn reset(&mut self) -> Result<&[f32], Error> {
+        check(unsafe { sys::ox_env_reset(self.raw, self.obs.as_mut_ptr() as *mut _, sys::OX_F32, sys::OX_MEM_HOST) })?;
+        Ok(&self.obs)
+    }
+    /// `Environment::step` (src/lib.rs:67-87): `action` is `[nenv][nu]`.
+    pub fn step(&mut self, action: &[f32]) -> Result<BatchedTimeStep<'_>, Error> {
+        check(unsafe { sys::ox_env_step(self.raw, action.as_ptr() as *const _, self.obs.as_mut_ptr() as *mut _, self.reward.as_mut_ptr() as *mut _,
+                                        self.discount.as_mut_ptr() as *mut _, self.finished.as_mut_ptr(), sys::OX_F32, sys::OX_MEM_HOST) })?;
+        Ok(BatchedTimeStep { observation: &self.obs, reward: &self.reward, discount: &self.discount, finished: &self.finished })
+    }
+}
+impl Drop for BatchedEnvironment<'_> { fn drop(&mut self) { unsafe { sys::ox_env_free(self.raw) } } }

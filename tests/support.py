@@ -211,3 +211,14 @@ def rel_err(a: np.ndarray, b: np.ndarray) -> float:
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def philox4x32_10(ctr, key):
+    """Pure-Python Philox4x32-10 (Random123), independent of both the oracle and the product; pinned by tests/test_philox.py."""
+    c0, c1, c2, c3 = [int(x) & 0xFFFFFFFF for x in ctr]
+    k0, k1 = [int(x) & 0xFFFFFFFF for x in key]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3

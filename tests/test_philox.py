@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 import oxide_control_b200 as ox
-from support import HostBatch, OracleData, SEED, hostcheck_lib, oracle_lib
+from support import HostBatch, OracleData, SEED, hostcheck_lib, oracle_lib, philox4x32_10
 
 KATS = [
     ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
@@ -22,6 +22,7 @@ def test_philox_known_answers():
         o2 = (C.c_uint32 * 4)()
         hostcheck_lib().hc_philox(*ctr, *key, o2)
         assert tuple(o2) == want
+        assert philox4x32_10(ctr, key) == want      # the pure-Python copy used by tests/test_env_layer.py
 
 
 def test_control_stream_is_identical_in_fp32_fp64_and_oracle():
