@@ -171,7 +171,7 @@ typedef struct ox_batch_config {
   int32_t use_graph;     /* capture the per-step launch sequence in a CUDA graph */
   int32_t block_threads; /* 0 = default */
   int64_t env_id_offset; /* global env id of env 0 (multi-GPU sharding; keys the Philox control stream) */
-  double tolerance;      /* <0 = model's */
+  double tolerance;      /* <0 = model's, floored at 8*eps of `precision` (1e-6 in fp32; no effect in fp64) */
   int32_t specialize;    /* 1 (default): use the model-specialised step kernel when one was compiled in (fused mode) */
   int32_t lanes_per_warp; /* active envs per warp, 1..32; 0 = auto (thin warps while the batch cannot fill every SM scheduler) */
   int32_t coop_solver;   /* staged mode: warp-per-env Newton solver; -1 auto (on when eligible and nv > 12), 0 off, 1 on */

@@ -422,7 +422,7 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     b->spec = ox::find_spec(ox::model_hash(t));
     b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;
     b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
-    b->spec_rt.tolerance = cfg->tolerance >= 0 ? cfg->tolerance : t.tolerance;
+    b->spec_rt.tolerance = b->f64 ? effective_tolerance<double>(t, cfg->tolerance) : effective_tolerance<float>(t, cfg->tolerance);
     b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && ox::solve_coop_eligible(t) && t.integrator == OX_INT_EULER;
   }
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));

@@ -51,6 +51,16 @@ struct DevModel {
 #undef OX_X
 };
 
+// Solver tolerance a batch runs with: the caller's if given, else the model's, but never below the resolution of the
+// arithmetic type (8 eps): a relative gradient of 1e-8 (MuJoCo's default, meant for doubles) cannot be resolved in fp32
+// and only buys extra iterations on round-off. No effect in fp64 (8 eps = 1.8e-15). ORACLE_DECISIONS #8, DESIGN 4.
+template <typename T>
+inline double effective_tolerance(const ox_model_tables& t, double user) {
+  if (user >= 0) return user;
+  const double floor_t = 8.0 * (sizeof(T) == 4 ? 1.1920928955078125e-7 : 2.220446049250313e-16);
+  return t.tolerance > floor_t ? t.tolerance : floor_t;
+}
+
 template <typename T>
 inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int iterations, int ls_iterations, double tolerance) {
   BlobHeader h;
@@ -63,7 +73,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   h.disableflags = t.disableflags;
   h.timestep = t.timestep;
   for (int k = 0; k < 3; k++) h.gravity[k] = t.gravity[k];
-  h.tolerance = tolerance >= 0 ? tolerance : t.tolerance;
+  h.tolerance = effective_tolerance<T>(t, tolerance);
   h.ls_tolerance = t.ls_tolerance; h.impratio = t.impratio; h.meaninertia = t.meaninertia;
   h.any_damping = 0;
   for (int i = 0; i < t.nv; i++) if (t.dof_damping[i] > 0) h.any_damping = 1;

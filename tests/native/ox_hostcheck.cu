@@ -43,7 +43,7 @@ HC_API hc_batch* hc_create(const ox_model_tables* t, int nenv, int precision, in
   b->hash = model_hash(*t);
   b->rt.iterations = iterations > 0 ? iterations : t->iterations;
   b->rt.ls_iterations = ls_iterations > 0 ? ls_iterations : t->ls_iterations;
-  b->rt.tolerance = tolerance >= 0 ? tolerance : t->tolerance;
+  b->rt.tolerance = precision == 1 ? effective_tolerance<double>(*t, tolerance) : effective_tolerance<float>(*t, tolerance);
   b->blob = b->f64 ? build_blob<double>(*t, iterations, ls_iterations, tolerance) : build_blob<float>(*t, iterations, ls_iterations, tolerance);
   size_t bytes = b->f64 ? layout_arena<double>(*t, b->stride, nullptr, nullptr, nullptr) : layout_arena<float>(*t, b->stride, nullptr, nullptr, nullptr);
   b->arena.assign(bytes + 256, 0);
