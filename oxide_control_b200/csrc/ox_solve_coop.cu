@@ -3,10 +3,12 @@
 // one thread's registers (humanoid class: nv = 27, H = 27x27): there the serial solve is >90 % of the step and the GPU
 // holds only nenv/32 warps. Here
 //   * every dof-vector (qacc, M*qacc, grad, search, ...) is one register per lane,
-//   * lane i owns row i of the dense Hessian H = M + J' D J, kept in shared memory (32 x 33 per warp) so that the
-//     rank-1 row updates, the right-looking Cholesky and the triangular solves are short rolled loops (v1 held H in
-//     registers, which forces full unrolling: 34 k-instruction body, `no_instruction` stall 10.7 cycles per issue -
-//     profiles/r1_ncu_coop_v1_humanoid_f32_4096.txt); M's row stays in registers,
+//   * lane i owns row i of the dense Hessian H = M + J' D J in 32 registers: the rank-1 row updates read the staged J
+//     row with broadcast shared-memory loads, the right-looking Cholesky exchanges one shuffle per (column, row) pair,
+//     the triangular solves one shuffle / butterfly per column. Only this block is unrolled (about 3 k instructions, one
+//     call site); v1 unrolled everything at three call sites (34 k instructions, `no_instruction` 10.7 cycles per issue -
+//     profiles/r1_ncu_coop_v1_humanoid_f32_4096.txt), v2/v3 kept H in shared memory (4 instructions and a shared-memory
+//     round trip per multiply-add); M's row also stays in registers,
 //   * constraint rows are distributed round-robin over lanes (row r -> lane r % 32) for jar / Jv / line search, their
 //     per-row scalars in per-warp shared arrays,
 //   * the active part of J is staged once per solve into shared memory ([row][dof], padded) because the batch stores it
@@ -29,8 +31,8 @@ template <typename T> __device__ __forceinline__ T wsum(T v) {
 }
 template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// per-warp shared memory: H (32 x 33), five row arrays of RCAP, J staging (SROWS x 33)
-__host__ __device__ inline size_t coop_warp_words() { return 32 * 33 + 5 * (size_t)COOP_RCAP + COOP_SROWS * 33; }
+// per-warp shared memory: five row arrays of RCAP, J staging (SROWS x 33)
+__host__ __device__ inline size_t coop_warp_words() { return 5 * (size_t)COOP_RCAP + COOP_SROWS * 33; }
 
 template <typename T>
 __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b) {
@@ -53,13 +55,13 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
     if (lane == 0) b.solver_niter[ue] = 0;
     return;
   }
-  T* Hs = reinterpret_cast<T*>(ox_smem + ((bytes + 127) / 128) * 128) + (size_t)wib * coop_warp_words();
-  T* sJ = Hs + 32 * 33 + 5 * COOP_RCAP;
+  T* srow = reinterpret_cast<T*>(ox_smem + ((bytes + 127) / 128) * 128) + (size_t)wib * coop_warp_words();
+  T* sJ = srow + 5 * COOP_RCAP;
   // per-row scalars: shared memory (stride 1) for the common case, the arena's own row arrays (stride S) when an env has
   // more rows than RCAP. efc_D / efc_aref are then read in place; jar, Jv and force use s_Jaref, s_Jv, efc_force.
   const bool small = nefc <= COOP_RCAP;
   const uint32_t rs = small ? 1u : S;
-  T* rowD = small ? Hs + 32 * 33 : b.efc_D + ue;
+  T* rowD = small ? srow : b.efc_D + ue;
   T* rowA = small ? rowD + COOP_RCAP : b.efc_aref + ue;
   T* rowJar = small ? rowA + COOP_RCAP : b.s_Jaref + ue;
   T* rowJv = small ? rowJar + COOP_RCAP : b.s_Jv + ue;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
 #define ROW(arr, r) arr[(uint32_t)(r) * rs]
   const int nsm = nefc < COOP_SROWS ? nefc : COOP_SROWS;
   for (int r = 0; r < nsm; r++)
-    if (me) sJ[r * 33 + lane] = GA(efc_J, r * nv + lane);
+    sJ[r * 33 + lane] = me ? GA(efc_J, r * nv + lane) : (T)0;
   if (small)
     for (int r = lane; r < nefc; r += 32) { rowD[r] = GA(efc_D, r); rowA[r] = GA(efc_aref, r); }
   __syncwarp();
@@ -213,42 +215,57 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
     {
       grad = me ? Ma - fs - fc : (T)0;
       gnorm = ox_sqrt(wsum(grad * grad));
-      T* Hr = Hs + lane * 33;
+      // row `lane` of H accumulates in registers (static indices: the j loops are fully unrolled, the row loop is not)
+      T Hreg[32];
 #pragma unroll
-      for (int j = 0; j < 32; j++) Hr[j] = Mrow[j];
+      for (int j = 0; j < 32; j++) Hreg[j] = Mrow[j];
       for (int r = 0; r < nefc; r++) {
         if (!(ROW(rowJar, r) < 0)) continue;  // warp-uniform
-        const T Jri = me ? Jat(r, lane) : (T)0;
-        const T s = ROW(rowD, r) * Jri;
-#pragma unroll 4
-        for (int j = 0; j < nv; j++) Hr[j] += s * bcast(Jri, j);
-      }
-      __syncwarp();
-      for (int kk = 0; kk < nv; kk++) {  // right-looking Cholesky, lower triangle; Hs[i][kk] becomes L[i][kk]
-        const T piv = Hs[kk * 33 + kk];
-        const T lkk = ox_sqrt(ox_max(piv, (T)OX_MINVAL));
-        const T inv = (T)1 / lkk;
-        const T lik = lane == kk ? lkk : Hr[kk] * inv;
-        __syncwarp();
-        if (lane >= kk && me) Hr[kk] = lik;
-        __syncwarp();
-#pragma unroll 4
-        for (int j = kk + 1; j < nv; j++) {
-          const T ljk = Hs[j * 33 + kk];
-          if (lane >= j && me) Hr[j] -= lik * ljk;
+        if (r < COOP_SROWS) {
+          const T* jr = sJ + r * 33;  // padding columns nv..31 are zero
+          const T s = ROW(rowD, r) * jr[lane];
+#pragma unroll
+          for (int j = 0; j < 32; j++) Hreg[j] += s * jr[j];  // broadcast reads
+        } else {
+          const T Jri = me ? GA(efc_J, r * nv + lane) : (T)0;
+          const T s = ROW(rowD, r) * Jri;
+#pragma unroll
+          for (int j = 0; j < 32; j++) Hreg[j] += s * bcast(Jri, j);
         }
-        __syncwarp();
+      }
+      // right-looking Cholesky on the register rows: at step kk lane i >= kk turns H[i][kk] into L[i][kk] and every lane
+      // subtracts L[i][kk] * L[j][kk] (lane j's value, one shuffle) from H[i][j]. Entries above the diagonal and the rows
+      // of idle lanes hold finite garbage that is never read.
+      T dinv = 1;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk++) {
+        if (kk < nv) {  // warp-uniform
+          const T piv = bcast(Hreg[kk], kk);
+          const T lkk = ox_sqrt(ox_max(piv, (T)OX_MINVAL));
+          const T inv = (T)1 / lkk;
+          const T lik = lane == kk ? lkk : Hreg[kk] * inv;
+          Hreg[kk] = lik;
+          if (lane == kk) dinv = inv;
+#pragma unroll
+          for (int j = kk + 1; j < 32; j++) Hreg[j] -= lik * bcast(lik, j);
+        }
       }
       T acc = grad, y = 0;
-      for (int kk = 0; kk < nv; kk++) {  // L y = grad, column-oriented
-        const T yk = bcast(acc / Hr[kk], kk);
-        if (lane == kk) y = yk;
-        if (lane > kk) acc -= Hr[kk] * yk;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk++) {  // L y = grad, column-oriented
+        if (kk < nv) {
+          const T yk = bcast(acc * dinv, kk);
+          if (lane == kk) y = yk;
+          if (lane > kk) acc -= Hreg[kk] * yk;
+        }
       }
       T x = 0;
-      for (int kk = nv - 1; kk >= 0; kk--) {  // L' x = y
-        const T s = wsum((lane > kk && me) ? Hr[kk] * x : (T)0);
-        if (lane == kk) x = (y - s) / Hr[kk];
+#pragma unroll
+      for (int kk = 31; kk >= 0; kk--) {  // L' x = y
+        if (kk < nv) {
+          const T s = wsum((lane > kk && me) ? Hreg[kk] * x : (T)0);
+          if (lane == kk) x = (y - s) * dinv;
+        }
       }
       Mgrad = x;
     }
