@@ -21,7 +21,7 @@
 namespace ox {
 
 constexpr int COOP_SROWS = 32;     // rows of J staged in shared memory per warp; the rest is read from the arena
-constexpr int COOP_WARPS = 4;      // warps (= envs) per CTA
+constexpr int COOP_WARPS = 8;      // warps (= consecutive envs) per CTA: their gathers from the [element][env] arena share 32-byte sectors
 constexpr int COOP_RCAP = 96;      // rows whose per-row scalars live in shared memory; envs with more rows use the arena's row arrays
 
 template <typename T> __device__ __forceinline__ T wsum(T v) {
@@ -30,9 +30,11 @@ template <typename T> __device__ __forceinline__ T wsum(T v) {
   return v;
 }
 template <typename T> __device__ __forceinline__ T bcast(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float coop_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double coop_rsqrt(double x) { return rsqrt(x); }
 
-// per-warp shared memory: five row arrays of RCAP, J staging (SROWS x 33)
-__host__ __device__ inline size_t coop_warp_words() { return 5 * (size_t)COOP_RCAP + COOP_SROWS * 33; }
+// per-warp shared memory: five row arrays of RCAP, J staging (SROWS x 33), the Cholesky factor (32 x 33) for the back substitution
+__host__ __device__ inline size_t coop_warp_words() { return 5 * (size_t)COOP_RCAP + COOP_SROWS * 33 + 32 * 33; }
 
 template <typename T>
 __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b) {
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
   }
   T* srow = reinterpret_cast<T*>(ox_smem + ((bytes + 127) / 128) * 128) + (size_t)wib * coop_warp_words();
   T* sJ = srow + 5 * COOP_RCAP;
+  T* sL = sJ + COOP_SROWS * 33;
   // per-row scalars: shared memory (stride 1) for the common case, the arena's own row arrays (stride S) when an env has
   // more rows than RCAP. efc_D / efc_aref are then read in place; jar, Jv and force use s_Jaref, s_Jv, efc_force.
   const bool small = nefc <= COOP_RCAP;
@@ -241,9 +244,8 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
       for (int kk = 0; kk < 32; kk++) {
         if (kk < nv) {  // warp-uniform
           const T piv = bcast(Hreg[kk], kk);
-          const T lkk = ox_sqrt(ox_max(piv, (T)OX_MINVAL));
-          const T inv = (T)1 / lkk;
-          const T lik = lane == kk ? lkk : Hreg[kk] * inv;
+          const T inv = coop_rsqrt(ox_max(piv, (T)OX_MINVAL));  // 1 / L[kk][kk]; the diagonal itself is never needed
+          const T lik = Hreg[kk] * inv;
           Hreg[kk] = lik;
           if (lane == kk) dinv = inv;
 #pragma unroll
@@ -259,14 +261,19 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
           if (lane > kk) acc -= Hreg[kk] * yk;
         }
       }
-      T x = 0;
+      // L' x = y, column-oriented: lane j needs L[kk][j], which sits in lane kk's register j - so the factor goes through
+      // shared memory once (row kk contiguous: conflict-free reads) instead of 27 butterfly reductions
 #pragma unroll
-      for (int kk = 31; kk >= 0; kk--) {  // L' x = y
-        if (kk < nv) {
-          const T s = wsum((lane > kk && me) ? Hreg[kk] * x : (T)0);
-          if (lane == kk) x = (y - s) * dinv;
-        }
+      for (int j = 0; j < 32; j++) sL[lane * 33 + j] = Hreg[j];
+      __syncwarp();
+      T x = 0;
+      acc = y;
+      for (int kk = nv - 1; kk >= 0; kk--) {
+        const T xk = bcast(acc * dinv, kk);
+        if (lane == kk) x = xk;
+        if (lane < kk) acc -= sL[kk * 33 + lane] * xk;
       }
+      __syncwarp();
       Mgrad = x;
     }
     if (init) {

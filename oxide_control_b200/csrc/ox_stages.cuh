@@ -467,10 +467,10 @@ struct Env {
     for (int k = nv - 1; k >= 0; k--) {
       const int Madr_kk = m.dof_Madr(k);
       int Madr_ki = Madr_kk + 1, i = m.dof_parentid(k);
-      const T dkk = at(qLD, Madr_kk);
+      const T inv = (T)1 / at(qLD, Madr_kk);  // one reciprocal per pivot; the row scalings multiply by it
       OX_MLOOP
       for (int d_ = 1; d_ < m.dof_depth(k); d_++) {
-        const T tmp = at(qLD, Madr_ki) / dkk;
+        const T tmp = at(qLD, Madr_ki) * inv;
         const int rowi = m.dof_Madr(i), n = m.dof_depth(i);
         OX_MLOOP
         for (int c = 0; c < n; c++) at(qLD, rowi + c) -= tmp * at(qLD, Madr_ki + c);
@@ -478,7 +478,7 @@ struct Env {
         i = m.dof_parentid(i);
         Madr_ki++;
       }
-      at(qLDiagInv, k) = (T)1 / dkk;
+      at(qLDiagInv, k) = inv;
     }
   }
   OX_HDN void factor_m() const {
