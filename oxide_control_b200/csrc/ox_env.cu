@@ -88,7 +88,15 @@ template <typename T, typename TU>
 __global__ void k_env_apply(DevBatch<T> b, const TU* __restrict__ action, int nu) {
   const int e = env_index(b);
   if (e < 0) return;
-  for (int i = 0; i < nu; i++) b.ctrl[(size_t)i * b.stride + e] = (T)action[(size_t)e * nu + i];
+  if (b.lanes == 32 && __activemask() == 0xffffffffu) {  // coalesced reads of the warp's contiguous [32][nu] block
+    const int e0 = e - (threadIdx.x & 31), n = 32 * nu;
+    for (int idx = threadIdx.x & 31; idx < n; idx += 32) {
+      const int el = idx / nu, k = idx - el * nu;
+      b.ctrl[(size_t)k * b.stride + e0 + el] = (T)action[(size_t)e0 * nu + idx];
+    }
+  } else {
+    for (int i = 0; i < nu; i++) b.ctrl[(size_t)i * b.stride + e] = (T)action[(size_t)e * nu + i];
+  }
 }
 
 // Observation::generate (+ reward, finish, bookkeeping, auto-reset when `post`)
@@ -98,8 +106,19 @@ __global__ void k_env_post(const unsigned char* __restrict__ gblob, int bytes, D
   DevModel<T> m{stage_model(gblob, bytes)};
   const int e = env_index(b);
   if (e < 0) return;
-  if (obs)
-    for (int k = 0; k < a.obs_dim; k++) obs[(size_t)e * a.obs_dim + k] = (TU)arena[a.obs_off[k] + e];
+  if (obs) {
+    // the 32 envs of a full warp own one contiguous [32][obs_dim] block of the output: lanes walk it linearly (coalesced
+    // stores; the gathers hit at most a few arena rows of consecutive envs per instruction)
+    if (b.lanes == 32 && __activemask() == 0xffffffffu) {
+      const int e0 = e - (threadIdx.x & 31), n = 32 * a.obs_dim;
+      for (int idx = threadIdx.x & 31; idx < n; idx += 32) {
+        const int el = idx / a.obs_dim, k = idx - el * a.obs_dim;
+        obs[(size_t)e0 * a.obs_dim + idx] = (TU)arena[a.obs_off[k] + e0 + el];
+      }
+    } else {
+      for (int k = 0; k < a.obs_dim; k++) obs[(size_t)e * a.obs_dim + k] = (TU)arena[a.obs_off[k] + e];
+    }
+  }
   if (!post) return;
   double r = a.bias;
   for (int k = 0; k < a.nterm; k++) {
