@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -91,16 +92,19 @@ __global__ void k_reset(const unsigned char* __restrict__ gblob, int bytes, DevB
 
 // layout / dtype conversion between a user buffer and a native SoA field
 // dir 0: user -> field, 1: field -> user
+// Threads walk the USER buffer linearly, so that side is always fully coalesced - it may be pinned host memory accessed
+// straight over PCIe (zero-copy, see host_mapped()); the SoA side is coalesced for the element-major layout and a gather
+// over a few rows of consecutive envs (L2-resident) for the env-major one.
 template <typename TF, typename TU>
 __global__ void k_pack(TF* __restrict__ field, TU* __restrict__ user, int nenv, int cnt, int stride, int layout, int dir) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nenv * cnt) return;
-  // consecutive threads walk consecutive envs: coalesced on the SoA side
-  const int e = (int)(idx % nenv), i = (int)(idx / nenv);
+  int e, i;
+  if (layout == OX_LAYOUT_ELEM_MAJOR) { i = (int)(idx / nenv); e = (int)(idx - (long long)i * nenv); }
+  else { e = (int)(idx / cnt); i = (int)(idx - (long long)e * cnt); }
   const size_t fi = (size_t)i * stride + e;
-  const size_t ui = layout == OX_LAYOUT_ELEM_MAJOR ? (size_t)i * nenv + e : (size_t)e * cnt + i;
-  if (dir == 0) field[fi] = (TF)user[ui];
-  else user[ui] = (TU)field[fi];
+  if (dir == 0) field[fi] = (TF)user[idx];
+  else user[idx] = (TU)field[fi];
 }
 
 }  // namespace ox
@@ -255,11 +259,16 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   const size_t usz = fi.is_int ? 4 : (dtype == OX_F64 ? 8 : 4);
   const size_t bytes = (size_t)b->nenv * fi.count * usz;
   void* dbuf = buf;
+  bool staged = false;
   if (mem == OX_MEM_HOST) {
-    ox_status s = ensure_tmp(b, tmp_off + bytes);
-    if (s) return s;
-    dbuf = (unsigned char*)b->d_tmp + tmp_off;
-    if (dir == 0) CU_TRY(cudaMemcpyAsync(dbuf, buf, bytes, cudaMemcpyHostToDevice, b->stream));
+    if (void* alias = host_mapped(buf)) dbuf = alias;
+    else {
+      ox_status s = ensure_tmp(b, tmp_off + bytes);
+      if (s) return s;
+      dbuf = (unsigned char*)b->d_tmp + tmp_off;
+      staged = true;
+      if (dir == 0) CU_TRY(cudaMemcpyAsync(dbuf, buf, bytes, cudaMemcpyHostToDevice, b->stream));
+    }
   } else if (mem != OX_MEM_DEVICE) { ox::set_error("bulk I/O: bad mem"); return OX_ERR_INVALID; }
   if (fi.is_int) launch_pack<int32_t, int32_t>(b, fi.ptr, dbuf, fi.count, layout, dir);
   else if (b->f64) {
@@ -271,7 +280,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   }
   CU_TRY(cudaGetLastError());
   if (mem == OX_MEM_HOST && dir == 1) {
-    CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
+    if (staged) CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
     if (sync) CU_TRY(cudaStreamSynchronize(b->stream));
   }
   return OX_OK;

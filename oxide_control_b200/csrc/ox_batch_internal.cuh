@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <string>
 
@@ -50,3 +51,17 @@ struct ox_batch {
     }                                                                                                  \
   } while (0)
 
+
+namespace ox {
+// Pinned (page-locked, mapped) host memory is addressable from the device: the pack kernels then read / write the
+// caller's buffer directly over PCIe instead of staging through a device buffer plus a cudaMemcpyAsync. Returns the
+// device-side alias, or nullptr for pageable memory (staged path). OX_ZERO_COPY=0 in the environment disables it.
+inline void* host_mapped(const void* p) {
+  static const bool enabled = [] { const char* v = getenv("OX_ZERO_COPY"); return !(v && v[0] == '0'); }();
+  if (!enabled || !p) return nullptr;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+}  // namespace ox

@@ -306,11 +306,12 @@ ox_status ox_env_reset(ox_env* e, void* obs, int32_t dtype, int32_t mem) {
   if (st) return st;
   if (obs && e->obs_dim) {
     const size_t usz = dtype == OX_F64 ? 8 : 4, bytes = (size_t)b->nenv * e->obs_dim * usz;
-    void* dobs = mem == OX_MEM_HOST ? (void*)((unsigned char*)e->d_io + e->io_obs) : obs;
+    void* alias = mem == OX_MEM_HOST ? ox::host_mapped(obs) : nullptr;  // pinned host buffer: the kernel writes it directly
+    void* dobs = mem == OX_MEM_HOST ? (alias ? alias : (void*)((unsigned char*)e->d_io + e->io_obs)) : obs;
     dispatch_post(e, dtype, dobs, nullptr, nullptr, nullptr, 0);
     CU_TRY(cudaGetLastError());
     if (mem == OX_MEM_HOST) {
-      CU_TRY(cudaMemcpyAsync(obs, dobs, bytes, cudaMemcpyDeviceToHost, b->stream));
+      if (!alias) CU_TRY(cudaMemcpyAsync(obs, dobs, bytes, cudaMemcpyDeviceToHost, b->stream));
       CU_TRY(cudaStreamSynchronize(b->stream));
     }
   }
@@ -329,8 +330,11 @@ ox_status ox_env_step(ox_env* e, const void* action, void* obs, void* reward, vo
   if (action && nu > 0) {
     const void* dact = action;
     if (host) {
-      CU_TRY(cudaMemcpyAsync(io + e->io_action, action, n * nu * usz, cudaMemcpyHostToDevice, b->stream));
-      dact = io + e->io_action;
+      if (void* alias = ox::host_mapped(action)) dact = alias;  // pinned: read straight over PCIe, stream-ordered
+      else {
+        CU_TRY(cudaMemcpyAsync(io + e->io_action, action, n * nu * usz, cudaMemcpyHostToDevice, b->stream));
+        dact = io + e->io_action;
+      }
     }
     if (b->f64) {
       if (dtype == OX_F64) k_env_apply<double, double><<<b->grid, b->block, 0, b->stream>>>(b->bd, (const double*)dact, nu);
@@ -344,17 +348,22 @@ ox_status ox_env_step(ox_env* e, const void* action, void* obs, void* reward, vo
   }
   ox_status st = ox_batch_step(b, e->spec.frame_skip);
   if (st) return st;
-  void* dobs = obs && host ? (void*)(io + e->io_obs) : obs;
-  void* drew = reward && host ? (void*)(io + e->io_reward) : reward;
-  void* ddis = discount && host ? (void*)(io + e->io_discount) : discount;
-  uint8_t* dfin = finished && host ? (uint8_t*)(io + e->io_finished) : finished;
+  // host outputs: pinned buffers are written by the kernel itself (zero-copy), pageable ones through the staging area
+  void* aobs = host ? ox::host_mapped(obs) : nullptr;
+  void* arew = host ? ox::host_mapped(reward) : nullptr;
+  void* adis = host ? ox::host_mapped(discount) : nullptr;
+  void* afin = host ? ox::host_mapped(finished) : nullptr;
+  void* dobs = obs && host ? (aobs ? aobs : (void*)(io + e->io_obs)) : obs;
+  void* drew = reward && host ? (arew ? arew : (void*)(io + e->io_reward)) : reward;
+  void* ddis = discount && host ? (adis ? adis : (void*)(io + e->io_discount)) : discount;
+  uint8_t* dfin = finished && host ? (afin ? (uint8_t*)afin : (uint8_t*)(io + e->io_finished)) : finished;
   dispatch_post(e, dtype, e->obs_dim ? dobs : nullptr, drew, ddis, dfin, 1);
   CU_TRY(cudaGetLastError());
   if (host) {
-    if (obs && e->obs_dim) CU_TRY(cudaMemcpyAsync(obs, dobs, n * e->obs_dim * usz, cudaMemcpyDeviceToHost, b->stream));
-    if (reward) CU_TRY(cudaMemcpyAsync(reward, drew, n * usz, cudaMemcpyDeviceToHost, b->stream));
-    if (discount) CU_TRY(cudaMemcpyAsync(discount, ddis, n * usz, cudaMemcpyDeviceToHost, b->stream));
-    if (finished) CU_TRY(cudaMemcpyAsync(finished, dfin, n, cudaMemcpyDeviceToHost, b->stream));
+    if (obs && e->obs_dim && !aobs) CU_TRY(cudaMemcpyAsync(obs, dobs, n * e->obs_dim * usz, cudaMemcpyDeviceToHost, b->stream));
+    if (reward && !arew) CU_TRY(cudaMemcpyAsync(reward, drew, n * usz, cudaMemcpyDeviceToHost, b->stream));
+    if (discount && !adis) CU_TRY(cudaMemcpyAsync(discount, ddis, n * usz, cudaMemcpyDeviceToHost, b->stream));
+    if (finished && !afin) CU_TRY(cudaMemcpyAsync(finished, dfin, n, cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaStreamSynchronize(b->stream));
   }
   return OX_OK;

@@ -132,3 +132,49 @@ def test_argument_errors_are_loud(ox):
         ox.BatchedPhysics(model, 0)
     with pytest.raises(ox.Error):
         ox.BatchedPhysics(model, 4, device=99)
+
+
+def test_pinned_host_buffers_take_the_zero_copy_path_and_agree_with_pageable_ones(ox):
+    """Pinned (mapped) host buffers are read / written by the kernels directly over PCIe; pageable ones are staged through
+    a device buffer. Same results either way, for bulk set / get / get_many and for the env layer."""
+    import torch
+    from oxide_control_b200 import _abi as A
+    model = ox.Model.from_xml_string(ox.models.CHEETAH)
+    nenv = 1000   # ragged: the last warp is partial
+    qpos, qvel = random_state(model, nenv, seed=26)
+    f32 = torch.float32
+    for layout in (A.LAYOUT_ENV_MAJOR, A.LAYOUT_ELEM_MAJOR):
+        b = ox.BatchedPhysics(model, nenv, precision="f32")
+        shape = (nenv, model.nq) if layout == A.LAYOUT_ENV_MAJOR else (model.nq, nenv)
+        src = torch.from_numpy((qpos if layout == A.LAYOUT_ENV_MAJOR else qpos.T).astype(np.float32).copy()).pin_memory()
+        b.set_ptr("qpos", src.data_ptr(), A.F32, A.MEM_HOST, layout)
+        b.sync()
+        assert np.array_equal(b.get("qpos"), qpos.astype(np.float32))            # pageable read-back of a pinned write
+        b.set("qvel", qvel); b.ctrl_philox(True, SEED); b.step(3)
+        out_q = torch.empty(shape, dtype=f32).pin_memory()
+        out_v = torch.empty((nenv, model.nv) if layout == A.LAYOUT_ENV_MAJOR else (model.nv, nenv), dtype=f32).pin_memory()
+        b.get_many_ptr(("qpos", "qvel"), (out_q.data_ptr(), out_v.data_ptr()), A.F32, A.MEM_HOST, layout)
+        q = out_q.numpy() if layout == A.LAYOUT_ENV_MAJOR else out_q.numpy().T
+        v = out_v.numpy() if layout == A.LAYOUT_ENV_MAJOR else out_v.numpy().T
+        assert np.array_equal(q, b.get("qpos")) and np.array_equal(v, b.get("qvel"))
+    # env layer: pinned vs pageable outputs of the same step
+    outs = []
+    for pinned in (False, True):
+        b = ox.BatchedPhysics(model, nenv, precision="f32")
+        env = ox.BatchedEnvironment(b, ox.TaskSpec(obs=[("qpos", 0, 9), ("qvel", 0, 9)], reward=[("qvel", 0, "linear", 1.0)],
+                                                   time_limit=0.03, init_qpos_noise=0.1, seed=3))
+        env.reset()
+        act = np.random.default_rng(0).uniform(-1, 1, (nenv, model.nu)).astype(np.float32)
+        if pinned:
+            a = torch.from_numpy(act).pin_memory()
+            o = torch.empty(nenv, 18, dtype=f32).pin_memory(); r = torch.empty(nenv, dtype=f32).pin_memory()
+            d = torch.empty(nenv, dtype=f32).pin_memory(); f = torch.empty(nenv, dtype=torch.uint8).pin_memory()
+            for _ in range(4):
+                env.step_ptr(a.data_ptr(), o.data_ptr(), r.data_ptr(), d.data_ptr(), f.data_ptr(), A.F32, A.MEM_HOST)
+            outs.append((o.numpy().copy(), r.numpy().copy(), d.numpy().copy(), f.numpy().astype(bool)))
+        else:
+            for _ in range(4):
+                ts = env.step(act)
+            outs.append((ts.observation, ts.reward, ts.discount, ts.finished))
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
