@@ -707,8 +707,14 @@ struct Env {
     OX_MLOOP
     for (int i = 0; i < nv; i++)
       at(b.qfrc_smooth, i) = at(b.qfrc_passive, i) - at(b.qfrc_bias, i) + at(b.qfrc_applied, i) + at(b.qfrc_actuator, i);
+    // Branch hygiene (here and in make_constraint / collision): a skipped block is a taken branch to a far target, which
+    // in these large straight-line kernels is an instruction-cache miss served from L2 (~500 cycles, profiles/r1_notes.md).
+    // So test the common "nothing to do" case once for the whole loop instead of once per body / joint / contact site.
+    bool any_xfrc = false;
     OX_MLOOP
-    for (int bd = 1; bd < nbody; bd++) {
+    for (int i = 6; i < 6 * nbody; i++) any_xfrc |= at(b.xfrc_applied, i) != 0;
+    OX_MLOOP
+    for (int bd = 1; any_xfrc && bd < nbody; bd++) {
       T f[6];
       ld<6>(f, b.xfrc_applied, 6 * bd);
       if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
@@ -812,6 +818,11 @@ struct Env {
           } else if (t2 == OX_GEOM_CAPSULE) {
             T axis[3] = {at(b.geom_xmat, 9 * g2 + 2), at(b.geom_xmat, 9 * g2 + 5), at(b.geom_xmat, 9 * g2 + 8)};
             const T hl = size2[1];
+            {  // neither end cap within reach of the plane (the common case): one branch for the pair
+              const T dc = (pos2[0] - pos1[0]) * n[0] + (pos2[1] - pos1[1]) * n[1] + (pos2[2] - pos1[2]) * n[2];
+              const T da = ox_abs(dot3(axis, n)) * hl;
+              if (dc - da > (margin + size2[0]) * (T)1.0001 + (T)1e-6) continue;   // conservative: the exact tests follow
+            }
 #pragma unroll
             for (int sgn = 1; sgn >= -1; sgn -= 2) {
               T pt[3] = {pos2[0] + sgn * axis[0] * hl, pos2[1] + sgn * axis[1] * hl, pos2[2] + sgn * axis[2] * hl};
@@ -1026,7 +1037,18 @@ struct Env {
     const int nv = h.nv, njnt = h.njnt;
     int nefc = 0;
     if (!dis(OX_DSBL_CONSTRAINT)) {
+      bool any_limit = false;  // one test for "no joint is near a limit" (the common case), see fwd_acceleration
       if (!dis(OX_DSBL_LIMIT)) {
+        OX_MLOOP
+        for (int j = 0; j < njnt; j++) {
+          if (!m.jnt_limited(j)) continue;
+          const int jt = m.jnt_type(j);
+          if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
+          const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
+          any_limit |= (value - m.jnt_range(2 * j) < margin) | (m.jnt_range(2 * j + 1) - value < margin);
+        }
+      }
+      if (any_limit) {
         OX_MLOOP
         for (int j = 0; j < njnt; j++) {
           if (!m.jnt_limited(j)) continue;
@@ -1056,6 +1078,10 @@ struct Env {
       if (STATIC_CON) {  // static contact slots: every index below is a compile-time constant after unrolling
         OX_MLOOP
         for (int p = 0; p < h.npair; p++) {
+          int pair_active = 0;
+          OX_MLOOP
+          for (int k = 0; k < m.pair_maxcon(p); k++) pair_active |= ati(b.con_active, m.pair_conadr(p) + k);
+          if (!pair_active) continue;
           OX_MLOOP
           for (int k = 0; k < m.pair_maxcon(p); k++) {
             const int c = m.pair_conadr(p) + k;
