@@ -187,6 +187,12 @@ OX_API void* ox_batch_stream(const ox_batch* b); /* cudaStream_t */
 /* step family: asynchronous on the batch's stream */
 OX_API ox_status ox_batch_step(ox_batch* b, int32_t nsteps);
 OX_API ox_status ox_batch_forward(ox_batch* b);
+/* Action::apply + Physics::step + Observation::generate of Environment::step (reference src/lib.rs:63-66) in ONE call for the
+ * whole batch: ctrl[nenv][nu] in (NULL = keep), one mj_step, qpos[nenv][nq] / qvel[nenv][nv] out (either may be NULL); env-major
+ * `dtype` buffers in `mem`. With a model-specialised kernel and device memory or pinned host memory the step kernel reads and
+ * writes the buffers itself (no extra launches, PCIe traffic overlaps the step); otherwise it is ox_batch_set + ox_batch_step +
+ * ox_batch_get_many. Host outputs are complete on return. */
+OX_API ox_status ox_batch_step_io(ox_batch* b, const void* ctrl, void* qpos, void* qvel, int32_t dtype, int32_t mem);
 OX_API ox_status ox_batch_reset(ox_batch* b, const uint8_t* host_mask_or_null);
 OX_API ox_status ox_batch_sync(ox_batch* b);
 

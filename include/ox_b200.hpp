@@ -79,6 +79,8 @@ class BatchedPhysics {
   }
   void step(int nsteps = 1) { check(ox_batch_step(b_, nsteps)); }
   void forward() { check(ox_batch_forward(b_)); }
+  // ctrl in, one step, qpos / qvel out in one call (Action::apply + step + Observation::generate, src/lib.rs:63-66)
+  void step_io(const void* ctrl, void* qpos, void* qvel, int dtype, int mem = OX_MEM_HOST) { check(ox_batch_step_io(b_, ctrl, qpos, qvel, dtype, mem)); }
   void reset(const uint8_t* mask = nullptr) { check(ox_batch_reset(b_, mask)); }
   void sync() { check(ox_batch_sync(b_)); }
   void set(int field, const void* buf, int dtype, int mem = OX_MEM_HOST, int layout = OX_LAYOUT_ENV_MAJOR) { check(ox_batch_set(b_, field, buf, dtype, mem, layout)); }

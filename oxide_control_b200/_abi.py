@@ -90,6 +90,7 @@ SYMBOLS = {
     "ox_batch_stream": (_P, [_P]),
     "ox_batch_step": (C.c_int32, [_P, C.c_int32]),
     "ox_batch_forward": (C.c_int32, [_P]),
+    "ox_batch_step_io": (C.c_int32, [_P, _P, _P, _P, C.c_int32, C.c_int32]),
     "ox_batch_reset": (C.c_int32, [_P, _P]),
     "ox_batch_sync": (C.c_int32, [_P]),
     "ox_batch_ctrl_philox": (C.c_int32, [_P, C.c_int32, C.c_uint64]),

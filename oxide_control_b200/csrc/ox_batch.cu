@@ -126,6 +126,7 @@ template <> DevBatch<double>& dev<double>(ox_batch* b) { return b->bd; }
 StepArgs make_args(ox_batch* b, int nsteps) {
   StepArgs a;
   a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset; a.d_step = b->d_step;
+  a.io_ctrl = b->io_ctrl; a.io_qpos = b->io_qpos; a.io_qvel = b->io_qvel; a.io_f64 = b->io_f64;
   return a;
 }
 
@@ -485,6 +486,37 @@ ox_status ox_batch_step(ox_batch* b, int32_t nsteps) {
   if (nsteps == 0) return OX_OK;
   CU_TRY(cudaSetDevice(b->cfg.device));
   return b->f64 ? do_step<double>(b, nsteps) : do_step<float>(b, nsteps);
+}
+
+// Action::apply + Physics::step + Observation::generate of the reference's Environment::step (src/lib.rs:63-66) as ONE call
+// for the whole batch: ctrl[nenv][nu] in, one mj_step, qpos[nenv][nq] / qvel[nenv][nv] out (env-major, `dtype`, in `mem`).
+// With a model-specialised kernel and device-addressable buffers (device memory, or pinned host memory) the step kernel
+// does the I/O itself; otherwise the call is ox_batch_set + ox_batch_step + ox_batch_get_many.
+ox_status ox_batch_step_io(ox_batch* b, const void* ctrl, void* qpos, void* qvel, int32_t dtype, int32_t mem) {
+  if (!b) { ox::set_error("ox_batch_step_io: null batch"); return OX_ERR_INVALID; }
+  if ((dtype != OX_F32 && dtype != OX_F64) || (mem != OX_MEM_HOST && mem != OX_MEM_DEVICE)) { ox::set_error("ox_batch_step_io: bad dtype / mem"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const void* dctrl = ctrl; void* dqpos = qpos; void* dqvel = qvel;
+  bool fused = b->spec != nullptr && b->cfg.mode == OX_MODE_FUSED;
+  if (fused && mem == OX_MEM_HOST) {
+    dctrl = ctrl ? ox::host_mapped(ctrl) : nullptr; dqpos = qpos ? ox::host_mapped(qpos) : nullptr; dqvel = qvel ? ox::host_mapped(qvel) : nullptr;
+    fused = (!ctrl || dctrl) && (!qpos || dqpos) && (!qvel || dqvel);
+  }
+  if (fused) {
+    b->io_ctrl = dctrl; b->io_qpos = dqpos; b->io_qvel = dqvel; b->io_f64 = dtype == OX_F64;
+    ox_status s = b->f64 ? do_step<double>(b, 1) : do_step<float>(b, 1);
+    b->io_ctrl = nullptr; b->io_qpos = nullptr; b->io_qvel = nullptr;
+    if (s) return s;
+    if (mem == OX_MEM_HOST && (qpos || qvel)) CU_TRY(cudaStreamSynchronize(b->stream));
+    return OX_OK;
+  }
+  if (ctrl && b->model->t.nu > 0) { ox_status s = ox_batch_set(b, OX_F_CTRL, ctrl, dtype, mem, OX_LAYOUT_ENV_MAJOR); if (s) return s; }
+  ox_status s = ox_batch_step(b, 1);
+  if (s) return s;
+  int32_t fields[2]; void* bufs[2]; int n = 0;
+  if (qpos) { fields[n] = OX_F_QPOS; bufs[n++] = qpos; }
+  if (qvel) { fields[n] = OX_F_QVEL; bufs[n++] = qvel; }
+  return n ? ox_batch_get_many(b, n, fields, bufs, dtype, mem, OX_LAYOUT_ENV_MAJOR) : OX_OK;
 }
 
 ox_status ox_batch_forward(ox_batch* b) {

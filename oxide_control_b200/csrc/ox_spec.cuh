@@ -20,6 +20,12 @@ struct StepArgs {
   uint64_t seed;
   int64_t env_id_offset;
   const long long* d_step;
+  // ox_batch_step_io: env-major user buffers (device memory or pinned host memory addressed over PCIe) that the step
+  // kernel itself reads the controls from and writes the new state to - no separate layout-conversion launches
+  const void* io_ctrl = nullptr;
+  void* io_qpos = nullptr;
+  void* io_qvel = nullptr;
+  int io_f64 = 0;  // element type of the user buffers
 };
 
 // FNV-1a over everything the generated code depends on
@@ -189,14 +195,61 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 }
 
 #if defined(__CUDACC__)
+// Fused I/O of ox_batch_step_io: a full warp owns one contiguous [32][cnt] block of an env-major user buffer and walks it
+// linearly (coalesced on the user side, which may be pinned host memory: whole PCIe lines), scattering to / gathering
+// from a few rows of the SoA field that the same warp's threads read right after / wrote right before (L1/L2 hits).
+template <typename T, typename TU>
+__device__ __forceinline__ void spec_io_in(T* field, int cnt, const TU* user, const DevBatch<T>& g, int e) {
+  const int lane = threadIdx.x & 31;
+  if (g.lanes == 32 && __activemask() == 0xffffffffu) {
+    const int e0 = e - lane;
+    for (int idx = lane; idx < 32 * cnt; idx += 32) {
+      const int el = idx / cnt, k = idx - el * cnt;
+      field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)(e0 + el)] = (T)user[(size_t)e0 * cnt + idx];
+    }
+    __syncwarp();
+  } else {
+    for (int k = 0; k < cnt; k++) field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)e] = (T)user[(size_t)e * cnt + k];
+  }
+}
+template <typename T, typename TU>
+__device__ __forceinline__ void spec_io_out(const T* field, int cnt, TU* user, const DevBatch<T>& g, int e) {
+  const int lane = threadIdx.x & 31;
+  if (g.lanes == 32 && __activemask() == 0xffffffffu) {
+    __syncwarp();
+    const int e0 = e - lane;
+    for (int idx = lane; idx < 32 * cnt; idx += 32) {
+      const int el = idx / cnt, k = idx - el * cnt;
+      user[(size_t)e0 * cnt + idx] = (TU)field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)(e0 + el)];
+    }
+  } else {
+    for (int k = 0; k < cnt; k++) user[(size_t)e * cnt + k] = (TU)field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)e];
+  }
+}
+
 template <class S, typename T, int PHASE>
 __global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
+  using H = typename S::Hdr;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (lane >= g.lanes) return;  // deliberately under-filled warps at small batch sizes (see env_index in ox_kernels.cuh)
   const int e = warp * g.lanes + lane;
   if (e >= g.nenv) return;
+  if (PHASE != 2 && a.io_ctrl && H::nu > 0) {
+    if (a.io_f64) spec_io_in<T, double>(g.ctrl, H::nu, (const double*)a.io_ctrl, g, e);
+    else spec_io_in<T, float>(g.ctrl, H::nu, (const float*)a.io_ctrl, g, e);
+  }
   const long long step0 = a.philox ? *a.d_step : 0;
   spec_step_env<S, T, PHASE>(g, e, a, rt, step0);
+  if (PHASE != 1) {
+    if (a.io_qpos) {
+      if (a.io_f64) spec_io_out<T, double>(g.qpos, H::nq, (double*)a.io_qpos, g, e);
+      else spec_io_out<T, float>(g.qpos, H::nq, (float*)a.io_qpos, g, e);
+    }
+    if (a.io_qvel) {
+      if (a.io_f64) spec_io_out<T, double>(g.qvel, H::nv, (double*)a.io_qvel, g, e);
+      else spec_io_out<T, float>(g.qvel, H::nv, (float*)a.io_qvel, g, e);
+    }
+  }
 }
 #endif
 

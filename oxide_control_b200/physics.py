@@ -217,6 +217,26 @@ class BatchedPhysics:
     def forward(self) -> None:
         _check(A.lib().ox_batch_forward(self._h))
 
+    def step_io(self, ctrl: Optional[np.ndarray] = None):
+        """Action::apply + step + Observation::generate (src/lib.rs:63-66) for the whole batch in one call:
+        ctrl[nenv, nu] in, one mj_step, (qpos[nenv, nq], qvel[nenv, nv]) out."""
+        dt = np.float64 if self.precision == "f64" else np.float32
+        code = A.F64 if self.precision == "f64" else A.F32
+        q = np.empty((self.nenv, self.model.nq), dt)
+        v = np.empty((self.nenv, self.model.nv), dt)
+        c = None
+        if ctrl is not None:
+            c = np.ascontiguousarray(ctrl, dt)
+            assert c.shape == (self.nenv, self.model.nu), c.shape
+        _check(A.lib().ox_batch_step_io(self._h, c.ctypes.data_as(C.c_void_p) if c is not None else None, q.ctypes.data_as(C.c_void_p),
+                                        v.ctypes.data_as(C.c_void_p), code, A.MEM_HOST))
+        return q, v
+
+    def step_io_ptr(self, ctrl_ptr: Optional[int], qpos_ptr: Optional[int], qvel_ptr: Optional[int], dtype_code: int, mem: int) -> None:
+        """Raw-pointer form (pinned host or device buffers): the specialised step kernel does the I/O itself."""
+        p = lambda x: C.c_void_p(x) if x else None
+        _check(A.lib().ox_batch_step_io(self._h, p(ctrl_ptr), p(qpos_ptr), p(qvel_ptr), dtype_code, mem))
+
     def reset(self, mask: Optional[np.ndarray] = None) -> None:
         if mask is None:
             _check(A.lib().ox_batch_reset(self._h, None))

@@ -64,6 +64,7 @@ extern "C" {
     pub fn ox_batch_stream(b: *const ox_batch) -> *mut c_void;
     pub fn ox_batch_step(b: *mut ox_batch, nsteps: i32) -> ox_status;
     pub fn ox_batch_forward(b: *mut ox_batch) -> ox_status;
+    pub fn ox_batch_step_io(b: *mut ox_batch, ctrl: *const c_void, qpos: *mut c_void, qvel: *mut c_void, dtype: i32, mem: i32) -> ox_status;
     pub fn ox_batch_reset(b: *mut ox_batch, host_mask_or_null: *const u8) -> ox_status;
     pub fn ox_batch_sync(b: *mut ox_batch) -> ox_status;
     pub fn ox_batch_ctrl_philox(b: *mut ox_batch, enable: i32, seed: u64) -> ox_status;

@@ -59,6 +59,10 @@ impl BatchedPhysics {
     pub fn nenv(&self) -> usize { self.nenv }
     pub fn step(&mut self, nsteps: i32) { let _ = unsafe { sys::ox_batch_step(self.raw, nsteps) }; }     // infallible like src/physics.rs:44
     pub fn forward(&mut self) { let _ = unsafe { sys::ox_batch_forward(self.raw) }; }
+    /// controls in, one step, qpos / qvel out in one call (Action::apply + step + Observation::generate, src/lib.rs:63-66)
+    pub fn step_io(&mut self, ctrl: &[f32], qpos: &mut [f32], qvel: &mut [f32]) -> Result<(), Error> {
+        check(unsafe { sys::ox_batch_step_io(self.raw, ctrl.as_ptr() as *const _, qpos.as_mut_ptr() as *mut _, qvel.as_mut_ptr() as *mut _, sys::OX_F32, sys::OX_MEM_HOST) })
+    }
     pub fn reset(&mut self, mask: Option<&[u8]>) { let _ = unsafe { sys::ox_batch_reset(self.raw, mask.map_or(std::ptr::null(), |m| m.as_ptr())) }; }
     pub fn sync(&mut self) -> Result<(), Error> { check(unsafe { sys::ox_batch_sync(self.raw) }) }
     /// bulk upload of controls, `[nenv][nu]` f32 from (ideally pinned) host memory

@@ -178,3 +178,41 @@ def test_pinned_host_buffers_take_the_zero_copy_path_and_agree_with_pageable_one
             outs.append((ts.observation, ts.reward, ts.discount, ts.finished))
     for x, y in zip(*outs):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name,precision,kw", [("cheetah", "f32", {}), ("cheetah", "f64", {}), ("humanoid", "f32", {}), ("cartpole", "f32", {}),
+                                                ("cheetah", "f32", dict(specialize=False)), ("cheetah", "f64", dict(mode="staged"))])
+def test_step_io_equals_set_step_get(ox, name, precision, kw):
+    """ox_batch_step_io (controls in, one step, qpos / qvel out in ONE call; the specialised kernels do the I/O themselves,
+    fused or split pipeline, pinned host / device / pageable buffers) == ox_batch_set(ctrl) + ox_batch_step(1) + ox_batch_get."""
+    import torch
+    from oxide_control_b200 import _abi as A
+    model = ox.Model.from_xml_string(getattr(ox.models, name.upper()))
+    nenv = 1000  # the last warp is partial
+    qpos, qvel = random_state(model, nenv, seed=27)
+    rng = np.random.default_rng(5)
+    acts = [rng.uniform(-1, 1, (nenv, model.nu)) for _ in range(4)]
+    dt = torch.float64 if precision == "f64" else torch.float32
+    code = A.F64 if precision == "f64" else A.F32
+    ref = ox.BatchedPhysics(model, nenv, precision=precision, **kw)
+    ref.set("qpos", qpos); ref.set("qvel", qvel)
+    want = []
+    for a in acts:
+        ref.set("ctrl", a); ref.step(1); ref.sync()
+        want.append((ref.get("qpos"), ref.get("qvel")))
+    for flavour in ("pageable", "pinned", "device"):
+        b = ox.BatchedPhysics(model, nenv, precision=precision, **kw)
+        b.set("qpos", qpos); b.set("qvel", qvel)
+        for a, (wq, wv) in zip(acts, want):
+            if flavour == "pageable":
+                q, v = b.step_io(a)
+            else:
+                mk = (lambda t: t.pin_memory()) if flavour == "pinned" else (lambda t: t.cuda())
+                ta = mk(torch.from_numpy(np.ascontiguousarray(a)).to(dt))
+                tq = mk(torch.empty(nenv, model.nq, dtype=dt)); tv = mk(torch.empty(nenv, model.nv, dtype=dt))
+                torch.cuda.synchronize()
+                b.step_io_ptr(ta.data_ptr(), tq.data_ptr(), tv.data_ptr(), code, A.MEM_HOST if flavour == "pinned" else A.MEM_DEVICE)
+                b.sync()
+                q, v = tq.cpu().numpy(), tv.cpu().numpy()
+            assert np.array_equal(q, wq) and np.array_equal(v, wv), flavour
+        assert np.array_equal(b.get("ctrl"), ref.get("ctrl"))
