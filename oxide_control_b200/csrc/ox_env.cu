@@ -90,9 +90,15 @@ __global__ void k_env_apply(DevBatch<T> b, const TU* __restrict__ action, int nu
   if (e < 0) return;
   if (b.lanes == 32 && __activemask() == 0xffffffffu) {  // coalesced reads of the warp's contiguous [32][nu] block
     const int e0 = e - (threadIdx.x & 31), n = 32 * nu;
-    for (int idx = threadIdx.x & 31; idx < n; idx += 32) {
-      const int el = idx / nu, k = idx - el * nu;
-      b.ctrl[(size_t)k * b.stride + e0 + el] = (T)action[(size_t)e0 * nu + idx];
+    for (int base = threadIdx.x & 31; base < n; base += 32 * 8) {  // 8 loads in flight: a pinned source is a PCIe round trip each
+      TU tmp[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int idx = base + 32 * j; tmp[j] = idx < n ? action[(size_t)e0 * nu + idx] : (TU)0; }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int idx = base + 32 * j;
+        if (idx < n) { const int el = idx / nu, k = idx - el * nu; b.ctrl[(size_t)k * b.stride + e0 + el] = (T)tmp[j]; }
+      }
     }
   } else {
     for (int i = 0; i < nu; i++) b.ctrl[(size_t)i * b.stride + e] = (T)action[(size_t)e * nu + i];

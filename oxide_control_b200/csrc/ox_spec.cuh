@@ -202,10 +202,16 @@ template <typename T, typename TU>
 __device__ __forceinline__ void spec_io_in(T* field, int cnt, const TU* user, const DevBatch<T>& g, int e) {
   const int lane = threadIdx.x & 31;
   if (g.lanes == 32 && __activemask() == 0xffffffffu) {
-    const int e0 = e - lane;
-    for (int idx = lane; idx < 32 * cnt; idx += 32) {
-      const int el = idx / cnt, k = idx - el * cnt;
-      field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)(e0 + el)] = (T)user[(size_t)e0 * cnt + idx];
+    const int e0 = e - lane, n = 32 * cnt;
+    for (int base = lane; base < n; base += 32 * 8) {  // 8 loads in flight per lane: a pinned source is a PCIe round trip each
+      TU tmp[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int idx = base + 32 * j; tmp[j] = idx < n ? user[(size_t)e0 * cnt + idx] : (TU)0; }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int idx = base + 32 * j;
+        if (idx < n) { const int el = idx / cnt, k = idx - el * cnt; field[(uint32_t)k * (uint32_t)g.stride + (uint32_t)(e0 + el)] = (T)tmp[j]; }
+      }
     }
     __syncwarp();
   } else {
