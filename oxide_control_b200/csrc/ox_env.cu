@@ -342,17 +342,20 @@ ox_status ox_env_step(ox_env* e, const void* action, void* obs, void* reward, vo
         dact = io + e->io_action;
       }
     }
-    if (b->f64) {
+    if (b->spec && b->cfg.mode == OX_MODE_FUSED) {
+      // the model-specialised step kernel reads the actions itself (StepArgs::io_ctrl): no separate launch
+      b->io_ctrl = dact; b->io_f64 = dtype == OX_F64;
+    } else if (b->f64) {
       if (dtype == OX_F64) k_env_apply<double, double><<<b->grid, b->block, 0, b->stream>>>(b->bd, (const double*)dact, nu);
       else k_env_apply<double, float><<<b->grid, b->block, 0, b->stream>>>(b->bd, (const float*)dact, nu);
     } else {
       if (dtype == OX_F64) k_env_apply<float, double><<<b->grid, b->block, 0, b->stream>>>(b->bf, (const double*)dact, nu);
       else k_env_apply<float, float><<<b->grid, b->block, 0, b->stream>>>(b->bf, (const float*)dact, nu);
     }
-    b->launches++;
-    CU_TRY(cudaGetLastError());
+    if (!b->io_ctrl) { b->launches++; CU_TRY(cudaGetLastError()); }
   }
   ox_status st = ox_batch_step(b, e->spec.frame_skip);
+  b->io_ctrl = nullptr;
   if (st) return st;
   // host outputs: pinned buffers are written by the kernel itself (zero-copy), pageable ones through the staging area
   void* aobs = host ? ox::host_mapped(obs) : nullptr;
