@@ -337,8 +337,8 @@ def main():
                "three_call_value": world * nenv * Ke / e2e3_s, "three_call_ms_per_step": 1e3 * e2e3_s / Ke,
                "timing": "host wall clock around K x ox_batch_step_io(ctrl pinned host -> qpos, qvel pinned host), which returns "
                          "after the outputs are complete; the step kernel reads / writes the pinned buffers over PCIe itself. "
-                         "three_call_* = the same loop as ox_batch_set(ctrl) + ox_batch_step(1) + ox_batch_get_many(qpos, qvel); "
-                         "max over ranks"}
+                         "three_call_* = the same loop as ox_batch_set(ctrl) + ox_batch_step(1) + ox_batch_get_many(qpos, qvel). "
+                         "No L2 flush inside this loop (value is measured with one), so e2e can exceed value; max over ranks"}
         finite = bool(np.isfinite(obs_q.numpy()).all())
         # ---------------- N1: the same loop through the on-device Environment / Task layer (ox_env_step): actions in,
         # observation + reward + discount + finished out, reward / finish / auto-reset evaluated on the GPU

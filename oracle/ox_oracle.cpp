@@ -1009,8 +1009,22 @@ void mat2Quat(double* q, const double* m) {
   normalize4(q);
 }
 
+// body accelerations in the com frame (mj_rnePostConstraint's forward pass):
+// cacc[0] = (0, -gravity); cacc[b] = cacc[parent] + sum over the body's dofs of cdof_dot*qvel + cdof*qacc
+void bodyAcc(const Model* m, const Data* d, std::vector<double>& cacc) {
+  cacc.assign(6 * m->nbody, 0.0);
+  if (!(m->disableflags & OX_DSBL_GRAVITY))
+    for (int k = 0; k < 3; k++) cacc[3 + k] = -m->gravity[k];
+  for (int b = 1; b < m->nbody; b++) {
+    const int p = m->body_parentid[b];
+    for (int k = 0; k < 6; k++) cacc[6 * b + k] = cacc[6 * p + k];
+    for (int i = m->body_dofadr[b]; i < m->body_dofadr[b] + m->body_dofnum[b]; i++)
+      for (int k = 0; k < 6; k++) cacc[6 * b + k] += d->cdof_dot[6 * i + k] * d->qvel[i] + d->cdof[6 * i + k] * d->qacc[i];
+  }
+}
+
 void sensors(const Model* m, Data* d) {
-  std::vector<double> slv;
+  std::vector<double> slv, cacc;
   for (int s = 0; s < m->nsensor; s++) {
     double* out = &d->sensordata[m->sensor_adr[s]];
     int id = m->sensor_objid[s], ot = m->sensor_objtype[s];
@@ -1042,6 +1056,22 @@ void sensors(const Model* m, Data* d) {
         if (ty == OX_SENS_VELOCIMETER || ty == OX_SENS_GYRO) {  // local frame: mat' * v
           for (int k = 0; k < 3; k++) out[k] = mat[k] * src[0] + mat[3 + k] * src[1] + mat[6 + k] * src[2];
         } else std::memcpy(out, src, 3 * sizeof(double));
+        break;
+      }
+      case OX_SENS_ACCELEROMETER: {
+        // mj_objectAcceleration(local): cacc and cvel transported to the site, plus omega x v, in the site frame.
+        // At rest this reads -gravity (an accelerometer measures proper acceleration).
+        if (cacc.empty()) bodyAcc(m, d, cacc);
+        objFrame(m, d, OX_OBJ_SITE, id, &pos, &mat, &body);
+        const double *cv = &d->cvel[6 * body], *ca = &cacc[6 * body];
+        double dif[3], lv[3], la[3], t1[3], t2[3], t3[3];
+        for (int k = 0; k < 3; k++) dif[k] = pos[k] - d->subtree_com[3 * m->body_rootid[body] + k];
+        cross3(t1, cv, dif);
+        cross3(t2, ca, dif);
+        for (int k = 0; k < 3; k++) { lv[k] = cv[3 + k] + t1[k]; la[k] = ca[3 + k] + t2[k]; }
+        cross3(t3, cv, lv);
+        for (int k = 0; k < 3; k++) la[k] += t3[k];
+        for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
         break;
       }
       case OX_SENS_CLOCK: out[0] = d->time; break;

@@ -433,7 +433,9 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;
     b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
     b->spec_rt.tolerance = b->f64 ? effective_tolerance<double>(t, cfg->tolerance) : effective_tolerance<float>(t, cfg->tolerance);
-    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && ox::solve_coop_eligible(t) && t.integrator == OX_INT_EULER;
+    bool acc_sensor = false;  // acceleration-stage sensors read the solved qacc: the PRE phase of the split pipeline runs too early for them
+    for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER;
+    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && ox::solve_coop_eligible(t) && t.integrator == OX_INT_EULER && !acc_sensor;
   }
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
   CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));

@@ -1368,7 +1368,7 @@ struct Env {
   OX_HDN void sensors() const {
     const auto& h = m.h();
     const int ns = h.nsensor, nbody = h.nbody;
-    bool have_slv = false;
+    bool have_slv = false, have_cacc = false;
     OX_MLOOP
     for (int s = 0; s < ns; s++) {
       const int adr = m.sensor_adr(s), id = m.sensor_objid(s), ot = m.sensor_objtype(s), ty = m.sensor_type(s);
@@ -1432,6 +1432,51 @@ struct Env {
             OX_MLOOP
             for (int k = 0; k < 3; k++) out[k] = mat[k] * src[0] + mat[3 + k] * src[1] + mat[6 + k] * src[2];
           } else { out[0] = src[0]; out[1] = src[1]; out[2] = src[2]; }
+          st<3>(b.sensordata, adr, out);
+          break;
+        }
+        case OX_SENS_ACCELEROMETER: {
+          // mj_objectAcceleration(local) on top of mj_rnePostConstraint's forward pass: cacc[0] = (0, -gravity),
+          // cacc[b] = cacc[parent] + sum over the body's dofs of cdof_dot*qvel + cdof*qacc (b.cacc is free after rne())
+          if (!have_cacc) {
+            OX_MLOOP
+            for (int k = 0; k < 3; k++) { at(b.cacc, k) = 0; at(b.cacc, 3 + k) = dis(OX_DSBL_GRAVITY) ? (T)0 : -(T)h.grav(k); }
+            OX_MLOOP
+            for (int bd = 1; bd < nbody; bd++) {
+              T a[6];
+              ld<6>(a, b.cacc, 6 * m.body_parentid(bd));
+              OX_MLOOP
+              for (int d_ = 0; d_ < m.body_dofnum(bd); d_++) {
+                const int i = m.body_dofadr(bd) + d_;
+                T cd[6], cdd[6];
+                ld<6>(cd, b.cdof, 6 * i);
+                ld<6>(cdd, b.cdof_dot, 6 * i);
+                const T v = at(b.qvel, i), qa = at(b.qacc, i);
+                OX_MLOOP
+                for (int k = 0; k < 6; k++) a[k] += cdd[k] * v + cd[k] * qa;
+              }
+              st<6>(b.cacc, 6 * bd, a);
+            }
+            have_cacc = true;
+          }
+          T pos[3], mat[9];
+          int body;
+          obj_frame(OX_OBJ_SITE, id, pos, mat, &body);
+          T cv[6], ca[6], sc[3], dif[3], lv[3], la[3], t1[3], t2[3], t3[3];
+          ld<6>(cv, b.cvel, 6 * body);
+          ld<6>(ca, b.cacc, 6 * body);
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
+          dif[0] = pos[0] - sc[0]; dif[1] = pos[1] - sc[1]; dif[2] = pos[2] - sc[2];
+          cross3(t1, cv, dif);
+          cross3(t2, ca, dif);
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) { lv[k] = cv[3 + k] + t1[k]; la[k] = ca[3 + k] + t2[k]; }
+          cross3(t3, cv, lv);
+          T out[3];
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) la[k] += t3[k];
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
           st<3>(b.sensordata, adr, out);
           break;
         }

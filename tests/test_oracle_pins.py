@@ -470,3 +470,34 @@ def test_collision_known_answers():
     m = ox.Model.from_xml_string(xml)
     od = OracleData(m); od.forward()
     assert od.int("ncon") == 2 and np.allclose(od.field("con_dist")[:2], -0.02)
+
+
+def test_accelerometer_closed_form_pendulum():
+    """Accelerometer (mj_objectAcceleration in the site frame) on a swinging pendulum: R^T (alpha x r + w x (w x r) - g),
+    and -g at rest. Pins the oracle's body-acceleration pass; the kernels are checked against the oracle on the zoo models."""
+    xml = """
+    <mujoco><compiler angle="radian"/><option timestep="0.002" gravity="0 0 -9.81"/>
+      <worldbody><body name="p" pos="0 0 1">
+        <joint name="h" type="hinge" axis="0 1 0" damping="0.05"/>
+        <geom type="capsule" fromto="0 0 0 0 0 -0.5" size="0.03" density="900"/>
+        <site name="imu" pos="0.02 0 -0.4" euler="0 0.3 0"/>
+      </body></worldbody>
+      <actuator><motor joint="h" gear="1"/></actuator>
+      <sensor><accelerometer site="imu"/><gyro site="imu"/></sensor>
+    </mujoco>"""
+    m = ox.Model.from_xml_string(xml)
+    od = OracleData(m)
+    for theta, w, u in [(0.0, 0.0, 0.0), (0.7, -1.3, 0.4), (-2.1, 3.0, -1.0)]:
+        od.reset()
+        od.field("qpos")[0] = theta; od.field("qvel")[0] = w; od.field("ctrl")[0] = u
+        od.forward()
+        alpha = od.field("qacc")[0]
+        c, s = np.cos(theta), np.sin(theta)
+        Rb = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])                      # body orientation (rotation about y)
+        ce, se = np.cos(0.3), np.sin(0.3)
+        Rs = Rb @ np.array([[ce, 0, se], [0, 1, 0], [-se, 0, ce]])             # site orientation
+        r = Rb @ np.array([0.02, 0, -0.4])
+        wv, av = np.array([0, w, 0.0]), np.array([0, alpha, 0.0])
+        a = np.cross(av, r) + np.cross(wv, np.cross(wv, r)) - np.array([0, 0, -9.81])
+        assert np.allclose(od.field("sensordata")[:3], Rs.T @ a, rtol=0, atol=1e-10)
+        assert np.allclose(od.field("sensordata")[3:6], Rs.T @ wv, atol=1e-12)

@@ -47,7 +47,7 @@ ZOO_A = """
     <framepos objtype="site" objname="tip"/> <framequat objtype="site" objname="top"/> <framepos objtype="body" objname="hand"/>
     <framepos objtype="xbody" objname="arm"/> <framepos objtype="geom" objname="arm"/>
     <framelinvel objtype="site" objname="tip"/> <frameangvel objtype="body" objname="hand"/>
-    <velocimeter site="tip"/> <gyro site="top"/>
+    <velocimeter site="tip"/> <gyro site="top"/> <accelerometer site="tip"/> <accelerometer site="top"/>
     <subtreecom body="boxy"/> <subtreelinvel body="boxy"/> <subtreelinvel body="arm"/> <clock/>
   </sensor>
 </mujoco>
