@@ -132,6 +132,11 @@ def test_argument_errors_are_loud(ox):
         ox.BatchedPhysics(model, 0)
     with pytest.raises(ox.Error):
         ox.BatchedPhysics(model, 4, device=99)
+    # maximum size: device code indexes every field with 32 bits; a batch whose largest field would overflow is refused
+    # before anything is allocated
+    big = ox.Model.from_xml_string(ox.models.HUMANOID)
+    with pytest.raises(ox.Error, match="32-bit"):
+        ox.BatchedPhysics(big, 1 << 22)
 
 
 def test_pinned_host_buffers_take_the_zero_copy_path_and_agree_with_pageable_ones(ox):
