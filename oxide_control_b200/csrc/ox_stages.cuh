@@ -185,6 +185,9 @@ OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 // makes their bounds compile-time constants (LOCAL specialisation), left as loops in the generic kernels.
 #define OX_MLOOP _Pragma("unroll")
 // loops of the constraint solver over dofs: unrolled only for small specialised models (see Env::UNROLL_NV)
+// loops over constraint rows in the solver: never unrolled. Their trip count is a handful, and the 4x unrolling the compiler
+// would apply pushes the Newton iteration body past the 32 KB L1.5 instruction cache (profiles/r1_notes.md)
+#define OX_ROWLOOP _Pragma("unroll 1")
 #define OX_NVLOOP _Pragma("unroll (UNROLL_NV ? 64 : 1)")  // no count: full unroll iff the trip count is a compile-time constant, else none
 
 // ---------------------------------------------------------------- one environment
@@ -1106,6 +1109,7 @@ struct Env {
     p.d0 = 2 * a * qg2 + qg1;
     p.d1 = 2 * qg2;
     p.s0 = ox_abs(2 * a * qg2) + ox_abs(qg1);
+    OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
@@ -1126,6 +1130,7 @@ struct Env {
     T c = 0;
     OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
+    OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r);
       T f = 0;
@@ -1169,6 +1174,7 @@ struct Env {
       OX_NVLOOP
       for (int d_ = 0, j = i; d_ < m.dof_depth(i); d_++, j = m.dof_parentid(j)) at(H, i * nv + j) = at(b.qM, adr++);
     }
+    OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       if (!(at(b.s_Jaref, r) < 0)) continue;
       const T D = at(b.efc_D, r);
@@ -1230,6 +1236,7 @@ struct Env {
     T c = 0;
     OX_NVLOOP
     for (int i = 0; i < nv; i++) c += (T)0.5 * (at(b.s_Mv, i) - at(b.qfrc_smooth, i)) * (at(qacc, i) - at(b.qacc_smooth, i));
+    OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
       OX_NVLOOP
@@ -1267,6 +1274,7 @@ struct Env {
     for (int i = 0; i < nv; i++) at(b.qacc, i) = use_smooth ? at(b.qacc_smooth, i) : at(b.qacc_warmstart, i);
     // initial state
     mul_m(b.s_Ma, b.qacc);
+    OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       T v = -at(b.efc_aref, r);
       OX_NVLOOP
@@ -1293,6 +1301,7 @@ struct Env {
       if (snorm < (T)OX_MINVAL) break;
       const T gtol = tol * (T)h.ls_tolerance * snorm * mscale;
       mul_m(b.s_Mv, b.s_search);
+      OX_ROWLOOP
       for (int r = 0; r < nefc; r++) {
         T v = 0;
         OX_NVLOOP
@@ -1327,6 +1336,7 @@ struct Env {
         at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
         if (!newton) { at(b.s_gradold, i) = at(b.s_grad, i); at(b.s_Mgradold, i) = at(b.s_Mgrad, i); }
       }
+      OX_ROWLOOP
       for (int r = 0; r < nefc; r++) at(b.s_Jaref, r) += alpha * at(b.s_Jv, r);
       const T oldcost = cost;
       cost = update_constraint(nv, nefc, &gauss);
