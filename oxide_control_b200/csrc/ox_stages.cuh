@@ -185,9 +185,10 @@ OX_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 // makes their bounds compile-time constants (LOCAL specialisation), left as loops in the generic kernels.
 #define OX_MLOOP _Pragma("unroll")
 // loops of the constraint solver over dofs: unrolled only for small specialised models (see Env::UNROLL_NV)
-// loops over constraint rows in the solver: never unrolled. Their trip count is a handful, and the 4x unrolling the compiler
-// would apply pushes the Newton iteration body past the 32 KB L1.5 instruction cache (profiles/r1_notes.md)
-#define OX_ROWLOOP _Pragma("unroll 1")
+// loops over constraint rows in the solver: left to the compiler's own unrolling (x4). Forcing them rolled shrinks the Newton
+// iteration body and speeds up the mean warp (K steps in one launch: 104 -> 126 M env-steps/s) but slows the slowest warp of
+// every launch, which is what a one-step launch waits for (0.076 -> 0.087 ms) - measured, profiles/r1_notes.md
+#define OX_ROWLOOP
 #define OX_NVLOOP _Pragma("unroll (UNROLL_NV ? 64 : 1)")  // no count: full unroll iff the trip count is a compile-time constant, else none
 
 // ---------------------------------------------------------------- one environment
@@ -1281,73 +1282,90 @@ struct Env {
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.qacc, i);
       at(b.s_Jaref, r) = v;
     }
-    T gauss;
-    T cost = update_constraint(nv, nefc, &gauss);
-    T gnorm = update_gradient(nv, nefc, newton);
-    OX_NVLOOP
-    for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
+    // One loop, one call site of update_constraint / update_gradient (the first pass evaluates the starting point, every
+    // later pass follows a line search and a move) and one of ls_eval (its first trip evaluates alpha = 0): the iteration
+    // body is what the instruction cache has to hold, and duplicated inlined copies are pure fetch traffic.
+    T gauss = 0, cost = 0, gnorm = 0;
     const T tol = (T)h.tolerance;
     const T mscale = (T)h.meaninertia * (T)(nv > 1 ? nv : 1);
     const T scale = 1 / mscale;
-    int maxiter = h.iterations;
-    if (scale * gnorm < tol) maxiter = 0;
+    const int maxiter = h.iterations;
     int iter = 0;
-    while (iter < maxiter) {
-      // ---- exact line search on the convex piecewise-quadratic phi(alpha)
-      T snorm = 0;
-      OX_NVLOOP
-      for (int i = 0; i < nv; i++) { const T s = at(b.s_search, i); snorm += s * s; }
-      snorm = ox_sqrt(snorm);
-      if (snorm < (T)OX_MINVAL) break;
-      const T gtol = tol * (T)h.ls_tolerance * snorm * mscale;
-      mul_m(b.s_Mv, b.s_search);
-      OX_ROWLOOP
-      for (int r = 0; r < nefc; r++) {
-        T v = 0;
+    bool init = true;
+#pragma unroll 1
+    for (;;) {
+      if (!init) {
+        if (iter >= maxiter) break;
+        // ---- exact line search on the convex piecewise-quadratic phi(alpha)
+        T snorm = 0;
         OX_NVLOOP
-        for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.s_search, i);
-        at(b.s_Jv, r) = v;
+        for (int i = 0; i < nv; i++) { const T s = at(b.s_search, i); snorm += s * s; }
+        snorm = ox_sqrt(snorm);
+        if (snorm < (T)OX_MINVAL) break;
+        const T gtol = tol * (T)h.ls_tolerance * snorm * mscale;
+        mul_m(b.s_Mv, b.s_search);
+        OX_ROWLOOP
+        for (int r = 0; r < nefc; r++) {
+          T v = 0;
+          OX_NVLOOP
+          for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(b.s_search, i);
+          at(b.s_Jv, r) = v;
+        }
+        T qg1 = 0, qg2 = 0;
+        OX_NVLOOP
+        for (int i = 0; i < nv; i++) {
+          const T s = at(b.s_search, i);
+          qg1 += s * (at(b.s_Ma, i) - at(b.qfrc_smooth, i));
+          qg2 += (T)0.5 * s * at(b.s_Mv, i);
+        }
+        LsPt p0, lo, hi, cur;
+        bool have_hi = false, descent = true;
+        T a = 0;
+#pragma unroll 1
+        for (int it = -1; it < h.ls_iterations; it++) {  // it = -1 evaluates alpha = 0
+          if (it >= 0) {
+            a = cur.alpha - cur.d0 / cur.d1;
+            if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = (T)0.5 * (lo.alpha + hi.alpha);
+            if (ox_abs(a - cur.alpha) <= Eps<T>::v() * ox_abs(a)) break;
+          }
+          cur = ls_eval(a, nefc, gauss, qg1, qg2);
+          if (it < 0) {
+            p0 = cur; lo = cur; hi = cur;
+            if (!(p0.d0 < 0)) { descent = false; break; }
+          } else {
+            if (ox_abs(cur.d0) < gtol || ox_abs(cur.d0) <= 8 * Eps<T>::v() * cur.s0) break;  // converged, or phi' below its own round-off
+            if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
+          }
+        }
+        if (!descent) break;
+        const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
+        if (alpha == 0) break;
+        // ---- move
+        OX_NVLOOP
+        for (int i = 0; i < nv; i++) {
+          at(b.qacc, i) += alpha * at(b.s_search, i);
+          at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
+          if (!newton) { at(b.s_gradold, i) = at(b.s_grad, i); at(b.s_Mgradold, i) = at(b.s_Mgrad, i); }
+        }
+        OX_ROWLOOP
+        for (int r = 0; r < nefc; r++) at(b.s_Jaref, r) += alpha * at(b.s_Jv, r);
       }
-      T qg1 = 0, qg2 = 0;
-      OX_NVLOOP
-      for (int i = 0; i < nv; i++) {
-        const T s = at(b.s_search, i);
-        qg1 += s * (at(b.s_Ma, i) - at(b.qfrc_smooth, i));
-        qg2 += (T)0.5 * s * at(b.s_Mv, i);
-      }
-      const LsPt p0 = ls_eval(0, nefc, gauss, qg1, qg2);
-      if (!(p0.d0 < 0)) break;
-      LsPt lo = p0, hi = p0, cur = p0;
-      bool have_hi = false;
-      for (int it = 0; it < h.ls_iterations; it++) {
-        T a = cur.alpha - cur.d0 / cur.d1;
-        if (have_hi && !(a > lo.alpha && a < hi.alpha)) a = (T)0.5 * (lo.alpha + hi.alpha);
-        if (ox_abs(a - cur.alpha) <= Eps<T>::v() * ox_abs(a)) break;
-        cur = ls_eval(a, nefc, gauss, qg1, qg2);
-        if (ox_abs(cur.d0) < gtol || ox_abs(cur.d0) <= 8 * Eps<T>::v() * cur.s0) break;  // converged, or phi' below its own round-off
-        if (cur.d0 < 0) lo = cur; else { hi = cur; have_hi = true; }
-      }
-      const T alpha = cur.cost <= p0.cost ? cur.alpha : 0;
-      if (alpha == 0) break;
-      // ---- move
-      OX_NVLOOP
-      for (int i = 0; i < nv; i++) {
-        at(b.qacc, i) += alpha * at(b.s_search, i);
-        at(b.s_Ma, i) += alpha * at(b.s_Mv, i);
-        if (!newton) { at(b.s_gradold, i) = at(b.s_grad, i); at(b.s_Mgradold, i) = at(b.s_Mgrad, i); }
-      }
-      OX_ROWLOOP
-      for (int r = 0; r < nefc; r++) at(b.s_Jaref, r) += alpha * at(b.s_Jv, r);
       const T oldcost = cost;
       cost = update_constraint(nv, nefc, &gauss);
       gnorm = update_gradient(nv, nefc, newton);
-      iter++;
-      const T improvement = scale * (oldcost - cost), gradient = scale * gnorm;
-      if (improvement < tol || gradient < tol) break;
-      // floating-point floor: a decrease below the resolution of the cost itself is round-off, not progress
-      // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
-      if (oldcost - cost <= OX_FLOOR_MULT * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
-      if (newton) {
+      bool first = init;
+      if (init) {
+        init = false;
+        if (scale * gnorm < tol) break;
+      } else {
+        iter++;
+        const T improvement = scale * (oldcost - cost), gradient = scale * gnorm;
+        if (improvement < tol || gradient < tol) break;
+        // floating-point floor: a decrease below the resolution of the cost itself is round-off, not progress
+        // (inert in fp64 at MuJoCo's tolerances; in fp32 it removes the noise-driven iteration tail)
+        if (oldcost - cost <= OX_FLOOR_MULT * Eps<T>::v() * (ox_abs(oldcost) + ox_abs(cost))) break;
+      }
+      if (newton || first) {
         OX_NVLOOP
         for (int i = 0; i < nv; i++) at(b.s_search, i) = -at(b.s_Mgrad, i);
       } else {
