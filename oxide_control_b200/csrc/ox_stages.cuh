@@ -16,6 +16,21 @@ namespace ox {
 // ---------------------------------------------------------------- scalar helpers
 OX_HD float ox_sqrt(float x) { return sqrtf(x); }
 OX_HD double ox_sqrt(double x) { return sqrt(x); }
+// 1/sqrt(x): one MUFU + a Newton step on the device instead of an IEEE sqrt followed by an IEEE division on the critical path
+OX_HD float ox_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+OX_HD double ox_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 OX_HD float ox_abs(float x) { return fabsf(x); }
 OX_HD double ox_abs(double x) { return fabs(x); }
 OX_HD float ox_pow(float x, float y) { return powf(x, y); }
@@ -1204,9 +1219,8 @@ struct Env {
       T s = at(H, j * nv + j);
       OX_NVLOOP
       for (int k = 0; k < j; k++) { const T l = at(H, j * nv + k); s -= l * l; }
-      s = ox_sqrt(ox_max(s, (T)OX_MINVAL));
-      at(H, j * nv + j) = s;
-      const T inv = 1 / s;
+      const T inv = ox_rsqrt(ox_max(s, (T)OX_MINVAL));
+      at(H, j * nv + j) = inv;  // the diagonal holds 1 / L[j][j]: the substitutions below multiply instead of dividing
       OX_NVLOOP
       for (int i = j + 1; i < nv; i++) {
         T v = at(H, i * nv + j);
@@ -1220,14 +1234,14 @@ struct Env {
       T v = at(b.s_grad, i);
       OX_NVLOOP
       for (int k = 0; k < i; k++) v -= at(H, i * nv + k) * at(b.s_Mgrad, k);
-      at(b.s_Mgrad, i) = v / at(H, i * nv + i);
+      at(b.s_Mgrad, i) = v * at(H, i * nv + i);
     }
     OX_NVLOOP
     for (int i = nv - 1; i >= 0; i--) {
       T v = at(b.s_Mgrad, i);
       OX_NVLOOP
       for (int k = i + 1; k < nv; k++) v -= at(H, k * nv + i) * at(b.s_Mgrad, k);
-      at(b.s_Mgrad, i) = v / at(H, i * nv + i);
+      at(b.s_Mgrad, i) = v * at(H, i * nv + i);
     }
     return ox_sqrt(gn);
   }
