@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="active envs per warp (0 = library default)")
     ap.add_argument("--iterations", type=int, default=0)
     ap.add_argument("--ls-iterations", type=int, default=0)
     ap.add_argument("--stage-times", action="store_true", help="also print per-stage device times (staged kernels)")
@@ -208,7 +209,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("OX_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no NCCL version banner)
     import torch
     import torch.distributed as dist
     import oxide_control_b200 as ox
@@ -227,7 +227,7 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     b = ox.BatchedPhysics(model, nenv, precision=precision, device=local_rank, mode=args.mode, env_id_offset=rank * nenv,
-                          block_threads=args.block, iterations=args.iterations, ls_iterations=args.ls_iterations, specialize=not args.no_spec)
+                          block_threads=args.block, lanes_per_warp=args.lanes, iterations=args.iterations, ls_iterations=args.ls_iterations, specialize=not args.no_spec)
     qpos, qvel = initial_state(model, world * nenv, rank * nenv, (rank + 1) * nenv)
     b.set("qpos", qpos)
     b.set("qvel", qvel)
@@ -373,7 +373,7 @@ def main():
         finite = True
         env_line = None
 
-    # ---------------- roofline of the dominant kernel (the step kernel: the only kernel of a step besides the 1-thread counter bump)
+    # ---------------- roofline of the dominant kernel (the step kernel: the only kernel of a step)
     peaks, peak_src = load_peaks()
     step_ms = dev_ms / K  # this rank's average launch duration
     alg_bytes = algorithmic_bytes_per_env_step(model, real_bytes) * nenv

@@ -184,7 +184,9 @@ class Physics {
   std::vector<double> qacc() { return batch_.get1(OX_F_QACC, 0, 0, model_.tables().nv); }
   std::vector<double> sensordata() { return batch_.get1(OX_F_SENSORDATA, 0, 0, model_.tables().nsensordata); }
  private:
-  explicit Physics(Model&& m) : model_(std::move(m)), batch_(model_, BatchedPhysics::default_config(1, OX_F64)) {}
+  // one env, fp64, generic kernels: data() stands for &mjData, so every derived field must be current after step()
+  static ox_batch_config single_config() { ox_batch_config c = BatchedPhysics::default_config(1, OX_F64); c.specialize = 0; return c; }
+  explicit Physics(Model&& m) : model_(std::move(m)), batch_(model_, single_config()) {}
   template <class J> void check_joint(obj::Joint id) const {
     if (model_.tables().jnt_type[id.index] != J::type) throw Error(Error::Kind::JointTypeNotMatch, "joint type does not match");
   }

@@ -35,7 +35,7 @@ __global__ void k_step_fused(const unsigned char* __restrict__ gblob, int bytes,
   const int e = env_index(b);
   if (e < 0) return;
   Env<T> env(m, b, e);
-  const long long step0 = a.philox ? *a.d_step : 0;
+  const long long step0 = a.d_step ? *a.d_step : a.step0;
   for (int s = 0; s < a.nsteps; s++) {
     if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
     env.step();
@@ -57,7 +57,7 @@ __global__ void k_stage(const unsigned char* __restrict__ gblob, int bytes, DevB
   const int e = env_index(b);
   if (e < 0) return;
   Env<T> env(m, b, e);
-  if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, *a.d_step);
+  if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, a.d_step ? *a.d_step : a.step0);
   if (STAGE == ST_CHECK) {
     if (env.bad_state()) { env.reset_data(); env.ati(b.diverged, 0) += 1; }
   }
@@ -75,10 +75,11 @@ __global__ void k_stage(const unsigned char* __restrict__ gblob, int bytes, DevB
   }
   if (STAGE == ST_INTEGRATE) {
     if (m.h().integrator == OX_INT_RK4) env.rk4(); else env.euler();
+    // captured CUDA graph only (frozen arguments): the last kernel of the step advances the device-side Philox step counter.
+    // Nothing else in this launch reads it, and the next launch is stream-ordered after this one.
+    if (a.d_step && a.philox && e == 0) *a.d_step += 1;
   }
 }
-
-__global__ void k_bump(long long* d_step, int n) { *d_step += n; }
 
 template <typename T>
 __global__ void k_reset(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, const uint8_t* __restrict__ mask) {
@@ -114,7 +115,9 @@ using namespace ox;
 namespace ox {
 cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax);
 cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int nefcmax);
+cudaError_t solve_coop_prepare(int blob_bytes, bool f64);  // per-device opt-in to > 48 KB dynamic shared memory
 bool solve_coop_eligible(const ox_model_tables& t);
+size_t solve_coop_smem(int blob_bytes, bool f64);
 }  // namespace ox
 
 namespace {
@@ -123,9 +126,17 @@ template <typename T> DevBatch<T>& dev(ox_batch* b);
 template <> DevBatch<float>& dev<float>(ox_batch* b) { return b->bf; }
 template <> DevBatch<double>& dev<double>(ox_batch* b) { return b->bd; }
 
+template <typename T>
+cudaError_t launch_solve_coop(ox_batch* b) {
+  b->launches++;
+  if (sizeof(T) == 8) return launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
+  return launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
+}
+
 StepArgs make_args(ox_batch* b, int nsteps) {
   StepArgs a;
-  a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset; a.d_step = b->d_step;
+  a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset;
+  a.step0 = b->h_step; a.d_step = nullptr; a.applied = b->applied;
   a.io_ctrl = b->io_ctrl; a.io_qpos = b->io_qpos; a.io_qvel = b->io_qvel; a.io_f64 = b->io_f64;
   return a;
 }
@@ -137,8 +148,9 @@ void launch_stage(ox_batch* b, const StepArgs& a) {
 }
 
 template <typename T>
-void launch_staged_step(ox_batch* b) {
+ox_status launch_staged_step(ox_batch* b, bool capturing = false) {
   StepArgs a = make_args(b, 1);
+  if (capturing) a.d_step = b->d_step;
   if (b->philox) launch_stage<T, ST_CTRL>(b, a);
   launch_stage<T, ST_CHECK>(b, a);
   launch_stage<T, ST_KIN>(b, a);
@@ -148,18 +160,14 @@ void launch_staged_step(ox_batch* b) {
   launch_stage<T, ST_EFC>(b, a);
   launch_stage<T, ST_ACC>(b, a);
   if (b->coop) {
-    if (sizeof(T) == 8) launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
-    else launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
-    b->launches++;
+    CU_TRY(launch_solve_coop<T>(b));
   } else {
     launch_stage<T, ST_SOLVE>(b, a);
   }
   launch_stage<T, ST_SENSE>(b, a);
   launch_stage<T, ST_INTEGRATE>(b, a);
-  if (b->philox) {
-    k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
-    b->launches++;
-  }
+  if (b->philox) b->h_step++;
+  return OX_OK;
 }
 
 template <typename T>
@@ -169,50 +177,52 @@ ox_status do_step(ox_batch* b, int nsteps) {
       // specialised PRE -> warp-cooperative Newton solve -> specialised POST, one step at a time
       for (int s = 0; s < nsteps; s++) {
         const StepArgs a1 = make_args(b, 1);
-        if (sizeof(T) == 8) {
-          b->spec->launch_split_f64[0](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
-          launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
-          b->spec->launch_split_f64[1](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
-        } else {
-          b->spec->launch_split_f32[0](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
-          launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
-          b->spec->launch_split_f32[1](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
-        }
-        b->launches += 3;
-        if (b->philox && s + 1 < nsteps) {
-          k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
-          b->launches++;
-        }
+        if (sizeof(T) == 8) b->spec->launch_split_f64[0](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
+        else b->spec->launch_split_f32[0](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
+        b->launches++;
+        CU_TRY(launch_solve_coop<T>(b));
+        if (sizeof(T) == 8) b->spec->launch_split_f64[1](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
+        else b->spec->launch_split_f32[1](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
+        b->launches++;
+        if (b->philox) b->h_step++;
       }
-      b->launches--;               // the common increment below
-      if (b->philox) nsteps = 1;  // the final bump below advances the counter for the last step
+      b->derived_stale = true;
+      CU_TRY(cudaGetLastError());
+      return OX_OK;
     } else if (b->spec) {
+      b->derived_stale = true;
       if (sizeof(T) == 8) b->spec->launch_f64(b->grid, b->block, b->stream, b->bd, make_args(b, nsteps), b->spec_rt);
       else b->spec->launch_f32(b->grid, b->block, b->stream, b->bf, make_args(b, nsteps), b->spec_rt);
     } else {
       k_step_fused<T><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), make_args(b, nsteps));
     }
     b->launches++;
-    if (b->philox) {
-      k_bump<<<1, 1, 0, b->stream>>>(b->d_step, nsteps);
-      b->launches++;
-    }
+    if (b->philox) b->h_step += nsteps;
   } else if (b->cfg.use_graph) {
     if (!b->graph_exec) {
-      long long saved = b->launches;
+      // the captured kernels read the Philox step index from the device counter (their arguments are frozen): bring it
+      // up to date with the host counter first
+      const long long saved = b->launches, saved_step = b->h_step;
       CU_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
-      launch_staged_step<T>(b);
-      CU_TRY(cudaStreamEndCapture(b->stream, &b->graph));
+      ox_status cs = launch_staged_step<T>(b, true);
+      cudaError_t ce = cudaStreamEndCapture(b->stream, &b->graph);
+      b->launches = saved; b->h_step = saved_step;
+      if (cs) return cs;
+      CU_TRY(ce);
       CU_TRY(cudaGraphInstantiate(&b->graph_exec, b->graph, 0));
-      b->launches = saved;
     }
-    const int per = ST_COUNT - 1 + (b->philox ? 2 : 0);
+    const int per = ST_COUNT - 1 + (b->philox ? 1 : 0);
+    if (b->d_step_val != b->h_step) {  // set_step_counter / stage_times moved the host counter
+      CU_TRY(cudaMemcpyAsync(b->d_step, &b->h_step, sizeof(long long), cudaMemcpyHostToDevice, b->stream));
+      b->d_step_val = b->h_step;
+    }
     for (int s = 0; s < nsteps; s++) {
       CU_TRY(cudaGraphLaunch(b->graph_exec, b->stream));
       b->launches += per;
+      if (b->philox) { b->h_step++; b->d_step_val++; }
     }
   } else {
-    for (int s = 0; s < nsteps; s++) launch_staged_step<T>(b);
+    for (int s = 0; s < nsteps; s++) { ox_status st = launch_staged_step<T>(b); if (st) return st; }
   }
   CU_TRY(cudaGetLastError());
   return OX_OK;
@@ -254,6 +264,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   const FieldInfo& fi = it->second;
   if (field == OX_F_ACT) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
   if (fi.count == 0) return OX_OK;
+  if (dir == 1 && !field_live(b, field)) { ox::set_error("ox_batch_get: " + OX_STALE_MSG(field)); return OX_ERR_INVALID; }
   if (layout != OX_LAYOUT_ENV_MAJOR && layout != OX_LAYOUT_ELEM_MAJOR) { ox::set_error("bulk I/O: bad layout"); return OX_ERR_INVALID; }
   if (!fi.is_int && dtype != OX_F32 && dtype != OX_F64) { ox::set_error("bulk I/O: bad dtype"); return OX_ERR_INVALID; }
   CU_TRY(cudaSetDevice(b->cfg.device));
@@ -280,6 +291,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
     else launch_pack<float, float>(b, fi.ptr, dbuf, fi.count, layout, dir);
   }
   CU_TRY(cudaGetLastError());
+  if (dir == 0 && (field == OX_F_QFRC_APPLIED || field == OX_F_XFRC_APPLIED)) b->applied = 1;
   if (mem == OX_MEM_HOST && dir == 1) {
     if (staged) CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
     if (sync) CU_TRY(cudaStreamSynchronize(b->stream));
@@ -299,6 +311,7 @@ ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, doubl
   }
   if ((iout != nullptr) != fi.is_int) { ox::set_error("per-env I/O: int/real field mismatch"); return OX_ERR_INVALID; }
   if (count == 0) return OX_OK;
+  if (!din && !field_live(b, field)) { ox::set_error("ox_batch_get1: " + OX_STALE_MSG(field)); return OX_ERR_INVALID; }
   CU_TRY(cudaSetDevice(b->cfg.device));
   const size_t esz = fi.is_int ? 4 : (b->f64 ? 8 : 4);
   ox_status s = ensure_htmp(b, (size_t)count * 8);
@@ -306,6 +319,7 @@ ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, doubl
   unsigned char* base = (unsigned char*)fi.ptr + ((size_t)offset * b->stride + env) * esz;
   const size_t pitch = (size_t)b->stride * esz;
   if (din) {
+    if (field == OX_F_QFRC_APPLIED || field == OX_F_XFRC_APPLIED) b->applied = 1;
     if (b->f64) for (int i = 0; i < count; i++) ((double*)b->h_tmp)[i] = din[i];
     else for (int i = 0; i < count; i++) ((float*)b->h_tmp)[i] = (float)din[i];
     CU_TRY(cudaMemcpy2DAsync(base, pitch, b->h_tmp, esz, esz, count, cudaMemcpyHostToDevice, b->stream));
@@ -324,28 +338,35 @@ ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, doubl
 
 template <typename T>
 static ox_status stage_times_impl(ox_batch* b, int reps, double* out_ms) {
-  std::vector<cudaEvent_t> ev(ST_COUNT + 1);
+  // Steps the batch `reps` times in staged order (it DOES advance the simulation, exactly like ox_batch_step(reps) in
+  // staged mode: user controls are kept unless the Philox source is on), with an event after every stage.
+  struct Events {
+    std::vector<cudaEvent_t> ev;
+    ~Events() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+  } E;
+  E.ev.assign(ST_COUNT + 1, nullptr);
+  auto& ev = E.ev;
   for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
   for (int s = 0; s < ST_COUNT; s++) out_ms[s] = 0;
-  StepArgs a = make_args(b, 1);
   for (int r = 0; r < reps; r++) {
+    StepArgs a = make_args(b, 1);
     CU_TRY(cudaEventRecord(ev[0], b->stream));
 #define RUN(S)                                          \
   launch_stage<T, S>(b, a);                             \
   CU_TRY(cudaEventRecord(ev[S + 1], b->stream));
-    RUN(ST_CTRL) RUN(ST_CHECK) RUN(ST_KIN) RUN(ST_CRB) RUN(ST_COLLIDE) RUN(ST_VEL) RUN(ST_EFC) RUN(ST_ACC)
+    if (b->philox) launch_stage<T, ST_CTRL>(b, a);
+    CU_TRY(cudaEventRecord(ev[ST_CTRL + 1], b->stream));
+    RUN(ST_CHECK) RUN(ST_KIN) RUN(ST_CRB) RUN(ST_COLLIDE) RUN(ST_VEL) RUN(ST_EFC) RUN(ST_ACC)
     if (b->coop) {
-      if (sizeof(T) == 8) launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
-      else launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
-      b->launches++;
+      CU_TRY(launch_solve_coop<T>(b));
       CU_TRY(cudaEventRecord(ev[ST_SOLVE + 1], b->stream));
     } else {
       RUN(ST_SOLVE)
     }
     RUN(ST_SENSE) RUN(ST_INTEGRATE)
 #undef RUN
-    k_bump<<<1, 1, 0, b->stream>>>(b->d_step, 1);
-    b->launches++;
+    if (b->philox) b->h_step++;
+    CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(b->stream));
     for (int s = 0; s < ST_COUNT; s++) {
       float ms = 0;
@@ -354,7 +375,6 @@ static ox_status stage_times_impl(ox_batch* b, int reps, double* out_ms) {
     }
   }
   for (int s = 0; s < ST_COUNT; s++) out_ms[s] /= std::max(1, reps);
-  for (auto& e : ev) cudaEventDestroy(e);
   return OX_OK;
 }
 
@@ -422,10 +442,12 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   CU_TRY(cudaMemset(b->arena, 0, b->arena_bytes));
   if (b->f64) { layout_arena<double>(t, b->stride, b->arena, &b->bd, &b->fields); b->bd.nenv = b->nenv; b->bd.stride = b->stride; b->bd.lanes = b->lanes; }
   else { layout_arena<float>(t, b->stride, b->arena, &b->bf, &b->fields); b->bf.nenv = b->nenv; b->bf.stride = b->stride; b->bf.lanes = b->lanes; }
-  if (cfg->mode == OX_MODE_STAGED && ox::solve_coop_eligible(t))
+  // the warp-cooperative solver also needs its shared-memory footprint (model tables + 8 warps of row scratch) to fit
+  const bool coop_ok = ox::solve_coop_eligible(t) && ox::solve_coop_smem(b->blob_bytes, b->f64) <= 200 * 1024;
+  if (cfg->mode == OX_MODE_STAGED && coop_ok)
     b->coop = cfg->coop_solver > 0 || (cfg->coop_solver < 0 && t.nv > 12);
   if (cfg->coop_solver > 0 && !b->coop) {
-    ox::set_error("ox_batch_create: coop_solver needs mode=staged, the Newton solver, nv <= 32");
+    ox::set_error("ox_batch_create: coop_solver needs mode=staged, the Newton solver, nv <= 32 and model tables + solver scratch within 200 KB of shared memory");
     return OX_ERR_INVALID;
   }
   if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
@@ -435,8 +457,9 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     b->spec_rt.tolerance = b->f64 ? effective_tolerance<double>(t, cfg->tolerance) : effective_tolerance<float>(t, cfg->tolerance);
     bool acc_sensor = false;  // acceleration-stage sensors read the solved qacc: the PRE phase of the split pipeline runs too early for them
     for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER;
-    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && ox::solve_coop_eligible(t) && t.integrator == OX_INT_EULER && !acc_sensor;
+    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && coop_ok && t.integrator == OX_INT_EULER && !acc_sensor;
   }
+  if (b->coop || b->split) CU_TRY(ox::solve_coop_prepare(b->blob_bytes, b->f64));
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
   CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));
   CU_TRY(cudaMalloc(&b->d_mask, b->stride));
@@ -527,6 +550,7 @@ ox_status ox_batch_forward(ox_batch* b) {
   if (b->f64) k_forward_fused<double><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bd);
   else k_forward_fused<float><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bf);
   b->launches++;
+  b->derived_stale = false;
   CU_TRY(cudaGetLastError());
   return OX_OK;
 }
@@ -543,6 +567,7 @@ ox_status ox_batch_reset(ox_batch* b, const uint8_t* host_mask) {
   else k_reset<float><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, b->bf, dm);
   b->launches++;
   CU_TRY(cudaGetLastError());
+  if (!host_mask) b->applied = 0;  // mj_resetData on every env zeroed the applied forces
   return OX_OK;
 }
 
@@ -565,9 +590,7 @@ ox_status ox_batch_ctrl_philox(ox_batch* b, int32_t enable, uint64_t seed) {
 ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step) {
   if (!b) { ox::set_error("ox_batch_set_step_counter: null batch"); return OX_ERR_INVALID; }
   CU_TRY(cudaSetDevice(b->cfg.device));
-  long long v = step;
-  CU_TRY(cudaMemcpyAsync(b->d_step, &v, sizeof v, cudaMemcpyHostToDevice, b->stream));
-  CU_TRY(cudaStreamSynchronize(b->stream));
+  b->h_step = step;  // a captured graph picks it up at its next launch (do_step compares with d_step_val)
   return OX_OK;
 }
 

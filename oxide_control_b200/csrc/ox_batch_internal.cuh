@@ -27,7 +27,11 @@ struct ox_batch {
   long long launches = 0;
   int philox = 0;
   uint64_t seed = 0;
-  long long* d_step = nullptr;
+  long long h_step = 0;          // Philox step index of the next step (passed to the kernels by value)
+  long long* d_step = nullptr;   // device copy, read only by a captured CUDA graph (staged mode)
+  long long d_step_val = 0;      // what *d_step holds (host's view)
+  bool derived_stale = false;    // see field_live() below
+  int applied = 0;               // a user wrote qfrc_applied / xfrc_applied since the last full reset
   void* d_tmp = nullptr;  // staging for bulk I/O
   size_t d_tmp_bytes = 0;
   void* h_tmp = nullptr;  // pinned staging for per-env I/O
@@ -46,6 +50,31 @@ struct ox_batch {
   int io_f64 = 0;
 };
 
+
+// Which fields hold current values. The generic kernels keep every mjData field in the batch; the model-specialised step
+// kernel keeps intermediates on-chip and writes back only the state, qacc, qacc_warmstart, sensordata and the counters
+// (the split pipeline for large models also exchanges qM, the smooth forces / accelerations and the constraint rows).
+// After such a step every other field still holds what the last ox_batch_forward / generic step left there, so reading
+// it is refused (loudly) until ox_batch_forward has refreshed the batch.
+inline bool field_live(bool stale, bool split, int field) {
+  if (!stale) return true;
+  switch (field) {
+    case OX_F_QPOS: case OX_F_QVEL: case OX_F_CTRL: case OX_F_QFRC_APPLIED: case OX_F_XFRC_APPLIED: case OX_F_QACC_WARMSTART:
+    case OX_F_TIME: case OX_F_ACT: case OX_F_QACC: case OX_F_SENSORDATA: case OX_F_NCON: case OX_F_NEFC: case OX_F_SOLVER_NITER:
+    case OX_F_DIVERGED:
+      return true;
+    case OX_F_QM: case OX_F_QFRC_SMOOTH: case OX_F_QACC_SMOOTH: case OX_F_QFRC_CONSTRAINT: case OX_F_EFC_J: case OX_F_EFC_POS:
+    case OX_F_EFC_MARGIN: case OX_F_EFC_D: case OX_F_EFC_AREF: case OX_F_EFC_FORCE:
+      return split;
+    default:
+      return false;
+  }
+}
+inline bool field_live(const ox_batch* b, int field) { return field_live(b->derived_stale, b->split, field); }
+#define OX_STALE_MSG(field)                                                                                              \
+  ("field " + std::to_string(field) + " is not maintained by the model-specialised step kernel (it writes back qpos, qvel, " \
+   "time, qacc, qacc_warmstart, sensordata and the counters only): call ox_batch_forward() first, or create the batch with " \
+   "specialize = 0")
 
 #define CU_TRY(expr)                                                                                   \
   do {                                                                                                 \

@@ -121,6 +121,7 @@ __global__ void k_env_post(const unsigned char* __restrict__ gblob, int bytes, D
         const int el = idx / a.obs_dim, k = idx - el * a.obs_dim;
         obs[(size_t)e0 * a.obs_dim + idx] = (TU)arena[a.obs_off[k] + e0 + el];
       }
+      __syncwarp();  // the gather read OTHER lanes' arena values; an auto-reset below rewrites this lane's qpos / qvel
     } else {
       for (int k = 0; k < a.obs_dim; k++) obs[(size_t)e * a.obs_dim + k] = (TU)arena[a.obs_off[k] + e];
     }
@@ -178,6 +179,9 @@ ox_status resolve(const ox_batch* b, int field, int index, const char* what, lon
   if (it == b->fields.end() || it->second.is_int || !it->second.ptr) {
     ox::set_error(std::string("ox_env_create: ") + what + " names field " + std::to_string(field) + ", which is not a real-valued batch field");
     return OX_ERR_INVALID;
+  }
+  {  // a task may only read what the batch's step kernel keeps current (see field_live in ox_batch_internal.cuh)
+    if (!field_live(b->spec != nullptr && b->cfg.mode == OX_MODE_FUSED, b->split, field)) { ox::set_error(std::string("ox_env_create: ") + what + ": " + OX_STALE_MSG(field)); return OX_ERR_INVALID; }
   }
   if (index < 0 || index >= it->second.count) {
     ox::set_error(std::string("ox_env_create: ") + what + " index " + std::to_string(index) + " out of range for field " + std::to_string(field) +

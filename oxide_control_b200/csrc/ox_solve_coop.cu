@@ -295,19 +295,27 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
 #undef ROW
 }
 
+constexpr size_t COOP_SMEM_LIMIT = 200 * 1024;  // opt-in dynamic shared memory per CTA this kernel asks for (the SM has 227 KB)
+
+size_t solve_coop_smem(int blob_bytes, bool f64) {
+  return (size_t)((blob_bytes + 127) / 128) * 128 + (size_t)COOP_WARPS * coop_warp_words() * (f64 ? sizeof(double) : sizeof(float));
+}
+
+// cudaFuncSetAttribute is per DEVICE: called from ox_batch_create (after cudaSetDevice) for every batch that will use the
+// cooperative solver, so that a second batch on another GPU of the same process gets the opt-in too.
+cudaError_t solve_coop_prepare(int blob_bytes, bool f64) {
+  if (solve_coop_smem(blob_bytes, f64) > COOP_SMEM_LIMIT) return cudaErrorInvalidValue;
+  return f64 ? cudaFuncSetAttribute(k_solve_coop<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_LIMIT)
+             : cudaFuncSetAttribute(k_solve_coop<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_LIMIT);
+}
+
 template <typename T>
 static cudaError_t launch_coop(cudaStream_t stream, const unsigned char* blob, int bytes, const DevBatch<T>& b, int nefcmax) {
   (void)nefcmax;
-  const size_t smem = (size_t)((bytes + 127) / 128) * 128 + (size_t)COOP_WARPS * coop_warp_words() * sizeof(T);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_solve_coop<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  const size_t smem = solve_coop_smem(bytes, sizeof(T) == 8);
   const int grid = (b.nenv + COOP_WARPS - 1) / COOP_WARPS;
   k_solve_coop<T><<<grid, 32 * COOP_WARPS, smem, stream>>>(blob, bytes, b);
-  return cudaGetLastError();
+  return cudaPeekAtLastError();  // the caller propagates it (CU_TRY); peek so that the sticky state is not silently cleared
 }
 
 cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax) { return launch_coop<float>(s, blob, bytes, b, nefcmax); }

@@ -19,7 +19,14 @@ struct StepArgs {
   int philox;
   uint64_t seed;
   int64_t env_id_offset;
-  const long long* d_step;
+  // Philox step index of the first step of this launch: a kernel argument from the batch's host-side counter, so that a
+  // step is ONE launch. Only a captured CUDA graph (staged mode, frozen arguments) reads the device counter d_step
+  // instead, which the last stage kernel of the captured step advances itself.
+  long long step0 = 0;
+  long long* d_step = nullptr;
+  // 0: no user of this batch has written qfrc_applied / xfrc_applied since the last full reset, so the step neither loads
+  // nor tests them (they are 57 of the cheetah's 128 words read per env-step, all zero in an RL loop)
+  int applied = 1;
   // ox_batch_step_io: env-major user buffers (device memory or pinned host memory addressed over PCIe) that the step
   // kernel itself reads the controls from and writes the new state to - no separate layout-conversion launches
   const void* io_ctrl = nullptr;
@@ -91,13 +98,24 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   for (int i = 0; i < H::nv; i++) loc_qvel[i] = G(qvel, i);
   loc_time[0] = G(time, 0);
   loc_diverged[0] = G(diverged, 0);
+  const int32_t div0 = loc_diverged[0];
+  (void)div0;
   auto load_inputs = [&]() {
 #pragma unroll
-    for (int i = 0; i < H::nv; i++) { loc_qacc_warmstart[i] = G(qacc_warmstart, i); loc_qfrc_applied[i] = G(qfrc_applied, i); }
+    for (int i = 0; i < H::nv; i++) loc_qacc_warmstart[i] = G(qacc_warmstart, i);
 #pragma unroll
     for (int i = 0; i < H::nu; i++) loc_ctrl[i] = G(ctrl, i);
+    if (a.applied) {
 #pragma unroll
-    for (int i = 0; i < 6 * H::nbody; i++) loc_xfrc_applied[i] = G(xfrc_applied, i);
+      for (int i = 0; i < H::nv; i++) loc_qfrc_applied[i] = G(qfrc_applied, i);
+#pragma unroll
+      for (int i = 0; i < 6 * H::nbody; i++) loc_xfrc_applied[i] = G(xfrc_applied, i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < H::nv; i++) loc_qfrc_applied[i] = 0;
+#pragma unroll
+      for (int i = 0; i < 6 * H::nbody; i++) loc_xfrc_applied[i] = 0;
+    }
   };
   auto store_state = [&](bool inputs_too) {
 #pragma unroll
@@ -124,10 +142,13 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
       env.step();
     }
     // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
-    store_state(false);
+    // an auto-reset (mj_checkPos/Vel/Acc -> mj_resetData) inside this launch also cleared ctrl and the applied forces: the
+    // batch copy must see that too, as it does with the generic kernels
+    const bool did_reset = loc_diverged[0] != div0;
+    store_state(did_reset);
 #pragma unroll
     for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = loc_qacc_warmstart[i]; G(qacc, i) = loc_qacc[i]; }
-    if (a.philox) {
+    if (a.philox || did_reset) {
 #pragma unroll
       for (int i = 0; i < H::nu; i++) G(ctrl, i) = loc_ctrl[i];
     }
@@ -187,6 +208,8 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
       for (int i = 0; i < H::nv; i++) { G(qacc, i) = loc_qacc[i]; G(qacc_warmstart, i) = loc_qacc_warmstart[i]; }
 #pragma unroll
       for (int i = 0; i < H::nu; i++) G(ctrl, i) = loc_ctrl[i];
+#pragma unroll
+      for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = loc_sensordata[i];
       G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = loc_nefc[0]; G(solver_niter, 0) = loc_solver_niter[0];
     }
     G(acc_ncon, 0) = loc_acc_ncon[0]; G(acc_nefc, 0) = loc_acc_nefc[0]; G(acc_niter, 0) = loc_acc_niter[0];
@@ -244,7 +267,7 @@ __global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
     if (a.io_f64) spec_io_in<T, double>(g.ctrl, H::nu, (const double*)a.io_ctrl, g, e);
     else spec_io_in<T, float>(g.ctrl, H::nu, (const float*)a.io_ctrl, g, e);
   }
-  const long long step0 = a.philox ? *a.d_step : 0;
+  const long long step0 = a.d_step ? *a.d_step : a.step0;
   spec_step_env<S, T, PHASE>(g, e, a, rt, step0);
   if (PHASE != 1) {
     if (a.io_qpos) {

@@ -388,6 +388,10 @@ class Physics:
 
     def __init__(self, model: Model, **kw):
         kw.setdefault("precision", "f64")
+        # data() stands for &mjData: every derived field must be current after step(), which only the generic kernels
+        # guarantee (the model-specialised kernel writes back state, qacc, sensordata and counters only - see
+        # field_live() in csrc/ox_batch_internal.cuh; reading anything else after such a step is an error)
+        kw.setdefault("specialize", False)
         self._model = model
         self._b = BatchedPhysics(model, 1, **kw)
 
