@@ -172,7 +172,10 @@ typedef struct ox_batch_config {
   int32_t block_threads; /* 0 = default */
   int64_t env_id_offset; /* global env id of env 0 (multi-GPU sharding; keys the Philox control stream) */
   double tolerance;      /* <0 = model's, floored at 8*eps of `precision` (1e-6 in fp32; no effect in fp64) */
-  int32_t specialize;    /* 1 (default): use the model-specialised step kernel when one was compiled in (fused mode) */
+  int32_t specialize;    /* fused mode. 0: generic kernels (every mjData field stays current). 1 (default): the model-specialised
+                            step kernel - compiled into the library for the spec_models, otherwise compiled at run time
+                            (nvcc, cached on disk) when nenv >= 1024; generic kernel if neither is available.
+                            2: always specialise at run time if needed; ox_batch_create fails if that is impossible. */
   int32_t lanes_per_warp; /* active envs per warp, 1..32; 0 = auto (thin warps while the batch cannot fill every SM scheduler) */
   int32_t coop_solver;   /* staged mode: warp-per-env Newton solver; -1 auto (on when eligible and nv > 12), 0 off, 1 on */
   int32_t reserved_;
@@ -237,6 +240,12 @@ OX_API ox_status ox_batch_stats(ox_batch* b, double* out4);
 OX_API int64_t ox_batch_launch_count(const ox_batch* b);
 /* which step kernel this batch launches: a spec name ("cheetah"), or the generic kernel */
 OX_API const char* ox_batch_kernel_name(const ox_batch* b);
+/* "" or the reason a batch that asked for a specialised kernel runs the generic one (no nvcc, compile error, ...) */
+OX_API const char* ox_batch_jit_note(const ox_batch* b);
+/* Run-time specialisation without a batch (and without a GPU): compile the model's step kernel with nvcc into the on-disk
+ * cache ($OX_B200_CACHE_DIR, default ~/.cache/ox_b200) or find it there; the cubin path is copied into path_out. A later
+ * ox_batch_create for the same model and precision then loads it from the cache. OX_B200_JIT=0 disables the mechanism. */
+OX_API ox_status ox_jit_compile(const ox_model* m, int32_t precision, char* path_out, int32_t path_cap);
 /* model-specialised kernels compiled into the library (every .xml under oxide_control_b200/spec_models at build time) */
 OX_API int32_t ox_spec_count(void);
 OX_API const char* ox_spec_name(int32_t i);

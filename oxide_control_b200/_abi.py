@@ -105,6 +105,8 @@ SYMBOLS = {
     "ox_batch_stats": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "ox_batch_launch_count": (C.c_int64, [_P]),
     "ox_batch_kernel_name": (C.c_char_p, [_P]),
+    "ox_batch_jit_note": (C.c_char_p, [_P]),
+    "ox_jit_compile": (C.c_int32, [_P, C.c_int32, C.c_char_p, C.c_int32]),
     "ox_spec_count": (C.c_int32, []),
     "ox_spec_name": (C.c_char_p, [C.c_int32]),
     "ox_batch_stage_times": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

@@ -133,6 +133,22 @@ cudaError_t launch_solve_coop(ox_batch* b) {
   return launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
 }
 
+// launch one phase (0 = whole step, 1 = PRE, 2 = POST) of the batch's model-specialised kernel: a compiled-in launcher, or a
+// kernel compiled at run time (cudaKernel_t from ox_jit.cpp)
+template <typename T>
+cudaError_t launch_spec(ox_batch* b, int phase, const StepArgs& a) {
+  const SpecEntry* sp = b->spec;
+  b->launches++;
+  void* k = sizeof(T) == 8 ? sp->jit_f64[phase] : sp->jit_f32[phase];
+  if (k) {
+    void* args[3] = {(void*)&dev<T>(b), (void*)&a, (void*)&b->spec_rt};
+    return cudaLaunchKernel((const void*)k, dim3(b->grid), dim3(b->block), args, 0, b->stream);
+  }
+  if (sizeof(T) == 8) (phase == 0 ? sp->launch_f64 : sp->launch_split_f64[phase - 1])(b->grid, b->block, b->stream, b->bd, a, b->spec_rt);
+  else (phase == 0 ? sp->launch_f32 : sp->launch_split_f32[phase - 1])(b->grid, b->block, b->stream, b->bf, a, b->spec_rt);
+  return cudaPeekAtLastError();
+}
+
 StepArgs make_args(ox_batch* b, int nsteps) {
   StepArgs a;
   a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset;
@@ -177,13 +193,9 @@ ox_status do_step(ox_batch* b, int nsteps) {
       // specialised PRE -> warp-cooperative Newton solve -> specialised POST, one step at a time
       for (int s = 0; s < nsteps; s++) {
         const StepArgs a1 = make_args(b, 1);
-        if (sizeof(T) == 8) b->spec->launch_split_f64[0](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
-        else b->spec->launch_split_f32[0](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
-        b->launches++;
+        CU_TRY(launch_spec<T>(b, 1, a1));
         CU_TRY(launch_solve_coop<T>(b));
-        if (sizeof(T) == 8) b->spec->launch_split_f64[1](b->grid, b->block, b->stream, b->bd, a1, b->spec_rt);
-        else b->spec->launch_split_f32[1](b->grid, b->block, b->stream, b->bf, a1, b->spec_rt);
-        b->launches++;
+        CU_TRY(launch_spec<T>(b, 2, a1));
         if (b->philox) b->h_step++;
       }
       b->derived_stale = true;
@@ -191,12 +203,11 @@ ox_status do_step(ox_batch* b, int nsteps) {
       return OX_OK;
     } else if (b->spec) {
       b->derived_stale = true;
-      if (sizeof(T) == 8) b->spec->launch_f64(b->grid, b->block, b->stream, b->bd, make_args(b, nsteps), b->spec_rt);
-      else b->spec->launch_f32(b->grid, b->block, b->stream, b->bf, make_args(b, nsteps), b->spec_rt);
+      CU_TRY(launch_spec<T>(b, 0, make_args(b, nsteps)));
     } else {
       k_step_fused<T><<<b->grid, b->block, b->blob_bytes, b->stream>>>(b->d_blob, b->blob_bytes, dev<T>(b), make_args(b, nsteps));
+      b->launches++;
     }
-    b->launches++;
     if (b->philox) b->h_step += nsteps;
   } else if (b->cfg.use_graph) {
     if (!b->graph_exec) {
@@ -452,12 +463,27 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
   }
   if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
     b->spec = ox::find_spec(ox::model_hash(t));
+    if (b->spec && !b->spec->has_phase(b->f64, 0)) b->spec = nullptr;
+    if (!b->spec) {
+      // not one of the models compiled into the library: specialise at run time (ox_jit.cpp). specialize = 1 does so for
+      // batches where throughput is the point (>= 1024 envs; a cached cubin is a file read, a miss is one nvcc run) and
+      // silently keeps the generic kernel otherwise or when the JIT is unavailable; specialize = 2 insists.
+      const bool want = cfg->specialize >= 2 || b->nenv >= 1024;
+      if (want) {
+        std::string why;
+        b->spec = ox::jit_spec(t, b->f64, true, true, &why, nullptr);
+        if (!b->spec) {
+          if (cfg->specialize >= 2) { ox::set_error("ox_batch_create: specialize = 2 but no specialised kernel could be built: " + why); return OX_ERR_CUDA; }
+          b->jit_note = why;
+        }
+      }
+    }
     b->spec_rt.iterations = cfg->iterations > 0 ? cfg->iterations : t.iterations;
     b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
     b->spec_rt.tolerance = b->f64 ? effective_tolerance<double>(t, cfg->tolerance) : effective_tolerance<float>(t, cfg->tolerance);
     bool acc_sensor = false;  // acceleration-stage sensors read the solved qacc: the PRE phase of the split pipeline runs too early for them
     for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER;
-    b->split = b->spec && b->spec->launch_split_f32[0] && cfg->coop_solver != 0 && coop_ok && t.integrator == OX_INT_EULER && !acc_sensor;
+    b->split = b->spec && b->spec->has_phase(b->f64, 1) && b->spec->has_phase(b->f64, 2) && cfg->coop_solver != 0 && coop_ok && t.integrator == OX_INT_EULER && !acc_sensor;
   }
   if (b->coop || b->split) CU_TRY(ox::solve_coop_prepare(b->blob_bytes, b->f64));
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
@@ -502,6 +528,18 @@ const char* ox_batch_kernel_name(const ox_batch* b) {
   if (b->cfg.mode != OX_MODE_FUSED) return b->coop ? "k_stage + k_solve_coop (warp-per-env Newton)" : "k_stage (generic, one kernel per stage)";
   if (b->spec && b->split) { static thread_local std::string nm; nm = std::string(b->spec->name) + " (split: spec PRE + k_solve_coop + spec POST)"; return nm.c_str(); }
   return b->spec ? b->spec->name : "k_step_fused (generic)";
+}
+/* why a batch that asked for a specialised kernel runs the generic one ("" when it does not) */
+const char* ox_batch_jit_note(const ox_batch* b) { return b ? b->jit_note.c_str() : nullptr; }
+
+/* Compile (or find in the on-disk cache) the run-time specialised step kernel of a model WITHOUT creating a batch: needs
+ * nvcc but no GPU, so images can be warmed at build / deploy time. The cubin's path is copied into path_out. */
+ox_status ox_jit_compile(const ox_model* m, int32_t precision, char* path_out, int32_t path_cap) {
+  if (!m || (precision != OX_F32 && precision != OX_F64)) { ox::set_error("ox_jit_compile: bad argument"); return OX_ERR_INVALID; }
+  std::string why, path;
+  if (!ox::jit_spec(m->t, precision == OX_F64, true, false, &why, &path)) { ox::set_error("ox_jit_compile: " + why); return OX_ERR_COMPILE; }
+  if (path_out && path_cap > 0) { snprintf(path_out, (size_t)path_cap, "%s", path.c_str()); }
+  return OX_OK;
 }
 int32_t ox_spec_count(void) { return ox::spec_count(); }
 const char* ox_spec_name(int32_t i) { const ox::SpecEntry* e = ox::spec_at(i); return e ? e->name : nullptr; }

@@ -43,6 +43,7 @@ struct ox_batch {
   bool coop = false;  // staged mode: warp-cooperative Newton solver (ox_solve_coop.cu) instead of the thread-per-env solve stage
   const ox::SpecEntry* spec = nullptr;  // model-specialised step kernel, when one was compiled in for this model
   ox::SpecRuntime spec_rt{};
+  std::string jit_note;  // why a batch that wanted a specialised kernel fell back to the generic one
   // transient: set by ox_batch_step_io around one do_step (device-addressable env-major buffers, see StepArgs)
   const void* io_ctrl = nullptr;
   void* io_qpos = nullptr;

@@ -5,6 +5,8 @@
 //     registers; only the algorithmic state is read from / written to the SoA batch in HBM.
 // One thread = one environment, one launch = nsteps steps.
 #pragma once
+#include <string>
+
 #include "ox_stages.cuh"
 
 namespace ox {
@@ -256,8 +258,9 @@ __device__ __forceinline__ void spec_io_out(const T* field, int cnt, TU* user, c
   }
 }
 
+// body shared by the compiled-in kernels (k_step_spec below) and the run-time compiled ones (extern "C" ox_jit_*, ox_specsrc.h)
 template <class S, typename T, int PHASE>
-__global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
+__device__ __forceinline__ void spec_kernel_body(const DevBatch<T>& g, const StepArgs& a, const SpecRuntime& rt) {
   using H = typename S::Hdr;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (lane >= g.lanes) return;  // deliberately under-filled warps at small batch sizes (see env_index in ox_kernels.cuh)
@@ -280,25 +283,39 @@ __global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) {
     }
   }
 }
+
+template <class S, typename T, int PHASE>
+__global__ void k_step_spec(DevBatch<T> g, StepArgs a, SpecRuntime rt) { spec_kernel_body<S, T, PHASE>(g, a, rt); }
 #endif
 
-// ---- registry of the specialisations compiled into this library
+// ---- registry of the specialisations: compiled into this library (ox_specgen at build time) or compiled at run time for
+// the model of a batch (ox_jit.cpp; jit_* hold cudaKernel_t handles of the extern "C" kernels, PHASE 0 / 1 / 2)
 struct SpecEntry {
-  uint64_t hash;
-  const char* name;
-  void (*launch_f32)(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt);
-  void (*launch_f64)(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt);
+  uint64_t hash = 0;
+  const char* name = nullptr;
+  void (*launch_f32)(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt) = nullptr;
+  void (*launch_f64)(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt) = nullptr;
   // split pipeline around the warp-cooperative solver (null when not generated for this model): [0] = PRE, [1] = POST
-  void (*launch_split_f32[2])(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt);
-  void (*launch_split_f64[2])(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt);
-  void (*host_f32)(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);   // tests/native only
-  void (*host_f64)(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
-  void (*host_split_f32[2])(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
-  void (*host_split_f64[2])(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0);
+  void (*launch_split_f32[2])(int grid, int block, void* stream, const DevBatch<float>& g, const StepArgs& a, const SpecRuntime& rt) = {nullptr, nullptr};
+  void (*launch_split_f64[2])(int grid, int block, void* stream, const DevBatch<double>& g, const StepArgs& a, const SpecRuntime& rt) = {nullptr, nullptr};
+  void (*host_f32)(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) = nullptr;   // tests/native only
+  void (*host_f64)(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) = nullptr;
+  void (*host_split_f32[2])(const DevBatch<float>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) = {nullptr, nullptr};
+  void (*host_split_f64[2])(const DevBatch<double>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) = {nullptr, nullptr};
+  void* jit_f32[3] = {nullptr, nullptr, nullptr};
+  void* jit_f64[3] = {nullptr, nullptr, nullptr};
+  bool has_phase(bool f64, int phase) const {
+    if (f64) return jit_f64[phase] || (phase == 0 ? launch_f64 != nullptr : launch_split_f64[phase - 1] != nullptr);
+    return jit_f32[phase] || (phase == 0 ? launch_f32 != nullptr : launch_split_f32[phase - 1] != nullptr);
+  }
 };
 void register_spec(const SpecEntry& e);
 const SpecEntry* find_spec(uint64_t hash);
 int spec_count();
 const SpecEntry* spec_at(int i);
+// run-time specialisation (ox_jit.cpp): a SpecEntry whose jit_f32 / jit_f64 kernels exist for `f64`, compiling the model's
+// unit with nvcc if the on-disk cache has none and `allow_compile`; nullptr + *why otherwise. Needs no GPU unless `load`.
+const SpecEntry* jit_spec(const ox_model_tables& t, bool f64, bool allow_compile, bool load, std::string* why, std::string* cubin_path);
+bool jit_enabled();
 
 }  // namespace ox

@@ -1,31 +1,14 @@
 // ox_specgen: build-time generator of a model-specialised translation unit.
 //   ox_specgen <model.xml> <name> > spec_<name>.cu
-// It compiles the MJCF with the product's own compiler and prints a model policy type whose table lookups are
-// compile-time constants (function-local constexpr arrays), plus the launchers and the registry entry.
-#include <cinttypes>
+// It compiles the MJCF with the product's own compiler and prints the unit ox_specsrc.h generates: a model policy type
+// whose table lookups are compile-time constants, plus the launchers and the registry entry.
 #include <cstdio>
 #include <fstream>
 #include <sstream>
 #include <string>
 
-#include "ox_model.h"
-#include "ox_spec.cuh"
+#include "ox_specsrc.h"
 #include "ox_xml.h"
-
-static void emit_int(const char* name, const int32_t* v, long n) {
-  std::printf("  static OX_HD int32_t %s(int i) {\n", name);
-  if (n == 0) { std::printf("    (void)i; return 0;\n  }\n"); return; }
-  std::printf("    static constexpr int32_t t_[%ld] = {", n);
-  for (long i = 0; i < n; i++) std::printf("%s%d", i ? ", " : "", v[i]);
-  std::printf("};\n    return t_[i];\n  }\n");
-}
-static void emit_real(const char* name, const double* v, long n) {
-  std::printf("  static OX_HD T %s(int i) {\n", name);
-  if (n == 0) { std::printf("    (void)i; return (T)0;\n  }\n"); return; }
-  std::printf("    static constexpr T t_[%ld] = {", n);
-  for (long i = 0; i < n; i++) std::printf("%s(T)%.17g", i ? ", " : "", v[i]);
-  std::printf("};\n    return t_[i];\n  }\n");
-}
 
 int main(int argc, char** argv) {
   if (argc != 3) { std::fprintf(stderr, "usage: ox_specgen model.xml name\n"); return 2; }
@@ -40,49 +23,8 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "ox_specgen: %s: %s\n", argv[1], e.what());
     return 1;
   }
-  const ox_model_tables& t = m->t;
-  const char* nm = argv[2];
-  int any_damping = 0;
-  for (int i = 0; i < t.nv; i++) if (t.dof_damping[i] > 0) any_damping = 1;
-  std::printf("// GENERATED by ox_specgen from %s - do not edit. Model hash 0x%016" PRIx64 "\n", argv[1], ox::model_hash(t));
-  std::printf("#include \"ox_spec.cuh\"\n#ifdef __CUDACC__\n#include <cuda_runtime.h>\n#endif\nnamespace ox {\nnamespace {\n");
-  std::printf("template <typename T>\nstruct Spec_%s {\n  struct Hdr {\n", nm);
-  std::printf("    static constexpr int nq = %d, nv = %d, nu = %d, na = %d, nbody = %d, njnt = %d, ngeom = %d, nsite = %d, nM = %d, npair = %d,\n"
-              "                         nsensor = %d, nsensordata = %d, nconmax = %d, nefcmax = %d;\n",
-              t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata, t.nconmax, t.nefcmax);
-  std::printf("    static constexpr int integrator = %d, solver = %d, cone = %d, disableflags = %d, any_damping = %d;\n", t.integrator,
-              t.solver, t.cone, t.disableflags, any_damping);
-  std::printf("    static constexpr double timestep = %.17g, ls_tolerance = %.17g, impratio = %.17g, meaninertia = %.17g;\n", t.timestep,
-              t.ls_tolerance, t.impratio, t.meaninertia);
-  std::printf("    static OX_HD double grav(int k) { return k == 0 ? %.17g : (k == 1 ? %.17g : %.17g); }\n", t.gravity[0], t.gravity[1],
-              t.gravity[2]);
-  std::printf("    int iterations, ls_iterations;\n    double tolerance;\n  };\n  Hdr hdr;\n  OX_HD const Hdr& h() const { return hdr; }\n");
-#define OX_X(name, n, w) emit_int(#name, t.name, (long)t.n * (w));
-  OX_MODEL_INT_TABLES(OX_X)
-#undef OX_X
-#define OX_X(name, n, w) emit_real(#name, t.name, (long)t.n * (w));
-  OX_MODEL_REAL_TABLES(OX_X)
-#undef OX_X
-  std::printf("};\n\n");
-  const bool split = t.nv > 12 && t.integrator == OX_INT_EULER && t.solver == OX_SOL_NEWTON && t.nv <= 32;
-  std::printf("#ifdef __CUDACC__\ntemplate <typename T, int PHASE>\nvoid launch_%s(int grid, int block, void* stream, const DevBatch<T>& g, const StepArgs& a, const SpecRuntime& rt) {\n"
-              "  k_step_spec<Spec_%s<T>, T, PHASE><<<grid, block, 0, (cudaStream_t)stream>>>(g, a, rt);\n}\n#define OX_LAUNCH_F32 &launch_%s<float, 0>\n#define OX_LAUNCH_F64 &launch_%s<double, 0>\n",
-              nm, nm, nm, nm);
-  if (split)
-    std::printf("#define OX_SPLIT_F32 {&launch_%s<float, 1>, &launch_%s<float, 2>}\n#define OX_SPLIT_F64 {&launch_%s<double, 1>, &launch_%s<double, 2>}\n", nm, nm, nm, nm);
-  else
-    std::printf("#define OX_SPLIT_F32 {nullptr, nullptr}\n#define OX_SPLIT_F64 {nullptr, nullptr}\n");
-  std::printf("#else\n#define OX_LAUNCH_F32 nullptr\n#define OX_LAUNCH_F64 nullptr\n#define OX_SPLIT_F32 {nullptr, nullptr}\n#define OX_SPLIT_F64 {nullptr, nullptr}\n#endif\n");
-  std::printf("template <typename T, int PHASE>\nvoid host_%s(const DevBatch<T>& g, int e, const StepArgs& a, const SpecRuntime& rt, long long step0) {\n"
-              "#ifdef OX_SPEC_HOST\n  spec_step_env<Spec_%s<T>, T, PHASE>(g, e, a, rt, step0);\n#else\n  (void)g; (void)e; (void)a; (void)rt; (void)step0;\n#endif\n}\n", nm, nm);
-  if (split)
-    std::printf("#define OX_HOST_SPLIT_F32 {&host_%s<float, 1>, &host_%s<float, 2>}\n#define OX_HOST_SPLIT_F64 {&host_%s<double, 1>, &host_%s<double, 2>}\n", nm, nm, nm, nm);
-  else
-    std::printf("#define OX_HOST_SPLIT_F32 {nullptr, nullptr}\n#define OX_HOST_SPLIT_F64 {nullptr, nullptr}\n");
-  std::printf("struct Reg_%s {\n  Reg_%s() {\n    register_spec(SpecEntry{0x%016" PRIx64 "ull, \"%s\", OX_LAUNCH_F32, OX_LAUNCH_F64, OX_SPLIT_F32, OX_SPLIT_F64,\n"
-              "#ifdef OX_SPEC_HOST\n                            &host_%s<float, 0>, &host_%s<double, 0>, OX_HOST_SPLIT_F32, OX_HOST_SPLIT_F64});\n#else\n                            nullptr, nullptr, {nullptr, nullptr}, {nullptr, nullptr}});\n#endif\n  }\n} reg_%s;\n",
-              nm, nm, ox::model_hash(t), nm, nm, nm, nm);
-  std::printf("}  // namespace\n}  // namespace ox\n");
+  const std::string src = ox::spec_source_static(m->t, argv[2], argv[1]);
+  std::fwrite(src.data(), 1, src.size(), stdout);
   ox_model_free(m);
   return 0;
 }

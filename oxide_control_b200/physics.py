@@ -152,6 +152,12 @@ class Model:
         raise AttributeError(f"model has no table or size '{name}'")
 
     # src/physics.rs:56-62
+    def jit_compile(self, precision: str = "f32") -> str:
+        """Compile (or find cached) the run-time specialised step kernel of this model; needs nvcc, not a GPU. Returns the cubin path."""
+        buf = C.create_string_buffer(4096)
+        _check(A.lib().ox_jit_compile(self._h, A.F64 if precision == "f64" else A.F32, buf, 4096))
+        return buf.value.decode()
+
     def object_id(self, objtype: int, name: str) -> Optional[ObjectId]:
         i = A.lib().ox_model_name2id(self._h, objtype, name.encode())
         return None if i < 0 else ObjectId(objtype, i)
@@ -343,6 +349,9 @@ class BatchedPhysics:
 
     def kernel_name(self) -> str:
         return A.lib().ox_batch_kernel_name(self._h).decode()
+
+    def jit_note(self) -> str:
+        return (A.lib().ox_batch_jit_note(self._h) or b"").decode()
 
     def launch_count(self) -> int:
         return int(A.lib().ox_batch_launch_count(self._h))

@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+# run-time specialised kernels (csrc/ox_jit.cpp) compiled by the tests are cached in-tree: build/ is git-ignored but
+# travels to the GPU box with the snapshot, so the GPU tests load the cubins the CPU tests compiled here
+os.environ.setdefault("OX_B200_CACHE_DIR", os.path.join(ROOT, "build", "jit_cache"))
 
 
 def pytest_configure(config):

@@ -1,0 +1,554 @@
+"""Dense whole-step checker: a SECOND, structurally different restatement of mj_step used to pin the oracle.
+
+The oracle (oracle/ox_oracle.cpp) and the CUDA kernels (csrc/ox_stages.cuh) follow MuJoCo's own recursive algorithms
+(CRB, RNE, sparse L'DL, primal Newton with exact line search) and share the product's MJCF compiler, so their agreement
+proves a faithful port of each other. This module shares none of that machinery:
+
+  * kinematics is a plain product of homogeneous transforms written from the model tables, differentiated by torch
+    forward-mode autodiff (exact Jacobians and exact second directional derivatives - no finite differences);
+  * the mass matrix is the dense sum  M = sum_b m_b Jc_b' Jc_b + Jw_b' I_b Jw_b (+ armature) and the bias force is the
+    projected Newton-Euler (Kane) sum  c = sum_b Jc_b' m_b (a_b - g) + Jw_b' (I_b alpha_b + w_b x I_b w_b), where a_b and
+    alpha_b are the accelerations at zero generalised acceleration - no composite bodies, no com frame, no recursion;
+  * collision is brute-force geometry (exact segment-segment closest points over the feasible square) on the world-frame
+    geoms, with contact parameters re-mixed here from the geom tables (so the compiler's pair tables are checked too);
+  * constraint Jacobians are d(point)/dq of the same autodiff kinematics; impedance / reference / regularisation are
+    written from the formulas of the MuJoCo documentation as restated in SURVEY.md Appendix A.5-A.6;
+  * the constrained acceleration is the minimiser of the convex objective found by a dense damped Newton iteration with a
+    backtracking line search (scipy-free, LAPACK solves), run to a gradient norm of ~1e-13;
+  * Euler (with the implicit joint-damping solve on the dense M + hB) and RK4 advance the state.
+
+What it shares with the oracle: the compiled model tables as input (body frames, inertias, invweight0 - themselves pinned
+by tests/test_compiler.py and the autograd-Lagrangian tests) and the reading of MuJoCo's documentation by the same author.
+It is test infrastructure: nothing in the product imports it. tools/make_golden.py runs it to produce tests/golden/*.json.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.func import jacfwd, jvp
+
+torch.set_default_dtype(torch.float64)
+
+MINVAL, MINIMP, MAXIMP = 1e-15, 1e-4, 0.9999
+PLANE, SPHERE, CAPSULE, BOX = 0, 2, 3, 6
+FREE, BALL, SLIDE, HINGE = 0, 1, 2, 3
+DSBL = dict(constraint=1 << 0, limit=1 << 3, contact=1 << 4, passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7,
+            filterparent=1 << 9, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
+
+
+def _T(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float64))
+
+
+def quat2mat_t(q):
+    w, x, y, z = q[0], q[1], q[2], q[3]
+    return torch.stack([torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)]),
+                        torch.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)]),
+                        torch.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)])])
+
+
+def hat_t(v):
+    z = torch.zeros((), dtype=v.dtype)
+    return torch.stack([torch.stack([z, -v[2], v[1]]), torch.stack([v[2], z, -v[0]]), torch.stack([-v[1], v[0], z])])
+
+
+def vee(W):
+    return np.array([W[2, 1], W[0, 2], W[1, 0]])
+
+
+def quat_mul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def quat2mat(q):
+    return quat2mat_t(_T(q)).numpy()
+
+
+class DenseModel:
+    """numpy copies of the compiled tables (read through the Python Model mirror)."""
+    INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
+           "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
+           "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited"]
+    REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
+            "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
+            "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
+            "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
+            "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange"]
+
+    def __init__(self, model):
+        self.m = model
+        for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags"):
+            setattr(self, k, int(getattr(model, k)))
+        for k in ("timestep", "impratio"):
+            setattr(self, k, float(getattr(model, k)))
+        self.gravity = np.asarray(model.gravity, dtype=np.float64)
+        for k in self.INT:
+            setattr(self, k, np.asarray(getattr(model, k), dtype=np.int64))
+        for k in self.REAL:
+            setattr(self, k, np.asarray(getattr(model, k), dtype=np.float64))
+
+    def dis(self, name):
+        return bool(self.disableflags & DSBL[name])
+
+
+# ------------------------------------------------------------------------------------------------ kinematics (autodiff)
+def fk(dm: DenseModel, qpos, x):
+    """Body frames from generalised coordinates. x[nv]: hinge/slide coordinates; for free joints global position + a LOCAL
+    rotation vector on top of the quaternion stored in qpos (evaluated at 0); for ball joints a local rotation vector.
+    d/dt x = qvel in MuJoCo's convention. Returns P[nbody,3], R[nbody,3,3]."""
+    P, R = [torch.zeros(3)], [torch.eye(3)]
+    for b in range(1, dm.nbody):
+        p = int(dm.body_parentid[b])
+        Pb = P[p] + R[p] @ _T(dm.body_pos[3 * b:3 * b + 3])
+        Rb = R[p] @ quat2mat_t(_T(dm.body_quat[4 * b:4 * b + 4]))
+        for j in range(int(dm.body_jntadr[b]), int(dm.body_jntadr[b] + dm.body_jntnum[b])):
+            jt, qa, da = int(dm.jnt_type[j]), int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
+            ax, jp = _T(dm.jnt_axis[3 * j:3 * j + 3]), _T(dm.jnt_pos[3 * j:3 * j + 3])
+            if jt == SLIDE:
+                Pb = Pb + Rb @ ax * (x[da] - dm.qpos0[qa])
+            elif jt == HINGE:
+                anchor = Pb + Rb @ jp
+                K = hat_t(ax)
+                ang = x[da] - dm.qpos0[qa]
+                Rb = Rb @ (torch.eye(3) + torch.sin(ang) * K + (1 - torch.cos(ang)) * (K @ K))
+                Pb = anchor - Rb @ jp
+            else:
+                if jt == FREE:
+                    Pb = x[da:da + 3]
+                    th, q = x[da + 3:da + 6], _T(qpos[qa + 3:qa + 7])
+                    anchor = None
+                else:
+                    th, q = x[da:da + 3], _T(qpos[qa:qa + 4])
+                    anchor = Pb + Rb @ jp
+                q = q / torch.linalg.norm(q)
+                Hh = hat_t(th)
+                local = quat2mat_t(q) @ (torch.eye(3) + Hh + 0.5 * Hh @ Hh)     # exp(hat th) to second order: exact derivatives at th = 0
+                Rb = local if jt == FREE else Rb @ local
+                if anchor is not None:
+                    Pb = anchor - Rb @ jp
+        P.append(Pb)
+        R.append(Rb)
+    return torch.stack(P), torch.stack(R)
+
+
+def coords(dm: DenseModel, qpos):
+    x = np.zeros(dm.nv)
+    for j in range(dm.njnt):
+        jt, qa, da = int(dm.jnt_type[j]), int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
+        if jt in (SLIDE, HINGE):
+            x[da] = qpos[qa]
+        elif jt == FREE:
+            x[da:da + 3] = qpos[qa:qa + 3]
+    return x
+
+
+class Kin:
+    """Frames, exact Jacobians and zero-acceleration accelerations of every body at (qpos, qvel)."""
+
+    def __init__(self, dm: DenseModel, qpos, qvel):
+        self.dm = dm
+        x, v = _T(coords(dm, qpos)), _T(qvel)
+        f = lambda y: fk(dm, qpos, y)
+        (P, R) = f(x)
+        dP, dR = jacfwd(f)(x)                                           # [nb,3,nv], [nb,3,3,nv]
+        first = lambda y: jvp(f, (y,), (v,))[1]                         # d/dt of (P, R) along qvel
+        (vP, vR), (aP, aR) = jvp(first, (x,), (v,))                     # and its derivative along qvel again (qacc = 0)
+        self.P, self.R = P.numpy(), R.numpy()
+        self.JP = dP.numpy()                                            # translational Jacobian of the body origin
+        nb, nv = dm.nbody, dm.nv
+        self.JW = np.zeros((nb, 3, nv))                                 # angular Jacobian (world frame)
+        for b in range(nb):
+            for k in range(nv):
+                self.JW[b, :, k] = vee(dR[b, :, :, k].numpy() @ self.R[b].T)
+        self.vP, self.aP = vP.numpy(), aP.numpy()
+        self.w = np.stack([vee(vR[b].numpy() @ self.R[b].T) for b in range(nb)])
+        self.alpha = np.stack([vee(aR[b].numpy() @ self.R[b].T + vR[b].numpy() @ vR[b].numpy().T) for b in range(nb)])
+        self.vR, self.aR = vR.numpy(), aR.numpy()
+
+    def point_jac(self, b, p):
+        """3 x nv Jacobian of the world position of the material point of body b currently at p."""
+        r = p - self.P[b]
+        return self.JP[b] - np.array([[0, -r[2], r[1]], [r[2], 0, -r[0]], [-r[1], r[0], 0]]) @ self.JW[b]
+
+
+def mass_matrix_and_bias(dm: DenseModel, kin: Kin):
+    nv = dm.nv
+    M = np.diag(dm.dof_armature.copy())
+    c = np.zeros(nv)
+    g = np.zeros(3) if dm.dis("gravity") else dm.gravity
+    for b in range(1, dm.nbody):
+        mb = dm.body_mass[b]
+        ipos = dm.body_ipos[3 * b:3 * b + 3]
+        Ri = kin.R[b] @ quat2mat(dm.body_iquat[4 * b:4 * b + 4])
+        Iw = Ri @ np.diag(dm.body_inertia[3 * b:3 * b + 3]) @ Ri.T
+        com = kin.P[b] + kin.R[b] @ ipos
+        Jc = kin.point_jac(b, com)
+        Jw = kin.JW[b]
+        M += mb * Jc.T @ Jc + Jw.T @ Iw @ Jw
+        a_com = kin.aP[b] + kin.aR[b] @ ipos                            # second time derivative of the com at qacc = 0
+        w = kin.w[b]
+        c += Jc.T @ (mb * (a_com - g)) + Jw.T @ (Iw @ kin.alpha[b] + np.cross(w, Iw @ w))
+    return M, c
+
+
+# ------------------------------------------------------------------------------------------------ smooth forces
+def sub_quat(qa, qb):
+    """3-vector log of qb^-1 * qa (mju_subQuat)."""
+    d = quat_mul(np.array([qb[0], -qb[1], -qb[2], -qb[3]]), qa)
+    s = np.linalg.norm(d[1:])
+    if s < MINVAL:
+        return np.zeros(3)
+    ang = 2 * np.arctan2(s, d[0])
+    if ang > np.pi:
+        ang -= 2 * np.pi
+    return d[1:] / s * ang
+
+
+def passive_force(dm, qpos, qvel):
+    f = np.zeros(dm.nv)
+    if dm.dis("passive"):
+        return f
+    for j in range(dm.njnt):
+        k, jt, qa, da = dm.jnt_stiffness[j], int(dm.jnt_type[j]), int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
+        if k == 0:
+            continue
+        if jt == FREE:
+            f[da:da + 3] -= k * (qpos[qa:qa + 3] - dm.qpos_spring[qa:qa + 3])
+            qa, da = qa + 3, da + 3
+        if jt in (FREE, BALL):
+            q = qpos[qa:qa + 4] / np.linalg.norm(qpos[qa:qa + 4])
+            f[da:da + 3] -= k * sub_quat(q, dm.qpos_spring[qa:qa + 4])
+        else:
+            f[da] -= k * (qpos[qa] - dm.qpos_spring[qa])
+    return f - dm.dof_damping * qvel
+
+
+def actuator_force(dm, qpos, qvel, ctrl):
+    f, frc = np.zeros(dm.nv), np.zeros(dm.nu)
+    if dm.dis("actuation"):
+        return f, frc
+    for i in range(dm.nu):
+        j = int(dm.actuator_trnid[i])
+        qa, da, gear = int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j]), dm.actuator_gear[i]
+        length, vel = gear * qpos[qa], gear * qvel[da]
+        u = ctrl[i]
+        if dm.actuator_ctrllimited[i] and not dm.dis("clampctrl"):
+            u = min(max(u, dm.actuator_ctrlrange[2 * i]), dm.actuator_ctrlrange[2 * i + 1])
+        gp, bp = dm.actuator_gainprm[3 * i:3 * i + 3], dm.actuator_biasprm[3 * i:3 * i + 3]
+        gain = gp[0] + (gp[1] * length + gp[2] * vel if dm.actuator_gaintype[i] == 1 else 0.0)
+        bias = bp[0] + bp[1] * length + bp[2] * vel if dm.actuator_biastype[i] == 1 else 0.0
+        force = gain * u + bias
+        if dm.actuator_forcelimited[i]:
+            force = min(max(force, dm.actuator_forcerange[2 * i]), dm.actuator_forcerange[2 * i + 1])
+        frc[i] = force
+        f[da] += gear * force
+    return f, frc
+
+
+# ------------------------------------------------------------------------------------------------ collision
+def make_frame(n, hint=None):
+    n = n / np.linalg.norm(n)
+    if hint is None or np.linalg.norm(hint) < 0.5:
+        hint = np.array([0.0, 1.0, 0.0]) if -0.5 < n[1] < 0.5 else np.array([0.0, 0.0, 1.0])
+    t = hint - n * (n @ hint)
+    t = t / np.linalg.norm(t)
+    return np.stack([n, t, np.cross(n, t)])
+
+
+def sphere_sphere(p1, r1, p2, r2, margin):
+    d = p2 - p1
+    dist = np.linalg.norm(d)
+    if dist > margin + r1 + r2:
+        return None
+    n = d / dist
+    return dist - r1 - r2, p1 + n * (r1 + (dist - r1 - r2) / 2), n
+
+
+def plane_sphere(p0, n, c, r, margin):
+    h = n @ (c - p0)
+    if h > margin + r:
+        return None
+    dist = h - r
+    return dist, c - n * (r + dist / 2), n
+
+
+def segment_closest(p1, a1, p2, a2):
+    """argmin over s,t in [-1,1] of |p1 + s a1 - p2 - t a2|: the interior stationary point if feasible, else the best of
+    the four edges of the square (each a clamped 1-D problem). Brute force on purpose."""
+    d = p1 - p2
+    A, B, Cc = a1 @ a1, a1 @ a2, a2 @ a2
+    best = None
+
+    def consider(s, t):
+        nonlocal best
+        v = d + s * a1 - t * a2
+        val = v @ v
+        if best is None or val < best[0] - 1e-300:
+            best = (val, s, t)
+    det = A * Cc - B * B
+    assert abs(det) > 1e-12 * A * Cc, "parallel capsules: outside the dense checker's scope"
+    s = (B * (a2 @ d) - Cc * (a1 @ d)) / det
+    t = (A * (a2 @ d) - B * (a1 @ d)) / det
+    if -1 <= s <= 1 and -1 <= t <= 1:
+        consider(s, t)
+    else:
+        for s0 in (-1.0, 1.0):
+            consider(s0, float(np.clip((a2 @ (d + s0 * a1)) / Cc, -1, 1)))
+        for t0 in (-1.0, 1.0):
+            consider(float(np.clip(-(a1 @ (d - t0 * a2)) / A, -1, 1)), t0)
+    return best[1], best[2]
+
+
+def mix_params(dm, g1, g2):
+    """mj_contactParam."""
+    p1, p2 = dm.geom_priority[g1], dm.geom_priority[g2]
+    margin = max(dm.geom_margin[g1], dm.geom_margin[g2])
+    gap = max(dm.geom_gap[g1], dm.geom_gap[g2])
+    if p1 != p2:
+        g = g1 if p1 > p2 else g2
+        fr, sr, si, dim = dm.geom_friction[3 * g:3 * g + 3], dm.geom_solref[2 * g:2 * g + 2], dm.geom_solimp[5 * g:5 * g + 5], int(dm.geom_condim[g])
+    else:
+        dim = int(max(dm.geom_condim[g1], dm.geom_condim[g2]))
+        fr = np.maximum(dm.geom_friction[3 * g1:3 * g1 + 3], dm.geom_friction[3 * g2:3 * g2 + 3])
+        s1, s2 = dm.geom_solmix[g1], dm.geom_solmix[g2]
+        if s1 >= MINVAL and s2 >= MINVAL:
+            mix = s1 / (s1 + s2)
+        elif s1 < MINVAL and s2 < MINVAL:
+            mix = 0.5
+        else:
+            mix = 0.0 if s1 < MINVAL else 1.0
+        r1, r2 = dm.geom_solref[2 * g1:2 * g1 + 2], dm.geom_solref[2 * g2:2 * g2 + 2]
+        sr = mix * r1 + (1 - mix) * r2 if (r1[0] > 0 and r2[0] > 0) else np.minimum(r1, r2)
+        si = mix * dm.geom_solimp[5 * g1:5 * g1 + 5] + (1 - mix) * dm.geom_solimp[5 * g2:5 * g2 + 5]
+    fr5 = np.array([fr[0], fr[0], fr[1], fr[2], fr[2]])
+    return dict(dim=dim, friction=fr5, solref=np.asarray(sr, float), solimp=np.asarray(si, float), margin=margin, gap=gap)
+
+
+def collide(dm: DenseModel, kin: Kin):
+    """List of contacts dict(dist, pos, frame[3,3], pair) over the model's candidate pair list."""
+    out = []
+    if dm.dis("contact") or dm.dis("constraint"):
+        return out
+    gpos = [kin.P[dm.geom_bodyid[g]] + kin.R[dm.geom_bodyid[g]] @ dm.geom_pos[3 * g:3 * g + 3] for g in range(dm.ngeom)]
+    gmat = [kin.R[dm.geom_bodyid[g]] @ quat2mat(dm.geom_quat[4 * g:4 * g + 4]) for g in range(dm.ngeom)]
+    for p in range(dm.npair):
+        g1, g2 = int(dm.pair_geom1[p]), int(dm.pair_geom2[p])
+        t1, t2 = int(dm.geom_type[g1]), int(dm.geom_type[g2])
+        assert t1 <= t2
+        prm = mix_params(dm, g1, g2)
+        margin = prm["margin"]
+        s1, s2 = dm.geom_size[3 * g1:3 * g1 + 3], dm.geom_size[3 * g2:3 * g2 + 3]
+        found = []
+        if t1 == PLANE:
+            n = gmat[g1][:, 2]
+            if t2 == SPHERE:
+                r = plane_sphere(gpos[g1], n, gpos[g2], s2[0], margin)
+                if r: found.append((r, None))
+            elif t2 == CAPSULE:
+                ax = gmat[g2][:, 2]
+                for sgn in (1.0, -1.0):
+                    r = plane_sphere(gpos[g1], n, gpos[g2] + sgn * ax * s2[1], s2[0], margin)
+                    if r: found.append((r, ax))
+            elif t2 == BOX:
+                cnt = 0
+                for i in range(8):
+                    corner = gmat[g2] @ (np.array([1 if i & 1 else -1, 1 if i & 2 else -1, 1 if i & 4 else -1]) * s2)
+                    ld, dist0 = n @ corner, n @ (gpos[g2] - gpos[g1])
+                    if dist0 + ld > margin or ld > 0 or cnt >= 4:
+                        continue
+                    dist = dist0 + ld
+                    found.append(((dist, corner + gpos[g2] - n * dist / 2, n), None))
+                    cnt += 1
+            else:
+                raise NotImplementedError((t1, t2))
+        elif t1 == SPHERE and t2 == SPHERE:
+            r = sphere_sphere(gpos[g1], s1[0], gpos[g2], s2[0], margin)
+            if r: found.append((r, None))
+        elif t1 == SPHERE and t2 == CAPSULE:
+            ax = gmat[g2][:, 2]
+            x = float(np.clip(ax @ (gpos[g1] - gpos[g2]), -s2[1], s2[1]))
+            r = sphere_sphere(gpos[g1], s1[0], gpos[g2] + ax * x, s2[0], margin)
+            if r: found.append((r, None))
+        elif t1 == CAPSULE and t2 == CAPSULE:
+            a1, a2 = gmat[g1][:, 2] * s1[1], gmat[g2][:, 2] * s2[1]
+            s, t = segment_closest(gpos[g1], a1, gpos[g2], a2)
+            r = sphere_sphere(gpos[g1] + s * a1, s1[0], gpos[g2] + t * a2, s2[0], margin)
+            if r: found.append((r, None))
+        else:
+            raise NotImplementedError((t1, t2))
+        for (dist, pos, n), hint in found:
+            out.append(dict(dist=dist, pos=pos, frame=make_frame(n, hint), pair=p, g1=g1, g2=g2, prm=prm))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ constraints
+def impedance(solimp, x):
+    d0, dmax, width, mid, power = solimp
+    if d0 == dmax or width <= MINVAL:
+        d = 0.5 * (d0 + dmax)
+    else:
+        r = abs(x) / width
+        if r >= 1:
+            d = dmax
+        elif r <= 0:
+            d = d0
+        else:
+            if power == 1:
+                y = r
+            elif r <= mid:
+                y = r ** power / mid ** (power - 1)
+            else:
+                y = 1 - (1 - r) ** power / (1 - mid) ** (power - 1)
+            d = d0 + y * (dmax - d0)
+    return min(max(d, MINIMP), MAXIMP)
+
+
+def row_params(dm, solref, solimp, pos, margin, diag_approx, vel):
+    d = impedance(solimp, pos - margin)
+    dmax = solimp[1]
+    if solref[0] > 0:
+        tc, dr = solref
+        if not dm.dis("refsafe"):
+            tc = max(tc, 2 * dm.timestep)
+        K = 1 / max(MINVAL, dmax * dmax * tc * tc * dr * dr)
+        Bd = 2 / max(MINVAL, dmax * tc)
+    else:
+        K, Bd = -solref[0] / max(MINVAL, dmax * dmax), -solref[1] / max(MINVAL, dmax)
+    aref = -Bd * vel - K * d * (pos - margin)
+    R = max(MINVAL, (1 - d) / d * diag_approx)
+    return aref, R
+
+
+def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts):
+    J, D, aref = [], [], []
+    if dm.dis("constraint"):
+        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0)
+    if not dm.dis("limit"):
+        for j in range(dm.njnt):
+            if not dm.jnt_limited[j] or int(dm.jnt_type[j]) not in (SLIDE, HINGE):
+                continue
+            q, da = qpos[int(dm.jnt_qposadr[j])], int(dm.jnt_dofadr[j])
+            for sign, dist in ((1.0, q - dm.jnt_range[2 * j]), (-1.0, dm.jnt_range[2 * j + 1] - q)):
+                if dist < dm.jnt_margin[j]:
+                    row = np.zeros(dm.nv)
+                    row[da] = sign
+                    a, R = row_params(dm, dm.jnt_solref[2 * j:2 * j + 2], dm.jnt_solimp[5 * j:5 * j + 5], dist, dm.jnt_margin[j],
+                                      dm.dof_invweight0[da], row @ qvel)
+                    J.append(row); D.append(1 / R); aref.append(a)
+    for c in contacts:
+        prm = c["prm"]
+        incl = prm["margin"] - prm["gap"]
+        if c["dist"] >= incl:
+            continue
+        b1, b2 = int(dm.geom_bodyid[c["g1"]]), int(dm.geom_bodyid[c["g2"]])
+        Jd = c["frame"] @ (kin.point_jac(b2, c["pos"]) - kin.point_jac(b1, c["pos"]))      # rows: normal, tangent 1, tangent 2
+        tran = dm.body_invweight0[2 * b1] + dm.body_invweight0[2 * b2]
+        if prm["dim"] == 1:
+            a, R = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, Jd[0] @ qvel)
+            J.append(Jd[0]); D.append(1 / R); aref.append(a)
+        else:
+            assert prm["dim"] == 3, "condim 4/6 are outside the product's scope"
+            rows = [Jd[0] + s * prm["friction"][k] * Jd[1 + k] for k in range(2) for s in (1.0, -1.0)]
+            _, R0 = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran + prm["friction"][0] ** 2 * tran, rows[0] @ qvel)
+            mu = prm["friction"][0] * np.sqrt(1 / dm.impratio)
+            Rpy = 2 * mu * mu * R0
+            for r in rows:
+                a, _ = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, r @ qvel)
+                J.append(r); D.append(1 / Rpy); aref.append(a)
+    if not J:
+        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0)
+    return np.array(J), np.array(D), np.array(aref)
+
+
+def solve_qacc(M, qfrc_smooth, J, D, aref):
+    """argmin_a 1/2 (a-a0)' M (a-a0) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2 by damped Newton with backtracking."""
+    a0 = np.linalg.solve(M, qfrc_smooth)
+    if J.shape[0] == 0:
+        return a0, np.zeros(0)
+    cost = lambda a: 0.5 * (a - a0) @ M @ (a - a0) + 0.5 * np.sum(D * np.minimum(0.0, J @ a - aref) ** 2)
+    a = a0.copy()
+    for _ in range(500):
+        jar = J @ a - aref
+        act = jar < 0
+        g = M @ (a - a0) + J.T @ (D * jar * act)
+        if np.linalg.norm(g) <= 1e-13 * max(1.0, np.linalg.norm(M @ a0)):
+            break
+        H = M + (J[act].T * D[act]) @ J[act]
+        step = -np.linalg.solve(H, g)
+        c0, t = cost(a), 1.0
+        while cost(a + t * step) > c0 + 1e-4 * t * (g @ step) and t > 1e-12:
+            t *= 0.5
+        if t <= 1e-12:
+            break
+        a = a + t * step
+    jar = J @ a - aref
+    return a, np.where(jar < 0, -D * jar, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------ whole step
+def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None):
+    qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
+    kin = Kin(dm, qpos, qvel)
+    M, c = mass_matrix_and_bias(dm, kin)
+    fa, frc = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float))
+    f = passive_force(dm, qpos, qvel) - c + fa
+    if qfrc_applied is not None:
+        f = f + qfrc_applied
+    if xfrc_applied is not None:
+        for b in range(1, dm.nbody):
+            w = xfrc_applied[6 * b:6 * b + 6]
+            if np.any(w != 0):
+                com = kin.P[b] + kin.R[b] @ dm.body_ipos[3 * b:3 * b + 3]
+                f = f + kin.point_jac(b, com).T @ w[:3] + kin.JW[b].T @ w[3:]
+    cons = collide(dm, kin)
+    J, D, aref = constraints(dm, kin, qpos, qvel, cons)
+    qacc, force = solve_qacc(M, f, J, D, aref)
+    return dict(qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
+                nefc=J.shape[0], efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]))
+
+
+def integrate_pos(dm, qpos, vel, h):
+    q = np.array(qpos, float)
+    for j in range(dm.njnt):
+        jt, qa, da = int(dm.jnt_type[j]), int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
+        if jt in (SLIDE, HINGE):
+            q[qa] += h * vel[da]
+            continue
+        if jt == FREE:
+            q[qa:qa + 3] += h * vel[da:da + 3]
+            qa, da = qa + 3, da + 3
+        w = vel[da:da + 3]
+        quat = q[qa:qa + 4] / np.linalg.norm(q[qa:qa + 4])
+        ang = h * np.linalg.norm(w)
+        if ang > 0:
+            ax = w / np.linalg.norm(w)
+            quat = quat_mul(quat, np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * ax]))
+        q[qa:qa + 4] = quat
+    return q
+
+
+def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None):
+    """One mj_step. Returns dict(qpos, qvel, qacc, ncon, nefc, ...) - qacc is the forward's (pre-integration) acceleration."""
+    h = dm.timestep
+    qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
+    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied)
+    if dm.integrator == 0:
+        qacc = f0["qacc"]
+        if np.any(dm.dof_damping > 0) and not dm.dis("eulerdamp"):
+            qacc = np.linalg.solve(f0["M"] + h * np.diag(dm.dof_damping), f0["qfrc_smooth"] + f0["qfrc_constraint"])
+        v1 = qvel + h * qacc
+        out = dict(f0, qpos=integrate_pos(dm, qpos, v1, h), qvel=v1)
+    else:                                                               # RK4, classic tableau
+        A, Bw = [0.5, 0.5, 1.0], [1 / 6, 1 / 3, 1 / 3, 1 / 6]
+        F = [(qvel, f0["qacc"])]
+        last = f0
+        for i in range(3):
+            qi = integrate_pos(dm, qpos, F[i][0], A[i] * h)
+            vi = qvel + A[i] * h * F[i][1]
+            last = forward(dm, qi, vi, ctrl, qfrc_applied, xfrc_applied)
+            F.append((vi, last["qacc"]))
+        sv = sum(w * Fi[0] for w, Fi in zip(Bw, F))
+        sa = sum(w * Fi[1] for w, Fi in zip(Bw, F))
+        out = dict(last, qpos=integrate_pos(dm, qpos, sv, h), qvel=qvel + h * sa)   # derived fields: those of the 4th stage, as in mjData
+    return out

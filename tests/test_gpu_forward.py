@@ -76,7 +76,7 @@ def test_specialised_kernel_refuses_stale_derived_fields():
     for b in (spec, gen):
         b.set("qpos", qpos); b.set("qvel", qvel); b.ctrl_philox(True, SEED); b.step(3); b.sync()
     for f in ("qpos", "qvel", "qacc", "sensordata", "time", "ctrl"):
-        assert np.array_equal(spec.get(f), gen.get(f)), f   # same arithmetic in the same order
+        assert rel_err(spec.get(f), gen.get(f)) <= 1e-11, f   # same algorithm; nvcc contracts FMAs differently in the two kernels
     with pytest.raises(ox.Error, match="not maintained by the model-specialised"):
         spec.get("xpos")
     with pytest.raises(ox.Error, match="not maintained by the model-specialised"):
@@ -84,7 +84,7 @@ def test_specialised_kernel_refuses_stale_derived_fields():
     assert gen.get("xpos").shape == (nenv, 3 * m.nbody)       # generic kernels keep everything current
     spec.forward(); gen.forward(); spec.sync(); gen.sync()
     for f in ("xpos", "xmat", "subtree_com", "cvel", "qfrc_bias", "qM"):
-        assert np.array_equal(spec.get(f), gen.get(f)), f
+        assert rel_err(spec.get(f), gen.get(f)) <= 1e-10, f
     # an Environment task on a specialised batch may only observe / reward on maintained fields
     from oxide_control_b200.environment import BatchedEnvironment, TaskSpec
     with pytest.raises(ox.Error, match="not maintained by the model-specialised"):

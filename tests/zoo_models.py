@@ -84,4 +84,42 @@ ZOO_B = """
 </mujoco>
 """
 
+# a user-supplied model that is NOT compiled into the library: exercises the run-time specialisation (csrc/ox_jit.cpp)
+HOPPER = """
+<mujoco model="hopper_user">
+  <compiler angle="radian"/>
+  <option timestep="0.004"/>
+  <default>
+    <joint armature="0.02" damping="1" limited="true"/>
+    <geom friction="0.9 0.1 0.1" solref="0.02 1" solimp="0.9 0.95 0.001"/>
+    <motor ctrllimited="true" ctrlrange="-1 1"/>
+  </default>
+  <worldbody>
+    <geom name="floor" type="plane" size="20 20 0.1"/>
+    <body name="torso" pos="0 0 1.25">
+      <joint name="rootx" type="slide" axis="1 0 0" armature="0" damping="0" limited="false"/>
+      <joint name="rootz" type="slide" axis="0 0 1" armature="0" damping="0" limited="false"/>
+      <joint name="rooty" type="hinge" axis="0 1 0" armature="0" damping="0" limited="false"/>
+      <geom name="torso" type="capsule" fromto="0 0 -0.2 0 0 0.2" size="0.05"/>
+      <body name="thigh" pos="0 0 -0.2">
+        <joint name="thigh" type="hinge" axis="0 -1 0" range="-2.6 0"/>
+        <geom name="thigh" type="capsule" fromto="0 0 0 0 0 -0.45" size="0.05"/>
+        <body name="leg" pos="0 0 -0.45">
+          <joint name="leg" type="hinge" axis="0 -1 0" range="-2.6 0"/>
+          <geom name="leg" type="capsule" fromto="0 0 0 0 0 -0.5" size="0.04"/>
+          <body name="foot" pos="0 0 -0.5">
+            <joint name="foot" type="hinge" axis="0 -1 0" range="-0.78 0.78"/>
+            <geom name="foot" type="capsule" fromto="-0.13 0 -0.06 0.26 0 -0.06" size="0.06" friction="2 0.1 0.1"/>
+          </body>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor joint="thigh" gear="200"/> <motor joint="leg" gear="200"/> <motor joint="foot" gear="100"/>
+  </actuator>
+  <sensor><subtreecom body="torso"/><jointvel joint="foot"/></sensor>
+</mujoco>
+"""
+
 ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B}
