@@ -61,7 +61,9 @@ enum { OX_GEOM_PLANE = 0, OX_GEOM_HFIELD = 1, OX_GEOM_SPHERE = 2, OX_GEOM_CAPSUL
 enum { OX_OBJ_UNKNOWN = 0, OX_OBJ_BODY = 1, OX_OBJ_XBODY = 2, OX_OBJ_JOINT = 3, OX_OBJ_DOF = 4,
        OX_OBJ_GEOM = 5, OX_OBJ_SITE = 6, OX_OBJ_EQUALITY = 17, OX_OBJ_ACTUATOR = 19,
        OX_OBJ_SENSOR = 20, OX_OBJ_PLUGIN = 25 };
-enum { OX_INT_EULER = 0, OX_INT_RK4 = 1 };
+enum { OX_INT_EULER = 0, OX_INT_RK4 = 1, OX_INT_IMPLICIT = 2 /* refused by the compiler */, OX_INT_IMPLICITFAST = 3 };
+/* mjtDyn subset: activation dynamics of stateful actuators (act, src/physics.rs:96-102) */
+enum { OX_DYN_NONE = 0, OX_DYN_INTEGRATOR = 1, OX_DYN_FILTER = 2, OX_DYN_FILTEREXACT = 3 };
 enum { OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
 enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
@@ -96,6 +98,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1) X(pair_conadr, npair, 1)   \
   X(actuator_trnid, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
   X(actuator_ctrllimited, nu, 1) X(actuator_forcelimited, nu, 1)                                    \
+  X(actuator_dyntype, nu, 1) X(actuator_actadr, nu, 1) X(actuator_actlimited, nu, 1)                \
   X(sensor_type, nsensor, 1) X(sensor_objtype, nsensor, 1) X(sensor_objid, nsensor, 1)             \
   X(sensor_adr, nsensor, 1) X(sensor_dim, nsensor, 1)
 
@@ -114,7 +117,8 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(pair_friction, npair, 5) X(pair_solref, npair, 2) X(pair_solimp, npair, 5)                     \
   X(pair_margin, npair, 1) X(pair_gap, npair, 1)                                                    \
   X(actuator_gear, nu, 1) X(actuator_gainprm, nu, 3) X(actuator_biasprm, nu, 3)                    \
-  X(actuator_ctrlrange, nu, 2) X(actuator_forcerange, nu, 2)
+  X(actuator_ctrlrange, nu, 2) X(actuator_forcerange, nu, 2)                                        \
+  X(actuator_dynprm, nu, 3) X(actuator_actrange, nu, 2)
 
 typedef struct ox_model_tables {
   /* sizes */
@@ -215,6 +219,7 @@ enum {
   OX_F_QFRC_SMOOTH, OX_F_QACC_SMOOTH, OX_F_QFRC_CONSTRAINT,
   OX_F_CON_DIST, OX_F_CON_POS, OX_F_CON_FRAME,
   OX_F_EFC_J, OX_F_EFC_POS, OX_F_EFC_MARGIN, OX_F_EFC_D, OX_F_EFC_AREF, OX_F_EFC_FORCE,
+  OX_F_ACT_DOT,
   OX_F_COUNT_REAL,
   /* int32 fields */
   OX_F_NCON = 100, OX_F_NEFC, OX_F_SOLVER_NITER, OX_F_DIVERGED, OX_F_CON_PAIR
@@ -232,6 +237,16 @@ OX_API ox_status ox_batch_get_many(ox_batch* b, int32_t nfields, const int32_t* 
 OX_API ox_status ox_batch_get1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, double* out);
 OX_API ox_status ox_batch_set1(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, const double* in);
 OX_API ox_status ox_batch_get1_int(ox_batch* b, int32_t field, int32_t env, int32_t offset, int32_t count, int32_t* out);
+
+/* Checkpoint / resume (the reference keeps no such API - its state is whatever the user copies out through the
+ * getters of src/physics.rs:82-145, which is exactly this tuple): one record per env, env-major,
+ *   [ time, qpos(nq), qvel(nv), act(na), ctrl(nu), qfrc_applied(nv), xfrc_applied(6 nbody), qacc_warmstart(nv) ]
+ * = ox_batch_state_size() elements of `dtype`. Restoring a record and the Philox step counter reproduces the trajectory
+ * bit for bit in the same precision (qacc_warmstart seeds the solver). */
+OX_API int32_t ox_batch_state_size(const ox_batch* b);
+OX_API ox_status ox_batch_get_state(ox_batch* b, void* buf, int32_t dtype, int32_t mem);
+OX_API ox_status ox_batch_set_state(ox_batch* b, const void* buf, int32_t dtype, int32_t mem);
+OX_API int64_t ox_batch_get_step_counter(const ox_batch* b);
 
 /* run statistics accumulated on device since the last call (mean ncon, nefc, solver iterations,
  * number of divergence auto-resets); out[4]. */

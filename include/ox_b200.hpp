@@ -151,8 +151,18 @@ class Physics {
   void set_time(double t) { batch_.set1(OX_F_TIME, 0, 0, &t, 1); }
   double ctrl(obj::Actuator id) { return batch_.get1(OX_F_CTRL, 0, id.index, 1)[0]; }                            // :89-94
   void set_ctrl(obj::Actuator id, double v) { batch_.set1(OX_F_CTRL, 0, id.index, &v, 1); }
-  std::optional<double> act(obj::Actuator) { return std::nullopt; }                                              // :96-102 (stateless)
-  std::optional<std::monostate> set_act(obj::Actuator, double) { return std::nullopt; }
+  // :96-102: Some(activation) for stateful actuators (dyntype integrator / filter / filterexact), None for stateless ones
+  int actadr(obj::Actuator id) const { return model_.tables().na > 0 ? model_.tables().actuator_actadr[id.index] : -1; }
+  std::optional<double> act(obj::Actuator id) {
+    const int adr = actadr(id);
+    if (adr < 0) return std::nullopt;
+    return batch_.get1(OX_F_ACT, 0, adr, 1)[0];
+  }
+  std::optional<std::monostate> set_act(obj::Actuator id, double value) {
+    const int adr = actadr(id);
+    if (adr < 0) return std::nullopt;
+    batch_.set1(OX_F_ACT, 0, adr, &value, 1); return std::monostate{};
+  }
   template <class J> std::array<double, J::nq> qpos(obj::Joint id) {                                             // :104-109
     check_joint<J>(id);
     auto v = batch_.get1(OX_F_QPOS, 0, model_.tables().jnt_qposadr[id.index], J::nq);

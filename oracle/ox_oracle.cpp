@@ -35,7 +35,7 @@ typedef ox_model_tables Model;
 
 struct oxo_data {
   // state (mjData fields of the same names)
-  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart;
+  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot;
   double time = 0;
   // position stage
   std::vector<double> xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, geom_xpos, geom_xmat, site_xpos, site_xmat;
@@ -714,6 +714,13 @@ void actuation(const Model* m, Data* d) {
     double ctrl = d->ctrl[i];
     if (m->actuator_ctrllimited[i] && !disabled(m, OX_DSBL_CLAMPCTRL))
       ctrl = clip(ctrl, m->actuator_ctrlrange[2 * i], m->actuator_ctrlrange[2 * i + 1]);
+    // mj_fwdActuation, stateful actuators: act_dot from the control, force from the activation
+    //   integrator: act_dot = ctrl;  filter / filterexact: act_dot = (ctrl - act) / max(mjMINVAL, dynprm[0])
+    if (m->actuator_dyntype[i] != OX_DYN_NONE) {
+      int aa = m->actuator_actadr[i];
+      d->act_dot[aa] = m->actuator_dyntype[i] == OX_DYN_INTEGRATOR ? ctrl : (ctrl - d->act[aa]) / std::max(OX_MINVAL, m->actuator_dynprm[3 * i]);
+      ctrl = d->act[aa];
+    }
     const double* gp = m->actuator_gainprm + 3 * i;
     const double* bp = m->actuator_biasprm + 3 * i;
     double gain = gp[0];
@@ -1110,7 +1117,23 @@ void integratePos(const Model* m, double* qpos, const double* qvel, double dt) {
     }
   }
 }
-void advance(const Model* m, Data* d, const double* qacc, const double* qvel_override) {
+// mj_nextActivation: act + h act_dot, or the exact first-order-filter update act + act_dot tau (1 - exp(-h/tau)); then actrange
+double nextActivation(const Model* m, int i, double act, double act_dot) {
+  if (m->actuator_dyntype[i] == OX_DYN_FILTEREXACT) {
+    double tau = std::max(OX_MINVAL, m->actuator_dynprm[3 * i]);
+    act += act_dot * tau * (1 - std::exp(-m->timestep / tau));
+  } else {
+    act += act_dot * m->timestep;
+  }
+  if (m->actuator_actlimited[i]) act = clip(act, m->actuator_actrange[2 * i], m->actuator_actrange[2 * i + 1]);
+  return act;
+}
+void advance(const Model* m, Data* d, const double* qacc, const double* qvel_override, const double* act_dot) {
+  for (int i = 0; i < m->nu; i++)
+    if (m->actuator_dyntype[i] != OX_DYN_NONE) {
+      int aa = m->actuator_actadr[i];
+      d->act[aa] = nextActivation(m, i, d->act[aa], act_dot[aa]);
+    }
   for (int i = 0; i < m->nv; i++) d->qvel[i] += m->timestep * qacc[i];
   integratePos(m, d->qpos.data(), qvel_override ? qvel_override : d->qvel.data(), m->timestep);
   d->time += m->timestep;
@@ -1118,18 +1141,37 @@ void advance(const Model* m, Data* d, const double* qacc, const double* qvel_ove
 void euler(const Model* m, Data* d) {
   int nv = m->nv;
   bool damping = false;
+  const bool fast = m->integrator == OX_INT_IMPLICITFAST;
   if (!disabled(m, OX_DSBL_EULERDAMP))
     for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) damping = true;
-  if (!damping) { advance(m, d, d->qacc.data(), nullptr); return; }
+  if (!damping && !fast) { advance(m, d, d->qacc.data(), nullptr, d->act_dot.data()); return; }
   // implicit-in-velocity joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint.
   // MuJoCo factors into d->qLD, overwriting the factor of M; so do we.
   d->qLD = d->qM;
   for (int i = 0; i < nv; i++) d->qLD[m->dof_Madr[i]] += m->timestep * m->dof_damping[i];
+  if (fast && !disabled(m, OX_DSBL_ACTUATION)) {
+    // mj_implicit, implicitfast flavour: M - h d(qfrc_smooth)/d(qvel) with the RNE terms dropped. In this
+    // subset the derivative is diagonal: -damping (above) + moment' (d force / d velocity) moment for affine gain / bias
+    // terms (mjd_actuator_vel), skipped while the force is clamped at its forcerange.
+    for (int i = 0; i < m->nu; i++) {
+      double dfdv = 0;
+      double in = d->ctrl[i];
+      if (m->actuator_ctrllimited[i] && !disabled(m, OX_DSBL_CLAMPCTRL)) in = clip(in, m->actuator_ctrlrange[2 * i], m->actuator_ctrlrange[2 * i + 1]);
+      if (m->actuator_dyntype[i] != OX_DYN_NONE) in = d->act[m->actuator_actadr[i]];
+      if (m->actuator_gaintype[i] == OX_GAIN_AFFINE) dfdv += m->actuator_gainprm[3 * i + 2] * in;
+      if (m->actuator_biastype[i] == OX_BIAS_AFFINE) dfdv += m->actuator_biasprm[3 * i + 2];
+      if (dfdv == 0 && m->actuator_gaintype[i] != OX_GAIN_AFFINE && m->actuator_biastype[i] != OX_BIAS_AFFINE) continue;
+      if (m->actuator_forcelimited[i] &&
+          (d->actuator_force[i] <= m->actuator_forcerange[2 * i] || d->actuator_force[i] >= m->actuator_forcerange[2 * i + 1])) continue;
+      int da = m->jnt_dofadr[m->actuator_trnid[i]];
+      d->qLD[m->dof_Madr[da]] -= m->timestep * m->actuator_gear[i] * m->actuator_gear[i] * dfdv;
+    }
+  }
   factorLD(m, d->qLD.data(), d->qLDiagInv.data());
   std::vector<double> qacc(nv);
   for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
   solveLD(m, d->qLD.data(), d->qLDiagInv.data(), qacc.data());
-  advance(m, d, qacc.data(), nullptr);
+  advance(m, d, qacc.data(), nullptr, d->act_dot.data());
 }
 void rk4(const Model* m, Data* d) {
   static const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1}, Bw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
@@ -1137,32 +1179,39 @@ void rk4(const Model* m, Data* d) {
   double h = m->timestep, time = d->time;
   double C[3], T[3];
   for (int i = 0; i < 3; i++) { C[i] = A[3 * i] + A[3 * i + 1] + A[3 * i + 2]; T[i] = time + C[i] * h; }
-  std::vector<double> X0q = d->qpos, X0v = d->qvel;
-  std::vector<std::vector<double>> Fv(4), Fa(4);
-  Fv[0] = d->qvel; Fa[0] = d->qacc;
-  std::vector<double> dXv(nv), dXa(nv);
+  std::vector<double> X0q = d->qpos, X0v = d->qvel, X0act = d->act;
+  std::vector<std::vector<double>> Fv(4), Fa(4), Fact(4);
+  Fv[0] = d->qvel; Fa[0] = d->qacc; Fact[0] = d->act_dot;
+  const int na = (int)d->act.size();
+  std::vector<double> dXv(nv), dXa(nv), dXact(na);
   for (int i = 1; i < 4; i++) {
     std::fill(dXv.begin(), dXv.end(), 0.0);
     std::fill(dXa.begin(), dXa.end(), 0.0);
+    std::fill(dXact.begin(), dXact.end(), 0.0);
     for (int j = 0; j < i; j++) {
       double a = A[(i - 1) * 3 + j];
       for (int k = 0; k < nv; k++) { dXv[k] += a * Fv[j][k]; dXa[k] += a * Fa[j][k]; }
+      for (int k = 0; k < na; k++) dXact[k] += a * Fact[j][k];
     }
+    for (int k = 0; k < na; k++) d->act[k] = X0act[k] + h * dXact[k];
     d->qpos = X0q;
     integratePos(m, d->qpos.data(), dXv.data(), h);
     for (int k = 0; k < nv; k++) d->qvel[k] = X0v[k] + h * dXa[k];
     d->time = T[i - 1];
     forwardSkip(m, d, true);
-    Fv[i] = d->qvel; Fa[i] = d->qacc;
+    Fv[i] = d->qvel; Fa[i] = d->qacc; Fact[i] = d->act_dot;
   }
   std::fill(dXv.begin(), dXv.end(), 0.0);
   std::fill(dXa.begin(), dXa.end(), 0.0);
-  for (int j = 0; j < 4; j++)
+  std::fill(dXact.begin(), dXact.end(), 0.0);
+  for (int j = 0; j < 4; j++) {
     for (int k = 0; k < nv; k++) { dXv[k] += Bw[j] * Fv[j][k]; dXa[k] += Bw[j] * Fa[j][k]; }
+    for (int k = 0; k < na; k++) dXact[k] += Bw[j] * Fact[j][k];
+  }
   d->time = time;
-  d->qpos = X0q; d->qvel = X0v;
+  d->qpos = X0q; d->qvel = X0v; d->act = X0act;
   (void)nq;
-  advance(m, d, dXa.data(), dXv.data());
+  advance(m, d, dXa.data(), dXv.data(), dXact.data());
 }
 
 bool isBad(double x) { return std::isnan(x) || x > OX_MAXVAL || x < -OX_MAXVAL; }
@@ -1170,7 +1219,7 @@ bool isBad(double x) { return std::isnan(x) || x > OX_MAXVAL || x < -OX_MAXVAL; 
 void resetData(const Model* m, Data* d) {
   std::memcpy(d->qpos.data(), m->qpos0, m->nq * sizeof(double));
   auto z = [](std::vector<double>& v) { std::fill(v.begin(), v.end(), 0.0); };
-  z(d->qvel); z(d->ctrl); z(d->qfrc_applied); z(d->xfrc_applied); z(d->qacc_warmstart); z(d->qacc);
+  z(d->qvel); z(d->ctrl); z(d->qfrc_applied); z(d->xfrc_applied); z(d->qacc_warmstart); z(d->qacc); z(d->act); z(d->act_dot);
   z(d->xpos); z(d->xquat); z(d->xmat); z(d->xipos); z(d->ximat); z(d->xanchor); z(d->xaxis); z(d->geom_xpos); z(d->geom_xmat);
   z(d->site_xpos); z(d->site_xmat); z(d->subtree_com); z(d->cinert); z(d->cdof); z(d->qM); z(d->qLD); z(d->qLDiagInv);
   z(d->cvel); z(d->cdof_dot); z(d->qfrc_bias); z(d->qfrc_passive); z(d->actuator_force); z(d->qfrc_actuator); z(d->qfrc_smooth);
@@ -1182,6 +1231,7 @@ void step(const Model* m, Data* d) {
   bool bad = false;
   for (double x : d->qpos) bad |= isBad(x);
   for (double x : d->qvel) bad |= isBad(x);
+  for (double x : d->act) bad |= isBad(x);
   if (bad) { resetData(m, d); d->diverged++; }
   forwardSkip(m, d, false);
   bad = false;
@@ -1223,7 +1273,7 @@ OXO_API oxo_data* oxo_make_data(const Model* m) {
   Data* d = new Data();
   int nb = m->nbody, nv = m->nv;
   d->qpos.resize(m->nq); d->qvel.resize(nv); d->ctrl.resize(m->nu); d->qfrc_applied.resize(nv); d->xfrc_applied.resize(6 * nb);
-  d->qacc_warmstart.resize(nv);
+  d->qacc_warmstart.resize(nv); d->act.resize(m->na); d->act_dot.resize(m->na);
   d->xpos.resize(3 * nb); d->xquat.resize(4 * nb); d->xmat.resize(9 * nb); d->xipos.resize(3 * nb); d->ximat.resize(9 * nb);
   d->xanchor.resize(3 * m->njnt); d->xaxis.resize(3 * m->njnt); d->geom_xpos.resize(3 * m->ngeom); d->geom_xmat.resize(9 * m->ngeom);
   d->site_xpos.resize(3 * m->nsite); d->site_xmat.resize(9 * m->nsite);
@@ -1271,7 +1321,7 @@ OXO_API void oxo_stage(const Model* m, oxo_data* d, const char* name) {
 OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
   std::string s(name);
 #define F(f) if (s == #f) { *count = (int32_t)d->f.size(); return d->f.data(); }
-  F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
+  F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
   F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
   F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
   F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)

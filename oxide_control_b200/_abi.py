@@ -23,14 +23,14 @@ F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_ENV_MAJOR, LAYOUT_ELEM_MAJOR = 0, 1
 MODE_FUSED, MODE_STAGED = 0, 1
-INT_EULER, INT_RK4 = 0, 1
+INT_EULER, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST = 0, 1, 2, 3
 
 _REAL_FIELDS = [
     "qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "qacc_warmstart", "time", "act",
     "qacc", "sensordata", "xpos", "xquat", "xmat", "xipos", "ximat", "xanchor", "xaxis", "geom_xpos", "geom_xmat",
     "site_xpos", "site_xmat", "subtree_com", "cinert", "cdof", "qM", "qLD", "qLDiagInv", "cvel", "cdof_dot",
     "qfrc_bias", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint",
-    "con_dist", "con_pos", "con_frame", "efc_J", "efc_pos", "efc_margin", "efc_D", "efc_aref", "efc_force",
+    "con_dist", "con_pos", "con_frame", "efc_J", "efc_pos", "efc_margin", "efc_D", "efc_aref", "efc_force", "act_dot",
 ]
 FIELD = {name: i for i, name in enumerate(_REAL_FIELDS)}
 FIELD.update({"ncon": 100, "nefc": 101, "solver_niter": 102, "diverged": 103, "con_pair": 104})
@@ -96,6 +96,10 @@ SYMBOLS = {
     "ox_batch_ctrl_philox": (C.c_int32, [_P, C.c_int32, C.c_uint64]),
     "ox_batch_set_step_counter": (C.c_int32, [_P, C.c_int64]),
     "ox_batch_field_size": (C.c_int32, [_P, C.c_int32]),
+    "ox_batch_state_size": (C.c_int32, [_P]),
+    "ox_batch_get_state": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
+    "ox_batch_set_state": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
+    "ox_batch_get_step_counter": (C.c_int64, [_P]),
     "ox_batch_get": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
     "ox_batch_set": (C.c_int32, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32]),
     "ox_batch_get_many": (C.c_int32, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32]),

@@ -15,7 +15,7 @@ struct FieldInfo {
 
 template <typename T>
 size_t layout_arena(const ox_model_tables& t, int stride, unsigned char* base, DevBatch<T>* out, std::map<int, FieldInfo>* fields) {
-  const long nq = t.nq, nv = t.nv, nu = t.nu, nb = t.nbody, nj = t.njnt, ng = t.ngeom, ns = t.nsite, nM = t.nM;
+  const long nq = t.nq, nv = t.nv, nu = t.nu, na = t.na, nb = t.nbody, nj = t.njnt, ng = t.ngeom, ns = t.nsite, nM = t.nM;
   const long ncm = std::max(1, t.nconmax), nem = std::max(1, t.nefcmax), nsd = t.nsensordata;
   size_t off = 0;
   auto take = [&](size_t elems, size_t esz) {
@@ -53,12 +53,12 @@ size_t layout_arena(const ox_model_tables& t, int stride, unsigned char* base, D
     R(OX_F_QFRC_CONSTRAINT, qfrc_constraint, nv) R(OX_F_CON_DIST, con_dist, ncm) R(OX_F_CON_POS, con_pos, 3 * ncm)
     R(OX_F_CON_FRAME, con_frame, 9 * ncm) R(OX_F_EFC_J, efc_J, nem * nv) R(OX_F_EFC_POS, efc_pos, nem)
     R(OX_F_EFC_MARGIN, efc_margin, nem) R(OX_F_EFC_D, efc_D, nem) R(OX_F_EFC_AREF, efc_aref, nem) R(OX_F_EFC_FORCE, efc_force, nem)
+    R(OX_F_ACT, act, na) R(OX_F_ACT_DOT, act_dot, na)
 #undef R
 #define I(id, name, cnt) f[id] = FieldInfo{out->name, (int)(cnt), true};
     I(OX_F_NCON, ncon, 1) I(OX_F_NEFC, nefc, 1) I(OX_F_SOLVER_NITER, solver_niter, 1) I(OX_F_DIVERGED, diverged, 1)
     I(OX_F_CON_PAIR, con_pair, ncm)
 #undef I
-    f[OX_F_ACT] = FieldInfo{nullptr, 0, false};
   }
   return off;
 }

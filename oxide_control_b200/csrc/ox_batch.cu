@@ -108,6 +108,17 @@ __global__ void k_pack(TF* __restrict__ field, TU* __restrict__ user, int nenv, 
   else user[idx] = (TU)field[fi];
 }
 
+// one field of the packed per-env state record (ox_batch_get_state / set_state): user[e * ustride + uoff + i] <-> field[i][e]
+template <typename TF, typename TU>
+__global__ void k_pack_record(TF* __restrict__ field, TU* __restrict__ user, int nenv, int cnt, int stride, int ustride, int uoff, int dir) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nenv * cnt) return;
+  const int e = (int)(idx / cnt), i = (int)(idx - (long long)e * cnt);
+  const size_t fi = (size_t)i * stride + e, ui = (size_t)e * ustride + uoff + i;
+  if (dir == 0) field[fi] = (TF)user[ui];
+  else user[ui] = (TU)field[fi];
+}
+
 }  // namespace ox
 
 using namespace ox;
@@ -273,7 +284,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   auto it = b->fields.find(field);
   if (it == b->fields.end()) { ox::set_error("bulk I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
   const FieldInfo& fi = it->second;
-  if (field == OX_F_ACT) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if ((field == OX_F_ACT || field == OX_F_ACT_DOT) && b->model->t.na == 0) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
   if (fi.count == 0) return OX_OK;
   if (dir == 1 && !field_live(b, field)) { ox::set_error("ox_batch_get: " + OX_STALE_MSG(field)); return OX_ERR_INVALID; }
   if (layout != OX_LAYOUT_ENV_MAJOR && layout != OX_LAYOUT_ELEM_MAJOR) { ox::set_error("bulk I/O: bad layout"); return OX_ERR_INVALID; }
@@ -315,7 +326,7 @@ ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, doubl
   auto it = b->fields.find(field);
   if (it == b->fields.end()) { ox::set_error("per-env I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
   const FieldInfo& fi = it->second;
-  if (field == OX_F_ACT) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if ((field == OX_F_ACT || field == OX_F_ACT_DOT) && b->model->t.na == 0) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
   if (env < 0 || env >= b->nenv || offset < 0 || count < 0 || offset + count > fi.count) {
     ox::set_error("per-env I/O: index out of range");
     return OX_ERR_INVALID;
@@ -631,6 +642,58 @@ ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step) {
   b->h_step = step;  // a captured graph picks it up at its next launch (do_step compares with d_step_val)
   return OX_OK;
 }
+
+// ---- checkpoint / resume: the integration state of mj_step plus the inputs that persist between steps
+static const int kStateFields[] = {OX_F_TIME, OX_F_QPOS, OX_F_QVEL, OX_F_ACT, OX_F_CTRL, OX_F_QFRC_APPLIED, OX_F_XFRC_APPLIED, OX_F_QACC_WARMSTART};
+
+int32_t ox_batch_state_size(const ox_batch* b) {
+  if (!b) return -1;
+  int n = 0;
+  for (int f : kStateFields) n += b->fields.at(f).count;
+  return n;
+}
+int64_t ox_batch_get_step_counter(const ox_batch* b) { return b ? b->h_step : -1; }
+
+static ox_status state_io(ox_batch* b, void* buf, int32_t dtype, int32_t mem, int dir) {
+  if (!b || !buf) { ox::set_error("ox_batch_get_state / set_state: null argument"); return OX_ERR_INVALID; }
+  if ((dtype != OX_F32 && dtype != OX_F64) || (mem != OX_MEM_HOST && mem != OX_MEM_DEVICE)) { ox::set_error("ox_batch_get_state / set_state: bad dtype / mem"); return OX_ERR_INVALID; }
+  CU_TRY(cudaSetDevice(b->cfg.device));
+  const int rec = ox_batch_state_size(b);
+  const size_t usz = dtype == OX_F64 ? 8 : 4, bytes = (size_t)b->nenv * rec * usz;
+  void* dbuf = buf;
+  bool staged = false;
+  if (mem == OX_MEM_HOST) {
+    if (void* alias = host_mapped(buf)) dbuf = alias;
+    else {
+      ox_status s = ensure_tmp(b, bytes);
+      if (s) return s;
+      dbuf = b->d_tmp; staged = true;
+      if (dir == 0) CU_TRY(cudaMemcpyAsync(dbuf, buf, bytes, cudaMemcpyHostToDevice, b->stream));
+    }
+  }
+  int off = 0;
+  for (int f : kStateFields) {
+    const FieldInfo& fi = b->fields.at(f);
+    if (fi.count == 0) continue;
+    const long long n = (long long)b->nenv * fi.count;
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+#define PACK(TF, TU) k_pack_record<TF, TU><<<blocks, threads, 0, b->stream>>>((TF*)fi.ptr, (TU*)dbuf, b->nenv, fi.count, b->stride, rec, off, dir)
+    if (b->f64) { if (dtype == OX_F64) PACK(double, double); else PACK(double, float); }
+    else { if (dtype == OX_F64) PACK(float, double); else PACK(float, float); }
+#undef PACK
+    b->launches++;
+    off += fi.count;
+  }
+  CU_TRY(cudaGetLastError());
+  if (dir == 0) b->applied = 1;  // the record carries qfrc_applied / xfrc_applied
+  if (mem == OX_MEM_HOST && dir == 1) {
+    if (staged) CU_TRY(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+  }
+  return OX_OK;
+}
+ox_status ox_batch_get_state(ox_batch* b, void* buf, int32_t dtype, int32_t mem) { return state_io(b, buf, dtype, mem, 1); }
+ox_status ox_batch_set_state(ox_batch* b, const void* buf, int32_t dtype, int32_t mem) { return state_io(b, const_cast<void*>(buf), dtype, mem, 0); }
 
 int32_t ox_batch_field_size(const ox_batch* b, int32_t field) {
   if (!b) return -1;

@@ -109,7 +109,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
 #define OX_BATCH_REAL_FIELDS(X)                                                                        \
   /* state */                                                                                          \
   X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(xfrc_applied, 6 * nb) X(qacc_warmstart, nv) \
-  X(time, 1)                                                                                           \
+  X(time, 1) X(act, na) X(act_dot, na)                                                                 \
   /* position stage */                                                                                 \
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(xmat, 9 * nb) X(xipos, 3 * nb) X(ximat, 9 * nb)                   \
   X(xanchor, 3 * nj) X(xaxis, 3 * nj) X(geom_xpos, 3 * ng) X(geom_xmat, 9 * ng)                        \
@@ -125,7 +125,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   X(qacc, nv) X(qfrc_constraint, nv) X(s_Ma, nv) X(s_Jaref, nem) X(s_grad, nv) X(s_Mgrad, nv)          \
   X(s_search, nv) X(s_Mv, nv) X(s_Jv, nem) X(s_H, nv * nv) X(s_gradold, nv) X(s_Mgradold, nv)          \
   /* integrator scratch */                                                                             \
-  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(rk_t0, 1) X(i_qacc, nv)                                    \
+  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(rk_t0, 1) X(i_qacc, nv) X(rk_a0, na) X(rk_sad, na)        \
   X(sensordata, nsd) X(subtree_linvel, 3 * nb)
 
 #define OX_BATCH_INT_FIELDS(X) \

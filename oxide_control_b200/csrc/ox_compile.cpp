@@ -557,6 +557,8 @@ struct ActDef {
   double gainprm[3] = {1, 0, 0}, biasprm[3] = {0, 0, 0};
   int ctrllimited = 0, forcelimited = 0;
   double ctrlrange[2] = {0, 0}, forcerange[2] = {0, 0};
+  int dyntype = OX_DYN_NONE, actlimited = 0;
+  double dynprm[3] = {1, 0, 0}, actrange[2] = {0, 0};
 };
 struct SensorDef {
   std::string name;
@@ -641,7 +643,8 @@ ox_model* compile_mjcf(const std::string& xml) {
         const std::string& s = a.str("integrator");
         if (s == "Euler") t.integrator = OX_INT_EULER;
         else if (s == "RK4") t.integrator = OX_INT_RK4;
-        else if (s == "implicit" || s == "implicitfast") cfail("integrator '" + s + "' is outside the supported subset (Euler, RK4)");
+        else if (s == "implicitfast") t.integrator = OX_INT_IMPLICITFAST;
+        else if (s == "implicit") cfail("integrator 'implicit' (full RNE velocity derivatives, non-symmetric solve) is outside the supported subset (Euler, RK4, implicitfast)");
         else pfail(*ch, "unknown integrator '" + s + "'");
       }
       if (a.has("solver")) {
@@ -999,7 +1002,25 @@ ox_model* compile_mjcf(const std::string& xml) {
         int jt = B.joints[ad.joint].type;
         if (jt != OX_JNT_HINGE && jt != OX_JNT_SLIDE) cfail("actuator '" + ad.name + "': only hinge/slide joint transmissions are supported");
         if (a.has("gear")) ad.gear = a.nums("gear").at(0);
-        if (a.has("dyntype") && a.str("dyntype") != "none") cfail("actuator '" + ad.name + "': stateful actuators (dyntype) are outside the supported subset");
+        if (a.has("dyntype")) {
+          const std::string& s = a.str("dyntype");
+          if (e->name != "general" && s != "none") cfail("actuator '" + ad.name + "': dyntype is an attribute of <general>");
+          if (s == "none") ad.dyntype = OX_DYN_NONE;
+          else if (s == "integrator") ad.dyntype = OX_DYN_INTEGRATOR;
+          else if (s == "filter") ad.dyntype = OX_DYN_FILTER;
+          else if (s == "filterexact") ad.dyntype = OX_DYN_FILTEREXACT;
+          else cfail("actuator '" + ad.name + "': dyntype '" + s + "' is outside the supported subset (none, integrator, filter, filterexact)");
+        }
+        if (a.has("actdim") || a.has("actearly")) cfail("actuator '" + ad.name + "': actdim / actearly are outside the supported subset");
+        a.vec("dynprm", ad.dynprm, 3, true);
+        {
+          const bool has_ar = a.has("actrange");
+          if (has_ar) a.vec("actrange", ad.actrange, 2);
+          const int al = a.boolean("actlimited");
+          ad.actlimited = al >= 0 ? al : (has_ar && B.c.autolimits);
+          if (ad.actlimited && ad.dyntype == OX_DYN_NONE) cfail("actuator '" + ad.name + "': actlimited needs a stateful actuator (dyntype)");
+          if (ad.actlimited && !(ad.actrange[0] < ad.actrange[1])) cfail("actuator '" + ad.name + "': invalid actrange");
+        }
         if (e->name == "position") {
           double kp = a.num("kp", 1), kv = a.num("kv", 0);
           if (a.has("dampratio") || a.has("timeconst")) cfail("actuator '" + ad.name + "': dampratio/timeconst are outside the supported subset");
@@ -1039,7 +1060,10 @@ ox_model* compile_mjcf(const std::string& xml) {
   M->v_actuator_ctrllimited.resize(nu); M->v_actuator_forcelimited.resize(nu);
   M->v_actuator_gear.resize(nu); M->v_actuator_gainprm.resize(3 * nu); M->v_actuator_biasprm.resize(3 * nu);
   M->v_actuator_ctrlrange.resize(2 * nu); M->v_actuator_forcerange.resize(2 * nu);
+  M->v_actuator_dyntype.resize(nu); M->v_actuator_actadr.resize(nu); M->v_actuator_actlimited.resize(nu);
+  M->v_actuator_dynprm.resize(3 * nu); M->v_actuator_actrange.resize(2 * nu);
   nm[OX_OBJ_ACTUATOR].resize(nu);
+  int na = 0;
   for (int i = 0; i < nu; i++) {
     const ActDef& a = acts[i];
     nm[OX_OBJ_ACTUATOR][i] = a.name;
@@ -1048,7 +1072,12 @@ ox_model* compile_mjcf(const std::string& xml) {
     M->v_actuator_gear[i] = a.gear;
     for (int k = 0; k < 3; k++) { M->v_actuator_gainprm[3 * i + k] = a.gainprm[k]; M->v_actuator_biasprm[3 * i + k] = a.biasprm[k]; }
     for (int k = 0; k < 2; k++) { M->v_actuator_ctrlrange[2 * i + k] = a.ctrlrange[k]; M->v_actuator_forcerange[2 * i + k] = a.forcerange[k]; }
+    M->v_actuator_dyntype[i] = a.dyntype; M->v_actuator_actlimited[i] = a.actlimited;
+    M->v_actuator_actadr[i] = a.dyntype != OX_DYN_NONE ? na++ : -1;   // one activation variable per stateful actuator (actdim 1)
+    for (int k = 0; k < 3; k++) M->v_actuator_dynprm[3 * i + k] = a.dynprm[k];
+    for (int k = 0; k < 2; k++) M->v_actuator_actrange[2 * i + k] = a.actrange[k];
   }
+  t.na = na;
   check_unique(OX_OBJ_ACTUATOR, "actuator");
 
   // ---- sensors (N2 subset) ----

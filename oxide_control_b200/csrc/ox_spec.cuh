@@ -70,7 +70,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   // per-thread copy of every batch field, sized by the spec's compile-time dimensions. One local array per field (not one
   // struct): each array whose indices all fold to constants after unrolling is promoted to registers independently;
   // only the runtime-indexed ones (contact / constraint rows and what the contact Jacobian walk reads) stay in local memory.
-  constexpr int nq = H::nq, nv = H::nv, nu = H::nu, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
+  constexpr int nq = H::nq, nv = H::nv, nu = H::nu, na = H::na, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
                 ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata;
 #define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v];
   OX_BATCH_REAL_FIELDS(OX_X)
@@ -98,6 +98,8 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   for (int i = 0; i < H::nq; i++) loc_qpos[i] = G(qpos, i);
 #pragma unroll
   for (int i = 0; i < H::nv; i++) loc_qvel[i] = G(qvel, i);
+#pragma unroll
+  for (int i = 0; i < H::na; i++) loc_act[i] = G(act, i);
   loc_time[0] = G(time, 0);
   loc_diverged[0] = G(diverged, 0);
   const int32_t div0 = loc_diverged[0];
@@ -124,6 +126,8 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     for (int i = 0; i < H::nq; i++) G(qpos, i) = loc_qpos[i];
 #pragma unroll
     for (int i = 0; i < H::nv; i++) G(qvel, i) = loc_qvel[i];
+#pragma unroll
+    for (int i = 0; i < H::na; i++) { G(act, i) = loc_act[i]; G(act_dot, i) = loc_act_dot[i]; }
     G(time, 0) = loc_time[0];
     G(diverged, 0) = loc_diverged[0];
     if (inputs_too) {  // an auto-reset cleared them
@@ -178,6 +182,8 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #pragma unroll
     for (int i = 0; i < H::nM; i++) G(qM, i) = loc_qM[i];
 #pragma unroll
+    for (int i = 0; i < H::na; i++) G(act_dot, i) = loc_act_dot[i];   // POST integrates the activations
+#pragma unroll
     for (int i = 0; i < H::nv; i++) { G(qfrc_smooth, i) = loc_qfrc_smooth[i]; G(qacc_smooth, i) = loc_qacc_smooth[i]; }
 #pragma unroll
     for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = loc_sensordata[i];
@@ -193,6 +199,8 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     for (int i = 0; i < H::nv; i++) { loc_qacc[i] = G(qacc, i); loc_qfrc_constraint[i] = G(qfrc_constraint, i); loc_qfrc_smooth[i] = G(qfrc_smooth, i); }
 #pragma unroll
     for (int i = 0; i < H::nM; i++) loc_qM[i] = G(qM, i);
+#pragma unroll
+    for (int i = 0; i < H::na; i++) loc_act_dot[i] = G(act_dot, i);
     loc_acc_ncon[0] = G(acc_ncon, 0); loc_acc_nefc[0] = G(acc_nefc, 0); loc_acc_niter[0] = G(acc_niter, 0);
     loc_ncon[0] = G(ncon, 0); loc_nefc[0] = G(nefc, 0); loc_solver_niter[0] = G(solver_niter, 0);
     const bool redo = env.bad_acc();

@@ -35,6 +35,8 @@ OX_HD float ox_abs(float x) { return fabsf(x); }
 OX_HD double ox_abs(double x) { return fabs(x); }
 OX_HD float ox_pow(float x, float y) { return powf(x, y); }
 OX_HD double ox_pow(double x, double y) { return pow(x, y); }
+OX_HD float ox_exp(float x) { return expf(x); }
+OX_HD double ox_exp(double x) { return exp(x); }
 OX_HD float ox_atan2(float y, float x) { return atan2f(y, x); }
 OX_HD double ox_atan2(double y, double x) { return atan2(y, x); }
 // sincos: ONE out-of-line copy per kernel. Inlined, CUDA's sincosf (fast path + Payne-Hanek slow path) is ~1.3 k
@@ -705,6 +707,15 @@ struct Env {
       const T length = gear * at(b.qpos, qa), velocity = gear * at(b.qvel, da);
       T ctrl = at(b.ctrl, i);
       if (m.actuator_ctrllimited(i) && clamp) ctrl = ox_clip(ctrl, m.actuator_ctrlrange(2 * i), m.actuator_ctrlrange(2 * i + 1));
+      // stateful actuators (mjtDyn integrator / filter / filterexact): the force is driven by the activation state, and the
+      // control sets its time derivative (mj_fwdActuation); mj_advance integrates it (next_activation below)
+      const int dyn = m.actuator_dyntype(i);
+      if (dyn != OX_DYN_NONE) {
+        const int aa = m.actuator_actadr(i);
+        const T act = at(b.act, aa);
+        at(b.act_dot, aa) = dyn == OX_DYN_INTEGRATOR ? ctrl : (ctrl - act) / ox_max((T)OX_MINVAL, m.actuator_dynprm(3 * i));
+        ctrl = act;
+      }
       T gp[3], bp[3];
       OX_LDM(3, gp, actuator_gainprm, 3 * i);
       OX_LDM(3, bp, actuator_biasprm, 3 * i);
@@ -1563,9 +1574,32 @@ struct Env {
       }
     }
   }
-  OX_HD void advance(const T* qacc, const T* qvel_override) const {
+  // mj_nextActivation: explicit Euler, or the exact solution of the first-order filter over one step; clamped to actrange
+  OX_HD T next_activation(int i, T act, T act_dot) const {
+    const T dt = (T)m.h().timestep;
+    if (m.actuator_dyntype(i) == OX_DYN_FILTEREXACT) {
+      const T tau = ox_max((T)OX_MINVAL, m.actuator_dynprm(3 * i));
+      act += act_dot * tau * ((T)1 - ox_exp(-dt / tau));
+    } else {
+      act += act_dot * dt;
+    }
+    if (m.actuator_actlimited(i)) act = ox_clip(act, m.actuator_actrange(2 * i), m.actuator_actrange(2 * i + 1));
+    return act;
+  }
+  OX_HD void advance_act(const T* act_dot) const {
+    const int nu = m.h().nu;
+    if (m.h().na == 0) return;
+    OX_MLOOP
+    for (int i = 0; i < nu; i++) {
+      if (m.actuator_dyntype(i) == OX_DYN_NONE) continue;
+      const int aa = m.actuator_actadr(i);
+      at(b.act, aa) = next_activation(i, at(b.act, aa), at(act_dot, aa));
+    }
+  }
+  OX_HD void advance(const T* qacc, const T* qvel_override, const T* act_dot) const {
     const auto& h = m.h();
     const T dt = (T)h.timestep;
+    advance_act(act_dot);
     OX_MLOOP
     for (int i = 0; i < h.nv; i++) at(b.qvel, i) += dt * at(qacc, i);
     integrate_pos(b.qpos, qvel_override ? qvel_override : b.qvel, dt);
@@ -1573,20 +1607,42 @@ struct Env {
   }
   OX_HDN void euler() const {
     const auto& h = m.h();
-    const int nv = h.nv, nM = h.nM;
-    if (!h.any_damping || dis(OX_DSBL_EULERDAMP)) { advance(b.qacc, nullptr); return; }
+    const int nv = h.nv, nM = h.nM, nu = h.nu;
+    const bool fast = h.integrator == OX_INT_IMPLICITFAST;
+    if (!fast && (!h.any_damping || dis(OX_DSBL_EULERDAMP))) { advance(b.qacc, nullptr, b.act_dot); return; }
     // implicit-in-velocity joint damping: (M + h B) qacc' = qfrc_smooth + qfrc_constraint; like MuJoCo
     // the factor of M in qLD is overwritten by the factor of M + h B.
+    // implicitfast (mj_implicit with the RNE derivatives dropped): M - h dqfrc_smooth/dqvel, which for this subset (joint
+    // transmissions, joint damping) is diagonal: B_i = damping_i - sum over actuators on dof i of gear^2 dforce/dvelocity,
+    // so the same sparse L'DL serves; an actuator whose force sits on its forcerange bound contributes nothing.
     const T dt = (T)h.timestep;
     OX_MLOOP
     for (int i = 0; i < nM; i++) at(b.qLD, i) = at(b.qM, i);
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qLD, m.dof_Madr(i)) += dt * m.dof_damping(i);
+    if (fast && !dis(OX_DSBL_ACTUATION)) {
+      const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
+      OX_MLOOP
+      for (int i = 0; i < nu; i++) {
+        const bool gaff = m.actuator_gaintype(i) == OX_GAIN_AFFINE, baff = m.actuator_biastype(i) == OX_BIAS_AFFINE;
+        if (!gaff && !baff) continue;
+        if (m.actuator_forcelimited(i)) {
+          const T f = at(b.actuator_force, i);
+          if (f <= m.actuator_forcerange(2 * i) || f >= m.actuator_forcerange(2 * i + 1)) continue;
+        }
+        T input = at(b.ctrl, i);
+        if (m.actuator_ctrllimited(i) && clamp) input = ox_clip(input, m.actuator_ctrlrange(2 * i), m.actuator_ctrlrange(2 * i + 1));
+        if (m.actuator_dyntype(i) != OX_DYN_NONE) input = at(b.act, m.actuator_actadr(i));  // not advanced yet: what the force was computed from
+        const T gear = m.actuator_gear(i);
+        const T dfdv = (gaff ? m.actuator_gainprm(3 * i + 2) * input : (T)0) + (baff ? m.actuator_biasprm(3 * i + 2) : (T)0);
+        at(b.qLD, m.dof_Madr(m.jnt_dofadr(m.actuator_trnid(i)))) -= dt * gear * gear * dfdv;
+      }
+    }
     factor_ld(b.qLD, b.qLDiagInv);
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.i_qacc, i) = at(b.qfrc_smooth, i) + at(b.qfrc_constraint, i);
     solve_ld(b.i_qacc);
-    advance(b.i_qacc, nullptr);
+    advance(b.i_qacc, nullptr, b.act_dot);
   }
   // classic RK4; the Butcher matrix has one entry per row, so X_i = X_0 (+) h a_i F_{i-1}. Split into pieces so that
   // step() can drive all four forward evaluations through ONE call site (code size: forward() is inlined once).
@@ -1600,6 +1656,8 @@ struct Env {
       at(b.rk_sv, i) = (T)(1.0 / 6) * at(b.qvel, i);
       at(b.rk_sa, i) = (T)(1.0 / 6) * at(b.qacc, i);
     }
+    OX_MLOOP
+    for (int i = 0; i < h.na; i++) { at(b.rk_a0, i) = at(b.act, i); at(b.rk_sad, i) = (T)(1.0 / 6) * at(b.act_dot, i); }
     at(b.rk_t0, 0) = at(b.time, 0);
   }
   OX_HD void rk4_prepare(int st_) const {  // state for stage st_ = 1..3 from F_{st_-1} = (current qvel, current qacc)
@@ -1613,6 +1671,8 @@ struct Env {
     integrate_pos(b.qpos, b.s_gradold, dt);
     OX_MLOOP
     for (int i = 0; i < h.nv; i++) at(b.qvel, i) = at(b.rk_v0, i) + dt * at(b.s_Mgradold, i);
+    OX_MLOOP
+    for (int i = 0; i < h.na; i++) at(b.act, i) = at(b.rk_a0, i) + a * dt * at(b.act_dot, i);   // intermediate stages: plain Euler, no clamp
     at(b.time, 0) = at(b.rk_t0, 0) + a * dt;
   }
   OX_HD void rk4_accumulate(int st_) const {
@@ -1623,6 +1683,8 @@ struct Env {
       at(b.rk_sv, i) += w * at(b.qvel, i);
       at(b.rk_sa, i) += w * at(b.qacc, i);
     }
+    OX_MLOOP
+    for (int i = 0; i < h.na; i++) at(b.rk_sad, i) += w * at(b.act_dot, i);
   }
   OX_HD void rk4_finish() const {
     const auto& h = m.h();
@@ -1631,7 +1693,9 @@ struct Env {
     for (int i = 0; i < h.nq; i++) at(b.qpos, i) = at(b.rk_q0, i);
     OX_MLOOP
     for (int i = 0; i < h.nv; i++) at(b.qvel, i) = at(b.rk_v0, i);
-    advance(b.rk_sa, b.rk_sv);
+    OX_MLOOP
+    for (int i = 0; i < h.na; i++) at(b.act, i) = at(b.rk_a0, i);
+    advance(b.rk_sa, b.rk_sv, b.rk_sad);
   }
   OX_HDN void rk4() const {  // staged mode: stages 2..4 after the forward the step already ran
     rk4_begin();
@@ -1654,6 +1718,8 @@ struct Env {
     OX_MLOOP
     for (int i = 0; i < h.nu; i++) at(b.ctrl, i) = 0;
     OX_MLOOP
+    for (int i = 0; i < h.na; i++) { at(b.act, i) = 0; at(b.act_dot, i) = 0; }
+    OX_MLOOP
     for (int i = 0; i < 6 * h.nbody; i++) at(b.xfrc_applied, i) = 0;
     at(b.time, 0) = 0;
     ati(b.ncon, 0) = 0; ati(b.nefc, 0) = 0; ati(b.solver_niter, 0) = 0;
@@ -1665,6 +1731,8 @@ struct Env {
     for (int i = 0; i < h.nq; i++) bad |= ox_bad(at(b.qpos, i));
     OX_MLOOP
     for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qvel, i));
+    OX_MLOOP
+    for (int i = 0; i < h.na; i++) bad |= ox_bad(at(b.act, i));
     return bad;
   }
   OX_HD bool bad_acc() const {

@@ -262,6 +262,22 @@ class BatchedPhysics:
         _check(A.lib().ox_batch_set_step_counter(self._h, step))
 
     # ---- bulk I/O
+    # checkpoint / resume (ox_batch_get_state / ox_batch_set_state)
+    def get_state(self, dtype=np.float64) -> np.ndarray:
+        """[nenv, state_size] records: time, qpos, qvel, act, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart."""
+        n = A.lib().ox_batch_state_size(self._h)
+        out = np.empty((self.nenv, n), dtype=dtype)
+        _check(A.lib().ox_batch_get_state(self._h, out.ctypes.data_as(C.c_void_p), A.F64 if out.dtype == np.float64 else A.F32, A.MEM_HOST))
+        return out
+
+    def set_state(self, state: np.ndarray) -> None:
+        state = np.ascontiguousarray(state, dtype=np.float64 if state.dtype != np.float32 else np.float32)
+        assert state.shape == (self.nenv, A.lib().ox_batch_state_size(self._h)), state.shape
+        _check(A.lib().ox_batch_set_state(self._h, state.ctypes.data_as(C.c_void_p), A.F64 if state.dtype == np.float64 else A.F32, A.MEM_HOST))
+
+    def step_counter(self) -> int:
+        return int(A.lib().ox_batch_get_step_counter(self._h))
+
     def field_size(self, field: str) -> int:
         n = A.lib().ox_batch_field_size(self._h, A.FIELD[field])
         if n < 0:
@@ -467,12 +483,20 @@ class Physics:
     def set_ctrl(self, id: ObjectId, value: float) -> None:
         self._b.set1("ctrl", 0, [value], id.index)
 
-    # src/physics.rs:96-102: None when the actuator is stateless (all supported actuators are)
+    # src/physics.rs:96-102: Some(activation) for a stateful actuator (dyntype integrator / filter / filterexact), None otherwise
+    def _actadr(self, id: ObjectId) -> int:
+        return int(self._model.actuator_actadr[id.index]) if self._model.na else -1
+
     def act(self, id: ObjectId) -> Optional[float]:
-        return None
+        adr = self._actadr(id)
+        return None if adr < 0 else float(self._b.get1("act", 0, adr, 1)[0])
 
     def set_act(self, id: ObjectId, value: float) -> Optional[tuple]:
-        return None
+        adr = self._actadr(id)
+        if adr < 0:
+            return None
+        self._b.set1("act", 0, [value], adr)
+        return ()
 
     # src/physics.rs:104-116
     def _jnt(self, id: ObjectId, expected: Optional[int]):

@@ -69,16 +69,17 @@ class DenseModel:
     """numpy copies of the compiled tables (read through the Python Model mirror)."""
     INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
-           "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited"]
+           "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
+           "actuator_dyntype", "actuator_actadr", "actuator_actlimited"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
             "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
             "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
             "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
-            "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange"]
+            "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange"]
 
     def __init__(self, model):
         self.m = model
-        for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags"):
+        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags"):
             setattr(self, k, int(getattr(model, k)))
         for k in ("timestep", "impratio"):
             setattr(self, k, float(getattr(model, k)))
@@ -224,10 +225,12 @@ def passive_force(dm, qpos, qvel):
     return f - dm.dof_damping * qvel
 
 
-def actuator_force(dm, qpos, qvel, ctrl):
+def actuator_force(dm, qpos, qvel, ctrl, act=None):
+    """qfrc_actuator, actuator_force, act_dot and the diagonal of d qfrc_actuator / d qvel (used by implicitfast)."""
     f, frc = np.zeros(dm.nv), np.zeros(dm.nu)
+    act_dot, dfdv = np.zeros(dm.na), np.zeros(dm.nv)
     if dm.dis("actuation"):
-        return f, frc
+        return f, frc, act_dot, dfdv
     for i in range(dm.nu):
         j = int(dm.actuator_trnid[i])
         qa, da, gear = int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j]), dm.actuator_gear[i]
@@ -235,15 +238,44 @@ def actuator_force(dm, qpos, qvel, ctrl):
         u = ctrl[i]
         if dm.actuator_ctrllimited[i] and not dm.dis("clampctrl"):
             u = min(max(u, dm.actuator_ctrlrange[2 * i]), dm.actuator_ctrlrange[2 * i + 1])
+        dyn = int(dm.actuator_dyntype[i])
+        if dyn != 0:                                            # stateful: ctrl drives act_dot, act drives the force
+            aa = int(dm.actuator_actadr[i])
+            act_dot[aa] = u if dyn == 1 else (u - act[aa]) / max(MINVAL, dm.actuator_dynprm[3 * i])
+            u = act[aa]
         gp, bp = dm.actuator_gainprm[3 * i:3 * i + 3], dm.actuator_biasprm[3 * i:3 * i + 3]
-        gain = gp[0] + (gp[1] * length + gp[2] * vel if dm.actuator_gaintype[i] == 1 else 0.0)
-        bias = bp[0] + bp[1] * length + bp[2] * vel if dm.actuator_biastype[i] == 1 else 0.0
+        gaff, baff = dm.actuator_gaintype[i] == 1, dm.actuator_biastype[i] == 1
+        gain = gp[0] + (gp[1] * length + gp[2] * vel if gaff else 0.0)
+        bias = bp[0] + bp[1] * length + bp[2] * vel if baff else 0.0
         force = gain * u + bias
+        clamped = False
         if dm.actuator_forcelimited[i]:
-            force = min(max(force, dm.actuator_forcerange[2 * i]), dm.actuator_forcerange[2 * i + 1])
+            lo, hi = dm.actuator_forcerange[2 * i], dm.actuator_forcerange[2 * i + 1]
+            clamped = force <= lo or force >= hi
+            force = min(max(force, lo), hi)
         frc[i] = force
         f[da] += gear * force
-    return f, frc
+        if not clamped:
+            dfdv[da] += gear * gear * ((gp[2] * u if gaff else 0.0) + (bp[2] if baff else 0.0))
+    return f, frc, act_dot, dfdv
+
+
+def next_activation(dm, act, act_dot):
+    out = np.array(act, float)
+    h = dm.timestep
+    for i in range(dm.nu):
+        dyn = int(dm.actuator_dyntype[i])
+        if dyn == 0:
+            continue
+        aa = int(dm.actuator_actadr[i])
+        if dyn == 3:
+            tau = max(MINVAL, dm.actuator_dynprm[3 * i])
+            out[aa] += act_dot[aa] * tau * (1 - np.exp(-h / tau))
+        else:
+            out[aa] += h * act_dot[aa]
+        if dm.actuator_actlimited[i]:
+            out[aa] = min(max(out[aa], dm.actuator_actrange[2 * i]), dm.actuator_actrange[2 * i + 1])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ collision
@@ -487,11 +519,12 @@ def solve_qacc(M, qfrc_smooth, J, D, aref):
 
 
 # ------------------------------------------------------------------------------------------------ whole step
-def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None):
+def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None):
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
+    act = np.zeros(dm.na) if act is None else np.asarray(act, float)
     kin = Kin(dm, qpos, qvel)
     M, c = mass_matrix_and_bias(dm, kin)
-    fa, frc = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float))
+    fa, frc, act_dot, dfdv = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float), act)
     f = passive_force(dm, qpos, qvel) - c + fa
     if qfrc_applied is not None:
         f = f + qfrc_applied
@@ -505,7 +538,8 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     J, D, aref = constraints(dm, kin, qpos, qvel, cons)
     qacc, force = solve_qacc(M, f, J, D, aref)
     return dict(qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
-                nefc=J.shape[0], efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]))
+                nefc=J.shape[0], efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]), act_dot=act_dot,
+                dfdv=dfdv)
 
 
 def integrate_pos(dm, qpos, vel, h):
@@ -528,27 +562,32 @@ def integrate_pos(dm, qpos, vel, h):
     return q
 
 
-def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None):
-    """One mj_step. Returns dict(qpos, qvel, qacc, ncon, nefc, ...) - qacc is the forward's (pre-integration) acceleration."""
+def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None):
+    """One mj_step. Returns dict(qpos, qvel, act, qacc, ncon, nefc, ...) - qacc is the forward's (pre-integration) acceleration."""
     h = dm.timestep
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
-    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied)
-    if dm.integrator == 0:
+    act = np.zeros(dm.na) if act is None else np.asarray(act, float)
+    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied, act)
+    if dm.integrator in (0, 3):
         qacc = f0["qacc"]
-        if np.any(dm.dof_damping > 0) and not dm.dis("eulerdamp"):
+        if dm.integrator == 3:      # implicitfast: (M - h d qfrc_smooth / d qvel) qacc' = M qacc, derivative = -damping + actuator term
+            qacc = np.linalg.solve(f0["M"] + h * np.diag(dm.dof_damping - f0["dfdv"]), f0["qfrc_smooth"] + f0["qfrc_constraint"])
+        elif np.any(dm.dof_damping > 0) and not dm.dis("eulerdamp"):
             qacc = np.linalg.solve(f0["M"] + h * np.diag(dm.dof_damping), f0["qfrc_smooth"] + f0["qfrc_constraint"])
         v1 = qvel + h * qacc
-        out = dict(f0, qpos=integrate_pos(dm, qpos, v1, h), qvel=v1)
+        out = dict(f0, qpos=integrate_pos(dm, qpos, v1, h), qvel=v1, act=next_activation(dm, act, f0["act_dot"]))
     else:                                                               # RK4, classic tableau
         A, Bw = [0.5, 0.5, 1.0], [1 / 6, 1 / 3, 1 / 3, 1 / 6]
-        F = [(qvel, f0["qacc"])]
+        F = [(qvel, f0["qacc"], f0["act_dot"])]
         last = f0
         for i in range(3):
             qi = integrate_pos(dm, qpos, F[i][0], A[i] * h)
             vi = qvel + A[i] * h * F[i][1]
-            last = forward(dm, qi, vi, ctrl, qfrc_applied, xfrc_applied)
-            F.append((vi, last["qacc"]))
+            ai = act + A[i] * h * F[i][2]
+            last = forward(dm, qi, vi, ctrl, qfrc_applied, xfrc_applied, ai)
+            F.append((vi, last["qacc"], last["act_dot"]))
         sv = sum(w * Fi[0] for w, Fi in zip(Bw, F))
         sa = sum(w * Fi[1] for w, Fi in zip(Bw, F))
-        out = dict(last, qpos=integrate_pos(dm, qpos, sv, h), qvel=qvel + h * sa)   # derived fields: those of the 4th stage, as in mjData
+        sd = sum(w * Fi[2] for w, Fi in zip(Bw, F))
+        out = dict(last, qpos=integrate_pos(dm, qpos, sv, h), qvel=qvel + h * sa, act=next_activation(dm, act, sd))   # derived fields: those of the 4th stage, as in mjData
     return out

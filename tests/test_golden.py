@@ -13,14 +13,14 @@ import pytest
 
 import oxide_control_b200 as ox
 from support import OracleData, rel_err
-from zoo_models import HOPPER, ZOO
+from zoo_models import HOPPER, NOCONTACT, ZOO
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-XML = {**{k: v["xml"] for k, v in ox.models.CONFIGS.items()}, **ZOO, "hopper": HOPPER}
+XML = {**{k: v["xml"] for k, v in ox.models.CONFIGS.items()}, **ZOO, **NOCONTACT, "hopper": HOPPER}
 # single-step gates, rel = |a-b| / max(1,|b|). zoo_b runs the CG solver (tolerance 1e-10, RK4: four solves per step), whose
 # iterates stop at the tolerance instead of landing on the minimiser the way Newton's do - its qacc gate is the solver's.
-TOL = {name: dict(qpos=1e-9, qvel=1e-9, qacc=1e-8) for name in XML}
-TOL["zoo_b"] = dict(qpos=1e-8, qvel=1e-5, qacc=1e-3)
+TOL = {name: dict(qpos=1e-9, qvel=1e-9, qacc=1e-8, act=1e-12) for name in XML}
+TOL["zoo_b"] = dict(qpos=1e-8, qvel=1e-5, qacc=1e-3, act=1e-12)
 # derived arrays of the last forward of the step. With RK4 that is the 4th stage, whose inputs carry the (CG-tolerance) error
 # of the first three solves in zoo_b; everywhere else they are functions of the input state alone.
 AUX = {name: 1e-9 for name in XML}
@@ -39,11 +39,11 @@ def test_oracle_matches_dense_checker_fixtures(name):
     assert (g["nq"], g["nv"]) == (m.nq, m.nv) and len(g["cases"]) >= (64 if m.npair else 16)
     if m.npair:
         assert g["states_in_contact"] >= 30      # the fixtures really exercise the constrained path
-    worst = dict(qpos=0.0, qvel=0.0, qacc=0.0)
+    worst = dict(qpos=0.0, qvel=0.0, qacc=0.0, act=0.0)
     for case in g["cases"]:
         i, o = case["input"], case["output"]
         od = OracleData(m)
-        for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied"):
+        for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act"):
             if len(i[f]):
                 od.field(f)[:] = i[f]
         od.step()
@@ -63,16 +63,17 @@ def test_oracle_matches_dense_checker_fixtures(name):
         assert worst[f] <= t, (f, worst[f])
 
 
-@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a"])
+@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a", "zoo_c"])
 def test_fixtures_are_reproducible(name):
     import dense_checker as dc
     g = load(name)
     dm = dc.DenseModel(ox.Model.from_xml_string(XML[name]))
     for case in g["cases"][-2:]:
         i, o = case["input"], case["output"]
-        r = dc.step(dm, np.array(i["qpos"]), np.array(i["qvel"]), np.array(i["ctrl"]), np.array(i["qfrc_applied"]), np.array(i["xfrc_applied"]))
+        r = dc.step(dm, np.array(i["qpos"]), np.array(i["qvel"]), np.array(i["ctrl"]), np.array(i["qfrc_applied"]), np.array(i["xfrc_applied"]),
+                    np.array(i["act"]))
         assert r["ncon"] == o["ncon"] and r["nefc"] == o["nefc"]
-        for f in ("qpos", "qvel", "qacc", "qfrc_bias"):
+        for f in ("qpos", "qvel", "act", "qacc", "qfrc_bias"):
             assert rel_err(r[f], o[f]) <= 1e-11, f
 
 
@@ -85,7 +86,7 @@ def test_cuda_path_matches_dense_checker_fixtures(name, kernel):
     cases = g["cases"]
     n = len(cases)
     b = ox.BatchedPhysics(m, n, precision="f64", specialize=(kernel == "default"))
-    for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied"):
+    for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act"):
         v = np.array([c["input"][f] for c in cases], dtype=np.float64)
         if v.shape[1]:
             b.set(f, v)

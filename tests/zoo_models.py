@@ -122,4 +122,64 @@ HOPPER = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B}
+# N4 / N3: implicitfast integrator, stateful actuators (integrator with actrange, filter, filterexact), velocity-dependent
+# actuator terms (what implicitfast differentiates), a force-clamped velocity servo, contacts and joint limits
+ZOO_C = """
+<mujoco model="zoo_c">
+  <compiler angle="radian"/>
+  <option timestep="0.005" integrator="implicitfast"/>
+  <default><joint damping="0.3" armature="0.01"/><geom friction="0.7 0.01 0.001"/></default>
+  <worldbody>
+    <geom type="plane" size="3 3 0.1"/>
+    <body name="base" pos="0 0 0.45">
+      <joint name="slide_x" type="slide" axis="1 0 0" damping="2"/>
+      <joint name="slide_z" type="slide" axis="0 0 1" range="-0.4 0.6" limited="true"/>
+      <geom name="base" type="box" size="0.12 0.08 0.05" density="800"/>
+      <body name="upper" pos="0 0 -0.05">
+        <joint name="hip" type="hinge" axis="0 1 0" range="-1.2 1.2" limited="true"/>
+        <geom name="upper" type="capsule" fromto="0 0 0 0 0 -0.25" size="0.03"/>
+        <body name="lower" pos="0 0 -0.25">
+          <joint name="knee" type="hinge" axis="0 1 0" range="-2 0.1" limited="true" stiffness="2" springref="-0.4"/>
+          <geom name="lower" type="capsule" fromto="0 0 0 0 0 -0.22" size="0.025"/>
+          <geom name="toe" type="sphere" pos="0 0 -0.22" size="0.035"/>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <contact><exclude body1="base" body2="lower"/></contact>
+  <actuator>
+    <general name="hip_int" joint="hip" gear="3" dyntype="integrator" actlimited="true" actrange="-0.6 0.6" ctrlrange="-1 1" ctrllimited="true"
+             gaintype="fixed" gainprm="4" biastype="affine" biasprm="0 -4 -0.4"/>
+    <general name="knee_filt" joint="knee" gear="2" dyntype="filter" dynprm="0.03" ctrlrange="-1 1" ctrllimited="true"/>
+    <general name="x_fexact" joint="slide_x" gear="5" dyntype="filterexact" dynprm="0.02" gaintype="affine" gainprm="1 0 -0.2"/>
+    <velocity name="knee_vel" joint="knee" kv="1.5" forcerange="-0.8 0.8"/>
+    <position name="hip_pos" joint="hip" kp="3" kv="0.5"/>
+  </actuator>
+  <sensor><actuatorfrc actuator="hip_int"/><actuatorfrc actuator="x_fexact"/><jointvel joint="knee"/></sensor>
+</mujoco>
+"""
+
+# RK4 with activation states (the act component of the Runge-Kutta state vector), no contacts
+ZOO_D = """
+<mujoco model="zoo_d">
+  <compiler angle="radian"/>
+  <option timestep="0.004" integrator="RK4"/>
+  <worldbody>
+    <body name="l1" pos="0 0 1">
+      <joint name="j1" type="hinge" axis="0 1 0" damping="0.05"/>
+      <geom type="capsule" fromto="0 0 0 0 0 -0.4" size="0.03" contype="0" conaffinity="0"/>
+      <body name="l2" pos="0 0 -0.4">
+        <joint name="j2" type="hinge" axis="0 1 0" range="-2 2" limited="true"/>
+        <geom type="capsule" fromto="0 0 0 0 0 -0.3" size="0.025" contype="0" conaffinity="0"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <general name="a1" joint="j1" dyntype="integrator" actlimited="true" actrange="-0.3 0.3" gainprm="2"/>
+    <general name="a2" joint="j2" dyntype="filterexact" dynprm="0.05" gainprm="1.5" biastype="affine" biasprm="0 0 -0.1"/>
+  </actuator>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C}
+NOCONTACT = {"zoo_d": ZOO_D}

@@ -23,14 +23,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oxide_control_b200 as ox  # noqa: E402
 import dense_checker as dc  # noqa: E402
 from support import OracleData, random_state  # noqa: E402
-from zoo_models import HOPPER, ZOO  # noqa: E402
+from zoo_models import HOPPER, NOCONTACT, ZOO  # noqa: E402
 
 MODELS = {  # name -> (xml, number of states, apply external forces)
     "pendulum": (ox.models.PENDULUM, 16, False), "cartpole": (ox.models.CARTPOLE, 16, False), "acrobot": (ox.models.ACROBOT, 16, False),
     "cheetah": (ox.models.CHEETAH, 64, False), "humanoid": (ox.models.HUMANOID, 64, False),
     "zoo_a": (ZOO["zoo_a"], 64, True), "zoo_b": (ZOO["zoo_b"], 64, True), "hopper": (HOPPER, 64, True),
+    "zoo_c": (ZOO["zoo_c"], 64, True), "zoo_d": (NOCONTACT["zoo_d"], 16, False),
 }
-OUT_KEYS = ("qpos", "qvel", "qacc", "qfrc_bias", "qfrc_smooth", "qfrc_constraint", "actuator_force")
+OUT_KEYS = ("qpos", "qvel", "act", "qacc", "qfrc_bias", "qfrc_smooth", "qfrc_constraint", "actuator_force")
 
 
 def input_states(model, n, forces, seed=20261018):
@@ -41,6 +42,8 @@ def input_states(model, n, forces, seed=20261018):
     for e in range(n):
         od = OracleData(model)
         od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]
+        if model.na:
+            od.field("act")[:] = rng.uniform(-0.5, 0.5, model.na)
         for s in range(20 + 5 * e if model.nefcmax else e):
             od.fill_ctrl_philox(e, s)
             od.step()
@@ -50,12 +53,13 @@ def input_states(model, n, forces, seed=20261018):
         if forces and e % 2:
             xf = rng.normal(0, 1.0, 6 * model.nbody); xf[:6] = 0
             qf = rng.normal(0, 0.3, model.nv)
-        states.append(dict(qpos=od.field("qpos").copy(), qvel=od.field("qvel").copy(), ctrl=od.field("ctrl").copy(), qfrc_applied=qf, xfrc_applied=xf))
+        states.append(dict(qpos=od.field("qpos").copy(), qvel=od.field("qvel").copy(), ctrl=od.field("ctrl").copy(), qfrc_applied=qf, xfrc_applied=xf,
+                           act=od.field("act").copy()))
     return states
 
 
 def dense_case(dm, st):
-    r = dc.step(dm, st["qpos"], st["qvel"], st["ctrl"], st["qfrc_applied"], st["xfrc_applied"])
+    r = dc.step(dm, st["qpos"], st["qvel"], st["ctrl"], st["qfrc_applied"], st["xfrc_applied"], st["act"])
     out = {k: r[k] for k in OUT_KEYS}
     out.update(ncon=int(r["ncon"]), nefc=int(r["nefc"]), efc_D_sorted=np.sort(r["efc_D"]), efc_aref_sorted=np.sort(r["efc_aref"]),
                con_dist_sorted=np.sort(r["con_dist"]))
