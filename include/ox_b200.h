@@ -94,7 +94,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1) X(dof_Mdense, nvv, 1)               \
   X(geom_type, ngeom, 1) X(geom_bodyid, ngeom, 1) X(geom_contype, ngeom, 1)                        \
   X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
-  X(site_bodyid, nsite, 1)                                                                          \
+  X(site_bodyid, nsite, 1) X(site_type, nsite, 1)                                                   \
   X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1) X(pair_conadr, npair, 1)   \
   X(actuator_trnid, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
   X(actuator_ctrllimited, nu, 1) X(actuator_forcelimited, nu, 1)                                    \
@@ -113,7 +113,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(geom_size, ngeom, 3) X(geom_pos, ngeom, 3) X(geom_quat, ngeom, 4) X(geom_friction, ngeom, 3)   \
   X(geom_solmix, ngeom, 1) X(geom_solref, ngeom, 2) X(geom_solimp, ngeom, 5)                       \
   X(geom_margin, ngeom, 1) X(geom_gap, ngeom, 1)                                                    \
-  X(site_pos, nsite, 3) X(site_quat, nsite, 4)                                                      \
+  X(site_pos, nsite, 3) X(site_quat, nsite, 4) X(site_size, nsite, 3)                               \
   X(pair_friction, npair, 5) X(pair_solref, npair, 2) X(pair_solimp, npair, 5)                     \
   X(pair_margin, npair, 1) X(pair_gap, npair, 1)                                                    \
   X(actuator_gear, nu, 1) X(actuator_gainprm, nu, 3) X(actuator_biasprm, nu, 3)                    \

@@ -1030,6 +1030,51 @@ void bodyAcc(const Model* m, const Data* d, std::vector<double>& cacc) {
   }
 }
 
+// mju_rayGeom restated for the site shapes a touch sensor may have (sphere, capsule, box): distance along `vec` from `pnt` to
+// the nearest intersection with the shape, -1 if the ray misses. Written with explicit candidate lists rather than MuJoCo's
+// in-place minimum so that it can be read against the documentation.
+double rayGeom(const double* pos, const double* mat, const double* size, const double* pnt, const double* vec, int type) {
+  double lp[3], lv[3];
+  for (int k = 0; k < 3; k++) {
+    lp[k] = mat[k] * (pnt[0] - pos[0]) + mat[3 + k] * (pnt[1] - pos[1]) + mat[6 + k] * (pnt[2] - pos[2]);
+    lv[k] = mat[k] * vec[0] + mat[3 + k] * vec[1] + mat[6 + k] * vec[2];
+  }
+  std::vector<double> hits;
+  auto roots = [](double a, double b, double c, double* x) {  // a x^2 + 2 b x + c = 0
+    double det = b * b - a * c;
+    if (det < OX_MINVAL) return false;
+    x[0] = (-b - std::sqrt(det)) / a; x[1] = (-b + std::sqrt(det)) / a;
+    return true;
+  };
+  double x[2];
+  if (type == OX_GEOM_SPHERE) {
+    if (roots(dot3(lv, lv), dot3(lv, lp), dot3(lp, lp) - size[0] * size[0], x)) { if (x[0] >= 0) hits.push_back(x[0]); else if (x[1] >= 0) hits.push_back(x[1]); }
+  } else if (type == OX_GEOM_BOX) {
+    for (int i = 0; i < 3; i++) {
+      if (std::fabs(lv[i]) <= OX_MINVAL) continue;
+      for (double side : {-1.0, 1.0}) {
+        double t = (side * size[i] - lp[i]) / lv[i];
+        int j = (i + 1) % 3, k = (i + 2) % 3;
+        if (t >= 0 && std::fabs(lp[j] + t * lv[j]) <= size[j] && std::fabs(lp[k] + t * lv[k]) <= size[k]) hits.push_back(t);
+      }
+    }
+  } else {  // capsule along z: radius size[0], half-length size[1]
+    if (roots(lv[0] * lv[0] + lv[1] * lv[1], lv[0] * lp[0] + lv[1] * lp[1], lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0], x)) {
+      double t = x[0] >= 0 ? x[0] : (x[1] >= 0 ? x[1] : -1);
+      if (t >= 0 && std::fabs(lp[2] + t * lv[2]) <= size[1]) hits.push_back(t);
+    }
+    for (double side : {-1.0, 1.0}) {
+      double c[3] = {lp[0], lp[1], lp[2] - side * size[1]};
+      if (!roots(dot3(lv, lv), dot3(lv, c), dot3(c, c) - size[0] * size[0], x)) continue;
+      for (int i = 0; i < 2; i++) {
+        double z = lp[2] + x[i] * lv[2];
+        if (x[i] >= 0 && (side > 0 ? z >= size[1] : z <= -size[1])) hits.push_back(x[i]);
+      }
+    }
+  }
+  return hits.empty() ? -1.0 : *std::min_element(hits.begin(), hits.end());
+}
+
 void sensors(const Model* m, Data* d) {
   std::vector<double> slv, cacc;
   for (int s = 0; s < m->nsensor; s++) {
@@ -1043,6 +1088,25 @@ void sensors(const Model* m, Data* d) {
       case OX_SENS_ACTUATORPOS: out[0] = m->actuator_gear[id] * d->qpos[m->jnt_qposadr[m->actuator_trnid[id]]]; break;
       case OX_SENS_ACTUATORVEL: out[0] = m->actuator_gear[id] * d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]; break;
       case OX_SENS_ACTUATORFRC: out[0] = d->actuator_force[id]; break;
+      case OX_SENS_TOUCH: {
+        // mj_sensorAcc / mjSENS_TOUCH: normal forces (mj_contactForce: sum of the pyramid edge forces, or the single row of a
+        // frictionless contact) of contacts on the site's body whose point the site volume contains (ray along the normal)
+        out[0] = 0;
+        int sbody = m->site_bodyid[id];
+        for (int c = 0; c < d->ncon; c++) {
+          int p = d->con_pair[c], b1 = m->geom_bodyid[m->pair_geom1[p]], b2 = m->geom_bodyid[m->pair_geom2[p]];
+          if (sbody != b1 && sbody != b2) continue;
+          double fn = 0;
+          bool has_rows = false;
+          for (int r = 0; r < d->nefc; r++)
+            if (d->efc_type[r] != 0 && d->efc_id[r] == c) { fn += d->efc_force[r]; has_rows = true; }
+          if (!has_rows || fn <= 0) continue;
+          double ray[3] = {d->con_frame[9 * c], d->con_frame[9 * c + 1], d->con_frame[9 * c + 2]};
+          if (sbody == b2) for (double& v : ray) v = -v;
+          if (rayGeom(&d->site_xpos[3 * id], &d->site_xmat[9 * id], m->site_size + 3 * id, &d->con_pos[3 * c], ray, m->site_type[id]) >= 0) out[0] += fn;
+        }
+        break;
+      }
       case OX_SENS_SUBTREECOM: std::memcpy(out, &d->subtree_com[3 * id], 3 * sizeof(double)); break;
       case OX_SENS_SUBTREELINVEL:
         if (slv.empty()) subtreeLinvel(m, d, slv);

@@ -129,7 +129,8 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   X(sensordata, nsd) X(subtree_linvel, 3 * nb)
 
 #define OX_BATCH_INT_FIELDS(X) \
-  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(con_active, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1)
+  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(con_active, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1) \
+  X(con_efcadr, ncm)
 
 template <typename T>
 struct DevBatch {

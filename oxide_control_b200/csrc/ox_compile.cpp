@@ -232,6 +232,8 @@ struct SiteDef {
   std::string name;
   double pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0};
   int body = 0;
+  int type = OX_GEOM_SPHERE;                       // site shapes matter to the touch sensor only (its sensing volume)
+  double size[3] = {0.005, 0.005, 0.005};
 };
 struct JointDef {
   std::string name;
@@ -340,12 +342,16 @@ void parse_site(Builder& B, const XmlElem& e, int body, const std::string& child
   s.name = a.str_or("name", "");
   a.vec("pos", s.pos, 3);
   orientation(B.c, a, s.quat);
+  s.type = geom_type_from(a.str_or("type", "sphere"), e);
+  a.vec("size", s.size, 3, true);
   if (a.has("fromto")) {
     double ft[6];
     a.vec("fromto", ft, 6);
     double v[3] = {ft[0] - ft[3], ft[1] - ft[4], ft[2] - ft[5]};
     for (int i = 0; i < 3; i++) s.pos[i] = 0.5 * (ft[i] + ft[i + 3]);
     hm::z2quat(s.quat, v);
+    const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (s.type == OX_GEOM_CAPSULE || s.type == OX_GEOM_CYLINDER) s.size[1] = len / 2; else s.size[2] = len / 2;
   }
   B.sites.push_back(s);
 }
@@ -882,12 +888,15 @@ ox_model* compile_mjcf(const std::string& xml) {
     M->v_geom_margin[i] = g.margin; M->v_geom_gap[i] = g.gap;
   }
   M->v_site_bodyid.resize(nsite); M->v_site_pos.resize(3 * nsite); M->v_site_quat.resize(4 * nsite);
+  M->v_site_type.resize(nsite); M->v_site_size.resize(3 * nsite);
   for (int i = 0; i < nsite; i++) {
     const SiteDef& s = B.sites[sorder[i]];
     nm[OX_OBJ_SITE][i] = s.name;
     M->v_site_bodyid[i] = s.body;
     std::memcpy(&M->v_site_pos[3 * i], s.pos, 3 * sizeof(double));
     std::memcpy(&M->v_site_quat[4 * i], s.quat, 4 * sizeof(double));
+    M->v_site_type[i] = s.type;
+    std::memcpy(&M->v_site_size[3 * i], s.size, 3 * sizeof(double));
   }
   check_unique(OX_OBJ_BODY, "body"); check_unique(OX_OBJ_JOINT, "joint");
   check_unique(OX_OBJ_GEOM, "geom"); check_unique(OX_OBJ_SITE, "site");
@@ -1096,7 +1105,7 @@ ox_model* compile_mjcf(const std::string& xml) {
               {"subtreecom", OX_SENS_SUBTREECOM, OX_OBJ_BODY, "body", 3},
               {"subtreelinvel", OX_SENS_SUBTREELINVEL, OX_OBJ_BODY, "body", 3},
               {"velocimeter", OX_SENS_VELOCIMETER, OX_OBJ_SITE, "site", 3}, {"gyro", OX_SENS_GYRO, OX_OBJ_SITE, "site", 3},
-              {"accelerometer", OX_SENS_ACCELEROMETER, OX_OBJ_SITE, "site", 3},
+              {"accelerometer", OX_SENS_ACCELEROMETER, OX_OBJ_SITE, "site", 3}, {"touch", OX_SENS_TOUCH, OX_OBJ_SITE, "site", 1},
               {"framepos", OX_SENS_FRAMEPOS, -1, "objname", 3}, {"framequat", OX_SENS_FRAMEQUAT, -1, "objname", 4},
               {"framelinvel", OX_SENS_FRAMELINVEL, -1, "objname", 3}, {"frameangvel", OX_SENS_FRAMEANGVEL, -1, "objname", 3},
               {"clock", OX_SENS_CLOCK, OX_OBJ_UNKNOWN, nullptr, 1},
@@ -1125,6 +1134,11 @@ ox_model* compile_mjcf(const std::string& xml) {
             if ((sp->type == OX_SENS_JOINTPOS || sp->type == OX_SENS_JOINTVEL) &&
                 B.joints[objid].type != OX_JNT_HINGE && B.joints[objid].type != OX_JNT_SLIDE)
               cfail("jointpos/jointvel sensors require a hinge or slide joint");
+            if (sp->type == OX_SENS_TOUCH) {
+              const int st = M->v_site_type[objid];
+              if (st != OX_GEOM_SPHERE && st != OX_GEOM_CAPSULE && st != OX_GEOM_BOX)
+                cfail("touch sensor '" + *on + "': sensing volumes are sphere, capsule or box sites (ellipsoid / cylinder sites are outside the supported subset)");
+            }
           }
           M->v_sensor_type.push_back(sp->type); M->v_sensor_objtype.push_back(objtype); M->v_sensor_objid.push_back(objid);
           M->v_sensor_adr.push_back(adr); M->v_sensor_dim.push_back(sp->dim);

@@ -980,10 +980,12 @@ struct Env {
     const int nv = h.nv;
       const T includemargin = m.pair_margin(p) - m.pair_gap(p);
       const T dist = at(b.con_dist, c);
+      ati(b.con_efcadr, c) = -1;
       if (dist >= includemargin) return;
       const int dim = m.pair_dim(p);
       const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
       const int r0 = nefc;
+      ati(b.con_efcadr, c) = r0;   // contact.efc_address: where this contact's rows start (touch sensor, contact forces)
       nefc += nrow;
       T fri[5];
       OX_LDM(5, fri, pair_friction, 5 * p);
@@ -1411,6 +1413,61 @@ struct Env {
     for (int i = 0; i < nv; i++) at(b.qacc_warmstart, i) = at(b.qacc, i);
   }
 
+  // ============================================================ ray - site volume (mju_rayGeom for sphere / capsule / box)
+  // smallest non-negative root of a x^2 + 2 b x + c = 0 (both roots in xx), -1 if none
+  static OX_HD T ray_quad(T a, T bq, T c, T* xx) {
+    const T det = bq * bq - a * c;
+    if (det < (T)OX_MINVAL) { xx[0] = -1; xx[1] = -1; return -1; }
+    const T sq = ox_sqrt(det);
+    xx[0] = (-bq - sq) / a; xx[1] = (-bq + sq) / a;
+    if (xx[0] >= 0) return xx[0];
+    if (xx[1] >= 0) return xx[1];
+    return -1;
+  }
+  static OX_HD T ray_geom(const T* pos, const T* mat, const T* size, const T* pnt, const T* vec, int type) {
+    const T dif[3] = {pnt[0] - pos[0], pnt[1] - pos[1], pnt[2] - pos[2]};
+    T lp[3], lv[3];   // ray in the site frame
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      lp[k] = mat[k] * dif[0] + mat[3 + k] * dif[1] + mat[6 + k] * dif[2];
+      lv[k] = mat[k] * vec[0] + mat[3 + k] * vec[1] + mat[6 + k] * vec[2];
+    }
+    T xx[2];
+    if (type == OX_GEOM_SPHERE) return ray_quad(dot3(lv, lv), dot3(lv, lp), dot3(lp, lp) - size[0] * size[0], xx);
+    T x = -1;
+    if (type == OX_GEOM_BOX) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        if (ox_abs(lv[i]) > (T)OX_MINVAL) {
+#pragma unroll
+          for (int side = -1; side <= 1; side += 2) {
+            const T sol = ((T)side * size[i] - lp[i]) / lv[i];
+            if (sol >= 0) {
+              const int i0 = (i + 1) % 3, i1 = (i + 2) % 3;
+              const T p0 = lp[i0] + sol * lv[i0], p1 = lp[i1] + sol * lv[i1];
+              if (ox_abs(p0) <= size[i0] && ox_abs(p1) <= size[i1] && (x < 0 || sol < x)) x = sol;
+            }
+          }
+        }
+      }
+      return x;
+    }
+    // capsule: the cylinder between the flat ends, then the outer halves of the two cap spheres
+    T sol = ray_quad(lv[0] * lv[0] + lv[1] * lv[1], lv[0] * lp[0] + lv[1] * lp[1], lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0], xx);
+    if (sol >= 0 && ox_abs(lp[2] + sol * lv[2]) <= size[1]) x = sol;
+#pragma unroll
+    for (int side = -1; side <= 1; side += 2) {
+      const T ld_[3] = {lp[0], lp[1], lp[2] - (T)side * size[1]};
+      ray_quad(dot3(lv, lv), dot3(lv, ld_), dot3(ld_, ld_) - size[0] * size[0], xx);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const T z = lp[2] + xx[i] * lv[2];
+        if (xx[i] >= 0 && (side > 0 ? z >= size[1] : z <= -size[1]) && (x < 0 || xx[i] < x)) x = xx[i];
+      }
+    }
+    return x;
+  }
+
   // ============================================================ sensors (N2 subset)
   OX_HD void obj_frame(int objtype, int id, T* pos, T* mat, int* body) const {
     if (objtype == OX_OBJ_BODY) { ld<3>(pos, b.xipos, 3 * id); ld<9>(mat, b.ximat, 9 * id); *body = id; }
@@ -1531,6 +1588,47 @@ struct Env {
           OX_MLOOP
           for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
           st<3>(b.sensordata, adr, out);
+          break;
+        }
+        case OX_SENS_TOUCH: {
+          // mj_sensorAcc, mjSENS_TOUCH: sum of the normal forces of the contacts that involve the site's body and whose
+          // point lies in the site's volume - decided by a ray from the contact point along the contact normal (flipped
+          // when the sensorised body is the second one), which always hits when the point is inside
+          const int sbody = m.site_bodyid(id);
+          T spos[3], smat[9], ssize[3], total = 0;
+          ld<3>(spos, b.site_xpos, 3 * id);
+          ld<9>(smat, b.site_xmat, 9 * id);
+          OX_LDM(3, ssize, site_size, 3 * id);
+          const int stype = m.site_type(id);
+          auto one = [&](int c, int p) {
+            const int b1 = m.geom_bodyid(m.pair_geom1(p)), b2 = m.geom_bodyid(m.pair_geom2(p));
+            if (sbody != b1 && sbody != b2) return;
+            const int ea = ati(b.con_efcadr, c);
+            if (ea < 0) return;
+            const int dim = m.pair_dim(p);
+            T fn = at(b.efc_force, ea);                                   // frictionless: the row force; pyramid: sum over the edges
+            if (dim > 1) { fn += at(b.efc_force, ea + 1); fn += at(b.efc_force, ea + 2); fn += at(b.efc_force, ea + 3); }
+            if (!(fn > 0)) return;
+            T ray[3], cp[3];
+            ld<3>(ray, b.con_frame, 9 * c);
+            ld<3>(cp, b.con_pos, 3 * c);
+            if (sbody == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+            if (ray_geom(spos, smat, ssize, cp, ray, stype) >= 0) total += fn;
+          };
+          if (STATIC_CON) {
+            OX_MLOOP
+            for (int p = 0; p < h.npair; p++) {
+              OX_MLOOP
+              for (int k = 0; k < m.pair_maxcon(p); k++) {
+                const int c = m.pair_conadr(p) + k;
+                if (ati(b.con_active, c)) one(c, p);
+              }
+            }
+          } else {
+            const int ncon = ati(b.ncon, 0);
+            for (int c = 0; c < ncon; c++) one(c, ati(b.con_pair, c));
+          }
+          at(b.sensordata, adr) = total;
           break;
         }
         case OX_SENS_CLOCK: at(b.sensordata, adr) = at(b.time, 0); break;

@@ -14,6 +14,7 @@ ZOO_A = """
       <freejoint name="boxroot"/>
       <geom name="box" type="box" size="0.15 0.1 0.2" density="400"/>
       <site name="top" pos="0 0 0.2" euler="0 0.3 0"/>
+      <site name="box_sole" type="box" pos="0 0 -0.2" size="0.16 0.11 0.03"/>
       <body name="arm" pos="0.15 0 0.1">
         <joint name="shoulder" type="ball" pos="0 0 0" stiffness="3" damping="0.4"/>
         <geom name="arm" type="capsule" fromto="0 0 0 0.3 0 0" size="0.04"/>
@@ -28,10 +29,13 @@ ZOO_A = """
     <body name="ball" pos="0.6 0.1 0.12">
       <freejoint name="ballroot"/>
       <geom name="ball" type="sphere" size="0.1" priority="1" friction="0.3 0.02 0.002"/>
+      <site name="ball_skin" type="sphere" size="0.13"/>
     </body>
     <body name="rod" pos="-0.5 0 0.06" euler="0 1.5707963 0">
       <freejoint name="rodroot"/>
       <geom name="rod" type="capsule" size="0.05 0.2" solmix="3"/>
+      <site name="rod_skin" type="capsule" size="0.07 0.2"/>
+      <site name="rod_tip" type="sphere" pos="0 0 0.2" size="0.08"/>
       <inertial pos="0 0 0.01" mass="1.5" fullinertia="0.03 0.03 0.004 0.0005 0 0"/>
     </body>
   </worldbody>
@@ -49,6 +53,7 @@ ZOO_A = """
     <framelinvel objtype="site" objname="tip"/> <frameangvel objtype="body" objname="hand"/>
     <velocimeter site="tip"/> <gyro site="top"/> <accelerometer site="tip"/> <accelerometer site="top"/>
     <subtreecom body="boxy"/> <subtreelinvel body="boxy"/> <subtreelinvel body="arm"/> <clock/>
+    <touch site="ball_skin"/> <touch site="rod_skin"/> <touch site="rod_tip"/> <touch site="box_sole"/> <touch site="tip"/>
   </sensor>
 </mujoco>
 """
