@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--ls-iterations", type=int, default=0)
     ap.add_argument("--stage-times", action="store_true", help="also print per-stage device times (staged kernels)")
     ap.add_argument("--no-spec", action="store_true", help="use the generic fused kernel instead of the model-specialised one")
+    ap.add_argument("--ctrl-scale", type=float, default=1.0, help="amplitude of the Philox control stream (power of two; 0.125 = the "
+                    "resting-contact regime of the humanoid)")
     return ap.parse_args()
 
 
@@ -157,9 +159,10 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def cpu_oracle_rate(model, cfgname, steps, warmup, budget_s=20.0):
+def cpu_oracle_rate(model, cfgname, steps, warmup, budget_s=20.0, ctrl_scale=1.0):
     """Times the restated CPU oracle on all host cores on a bounded sample of the workload."""
     from support import oracle_bench, oracle_lib
+    oracle_lib().oxo_set_ctrl_scale(C.c_double(ctrl_scale))
     threads = max(1, oracle_lib().oxo_hardware_threads())
     q, v = initial_state(model, 2 * threads, 0, 2 * threads)
     sec, _ = oracle_bench(model, q, v, 20, threads)  # calibration (also warms the threads)
@@ -187,7 +190,7 @@ def run_reference(args, rank, world):
     cfg = ox.models.CONFIGS[args.config]
     model = ox.Model.from_xml_string(cfg["xml"])
     t0 = time.time()
-    base, nenv_s = cpu_oracle_rate(model, args.config, args.steps, args.warmup, budget_s=60.0)
+    base, nenv_s = cpu_oracle_rate(model, args.config, args.steps, args.warmup, budget_s=60.0, ctrl_scale=args.ctrl_scale)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"] / max(1, args.steps), "higher_is_better": True,
@@ -213,6 +216,7 @@ def main():
     import torch.distributed as dist
     import oxide_control_b200 as ox
     from oxide_control_b200 import _abi as A
+    from oxide_control_b200 import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -228,10 +232,13 @@ def main():
 
     b = ox.BatchedPhysics(model, nenv, precision=precision, device=local_rank, mode=args.mode, env_id_offset=rank * nenv,
                           block_threads=args.block, lanes_per_warp=args.lanes, iterations=args.iterations, ls_iterations=args.ls_iterations, specialize=not args.no_spec)
-    qpos, qvel = initial_state(model, world * nenv, rank * nenv, (rank + 1) * nenv)
+    lo, hi = sharding.shard_range(rank, world, nenv)   # global env ids of this rank: they key the Philox control stream
+    qpos, qvel = initial_state(model, world * nenv, lo, hi)
     b.set("qpos", qpos)
     b.set("qvel", qvel)
     b.ctrl_philox(True, SEED)
+    if args.ctrl_scale != 1.0:
+        b.ctrl_philox_scale(args.ctrl_scale)
     stream = torch.cuda.ExternalStream(A.lib().ox_batch_stream(b.handle), device=local_rank)
     flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -242,18 +249,11 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+        return sharding.max_over_ranks(x, device="cuda")   # NCCL all-reduce(MAX) of one double; the only collectives of the job are
+                                                           # these report-boundary reductions (none touches the step)
     def sum_over_ranks(vec):
-        if world == 1:
-            return vec
-        t = torch.tensor(vec, dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return [float(x) for x in t.tolist()]
+        tot = sharding.gather_stats(dict(zip(("sum_ncon", "sum_nefc", "sum_niter", "diverged"), vec)), device="cuda")
+        return [tot[k] for k in ("sum_ncon", "sum_nefc", "sum_niter", "diverged")]
 
     # ---------------- device-resident throughput: W warm-up steps, then exactly K timed steps
     b.step(W)
@@ -379,27 +379,34 @@ def main():
     alg_bytes = algorithmic_bytes_per_env_step(model, real_bytes) * nenv
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
     flops = algorithmic_flops_per_env_step(model, mean_ncon, mean_nefc, mean_iter)
-    fp_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12 * (0.5 if precision == "f64" else 1.0)
+    fp_nominal = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12 * (0.5 if precision == "f64" else 1.0)
+    fp_peak = ox.measure_fma_peak(local_rank, precision)   # measured on this GPU, now: register-resident FMA chains on every SM
     fp_achieved = flops * nenv / (step_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as f:
-                traffic = json.load(f).get(f"{args.config}_{precision}_{nenv}")
-        except Exception:
-            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_source": f"{peak_src} copy bandwidth (burst)", "kernel": (f"k_step_spec<Spec_{args.config},{precision}>" if b.kernel_name() == args.config else f"{b.kernel_name()} <{precision}>"),
+                "peak_source": f"{peak_src} copy bandwidth (burst)", "kernel": (f"k_step_spec<Spec_{args.config},{precision}>" if b.kernel_name() == args.config else f"{b.kernel_name()} <{precision}>"),
                 "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(model, real_bytes),
-                "fp_model_flops_per_env_step": flops, "fp_achieved_tflops": fp_achieved, "fp_peak_tflops_nominal": fp_peak,
-                "fp_frac": fp_achieved / fp_peak,
+                "fp_model_flops_per_env_step": flops, "fp_achieved_tflops": fp_achieved, "fp_peak_tflops_measured": fp_peak,
+                "fp_peak_tflops_nominal": fp_nominal, "fp_frac": fp_achieved / fp_peak,
                 "note": "latency/issue-bound physics: both fractions are small by construction (SURVEY 8d)"}
+    # per-launch DRAM traffic and issue-slot utilisation of the same kernel from the committed ncu capture (profiles/ncu_summary.json,
+    # written by tools/ncu_summary.py from an `ncu --set full` report); the keys are present only for configurations that were captured
+    spath = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    roofline["traffic"] = None
+    if os.path.exists(spath):
+        try:
+            with open(spath) as f:
+                cap = json.load(f).get(f"{args.config}_{precision}_{nenv}")
+            if cap:
+                roofline["traffic"] = cap.get("dram_bytes_per_launch")
+                roofline["issue_slot_util_pct_ncu"] = cap.get("issue_active_pct")
+                roofline["ncu_source"] = cap.get("source")
+        except Exception:
+            pass
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_oracle_rate(model, args.config, min(K, 200), min(W, 100), budget_s=15.0)
+        cpu, _ = cpu_oracle_rate(model, args.config, min(K, 200), min(W, 100), budget_s=15.0, ctrl_scale=args.ctrl_scale)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "mean_ncon", "mean_nefc", "mean_solver_iters")}
 
     stage_times = b.stage_times(5) if args.stage_times else None
@@ -410,7 +417,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": precision, "data": "synthetic",
-            "config": {"workload": f"{cfg['label']}: {nenv} envs per GPU, fresh Philox U(-1,1) controls every step, "
+            "config": {"workload": f"{cfg['label']}: {nenv} envs per GPU, fresh Philox {args.ctrl_scale:g}*U(-1,1) controls every step, "
                                    f"{'RK4' if model.integrator == 1 else 'Euler'}, Newton solver, mode={args.mode}, kernel={b.kernel_name()}",
                        "envs_per_gpu": nenv, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "none (state resident by design)" if args.no_flush else

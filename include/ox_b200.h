@@ -207,6 +207,9 @@ OX_API ox_status ox_batch_sync(ox_batch* b);
  * (seed, global env id, step, actuator) generated on device. enable=0 returns to user ctrl. */
 OX_API ox_status ox_batch_ctrl_philox(ox_batch* b, int32_t enable, uint64_t seed);
 OX_API ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step);
+/* amplitude of the Philox control stream: ctrl = scale * U(-1,1) (default 1). Use a power of two to keep the CPU fp64 and
+ * GPU fp32 control values bit-identical. 0.125 lets the humanoid settle into resting contact (ncon ~ 10) instead of thrashing. */
+OX_API ox_status ox_batch_ctrl_philox_scale(ox_batch* b, double scale);
 
 /* field ids for bulk / per-env access */
 enum {
@@ -320,6 +323,29 @@ OX_API ox_status ox_env_step(ox_env* e, const void* action, void* obs, void* rew
 /* episode bookkeeping since creation: out[0] = finished episodes, out[1] = sum of their returns,
  * out[2] = sum of their lengths (env steps) */
 OX_API ox_status ox_env_stats(ox_env* e, double* out3);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one batch per device of the box driven from ONE host process - what a Rust host needs to use all
+ * 8 GPUs without Python. Envs shard by global env id (rank r owns [env_id_offset + r*nenv, env_id_offset + (r+1)*nenv)),
+ * one host thread per device issues its launches, no data-path collective exists. ox_group_stats is the only exchange:
+ * 4 doubles per GPU summed by ncclAllReduce over NVLink (libnccl.so.2 via dlopen; host-side sum when NCCL is absent).
+ * cfg->nenv = envs PER DEVICE; cfg->device is ignored; devices = NULL means ordinals 0..ndevices-1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ox_group ox_group;
+OX_API ox_status ox_group_create(const ox_model* m, const ox_batch_config* cfg, int32_t ndevices, const int32_t* devices_or_null, ox_group** out);
+OX_API void ox_group_free(ox_group* g);
+OX_API int32_t ox_group_size(const ox_group* g);
+OX_API ox_batch* ox_group_batch(ox_group* g, int32_t rank);   /* borrowed: per-device I/O goes through the ox_batch_* calls */
+OX_API ox_status ox_group_step(ox_group* g, int32_t nsteps);  /* asynchronous on every device's stream */
+OX_API ox_status ox_group_sync(ox_group* g);
+OX_API ox_status ox_group_reset(ox_group* g);
+OX_API ox_status ox_group_ctrl_philox(ox_group* g, int32_t enable, uint64_t seed);
+OX_API ox_status ox_group_stats(ox_group* g, double* out4);   /* totals over all devices, same layout as ox_batch_stats */
+OX_API const char* ox_group_stats_backend(const ox_group* g); /* "nccl" or "host" */
+
+/* Measurement aid (bench.py roofline): peak FMA throughput of the device's CUDA cores in TFLOP/s, measured with a
+ * register-resident multiply-add kernel (8 independent chains per thread, every SM full), fp32 or fp64. */
+OX_API ox_status ox_measure_fma_peak(int32_t device, int32_t precision, double* tflops);
 
 #ifdef __cplusplus
 }

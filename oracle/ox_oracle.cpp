@@ -1318,12 +1318,13 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 inline double ctrl_from_bits(uint32_t x) {  // U(-1,1) on a 2^-23 lattice: exact in fp32 and fp64
   return (double)(int64_t)(((uint64_t)(x >> 9) * 2 + 1)) * (1.0 / 8388608.0) - 1.0;
 }
+double g_ctrl_scale = 1.0;  // amplitude of the benchmark control stream (oxo_set_ctrl_scale); a power of two keeps it exact in fp32
 void fillCtrlPhilox(const Model* m, Data* d, uint64_t seed, int64_t genv, int64_t stepno) {
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   for (int g = 0; g * 4 < m->nu; g++) {
     uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)((uint64_t)genv >> 32), (uint32_t)stepno, (uint32_t)g}, out[4];
     philox4x32_10(ctr, key, out);
-    for (int k = 0; k < 4 && g * 4 + k < m->nu; k++) d->ctrl[g * 4 + k] = ctrl_from_bits(out[k]);
+    for (int k = 0; k < 4 && g * 4 + k < m->nu; k++) d->ctrl[g * 4 + k] = g_ctrl_scale * ctrl_from_bits(out[k]);
   }
 }
 
@@ -1361,6 +1362,7 @@ OXO_API void oxo_step(const Model* m, oxo_data* d) { step(m, d); }
 OXO_API void oxo_fill_ctrl_philox(const Model* m, oxo_data* d, uint64_t seed, int64_t genv, int64_t stepno) {
   fillCtrlPhilox(m, d, seed, genv, stepno);
 }
+OXO_API void oxo_set_ctrl_scale(double s) { g_ctrl_scale = s; }
 OXO_API void oxo_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 
 // individual stages, in pipeline order

@@ -6,7 +6,7 @@ models of BASELINE.json's configs (models). Importing the package loads the shar
 loudly if it has not been built; there is no fallback implementation.
 """
 from . import _abi
-from .physics import (BatchedPhysics, Physics, Model, Actuators, ObjectId, obj, joint, Error, MujocoError, MjsError,
+from .physics import (BatchedPhysics, PhysicsGroup, measure_fma_peak, Physics, Model, Actuators, ObjectId, obj, joint, Error, MujocoError, MjsError,
                       NameNotFound, PhysicsDiverged, JointTypeNotMatch, CudaError)
 from .environment import Task, Observation, Action, Environment, TimeStep, TaskSpec, BatchedEnvironment, BatchedTimeStep
 from . import models
@@ -15,6 +15,6 @@ _abi.lib()  # fail loudly at import time when the extension is missing
 
 mjMAXVAL = 1e10
 mjMINVAL = 1e-15
-__all__ = ["BatchedPhysics", "Physics", "Model", "Actuators", "ObjectId", "obj", "joint", "Error", "MujocoError", "MjsError",
+__all__ = ["BatchedPhysics", "PhysicsGroup", "measure_fma_peak", "Physics", "Model", "Actuators", "ObjectId", "obj", "joint", "Error", "MujocoError", "MjsError",
            "NameNotFound", "PhysicsDiverged", "JointTypeNotMatch", "CudaError", "models", "mjMAXVAL", "mjMINVAL",
            "Task", "Observation", "Action", "Environment", "TimeStep", "TaskSpec", "BatchedEnvironment", "BatchedTimeStep"]

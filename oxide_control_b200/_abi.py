@@ -95,6 +95,18 @@ SYMBOLS = {
     "ox_batch_sync": (C.c_int32, [_P]),
     "ox_batch_ctrl_philox": (C.c_int32, [_P, C.c_int32, C.c_uint64]),
     "ox_batch_set_step_counter": (C.c_int32, [_P, C.c_int64]),
+    "ox_batch_ctrl_philox_scale": (C.c_int32, [_P, C.c_double]),
+    "ox_group_create": (C.c_int32, [_P, C.POINTER(BatchConfig), C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P)]),
+    "ox_group_free": (None, [_P]),
+    "ox_group_size": (C.c_int32, [_P]),
+    "ox_group_batch": (_P, [_P, C.c_int32]),
+    "ox_group_step": (C.c_int32, [_P, C.c_int32]),
+    "ox_group_sync": (C.c_int32, [_P]),
+    "ox_group_reset": (C.c_int32, [_P]),
+    "ox_group_ctrl_philox": (C.c_int32, [_P, C.c_int32, C.c_uint64]),
+    "ox_group_stats": (C.c_int32, [_P, C.POINTER(C.c_double)]),
+    "ox_group_stats_backend": (C.c_char_p, [_P]),
+    "ox_measure_fma_peak": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "ox_batch_field_size": (C.c_int32, [_P, C.c_int32]),
     "ox_batch_state_size": (C.c_int32, [_P]),
     "ox_batch_get_state": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),

@@ -37,7 +37,7 @@ __global__ void k_step_fused(const unsigned char* __restrict__ gblob, int bytes,
   Env<T> env(m, b, e);
   const long long step0 = a.d_step ? *a.d_step : a.step0;
   for (int s = 0; s < a.nsteps; s++) {
-    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
+    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s, (T)a.ctrl_scale);
     env.step();
   }
 }
@@ -57,7 +57,7 @@ __global__ void k_stage(const unsigned char* __restrict__ gblob, int bytes, DevB
   const int e = env_index(b);
   if (e < 0) return;
   Env<T> env(m, b, e);
-  if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, a.d_step ? *a.d_step : a.step0);
+  if (STAGE == ST_CTRL) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, a.d_step ? *a.d_step : a.step0, (T)a.ctrl_scale);
   if (STAGE == ST_CHECK) {
     if (env.bad_state()) { env.reset_data(); env.ati(b.diverged, 0) += 1; }
   }
@@ -163,7 +163,7 @@ cudaError_t launch_spec(ox_batch* b, int phase, const StepArgs& a) {
 StepArgs make_args(ox_batch* b, int nsteps) {
   StepArgs a;
   a.nsteps = nsteps; a.philox = b->philox; a.seed = b->seed; a.env_id_offset = b->cfg.env_id_offset;
-  a.step0 = b->h_step; a.d_step = nullptr; a.applied = b->applied;
+  a.step0 = b->h_step; a.d_step = nullptr; a.applied = b->applied; a.ctrl_scale = b->ctrl_scale;
   a.io_ctrl = b->io_ctrl; a.io_qpos = b->io_qpos; a.io_qvel = b->io_qvel; a.io_f64 = b->io_f64;
   return a;
 }
@@ -633,6 +633,13 @@ ox_status ox_batch_ctrl_philox(ox_batch* b, int32_t enable, uint64_t seed) {
   b->philox = enable ? 1 : 0;
   if (b->seed != seed) drop_graph(b);
   b->seed = seed;
+  return OX_OK;
+}
+
+ox_status ox_batch_ctrl_philox_scale(ox_batch* b, double scale) {
+  if (!b || !(scale > 0)) { ox::set_error("ox_batch_ctrl_philox_scale: bad argument"); return OX_ERR_INVALID; }
+  if ((float)scale != b->ctrl_scale) drop_graph(b);
+  b->ctrl_scale = (float)scale;
   return OX_OK;
 }
 

@@ -31,6 +31,7 @@ struct ox_batch {
   long long* d_step = nullptr;   // device copy, read only by a captured CUDA graph (staged mode)
   long long d_step_val = 0;      // what *d_step holds (host's view)
   bool derived_stale = false;    // see field_live() below
+  float ctrl_scale = 1.0f;       // amplitude of the Philox control stream
   int applied = 0;               // a user wrote qfrc_applied / xfrc_applied since the last full reset
   void* d_tmp = nullptr;  // staging for bulk I/O
   size_t d_tmp_bytes = 0;

@@ -29,6 +29,7 @@ struct StepArgs {
   // 0: no user of this batch has written qfrc_applied / xfrc_applied since the last full reset, so the step neither loads
   // nor tests them (they are 57 of the cheetah's 128 words read per env-step, all zero in an RL loop)
   int applied = 1;
+  float ctrl_scale = 1.0f;  // Philox controls are ctrl_scale * U(-1,1); powers of two keep CPU fp64 and GPU fp32 bit-identical
   // ox_batch_step_io: env-major user buffers (device memory or pinned host memory addressed over PCIe) that the step
   // kernel itself reads the controls from and writes the new state to - no separate layout-conversion launches
   const void* io_ctrl = nullptr;
@@ -144,7 +145,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #pragma unroll
     for (int i = 0; i < H::nv; i++) loc_qacc[i] = 0;
     for (int s = 0; s < a.nsteps; s++) {
-      if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s);
+      if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0 + s, (T)a.ctrl_scale);
       env.step();
     }
     // ---- algorithmic writes: qpos, qvel, qacc, qacc_warmstart, time (+ sensordata, ctrl actually applied, counters)
@@ -164,7 +165,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     G(acc_ncon, 0) = loc_acc_ncon[0]; G(acc_nefc, 0) = loc_acc_nefc[0]; G(acc_niter, 0) = loc_acc_niter[0];
   } else if constexpr (PHASE == 1) {
     load_inputs();
-    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0);
+    if (a.philox) env.fill_ctrl_philox(a.seed, a.env_id_offset + e, step0, (T)a.ctrl_scale);
     const bool did_reset = env.bad_state();
     if (did_reset) { env.reset_data(); loc_diverged[0] += 1; }
     env.fwd_position();

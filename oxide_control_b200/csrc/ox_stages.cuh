@@ -1840,7 +1840,7 @@ struct Env {
     for (int i = 0; i < h.nv; i++) bad |= ox_bad(at(b.qacc, i));
     return bad;
   }
-  OX_HD void fill_ctrl_philox(uint64_t seed, int64_t genv, int64_t stepno) const {
+  OX_HD void fill_ctrl_philox(uint64_t seed, int64_t genv, int64_t stepno, T scale = (T)1) const {
     const int nu = m.h().nu;
     OX_MLOOP
     for (int g = 0; g * 4 < nu; g++) {
@@ -1849,7 +1849,7 @@ struct Env {
                     (uint32_t)(seed >> 32), out);
       OX_MLOOP
       for (int k = 0; k < 4 && g * 4 + k < nu; k++)
-        at(b.ctrl, g * 4 + k) = (T)(int32_t)((out[k] >> 9) * 2u + 1u) * (T)(1.0 / 8388608.0) - (T)1;
+        at(b.ctrl, g * 4 + k) = scale * ((T)(int32_t)((out[k] >> 9) * 2u + 1u) * (T)(1.0 / 8388608.0) - (T)1);
     }
   }
   OX_HD void accumulate_stats() const {

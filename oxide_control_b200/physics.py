@@ -201,9 +201,17 @@ class BatchedPhysics:
     def from_xml_string(xml: str, nenv: int, **kw) -> "BatchedPhysics":
         return BatchedPhysics(Model.from_xml_string(xml), nenv, **kw)
 
+    @classmethod
+    def _borrowed(cls, handle, model: Model, nenv: int, precision: str) -> "BatchedPhysics":
+        """View of a batch owned by someone else (a PhysicsGroup): never freed from here."""
+        self = cls.__new__(cls)
+        self.model, self.nenv, self.precision, self._h, self._owned = model, nenv, precision, C.c_void_p(handle), False
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            A.lib().ox_batch_free(self._h)
+            if getattr(self, "_owned", True):
+                A.lib().ox_batch_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -257,6 +265,9 @@ class BatchedPhysics:
 
     def ctrl_philox(self, enable: bool, seed: int = 0x0B200) -> None:
         _check(A.lib().ox_batch_ctrl_philox(self._h, int(enable), seed))
+
+    def ctrl_philox_scale(self, scale: float) -> None:
+        _check(A.lib().ox_batch_ctrl_philox_scale(self._h, float(scale)))
 
     def set_step_counter(self, step: int) -> None:
         _check(A.lib().ox_batch_set_step_counter(self._h, step))
@@ -380,6 +391,63 @@ class BatchedPhysics:
 
 
 # ---------------------------------------------------------------- single-env handle (src/physics.rs)
+class PhysicsGroup:
+    """One batch per GPU of the box, driven from this one process (ox_group_* in include/ox_b200.h): envs shard by global
+    env id, one host thread per device issues its launches, the only exchange is the NCCL all-reduce of 4 statistics."""
+
+    def __init__(self, model: Model, nenv_per_device: int, ndevices: int, *, precision: str = "f32", devices: Optional[Sequence[int]] = None,
+                 env_id_offset: int = 0, specialize: int = 1, mode: str = "fused"):
+        cfg = A.BatchConfig()
+        A.lib().ox_batch_config_default(C.byref(cfg))
+        cfg.nenv, cfg.precision, cfg.env_id_offset = nenv_per_device, {"f32": A.F32, "f64": A.F64}[precision], env_id_offset
+        cfg.specialize, cfg.mode = int(specialize), {"fused": A.MODE_FUSED, "staged": A.MODE_STAGED}[mode]
+        devs = (C.c_int32 * ndevices)(*devices) if devices is not None else None
+        self.model, self._h = model, C.c_void_p()
+        _check(A.lib().ox_group_create(model.handle, C.byref(cfg), ndevices, devs, C.byref(self._h)))
+        self.size = A.lib().ox_group_size(self._h)
+        self.batches = [BatchedPhysics._borrowed(A.lib().ox_group_batch(self._h, r), model, nenv_per_device, precision) for r in range(self.size)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for b in self.batches:
+                b._h = None
+            A.lib().ox_group_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, nsteps: int = 1) -> None:
+        _check(A.lib().ox_group_step(self._h, nsteps))
+
+    def sync(self) -> None:
+        _check(A.lib().ox_group_sync(self._h))
+
+    def reset(self) -> None:
+        _check(A.lib().ox_group_reset(self._h))
+
+    def ctrl_philox(self, enable: bool, seed: int = 0x0B200) -> None:
+        _check(A.lib().ox_group_ctrl_philox(self._h, int(enable), seed))
+
+    def stats(self) -> dict:
+        out = (C.c_double * 4)()
+        _check(A.lib().ox_group_stats(self._h, out))
+        return {"sum_ncon": out[0], "sum_nefc": out[1], "sum_niter": out[2], "diverged": out[3]}
+
+    def stats_backend(self) -> str:
+        return A.lib().ox_group_stats_backend(self._h).decode()
+
+
+def measure_fma_peak(device: int = 0, precision: str = "f32") -> float:
+    """Measured FMA peak of the device's CUDA cores, TFLOP/s (ox_measure_fma_peak)."""
+    out = C.c_double()
+    _check(A.lib().ox_measure_fma_peak(device, A.F64 if precision == "f64" else A.F32, C.byref(out)))
+    return out.value
+
+
 class Actuators:
     """src/physics.rs:65-79: the only thing an Action may touch."""
 

@@ -49,6 +49,7 @@ def oracle_lib() -> C.CDLL:
         L.oxo_bench.restype = C.c_double
         L.oxo_bench.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, P, P, P]
         L.oxo_hardware_threads.restype = C.c_int32
+        L.oxo_set_ctrl_scale.argtypes = [C.c_double]
         _oracle = L
     return _oracle
 
