@@ -153,7 +153,9 @@ ox_status ox_group_create(const ox_model* m, const ox_batch_config* cfg, int32_t
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); ox::set_error("ox_group_create: no CUDA device available; libox_b200 has no CPU fallback"); return OX_ERR_CUDA; }
-  if (ndevices > ndev) { ox::set_error("ox_group_create: " + std::to_string(ndevices) + " devices requested, " + std::to_string(ndev) + " visible"); return OX_ERR_INVALID; }
+  if (!devices && ndevices > ndev) { ox::set_error("ox_group_create: " + std::to_string(ndevices) + " devices requested, " + std::to_string(ndev) + " visible"); return OX_ERR_INVALID; }
+  for (int r = 0; devices && r < ndevices; r++)
+    if (devices[r] < 0 || devices[r] >= ndev) { ox::set_error("ox_group_create: bad device ordinal " + std::to_string(devices[r])); return OX_ERR_INVALID; }
   std::unique_ptr<ox_group, void (*)(ox_group*)> g(new ox_group, ox_group_free);
   g->batches.assign(ndevices, nullptr);
   g->d_stats.assign(ndevices, nullptr);
@@ -173,7 +175,9 @@ ox_status ox_group_create(const ox_model* m, const ox_batch_config* cfg, int32_t
     return OX_OK;
   });
   if (s) return s;
-  if (ndevices > 1 && nccl().ok()) {
+  bool distinct = true;   // an explicit device list may repeat an ordinal (several shards on one GPU): NCCL needs one rank per device
+  for (int r = 0; r < ndevices; r++) for (int q = 0; q < r; q++) distinct &= devs[q] != devs[r];
+  if (ndevices > 1 && distinct && nccl().ok()) {
     g->comms.assign(ndevices, nullptr);
     const int rc = nccl().CommInitAll(g->comms.data(), ndevices, devs.data());
     if (rc != 0) g->comms.clear();   // fall back to the host sum; not an error

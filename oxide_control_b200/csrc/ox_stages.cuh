@@ -840,6 +840,16 @@ struct Env {
         T pos1[3], pos2[3];
         ld<3>(pos1, b.geom_xpos, 3 * g1);
         ld<3>(pos2, b.geom_xpos, 3 * g2);
+        if (t1 != OX_GEOM_PLANE) {
+          // bounding-sphere cull (what mj_collision's broadphase does): every point of a sphere / capsule lies within
+          // rbound = radius (+ half length) of its centre, so centres further apart than rbound1 + rbound2 + margin cannot
+          // produce a contact. Conservative (a hair of slack for round-off; the exact test follows when it does not fire),
+          // so the contact set is unchanged - but the capsule-capsule narrowphase is ~1 k instructions per pair, and for a
+          // humanoid's 20 self-collision pairs, almost always far apart, it was 43 % of the PRE kernel's instruction stream.
+          const T rb = size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0) + size2[0] + (t2 == OX_GEOM_CAPSULE ? size2[1] : (T)0) + margin;
+          const T dx = pos2[0] - pos1[0], dy = pos2[1] - pos1[1], dz = pos2[2] - pos1[2];
+          if (dx * dx + dy * dy + dz * dz > rb * rb * (T)1.0005 + (T)1e-9) continue;
+        }
         if (t1 == OX_GEOM_PLANE) {
           T n[3] = {at(b.geom_xmat, 9 * g1 + 2), at(b.geom_xmat, 9 * g1 + 5), at(b.geom_xmat, 9 * g1 + 8)};
           if (t2 == OX_GEOM_SPHERE) {

@@ -10,7 +10,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "libox_oracle.so")
-HOSTCHECK_SO = os.path.join(ROOT, "tests", "native", "libox_hostcheck.so")
+HOSTCHECK_SO = os.environ.get("OX_HOSTCHECK_SO") or os.path.join(ROOT, "tests", "native", "libox_hostcheck.so")   # the ASan build via tools/host_sanitizer_run.sh
+if not os.path.isabs(HOSTCHECK_SO):
+    HOSTCHECK_SO = os.path.join(ROOT, HOSTCHECK_SO)
 
 SEED = 0x0B200
 
