@@ -299,7 +299,7 @@ def main():
         nu, nq, nv = model.nu, model.nq, model.nv
         npool = 8
         rng = np.random.default_rng(7 + rank)
-        ctrl_pool = [torch.from_numpy(rng.uniform(-1, 1, (nenv, nu)).astype(np.float32)).pin_memory() for _ in range(npool)]
+        ctrl_pool = [torch.from_numpy((args.ctrl_scale * rng.uniform(-1, 1, (nenv, nu))).astype(np.float32)).pin_memory() for _ in range(npool)]
         obs_q = torch.empty((nenv, nq), dtype=torch.float32).pin_memory()
         obs_v = torch.empty((nenv, nv), dtype=torch.float32).pin_memory()
         b.ctrl_philox(False, SEED)
