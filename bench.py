@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--config", default="cheetah", choices=["pendulum", "cartpole", "acrobot", "cheetah", "humanoid"])
     ap.add_argument("--nenv", type=int, default=0, help="envs per GPU (0 = the BASELINE config's)")
     ap.add_argument("--precision", default="", choices=["", "f32", "f64"])
-    ap.add_argument("--mode", default="fused", choices=["fused", "staged"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "staged", "coop"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")

@@ -163,13 +163,15 @@ enum { OX_F32 = 0, OX_F64 = 1 };
 enum { OX_MEM_HOST = 0, OX_MEM_DEVICE = 1 };
 enum { OX_LAYOUT_ENV_MAJOR = 0 /* [env][elem] (AoS, what a Vec<mjData> would give) */,
        OX_LAYOUT_ELEM_MAJOR = 1 /* [elem][env] (native SoA) */ };
-enum { OX_MODE_FUSED = 0 /* one launch per step */, OX_MODE_STAGED = 1 /* one launch per mj_step stage */ };
+enum { OX_MODE_FUSED = 0 /* one launch per step, one thread per env */, OX_MODE_STAGED = 1 /* one launch per mj_step stage */,
+       OX_MODE_COOP = 2 /* one launch per step, one lane group (16 / 32 lanes) per env, intermediates in shared memory:
+                           any model with nv <= 32, Newton solver, Euler / implicitfast (csrc/ox_coop.cu) */ };
 
 typedef struct ox_batch_config {
   int32_t nenv;
   int32_t device;        /* CUDA ordinal */
   int32_t precision;     /* OX_F32 throughput mode | OX_F64 validation mode */
-  int32_t mode;          /* OX_MODE_FUSED | OX_MODE_STAGED */
+  int32_t mode;          /* OX_MODE_FUSED | OX_MODE_STAGED | OX_MODE_COOP */
   int32_t iterations;    /* solver iteration cap; 0 = model's <option iterations> */
   int32_t ls_iterations; /* line-search iteration cap; 0 = model's */
   int32_t use_graph;     /* capture the per-step launch sequence in a CUDA graph */

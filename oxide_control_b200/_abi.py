@@ -22,7 +22,7 @@ OBJ_EQUALITY, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_PLUGIN = 17, 19, 20, 25
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_ENV_MAJOR, LAYOUT_ELEM_MAJOR = 0, 1
-MODE_FUSED, MODE_STAGED = 0, 1
+MODE_FUSED, MODE_STAGED, MODE_COOP = 0, 1, 2
 INT_EULER, INT_RK4, INT_IMPLICIT, INT_IMPLICITFAST = 0, 1, 2, 3
 
 _REAL_FIELDS = [

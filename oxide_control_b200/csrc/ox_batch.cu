@@ -127,6 +127,12 @@ namespace ox {
 cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax);
 cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int nefcmax);
 cudaError_t solve_coop_prepare(int blob_bytes, bool f64);  // per-device opt-in to > 48 KB dynamic shared memory
+// cooperative whole-step kernel (ox_coop.cu)
+bool step_coop_eligible(const ox_model_tables& t);
+size_t step_coop_smem(const ox_model_tables& t, int blob_bytes, bool f64);
+cudaError_t step_coop_prepare(const ox_model_tables& t, int blob_bytes, bool f64);
+cudaError_t launch_step_coop_f32(cudaStream_t s, const ox_model_tables& t, const unsigned char* blob, int bytes, const DevBatch<float>& g, const StepArgs& a);
+cudaError_t launch_step_coop_f64(cudaStream_t s, const ox_model_tables& t, const unsigned char* blob, int bytes, const DevBatch<double>& g, const StepArgs& a);
 bool solve_coop_eligible(const ox_model_tables& t);
 size_t solve_coop_smem(int blob_bytes, bool f64);
 }  // namespace ox
@@ -199,6 +205,15 @@ ox_status launch_staged_step(ox_batch* b, bool capturing = false) {
 
 template <typename T>
 ox_status do_step(ox_batch* b, int nsteps) {
+  if (b->cfg.mode == OX_MODE_COOP) {
+    const StepArgs a = make_args(b, nsteps);
+    b->launches++;
+    b->derived_stale = true;   // intermediates stay in shared memory; rows / contacts use an env-contiguous layout in this mode
+    if (sizeof(T) == 8) CU_TRY(launch_step_coop_f64(b->stream, b->model->t, b->d_blob, b->blob_bytes, b->bd, a));
+    else CU_TRY(launch_step_coop_f32(b->stream, b->model->t, b->d_blob, b->blob_bytes, b->bf, a));
+    if (b->philox) b->h_step += nsteps;
+    return OX_OK;
+  }
   if (b->cfg.mode == OX_MODE_FUSED) {
     if (b->spec && b->split) {
       // specialised PRE -> warp-cooperative Newton solve -> specialised POST, one step at a time
@@ -472,6 +487,11 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     ox::set_error("ox_batch_create: coop_solver needs mode=staged, the Newton solver, nv <= 32 and model tables + solver scratch within 200 KB of shared memory");
     return OX_ERR_INVALID;
   }
+  if (cfg->mode == OX_MODE_COOP) {
+    if (!ox::step_coop_eligible(t)) { ox::set_error("ox_batch_create: mode = coop needs nv <= 32, the Newton solver and the Euler or implicitfast integrator"); return OX_ERR_INVALID; }
+    if (ox::step_coop_smem(t, b->blob_bytes, b->f64) > 227 * 1024) { ox::set_error("ox_batch_create: mode = coop: model tables + per-env intermediates exceed shared memory"); return OX_ERR_INVALID; }
+    CU_TRY(ox::step_coop_prepare(t, b->blob_bytes, b->f64));
+  }
   if (cfg->mode == OX_MODE_FUSED && cfg->specialize != 0) {
     b->spec = ox::find_spec(ox::model_hash(t));
     if (b->spec && !b->spec->has_phase(b->f64, 0)) b->spec = nullptr;
@@ -536,6 +556,7 @@ void* ox_batch_stream(const ox_batch* b) { return b ? (void*)b->stream : nullptr
 int64_t ox_batch_launch_count(const ox_batch* b) { return b ? b->launches : -1; }
 const char* ox_batch_kernel_name(const ox_batch* b) {
   if (!b) return nullptr;
+  if (b->cfg.mode == OX_MODE_COOP) return "k_step_coop (lane group per env, generic)";
   if (b->cfg.mode != OX_MODE_FUSED) return b->coop ? "k_stage + k_solve_coop (warp-per-env Newton)" : "k_stage (generic, one kernel per stage)";
   if (b->spec && b->split) { static thread_local std::string nm; nm = std::string(b->spec->name) + " (split: spec PRE + k_solve_coop + spec POST)"; return nm.c_str(); }
   return b->spec ? b->spec->name : "k_step_fused (generic)";

@@ -106,7 +106,9 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
 }
 
 // ---- batch arena fields: X(name, elements-per-env) in terms of nq nv nu nb nj ng ns nM ncm nem nsd ----
-#define OX_BATCH_REAL_FIELDS(X)                                                                        \
+// SMALL: O(nbody + nv + nM) words per env - what the cooperative kernel (ox_coop.cu) keeps in shared memory.
+// ROWS : the contact list, the constraint rows and the dense solver scratch, O(ncon + nefc * nv) - always in the arena.
+#define OX_BATCH_REAL_FIELDS_SMALL(X)                                                                  \
   /* state */                                                                                          \
   X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(xfrc_applied, 6 * nb) X(qacc_warmstart, nv) \
   X(time, 1) X(act, na) X(act_dot, na)                                                                 \
@@ -118,19 +120,21 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   /* velocity / actuation / acceleration */                                                            \
   X(cvel, 6 * nb) X(cdof_dot, 6 * nv) X(cacc, 6 * nb) X(cfrc, 6 * nb) X(qfrc_bias, nv)                 \
   X(qfrc_passive, nv) X(actuator_force, nu) X(qfrc_actuator, nv) X(qfrc_smooth, nv) X(qacc_smooth, nv) \
-  /* contacts and constraints */                                                                       \
+  /* solver vectors */                                                                                 \
+  X(qacc, nv) X(qfrc_constraint, nv) X(s_Ma, nv) X(s_grad, nv) X(s_Mgrad, nv)                          \
+  X(s_search, nv) X(s_Mv, nv) X(s_gradold, nv) X(s_Mgradold, nv)                                       \
+  /* integrator scratch */                                                                             \
+  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(rk_t0, 1) X(i_qacc, nv) X(rk_a0, na) X(rk_sad, na) \
+  X(sensordata, nsd) X(subtree_linvel, 3 * nb)
+#define OX_BATCH_REAL_FIELDS_ROWS(X)                                                                   \
   X(con_dist, ncm) X(con_pos, 3 * ncm) X(con_frame, 9 * ncm)                                           \
   X(efc_J, nem * nv) X(efc_pos, nem) X(efc_margin, nem) X(efc_D, nem) X(efc_aref, nem) X(efc_force, nem) \
-  /* solver */                                                                                         \
-  X(qacc, nv) X(qfrc_constraint, nv) X(s_Ma, nv) X(s_Jaref, nem) X(s_grad, nv) X(s_Mgrad, nv)          \
-  X(s_search, nv) X(s_Mv, nv) X(s_Jv, nem) X(s_H, nv * nv) X(s_gradold, nv) X(s_Mgradold, nv)          \
-  /* integrator scratch */                                                                             \
-  X(rk_q0, nq) X(rk_v0, nv) X(rk_sv, nv) X(rk_sa, nv) X(rk_t0, 1) X(i_qacc, nv) X(rk_a0, na) X(rk_sad, na)        \
-  X(sensordata, nsd) X(subtree_linvel, 3 * nb)
+  X(s_Jaref, nem) X(s_Jv, nem) X(s_H, nv * nv)
+#define OX_BATCH_REAL_FIELDS(X) OX_BATCH_REAL_FIELDS_SMALL(X) OX_BATCH_REAL_FIELDS_ROWS(X)
 
-#define OX_BATCH_INT_FIELDS(X) \
-  X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(con_pair, ncm) X(con_active, ncm) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1) \
-  X(con_efcadr, ncm)
+#define OX_BATCH_INT_FIELDS_SCALAR(X) X(ncon, 1) X(nefc, 1) X(solver_niter, 1) X(diverged, 1) X(acc_ncon, 1) X(acc_nefc, 1) X(acc_niter, 1)
+#define OX_BATCH_INT_FIELDS_ROWS(X) X(con_pair, ncm) X(con_active, ncm) X(con_efcadr, ncm)
+#define OX_BATCH_INT_FIELDS(X) OX_BATCH_INT_FIELDS_SCALAR(X) OX_BATCH_INT_FIELDS_ROWS(X)
 
 template <typename T>
 struct DevBatch {

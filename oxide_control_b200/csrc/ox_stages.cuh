@@ -222,9 +222,10 @@ struct Env {
   static constexpr bool UNROLL_NV = LOCAL && (M::Hdr::nv <= 12);
   static constexpr bool STATIC_CON = LOCAL && (M::Hdr::nconmax <= 24);
   M m;
-  DevBatch<T> b;
+  const DevBatch<T>& b;  // kernel parameter (arena), per-thread struct (specialised kernels) or per-group struct in shared memory (ox_coop.cu)
   int e;
   uint32_t S;  // env stride; every field index fits 32 bits (checked at batch creation)
+  bool slots = false;  // contacts go to static slots pair_conadr(p) + k at run time too (cooperative kernel: lanes own pairs)
 
   OX_HD Env(const M& m_, const DevBatch<T>& b_, int e_) : m(m_), b(b_), e(LOCAL ? 0 : e_), S(LOCAL ? 1u : (uint32_t)b_.stride) {}
 
@@ -243,11 +244,11 @@ struct Env {
   OX_HD bool dis(int bit) const { return (m.h().disableflags & bit) != 0; }
 
   // ============================================================ A.1 kinematics (+ geoms, sites)
-  OX_HDN void kinematics() const {
-    const auto& h = m.h();
-    const int nbody = h.nbody, ngeom = h.ngeom, nsite = h.nsite;
-    OX_MLOOP
-    for (int i = 0; i < nbody; i++) {
+  // The stage functions below are loops over per-item pieces (kin_body, kin_geom, cinert_body, mass_row, vel_body, ...).
+  // The thread-per-env kernels call the loops; the cooperative kernel (ox_coop.cu, one lane group per env) hands the items
+  // of one loop to different lanes and synchronises between tree levels - the arithmetic is the same code.
+  OX_HD void kin_body(int i) const {
+    {
       T pos[3], quat[4], mat[9];
       if (i == 0) {
         pos[0] = pos[1] = pos[2] = 0;
@@ -320,33 +321,42 @@ struct Env {
         st<3>(b.xipos, 3 * i, v);
         st<9>(b.ximat, 9 * i, im);
       }
-      OX_MLOOP
-      for (int g = 0; g < ngeom; g++) {
-        if (m.geom_bodyid(g) != i) continue;
-        T gp[3], gq[4], v[3], q[4], gm[9];
-        OX_LDM(3, gp, geom_pos, 3 * g);
-        OX_LDM(4, gq, geom_quat, 4 * g);
-        mat_vec3(v, mat, gp);
-        v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
-        mul_quat(q, quat, gq);
-        quat2mat(gm, q);
-        st<3>(b.geom_xpos, 3 * g, v);
-        st<9>(b.geom_xmat, 9 * g, gm);
-      }
-      OX_MLOOP
-      for (int s = 0; s < nsite; s++) {
-        if (m.site_bodyid(s) != i) continue;
-        T sp[3], sq[4], v[3], q[4], sm[9];
-        OX_LDM(3, sp, site_pos, 3 * s);
-        OX_LDM(4, sq, site_quat, 4 * s);
-        mat_vec3(v, mat, sp);
-        v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
-        mul_quat(q, quat, sq);
-        quat2mat(sm, q);
-        st<3>(b.site_xpos, 3 * s, v);
-        st<9>(b.site_xmat, 9 * s, sm);
-      }
     }
+  }
+  OX_HD void kin_geom(int g) const {
+    const int i = m.geom_bodyid(g);
+    T pos[3], quat[4], mat[9], gp[3], gq[4], v[3], q[4], gm[9];
+    ld<3>(pos, b.xpos, 3 * i); ld<4>(quat, b.xquat, 4 * i); ld<9>(mat, b.xmat, 9 * i);
+    OX_LDM(3, gp, geom_pos, 3 * g);
+    OX_LDM(4, gq, geom_quat, 4 * g);
+    mat_vec3(v, mat, gp);
+    v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
+    mul_quat(q, quat, gq);
+    quat2mat(gm, q);
+    st<3>(b.geom_xpos, 3 * g, v);
+    st<9>(b.geom_xmat, 9 * g, gm);
+  }
+  OX_HD void kin_site(int s) const {
+    const int i = m.site_bodyid(s);
+    T pos[3], quat[4], mat[9], sp[3], sq[4], v[3], q[4], sm[9];
+    ld<3>(pos, b.xpos, 3 * i); ld<4>(quat, b.xquat, 4 * i); ld<9>(mat, b.xmat, 9 * i);
+    OX_LDM(3, sp, site_pos, 3 * s);
+    OX_LDM(4, sq, site_quat, 4 * s);
+    mat_vec3(v, mat, sp);
+    v[0] += pos[0]; v[1] += pos[1]; v[2] += pos[2];
+    mul_quat(q, quat, sq);
+    quat2mat(sm, q);
+    st<3>(b.site_xpos, 3 * s, v);
+    st<9>(b.site_xmat, 9 * s, sm);
+  }
+  OX_HDN void kinematics() const {
+    const auto& h = m.h();
+    OX_MLOOP
+    for (int i = 0; i < h.nbody; i++) kin_body(i);
+    OX_MLOOP
+    for (int g = 0; g < h.ngeom; g++) kin_geom(g);
+    OX_MLOOP
+    for (int s = 0; s < h.nsite; s++) kin_site(s);
   }
 
   // ============================================================ A.2 subtree com, cinert, cdof
@@ -376,7 +386,12 @@ struct Env {
     OX_MLOOP
     for (int k = 0; k < 10; k++) at(b.cinert, k) = 0;
     OX_MLOOP
-    for (int i = 1; i < nbody; i++) {
+    for (int i = 1; i < nbody; i++) cinert_body(i);
+    OX_MLOOP
+    for (int j = 0; j < njnt; j++) cdof_joint(j);
+  }
+  OX_HD void cinert_body(int i) const {
+    {
       T mat[9], xi[3], sc[3], inert[3], dif[3], res[10], tmp[9];
       ld<9>(mat, b.ximat, 9 * i);
       ld<3>(xi, b.xipos, 3 * i);
@@ -403,8 +418,9 @@ struct Env {
       res[9] = ms;
       st<10>(b.cinert, 10 * i, res);
     }
-    OX_MLOOP
-    for (int j = 0; j < njnt; j++) {
+  }
+  OX_HD void cdof_joint(int j) const {
+    {
       const int bi = m.jnt_bodyid(j), da = m.jnt_dofadr(j), jt = m.jnt_type(j);
       T sc[3], anchor[3], offset[3];
       ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bi));
@@ -464,7 +480,10 @@ struct Env {
       }
     }
     OX_MLOOP
-    for (int i = 0; i < nv; i++) {
+    for (int i = 0; i < nv; i++) mass_row(i);
+  }
+  OX_HD void mass_row(int i) const {
+    {
       T in[10], cd[6], buf[6];
       ld<10>(in, b.crb, 10 * m.dof_bodyid(i));
       ld<6>(cd, b.cdof, 6 * i);
@@ -554,7 +573,10 @@ struct Env {
     OX_MLOOP
     for (int k = 0; k < 6; k++) at(b.cvel, k) = 0;
     OX_MLOOP
-    for (int i = 1; i < nbody; i++) {
+    for (int i = 1; i < nbody; i++) vel_body(i);
+  }
+  OX_HD void vel_body(int i) const {
+    {
       T cvel[6];
       ld<6>(cvel, b.cvel, 6 * m.body_parentid(i));
       const int jntadr = m.body_jntadr(i), jntnum = m.body_jntnum(i);
@@ -611,9 +633,14 @@ struct Env {
     for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) = 0;
     if (dis(OX_DSBL_PASSIVE)) return;
     OX_MLOOP
-    for (int j = 0; j < njnt; j++) {
+    for (int j = 0; j < njnt; j++) passive_joint(j);
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping(i) * at(b.qvel, i);
+  }
+  OX_HD void passive_joint(int j) const {  // joint spring: touches only this joint's dofs
+    {
       const T k = m.jnt_stiffness(j);
-      if (k == 0) continue;
+      if (k == 0) return;
       int pa = m.jnt_qposadr(j), da = m.jnt_dofadr(j);
       const int jt = m.jnt_type(j);
       if (jt == OX_JNT_FREE) {
@@ -633,8 +660,6 @@ struct Env {
         at(b.qfrc_passive, da) -= k * (at(b.qpos, pa) - m.qpos_spring(pa));
       }
     }
-    OX_MLOOP
-    for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping(i) * at(b.qvel, i);
   }
 
   // ============================================================ A.8 bias forces (RNE, no acceleration)
@@ -648,7 +673,30 @@ struct Env {
       st<6>(b.cfrc, 0, z);
     }
     OX_MLOOP
-    for (int i = 1; i < nbody; i++) {
+    for (int i = 1; i < nbody; i++) rne_fwd_body(i);
+    OX_MLOOP
+    for (int i = nbody - 1; i > 0; i--) {
+      const int p = m.body_parentid(i);
+      if (p) {
+        T a[6], c[6];
+        ld<6>(a, b.cfrc, 6 * p);
+        ld<6>(c, b.cfrc, 6 * i);
+#pragma unroll
+        for (int k = 0; k < 6; k++) a[k] += c[k];
+        st<6>(b.cfrc, 6 * p, a);
+      }
+    }
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) rne_bias_dof(i);
+  }
+  OX_HD void rne_bias_dof(int i) const {
+    T cd[6], f[6];
+    ld<6>(cd, b.cdof, 6 * i);
+    ld<6>(f, b.cfrc, 6 * m.dof_bodyid(i));
+    at(b.qfrc_bias, i) = dot6(cd, f);
+  }
+  OX_HD void rne_fwd_body(int i) const {
+    {
       const int bda = m.body_dofadr(i), nd = m.body_dofnum(i);
       T cacc[6], in[10], cv[6], f[6], tmp[6], tmp1[6];
       ld<6>(cacc, b.cacc, 6 * m.body_parentid(i));
@@ -670,25 +718,6 @@ struct Env {
       for (int c = 0; c < 6; c++) f[c] += tmp1[c];
       st<6>(b.cfrc, 6 * i, f);
     }
-    OX_MLOOP
-    for (int i = nbody - 1; i > 0; i--) {
-      const int p = m.body_parentid(i);
-      if (p) {
-        T a[6], c[6];
-        ld<6>(a, b.cfrc, 6 * p);
-        ld<6>(c, b.cfrc, 6 * i);
-#pragma unroll
-        for (int k = 0; k < 6; k++) a[k] += c[k];
-        st<6>(b.cfrc, 6 * p, a);
-      }
-    }
-    OX_MLOOP
-    for (int i = 0; i < nv; i++) {
-      T cd[6], f[6];
-      ld<6>(cd, b.cdof, 6 * i);
-      ld<6>(f, b.cfrc, 6 * m.dof_bodyid(i));
-      at(b.qfrc_bias, i) = dot6(cd, f);
-    }
   }
 
   // ============================================================ A.9 actuation (joint transmission)
@@ -697,11 +726,18 @@ struct Env {
     const int nv = h.nv, nu = h.nu;
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_actuator, i) = 0;
-    const bool off = dis(OX_DSBL_ACTUATION);
-    const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
     OX_MLOOP
     for (int i = 0; i < nu; i++) {
-      if (off) { at(b.actuator_force, i) = 0; continue; }
+      const T gf = actuator_one(i);   // gear * force (0 when actuation is disabled)
+      at(b.qfrc_actuator, m.jnt_dofadr(m.actuator_trnid(i))) += gf;
+    }
+  }
+  // force of one actuator -> actuator_force[i] (and act_dot for stateful ones); returns its generalised force gear * force
+  OX_HD T actuator_one(int i) const {
+    const bool off = dis(OX_DSBL_ACTUATION);
+    const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
+    {
+      if (off) { at(b.actuator_force, i) = 0; return (T)0; }
       const int j = m.actuator_trnid(i), qa = m.jnt_qposadr(j), da = m.jnt_dofadr(j);
       const T gear = m.actuator_gear(i);
       const T length = gear * at(b.qpos, qa), velocity = gear * at(b.qvel, da);
@@ -726,17 +762,26 @@ struct Env {
       T force = gain * ctrl + bias;
       if (m.actuator_forcelimited(i)) force = ox_clip(force, m.actuator_forcerange(2 * i), m.actuator_forcerange(2 * i + 1));
       at(b.actuator_force, i) = force;
-      at(b.qfrc_actuator, da) += gear * force;
+      return gear * force;
     }
   }
 
   // ============================================================ A.10 smooth acceleration
   OX_HDN void fwd_acceleration() const {
     const auto& h = m.h();
-    const int nv = h.nv, nbody = h.nbody;
+    const int nv = h.nv;
     OX_MLOOP
     for (int i = 0; i < nv; i++)
       at(b.qfrc_smooth, i) = at(b.qfrc_passive, i) - at(b.qfrc_bias, i) + at(b.qfrc_applied, i) + at(b.qfrc_actuator, i);
+    apply_xfrc();
+    OX_MLOOP
+    for (int i = 0; i < nv; i++) at(b.qacc_smooth, i) = at(b.qfrc_smooth, i);
+    solve_ld(b.qacc_smooth);
+  }
+  // qfrc_smooth += J' xfrc_applied (Cartesian forces / torques at the body com)
+  OX_HD void apply_xfrc() const {
+    const auto& h = m.h();
+    const int nbody = h.nbody;
     // Branch hygiene (here and in make_constraint / collision): a skipped block is a taken branch to a far target, which
     // in these large straight-line kernels is an instruction-cache miss served from L2 (~500 cycles, profiles/r1_notes.md).
     // So test the common "nothing to do" case once for the whole loop instead of once per body / joint / contact site.
@@ -765,9 +810,6 @@ struct Env {
         at(b.qfrc_smooth, i) += dot3(jp, f) + dot3(cd, f + 3);
       }
     }
-    OX_MLOOP
-    for (int i = 0; i < nv; i++) at(b.qacc_smooth, i) = at(b.qfrc_smooth, i);
-    solve_ld(b.qacc_smooth);
   }
 
   // ============================================================ A.5 collision (precompiled pair list)
@@ -812,12 +854,12 @@ struct Env {
   // contact arrays live in registers; walking the slots in order visits the contacts in the same order as the compact list.
   OX_HD void emit(Con& c, int p, int k, int& ncon) const {
     make_frame(c.frame);
-    const int idx = STATIC_CON ? m.pair_conadr(p) + k : ncon;
+    const int idx = (STATIC_CON || slots) ? m.pair_conadr(p) + k : ncon;
     at(b.con_dist, idx) = c.dist;
     st<3>(b.con_pos, 3 * idx, c.pos);
     st<9>(b.con_frame, 9 * idx, c.frame);
     ati(b.con_pair, idx) = p;
-    if (STATIC_CON) ati(b.con_active, idx) = 1;
+    if (STATIC_CON || slots) ati(b.con_active, idx) = 1;
     ncon++;
   }
 
@@ -831,7 +873,14 @@ struct Env {
     if (!(dis(OX_DSBL_CONTACT) || dis(OX_DSBL_CONSTRAINT))) {
       const int npair = h.npair;
       OX_MLOOP
-      for (int p = 0; p < npair; p++) {
+      for (int p = 0; p < npair; p++) collide_pair(p, ncon);
+    }
+    ati(b.ncon, 0) = ncon;
+  }
+  // narrowphase of one candidate pair; emits 0..pair_maxcon(p) contacts
+  OX_HD void collide_pair(int p, int& ncon) const {
+    {
+      {
         const int g1 = m.pair_geom1(p), g2 = m.pair_geom2(p), t1 = m.geom_type(g1), t2 = m.geom_type(g2);
         const T margin = m.pair_margin(p);
         T size1[3], size2[3];
@@ -848,7 +897,7 @@ struct Env {
           // humanoid's 20 self-collision pairs, almost always far apart, it was 43 % of the PRE kernel's instruction stream.
           const T rb = size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0) + size2[0] + (t2 == OX_GEOM_CAPSULE ? size2[1] : (T)0) + margin;
           const T dx = pos2[0] - pos1[0], dy = pos2[1] - pos1[1], dz = pos2[2] - pos1[2];
-          if (dx * dx + dy * dy + dz * dz > rb * rb * (T)1.0005 + (T)1e-9) continue;
+          if (dx * dx + dy * dy + dz * dz > rb * rb * (T)1.0005 + (T)1e-9) return;
         }
         if (t1 == OX_GEOM_PLANE) {
           T n[3] = {at(b.geom_xmat, 9 * g1 + 2), at(b.geom_xmat, 9 * g1 + 5), at(b.geom_xmat, 9 * g1 + 8)};
@@ -861,7 +910,7 @@ struct Env {
             {  // neither end cap within reach of the plane (the common case): one branch for the pair
               const T dc = (pos2[0] - pos1[0]) * n[0] + (pos2[1] - pos1[1]) * n[1] + (pos2[2] - pos1[2]) * n[2];
               const T da = ox_abs(dot3(axis, n)) * hl;
-              if (dc - da > (margin + size2[0]) * (T)1.0001 + (T)1e-6) continue;   // conservative: the exact tests follow
+              if (dc - da > (margin + size2[0]) * (T)1.0001 + (T)1e-6) return;   // conservative: the exact tests follow
             }
 #pragma unroll
             for (int sgn = 1; sgn >= -1; sgn -= 2) {
@@ -945,7 +994,6 @@ struct Env {
         }
       }
     }
-    ati(b.ncon, 0) = ncon;
   }
 
   // ============================================================ A.6 constraint assembly
@@ -1092,30 +1140,7 @@ struct Env {
       }
       if (any_limit) {
         OX_MLOOP
-        for (int j = 0; j < njnt; j++) {
-          if (!m.jnt_limited(j)) continue;
-          const int jt = m.jnt_type(j);
-          if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
-          const int da = m.jnt_dofadr(j);
-          const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
-          OX_MLOOP
-          for (int side = -1; side <= 1; side += 2) {
-            const T dist = side * (m.jnt_range(2 * j + (side + 1) / 2) - value);
-            if (dist < margin) {
-              const int r = nefc++;
-              OX_MLOOP
-              for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
-              at(b.efc_J, r * nv + da) = (T)(-side);
-              const T vel = (T)(-side) * at(b.qvel, da);
-              T aref;
-              T sr[2], si[5];
-              OX_LDM(2, sr, jnt_solref, 2 * j);
-              OX_LDM(5, si, jnt_solimp, 5 * j);
-              const T R = row_params(sr, si, dist, margin, m.dof_invweight0(da), vel, &aref);
-              at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
-            }
-          }
-        }
+        for (int j = 0; j < njnt; j++) limit_rows(j, nefc);
       }
       if (STATIC_CON) {  // static contact slots: every index below is a compile-time constant after unrolling
         OX_MLOOP
@@ -1136,6 +1161,43 @@ struct Env {
       }
     }
     ati(b.nefc, 0) = nefc;
+  }
+  // number of limit rows joint j contributes (0, 1 or 2) and the rows themselves
+  OX_HD int limit_count(int j) const {
+    if (!m.jnt_limited(j)) return 0;
+    const int jt = m.jnt_type(j);
+    if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) return 0;
+    const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
+    return (value - m.jnt_range(2 * j) < margin ? 1 : 0) + (m.jnt_range(2 * j + 1) - value < margin ? 1 : 0);
+  }
+  OX_HD void limit_rows(int j, int& nefc) const {
+    const int nv = m.h().nv;
+    {
+      {
+          if (!m.jnt_limited(j)) return;
+          const int jt = m.jnt_type(j);
+          if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) return;
+          const int da = m.jnt_dofadr(j);
+          const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
+          OX_MLOOP
+          for (int side = -1; side <= 1; side += 2) {
+            const T dist = side * (m.jnt_range(2 * j + (side + 1) / 2) - value);
+            if (dist < margin) {
+              const int r = nefc++;
+              OX_MLOOP
+              for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
+              at(b.efc_J, r * nv + da) = (T)(-side);
+              const T vel = (T)(-side) * at(b.qvel, da);
+              T aref;
+              T sr[2], si[5];
+              OX_LDM(2, sr, jnt_solref, 2 * j);
+              OX_LDM(5, si, jnt_solimp, 5 * j);
+              const T R = row_params(sr, si, dist, margin, m.dof_invweight0(da), vel, &aref);
+              at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
+            }
+          }
+      }
+    }
   }
 
   // ============================================================ A.11 primal solver (Newton / CG)
@@ -1625,7 +1687,7 @@ struct Env {
             if (sbody == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
             if (ray_geom(spos, smat, ssize, cp, ray, stype) >= 0) total += fn;
           };
-          if (STATIC_CON) {
+          if (STATIC_CON || slots) {
             OX_MLOOP
             for (int p = 0; p < h.npair; p++) {
               OX_MLOOP
@@ -1664,7 +1726,10 @@ struct Env {
   OX_HD void integrate_pos(T* qpos, const T* qvel, T dt) const {
     const int njnt = m.h().njnt;
     OX_MLOOP
-    for (int j = 0; j < njnt; j++) {
+    for (int j = 0; j < njnt; j++) integrate_pos_joint(qpos, qvel, dt, j);
+  }
+  OX_HD void integrate_pos_joint(T* qpos, const T* qvel, T dt, int j) const {
+    {
       int pa = m.jnt_qposadr(j), va = m.jnt_dofadr(j);
       const int jt = m.jnt_type(j);
       if (jt == OX_JNT_FREE) {

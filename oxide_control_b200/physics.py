@@ -182,7 +182,7 @@ class BatchedPhysics:
         cfg.nenv = nenv
         cfg.device = device
         cfg.precision = {"f32": A.F32, "f64": A.F64}[precision]
-        cfg.mode = {"fused": A.MODE_FUSED, "staged": A.MODE_STAGED}[mode]
+        cfg.mode = {"fused": A.MODE_FUSED, "staged": A.MODE_STAGED, "coop": A.MODE_COOP}[mode]
         cfg.iterations = iterations
         cfg.ls_iterations = ls_iterations
         cfg.tolerance = tolerance
@@ -400,7 +400,7 @@ class PhysicsGroup:
         cfg = A.BatchConfig()
         A.lib().ox_batch_config_default(C.byref(cfg))
         cfg.nenv, cfg.precision, cfg.env_id_offset = nenv_per_device, {"f32": A.F32, "f64": A.F64}[precision], env_id_offset
-        cfg.specialize, cfg.mode = int(specialize), {"fused": A.MODE_FUSED, "staged": A.MODE_STAGED}[mode]
+        cfg.specialize, cfg.mode = int(specialize), {"fused": A.MODE_FUSED, "staged": A.MODE_STAGED, "coop": A.MODE_COOP}[mode]
         devs = (C.c_int32 * ndevices)(*devices) if devices is not None else None
         self.model, self._h = model, C.c_void_p()
         _check(A.lib().ox_group_create(model.handle, C.byref(cfg), ndevices, devs, C.byref(self._h)))
