@@ -1,8 +1,11 @@
-"""Synthetic inline MJCF models for BASELINE.json's five configs.
+"""Inline MJCF models for BASELINE.json's five configs.
 
-All use <compiler angle="radian"/>. They are synthetic stand-ins with the topology and sizes of the
-named dm_control / gym tasks, written for this repo. The XML lives in spec_models/*.xml inside the package: the same
-files are read by csrc/ox_specgen at build time to emit the model-specialised step kernels (csrc/ox_spec.cuh).
+pendulum, cartpole and acrobot are small models written for this repo. cheetah.xml and humanoid.xml are the public
+dm_control / Gym assets (half-cheetah, humanoid) almost verbatim - same bodies, joints, geoms, actuators and options, minus
+what the MJCF subset does not parse (textures, materials, cameras, tendons) - so that the benchmark configs are the models
+the wider community steps with MuJoCo. The XML lives in spec_models/*.xml inside the package: the same files are read by
+csrc/ox_specgen at build time to emit the compiled-in model-specialised step kernels (csrc/ox_spec.cuh); any other model is
+specialised at run time (csrc/ox_jit.cpp).
 """
 import os as _os
 
