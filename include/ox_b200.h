@@ -64,6 +64,8 @@ enum { OX_OBJ_UNKNOWN = 0, OX_OBJ_BODY = 1, OX_OBJ_XBODY = 2, OX_OBJ_JOINT = 3, 
 enum { OX_INT_EULER = 0, OX_INT_RK4 = 1, OX_INT_IMPLICIT = 2 /* refused by the compiler */, OX_INT_IMPLICITFAST = 3 };
 /* mjtDyn subset: activation dynamics of stateful actuators (act, src/physics.rs:96-102) */
 enum { OX_DYN_NONE = 0, OX_DYN_INTEGRATOR = 1, OX_DYN_FILTER = 2, OX_DYN_FILTEREXACT = 3 };
+/* mjtEq subset: equality constraints */
+enum { OX_EQ_CONNECT = 0, OX_EQ_WELD = 1 /* refused */, OX_EQ_JOINT = 2 };
 enum { OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
 enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
@@ -71,7 +73,7 @@ enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
 enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 << 4,
        OX_DSBL_PASSIVE = 1 << 5, OX_DSBL_GRAVITY = 1 << 6, OX_DSBL_CLAMPCTRL = 1 << 7,
        OX_DSBL_WARMSTART = 1 << 8, OX_DSBL_FILTERPARENT = 1 << 9, OX_DSBL_ACTUATION = 1 << 10,
-       OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13 };
+       OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13, OX_DSBL_EQUALITY = 1 << 1 };
 /* mjtSensor subset */
 enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3,
        OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
@@ -89,6 +91,8 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
 #define OX_MODEL_INT_TABLES(X)                                                                      \
   X(body_parentid, nbody, 1) X(body_rootid, nbody, 1) X(body_weldid, nbody, 1)                     \
   X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
+  X(body_mocapid, nbody, 1)                                                                         \
+  X(eq_type, neq, 1) X(eq_obj1id, neq, 1) X(eq_obj2id, neq, 1) X(eq_active0, neq, 1)                \
   X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
   X(jnt_limited, njnt, 1)                                                                           \
   X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1) X(dof_Mdense, nvv, 1)               \
@@ -118,14 +122,17 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(pair_margin, npair, 1) X(pair_gap, npair, 1)                                                    \
   X(actuator_gear, nu, 1) X(actuator_gainprm, nu, 3) X(actuator_biasprm, nu, 3)                    \
   X(actuator_ctrlrange, nu, 2) X(actuator_forcerange, nu, 2)                                        \
-  X(actuator_dynprm, nu, 3) X(actuator_actrange, nu, 2)
+  X(actuator_dynprm, nu, 3) X(actuator_actrange, nu, 2)                                             \
+  X(eq_solref, neq, 2) X(eq_solimp, neq, 5) X(eq_data, neq, 11)
 
 typedef struct ox_model_tables {
   /* sizes */
   int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata;
   int32_t nvv;      /* nv*nv: size of dof_Mdense (index into qM of M(i,j), -1 where M is structurally zero) */
   int32_t nconmax;  /* sum of pair_maxcon: capacity of the per-env contact list         */
-  int32_t nefcmax;  /* 2*nlimited + sum of contact rows: capacity of the per-env efc list */
+  int32_t nefcmax;  /* equality rows + 2*nlimited + sum of contact rows: capacity of the per-env efc list */
+  int32_t nmocap;   /* mocap bodies (mocap_pos / mocap_quat, src/physics.rs:154-170) */
+  int32_t neq;      /* equality constraints (eq_active, src/physics.rs:147-152) */
   /* mjOption subset */
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
   double timestep, gravity[3], tolerance, ls_tolerance, impratio;
@@ -224,7 +231,7 @@ enum {
   OX_F_QFRC_SMOOTH, OX_F_QACC_SMOOTH, OX_F_QFRC_CONSTRAINT,
   OX_F_CON_DIST, OX_F_CON_POS, OX_F_CON_FRAME,
   OX_F_EFC_J, OX_F_EFC_POS, OX_F_EFC_MARGIN, OX_F_EFC_D, OX_F_EFC_AREF, OX_F_EFC_FORCE,
-  OX_F_ACT_DOT,
+  OX_F_ACT_DOT, OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE,
   OX_F_COUNT_REAL,
   /* int32 fields */
   OX_F_NCON = 100, OX_F_NEFC, OX_F_SOLVER_NITER, OX_F_DIVERGED, OX_F_CON_PAIR
@@ -245,7 +252,8 @@ OX_API ox_status ox_batch_get1_int(ox_batch* b, int32_t field, int32_t env, int3
 
 /* Checkpoint / resume (the reference keeps no such API - its state is whatever the user copies out through the
  * getters of src/physics.rs:82-145, which is exactly this tuple): one record per env, env-major,
- *   [ time, qpos(nq), qvel(nv), act(na), ctrl(nu), qfrc_applied(nv), xfrc_applied(6 nbody), qacc_warmstart(nv) ]
+ *   [ time, qpos(nq), qvel(nv), act(na), ctrl(nu), qfrc_applied(nv), xfrc_applied(6 nbody), qacc_warmstart(nv),
+ *     mocap_pos(3 nmocap), mocap_quat(4 nmocap), eq_active(neq) ]
  * = ox_batch_state_size() elements of `dtype`. Restoring a record and the Philox step counter reproduces the trajectory
  * bit for bit in the same precision (qacc_warmstart seeds the solver). */
 OX_API int32_t ox_batch_state_size(const ox_batch* b);

@@ -188,8 +188,30 @@ class Physics {
     auto v = batch_.get1(OX_F_XFRC_APPLIED, 0, 6 * id.index, 6); std::array<double, 6> a; for (int i = 0; i < 6; i++) a[i] = v[i]; return a;
   }
   void set_xfrc_applied(obj::Body id, const std::array<double, 6>& f) { batch_.set1(OX_F_XFRC_APPLIED, 0, 6 * id.index, f.data(), 6); }
-  std::optional<std::array<double, 3>> mocap_pos(obj::Body) { return std::nullopt; }                             // :154-161
-  std::optional<std::array<double, 4>> mocap_quat(obj::Body) { return std::nullopt; }                            // :163-170
+  bool eq_active(obj::Equality id) { return batch_.get1(OX_F_EQ_ACTIVE, 0, id.index, 1)[0] != 0; }                // :147-152
+  void set_eq_active(obj::Equality id, bool on) { const double v = on ? 1 : 0; batch_.set1(OX_F_EQ_ACTIVE, 0, id.index, &v, 1); }
+  // :154-170: None when the body is not a mocap body
+  int mocapid(obj::Body id) const { return model_.tables().nmocap > 0 ? model_.tables().body_mocapid[id.index] : -1; }
+  std::optional<std::array<double, 3>> mocap_pos(obj::Body id) {
+    const int m = mocapid(id);
+    if (m < 0) return std::nullopt;
+    auto v = batch_.get1(OX_F_MOCAP_POS, 0, 3 * m, 3); return std::array<double, 3>{v[0], v[1], v[2]};
+  }
+  std::optional<std::monostate> set_mocap_pos(obj::Body id, const std::array<double, 3>& p) {
+    const int m = mocapid(id);
+    if (m < 0) return std::nullopt;
+    batch_.set1(OX_F_MOCAP_POS, 0, 3 * m, p.data(), 3); return std::monostate{};
+  }
+  std::optional<std::array<double, 4>> mocap_quat(obj::Body id) {
+    const int m = mocapid(id);
+    if (m < 0) return std::nullopt;
+    auto v = batch_.get1(OX_F_MOCAP_QUAT, 0, 4 * m, 4); return std::array<double, 4>{v[0], v[1], v[2], v[3]};
+  }
+  std::optional<std::monostate> set_mocap_quat(obj::Body id, const std::array<double, 4>& q) {
+    const int m = mocapid(id);
+    if (m < 0) return std::nullopt;
+    batch_.set1(OX_F_MOCAP_QUAT, 0, 4 * m, q.data(), 4); return std::monostate{};
+  }
   // data(): derived arrays the reference reaches through Physics::data() (src/physics.rs:30-32)
   std::vector<double> qacc() { return batch_.get1(OX_F_QACC, 0, 0, model_.tables().nv); }
   std::vector<double> sensordata() { return batch_.get1(OX_F_SENSORDATA, 0, 0, model_.tables().nsensordata); }

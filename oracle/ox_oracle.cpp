@@ -35,7 +35,7 @@ typedef ox_model_tables Model;
 
 struct oxo_data {
   // state (mjData fields of the same names)
-  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot;
+  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot, mocap_pos, mocap_quat, eq_active;
   double time = 0;
   // position stage
   std::vector<double> xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, geom_xpos, geom_xmat, site_xpos, site_xmat;
@@ -47,7 +47,7 @@ struct oxo_data {
   std::vector<double> con_dist, con_pos, con_frame;
   std::vector<int> con_pair;
   // constraints
-  int nefc = 0;
+  int nefc = 0, ne = 0;  // ne = number of equality rows (they come first and are two-sided)
   std::vector<double> efc_J, efc_pos, efc_margin, efc_D, efc_R, efc_aref, efc_vel, efc_force, efc_diagApprox;
   std::vector<int> efc_type, efc_id;
   // solution
@@ -162,7 +162,13 @@ void kinematics(const Model* m, Data* d) {
   for (int i = 1; i < m->nbody; i++) {
     double pos[3], quat[4];
     int jntadr = m->body_jntadr[i], jntnum = m->body_jntnum[i];
-    if (jntnum == 1 && m->jnt_type[jntadr] == OX_JNT_FREE) {
+    if (m->nmocap > 0 && m->body_mocapid[i] >= 0) {
+      // mj_kinematics: a mocap body takes its pose from mjData.mocap_pos / mocap_quat (normalised copy)
+      int id = m->body_mocapid[i];
+      std::memcpy(pos, &d->mocap_pos[3 * id], 3 * sizeof(double));
+      std::memcpy(quat, &d->mocap_quat[4 * id], 4 * sizeof(double));
+      normalize4(quat);
+    } else if (jntnum == 1 && m->jnt_type[jntadr] == OX_JNT_FREE) {
       int qadr = m->jnt_qposadr[jntadr];
       std::memcpy(pos, &d->qpos[qadr], 3 * sizeof(double));
       std::memcpy(quat, &d->qpos[qadr + 3], 4 * sizeof(double));
@@ -566,8 +572,47 @@ void addRow(const Model* m, Data* d, const double* jrow, double pos, double marg
 void makeConstraint(const Model* m, Data* d) {
   int nv = m->nv;
   d->nefc = 0;
+  d->ne = 0;
   if (disabled(m, OX_DSBL_CONSTRAINT)) return;
   std::vector<double> jrow(nv), jacp(3 * nv), jac(3 * nv);
+  // equality constraints first (mj_instantiateEquality): residual as pos, margin 0, always active in the solver
+  if (!disabled(m, OX_DSBL_EQUALITY))
+    for (int i = 0; i < m->neq; i++) {
+      if (d->eq_active[i] == 0) continue;
+      const double* data = m->eq_data + 11 * i;
+      if (m->eq_type[i] == OX_EQ_CONNECT) {
+        // anchors of the two bodies in world coordinates must coincide: residual p1 - p2, Jacobian Jp(b1, p1) - Jp(b2, p2)
+        int b1 = m->eq_obj1id[i], b2 = m->eq_obj2id[i];
+        double p1[3], p2[3], w[3];
+        mulMatVec3(w, &d->xmat[9 * b1], data);
+        for (int k = 0; k < 3; k++) p1[k] = d->xpos[3 * b1 + k] + w[k];
+        mulMatVec3(w, &d->xmat[9 * b2], data + 3);
+        for (int k = 0; k < 3; k++) p2[k] = d->xpos[3 * b2 + k] + w[k];
+        std::fill(jacp.begin(), jacp.end(), 0.0);
+        addJacP(m, d, b1, p1, +1, jacp.data());
+        addJacP(m, d, b2, p2, -1, jacp.data());
+        double diag = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+        for (int k = 0; k < 3; k++)
+          addRow(m, d, &jacp[(size_t)k * nv], p1[k] - p2[k], 0.0, diag, m->eq_solref + 2 * i, m->eq_solimp + 5 * i, 3, i);
+      } else {
+        // joint coupling: q1 - q1_0 = c0 + c1 dq2 + ... + c4 dq2^4 with dq2 = q2 - q2_0 (only c0 without a second joint)
+        int j1 = m->eq_obj1id[i], j2 = m->eq_obj2id[i];
+        std::fill(jrow.begin(), jrow.end(), 0.0);
+        double pos = d->qpos[m->jnt_qposadr[j1]] - m->qpos0[m->jnt_qposadr[j1]];
+        double diag = m->dof_invweight0[m->jnt_dofadr[j1]];
+        jrow[m->jnt_dofadr[j1]] = 1;
+        if (j2 >= 0) {
+          double dq = d->qpos[m->jnt_qposadr[j2]] - m->qpos0[m->jnt_qposadr[j2]];
+          pos -= data[0] + data[1] * dq + data[2] * dq * dq + data[3] * dq * dq * dq + data[4] * dq * dq * dq * dq;
+          jrow[m->jnt_dofadr[j2]] = -(data[1] + 2 * data[2] * dq + 3 * data[3] * dq * dq + 4 * data[4] * dq * dq * dq);
+          diag += m->dof_invweight0[m->jnt_dofadr[j2]];
+        } else {
+          pos -= data[0];
+        }
+        addRow(m, d, jrow.data(), pos, 0.0, diag, m->eq_solref + 2 * i, m->eq_solimp + 5 * i, 3, i);
+      }
+    }
+  d->ne = d->nefc;
   // joint limits
   if (!disabled(m, OX_DSBL_LIMIT))
     for (int j = 0; j < m->njnt; j++) {
@@ -778,7 +823,7 @@ struct Solver {
   void updateConstraint() {
     double c = 0;
     for (int r = 0; r < nefc; r++) {
-      if (Jaref[r] < 0) {
+      if (Jaref[r] < 0 || r < d->ne) {   // equality rows are quadratic on both sides
         active[r] = 1;
         d->efc_force[r] = -d->efc_D[r] * Jaref[r];
         c += 0.5 * d->efc_D[r] * Jaref[r] * Jaref[r];
@@ -851,7 +896,7 @@ struct Solver {
     p.s0 = std::fabs(2 * a * quadGauss[2]) + std::fabs(quadGauss[1]);
     for (int r = 0; r < nefc; r++) {
       double x = Jaref[r] + a * Jv[r];
-      if (x < 0) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
+      if (x < 0 || r < d->ne) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
         const double Dx = d->efc_D[r] * x, Dj = d->efc_D[r] * Jv[r];
         p.cost += 0.5 * Dx * x;
         p.d0 += Dx * Jv[r];
@@ -949,7 +994,7 @@ struct Solver {
     for (int r = 0; r < nefc; r++) {
       double v = -d->efc_aref[r];
       for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * qacc[i];
-      if (v < 0) c += 0.5 * d->efc_D[r] * v * v;
+      if (v < 0 || r < d->ne) c += 0.5 * d->efc_D[r] * v * v;
     }
     return c;
   }
@@ -1099,7 +1144,7 @@ void sensors(const Model* m, Data* d) {
           double fn = 0;
           bool has_rows = false;
           for (int r = 0; r < d->nefc; r++)
-            if (d->efc_type[r] != 0 && d->efc_id[r] == c) { fn += d->efc_force[r]; has_rows = true; }
+            if ((d->efc_type[r] == 1 || d->efc_type[r] == 2) && d->efc_id[r] == c) { fn += d->efc_force[r]; has_rows = true; }
           if (!has_rows || fn <= 0) continue;
           double ray[3] = {d->con_frame[9 * c], d->con_frame[9 * c + 1], d->con_frame[9 * c + 2]};
           if (sbody == b2) for (double& v : ray) v = -v;
@@ -1284,11 +1329,17 @@ void resetData(const Model* m, Data* d) {
   std::memcpy(d->qpos.data(), m->qpos0, m->nq * sizeof(double));
   auto z = [](std::vector<double>& v) { std::fill(v.begin(), v.end(), 0.0); };
   z(d->qvel); z(d->ctrl); z(d->qfrc_applied); z(d->xfrc_applied); z(d->qacc_warmstart); z(d->qacc); z(d->act); z(d->act_dot);
+  for (int i = 1; i < m->nbody; i++)   // mj_resetData: mocap poses back to the model's body poses, equality constraints to their defaults
+    if (m->nmocap > 0 && m->body_mocapid[i] >= 0) {
+      std::memcpy(&d->mocap_pos[3 * m->body_mocapid[i]], m->body_pos + 3 * i, 3 * sizeof(double));
+      std::memcpy(&d->mocap_quat[4 * m->body_mocapid[i]], m->body_quat + 4 * i, 4 * sizeof(double));
+    }
+  for (int i = 0; i < m->neq; i++) d->eq_active[i] = m->eq_active0[i];
   z(d->xpos); z(d->xquat); z(d->xmat); z(d->xipos); z(d->ximat); z(d->xanchor); z(d->xaxis); z(d->geom_xpos); z(d->geom_xmat);
   z(d->site_xpos); z(d->site_xmat); z(d->subtree_com); z(d->cinert); z(d->cdof); z(d->qM); z(d->qLD); z(d->qLDiagInv);
   z(d->cvel); z(d->cdof_dot); z(d->qfrc_bias); z(d->qfrc_passive); z(d->actuator_force); z(d->qfrc_actuator); z(d->qfrc_smooth);
   z(d->qacc_smooth); z(d->qfrc_constraint); z(d->sensordata); z(d->efc_force);
-  d->time = 0; d->ncon = 0; d->nefc = 0; d->solver_niter = 0;
+  d->time = 0; d->ncon = 0; d->nefc = 0; d->ne = 0; d->solver_niter = 0;
 }
 
 void step(const Model* m, Data* d) {
@@ -1339,6 +1390,7 @@ OXO_API oxo_data* oxo_make_data(const Model* m) {
   int nb = m->nbody, nv = m->nv;
   d->qpos.resize(m->nq); d->qvel.resize(nv); d->ctrl.resize(m->nu); d->qfrc_applied.resize(nv); d->xfrc_applied.resize(6 * nb);
   d->qacc_warmstart.resize(nv); d->act.resize(m->na); d->act_dot.resize(m->na);
+  d->mocap_pos.resize(3 * m->nmocap); d->mocap_quat.resize(4 * m->nmocap); d->eq_active.resize(m->neq);
   d->xpos.resize(3 * nb); d->xquat.resize(4 * nb); d->xmat.resize(9 * nb); d->xipos.resize(3 * nb); d->ximat.resize(9 * nb);
   d->xanchor.resize(3 * m->njnt); d->xaxis.resize(3 * m->njnt); d->geom_xpos.resize(3 * m->ngeom); d->geom_xmat.resize(9 * m->ngeom);
   d->site_xpos.resize(3 * m->nsite); d->site_xmat.resize(9 * m->nsite);
@@ -1387,7 +1439,7 @@ OXO_API void oxo_stage(const Model* m, oxo_data* d, const char* name) {
 OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
   std::string s(name);
 #define F(f) if (s == #f) { *count = (int32_t)d->f.size(); return d->f.data(); }
-  F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
+  F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
   F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
   F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
   F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)
@@ -1401,6 +1453,7 @@ OXO_API int32_t oxo_int(oxo_data* d, const char* name) {
   std::string s(name);
   if (s == "ncon") return d->ncon;
   if (s == "nefc") return d->nefc;
+  if (s == "ne") return d->ne;
   if (s == "solver_niter") return d->solver_niter;
   if (s == "diverged") return d->diverged;
   return -1;

@@ -285,6 +285,15 @@ ox_status ensure_htmp(ox_batch* b, size_t bytes) {
   return OX_OK;
 }
 
+// fields of features the model does not have answer OX_ABSENT (the reference's Option::None, src/physics.rs:96-102,154-170)
+static ox_status field_absent(const ox_batch* b, int field) {
+  const ox_model_tables& t = b->model->t;
+  if ((field == OX_F_ACT || field == OX_F_ACT_DOT) && t.na == 0) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if ((field == OX_F_MOCAP_POS || field == OX_F_MOCAP_QUAT) && t.nmocap == 0) { ox::set_error("model has no mocap bodies (nmocap = 0)"); return OX_ABSENT; }
+  if (field == OX_F_EQ_ACTIVE && t.neq == 0) { ox::set_error("model has no equality constraints (neq = 0)"); return OX_ABSENT; }
+  return OX_OK;
+}
+
 template <typename TF, typename TU>
 void launch_pack(ox_batch* b, void* field, void* user, int cnt, int layout, int dir) {
   const long long n = (long long)b->nenv * cnt;
@@ -299,7 +308,7 @@ ox_status bulk_io(ox_batch* b, int field, void* buf, int dtype, int mem, int lay
   auto it = b->fields.find(field);
   if (it == b->fields.end()) { ox::set_error("bulk I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
   const FieldInfo& fi = it->second;
-  if ((field == OX_F_ACT || field == OX_F_ACT_DOT) && b->model->t.na == 0) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if (ox_status absent = field_absent(b, field)) return absent;
   if (fi.count == 0) return OX_OK;
   if (dir == 1 && !field_live(b, field)) { ox::set_error("ox_batch_get: " + OX_STALE_MSG(field)); return OX_ERR_INVALID; }
   if (layout != OX_LAYOUT_ENV_MAJOR && layout != OX_LAYOUT_ELEM_MAJOR) { ox::set_error("bulk I/O: bad layout"); return OX_ERR_INVALID; }
@@ -341,7 +350,7 @@ ox_status slice_io(ox_batch* b, int field, int env, int offset, int count, doubl
   auto it = b->fields.find(field);
   if (it == b->fields.end()) { ox::set_error("per-env I/O: unknown field id " + std::to_string(field)); return OX_ERR_INVALID; }
   const FieldInfo& fi = it->second;
-  if ((field == OX_F_ACT || field == OX_F_ACT_DOT) && b->model->t.na == 0) { ox::set_error("model has no stateful actuators (na = 0)"); return OX_ABSENT; }
+  if (ox_status absent = field_absent(b, field)) return absent;
   if (env < 0 || env >= b->nenv || offset < 0 || count < 0 || offset + count > fi.count) {
     ox::set_error("per-env I/O: index out of range");
     return OX_ERR_INVALID;
@@ -672,7 +681,8 @@ ox_status ox_batch_set_step_counter(ox_batch* b, int64_t step) {
 }
 
 // ---- checkpoint / resume: the integration state of mj_step plus the inputs that persist between steps
-static const int kStateFields[] = {OX_F_TIME, OX_F_QPOS, OX_F_QVEL, OX_F_ACT, OX_F_CTRL, OX_F_QFRC_APPLIED, OX_F_XFRC_APPLIED, OX_F_QACC_WARMSTART};
+static const int kStateFields[] = {OX_F_TIME, OX_F_QPOS, OX_F_QVEL, OX_F_ACT, OX_F_CTRL, OX_F_QFRC_APPLIED, OX_F_XFRC_APPLIED, OX_F_QACC_WARMSTART,
+                                   OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE};
 
 int32_t ox_batch_state_size(const ox_batch* b) {
   if (!b) return -1;

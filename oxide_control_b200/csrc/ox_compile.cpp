@@ -73,6 +73,7 @@ const std::map<std::string, std::set<std::string>>& schema() {
                            "actlimited", "user", "tendon", "site", "body", "jointinparent", "lengthrange", "cranklength",
                            "slidersite", "cranksite", "refsite", "actdim", "actearly", "inheritrange", "dampratio", "timeconst"}},
       {"exclude", {"name", "body1", "body2"}},
+      {"equality_common", {"name", "class", "active", "solref", "solimp", "body1", "body2", "anchor", "joint1", "joint2", "polycoef"}},
       {"sensor_common", {"name", "joint", "actuator", "site", "body", "objtype", "objname", "reftype", "refname", "cutoff",
                          "noise", "user"}},
   };
@@ -249,7 +250,7 @@ struct BodyDef {
   std::string name;
   int parent = 0;
   double pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0};
-  bool has_inertial = false;
+  bool has_inertial = false, mocap = false;
   double ipos[3] = {0, 0, 0}, iquat[4] = {1, 0, 0, 0}, mass = 0, inertia[3] = {0, 0, 0};
   std::vector<int> joints, geoms;
 };
@@ -420,7 +421,10 @@ void parse_body(Builder& B, const XmlElem& e, int parent, std::string childclass
     b.name = a.str_or("name", "");
     a.vec("pos", b.pos, 3);
     orientation(B.c, a, b.quat);
-    if (a.has("mocap") && a.str("mocap") == "true") cfail("body '" + b.name + "': mocap bodies are outside the supported subset");
+    if (a.has("mocap") && a.str("mocap") == "true") {
+      if (parent != 0) cfail("body '" + b.name + "': a mocap body must be a child of the world");
+      b.mocap = true;
+    }
     if (a.has("childclass")) {
       childclass = a.str("childclass");
       if (!B.c.defaults.count(childclass)) pfail(e, "unknown default class '" + childclass + "'");
@@ -678,7 +682,7 @@ ox_model* compile_mjcf(const std::string& xml) {
         };
         dis("constraint", OX_DSBL_CONSTRAINT); dis("limit", OX_DSBL_LIMIT); dis("contact", OX_DSBL_CONTACT);
         dis("passive", OX_DSBL_PASSIVE); dis("gravity", OX_DSBL_GRAVITY); dis("clampctrl", OX_DSBL_CLAMPCTRL);
-        dis("warmstart", OX_DSBL_WARMSTART); dis("filterparent", OX_DSBL_FILTERPARENT);
+        dis("warmstart", OX_DSBL_WARMSTART); dis("filterparent", OX_DSBL_FILTERPARENT); dis("equality", OX_DSBL_EQUALITY);
         dis("actuation", OX_DSBL_ACTUATION); dis("refsafe", OX_DSBL_REFSAFE); dis("eulerdamp", OX_DSBL_EULERDAMP);
         for (const char* k : {"energy", "fwdinv", "island", "multiccd", "override"})
           if (auto* s = f->attr(k))
@@ -692,7 +696,9 @@ ox_model* compile_mjcf(const std::string& xml) {
     } else if (n == "asset") {
       for (auto& as : ch->children)
         if (as->name == "mesh" || as->name == "hfield") cfail("asset <" + as->name + "> is outside the supported subset");
-    } else if (n == "equality" || n == "tendon" || n == "deformable" || n == "extension") {
+    } else if (n == "equality") {
+      // compiled after the joints and bodies are known (below)
+    } else if (n == "tendon" || n == "deformable" || n == "extension") {
       if (!ch->children.empty()) cfail("<" + n + "> is outside the supported subset");
     } else {
       pfail(*ch, "unrecognized top-level element");
@@ -990,7 +996,7 @@ ox_model* compile_mjcf(const std::string& xml) {
     t.npair = (int)M->v_pair_geom1.size();
     t.nconmax = nconmax;
     bool limits_on = !(t.disableflags & (OX_DSBL_LIMIT | OX_DSBL_CONSTRAINT));
-    t.nefcmax = (limits_on ? 2 * nlimited : 0) + ncontact_rows;
+    t.nefcmax = (limits_on ? 2 * nlimited : 0) + ncontact_rows;   // equality rows are added once they are compiled (below)
   }
 
   // ---- actuators ----
@@ -1278,6 +1284,79 @@ ox_model* compile_mjcf(const std::string& xml) {
     }
   } else {
     t.meaninertia = 1;
+  }
+
+  // ---- mocap bodies (src/physics.rs:154-170): static children of the world whose pose comes from mjData.mocap_pos / mocap_quat
+  M->v_body_mocapid.assign(nbody, -1);
+  t.nmocap = 0;
+  for (int i = 1; i < nbody; i++) {
+    if (!B.bodies[i].mocap) continue;
+    if (M->v_body_jntnum[i] > 0) cfail("body '" + B.bodies[i].name + "': a mocap body cannot have joints");
+    M->v_body_mocapid[i] = t.nmocap++;
+  }
+
+  // ---- equality constraints (src/physics.rs:147-152 eq_active): connect (3 rows) and joint (1 row); weld / tendon / flex are refused
+  t.neq = 0;
+  {
+    // body frames at qpos0 (joints contribute nothing at the reference configuration)
+    std::vector<double> xpos(3 * nbody, 0), xquat(4 * nbody, 0);
+    xquat[0] = 1;
+    for (int i = 1; i < nbody; i++) {
+      int p = M->v_body_parentid[i];
+      double r[3];
+      hm::rotvec(r, &M->v_body_pos[3 * i], &xquat[4 * p]);
+      for (int k = 0; k < 3; k++) xpos[3 * i + k] = xpos[3 * p + k] + r[k];
+      hm::mulquat(&xquat[4 * i], &xquat[4 * p], &M->v_body_quat[4 * i]);
+      hm::normalize4(&xquat[4 * i]);
+    }
+    int eq_rows = 0;
+    for (auto& ch : root->children)
+      if (ch->name == "equality")
+        for (auto& e : ch->children) {
+          if (e->name != "connect" && e->name != "joint") cfail("equality <" + e->name + "> is outside the supported subset (connect, joint)");
+          check_attrs(*e, "equality_common");
+          Attrs a = merged(B.c, *e, "equality", "");
+          const std::string ename = a.str_or("name", "");
+          double solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2}, data[11] = {0};
+          a.vec("solref", solref, 2);
+          a.vec("solimp", solimp, 5, true);
+          int type, o1, o2 = -1;
+          if (e->name == "connect") {
+            type = OX_EQ_CONNECT;
+            if (!a.has("body1") || !a.has("anchor")) pfail(*e, "connect requires body1 and anchor");
+            o1 = find_name(nm[OX_OBJ_BODY], a.str("body1"));
+            if (o1 < 0) cfail("equality '" + ename + "': unknown body '" + a.str("body1") + "'");
+            o2 = 0;
+            if (a.has("body2")) { o2 = find_name(nm[OX_OBJ_BODY], a.str("body2")); if (o2 < 0) cfail("equality '" + ename + "': unknown body '" + a.str("body2") + "'"); }
+            a.vec("anchor", data, 3);
+            // anchor in body2's frame such that both anchors coincide at qpos0
+            double w[3], d2[3], q2c[4] = {xquat[4 * o2], -xquat[4 * o2 + 1], -xquat[4 * o2 + 2], -xquat[4 * o2 + 3]};
+            hm::rotvec(w, data, &xquat[4 * o1]);
+            for (int k = 0; k < 3; k++) d2[k] = xpos[3 * o1 + k] + w[k] - xpos[3 * o2 + k];
+            hm::rotvec(data + 3, d2, q2c);
+            eq_rows += 3;
+          } else {
+            type = OX_EQ_JOINT;
+            if (!a.has("joint1")) pfail(*e, "joint equality requires joint1");
+            o1 = find_name(nm[OX_OBJ_JOINT], a.str("joint1"));
+            if (o1 < 0) cfail("equality '" + ename + "': unknown joint '" + a.str("joint1") + "'");
+            if (a.has("joint2")) { o2 = find_name(nm[OX_OBJ_JOINT], a.str("joint2")); if (o2 < 0) cfail("equality '" + ename + "': unknown joint '" + a.str("joint2") + "'"); }
+            for (int j : {o1, o2})
+              if (j >= 0 && B.joints[j].type != OX_JNT_HINGE && B.joints[j].type != OX_JNT_SLIDE) cfail("equality '" + ename + "': joint equalities couple hinge / slide joints");
+            data[1] = 1;  // polycoef default "0 1 0 0 0"
+            a.vec("polycoef", data, 5, true);
+            eq_rows += 1;
+          }
+          const int act = a.boolean("active");
+          M->v_eq_type.push_back(type); M->v_eq_obj1id.push_back(o1); M->v_eq_obj2id.push_back(o2); M->v_eq_active0.push_back(act == 0 ? 0 : 1);
+          for (double v : solref) M->v_eq_solref.push_back(v);
+          for (double v : solimp) M->v_eq_solimp.push_back(v);
+          for (double v : data) M->v_eq_data.push_back(v);
+          nm[OX_OBJ_EQUALITY].push_back(ename);
+          t.neq++;
+        }
+    if (!(t.disableflags & (OX_DSBL_EQUALITY | OX_DSBL_CONSTRAINT))) t.nefcmax += eq_rows;
+    check_unique(OX_OBJ_EQUALITY, "equality");
   }
 
   M->finalize();

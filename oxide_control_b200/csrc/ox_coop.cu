@@ -33,11 +33,11 @@ constexpr int CP_SROWS = 32;   // constraint rows of J staged in shared memory f
 // ---- per-group shared-memory layout: [DevBatch<T> view][int scalars + body levels][real fields][solver scratch]
 template <typename T>
 struct CoopSizes {
-  int nq, nv, nu, na, nb, nj, ng, ns, nM, ncm, nem, nsd;
+  int nq, nv, nu, na, nb, nj, ng, ns, nM, ncm, nem, nsd, nmc, neq;
   OX_HD static CoopSizes from(const BlobHeader& h) {
     CoopSizes s;
     s.nq = h.nq; s.nv = h.nv; s.nu = h.nu; s.na = h.na; s.nb = h.nbody; s.nj = h.njnt; s.ng = h.ngeom; s.ns = h.nsite; s.nM = h.nM;
-    s.ncm = h.nconmax > 1 ? h.nconmax : 1; s.nem = h.nefcmax > 1 ? h.nefcmax : 1; s.nsd = h.nsensordata;
+    s.ncm = h.nconmax > 1 ? h.nconmax : 1; s.nem = h.nefcmax > 1 ? h.nefcmax : 1; s.nsd = h.nsensordata; s.nmc = h.nmocap; s.neq = h.neq;
     return s;
   }
 };
@@ -46,8 +46,8 @@ constexpr int COOP_NINT = 16;  // int scalars (ncon, nefc, ...) rounded up
 // words of T of shared memory one group needs (G enters through the solver scratch)
 template <typename T>
 OX_HD size_t coop_group_bytes(const CoopSizes<T>& z, int G) {
-  const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd;
-  (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd;
+  const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
+  (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq;
   size_t words = 0;
 #define OX_X(name, cnt) words += (size_t)((cnt) > 0 ? (cnt) : 1);
   OX_BATCH_REAL_FIELDS_SMALL(OX_X)
@@ -268,6 +268,16 @@ struct Coop {
     const DevBatch<T>& b = env.b;
     int base = 0;
     if (!env.dis(OX_DSBL_CONSTRAINT)) {
+      if (!env.dis(OX_DSBL_EQUALITY)) {
+        for (int i0 = 0; i0 < h.neq; i0 += G) {
+          const int i = i0 + gl;
+          const int cnt = i < h.neq ? env.equality_count(i) : 0;
+          int r = base + gscan_excl(cnt);
+          if (cnt) env.equality_rows(i, r);
+          base += gsumi(cnt);
+        }
+      }
+      if (gl == 0) b.ne[0] = base;
       if (!env.dis(OX_DSBL_LIMIT)) {
         for (int j0 = 0; j0 < h.njnt; j0 += G) {
           const int j = j0 + gl;
@@ -290,7 +300,7 @@ struct Coop {
         base += gsumi(cnt);
       }
     }
-    if (gl == 0) b.nefc[0] = base;
+    if (gl == 0) { b.nefc[0] = base; if (env.dis(OX_DSBL_CONSTRAINT)) b.ne[0] = 0; }
     gsync();
   }
   __device__ void actuation_and_smooth() const {
@@ -325,7 +335,7 @@ struct Coop {
     const auto& m = env.m;
     const auto& h = m.h();
     const DevBatch<T>& b = env.b;
-    const int nv = h.nv, nefc = b.nefc[0];
+    const int nv = h.nv, nefc = b.nefc[0], ne = b.ne[0];   // rows below ne are equality rows: active on both sides
     const bool me = gl < nv;
     if (nefc == 0) {
       if (me) { const T a = b.qacc_smooth[gl]; b.qacc[gl] = a; b.qacc_warmstart[gl] = a; b.qfrc_constraint[gl] = 0; }
@@ -373,7 +383,7 @@ struct Coop {
         Jdot(x, rowJv, true);
         for (int r = gl; r < nefc; r += G) {
           const T v = rowJv[r];
-          if (v < 0) cc += (T)0.5 * rowD[r] * v * v;
+          if (v < 0 || r < ne) cc += (T)0.5 * rowD[r] * v * v;
         }
         cand[c] = gsum(cc);
         gsync();
@@ -414,7 +424,7 @@ struct Coop {
           for (int r = gl; r < nefc; r += G) {
             const T ja = rowJar[r], jvr = rowJv[r];
             const T x = ja + an * jvr;
-            if (x < 0) {
+            if (x < 0 || r < ne) {
               const T Dx = rowD[r] * x, Dj = rowD[r] * jvr;
               c += (T)0.5 * Dx * x;
               d0 += Dx * jvr;
@@ -450,7 +460,7 @@ struct Coop {
         for (int r = gl; r < nefc; r += G) {
           const T ja = rowJar[r];
           T f = 0;
-          if (ja < 0) { f = -rowD[r] * ja; crow += (T)0.5 * rowD[r] * ja * ja; }
+          if (ja < 0 || r < ne) { f = -rowD[r] * ja; crow += (T)0.5 * rowD[r] * ja * ja; }
           rowF[r] = f;
         }
         gsync();
@@ -469,7 +479,7 @@ struct Coop {
 #pragma unroll
         for (int j = 0; j < G; j++) Hreg[j] = Mrow[j];
         for (int r = 0; r < nefc; r++) {
-          if (!(rowJar[r] < 0)) continue;  // group-uniform
+          if (!(rowJar[r] < 0 || r < ne)) continue;  // group-uniform
           if (r < CP_SROWS) {
             const T* jr = sJ + r * (G + 1);
             const T s = rowD[r] * jr[gl];
@@ -625,8 +635,8 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   T* rb = reinterpret_cast<T*>(base + (sizeof(DevBatch<T>) + (COOP_NINT + (size_t)h.nbody) * sizeof(int32_t) + 15) / 16 * 16);
   const CoopSizes<T> z = CoopSizes<T>::from(h);
   if (gl == 0) {
-    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, ncm = z.ncm, nem = z.nem, nsd = z.nsd;
-    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)ncm; (void)nem; (void)nsd;
+    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, ncm = z.ncm, nem = z.nem, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
+    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)ncm; (void)nem; (void)nsd; (void)nmc; (void)neq;
     lb->nenv = 1; lb->stride = 1; lb->lanes = 32;
     T* p = rb;
 #define OX_X(name, cnt) lb->name = p; p += ((cnt) > 0 ? (cnt) : 1);
@@ -645,8 +655,8 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   __syncwarp(gmask);
   T* scratch = rb;
   {
-    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd;
-    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd;
+    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
+    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq;
 #define OX_X(name, cnt) scratch += ((cnt) > 0 ? (cnt) : 1);
     OX_BATCH_REAL_FIELDS_SMALL(OX_X)
 #undef OX_X
@@ -667,11 +677,14 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   c.each(h.nv, [&](int i) { b.qvel[i] = GA(qvel, i); b.qacc_warmstart[i] = GA(qacc_warmstart, i); b.qfrc_applied[i] = a.applied ? GA(qfrc_applied, i) : (T)0; b.qacc[i] = 0; });
   c.each(h.nu, [&](int i) { b.ctrl[i] = GA(ctrl, i); });
   c.each(h.na, [&](int i) { b.act[i] = GA(act, i); b.act_dot[i] = 0; });
+  c.each(3 * h.nmocap, [&](int i) { b.mocap_pos[i] = GA(mocap_pos, i); });
+  c.each(4 * h.nmocap, [&](int i) { b.mocap_quat[i] = GA(mocap_quat, i); });
+  c.each(h.neq, [&](int i) { b.eq_active[i] = GA(eq_active, i); });
   c.each(6 * h.nbody, [&](int i) { b.xfrc_applied[i] = a.applied ? GA(xfrc_applied, i) : (T)0; });
   if (gl == 0) {
     b.time[0] = GA(time, 0);
     b.diverged[0] = g.diverged[ue]; b.acc_ncon[0] = g.acc_ncon[ue]; b.acc_nefc[0] = g.acc_nefc[ue]; b.acc_niter[0] = g.acc_niter[ue];
-    b.ncon[0] = 0; b.nefc[0] = 0; b.solver_niter[0] = 0;
+    b.ncon[0] = 0; b.nefc[0] = 0; b.solver_niter[0] = 0; b.ne[0] = 0;
   }
   }
   __syncwarp(gmask);
@@ -693,6 +706,9 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   c.each(h.nsensordata, [&](int i) { GA(sensordata, i) = b.sensordata[i]; });
   if (a.philox || did_reset) c.each(h.nu, [&](int i) { GA(ctrl, i) = b.ctrl[i]; });
   if (did_reset) {
+    c.each(3 * h.nmocap, [&](int i) { GA(mocap_pos, i) = b.mocap_pos[i]; });
+    c.each(4 * h.nmocap, [&](int i) { GA(mocap_quat, i) = b.mocap_quat[i]; });
+    c.each(h.neq, [&](int i) { GA(eq_active, i) = b.eq_active[i]; });
     c.each(h.nv, [&](int i) { GA(qfrc_applied, i) = b.qfrc_applied[i]; });
     c.each(6 * h.nbody, [&](int i) { GA(xfrc_applied, i) = b.xfrc_applied[i]; });
   }
@@ -716,7 +732,7 @@ template <typename T>
 static size_t coop_group_bytes_host(const ox_model_tables& t, int G) {
   CoopSizes<T> z;
   z.nq = t.nq; z.nv = t.nv; z.nu = t.nu; z.na = t.na; z.nb = t.nbody; z.nj = t.njnt; z.ng = t.ngeom; z.ns = t.nsite; z.nM = t.nM;
-  z.ncm = t.nconmax > 1 ? t.nconmax : 1; z.nem = t.nefcmax > 1 ? t.nefcmax : 1; z.nsd = t.nsensordata;
+  z.ncm = t.nconmax > 1 ? t.nconmax : 1; z.nem = t.nefcmax > 1 ? t.nefcmax : 1; z.nsd = t.nsensordata; z.nmc = t.nmocap; z.neq = t.neq;
   return coop_group_bytes<T>(z, G);
 }
 size_t step_coop_smem(const ox_model_tables& t, int blob_bytes, bool f64) {

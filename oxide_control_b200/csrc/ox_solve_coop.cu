@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
   const bool me = lane < nv;
   const uint32_t S = (uint32_t)b.stride, ue = (uint32_t)env;
 #define GA(field, i) b.field[(uint32_t)(i) * S + ue]
-  const int nefc = b.nefc[ue];
+  const int nefc = b.nefc[ue], ne = b.ne[ue];   // rows below ne are equality rows: active on both sides
   if (nefc == 0) {
     if (me) {
       const T a = GA(qacc_smooth, lane);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
       Jdot(x, rowJv, true);
       for (int r = lane; r < nefc; r += 32) {
         const T v = ROW(rowJv, r);
-        if (v < 0) cc += (T)0.5 * ROW(rowD, r) * v * v;
+        if (v < 0 || r < ne) cc += (T)0.5 * ROW(rowD, r) * v * v;
       }
       cand[c] = wsum(cc);
       __syncwarp();
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
         for (int r = lane; r < nefc; r += 32) {
           const T ja = ROW(rowJar, r), jvr = ROW(rowJv, r);
           const T x = ja + an * jvr;
-          if (x < 0) {
+          if (x < 0 || r < ne) {
             const T Dx = ROW(rowD, r) * x, Dj = ROW(rowD, r) * jvr;
             c += (T)0.5 * Dx * x;
             d0 += Dx * jvr;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
       for (int r = lane; r < nefc; r += 32) {
         const T ja = ROW(rowJar, r);
         T f = 0;
-        if (ja < 0) { f = -ROW(rowD, r) * ja; crow += (T)0.5 * ROW(rowD, r) * ja * ja; }
+        if (ja < 0 || r < ne) { f = -ROW(rowD, r) * ja; crow += (T)0.5 * ROW(rowD, r) * ja * ja; }
         ROW(rowF, r) = f;
       }
       __syncwarp();
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
 #pragma unroll
       for (int j = 0; j < 32; j++) Hreg[j] = Mrow[j];
       for (int r = 0; r < nefc; r++) {
-        if (!(ROW(rowJar, r) < 0)) continue;  // warp-uniform
+        if (!(ROW(rowJar, r) < 0 || r < ne)) continue;  // warp-uniform
         if (r < COOP_SROWS) {
           const T* jr = sJ + r * 33;  // padding columns nv..31 are zero
           const T s = ROW(rowD, r) * jr[lane];

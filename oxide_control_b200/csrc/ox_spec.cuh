@@ -45,7 +45,7 @@ inline uint64_t model_hash(const ox_model_tables& t) {
     const unsigned char* c = static_cast<const unsigned char*>(p);
     for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
   };
-  const int32_t sizes[] = {t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
+  const int32_t sizes[] = {t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
                            t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags};
   mix(sizes, sizeof sizes);
   const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia};
@@ -72,7 +72,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   // struct): each array whose indices all fold to constants after unrolling is promoted to registers independently;
   // only the runtime-indexed ones (contact / constraint rows and what the contact Jacobian walk reads) stay in local memory.
   constexpr int nq = H::nq, nv = H::nv, nu = H::nu, na = H::na, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
-                ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata;
+                ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata, nmc = H::nmocap, neq = H::neq;
 #define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v];
   OX_BATCH_REAL_FIELDS(OX_X)
 #undef OX_X
@@ -110,6 +110,12 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     for (int i = 0; i < H::nv; i++) loc_qacc_warmstart[i] = G(qacc_warmstart, i);
 #pragma unroll
     for (int i = 0; i < H::nu; i++) loc_ctrl[i] = G(ctrl, i);
+#pragma unroll
+    for (int i = 0; i < 3 * H::nmocap; i++) loc_mocap_pos[i] = G(mocap_pos, i);
+#pragma unroll
+    for (int i = 0; i < 4 * H::nmocap; i++) loc_mocap_quat[i] = G(mocap_quat, i);
+#pragma unroll
+    for (int i = 0; i < H::neq; i++) loc_eq_active[i] = G(eq_active, i);
     if (a.applied) {
 #pragma unroll
       for (int i = 0; i < H::nv; i++) loc_qfrc_applied[i] = G(qfrc_applied, i);
@@ -133,6 +139,12 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
     G(diverged, 0) = loc_diverged[0];
     if (inputs_too) {  // an auto-reset cleared them
 #pragma unroll
+      for (int i = 0; i < 3 * H::nmocap; i++) G(mocap_pos, i) = loc_mocap_pos[i];
+#pragma unroll
+      for (int i = 0; i < 4 * H::nmocap; i++) G(mocap_quat, i) = loc_mocap_quat[i];
+#pragma unroll
+      for (int i = 0; i < H::neq; i++) G(eq_active, i) = loc_eq_active[i];
+#pragma unroll
       for (int i = 0; i < H::nv; i++) { G(qacc_warmstart, i) = loc_qacc_warmstart[i]; G(qfrc_applied, i) = loc_qfrc_applied[i]; }
 #pragma unroll
       for (int i = 0; i < 6 * H::nbody; i++) G(xfrc_applied, i) = loc_xfrc_applied[i];
@@ -141,7 +153,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   if constexpr (PHASE == 0) {
     load_inputs();
     loc_acc_ncon[0] = G(acc_ncon, 0); loc_acc_nefc[0] = G(acc_nefc, 0); loc_acc_niter[0] = G(acc_niter, 0);
-    loc_ncon[0] = 0; loc_nefc[0] = 0; loc_solver_niter[0] = 0;
+    loc_ncon[0] = 0; loc_nefc[0] = 0; loc_solver_niter[0] = 0; loc_ne[0] = 0;
 #pragma unroll
     for (int i = 0; i < H::nv; i++) loc_qacc[i] = 0;
     for (int s = 0; s < a.nsteps; s++) {
@@ -189,7 +201,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
 #pragma unroll
     for (int i = 0; i < H::nsensordata; i++) G(sensordata, i) = loc_sensordata[i];
     const int nefc = loc_nefc[0];
-    G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = nefc;
+    G(ncon, 0) = loc_ncon[0]; G(nefc, 0) = nefc; G(ne, 0) = loc_ne[0];
     for (int r = 0; r < nefc; r++) {
       G(efc_D, r) = loc_efc_D[r]; G(efc_aref, r) = loc_efc_aref[r]; G(efc_pos, r) = loc_efc_pos[r]; G(efc_margin, r) = loc_efc_margin[r];
 #pragma unroll

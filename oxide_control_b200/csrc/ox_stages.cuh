@@ -255,7 +255,12 @@ struct Env {
         quat[0] = 1; quat[1] = quat[2] = quat[3] = 0;
       } else {
         const int jntadr = m.body_jntadr(i), jntnum = m.body_jntnum(i);
-        if (jntnum == 1 && m.jnt_type(jntadr) == OX_JNT_FREE) {
+        const int mocapid = m.h().nmocap > 0 ? m.body_mocapid(i) : -1;
+        if (mocapid >= 0) {   // mocap body: pose straight from mjData (mj_kinematics), quaternion normalised on the fly
+          ld<3>(pos, b.mocap_pos, 3 * mocapid);
+          ld<4>(quat, b.mocap_quat, 4 * mocapid);
+          normalize4(quat);
+        } else if (jntnum == 1 && m.jnt_type(jntadr) == OX_JNT_FREE) {
           const int qadr = m.jnt_qposadr(jntadr);
           ld<3>(pos, b.qpos, qadr);
           ld<4>(quat, b.qpos, qadr + 3);
@@ -1126,7 +1131,13 @@ struct Env {
     const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
     int nefc = 0;
+    ati(b.ne, 0) = 0;
     if (!dis(OX_DSBL_CONSTRAINT)) {
+      if (!dis(OX_DSBL_EQUALITY)) {   // equality rows come first (mj_makeConstraint order) and are always active in the solver
+        OX_MLOOP
+        for (int i = 0; i < h.neq; i++) equality_rows(i, nefc);
+      }
+      ati(b.ne, 0) = nefc;
       bool any_limit = false;  // one test for "no joint is near a limit" (the common case), see fwd_acceleration
       if (!dis(OX_DSBL_LIMIT)) {
         OX_MLOOP
@@ -1161,6 +1172,86 @@ struct Env {
       }
     }
     ati(b.nefc, 0) = nefc;
+  }
+  // rows of equality constraint i (mj_instantiateEquality): connect = the two anchors coincide (3 rows), joint = q1 tracks a
+  // quartic polynomial of q2 (1 row). pos = residual, margin = 0.
+  OX_HD int equality_count(int i) const {
+    if (!(at(b.eq_active, i) != 0)) return 0;
+    return m.eq_type(i) == OX_EQ_CONNECT ? 3 : 1;
+  }
+  OX_HD void eq_row_finish(int i, int r, T pos, T diag) const {
+    const int nv = m.h().nv;
+    T vel = 0;
+    OX_MLOOP
+    for (int k = 0; k < nv; k++) vel += at(b.efc_J, r * nv + k) * at(b.qvel, k);
+    T sr[2], si[5], aref;
+    OX_LDM(2, sr, eq_solref, 2 * i);
+    OX_LDM(5, si, eq_solimp, 5 * i);
+    const T R = row_params(sr, si, pos, (T)0, diag, vel, &aref);
+    at(b.efc_pos, r) = pos; at(b.efc_margin, r) = 0; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
+  }
+  OX_HD void equality_rows(int i, int& nefc) const {
+    const int nv = m.h().nv;
+    if (!(at(b.eq_active, i) != 0)) return;
+    if (m.eq_type(i) == OX_EQ_CONNECT) {
+      const int b1 = m.eq_obj1id(i), b2 = m.eq_obj2id(i);
+      T p[2][3];
+      const int bodies[2] = {b1, b2};
+      OX_MLOOP
+      for (int s = 0; s < 2; s++) {
+        T mat[9], xp[3], a[3], w[3];
+        ld<9>(mat, b.xmat, 9 * bodies[s]);
+        ld<3>(xp, b.xpos, 3 * bodies[s]);
+        OX_LDM(3, a, eq_data, 11 * i + 3 * s);
+        mat_vec3(w, mat, a);
+        p[s][0] = xp[0] + w[0]; p[s][1] = xp[1] + w[1]; p[s][2] = xp[2] + w[2];
+      }
+      const int r0 = nefc;
+      nefc += 3;
+      OX_MLOOP
+      for (int k = 0; k < 3 * nv; k++) at(b.efc_J, r0 * nv + k) = 0;
+      OX_MLOOP
+      for (int s = 0; s < 2; s++) {   // J = Jp(body1, p1) - Jp(body2, p2), rows = world x, y, z
+        const T sign = s == 0 ? (T)1 : (T)-1;
+        int body = m.body_weldid(bodies[s]);
+        if (!body) continue;
+        T sc[3], offset[3];
+        ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bodies[s]));
+        offset[0] = p[s][0] - sc[0]; offset[1] = p[s][1] - sc[1]; offset[2] = p[s][2] - sc[2];
+        const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+        OX_MLOOP
+        for (int d_ = 0, dof = last_; d_ < m.dof_depth(last_); d_++, dof = m.dof_parentid(dof)) {
+          T cd[6], jp[3];
+          ld<6>(cd, b.cdof, 6 * dof);
+          cross3(jp, cd, offset);
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) at(b.efc_J, (r0 + k) * nv + dof) += sign * (jp[k] + cd[3 + k]);
+        }
+      }
+      const T diag = m.body_invweight0(2 * b1) + m.body_invweight0(2 * b2);
+      OX_MLOOP
+      for (int k = 0; k < 3; k++) eq_row_finish(i, r0 + k, p[0][k] - p[1][k], diag);
+    } else {
+      const int j1 = m.eq_obj1id(i), j2 = m.eq_obj2id(i);
+      const int d1 = m.jnt_dofadr(j1), q1 = m.jnt_qposadr(j1);
+      const int r = nefc++;
+      OX_MLOOP
+      for (int k = 0; k < nv; k++) at(b.efc_J, r * nv + k) = 0;
+      T c[5];
+      OX_LDM(5, c, eq_data, 11 * i);
+      T pos = at(b.qpos, q1) - m.qpos0(q1), diag = m.dof_invweight0(d1);
+      at(b.efc_J, r * nv + d1) = 1;
+      if (j2 >= 0) {
+        const int d2 = m.jnt_dofadr(j2), q2 = m.jnt_qposadr(j2);
+        const T dq = at(b.qpos, q2) - m.qpos0(q2);
+        pos -= c[0] + dq * (c[1] + dq * (c[2] + dq * (c[3] + dq * c[4])));
+        at(b.efc_J, r * nv + d2) = -(c[1] + dq * (2 * c[2] + dq * (3 * c[3] + dq * 4 * c[4])));
+        diag += m.dof_invweight0(d2);
+      } else {
+        pos -= c[0];
+      }
+      eq_row_finish(i, r, pos, diag);
+    }
   }
   // number of limit rows joint j contributes (0, 1 or 2) and the rows themselves
   OX_HD int limit_count(int j) const {
@@ -1204,6 +1295,7 @@ struct Env {
   struct LsPt { T alpha, cost, d0, d1, s0; };  // s0 = sum of |terms| of d0: the resolution of the derivative
 
   OX_HD LsPt ls_eval(T a, int nefc, T qg0, T qg1, T qg2) const {
+    const int ne_ = ati(b.ne, 0);
     LsPt p;
     p.alpha = a;
     p.cost = a * a * qg2 + a * qg1 + qg0;
@@ -1214,7 +1306,7 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
-      if (x < 0) {  // active at alpha: 1/2 D x^2 and its first / second derivative in alpha
+      if (x < 0 || r < ne_) {  // active at alpha (equality rows always): 1/2 D x^2 and its first / second derivative in alpha
         const T Dx = at(b.efc_D, r) * x, Dj = at(b.efc_D, r) * jv;
         p.cost += (T)0.5 * Dx * x;
         p.d0 += Dx * jv;
@@ -1228,6 +1320,7 @@ struct Env {
 
   // efc_force, qfrc_constraint and total cost at the current (qacc, Ma, Jaref); returns cost, gauss via pointer
   OX_HD T update_constraint(int nv, int nefc, T* gauss_out) const {
+    const int ne_ = ati(b.ne, 0);
     T c = 0;
     OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
@@ -1235,7 +1328,7 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r);
       T f = 0;
-      if (ja < 0) {
+      if (ja < 0 || r < ne_) {
         const T D = at(b.efc_D, r);
         f = -D * ja;
         c += (T)0.5 * D * ja * ja;
@@ -1267,6 +1360,7 @@ struct Env {
       return ox_sqrt(gn);
     }
     T* H = b.s_H;
+    const int ne_ = ati(b.ne, 0);
     OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       OX_NVLOOP
@@ -1277,7 +1371,7 @@ struct Env {
     }
     OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
-      if (!(at(b.s_Jaref, r) < 0)) continue;
+      if (!(at(b.s_Jaref, r) < 0 || r < ne_)) continue;
       const T D = at(b.efc_D, r);
       if constexpr (UNROLL_NV) {  // the row once into registers, then the rank-1 update on register-resident H
         constexpr int NV = M::Hdr::nv;
@@ -1332,6 +1426,7 @@ struct Env {
   }
 
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
+    const int ne_ = ati(b.ne, 0);
     mul_m(b.s_Mv, qacc);
     T c = 0;
     OX_NVLOOP
@@ -1341,7 +1436,7 @@ struct Env {
       T v = -at(b.efc_aref, r);
       OX_NVLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(qacc, i);
-      if (v < 0) c += (T)0.5 * at(b.efc_D, r) * v * v;
+      if (v < 0 || r < ne_) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
     return c;
   }
@@ -1892,10 +1987,23 @@ struct Env {
     for (int i = 0; i < h.nu; i++) at(b.ctrl, i) = 0;
     OX_MLOOP
     for (int i = 0; i < h.na; i++) { at(b.act, i) = 0; at(b.act_dot, i) = 0; }
+    if (h.nmocap > 0) {
+      OX_MLOOP
+      for (int i = 1; i < h.nbody; i++) {
+        const int id = m.body_mocapid(i);
+        if (id < 0) continue;
+        OX_MLOOP
+        for (int k = 0; k < 3; k++) at(b.mocap_pos, 3 * id + k) = m.body_pos(3 * i + k);
+        OX_MLOOP
+        for (int k = 0; k < 4; k++) at(b.mocap_quat, 4 * id + k) = m.body_quat(4 * i + k);
+      }
+    }
+    OX_MLOOP
+    for (int i = 0; i < h.neq; i++) at(b.eq_active, i) = (T)m.eq_active0(i);
     OX_MLOOP
     for (int i = 0; i < 6 * h.nbody; i++) at(b.xfrc_applied, i) = 0;
     at(b.time, 0) = 0;
-    ati(b.ncon, 0) = 0; ati(b.nefc, 0) = 0; ati(b.solver_niter, 0) = 0;
+    ati(b.ncon, 0) = 0; ati(b.nefc, 0) = 0; ati(b.solver_niter, 0) = 0; ati(b.ne, 0) = 0;
   }
   OX_HD bool bad_state() const {
     const auto& h = m.h();

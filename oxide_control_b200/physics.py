@@ -624,22 +624,43 @@ class Physics:
         assert v.shape == (6,)
         self._b.set1("xfrc_applied", 0, v, 6 * id.index)
 
-    # src/physics.rs:147-152: no equality constraints in the supported subset (neq = 0)
+    # src/physics.rs:147-152: equality constraints (connect, joint) can be switched on and off at run time
     def eq_active(self, id: ObjectId) -> bool:
-        raise Error("model has no equality constraints (neq = 0)")
+        if not self._model.neq:
+            raise Error("model has no equality constraints (neq = 0)")
+        return bool(self._b.get1("eq_active", 0, id.index, 1)[0] != 0)
 
     def set_eq_active(self, id: ObjectId, value: bool) -> None:
-        raise Error("model has no equality constraints (neq = 0)")
+        if not self._model.neq:
+            raise Error("model has no equality constraints (neq = 0)")
+        self._b.set1("eq_active", 0, [1.0 if value else 0.0], id.index)
 
-    # src/physics.rs:154-170: None when the body is not a mocap body (none are)
+    # src/physics.rs:154-170: None when the body is not a mocap body
+    def _mocapid(self, id: ObjectId) -> int:
+        return int(self._model.body_mocapid[id.index]) if self._model.nmocap else -1
+
     def mocap_pos(self, id: ObjectId):
-        return None
+        mid = self._mocapid(id)
+        return None if mid < 0 else self._b.get1("mocap_pos", 0, 3 * mid, 3)
 
     def set_mocap_pos(self, id: ObjectId, pos):
-        return None
+        mid = self._mocapid(id)
+        if mid < 0:
+            return None
+        v = np.asarray(pos, dtype=np.float64)
+        assert v.shape == (3,)
+        self._b.set1("mocap_pos", 0, v, 3 * mid)
+        return ()
 
     def mocap_quat(self, id: ObjectId):
-        return None
+        mid = self._mocapid(id)
+        return None if mid < 0 else self._b.get1("mocap_quat", 0, 4 * mid, 4)
 
     def set_mocap_quat(self, id: ObjectId, quat):
-        return None
+        mid = self._mocapid(id)
+        if mid < 0:
+            return None
+        v = np.asarray(quat, dtype=np.float64)
+        assert v.shape == (4,)
+        self._b.set1("mocap_quat", 0, v, 4 * mid)
+        return ()

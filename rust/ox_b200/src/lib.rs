@@ -327,18 +327,32 @@ impl Physics {
     }
     pub fn set_xfrc_applied(&mut self, id: ObjectId<obj::Body>, value: [f64; 6]) { self.put(sys::OX_F_XFRC_APPLIED, 6 * id.index, &value); }   // :143-145
 
-    /// Equality constraints are outside the supported MJCF subset (the compiler refuses them), so no id can exist.   // :147-149
-    pub fn eq_active(&self, _id: ObjectId<obj::Equality>) -> bool { false }
-    pub fn set_eq_active(&mut self, _id: ObjectId<obj::Equality>, _value: bool) {}                       // :150-152
+    /// Whether equality constraint `id` (connect / joint) is currently enforced.                                     // :147-149
+    pub fn eq_active(&self, id: ObjectId<obj::Equality>) -> bool { self.scalar(sys::OX_F_EQ_ACTIVE, id.index) != 0.0 }
+    pub fn set_eq_active(&mut self, id: ObjectId<obj::Equality>, value: bool) { self.put(sys::OX_F_EQ_ACTIVE, id.index, &[if value { 1.0 } else { 0.0 }]); }   // :150-152
 
-    /// `None` when the body is not a mocap body (mocap bodies are outside the supported subset: always `None`).      // :154-157
-    pub fn mocap_pos(&self, _id: ObjectId<obj::Body>) -> Option<[f64; 3]> { None }
+    fn mocap_id(&self, id: ObjectId<obj::Body>) -> Option<usize> {
+        let t = self.model.int_table("body_mocapid");
+        if id.index < t.len() && t[id.index] >= 0 { Some(t[id.index] as usize) } else { None }
+    }
+    /// `None` when the body is not a mocap body.                                                      // :154-157
+    pub fn mocap_pos(&self, id: ObjectId<obj::Body>) -> Option<[f64; 3]> {
+        let m = self.mocap_id(id)?;
+        let mut v = [0.0; 3];
+        let _ = self.data.get1(sys::OX_F_MOCAP_POS, 0, 3 * m, &mut v);
+        Some(v)
+    }
     /// Set the mocap position. Returns `None` if the body is not a mocap body.                        // :158-161
-    pub fn set_mocap_pos(&mut self, _id: ObjectId<obj::Body>, _pos: [f64; 3]) -> Option<()> { None }
+    pub fn set_mocap_pos(&mut self, id: ObjectId<obj::Body>, pos: [f64; 3]) -> Option<()> { let m = self.mocap_id(id)?; self.put(sys::OX_F_MOCAP_POS, 3 * m, &pos); Some(()) }
     /// `None` when the body is not a mocap body.                                                      // :163-166
-    pub fn mocap_quat(&self, _id: ObjectId<obj::Body>) -> Option<[f64; 4]> { None }
+    pub fn mocap_quat(&self, id: ObjectId<obj::Body>) -> Option<[f64; 4]> {
+        let m = self.mocap_id(id)?;
+        let mut v = [0.0; 4];
+        let _ = self.data.get1(sys::OX_F_MOCAP_QUAT, 0, 4 * m, &mut v);
+        Some(v)
+    }
     /// Set the mocap quaternion. Returns `None` if the body is not a mocap body.                      // :167-170
-    pub fn set_mocap_quat(&mut self, _id: ObjectId<obj::Body>, _quat: [f64; 4]) -> Option<()> { None }
+    pub fn set_mocap_quat(&mut self, id: ObjectId<obj::Body>, quat: [f64; 4]) -> Option<()> { let m = self.mocap_id(id)?; self.put(sys::OX_F_MOCAP_QUAT, 4 * m, &quat); Some(()) }
 }
 
 // ------------------------------------------------------------------------------------------------ Environment (src/lib.rs)

@@ -33,7 +33,7 @@ MINVAL, MINIMP, MAXIMP = 1e-15, 1e-4, 0.9999
 PLANE, SPHERE, CAPSULE, BOX = 0, 2, 3, 6
 FREE, BALL, SLIDE, HINGE = 0, 1, 2, 3
 DSBL = dict(constraint=1 << 0, limit=1 << 3, contact=1 << 4, passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7,
-            filterparent=1 << 9, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
+            filterparent=1 << 9, equality=1 << 1, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
 
 
 def _T(a):
@@ -70,16 +70,17 @@ class DenseModel:
     INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
            "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
-           "actuator_dyntype", "actuator_actadr", "actuator_actlimited"]
+           "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
             "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
             "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
             "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
-            "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange"]
+            "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange",
+            "eq_solref", "eq_solimp", "eq_data"]
 
     def __init__(self, model):
         self.m = model
-        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags"):
+        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq"):
             setattr(self, k, int(getattr(model, k)))
         for k in ("timestep", "impratio"):
             setattr(self, k, float(getattr(model, k)))
@@ -94,8 +95,8 @@ class DenseModel:
 
 
 # ------------------------------------------------------------------------------------------------ kinematics (autodiff)
-def fk(dm: DenseModel, qpos, x):
-    """Body frames from generalised coordinates. x[nv]: hinge/slide coordinates; for free joints global position + a LOCAL
+def fk(dm: DenseModel, qpos, x, mocap=None):
+    """Body frames from generalised coordinates. mocap = (mocap_pos, mocap_quat) for models with mocap bodies. x[nv]: hinge/slide coordinates; for free joints global position + a LOCAL
     rotation vector on top of the quaternion stored in qpos (evaluated at 0); for ball joints a local rotation vector.
     d/dt x = qvel in MuJoCo's convention. Returns P[nbody,3], R[nbody,3,3]."""
     P, R = [torch.zeros(3)], [torch.eye(3)]
@@ -103,6 +104,10 @@ def fk(dm: DenseModel, qpos, x):
         p = int(dm.body_parentid[b])
         Pb = P[p] + R[p] @ _T(dm.body_pos[3 * b:3 * b + 3])
         Rb = R[p] @ quat2mat_t(_T(dm.body_quat[4 * b:4 * b + 4]))
+        if dm.nmocap and dm.body_mocapid[b] >= 0:                        # pose prescribed by the user, not by the tree
+            k = int(dm.body_mocapid[b])
+            mq = _T(mocap[1][4 * k:4 * k + 4])
+            Pb, Rb = _T(mocap[0][3 * k:3 * k + 3]), quat2mat_t(mq / torch.linalg.norm(mq))
         for j in range(int(dm.body_jntadr[b]), int(dm.body_jntadr[b] + dm.body_jntnum[b])):
             jt, qa, da = int(dm.jnt_type[j]), int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
             ax, jp = _T(dm.jnt_axis[3 * j:3 * j + 3]), _T(dm.jnt_pos[3 * j:3 * j + 3])
@@ -147,10 +152,10 @@ def coords(dm: DenseModel, qpos):
 class Kin:
     """Frames, exact Jacobians and zero-acceleration accelerations of every body at (qpos, qvel)."""
 
-    def __init__(self, dm: DenseModel, qpos, qvel):
+    def __init__(self, dm: DenseModel, qpos, qvel, mocap=None):
         self.dm = dm
         x, v = _T(coords(dm, qpos)), _T(qvel)
-        f = lambda y: fk(dm, qpos, y)
+        f = lambda y: fk(dm, qpos, y, mocap)
         (P, R) = f(x)
         dP, dR = jacfwd(f)(x)                                           # [nb,3,nv], [nb,3,3,nv]
         first = lambda y: jvp(f, (y,), (v,))[1]                         # d/dt of (P, R) along qvel
@@ -452,10 +457,41 @@ def row_params(dm, solref, solimp, pos, margin, diag_approx, vel):
     return aref, R
 
 
-def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts):
+def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
+    """Rows (J, D, aref) and ne = number of leading equality rows (quadratic on both sides)."""
     J, D, aref = [], [], []
     if dm.dis("constraint"):
-        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0)
+        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
+    if dm.neq and not dm.dis("equality"):
+        for i in range(dm.neq):
+            if eq_active is not None and not eq_active[i]:
+                continue
+            data, sr, si = dm.eq_data[11 * i:11 * i + 11], dm.eq_solref[2 * i:2 * i + 2], dm.eq_solimp[5 * i:5 * i + 5]
+            if int(dm.eq_type[i]) == 0:                                  # connect: the two anchors coincide
+                b1, b2 = int(dm.eq_obj1id[i]), int(dm.eq_obj2id[i])
+                p1, p2 = kin.P[b1] + kin.R[b1] @ data[0:3], kin.P[b2] + kin.R[b2] @ data[3:6]
+                Jd = kin.point_jac(b1, p1) - kin.point_jac(b2, p2)
+                diag = dm.body_invweight0[2 * b1] + dm.body_invweight0[2 * b2]
+                for k in range(3):
+                    a, R = row_params(dm, sr, si, p1[k] - p2[k], 0.0, diag, Jd[k] @ qvel)
+                    J.append(Jd[k]); D.append(1 / R); aref.append(a)
+            else:                                                        # joint: q1 follows a quartic polynomial of q2
+                j1, j2 = int(dm.eq_obj1id[i]), int(dm.eq_obj2id[i])
+                q1, d1 = int(dm.jnt_qposadr[j1]), int(dm.jnt_dofadr[j1])
+                row = np.zeros(dm.nv)
+                row[d1] = 1.0
+                pos, diag = qpos[q1] - dm.qpos0[q1], dm.dof_invweight0[d1]
+                if j2 >= 0:
+                    q2, d2 = int(dm.jnt_qposadr[j2]), int(dm.jnt_dofadr[j2])
+                    dq = qpos[q2] - dm.qpos0[q2]
+                    pos -= np.polyval(data[4::-1], dq)
+                    row[d2] = -np.polyval(np.polyder(np.poly1d(data[4::-1])).coeffs, dq)
+                    diag += dm.dof_invweight0[d2]
+                else:
+                    pos -= data[0]
+                a, R = row_params(dm, sr, si, pos, 0.0, diag, row @ qvel)
+                J.append(row); D.append(1 / R); aref.append(a)
+    ne = len(J)
     if not dm.dis("limit"):
         for j in range(dm.njnt):
             if not dm.jnt_limited[j] or int(dm.jnt_type[j]) not in (SLIDE, HINGE):
@@ -489,20 +525,22 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts):
                 a, _ = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, r @ qvel)
                 J.append(r); D.append(1 / Rpy); aref.append(a)
     if not J:
-        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0)
-    return np.array(J), np.array(D), np.array(aref)
+        return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
+    return np.array(J), np.array(D), np.array(aref), ne
 
 
-def solve_qacc(M, qfrc_smooth, J, D, aref):
+def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0):
     """argmin_a 1/2 (a-a0)' M (a-a0) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2 by damped Newton with backtracking."""
     a0 = np.linalg.solve(M, qfrc_smooth)
     if J.shape[0] == 0:
         return a0, np.zeros(0)
-    cost = lambda a: 0.5 * (a - a0) @ M @ (a - a0) + 0.5 * np.sum(D * np.minimum(0.0, J @ a - aref) ** 2)
+    two_sided = np.arange(J.shape[0]) < ne                              # equality rows: 1/2 D x^2 for either sign of x
+    pen = lambda x: np.where(two_sided, x, np.minimum(0.0, x))
+    cost = lambda a: 0.5 * (a - a0) @ M @ (a - a0) + 0.5 * np.sum(D * pen(J @ a - aref) ** 2)
     a = a0.copy()
     for _ in range(500):
         jar = J @ a - aref
-        act = jar < 0
+        act = (jar < 0) | two_sided
         g = M @ (a - a0) + J.T @ (D * jar * act)
         if np.linalg.norm(g) <= 1e-13 * max(1.0, np.linalg.norm(M @ a0)):
             break
@@ -515,14 +553,14 @@ def solve_qacc(M, qfrc_smooth, J, D, aref):
             break
         a = a + t * step
     jar = J @ a - aref
-    return a, np.where(jar < 0, -D * jar, 0.0)
+    return a, np.where((jar < 0) | two_sided, -D * jar, 0.0)
 
 
 # ------------------------------------------------------------------------------------------------ whole step
-def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None):
+def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None):
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
     act = np.zeros(dm.na) if act is None else np.asarray(act, float)
-    kin = Kin(dm, qpos, qvel)
+    kin = Kin(dm, qpos, qvel, mocap)
     M, c = mass_matrix_and_bias(dm, kin)
     fa, frc, act_dot, dfdv = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float), act)
     f = passive_force(dm, qpos, qvel) - c + fa
@@ -535,10 +573,10 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
                 com = kin.P[b] + kin.R[b] @ dm.body_ipos[3 * b:3 * b + 3]
                 f = f + kin.point_jac(b, com).T @ w[:3] + kin.JW[b].T @ w[3:]
     cons = collide(dm, kin)
-    J, D, aref = constraints(dm, kin, qpos, qvel, cons)
-    qacc, force = solve_qacc(M, f, J, D, aref)
+    J, D, aref, ne = constraints(dm, kin, qpos, qvel, cons, eq_active)
+    qacc, force = solve_qacc(M, f, J, D, aref, ne)
     return dict(qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
-                nefc=J.shape[0], efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]), act_dot=act_dot,
+                nefc=J.shape[0], ne=ne, efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]), act_dot=act_dot,
                 dfdv=dfdv)
 
 
@@ -562,12 +600,12 @@ def integrate_pos(dm, qpos, vel, h):
     return q
 
 
-def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None):
+def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None):
     """One mj_step. Returns dict(qpos, qvel, act, qacc, ncon, nefc, ...) - qacc is the forward's (pre-integration) acceleration."""
     h = dm.timestep
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
     act = np.zeros(dm.na) if act is None else np.asarray(act, float)
-    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied, act)
+    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied, act, mocap, eq_active)
     if dm.integrator in (0, 3):
         qacc = f0["qacc"]
         if dm.integrator == 3:      # implicitfast: (M - h d qfrc_smooth / d qvel) qacc' = M qacc, derivative = -damping + actuator term
@@ -584,7 +622,7 @@ def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None,
             qi = integrate_pos(dm, qpos, F[i][0], A[i] * h)
             vi = qvel + A[i] * h * F[i][1]
             ai = act + A[i] * h * F[i][2]
-            last = forward(dm, qi, vi, ctrl, qfrc_applied, xfrc_applied, ai)
+            last = forward(dm, qi, vi, ctrl, qfrc_applied, xfrc_applied, ai, mocap, eq_active)
             F.append((vi, last["qacc"], last["act_dot"]))
         sv = sum(w * Fi[0] for w, Fi in zip(Bw, F))
         sa = sum(w * Fi[1] for w, Fi in zip(Bw, F))

@@ -15,6 +15,7 @@ import oxide_control_b200 as ox
 from support import OracleData, rel_err
 from zoo_models import HOPPER, NOCONTACT, ZOO
 
+INPUTS = ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act", "mocap_pos", "mocap_quat", "eq_active")
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 XML = {**{k: v["xml"] for k, v in ox.models.CONFIGS.items()}, **ZOO, **NOCONTACT, "hopper": HOPPER}
 # single-step gates, rel = |a-b| / max(1,|b|). zoo_b runs the CG solver (tolerance 1e-10, RK4: four solves per step), whose
@@ -43,8 +44,8 @@ def test_oracle_matches_dense_checker_fixtures(name):
     for case in g["cases"]:
         i, o = case["input"], case["output"]
         od = OracleData(m)
-        for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act"):
-            if len(i[f]):
+        for f in INPUTS:
+            if len(i.get(f, ())):
                 od.field(f)[:] = i[f]
         od.step()
         assert od.int("ncon") == o["ncon"] and od.int("nefc") == o["nefc"]
@@ -63,7 +64,7 @@ def test_oracle_matches_dense_checker_fixtures(name):
         assert worst[f] <= t, (f, worst[f])
 
 
-@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a", "zoo_c"])
+@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a", "zoo_c", "zoo_e"])
 def test_fixtures_are_reproducible(name):
     import dense_checker as dc
     g = load(name)
@@ -71,7 +72,8 @@ def test_fixtures_are_reproducible(name):
     for case in g["cases"][-2:]:
         i, o = case["input"], case["output"]
         r = dc.step(dm, np.array(i["qpos"]), np.array(i["qvel"]), np.array(i["ctrl"]), np.array(i["qfrc_applied"]), np.array(i["xfrc_applied"]),
-                    np.array(i["act"]))
+                    np.array(i["act"]), mocap=(np.array(i.get("mocap_pos", [])), np.array(i.get("mocap_quat", []))),
+                    eq_active=np.array(i["eq_active"]) if "eq_active" in i else None)
         assert r["ncon"] == o["ncon"] and r["nefc"] == o["nefc"]
         for f in ("qpos", "qvel", "act", "qacc", "qfrc_bias"):
             assert rel_err(r[f], o[f]) <= 1e-11, f
@@ -86,8 +88,8 @@ def test_cuda_path_matches_dense_checker_fixtures(name, kernel):
     cases = g["cases"]
     n = len(cases)
     b = ox.BatchedPhysics(m, n, precision="f64", specialize=(kernel == "default"))
-    for f in ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act"):
-        v = np.array([c["input"][f] for c in cases], dtype=np.float64)
+    for f in INPUTS:
+        v = np.array([c["input"].get(f, []) for c in cases], dtype=np.float64)
         if v.shape[1]:
             b.set(f, v)
     b.step(1); b.sync()

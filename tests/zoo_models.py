@@ -186,5 +186,55 @@ ZOO_D = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C}
+# N3: equality constraints (connect between two moving bodies and to a mocap body; joint coupling with a quadratic polynomial, one
+# of them switched off in the model), a mocap body that carries a colliding geom, contacts on top (src/physics.rs:147-170)
+ZOO_E = """
+<mujoco model="zoo_e">
+  <compiler angle="radian"/>
+  <option timestep="0.004"/>
+  <default><joint damping="0.1" armature="0.005"/><geom friction="0.8 0.01 0.001"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <body name="hand" mocap="true" pos="0.72 0.02 0.95" quat="0.98 0 0.2 0">
+      <geom name="paddle" type="capsule" fromto="-0.2 0 -0.25 0.2 0 -0.25" size="0.04"/>
+    </body>
+    <body name="upper" pos="0 0 1">
+      <joint name="sh" type="hinge" axis="0 1 0"/>
+      <geom name="upper" type="capsule" fromto="0 0 0 0.4 0 0" size="0.03"/>
+      <body name="fore" pos="0.4 0 0">
+        <joint name="el" type="hinge" axis="0 1 0" range="-2 2" limited="true"/>
+        <geom name="fore" type="capsule" fromto="0 0 0 0.3 0 0" size="0.025"/>
+      </body>
+    </body>
+    <body name="gear1" pos="-0.5 0 0.5">
+      <joint name="g1" type="hinge" axis="1 0 0"/>
+      <geom type="capsule" fromto="0 0 0 0 0.2 0" size="0.03" contype="0" conaffinity="0"/>
+      <body name="gear2" pos="0 0.2 0">
+        <joint name="g2" type="slide" axis="0 1 0" stiffness="5"/>
+        <geom type="sphere" size="0.05" contype="0" conaffinity="0"/>
+      </body>
+    </body>
+    <body name="ball" pos="0.7 0 0.85">
+      <freejoint name="ballroot"/>
+      <geom name="ball" type="sphere" size="0.07" density="600"/>
+    </body>
+    <body name="puck" pos="0.2 0.4 0.06">
+      <freejoint name="puckroot"/>
+      <geom name="puck" type="sphere" size="0.06"/>
+    </body>
+  </worldbody>
+  <contact><exclude body1="fore" body2="ball"/></contact>
+  <equality>
+    <connect name="hook" body1="fore" body2="hand" anchor="0.3 0 0" solref="0.01 1"/>
+    <connect name="tether" body1="ball" body2="fore" anchor="0 0 0.15" solimp="0.8 0.9 0.01 0.5 2"/>
+    <joint name="couple" joint1="g1" joint2="g2" polycoef="0.05 1.5 -2 0 0"/>
+    <joint name="hold" joint1="sh" polycoef="0.2 0 0 0 0" active="false"/>
+    <connect name="pin" body1="puck" anchor="0 0 0.3" active="false"/>
+  </equality>
+  <actuator><motor joint="sh" gear="3"/><motor joint="g2" gear="2"/></actuator>
+  <sensor><jointpos joint="g1"/><framepos objtype="body" objname="ball"/><framepos objtype="body" objname="hand"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E}
 NOCONTACT = {"zoo_d": ZOO_D}

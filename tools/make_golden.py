@@ -29,7 +29,7 @@ MODELS = {  # name -> (xml, number of states, apply external forces)
     "pendulum": (ox.models.PENDULUM, 16, False), "cartpole": (ox.models.CARTPOLE, 16, False), "acrobot": (ox.models.ACROBOT, 16, False),
     "cheetah": (ox.models.CHEETAH, 64, False), "humanoid": (ox.models.HUMANOID, 64, False),
     "zoo_a": (ZOO["zoo_a"], 64, True), "zoo_b": (ZOO["zoo_b"], 64, True), "hopper": (HOPPER, 64, True),
-    "zoo_c": (ZOO["zoo_c"], 64, True), "zoo_d": (NOCONTACT["zoo_d"], 16, False),
+    "zoo_c": (ZOO["zoo_c"], 64, True), "zoo_d": (NOCONTACT["zoo_d"], 16, False), "zoo_e": (ZOO["zoo_e"], 64, True),
 }
 OUT_KEYS = ("qpos", "qvel", "act", "qacc", "qfrc_bias", "qfrc_smooth", "qfrc_constraint", "actuator_force")
 
@@ -44,6 +44,11 @@ def input_states(model, n, forces, seed=20261018):
         od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]
         if model.na:
             od.field("act")[:] = rng.uniform(-0.5, 0.5, model.na)
+        if model.nmocap:                      # the user moves the mocap bodies: a random pose near the model's
+            od.field("mocap_pos")[:] += rng.uniform(-0.05, 0.05, 3 * model.nmocap)
+            od.field("mocap_quat")[:] += rng.normal(0, 0.05, 4 * model.nmocap)      # left un-normalised on purpose (mj_kinematics normalises)
+        if model.neq and e % 3 == 1:          # ... and switches equality constraints on and off
+            od.field("eq_active")[:] = rng.integers(0, 2, model.neq)
         for s in range(20 + 5 * e if model.nefcmax else e):
             od.fill_ctrl_philox(e, s)
             od.step()
@@ -54,12 +59,14 @@ def input_states(model, n, forces, seed=20261018):
             xf = rng.normal(0, 1.0, 6 * model.nbody); xf[:6] = 0
             qf = rng.normal(0, 0.3, model.nv)
         states.append(dict(qpos=od.field("qpos").copy(), qvel=od.field("qvel").copy(), ctrl=od.field("ctrl").copy(), qfrc_applied=qf, xfrc_applied=xf,
-                           act=od.field("act").copy()))
+                           act=od.field("act").copy(), mocap_pos=od.field("mocap_pos").copy(), mocap_quat=od.field("mocap_quat").copy(),
+                           eq_active=od.field("eq_active").copy()))
     return states
 
 
 def dense_case(dm, st):
-    r = dc.step(dm, st["qpos"], st["qvel"], st["ctrl"], st["qfrc_applied"], st["xfrc_applied"], st["act"])
+    r = dc.step(dm, st["qpos"], st["qvel"], st["ctrl"], st["qfrc_applied"], st["xfrc_applied"], st["act"],
+                mocap=(st["mocap_pos"], st["mocap_quat"]), eq_active=st["eq_active"])
     out = {k: r[k] for k in OUT_KEYS}
     out.update(ncon=int(r["ncon"]), nefc=int(r["nefc"]), efc_D_sorted=np.sort(r["efc_D"]), efc_aref_sorted=np.sort(r["efc_aref"]),
                con_dist_sorted=np.sort(r["con_dist"]))
