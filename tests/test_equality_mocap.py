@@ -90,8 +90,9 @@ def test_connect_to_mocap_closed_form_and_steady_state():
 def _inputs(m, nenv, seed):
     rng = np.random.default_rng(seed)
     qpos, qvel = random_state(m, nenv, seed=seed)
-    mpos = np.tile(OracleData(m).field("mocap_pos"), (nenv, 1)) + rng.uniform(-0.05, 0.05, (nenv, 3 * m.nmocap))
-    mquat = np.tile(OracleData(m).field("mocap_quat"), (nenv, 1)) + rng.normal(0, 0.05, (nenv, 4 * m.nmocap))
+    od = OracleData(m)                 # keep it alive: field() returns views of its memory
+    mpos = np.tile(od.field("mocap_pos"), (nenv, 1)) + rng.uniform(-0.05, 0.05, (nenv, 3 * m.nmocap))
+    mquat = np.tile(od.field("mocap_quat"), (nenv, 1)) + rng.normal(0, 0.05, (nenv, 4 * m.nmocap))
     eqa = np.tile(np.asarray(m.eq_active0, dtype=np.float64), (nenv, 1))
     eqa[::3] = rng.integers(0, 2, eqa[::3].shape)
     return qpos, qvel, mpos, mquat, eqa
@@ -173,9 +174,13 @@ def test_gpu_vs_oracle(mode, specialize, precision):
     b.ctrl_philox(True, SEED)
     b.step(1); b.sync()
     ods = _oracle(m, inputs, 1)
-    tol1 = 1e-9 if precision == "f64" else 2e-3
+    # fp32: the hook's solref 0.01 makes D ~ 1e5 / invweight, so cond(M + J'DJ) ~ 1e6 and eps * cond bounds the forward error of
+    # qacc (|qacc| ~ 1e3 here); measured 1e-3 .. 3e-3 on qvel across the kernel families (tools/fp32_study.py has the analysis)
+    tol1 = 1e-9 if precision == "f64" else 1e-2
     for f in ("qpos", "qvel", "qacc"):
-        assert rel_err(b.get(f), np.stack([od.field(f) for od in ods])) <= tol1, f
+        err = rel_err(b.get(f), np.stack([od.field(f) for od in ods]))
+        print(mode, specialize, precision, f, "%.2e" % err)
+        assert err <= tol1, f
     assert np.array_equal(b.get("nefc")[:, 0], [od.int("nefc") for od in ods])
     b.step(29); b.sync()
     b.set("mocap_pos", b.get("mocap_pos") + 0.03)
@@ -183,8 +188,10 @@ def test_gpu_vs_oracle(mode, specialize, precision):
     ods = _oracle(m, inputs, nsteps, nudge_at=30)
     assert sum(od.int("ncon") for od in ods) > 0
     tol = 1e-6 if precision == "f64" else 5e-2
-    assert rel_err(b.get("qpos"), np.stack([od.field("qpos") for od in ods])) <= tol
-    assert rel_err(b.get("sensordata"), np.stack([od.field("sensordata") for od in ods])) <= tol
+    for f in ("qpos", "sensordata"):
+        err = rel_err(b.get(f), np.stack([od.field(f) for od in ods]))
+        print(mode, specialize, precision, nsteps, "steps", f, "%.2e" % err)
+        assert err <= tol, f
     assert int(b.diverged().sum()) == 0
 
 
@@ -194,11 +201,12 @@ def test_physics_accessors_and_snapshot():
     hand, ball = p.object_id(ox.obj.Body, "hand"), p.object_id(ox.obj.Body, "ball")
     hold = p.object_id(ox.obj.Equality, "hold")
     assert p.mocap_pos(ball) is None and p.set_mocap_pos(ball, [0, 0, 0]) is None and p.mocap_quat(ball) is None
-    assert np.allclose(p.mocap_pos(hand), [0.72, 0.02, 0.95]) and np.allclose(p.mocap_quat(hand), [0.98, 0, 0.2, 0])
+    quat0 = np.array([0.98, 0, 0.2, 0]) / np.linalg.norm([0.98, 0.2])      # the compiler normalises body quaternions
+    assert np.allclose(p.mocap_pos(hand), [0.72, 0.02, 0.95]) and np.allclose(p.mocap_quat(hand), quat0)
     assert p.eq_active(hold) is False and p.eq_active(p.object_id(ox.obj.Equality, "hook")) is True
     assert p.set_mocap_pos(hand, [0.7, 0.0, 0.9]) == () and p.set_mocap_quat(hand, [1, 0, 0, 0]) == ()
     p.set_eq_active(hold, True)
-    od = OracleData(p.model)
+    od = OracleData(p.model())
     od.field("mocap_pos")[:] = [0.7, 0.0, 0.9]; od.field("mocap_quat")[:] = [1, 0, 0, 0]; od.field("eq_active")[3] = 1
     for _ in range(25):
         p.step(); od.step()
