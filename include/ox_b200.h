@@ -157,6 +157,15 @@ OX_API const char* ox_version(void);
 OX_API ox_status ox_model_from_xml_string(const char* xml, ox_model** out);
 OX_API ox_status ox_model_from_xml_path(const char* path, ox_model** out);
 OX_API void ox_model_free(ox_model* m);
+/* Binary model format (MuJoCo's counterpart is mj_saveModel / mj_loadModel on an .mjb file, which the reference
+ * reaches through rusty_mujoco's mjModel but does not wrap): the compiled tables, options and names in one little-endian
+ * blob, "OXB2MDL" magic + format version + table-layout fingerprint + FNV-1a checksum. A model loaded from it is
+ * bit-identical to the one compiled from the XML (same model hash, so the same specialised kernel).
+ * ox_model_serialize writes at most `capacity` bytes into `buf` and returns the size needed (call with NULL / 0 to size). */
+OX_API int64_t ox_model_serialize(const ox_model* m, void* buf, int64_t capacity);
+OX_API ox_status ox_model_deserialize(const void* buf, int64_t size, ox_model** out);
+OX_API ox_status ox_model_save(const ox_model* m, const char* path);
+OX_API ox_status ox_model_load(const char* path, ox_model** out);
 OX_API const ox_model_tables* ox_model_get_tables(const ox_model* m);
 /* name-addressed table access for bindings that cannot see the struct (ctypes, Rust sys crate) */
 OX_API ox_status ox_model_int_table(const ox_model* m, const char* name, const int32_t** ptr, int32_t* count);

@@ -48,6 +48,9 @@ class Model {
  public:
   static Model from_xml_string(const std::string& xml) { ox_model* m = nullptr; check(ox_model_from_xml_string(xml.c_str(), &m)); return Model(m); }
   static Model from_xml(const std::string& path) { ox_model* m = nullptr; check(ox_model_from_xml_path(path.c_str(), &m)); return Model(m); }
+  // binary model format (MuJoCo: mj_saveModel / mj_loadModel)
+  static Model load(const std::string& path) { ox_model* m = nullptr; check(ox_model_load(path.c_str(), &m)); return Model(m); }
+  void save(const std::string& path) const { check(ox_model_save(m_, path.c_str())); }
   Model(Model&& o) noexcept : m_(o.m_) { o.m_ = nullptr; }
   Model(const Model&) = delete;
   ~Model() { ox_model_free(m_); }

@@ -78,6 +78,10 @@ SYMBOLS = {
     "ox_model_from_xml_string": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "ox_model_from_xml_path": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "ox_model_free": (None, [_P]),
+    "ox_model_serialize": (C.c_int64, [_P, _P, C.c_int64]),
+    "ox_model_deserialize": (C.c_int32, [_P, C.c_int64, C.POINTER(_P)]),
+    "ox_model_save": (C.c_int32, [_P, C.c_char_p]),
+    "ox_model_load": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "ox_model_get_tables": (_P, [_P]),
     "ox_model_int_table": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]),
     "ox_model_real_table": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int32)]),

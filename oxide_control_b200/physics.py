@@ -105,6 +105,28 @@ class Model:
         _check(A.lib().ox_model_from_xml_path(str(path).encode("utf-8"), C.byref(h)))
         return Model(h.value)
 
+    # binary model format (MuJoCo: mj_saveModel / mj_loadModel)
+    def save(self, path) -> None:
+        _check(A.lib().ox_model_save(self._h, str(path).encode("utf-8")))
+
+    @staticmethod
+    def load(path) -> "Model":
+        h = C.c_void_p()
+        _check(A.lib().ox_model_load(str(path).encode("utf-8"), C.byref(h)))
+        return Model(h.value)
+
+    def to_bytes(self) -> bytes:
+        n = A.lib().ox_model_serialize(self._h, None, 0)
+        buf = C.create_string_buffer(n)
+        assert A.lib().ox_model_serialize(self._h, buf, n) == n
+        return buf.raw
+
+    @staticmethod
+    def from_bytes(data: bytes) -> "Model":
+        h = C.c_void_p()
+        _check(A.lib().ox_model_deserialize(data, len(data), C.byref(h)))
+        return Model(h.value)
+
     def __del__(self):
         try:
             if self._h:

@@ -107,6 +107,17 @@ impl Model {
         check(unsafe { sys::ox_model_from_xml_path(c.as_ptr(), &mut raw) })?;
         Ok(Self { raw })
     }
+    /// binary model format (MuJoCo: mj_loadModel / mj_saveModel)
+    pub fn load(path: impl AsRef<std::path::Path>) -> Result<Self, Error> {
+        let c = CString::new(path.as_ref().to_str().unwrap()).unwrap();
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { sys::ox_model_load(c.as_ptr(), &mut raw) })?;
+        Ok(Self { raw })
+    }
+    pub fn save(&self, path: impl AsRef<std::path::Path>) -> Result<(), Error> {
+        let c = CString::new(path.as_ref().to_str().unwrap()).unwrap();
+        check(unsafe { sys::ox_model_save(self.raw, c.as_ptr()) })
+    }
     pub fn size(&self, name: &str) -> i32 { let c = CString::new(name).unwrap(); unsafe { sys::ox_model_size(self.raw, c.as_ptr()) } }
     /// a compiled integer table by mjModel field name ("jnt_type", "jnt_qposadr", "actuator_actadr", ...)
     pub fn int_table(&self, name: &str) -> &[i32] {
