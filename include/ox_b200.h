@@ -66,7 +66,7 @@ enum { OX_INT_EULER = 0, OX_INT_RK4 = 1, OX_INT_IMPLICIT = 2 /* refused by the c
 enum { OX_DYN_NONE = 0, OX_DYN_INTEGRATOR = 1, OX_DYN_FILTER = 2, OX_DYN_FILTEREXACT = 3 };
 /* mjtEq subset: equality constraints */
 enum { OX_EQ_CONNECT = 0, OX_EQ_WELD = 1 /* refused */, OX_EQ_JOINT = 2 };
-enum { OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
+enum { OX_SOL_PGS = 0, OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
 enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
 /* mjtDisableBit subset */
@@ -135,7 +135,8 @@ typedef struct ox_model_tables {
   int32_t neq;      /* equality constraints (eq_active, src/physics.rs:147-152) */
   /* mjOption subset */
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
-  double timestep, gravity[3], tolerance, ls_tolerance, impratio;
+  int32_t noslip_iterations, padopt_;   /* noslip post-pass of the friction dimensions (0 = off, MuJoCo's default) */
+  double timestep, gravity[3], tolerance, ls_tolerance, impratio, noslip_tolerance;
   /* mjStatistic subset */
   double meaninertia;
 #define OX_X(name, n, w) const int32_t* name;

@@ -1000,6 +1000,117 @@ struct Solver {
   }
 };
 
+// ---------------------------------------------------------------- dual solvers: PGS (mj_solPGS) and the noslip post-pass (mj_solNoSlip)
+// Both work on the constraint forces f with  A = J M^-1 J' (+ diag R for PGS),  b = J qacc_smooth - aref.  The matrix is never
+// formed: the solver carries w = qacc_smooth + M^-1 J' f, so that row r's residual is J_r w - aref_r (+ R_r f_r), and a change
+// of f_r by delta moves w by delta * M^-1 J_r' (one sparse L'DL solve) - O(nefc nv) memory instead of O(nefc^2).
+struct DualSolver {
+  const Model* m;
+  Data* d;
+  int nv, nefc;
+  std::vector<double> w, u;
+  DualSolver(const Model* m_, Data* d_) : m(m_), d(d_), nv(m_->nv), nefc(d_->nefc), w(m_->nv), u(m_->nv) {}
+  void minvJt(int r, double scale_b = 0, int rb = -1) {   // u = M^-1 (J_r - scale_b * J_rb)'
+    for (int i = 0; i < nv; i++) u[i] = d->efc_J[(size_t)r * nv + i] - (rb >= 0 ? scale_b * d->efc_J[(size_t)rb * nv + i] : 0.0);
+    solveLD(m, d->qLD.data(), d->qLDiagInv.data(), u.data());
+  }
+  double rowDot(int r, const std::vector<double>& v) const {
+    double s = 0;
+    for (int i = 0; i < nv; i++) s += d->efc_J[(size_t)r * nv + i] * v[i];
+    return s;
+  }
+  // w = qacc_smooth + M^-1 J' f  (also the final primal acceleration: mj dual2Primal); qfrc_constraint = J' f
+  void primalFromForces() {
+    for (int i = 0; i < nv; i++) {
+      double f = 0;
+      for (int r = 0; r < nefc; r++) f += d->efc_J[(size_t)r * nv + i] * d->efc_force[r];
+      d->qfrc_constraint[i] = f;
+    }
+    w = d->qfrc_constraint;
+    solveLD(m, d->qLD.data(), d->qLDiagInv.data(), w.data());
+    for (int i = 0; i < nv; i++) w[i] += d->qacc_smooth[i];
+  }
+  void pgs(int maxiter) {
+    const double scale = 1 / (m->meaninertia * std::max(1, nv));
+    // warm start: forces implied by qacc_warmstart (constraint update), kept only if their dual cost beats f = 0 (cost 0)
+    bool warm = false;
+    if (!disabled(m, OX_DSBL_WARMSTART)) {
+      for (int r = 0; r < nefc; r++) {
+        double jar = rowDot(r, d->qacc_warmstart) - d->efc_aref[r];
+        d->efc_force[r] = (jar < 0 || r < d->ne) ? -d->efc_D[r] * jar : 0.0;
+      }
+      primalFromForces();
+      double cost = 0;   // 1/2 f'(A + R) f + f'b  with  A f = J (w - qacc_smooth),  b = J qacc_smooth - aref
+      for (int r = 0; r < nefc; r++) {
+        const double f = d->efc_force[r], jw = rowDot(r, w), js = rowDot(r, d->qacc_smooth);
+        cost += 0.5 * f * (jw - js + f / d->efc_D[r]) + f * (js - d->efc_aref[r]);
+      }
+      warm = cost < 0;
+    }
+    if (!warm) {
+      std::fill(d->efc_force.begin(), d->efc_force.begin() + nefc, 0.0);
+      w = d->qacc_smooth;
+    }
+    int iter = 0;
+    while (iter < maxiter) {
+      double improvement = 0;
+      for (int r = 0; r < nefc; r++) {
+        minvJt(r);
+        const double R = 1 / d->efc_D[r], ARrr = rowDot(r, u) + R;
+        const double old = d->efc_force[r];
+        const double res = rowDot(r, w) - d->efc_aref[r] + R * old;
+        double f = old - res / ARrr;
+        if (r >= d->ne && f < 0) f = 0;             // limits and pyramidal contact edges push only; equalities pull both ways
+        const double delta = f - old;
+        if (delta != 0) {
+          d->efc_force[r] = f;
+          for (int i = 0; i < nv; i++) w[i] += delta * u[i];
+          improvement -= 0.5 * delta * delta * ARrr + delta * res;
+        }
+      }
+      iter++;
+      if (improvement * scale < m->tolerance) break;
+    }
+    d->solver_niter = iter;
+  }
+  // noslip: re-solves the friction dimensions WITHOUT regularisation (R = 0), normal forces fixed. For a pyramidal contact the
+  // opposing edges (f+, f-) of each friction direction keep their sum (= the normal load they carry) and only their
+  // difference y moves: 1-D quadratic in y with curvature K = (J+ - J-) M^-1 (J+ - J-)', clamped to |y| <= (f+ + f-)/2.
+  void noslip(int maxiter) {
+    const double scale = 1 / (m->meaninertia * std::max(1, nv));
+    primalFromForces();
+    for (int iter = 0; iter < maxiter; iter++) {
+      double improvement = 0;
+      for (int r = d->ne; r < nefc; r++) {
+        if (d->efc_type[r] != 2) continue;
+        const int c = d->efc_id[r];
+        int first = r;
+        while (first > 0 && d->efc_type[first - 1] == 2 && d->efc_id[first - 1] == c) first--;
+        if ((r - first) % 2) continue;               // r is the '+' edge of a pair
+        const int ra = r, rb = r + 1;
+        minvJt(ra, 1.0, rb);
+        const double K = rowDot(ra, u) - rowDot(rb, u);
+        if (K < OX_MINVAL) continue;
+        const double fa = d->efc_force[ra], fb = d->efc_force[rb], mid = 0.5 * (fa + fb), yold = 0.5 * (fa - fb);
+        const double dres = (rowDot(ra, w) - d->efc_aref[ra]) - (rowDot(rb, w) - d->efc_aref[rb]);
+        double y = yold - dres / K;
+        y = std::max(-mid, std::min(mid, y));
+        const double delta = y - yold;
+        if (delta != 0) {
+          d->efc_force[ra] = mid + y; d->efc_force[rb] = mid - y;
+          for (int i = 0; i < nv; i++) w[i] += delta * u[i];
+          improvement -= 0.5 * delta * delta * K + delta * dres;
+        }
+      }
+      if (improvement * scale < m->noslip_tolerance) break;
+    }
+  }
+  void finish() {
+    primalFromForces();
+    d->qacc = w;
+  }
+};
+
 void fwdConstraint(const Model* m, Data* d, int iterations, int ls_iterations) {
   int nv = m->nv;
   if (d->nefc == 0) {
@@ -1009,12 +1120,24 @@ void fwdConstraint(const Model* m, Data* d, int iterations, int ls_iterations) {
     d->solver_niter = 0;
     return;
   }
-  Solver s(m, d);
-  if (!disabled(m, OX_DSBL_WARMSTART)) {
-    double cw = s.costAt(d->qacc_warmstart.data()), cs = s.costAt(d->qacc_smooth.data());
-    d->qacc = cw > cs ? d->qacc_smooth : d->qacc_warmstart;
-  } else d->qacc = d->qacc_smooth;
-  s.solve(m->solver == OX_SOL_NEWTON, iterations, ls_iterations);
+  if (m->solver == OX_SOL_PGS) {
+    DualSolver ds(m, d);
+    ds.pgs(iterations);
+    if (m->noslip_iterations > 0) ds.noslip(m->noslip_iterations);
+    ds.finish();
+  } else {
+    Solver s(m, d);
+    if (!disabled(m, OX_DSBL_WARMSTART)) {
+      double cw = s.costAt(d->qacc_warmstart.data()), cs = s.costAt(d->qacc_smooth.data());
+      d->qacc = cw > cs ? d->qacc_smooth : d->qacc_warmstart;
+    } else d->qacc = d->qacc_smooth;
+    s.solve(m->solver == OX_SOL_NEWTON, iterations, ls_iterations);
+    if (m->noslip_iterations > 0) {
+      DualSolver ds(m, d);
+      ds.noslip(m->noslip_iterations);
+      ds.finish();
+    }
+  }
   for (int i = 0; i < nv; i++) d->qacc_warmstart[i] = d->qacc[i];
 }
 

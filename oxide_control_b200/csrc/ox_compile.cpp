@@ -609,6 +609,8 @@ ox_model* compile_mjcf(const std::string& xml) {
   t.ls_tolerance = 0.01;
   t.impratio = 1;
   t.disableflags = 0;
+  t.noslip_iterations = 0;
+  t.noslip_tolerance = 1e-6;
 
   // pass 1: compiler, option, defaults (must precede use regardless of document order)
   for (auto& ch : root->children) {
@@ -649,6 +651,9 @@ ox_model* compile_mjcf(const std::string& xml) {
       t.ls_iterations = (int)a.num("ls_iterations", t.ls_iterations);
       t.ls_tolerance = a.num("ls_tolerance", t.ls_tolerance);
       t.impratio = a.num("impratio", t.impratio);
+      t.noslip_iterations = (int)a.num("noslip_iterations", t.noslip_iterations);
+      t.noslip_tolerance = a.num("noslip_tolerance", t.noslip_tolerance);
+      if (t.noslip_iterations < 0) cfail("noslip_iterations must be >= 0");
       if (a.has("integrator")) {
         const std::string& s = a.str("integrator");
         if (s == "Euler") t.integrator = OX_INT_EULER;
@@ -661,7 +666,7 @@ ox_model* compile_mjcf(const std::string& xml) {
         const std::string& s = a.str("solver");
         if (s == "Newton") t.solver = OX_SOL_NEWTON;
         else if (s == "CG") t.solver = OX_SOL_CG;
-        else if (s == "PGS") cfail("solver PGS is outside the supported subset (Newton, CG)");
+        else if (s == "PGS") t.solver = OX_SOL_PGS;
         else pfail(*ch, "unknown solver '" + s + "'");
       }
       if (a.has("cone")) {

@@ -46,9 +46,9 @@ inline uint64_t model_hash(const ox_model_tables& t) {
     for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
   };
   const int32_t sizes[] = {t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
-                           t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags};
+                           t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags, t.noslip_iterations};
   mix(sizes, sizeof sizes);
-  const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia};
+  const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia, t.noslip_tolerance};
   mix(opts, sizeof opts);
 #define OX_X(name, n, w) mix(t.name, (size_t)t.n * (w) * sizeof(int32_t));
   OX_MODEL_INT_TABLES(OX_X)

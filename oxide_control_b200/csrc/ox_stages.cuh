@@ -1441,6 +1441,143 @@ struct Env {
     return c;
   }
 
+  // ---- dual solvers: PGS (mj_solPGS) and the noslip post-pass (mj_solNoSlip). They work on the forces f with
+  // A = J M^-1 J' (+ diag R for PGS), b = J qacc_smooth - aref, WITHOUT forming the nefc x nefc matrix: s_Ma carries
+  // w = qacc_smooth + M^-1 J' f, so row r's residual is J_r w - aref_r (+ R_r f_r), and a change of f_r by delta moves w by
+  // delta * M^-1 J_r' (one sparse L'DL solve into s_Mv). Memory stays O(nefc nv) per env - what the primal solvers use.
+  OX_HD T row_dot(int r, const T* v, int nv) const {
+    T s = 0;
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) s += at(b.efc_J, r * nv + i) * at(v, i);
+    return s;
+  }
+  // qfrc_constraint = J' f;  s_Ma = w = qacc_smooth + M^-1 qfrc_constraint  (mj dual2Primal)
+  OX_HD void dual_to_primal(int nv, int nefc) const {
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
+    OX_ROWLOOP
+    for (int r = 0; r < nefc; r++) {
+      const T f = at(b.efc_force, r);
+      if (f == 0) continue;
+      OX_NVLOOP
+      for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, r * nv + i) * f;
+    }
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) at(b.s_Ma, i) = at(b.qfrc_constraint, i);
+    solve_ld(b.s_Ma);
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) at(b.s_Ma, i) += at(b.qacc_smooth, i);
+  }
+  OX_HD void dual_pgs(int nv, int nefc) const {
+    const auto& h = m.h();
+    const int ne_ = ati(b.ne, 0);
+    const T scale = 1 / ((T)h.meaninertia * (T)(nv > 1 ? nv : 1));
+    bool warm = false;
+    if (!dis(OX_DSBL_WARMSTART)) {  // forces implied by qacc_warmstart, kept only if their dual cost beats f = 0 (cost 0)
+      OX_ROWLOOP
+      for (int r = 0; r < nefc; r++) {
+        const T jar = row_dot(r, b.qacc_warmstart, nv) - at(b.efc_aref, r);
+        at(b.efc_force, r) = (jar < 0 || r < ne_) ? -at(b.efc_D, r) * jar : (T)0;
+      }
+      dual_to_primal(nv, nefc);
+      T cost = 0;
+      OX_ROWLOOP
+      for (int r = 0; r < nefc; r++) {
+        const T f = at(b.efc_force, r), jw = row_dot(r, b.s_Ma, nv), js = row_dot(r, b.qacc_smooth, nv);
+        cost += (T)0.5 * f * (jw - js + f / at(b.efc_D, r)) + f * (js - at(b.efc_aref, r));
+      }
+      warm = cost < 0;
+    }
+    if (!warm) {
+      OX_ROWLOOP
+      for (int r = 0; r < nefc; r++) at(b.efc_force, r) = 0;
+      OX_NVLOOP
+      for (int i = 0; i < nv; i++) at(b.s_Ma, i) = at(b.qacc_smooth, i);
+    }
+    int iter = 0;
+    const int maxiter = h.iterations;
+    const T tol = (T)h.tolerance;
+#pragma unroll 1
+    while (iter < maxiter) {
+      T improvement = 0;
+#pragma unroll 1
+      for (int r = 0; r < nefc; r++) {
+        OX_NVLOOP
+        for (int i = 0; i < nv; i++) at(b.s_Mv, i) = at(b.efc_J, r * nv + i);
+        solve_ld(b.s_Mv);
+        const T R = 1 / at(b.efc_D, r), ARrr = row_dot(r, b.s_Mv, nv) + R;
+        const T old = at(b.efc_force, r);
+        const T res = row_dot(r, b.s_Ma, nv) - at(b.efc_aref, r) + R * old;
+        T f = old - res / ARrr;
+        if (r >= ne_ && f < 0) f = 0;   // limits and pyramidal contact edges push only; equalities pull both ways
+        const T delta = f - old;
+        if (delta != 0) {
+          at(b.efc_force, r) = f;
+          OX_NVLOOP
+          for (int i = 0; i < nv; i++) at(b.s_Ma, i) += delta * at(b.s_Mv, i);
+          improvement -= (T)0.5 * delta * delta * ARrr + delta * res;
+        }
+      }
+      iter++;
+      if (improvement * scale < tol) break;
+    }
+    ati(b.solver_niter, 0) = iter;
+  }
+  // one friction direction of one pyramidal contact: edges ra = '+', rb = '-' keep their sum, their difference moves
+  OX_HD T noslip_pair(int ra, int rb, int nv) const {
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) at(b.s_Mv, i) = at(b.efc_J, ra * nv + i) - at(b.efc_J, rb * nv + i);
+    solve_ld(b.s_Mv);
+    const T K = row_dot(ra, b.s_Mv, nv) - row_dot(rb, b.s_Mv, nv);
+    if (K < (T)OX_MINVAL) return 0;
+    const T fa = at(b.efc_force, ra), fb = at(b.efc_force, rb), mid = (T)0.5 * (fa + fb), yold = (T)0.5 * (fa - fb);
+    const T dres = (row_dot(ra, b.s_Ma, nv) - at(b.efc_aref, ra)) - (row_dot(rb, b.s_Ma, nv) - at(b.efc_aref, rb));
+    T y = yold - dres / K;
+    y = ox_max(-mid, ox_min(mid, y));
+    const T delta = y - yold;
+    if (delta == 0) return 0;
+    at(b.efc_force, ra) = mid + y; at(b.efc_force, rb) = mid - y;
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) at(b.s_Ma, i) += delta * at(b.s_Mv, i);
+    return -((T)0.5 * delta * delta * K + delta * dres);
+  }
+  OX_HD T noslip_contact(int c, int p, int nv) const {
+    const int ea = ati(b.con_efcadr, c), dim = m.pair_dim(p);
+    T imp = 0;
+    if (ea < 0 || dim < 3) return imp;
+#pragma unroll 1
+    for (int k = 0; k < dim - 1; k++) imp += noslip_pair(ea + 2 * k, ea + 2 * k + 1, nv);
+    return imp;
+  }
+  OX_HD void dual_noslip(int nv, int nefc) const {
+    const auto& h = m.h();
+    const T scale = 1 / ((T)h.meaninertia * (T)(nv > 1 ? nv : 1));
+    dual_to_primal(nv, nefc);
+#pragma unroll 1
+    for (int iter = 0; iter < h.noslip_iterations; iter++) {
+      T improvement = 0;
+      if (STATIC_CON || slots) {
+#pragma unroll 1
+        for (int p = 0; p < h.npair; p++)
+#pragma unroll 1
+          for (int k = 0; k < m.pair_maxcon(p); k++) {
+            const int c = m.pair_conadr(p) + k;
+            if (ati(b.con_active, c)) improvement += noslip_contact(c, p, nv);
+          }
+      } else {
+        const int ncon = ati(b.ncon, 0);
+#pragma unroll 1
+        for (int c = 0; c < ncon; c++) improvement += noslip_contact(c, ati(b.con_pair, c), nv);
+      }
+      if (improvement * scale < (T)h.noslip_tolerance) break;
+    }
+  }
+  OX_HD void dual_finish(int nv, int nefc) const {
+    dual_to_primal(nv, nefc);
+    OX_NVLOOP
+    for (int i = 0; i < nv; i++) { const T a = at(b.s_Ma, i); at(b.qacc, i) = a; at(b.qacc_warmstart, i) = a; }
+  }
+
   OX_HDN void fwd_constraint() const {
     const auto& h = m.h();
     const int nv = h.nv, nefc = ati(b.nefc, 0);
@@ -1451,6 +1588,12 @@ struct Env {
         at(b.qacc, i) = a; at(b.qacc_warmstart, i) = a; at(b.qfrc_constraint, i) = 0;
       }
       ati(b.solver_niter, 0) = 0;
+      return;
+    }
+    if (h.solver == OX_SOL_PGS) {
+      dual_pgs(nv, nefc);
+      if (h.noslip_iterations > 0) dual_noslip(nv, nefc);
+      dual_finish(nv, nefc);
       return;
     }
     const bool newton = h.solver == OX_SOL_NEWTON;
@@ -1576,6 +1719,11 @@ struct Env {
       }
     }
     ati(b.solver_niter, 0) = iter;
+    if (h.noslip_iterations > 0) {
+      dual_noslip(nv, nefc);
+      dual_finish(nv, nefc);
+      return;
+    }
     OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qacc_warmstart, i) = at(b.qacc, i);
   }

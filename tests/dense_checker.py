@@ -33,7 +33,7 @@ MINVAL, MINIMP, MAXIMP = 1e-15, 1e-4, 0.9999
 PLANE, SPHERE, CAPSULE, BOX = 0, 2, 3, 6
 FREE, BALL, SLIDE, HINGE = 0, 1, 2, 3
 DSBL = dict(constraint=1 << 0, limit=1 << 3, contact=1 << 4, passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7,
-            filterparent=1 << 9, equality=1 << 1, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
+            filterparent=1 << 9, equality=1 << 1, warmstart=1 << 8, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
 
 
 def _T(a):
@@ -460,6 +460,7 @@ def row_params(dm, solref, solimp, pos, margin, diag_approx, vel):
 def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     """Rows (J, D, aref) and ne = number of leading equality rows (quadratic on both sides)."""
     J, D, aref = [], [], []
+    dm._friction_pairs = []                                              # (row of edge +, row of edge -) of every pyramidal friction direction
     if dm.dis("constraint"):
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
     if dm.neq and not dm.dis("equality"):
@@ -521,6 +522,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
             _, R0 = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran + prm["friction"][0] ** 2 * tran, rows[0] @ qvel)
             mu = prm["friction"][0] * np.sqrt(1 / dm.impratio)
             Rpy = 2 * mu * mu * R0
+            dm._friction_pairs += [(len(J) + 2 * k, len(J) + 2 * k + 1) for k in range(2)]
             for r in rows:
                 a, _ = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, r @ qvel)
                 J.append(r); D.append(1 / Rpy); aref.append(a)
@@ -556,8 +558,61 @@ def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0):
     return a, np.where((jar < 0) | two_sided, -D * jar, 0.0)
 
 
+def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
+    """MuJoCo's dual solvers written the way mj_solPGS / mj_solNoSlip are: on the EXPLICIT matrix A = J M^-1 J' (the product keeps
+    it implicit). pgs=True: projected Gauss-Seidel on AR = A + diag(R); then, if the model asks for it, the noslip pass on the
+    friction dimensions with the unregularised A. pgs=False: noslip only, starting from the forces of the primal solution."""
+    nv, n = dm.nv, J.shape[0]
+    a0 = np.linalg.solve(M, qfrc_smooth)
+    if n == 0:
+        return a0, np.zeros(0), 0
+    A = J @ np.linalg.solve(M, J.T)
+    R = 1 / D
+    bvec = J @ a0 - aref
+    scale = 1 / (float(dm.m.meaninertia) * max(1, nv))
+    two_sided = np.arange(n) < ne
+    niter = 0
+    if pgs:
+        f = np.zeros(n)
+        if not dm.dis("warmstart"):
+            jar = J @ warmstart - aref
+            fw = np.where((jar < 0) | two_sided, -D * jar, 0.0)
+            if 0.5 * fw @ (A @ fw + R * fw) + fw @ bvec < 0:
+                f = fw
+        AR = A + np.diag(R)
+        for niter in range(1, int(dm.m.iterations) + 1):
+            improvement = 0.0
+            for r in range(n):
+                res = AR[r] @ f + bvec[r]
+                new = f[r] - res / AR[r, r]
+                if not two_sided[r]:
+                    new = max(0.0, new)
+                delta = new - f[r]
+                f[r] = new
+                improvement -= 0.5 * delta * delta * AR[r, r] + delta * res
+            if improvement * scale < float(dm.m.tolerance):
+                break
+    else:
+        f = warmstart                                                   # the primal solver's forces
+    for _ in range(int(dm.m.noslip_iterations)):
+        improvement = 0.0
+        for ra, rb in dm._friction_pairs:
+            K = A[ra, ra] + A[rb, rb] - 2 * A[ra, rb]
+            if K < MINVAL:
+                continue
+            res = A @ f + bvec
+            mid, yold = 0.5 * (f[ra] + f[rb]), 0.5 * (f[ra] - f[rb])
+            y = min(mid, max(-mid, yold - (res[ra] - res[rb]) / K))
+            delta = y - yold
+            f[ra], f[rb] = mid + y, mid - y
+            improvement -= 0.5 * delta * delta * K + delta * (res[ra] - res[rb])
+        if improvement * scale < float(dm.m.noslip_tolerance):
+            break
+    return a0 + np.linalg.solve(M, J.T @ f), f, niter
+
+
 # ------------------------------------------------------------------------------------------------ whole step
-def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None):
+def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None, warmstart=None):
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
     act = np.zeros(dm.na) if act is None else np.asarray(act, float)
     kin = Kin(dm, qpos, qvel, mocap)
@@ -574,7 +629,13 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
                 f = f + kin.point_jac(b, com).T @ w[:3] + kin.JW[b].T @ w[3:]
     cons = collide(dm, kin)
     J, D, aref, ne = constraints(dm, kin, qpos, qvel, cons, eq_active)
-    qacc, force = solve_qacc(M, f, J, D, aref, ne)
+    solver, noslip = int(dm.m.solver), int(dm.m.noslip_iterations)
+    if solver == 0:                                                      # PGS (+ noslip)
+        qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, np.zeros(dm.nv) if warmstart is None else np.asarray(warmstart, float), True)
+    else:
+        qacc, force = solve_qacc(M, f, J, D, aref, ne)
+        if noslip and len(force):
+            qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, force.copy(), False)
     return dict(qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
                 nefc=J.shape[0], ne=ne, efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]), act_dot=act_dot,
                 dfdv=dfdv)
@@ -600,12 +661,12 @@ def integrate_pos(dm, qpos, vel, h):
     return q
 
 
-def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None):
+def step(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None, warmstart=None):
     """One mj_step. Returns dict(qpos, qvel, act, qacc, ncon, nefc, ...) - qacc is the forward's (pre-integration) acceleration."""
     h = dm.timestep
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
     act = np.zeros(dm.na) if act is None else np.asarray(act, float)
-    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied, act, mocap, eq_active)
+    f0 = forward(dm, qpos, qvel, ctrl, qfrc_applied, xfrc_applied, act, mocap, eq_active, warmstart)
     if dm.integrator in (0, 3):
         qacc = f0["qacc"]
         if dm.integrator == 3:      # implicitfast: (M - h d qfrc_smooth / d qvel) qacc' = M qacc, derivative = -damping + actuator term

@@ -15,7 +15,7 @@ import oxide_control_b200 as ox
 from support import OracleData, rel_err
 from zoo_models import HOPPER, NOCONTACT, ZOO
 
-INPUTS = ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act", "mocap_pos", "mocap_quat", "eq_active")
+INPUTS = ("qpos", "qvel", "ctrl", "qfrc_applied", "xfrc_applied", "act", "mocap_pos", "mocap_quat", "eq_active", "qacc_warmstart")
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 XML = {**{k: v["xml"] for k, v in ox.models.CONFIGS.items()}, **ZOO, **NOCONTACT, "hopper": HOPPER}
 # single-step gates, rel = |a-b| / max(1,|b|). zoo_b runs the CG solver (tolerance 1e-10, RK4: four solves per step), whose
@@ -64,7 +64,7 @@ def test_oracle_matches_dense_checker_fixtures(name):
         assert worst[f] <= t, (f, worst[f])
 
 
-@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a", "zoo_c", "zoo_e"])
+@pytest.mark.parametrize("name", ["cheetah", "humanoid", "zoo_a", "zoo_c", "zoo_e", "zoo_f"])
 def test_fixtures_are_reproducible(name):
     import dense_checker as dc
     g = load(name)
@@ -73,7 +73,8 @@ def test_fixtures_are_reproducible(name):
         i, o = case["input"], case["output"]
         r = dc.step(dm, np.array(i["qpos"]), np.array(i["qvel"]), np.array(i["ctrl"]), np.array(i["qfrc_applied"]), np.array(i["xfrc_applied"]),
                     np.array(i["act"]), mocap=(np.array(i.get("mocap_pos", [])), np.array(i.get("mocap_quat", []))),
-                    eq_active=np.array(i["eq_active"]) if "eq_active" in i else None)
+                    eq_active=np.array(i["eq_active"]) if "eq_active" in i else None,
+                    warmstart=np.array(i["qacc_warmstart"]) if "qacc_warmstart" in i else None)
         assert r["ncon"] == o["ncon"] and r["nefc"] == o["nefc"]
         for f in ("qpos", "qvel", "act", "qacc", "qfrc_bias"):
             assert rel_err(r[f], o[f]) <= 1e-11, f

@@ -236,5 +236,40 @@ ZOO_E = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E}
+# N4: the dual solvers. zoo_f = PGS (projected Gauss-Seidel on the constraint forces) followed by the noslip pass, with contacts
+# (pyramidal and frictionless), a joint limit and an equality row in the same problem; zoo_g = Newton followed by noslip.
+ZOO_F = """
+<mujoco model="zoo_f">
+  <compiler angle="radian"/>
+  <option timestep="0.004" solver="PGS" iterations="60" tolerance="1e-10" noslip_iterations="4" noslip_tolerance="1e-8"/>
+  <default><geom friction="1.2 0.01 0.001"/><joint damping="0.05"/></default>
+  <worldbody>
+    <geom name="ramp" type="plane" size="3 3 0.1" euler="0 0.25 0"/>
+    <body name="crate" pos="0 0 0.25" euler="0 0.25 0.1">
+      <freejoint name="crateroot"/>
+      <geom name="crate" type="box" size="0.12 0.1 0.08" density="500"/>
+      <body name="flag" pos="0 0 0.08">
+        <joint name="mast" type="hinge" axis="0 1 0" range="-0.5 0.5" limited="true"/>
+        <geom name="mast" type="capsule" fromto="0 0 0 0 0 0.25" size="0.015"/>
+      </body>
+    </body>
+    <body name="roller" pos="0.5 0.2 0.2">
+      <freejoint name="rollerroot"/>
+      <geom name="roller" type="capsule" size="0.06 0.15" euler="1.5707963 0 0" friction="0.4 0.01 0.001"/>
+    </body>
+    <body name="marble" pos="-0.4 -0.2 0.1">
+      <freejoint name="marbleroot"/>
+      <geom name="marble" type="sphere" size="0.05" condim="1"/>
+    </body>
+  </worldbody>
+  <contact><exclude body1="crate" body2="roller"/><exclude body1="crate" body2="marble"/></contact>
+  <equality><connect name="leash" body1="marble" body2="crate" anchor="0 0 0.25" solref="0.03 1"/></equality>
+  <actuator><motor joint="mast" gear="0.5"/></actuator>
+  <sensor><framepos objtype="body" objname="crate"/><jointpos joint="mast"/></sensor>
+</mujoco>
+"""
+
+ZOO_G = HOPPER.replace('model="hopper_user"', 'model="zoo_g"').replace('<option timestep="0.004"/>', '<option timestep="0.004" noslip_iterations="3"/>')
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G}
 NOCONTACT = {"zoo_d": ZOO_D}

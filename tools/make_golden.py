@@ -30,6 +30,7 @@ MODELS = {  # name -> (xml, number of states, apply external forces)
     "cheetah": (ox.models.CHEETAH, 64, False), "humanoid": (ox.models.HUMANOID, 64, False),
     "zoo_a": (ZOO["zoo_a"], 64, True), "zoo_b": (ZOO["zoo_b"], 64, True), "hopper": (HOPPER, 64, True),
     "zoo_c": (ZOO["zoo_c"], 64, True), "zoo_d": (NOCONTACT["zoo_d"], 16, False), "zoo_e": (ZOO["zoo_e"], 64, True),
+    "zoo_f": (ZOO["zoo_f"], 64, True), "zoo_g": (ZOO["zoo_g"], 64, True),
 }
 OUT_KEYS = ("qpos", "qvel", "act", "qacc", "qfrc_bias", "qfrc_smooth", "qfrc_constraint", "actuator_force")
 
@@ -60,13 +61,13 @@ def input_states(model, n, forces, seed=20261018):
             qf = rng.normal(0, 0.3, model.nv)
         states.append(dict(qpos=od.field("qpos").copy(), qvel=od.field("qvel").copy(), ctrl=od.field("ctrl").copy(), qfrc_applied=qf, xfrc_applied=xf,
                            act=od.field("act").copy(), mocap_pos=od.field("mocap_pos").copy(), mocap_quat=od.field("mocap_quat").copy(),
-                           eq_active=od.field("eq_active").copy()))
+                           eq_active=od.field("eq_active").copy(), qacc_warmstart=od.field("qacc_warmstart").copy()))
     return states
 
 
 def dense_case(dm, st):
     r = dc.step(dm, st["qpos"], st["qvel"], st["ctrl"], st["qfrc_applied"], st["xfrc_applied"], st["act"],
-                mocap=(st["mocap_pos"], st["mocap_quat"]), eq_active=st["eq_active"])
+                mocap=(st["mocap_pos"], st["mocap_quat"]), eq_active=st["eq_active"], warmstart=st["qacc_warmstart"])
     out = {k: r[k] for k in OUT_KEYS}
     out.update(ncon=int(r["ncon"]), nefc=int(r["nefc"]), efc_D_sorted=np.sort(r["efc_D"]), efc_aref_sorted=np.sort(r["efc_aref"]),
                con_dist_sorted=np.sort(r["con_dist"]))
