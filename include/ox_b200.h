@@ -75,7 +75,7 @@ enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 
        OX_DSBL_WARMSTART = 1 << 8, OX_DSBL_FILTERPARENT = 1 << 9, OX_DSBL_ACTUATION = 1 << 10,
        OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13, OX_DSBL_EQUALITY = 1 << 1 };
 /* mjtSensor subset */
-enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3,
+enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3, OX_SENS_FORCE = 4, OX_SENS_TORQUE = 5,
        OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
        OX_SENS_ACTUATORFRC = 15, OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26,
        OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_SUBTREECOM = 34,

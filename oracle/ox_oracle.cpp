@@ -1243,8 +1243,80 @@ double rayGeom(const double* pos, const double* mat, const double* size, const d
   return hits.empty() ? -1.0 : *std::min_element(hits.begin(), hits.end());
 }
 
+// mj_rnePostConstraint: com-based interaction force of every body with its parent, cfrc_int = [torque; force] about
+// subtree_com[root] in world axes.  cfrc_ext collects the Cartesian forces applied to each body (xfrc_applied, contact forces,
+// connect-equality forces); cfrc_int[b] = cinert cacc + cvel x* (cinert cvel) - cfrc_ext, accumulated from the leaves to the root.
+void addExtForce(const Model* m, const Data* d, std::vector<double>& ext, int body, const double* point, const double* force, const double* torque,
+                 double sign) {
+  if (body == 0) return;
+  const double* sc = &d->subtree_com[3 * m->body_rootid[body]];
+  double dif[3] = {point[0] - sc[0], point[1] - sc[1], point[2] - sc[2]}, t[3];
+  cross3(t, dif, force);                       // moving the force to the com-frame origin adds (point - origin) x f
+  for (int k = 0; k < 3; k++) {
+    ext[6 * body + k] += sign * (t[k] + (torque ? torque[k] : 0.0));
+    ext[6 * body + 3 + k] += sign * force[k];
+  }
+}
+void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>& cacc, std::vector<double>& cfrc_int) {
+  const int nb = m->nbody, nv = m->nv;
+  (void)nv;
+  std::vector<double> ext(6 * nb, 0.0);
+  for (int b = 1; b < nb; b++) {
+    const double* f = &d->xfrc_applied[6 * b];
+    bool any = false;
+    for (int k = 0; k < 6; k++) any |= f[k] != 0;
+    if (any) addExtForce(m, d, ext, b, &d->xipos[3 * b], f, f + 3, 1.0);
+  }
+  // contacts: mj_contactForce in the contact frame (pyramid: normal = sum of the edge forces, tangent k = (f+ - f-) mu_k), rotated
+  // to the world; it pushes geom2's body along +normal and geom1's body the other way
+  for (int c = 0; c < d->ncon; c++) {
+    int first = -1, n = 0;
+    for (int r = 0; r < d->nefc; r++)
+      if ((d->efc_type[r] == 1 || d->efc_type[r] == 2) && d->efc_id[r] == c) { if (first < 0) first = r; n++; }
+    if (first < 0) continue;
+    const int p = d->con_pair[c];
+    const double* fri = m->pair_friction + 5 * p;
+    double lf[3] = {0, 0, 0};
+    if (n == 1) lf[0] = d->efc_force[first];
+    else
+      for (int k = 0; k < n / 2; k++) {
+        lf[0] += d->efc_force[first + 2 * k] + d->efc_force[first + 2 * k + 1];
+        lf[1 + k] = (d->efc_force[first + 2 * k] - d->efc_force[first + 2 * k + 1]) * fri[k];
+      }
+    const double* fr = &d->con_frame[9 * c];
+    double wf[3];
+    for (int k = 0; k < 3; k++) wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom1[p]], &d->con_pos[3 * c], wf, nullptr, -1.0);
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom2[p]], &d->con_pos[3 * c], wf, nullptr, +1.0);
+  }
+  // connect equalities: the three row forces are a world-frame force on body1 at its anchor and the opposite on body2 at its own
+  for (int r = 0; r + 2 < d->ne; r++) {
+    if (d->efc_type[r] != 3 || m->eq_type[d->efc_id[r]] != OX_EQ_CONNECT) continue;
+    const int i = d->efc_id[r], b1 = m->eq_obj1id[i], b2 = m->eq_obj2id[i];
+    const double* data = m->eq_data + 11 * i;
+    double p1[3], p2[3], w[3];
+    mulMatVec3(w, &d->xmat[9 * b1], data);
+    for (int k = 0; k < 3; k++) p1[k] = d->xpos[3 * b1 + k] + w[k];
+    mulMatVec3(w, &d->xmat[9 * b2], data + 3);
+    for (int k = 0; k < 3; k++) p2[k] = d->xpos[3 * b2 + k] + w[k];
+    addExtForce(m, d, ext, b1, p1, &d->efc_force[r], nullptr, +1.0);
+    addExtForce(m, d, ext, b2, p2, &d->efc_force[r], nullptr, -1.0);
+    r += 2;
+  }
+  cfrc_int.assign(6 * nb, 0.0);
+  for (int b = 1; b < nb; b++) {
+    double ia[6], iv[6], cf[6];
+    mulInertVec(ia, &d->cinert[10 * b], &cacc[6 * b]);
+    mulInertVec(iv, &d->cinert[10 * b], &d->cvel[6 * b]);
+    crossForce(cf, &d->cvel[6 * b], iv);
+    for (int k = 0; k < 6; k++) cfrc_int[6 * b + k] = ia[k] + cf[k] - ext[6 * b + k];
+  }
+  for (int b = nb - 1; b > 0; b--)
+    for (int k = 0; k < 6; k++) cfrc_int[6 * m->body_parentid[b] + k] += cfrc_int[6 * b + k];
+}
+
 void sensors(const Model* m, Data* d) {
-  std::vector<double> slv, cacc;
+  std::vector<double> slv, cacc, cfrc_int;
   for (int s = 0; s < m->nsensor; s++) {
     double* out = &d->sensordata[m->sensor_adr[s]];
     int id = m->sensor_objid[s], ot = m->sensor_objtype[s];
@@ -1311,6 +1383,19 @@ void sensors(const Model* m, Data* d) {
         cross3(t3, cv, lv);
         for (int k = 0; k < 3; k++) la[k] += t3[k];
         for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
+        break;
+      }
+      case OX_SENS_FORCE: case OX_SENS_TORQUE: {
+        // interaction force / torque between the site's body and its parent, at the site, in the site frame (mj_sensorAcc)
+        if (cacc.empty()) bodyAcc(m, d, cacc);
+        if (cfrc_int.empty()) rnePostConstraint(m, d, cacc, cfrc_int);
+        objFrame(m, d, OX_OBJ_SITE, id, &pos, &mat, &body);
+        const double* ci = &cfrc_int[6 * body];
+        double dif[3], t[3], v[3];
+        for (int k = 0; k < 3; k++) dif[k] = pos[k] - d->subtree_com[3 * m->body_rootid[body] + k];
+        cross3(t, dif, ci + 3);
+        for (int k = 0; k < 3; k++) v[k] = m->sensor_type[s] == OX_SENS_FORCE ? ci[3 + k] : ci[k] - t[k];   // torque moved to the site: tau - (site - origin) x f
+        for (int k = 0; k < 3; k++) out[k] = mat[k] * v[0] + mat[3 + k] * v[1] + mat[6 + k] * v[2];
         break;
       }
       case OX_SENS_CLOCK: out[0] = d->time; break;

@@ -1117,6 +1117,7 @@ ox_model* compile_mjcf(const std::string& xml) {
               {"subtreelinvel", OX_SENS_SUBTREELINVEL, OX_OBJ_BODY, "body", 3},
               {"velocimeter", OX_SENS_VELOCIMETER, OX_OBJ_SITE, "site", 3}, {"gyro", OX_SENS_GYRO, OX_OBJ_SITE, "site", 3},
               {"accelerometer", OX_SENS_ACCELEROMETER, OX_OBJ_SITE, "site", 3}, {"touch", OX_SENS_TOUCH, OX_OBJ_SITE, "site", 1},
+              {"force", OX_SENS_FORCE, OX_OBJ_SITE, "site", 3}, {"torque", OX_SENS_TORQUE, OX_OBJ_SITE, "site", 3},
               {"framepos", OX_SENS_FRAMEPOS, -1, "objname", 3}, {"framequat", OX_SENS_FRAMEQUAT, -1, "objname", 4},
               {"framelinvel", OX_SENS_FRAMELINVEL, -1, "objname", 3}, {"frameangvel", OX_SENS_FRAMEANGVEL, -1, "objname", 3},
               {"clock", OX_SENS_CLOCK, OX_OBJ_UNKNOWN, nullptr, 1},

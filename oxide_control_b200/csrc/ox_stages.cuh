@@ -1790,10 +1790,144 @@ struct Env {
     else if (objtype == OX_OBJ_GEOM) { ld<3>(pos, b.geom_xpos, 3 * id); ld<9>(mat, b.geom_xmat, 9 * id); *body = m.geom_bodyid(id); }
     else { ld<3>(pos, b.site_xpos, 3 * id); ld<9>(mat, b.site_xmat, 9 * id); *body = m.site_bodyid(id); }
   }
+  // body accelerations in the com frame (forward pass of mj_rnePostConstraint): cacc[0] = (0, -gravity),
+  // cacc[b] = cacc[parent] + sum over the body's dofs of cdof_dot*qvel + cdof*qacc (b.cacc is free after rne())
+  OX_HD void body_acc() const {
+    const auto& h = m.h();
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) { at(b.cacc, k) = 0; at(b.cacc, 3 + k) = dis(OX_DSBL_GRAVITY) ? (T)0 : -(T)h.grav(k); }
+    OX_MLOOP
+    for (int bd = 1; bd < h.nbody; bd++) {
+      T a[6];
+      ld<6>(a, b.cacc, 6 * m.body_parentid(bd));
+      OX_MLOOP
+      for (int d_ = 0; d_ < m.body_dofnum(bd); d_++) {
+        const int i = m.body_dofadr(bd) + d_;
+        T cd[6], cdd[6];
+        ld<6>(cd, b.cdof, 6 * i);
+        ld<6>(cdd, b.cdof_dot, 6 * i);
+        const T v = at(b.qvel, i), qa = at(b.qacc, i);
+        OX_MLOOP
+        for (int k = 0; k < 6; k++) a[k] += cdd[k] * v + cd[k] * qa;
+      }
+      st<6>(b.cacc, 6 * bd, a);
+    }
+  }
+  // b.cfrc[body] -= sign * (Cartesian force at `point` [+ torque]) moved to the com-frame origin subtree_com[root]
+  OX_HD void sub_ext_force(int body, const T* point, const T* force, const T* torque, T sign) const {
+    if (body == 0) return;
+    T sc[3], dif[3], t[3];
+    ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
+    dif[0] = point[0] - sc[0]; dif[1] = point[1] - sc[1]; dif[2] = point[2] - sc[2];
+    cross3(t, dif, force);
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) {
+      at(b.cfrc, 6 * body + k) -= sign * (t[k] + (torque ? torque[k] : (T)0));
+      at(b.cfrc, 6 * body + 3 + k) -= sign * force[k];
+    }
+  }
+  // mj_rnePostConstraint: b.cfrc = cfrc_int, the com-based [torque; force] each body exchanges with its parent
+  // (needs body_acc() first; b.cfrc is free after rne())
+  OX_HD void cfrc_int() const {
+    const auto& h = m.h();
+    const int nbody = h.nbody;
+    OX_MLOOP
+    for (int bd = 1; bd < nbody; bd++) {   // inertial part: cinert cacc + cvel x* (cinert cvel)
+      T in[10], ca[6], cv[6], ia[6], iv[6], cf[6];
+      ld<10>(in, b.cinert, 10 * bd);
+      ld<6>(ca, b.cacc, 6 * bd);
+      ld<6>(cv, b.cvel, 6 * bd);
+      mul_inert_vec(ia, in, ca);
+      mul_inert_vec(iv, in, cv);
+      cross_force(cf, cv, iv);
+      OX_MLOOP
+      for (int k = 0; k < 6; k++) ia[k] += cf[k];
+      st<6>(b.cfrc, 6 * bd, ia);
+    }
+    OX_MLOOP
+    for (int bd = 1; bd < nbody; bd++) {   // minus the applied Cartesian forces
+      T f[6], xi[3];
+      ld<6>(f, b.xfrc_applied, 6 * bd);
+      if (f[0] == 0 && f[1] == 0 && f[2] == 0 && f[3] == 0 && f[4] == 0 && f[5] == 0) continue;
+      ld<3>(xi, b.xipos, 3 * bd);
+      sub_ext_force(bd, xi, f, f + 3, (T)1);
+    }
+    // minus the contact forces (mj_contactForce: pyramid normal = sum of the edge forces, tangent k = (f+ - f-) mu_k): geom2's body
+    // is pushed along +normal, geom1's body the other way
+    auto one = [&](int c, int p) {
+      const int ea = ati(b.con_efcadr, c);
+      if (ea < 0) return;
+      const int dim = m.pair_dim(p);
+      T lf[3] = {0, 0, 0};
+      if (dim == 1) lf[0] = at(b.efc_force, ea);
+      else {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (k >= dim - 1) break;
+          const T fp = at(b.efc_force, ea + 2 * k), fm = at(b.efc_force, ea + 2 * k + 1);
+          lf[0] += fp + fm;
+          lf[1 + k] = (fp - fm) * m.pair_friction(5 * p + k);
+        }
+      }
+      T fr[9], cp[3], wf[3];
+      ld<9>(fr, b.con_frame, 9 * c);
+      ld<3>(cp, b.con_pos, 3 * c);
+      OX_MLOOP
+      for (int k = 0; k < 3; k++) wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
+      sub_ext_force(m.geom_bodyid(m.pair_geom1(p)), cp, wf, nullptr, (T)-1);
+      sub_ext_force(m.geom_bodyid(m.pair_geom2(p)), cp, wf, nullptr, (T)1);
+    };
+    if (STATIC_CON || slots) {
+      OX_MLOOP
+      for (int p = 0; p < h.npair; p++) {
+        OX_MLOOP
+        for (int k = 0; k < m.pair_maxcon(p); k++) {
+          const int c = m.pair_conadr(p) + k;
+          if (ati(b.con_active, c)) one(c, p);
+        }
+      }
+    } else {
+      const int ncon = ati(b.ncon, 0);
+      for (int c = 0; c < ncon; c++) one(c, ati(b.con_pair, c));
+    }
+    // minus the connect-equality forces: a world-frame force on body1 at its anchor, the opposite on body2 at its own
+    if (h.neq > 0 && ati(b.ne, 0) > 0) {
+      int r = 0;
+      OX_MLOOP
+      for (int i = 0; i < h.neq; i++) {
+        if (!(at(b.eq_active, i) != 0)) continue;
+        if (m.eq_type(i) != OX_EQ_CONNECT) { r += 1; continue; }
+        T f[3] = {at(b.efc_force, r), at(b.efc_force, r + 1), at(b.efc_force, r + 2)};
+        r += 3;
+        const int bodies[2] = {m.eq_obj1id(i), m.eq_obj2id(i)};
+        OX_MLOOP
+        for (int s = 0; s < 2; s++) {
+          T mat[9], xp[3], a[3], w[3], pt[3];
+          ld<9>(mat, b.xmat, 9 * bodies[s]);
+          ld<3>(xp, b.xpos, 3 * bodies[s]);
+          OX_LDM(3, a, eq_data, 11 * i + 3 * s);
+          mat_vec3(w, mat, a);
+          pt[0] = xp[0] + w[0]; pt[1] = xp[1] + w[1]; pt[2] = xp[2] + w[2];
+          sub_ext_force(bodies[s], pt, f, nullptr, s == 0 ? (T)1 : (T)-1);
+        }
+      }
+    }
+    OX_MLOOP
+    for (int bd = nbody - 1; bd > 0; bd--) {   // leaves to root
+      const int p = m.body_parentid(bd);
+      if (p == 0) continue;
+      T c[6], pc[6];
+      ld<6>(c, b.cfrc, 6 * bd);
+      ld<6>(pc, b.cfrc, 6 * p);
+      OX_MLOOP
+      for (int k = 0; k < 6; k++) pc[k] += c[k];
+      st<6>(b.cfrc, 6 * p, pc);
+    }
+  }
   OX_HDN void sensors() const {
     const auto& h = m.h();
     const int ns = h.nsensor, nbody = h.nbody;
-    bool have_slv = false, have_cacc = false;
+    bool have_slv = false, have_cacc = false, have_cfrc = false;
     OX_MLOOP
     for (int s = 0; s < ns; s++) {
       const int adr = m.sensor_adr(s), id = m.sensor_objid(s), ot = m.sensor_objtype(s), ty = m.sensor_type(s);
@@ -1863,27 +1997,7 @@ struct Env {
         case OX_SENS_ACCELEROMETER: {
           // mj_objectAcceleration(local) on top of mj_rnePostConstraint's forward pass: cacc[0] = (0, -gravity),
           // cacc[b] = cacc[parent] + sum over the body's dofs of cdof_dot*qvel + cdof*qacc (b.cacc is free after rne())
-          if (!have_cacc) {
-            OX_MLOOP
-            for (int k = 0; k < 3; k++) { at(b.cacc, k) = 0; at(b.cacc, 3 + k) = dis(OX_DSBL_GRAVITY) ? (T)0 : -(T)h.grav(k); }
-            OX_MLOOP
-            for (int bd = 1; bd < nbody; bd++) {
-              T a[6];
-              ld<6>(a, b.cacc, 6 * m.body_parentid(bd));
-              OX_MLOOP
-              for (int d_ = 0; d_ < m.body_dofnum(bd); d_++) {
-                const int i = m.body_dofadr(bd) + d_;
-                T cd[6], cdd[6];
-                ld<6>(cd, b.cdof, 6 * i);
-                ld<6>(cdd, b.cdof_dot, 6 * i);
-                const T v = at(b.qvel, i), qa = at(b.qacc, i);
-                OX_MLOOP
-                for (int k = 0; k < 6; k++) a[k] += cdd[k] * v + cd[k] * qa;
-              }
-              st<6>(b.cacc, 6 * bd, a);
-            }
-            have_cacc = true;
-          }
+          if (!have_cacc) { body_acc(); have_cacc = true; }
           T pos[3], mat[9];
           int body;
           obj_frame(OX_OBJ_SITE, id, pos, mat, &body);
@@ -1944,6 +2058,24 @@ struct Env {
             for (int c = 0; c < ncon; c++) one(c, ati(b.con_pair, c));
           }
           at(b.sensordata, adr) = total;
+          break;
+        }
+        case OX_SENS_FORCE: case OX_SENS_TORQUE: {
+          // interaction force / torque between the site's body and its parent, at the site, in the site frame (mj_sensorAcc)
+          if (!have_cacc) { body_acc(); have_cacc = true; }
+          if (!have_cfrc) { cfrc_int(); have_cfrc = true; }
+          T pos[3], mat[9], ci[6], sc[3], dif[3], t[3], v[3], out[3];
+          int body;
+          obj_frame(OX_OBJ_SITE, id, pos, mat, &body);
+          ld<6>(ci, b.cfrc, 6 * body);
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
+          dif[0] = pos[0] - sc[0]; dif[1] = pos[1] - sc[1]; dif[2] = pos[2] - sc[2];
+          cross3(t, dif, ci + 3);
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) v[k] = ty == OX_SENS_FORCE ? ci[3 + k] : ci[k] - t[k];
+          OX_MLOOP
+          for (int k = 0; k < 3; k++) out[k] = mat[k] * v[0] + mat[3 + k] * v[1] + mat[6 + k] * v[2];
+          st<3>(b.sensordata, adr, out);
           break;
         }
         case OX_SENS_CLOCK: at(b.sensordata, adr) = at(b.time, 0); break;

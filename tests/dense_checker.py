@@ -70,17 +70,18 @@ class DenseModel:
     INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
            "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
-           "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id"]
+           "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id",
+           "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
             "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
             "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
             "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
             "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange",
-            "eq_solref", "eq_solimp", "eq_data"]
+            "eq_solref", "eq_solimp", "eq_data", "site_pos", "site_quat"]
 
     def __init__(self, model):
         self.m = model
-        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq"):
+        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq", "nsensor", "nsensordata"):
             setattr(self, k, int(getattr(model, k)))
         for k in ("timestep", "impratio"):
             setattr(self, k, float(getattr(model, k)))
@@ -461,6 +462,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     """Rows (J, D, aref) and ne = number of leading equality rows (quadratic on both sides)."""
     J, D, aref = [], [], []
     dm._friction_pairs = []                                              # (row of edge +, row of edge -) of every pyramidal friction direction
+    cart = dm._row_cart = []                                             # per row: (body+, point+, body-, point-, direction) of the Cartesian force it is, or None
     if dm.dis("constraint"):
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
     if dm.neq and not dm.dis("equality"):
@@ -475,7 +477,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                 diag = dm.body_invweight0[2 * b1] + dm.body_invweight0[2 * b2]
                 for k in range(3):
                     a, R = row_params(dm, sr, si, p1[k] - p2[k], 0.0, diag, Jd[k] @ qvel)
-                    J.append(Jd[k]); D.append(1 / R); aref.append(a)
+                    J.append(Jd[k]); D.append(1 / R); aref.append(a); cart.append((b1, p1, b2, p2, np.eye(3)[k]))
             else:                                                        # joint: q1 follows a quartic polynomial of q2
                 j1, j2 = int(dm.eq_obj1id[i]), int(dm.eq_obj2id[i])
                 q1, d1 = int(dm.jnt_qposadr[j1]), int(dm.jnt_dofadr[j1])
@@ -491,7 +493,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                 else:
                     pos -= data[0]
                 a, R = row_params(dm, sr, si, pos, 0.0, diag, row @ qvel)
-                J.append(row); D.append(1 / R); aref.append(a)
+                J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
     ne = len(J)
     if not dm.dis("limit"):
         for j in range(dm.njnt):
@@ -504,7 +506,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                     row[da] = sign
                     a, R = row_params(dm, dm.jnt_solref[2 * j:2 * j + 2], dm.jnt_solimp[5 * j:5 * j + 5], dist, dm.jnt_margin[j],
                                       dm.dof_invweight0[da], row @ qvel)
-                    J.append(row); D.append(1 / R); aref.append(a)
+                    J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
     for c in contacts:
         prm = c["prm"]
         incl = prm["margin"] - prm["gap"]
@@ -515,17 +517,18 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
         tran = dm.body_invweight0[2 * b1] + dm.body_invweight0[2 * b2]
         if prm["dim"] == 1:
             a, R = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, Jd[0] @ qvel)
-            J.append(Jd[0]); D.append(1 / R); aref.append(a)
+            J.append(Jd[0]); D.append(1 / R); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], c["frame"][0]))
         else:
             assert prm["dim"] == 3, "condim 4/6 are outside the product's scope"
             rows = [Jd[0] + s * prm["friction"][k] * Jd[1 + k] for k in range(2) for s in (1.0, -1.0)]
+            dirs = [c["frame"][0] + s * prm["friction"][k] * c["frame"][1 + k] for k in range(2) for s in (1.0, -1.0)]
             _, R0 = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran + prm["friction"][0] ** 2 * tran, rows[0] @ qvel)
             mu = prm["friction"][0] * np.sqrt(1 / dm.impratio)
             Rpy = 2 * mu * mu * R0
             dm._friction_pairs += [(len(J) + 2 * k, len(J) + 2 * k + 1) for k in range(2)]
-            for r in rows:
+            for r, dr in zip(rows, dirs):
                 a, _ = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, r @ qvel)
-                J.append(r); D.append(1 / Rpy); aref.append(a)
+                J.append(r); D.append(1 / Rpy); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], dr))
     if not J:
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
     return np.array(J), np.array(D), np.array(aref), ne
@@ -611,6 +614,55 @@ def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
     return a0 + np.linalg.solve(M, J.T @ f), f, niter
 
 
+def force_torque_sensors(dm, kin, qacc, force, xfrc_applied):
+    """force / torque sensors WITHOUT spatial algebra: the wrench the subtree of the site's body exchanges with the parent is the
+    rate of change of the subtree's momentum (Newton-Euler per body, from the autodiff accelerations) minus every external Cartesian
+    force on the subtree (gravity, xfrc_applied, contact and connect-constraint forces read off the solver's row forces), taken
+    about the site and expressed in the site frame."""
+    out = {}
+    g = np.zeros(3) if dm.dis("gravity") else dm.gravity
+    for s in range(dm.nsensor):
+        ty = int(dm.sensor_type[s])
+        if ty not in (4, 5):
+            continue
+        site = int(dm.sensor_objid[s])
+        B = int(dm.site_bodyid[site])
+        P = kin.P[B] + kin.R[B] @ dm.site_pos[3 * site:3 * site + 3]
+        Rs = kin.R[B] @ quat2mat(dm.site_quat[4 * site:4 * site + 4])
+        sub = []
+        for k in range(1, dm.nbody):
+            a = k
+            while a > 0 and a != B:
+                a = int(dm.body_parentid[a])
+            if a == B:
+                sub.append(k)
+        F, Tq = np.zeros(3), np.zeros(3)
+        for k in sub:
+            mk, ipos = dm.body_mass[k], dm.body_ipos[3 * k:3 * k + 3]
+            Ri = kin.R[k] @ quat2mat(dm.body_iquat[4 * k:4 * k + 4])
+            Iw = Ri @ np.diag(dm.body_inertia[3 * k:3 * k + 3]) @ Ri.T
+            com = kin.P[k] + kin.R[k] @ ipos
+            a_com = kin.point_jac(k, com) @ qacc + kin.aP[k] + kin.aR[k] @ ipos
+            alpha = kin.JW[k] @ qacc + kin.alpha[k]
+            w = kin.w[k]
+            F += mk * (a_com - g)
+            Tq += Iw @ alpha + np.cross(w, Iw @ w) + np.cross(com - P, mk * (a_com - g))
+            if xfrc_applied is not None:
+                xf = xfrc_applied[6 * k:6 * k + 6]
+                F -= xf[:3]
+                Tq -= xf[3:] + np.cross(com - P, xf[:3])
+        for r, info in enumerate(dm._row_cart):
+            if info is None or force[r] == 0:
+                continue
+            bp, pp, bm, pm, dirv = info
+            if bp in sub:
+                F -= force[r] * dirv; Tq -= np.cross(pp - P, force[r] * dirv)
+            if bm in sub:
+                F += force[r] * dirv; Tq += np.cross(pm - P, force[r] * dirv)
+        out[int(dm.sensor_adr[s])] = Rs.T @ (F if ty == 4 else Tq)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ whole step
 def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=None, act=None, mocap=None, eq_active=None, warmstart=None):
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
@@ -636,7 +688,8 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
         qacc, force = solve_qacc(M, f, J, D, aref, ne)
         if noslip and len(force):
             qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, force.copy(), False)
-    return dict(qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
+    ft = force_torque_sensors(dm, kin, qacc, force, xfrc_applied) if dm.nsensor else {}
+    return dict(ft_sensors=ft, qacc=qacc, M=M, qfrc_bias=c, qfrc_smooth=f, qfrc_constraint=J.T @ force if len(force) else np.zeros(dm.nv), ncon=len(cons),
                 nefc=J.shape[0], ne=ne, efc_D=D, efc_aref=aref, actuator_force=frc, con_dist=np.array([k["dist"] for k in cons]), act_dot=act_dot,
                 dfdv=dfdv)
 

@@ -57,6 +57,9 @@ def test_oracle_matches_dense_checker_fixtures(name):
         assert rel_err(od.field("qfrc_bias"), o["qfrc_bias"]) <= aux
         assert rel_err(od.field("qfrc_smooth"), o["qfrc_smooth"]) <= aux
         assert rel_err(od.field("actuator_force"), o["actuator_force"]) <= aux
+        if "ft_adr" in o:    # force / torque sensors, derived independently (momentum balance of the subtree) by the dense checker
+            got = np.concatenate([od.field("sensordata")[a:a + 3] for a in o["ft_adr"]])
+            assert rel_err(got, o["ft_val"]) <= 1e-8, rel_err(got, o["ft_val"])
         for f in worst:
             worst[f] = max(worst[f], rel_err(od.field(f), o[f]))
     print(name, worst)
@@ -99,4 +102,8 @@ def test_cuda_path_matches_dense_checker_fixtures(name, kernel):
     for f, t in TOL[name].items():
         ref = np.array([c["output"][f] for c in cases])
         assert rel_err(b.get(f), ref) <= t, (f, rel_err(b.get(f), ref))
+    if "ft_adr" in cases[0]["output"]:
+        sd = b.get("sensordata")
+        got = np.stack([np.concatenate([sd[e, a:a + 3] for a in c["output"]["ft_adr"]]) for e, c in enumerate(cases)])
+        assert rel_err(got, np.array([c["output"]["ft_val"] for c in cases])) <= 1e-8
     assert int(b.diverged().sum()) == 0

@@ -54,6 +54,7 @@ ZOO_A = """
     <velocimeter site="tip"/> <gyro site="top"/> <accelerometer site="tip"/> <accelerometer site="top"/>
     <subtreecom body="boxy"/> <subtreelinvel body="boxy"/> <subtreelinvel body="arm"/> <clock/>
     <touch site="ball_skin"/> <touch site="rod_skin"/> <touch site="rod_tip"/> <touch site="box_sole"/> <touch site="tip"/>
+    <force site="tip"/> <torque site="tip"/> <force site="top"/> <torque site="top"/> <force site="ball_skin"/> <torque site="rod_tip"/>
   </sensor>
 </mujoco>
 """
@@ -204,7 +205,9 @@ ZOO_E = """
       <body name="fore" pos="0.4 0 0">
         <joint name="el" type="hinge" axis="0 1 0" range="-2 2" limited="true"/>
         <geom name="fore" type="capsule" fromto="0 0 0 0.3 0 0" size="0.025"/>
+        <site name="wrist" pos="0.05 0 0" euler="0.2 0 0.1"/>
       </body>
+      <site name="shoulder_ft" pos="0 0 0"/>
     </body>
     <body name="gear1" pos="-0.5 0 0.5">
       <joint name="g1" type="hinge" axis="1 0 0"/>
@@ -232,7 +235,8 @@ ZOO_E = """
     <connect name="pin" body1="puck" anchor="0 0 0.3" active="false"/>
   </equality>
   <actuator><motor joint="sh" gear="3"/><motor joint="g2" gear="2"/></actuator>
-  <sensor><jointpos joint="g1"/><framepos objtype="body" objname="ball"/><framepos objtype="body" objname="hand"/></sensor>
+  <sensor><jointpos joint="g1"/><framepos objtype="body" objname="ball"/><framepos objtype="body" objname="hand"/>
+    <force site="wrist"/><torque site="wrist"/><force site="shoulder_ft"/><torque site="shoulder_ft"/></sensor>
 </mujoco>
 """
 

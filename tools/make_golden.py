@@ -71,6 +71,8 @@ def dense_case(dm, st):
     out = {k: r[k] for k in OUT_KEYS}
     out.update(ncon=int(r["ncon"]), nefc=int(r["nefc"]), efc_D_sorted=np.sort(r["efc_D"]), efc_aref_sorted=np.sort(r["efc_aref"]),
                con_dist_sorted=np.sort(r["con_dist"]))
+    if r["ft_sensors"]:   # force / torque sensors: sensordata addresses and the dense checker's values (of the forward pass of the step)
+        out.update(ft_adr=[int(a) for a in sorted(r["ft_sensors"])], ft_val=np.concatenate([r["ft_sensors"][a] for a in sorted(r["ft_sensors"])]))
     return out
 
 
