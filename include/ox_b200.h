@@ -58,7 +58,7 @@ enum {
 enum { OX_JNT_FREE = 0, OX_JNT_BALL = 1, OX_JNT_SLIDE = 2, OX_JNT_HINGE = 3 };
 enum { OX_GEOM_PLANE = 0, OX_GEOM_HFIELD = 1, OX_GEOM_SPHERE = 2, OX_GEOM_CAPSULE = 3,
        OX_GEOM_ELLIPSOID = 4, OX_GEOM_CYLINDER = 5, OX_GEOM_BOX = 6, OX_GEOM_MESH = 7 };
-enum { OX_OBJ_UNKNOWN = 0, OX_OBJ_BODY = 1, OX_OBJ_XBODY = 2, OX_OBJ_JOINT = 3, OX_OBJ_DOF = 4,
+enum { OX_OBJ_UNKNOWN = 0, OX_OBJ_BODY = 1, OX_OBJ_XBODY = 2, OX_OBJ_JOINT = 3, OX_OBJ_TENDON = 18, OX_OBJ_DOF = 4,
        OX_OBJ_GEOM = 5, OX_OBJ_SITE = 6, OX_OBJ_EQUALITY = 17, OX_OBJ_ACTUATOR = 19,
        OX_OBJ_SENSOR = 20, OX_OBJ_PLUGIN = 25 };
 enum { OX_INT_EULER = 0, OX_INT_RK4 = 1, OX_INT_IMPLICIT = 2 /* refused by the compiler */, OX_INT_IMPLICITFAST = 3 };
@@ -76,7 +76,7 @@ enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 
        OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13, OX_DSBL_EQUALITY = 1 << 1 };
 /* mjtSensor subset */
 enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3, OX_SENS_FORCE = 4, OX_SENS_TORQUE = 5,
-       OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
+       OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_TENDONPOS = 11, OX_SENS_TENDONVEL = 12, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
        OX_SENS_ACTUATORFRC = 15, OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26,
        OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_SUBTREECOM = 34,
        OX_SENS_SUBTREELINVEL = 35, OX_SENS_CLOCK = 45 };
@@ -93,6 +93,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
   X(body_mocapid, nbody, 1)                                                                         \
   X(eq_type, neq, 1) X(eq_obj1id, neq, 1) X(eq_obj2id, neq, 1) X(eq_active0, neq, 1)                \
+  X(tendon_adr, ntendon, 1) X(tendon_num, ntendon, 1) X(tendon_limited, ntendon, 1) X(wrap_objid, nwrap, 1) \
   X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
   X(jnt_limited, njnt, 1)                                                                           \
   X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1) X(dof_Mdense, nvv, 1)               \
@@ -123,7 +124,11 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(actuator_gear, nu, 1) X(actuator_gainprm, nu, 3) X(actuator_biasprm, nu, 3)                    \
   X(actuator_ctrlrange, nu, 2) X(actuator_forcerange, nu, 2)                                        \
   X(actuator_dynprm, nu, 3) X(actuator_actrange, nu, 2)                                             \
-  X(eq_solref, neq, 2) X(eq_solimp, neq, 5) X(eq_data, neq, 11)
+  X(eq_solref, neq, 2) X(eq_solimp, neq, 5) X(eq_data, neq, 11)                                     \
+  X(wrap_prm, nwrap, 1) X(tendon_range, ntendon, 2) X(tendon_margin, ntendon, 1)                    \
+  X(tendon_solref_lim, ntendon, 2) X(tendon_solimp_lim, ntendon, 5)                                 \
+  X(tendon_stiffness, ntendon, 1) X(tendon_damping, ntendon, 1) X(tendon_lengthspring, ntendon, 2)  \
+  X(tendon_length0, ntendon, 1) X(tendon_invweight0, ntendon, 1)
 
 typedef struct ox_model_tables {
   /* sizes */
@@ -133,6 +138,7 @@ typedef struct ox_model_tables {
   int32_t nefcmax;  /* equality rows + 2*nlimited + sum of contact rows: capacity of the per-env efc list */
   int32_t nmocap;   /* mocap bodies (mocap_pos / mocap_quat, src/physics.rs:154-170) */
   int32_t neq;      /* equality constraints (eq_active, src/physics.rs:147-152) */
+  int32_t ntendon, nwrap; /* fixed tendons (linear combinations of scalar joint coordinates) and their joint entries */
   /* mjOption subset */
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
   int32_t noslip_iterations, padopt_;   /* noslip post-pass of the friction dimensions (0 = off, MuJoCo's default) */
@@ -241,7 +247,7 @@ enum {
   OX_F_QFRC_SMOOTH, OX_F_QACC_SMOOTH, OX_F_QFRC_CONSTRAINT,
   OX_F_CON_DIST, OX_F_CON_POS, OX_F_CON_FRAME,
   OX_F_EFC_J, OX_F_EFC_POS, OX_F_EFC_MARGIN, OX_F_EFC_D, OX_F_EFC_AREF, OX_F_EFC_FORCE,
-  OX_F_ACT_DOT, OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE,
+  OX_F_ACT_DOT, OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE, OX_F_TEN_LENGTH,
   OX_F_COUNT_REAL,
   /* int32 fields */
   OX_F_NCON = 100, OX_F_NEFC, OX_F_SOLVER_NITER, OX_F_DIVERGED, OX_F_CON_PAIR

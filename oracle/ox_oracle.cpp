@@ -35,7 +35,7 @@ typedef ox_model_tables Model;
 
 struct oxo_data {
   // state (mjData fields of the same names)
-  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot, mocap_pos, mocap_quat, eq_active;
+  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot, mocap_pos, mocap_quat, eq_active, ten_length;
   double time = 0;
   // position stage
   std::vector<double> xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, geom_xpos, geom_xmat, site_xpos, site_xmat;
@@ -400,6 +400,87 @@ int sphereSphere(RawContact* con, double margin, const double* pos1, double r1, 
 }
 inline double clip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
+// sphere (centre, radius) against a box (pos2, mat2, half sizes): mjc_SphereBox. The closest point of the box to the centre is
+// the centre clamped to the box in the box frame; a centre inside the box is pushed out through the nearest face.
+// The normal points from the sphere (geom1) to the box (geom2).
+int sphereBox(RawContact* con, double margin, const double* centre, double radius, const double* pos2, const double* mat2, const double* size2) {
+  double tmp[3] = {centre[0] - pos2[0], centre[1] - pos2[1], centre[2] - pos2[2]}, c[3], clamped[3], dir[3], lpos[3], lnorm[3];
+  for (int k = 0; k < 3; k++) c[k] = mat2[k] * tmp[0] + mat2[3 + k] * tmp[1] + mat2[6 + k] * tmp[2];   // mat2' * tmp
+  for (int k = 0; k < 3; k++) { clamped[k] = clip(c[k], -size2[k], size2[k]); dir[k] = clamped[k] - c[k]; }
+  double dist = std::sqrt(dot3(dir, dir));
+  if (dist - radius > margin) return 0;
+  if (dist <= OX_MINVAL) {   // centre inside the box
+    double closest = 2 * std::max(size2[0], std::max(size2[1], size2[2]));
+    int face = 0;
+    for (int i = 0; i < 6; i++) {
+      double fd = std::fabs((i % 2 ? 1.0 : -1.0) * size2[i / 2] - c[i / 2]);
+      if (fd < closest) { closest = fd; face = i; }
+    }
+    lnorm[0] = lnorm[1] = lnorm[2] = 0;
+    lnorm[face / 2] = face % 2 ? -1.0 : 1.0;
+    for (int k = 0; k < 3; k++) lpos[k] = c[k] + lnorm[k] * (radius - closest) / 2;
+    con->dist = -closest - radius;
+  } else {
+    for (int k = 0; k < 3; k++) lnorm[k] = dir[k] / dist;
+    for (int k = 0; k < 3; k++) lpos[k] = 0.5 * (clamped[k] + c[k] + lnorm[k] * radius);   // midway between the box point and the deepest sphere point
+    con->dist = dist - radius;
+  }
+  mulMatVec3(con->frame, mat2, lnorm);
+  con->frame[3] = con->frame[4] = con->frame[5] = 0;
+  mulMatVec3(tmp, mat2, lpos);
+  for (int k = 0; k < 3; k++) con->pos[k] = tmp[k] + pos2[k];
+  return 1;
+}
+
+// capsule against a box. NOT a restatement of mjc_CapsuleBox (its case analysis is not reproducible from the documentation; see
+// ORACLE_DECISIONS.md #12): the capsule is a swept sphere, so the first contact is sphereBox at the point of the axis segment
+// closest to the box - found EXACTLY: the derivative g(t) of half the squared distance along the segment is piecewise linear and
+// non-decreasing, with breakpoints where a coordinate crosses a face; its zero crossing lies between the last candidate with
+// g < 0 and the first with g >= 0. The second contact is the far end cap, if it is within the margin (a capsule lying along a
+// face or an edge gets two contacts, as with the plane).
+int capsuleBox(RawContact* con, double margin, const double* pos1, const double* mat1, const double* size1, const double* pos2, const double* mat2,
+               const double* size2) {
+  const double hl = size1[1], radius = size1[0];
+  double tmp[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]}, ax[3] = {mat1[2] * hl, mat1[5] * hl, mat1[8] * hl}, c[3], a[3];
+  for (int k = 0; k < 3; k++) {
+    c[k] = mat2[k] * tmp[0] + mat2[3 + k] * tmp[1] + mat2[6 + k] * tmp[2];
+    a[k] = mat2[k] * ax[0] + mat2[3 + k] * ax[1] + mat2[6 + k] * ax[2];
+  }
+  auto g = [&](double t) {
+    double s = 0;
+    for (int k = 0; k < 3; k++) { double pk = c[k] + t * a[k]; s += a[k] * (pk - clip(pk, -size2[k], size2[k])); }
+    return s;
+  };
+  double cand[8] = {-1, 1, 0, 0, 0, 0, 0, 0};
+  int nc = 2;
+  for (int k = 0; k < 3; k++)
+    if (std::fabs(a[k]) > OX_MINVAL)
+      for (double sgn : {-1.0, 1.0}) {
+        double t = (sgn * size2[k] - c[k]) / a[k];
+        if (t > -1 && t < 1) cand[nc++] = t;
+      }
+  double tstar;
+  if (g(-1) >= 0) tstar = -1;
+  else if (g(1) <= 0) tstar = 1;
+  else {
+    double ta = -1, ga = g(-1), tb = 1, gb = g(1);
+    for (int i = 2; i < nc; i++) {
+      double gi = g(cand[i]);
+      if (gi < 0) { if (cand[i] > ta) { ta = cand[i]; ga = gi; } }
+      else if (cand[i] < tb) { tb = cand[i]; gb = gi; }
+    }
+    tstar = gb - ga > OX_MINVAL ? ta - ga * (tb - ta) / (gb - ga) : ta;
+  }
+  double pt[3];
+  for (int k = 0; k < 3; k++) pt[k] = pos1[k] + tstar * ax[k];
+  int n = sphereBox(con, margin, pt, radius, pos2, mat2, size2);
+  const double tfar = tstar <= 0 ? 1.0 : -1.0;
+  for (int k = 0; k < 3; k++) pt[k] = pos1[k] + tfar * ax[k];
+  n += sphereBox(con + n, margin, pt, radius, pos2, mat2, size2);
+  for (int i = 0; i < n; i++) { con[i].frame[3] = mat1[2]; con[i].frame[4] = mat1[5]; con[i].frame[5] = mat1[8]; }   // tangent hint: the capsule axis
+  return n;
+}
+
 int collidePair(const Model* m, const Data* d, int p, RawContact* con) {
   int g1 = m->pair_geom1[p], g2 = m->pair_geom2[p];
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
@@ -444,6 +525,8 @@ int collidePair(const Model* m, const Data* d, int p, RawContact* con) {
     for (int k = 0; k < 3; k++) vec[k] = pos2[k] + axis[k] * x;
     return sphereSphere(con, margin, pos1, size1[0], vec, size2[0]);
   }
+  if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_BOX) return sphereBox(con, margin, pos1, size1[0], pos2, mat2, size2);
+  if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
   if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {
     double axis1[3] = {mat1[2] * size1[1], mat1[5] * size1[1], mat1[8] * size1[1]};
     double axis2[3] = {mat2[2] * size2[1], mat2[5] * size2[1], mat2[8] * size2[1]};
@@ -569,8 +652,23 @@ void addRow(const Model* m, Data* d, const double* jrow, double pos, double marg
   d->efc_aref[r] = -Bd * vel - K * imp * (pos - margin);
 }
 
+// fixed tendons (mj_tendon): length = sum of coef * joint coordinate; the Jacobian is the (constant) coefficient vector
+void tendonLength(const Model* m, Data* d) {
+  for (int i = 0; i < m->ntendon; i++) {
+    double L = 0;
+    for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) L += m->wrap_prm[w] * d->qpos[m->jnt_qposadr[m->wrap_objid[w]]];
+    d->ten_length[i] = L;
+  }
+}
+double tendonVelocity(const Model* m, const Data* d, int i) {
+  double v = 0;
+  for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) v += m->wrap_prm[w] * d->qvel[m->jnt_dofadr[m->wrap_objid[w]]];
+  return v;
+}
+
 void makeConstraint(const Model* m, Data* d) {
   int nv = m->nv;
+  tendonLength(m, d);   // position-stage quantity (mj_tendon); idempotent, so passive() may have computed it already
   d->nefc = 0;
   d->ne = 0;
   if (disabled(m, OX_DSBL_CONSTRAINT)) return;
@@ -627,6 +725,20 @@ void makeConstraint(const Model* m, Data* d) {
           jrow[m->jnt_dofadr[j]] = -side;
           addRow(m, d, jrow.data(), dist, margin, m->dof_invweight0[m->jnt_dofadr[j]], m->jnt_solref + 2 * j,
                  m->jnt_solimp + 5 * j, 0, j);
+        }
+      }
+    }
+  // tendon limits (after the joint limits, mj_instantiateLimit order)
+  if (!disabled(m, OX_DSBL_LIMIT))
+    for (int i = 0; i < m->ntendon; i++) {
+      if (!m->tendon_limited[i]) continue;
+      const double value = d->ten_length[i], margin = m->tendon_margin[i];
+      for (int side = -1; side <= 1; side += 2) {
+        double dist = side * (m->tendon_range[2 * i + (side + 1) / 2] - value);
+        if (dist < margin) {
+          std::fill(jrow.begin(), jrow.end(), 0.0);
+          for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) jrow[m->jnt_dofadr[m->wrap_objid[w]]] += -side * m->wrap_prm[w];
+          addRow(m, d, jrow.data(), dist, margin, m->tendon_invweight0[i], m->tendon_solref_lim + 2 * i, m->tendon_solimp_lim + 5 * i, 4, i);
         }
       }
     }
@@ -700,6 +812,7 @@ void comVel(const Model* m, Data* d) {
 
 void passive(const Model* m, Data* d) {
   std::fill(d->qfrc_passive.begin(), d->qfrc_passive.end(), 0.0);
+  tendonLength(m, d);
   if (disabled(m, OX_DSBL_PASSIVE)) return;
   for (int j = 0; j < m->njnt; j++) {
     double k = m->jnt_stiffness[j];
@@ -722,6 +835,16 @@ void passive(const Model* m, Data* d) {
     }
   }
   for (int i = 0; i < m->nv; i++) d->qfrc_passive[i] -= m->dof_damping[i] * d->qvel[i];
+  // tendon spring (dead band [lengthspring0, lengthspring1]) and damper, mapped through J' = the coefficients
+  for (int i = 0; i < m->ntendon; i++) {
+    const double L = d->ten_length[i], lo = m->tendon_lengthspring[2 * i], hi = m->tendon_lengthspring[2 * i + 1];
+    double f = 0;
+    if (L > hi) f = m->tendon_stiffness[i] * (hi - L);
+    else if (L < lo) f = m->tendon_stiffness[i] * (lo - L);
+    f -= m->tendon_damping[i] * tendonVelocity(m, d, i);
+    if (f != 0)
+      for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) d->qfrc_passive[m->jnt_dofadr[m->wrap_objid[w]]] += m->wrap_prm[w] * f;
+  }
 }
 
 // ---------------------------------------------------------------- A.8 bias forces (RNE, flg_acc = 0)
@@ -1328,6 +1451,8 @@ void sensors(const Model* m, Data* d) {
       case OX_SENS_ACTUATORPOS: out[0] = m->actuator_gear[id] * d->qpos[m->jnt_qposadr[m->actuator_trnid[id]]]; break;
       case OX_SENS_ACTUATORVEL: out[0] = m->actuator_gear[id] * d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]; break;
       case OX_SENS_ACTUATORFRC: out[0] = d->actuator_force[id]; break;
+      case OX_SENS_TENDONPOS: out[0] = d->ten_length[id]; break;
+      case OX_SENS_TENDONVEL: out[0] = tendonVelocity(m, d, id); break;
       case OX_SENS_TOUCH: {
         // mj_sensorAcc / mjSENS_TOUCH: normal forces (mj_contactForce: sum of the pyramid edge forces, or the single row of a
         // frictionless contact) of contacts on the site's body whose point the site volume contains (ray along the normal)
@@ -1598,7 +1723,7 @@ OXO_API oxo_data* oxo_make_data(const Model* m) {
   int nb = m->nbody, nv = m->nv;
   d->qpos.resize(m->nq); d->qvel.resize(nv); d->ctrl.resize(m->nu); d->qfrc_applied.resize(nv); d->xfrc_applied.resize(6 * nb);
   d->qacc_warmstart.resize(nv); d->act.resize(m->na); d->act_dot.resize(m->na);
-  d->mocap_pos.resize(3 * m->nmocap); d->mocap_quat.resize(4 * m->nmocap); d->eq_active.resize(m->neq);
+  d->mocap_pos.resize(3 * m->nmocap); d->mocap_quat.resize(4 * m->nmocap); d->eq_active.resize(m->neq); d->ten_length.resize(m->ntendon);
   d->xpos.resize(3 * nb); d->xquat.resize(4 * nb); d->xmat.resize(9 * nb); d->xipos.resize(3 * nb); d->ximat.resize(9 * nb);
   d->xanchor.resize(3 * m->njnt); d->xaxis.resize(3 * m->njnt); d->geom_xpos.resize(3 * m->ngeom); d->geom_xmat.resize(9 * m->ngeom);
   d->site_xpos.resize(3 * m->nsite); d->site_xmat.resize(9 * m->nsite);
@@ -1647,7 +1772,7 @@ OXO_API void oxo_stage(const Model* m, oxo_data* d, const char* name) {
 OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
   std::string s(name);
 #define F(f) if (s == #f) { *count = (int32_t)d->f.size(); return d->f.data(); }
-  F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
+  F(ten_length) F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
   F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
   F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
   F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)

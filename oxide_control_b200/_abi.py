@@ -18,7 +18,7 @@ OX_OK, OX_ERR_PARSE, OX_ERR_COMPILE, OX_ERR_CUDA, OX_ERR_INVALID, OX_ABSENT, OX_
 # enums
 JNT_FREE, JNT_BALL, JNT_SLIDE, JNT_HINGE = range(4)
 OBJ_BODY, OBJ_XBODY, OBJ_JOINT, OBJ_DOF, OBJ_GEOM, OBJ_SITE = 1, 2, 3, 4, 5, 6
-OBJ_EQUALITY, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_PLUGIN = 17, 19, 20, 25
+OBJ_EQUALITY, OBJ_TENDON, OBJ_ACTUATOR, OBJ_SENSOR, OBJ_PLUGIN = 17, 18, 19, 20, 25
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 LAYOUT_ENV_MAJOR, LAYOUT_ELEM_MAJOR = 0, 1
@@ -31,7 +31,7 @@ _REAL_FIELDS = [
     "site_xpos", "site_xmat", "subtree_com", "cinert", "cdof", "qM", "qLD", "qLDiagInv", "cvel", "cdof_dot",
     "qfrc_bias", "qfrc_passive", "actuator_force", "qfrc_actuator", "qfrc_smooth", "qacc_smooth", "qfrc_constraint",
     "con_dist", "con_pos", "con_frame", "efc_J", "efc_pos", "efc_margin", "efc_D", "efc_aref", "efc_force", "act_dot",
-    "mocap_pos", "mocap_quat", "eq_active",
+    "mocap_pos", "mocap_quat", "eq_active", "ten_length",
 ]
 FIELD = {name: i for i, name in enumerate(_REAL_FIELDS)}
 FIELD.update({"ncon": 100, "nefc": 101, "solver_niter": 102, "diverged": 103, "con_pair": 104})

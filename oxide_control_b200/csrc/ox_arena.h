@@ -16,7 +16,7 @@ struct FieldInfo {
 template <typename T>
 size_t layout_arena(const ox_model_tables& t, int stride, unsigned char* base, DevBatch<T>* out, std::map<int, FieldInfo>* fields) {
   const long nq = t.nq, nv = t.nv, nu = t.nu, na = t.na, nb = t.nbody, nj = t.njnt, ng = t.ngeom, ns = t.nsite, nM = t.nM;
-  const long ncm = std::max(1, t.nconmax), nem = std::max(1, t.nefcmax), nsd = t.nsensordata, nmc = t.nmocap, neq = t.neq;
+  const long ncm = std::max(1, t.nconmax), nem = std::max(1, t.nefcmax), nsd = t.nsensordata, nmc = t.nmocap, neq = t.neq, nten = t.ntendon;
   size_t off = 0;
   auto take = [&](size_t elems, size_t esz) {
     size_t o = off;
@@ -54,7 +54,7 @@ size_t layout_arena(const ox_model_tables& t, int stride, unsigned char* base, D
     R(OX_F_CON_FRAME, con_frame, 9 * ncm) R(OX_F_EFC_J, efc_J, nem * nv) R(OX_F_EFC_POS, efc_pos, nem)
     R(OX_F_EFC_MARGIN, efc_margin, nem) R(OX_F_EFC_D, efc_D, nem) R(OX_F_EFC_AREF, efc_aref, nem) R(OX_F_EFC_FORCE, efc_force, nem)
     R(OX_F_ACT, act, na) R(OX_F_ACT_DOT, act_dot, na) R(OX_F_MOCAP_POS, mocap_pos, 3 * nmc) R(OX_F_MOCAP_QUAT, mocap_quat, 4 * nmc)
-    R(OX_F_EQ_ACTIVE, eq_active, neq)
+    R(OX_F_EQ_ACTIVE, eq_active, neq) R(OX_F_TEN_LENGTH, ten_length, nten)
 #undef R
 #define I(id, name, cnt) f[id] = FieldInfo{out->name, (int)(cnt), true};
     I(OX_F_NCON, ncon, 1) I(OX_F_NEFC, nefc, 1) I(OX_F_SOLVER_NITER, solver_niter, 1) I(OX_F_DIVERGED, diverged, 1)

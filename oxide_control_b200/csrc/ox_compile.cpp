@@ -73,8 +73,11 @@ const std::map<std::string, std::set<std::string>>& schema() {
                            "actlimited", "user", "tendon", "site", "body", "jointinparent", "lengthrange", "cranklength",
                            "slidersite", "cranksite", "refsite", "actdim", "actearly", "inheritrange", "dampratio", "timeconst"}},
       {"exclude", {"name", "body1", "body2"}},
+      {"tendon_fixed", {"name", "class", "group", "limited", "range", "solreflimit", "solimplimit", "solreffriction", "solimpfriction", "margin",
+                        "frictionloss", "springlength", "stiffness", "damping", "user", "width", "material", "rgba"}},
+      {"tendon_joint", {"joint", "coef"}},
       {"equality_common", {"name", "class", "active", "solref", "solimp", "body1", "body2", "anchor", "joint1", "joint2", "polycoef"}},
-      {"sensor_common", {"name", "joint", "actuator", "site", "body", "objtype", "objname", "reftype", "refname", "cutoff",
+      {"sensor_common", {"name", "joint", "actuator", "site", "body", "tendon", "objtype", "objname", "reftype", "refname", "cutoff",
                          "noise", "user"}},
   };
   return s;
@@ -161,6 +164,7 @@ void parse_defaults(Ctx& c, const XmlElem& d, const std::string& parent_cls, boo
     if (tag == "geom") check_attrs(*ch, "geom");
     else if (tag == "joint") check_attrs(*ch, "joint");
     else if (tag == "site") check_attrs(*ch, "site");
+    else if (tag == "tendon") check_attrs(*ch, "tendon_fixed");
     else if (is_actuator_tag(tag)) { check_attrs(*ch, "actuator_common"); tag = "actuator"; }
     else if (tag == "camera" || tag == "light" || tag == "material" || tag == "mesh") continue;  // cosmetic
     else cfail("unsupported element <" + ch->name + "> inside <default> (line " + std::to_string(ch->line) + ")");
@@ -703,7 +707,9 @@ ox_model* compile_mjcf(const std::string& xml) {
         if (as->name == "mesh" || as->name == "hfield") cfail("asset <" + as->name + "> is outside the supported subset");
     } else if (n == "equality") {
       // compiled after the joints and bodies are known (below)
-    } else if (n == "tendon" || n == "deformable" || n == "extension") {
+    } else if (n == "tendon") {
+      // compiled after the joints are known (below)
+    } else if (n == "deformable" || n == "extension") {
       if (!ch->children.empty()) cfail("<" + n + "> is outside the supported subset");
     } else {
       pfail(*ch, "unrecognized top-level element");
@@ -956,6 +962,8 @@ ox_model* compile_mjcf(const std::string& xml) {
             else if (ta == OX_GEOM_SPHERE && tb == OX_GEOM_SPHERE) maxcon = 1;
             else if (ta == OX_GEOM_SPHERE && tb == OX_GEOM_CAPSULE) maxcon = 1;
             else if (ta == OX_GEOM_CAPSULE && tb == OX_GEOM_CAPSULE) maxcon = 2;
+            else if (ta == OX_GEOM_SPHERE && tb == OX_GEOM_BOX) maxcon = 1;
+            else if (ta == OX_GEOM_CAPSULE && tb == OX_GEOM_BOX) maxcon = 2;
             else {
               static const char* tn[] = {"plane", "hfield", "sphere", "capsule", "ellipsoid", "cylinder", "box", "mesh"};
               cfail(std::string("collision pair ") + tn[ta] + "-" + tn[tb] + " (geoms '" + G[ga].name + "', '" + G[gb].name +
@@ -1100,6 +1108,63 @@ ox_model* compile_mjcf(const std::string& xml) {
   t.na = na;
   check_unique(OX_OBJ_ACTUATOR, "actuator");
 
+  // ---- fixed tendons: length = sum_i coef_i * q_i over hinge / slide joints; limits, spring (with dead band) and damper.
+  // Spatial tendons (site / geom wrapping), tendon friction loss and tendon transmissions are outside the supported subset.
+  t.ntendon = 0; t.nwrap = 0;
+  for (auto& ch : root->children)
+    if (ch->name == "tendon")
+      for (auto& e : ch->children) {
+        if (e->name != "fixed") cfail("tendon <" + e->name + "> is outside the supported subset (fixed)");
+        check_attrs(*e, "tendon_fixed");
+        Attrs a = merged(B.c, *e, "tendon", "");
+        const std::string tname = a.str_or("name", "");
+        if (a.num("frictionloss", 0) != 0) cfail("tendon '" + tname + "': frictionloss is outside the supported subset");
+        double range[2] = {0, 0}, solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2}, spring[2] = {-1, -1};
+        const bool has_range = a.has("range");
+        a.vec("range", range, 2);
+        a.vec("solreflimit", solref, 2);
+        a.vec("solimplimit", solimp, 5, true);
+        if (a.has("springlength")) { const auto sv = a.nums("springlength"); a.vec("springlength", spring, 2, true); if (sv.size() == 1) spring[1] = spring[0]; }
+        const int lim = a.boolean("limited");
+        if (lim < 0 && has_range && !B.c.autolimits) cfail("tendon '" + tname + "': range given but limited unspecified and autolimits=false");
+        const bool limited = lim >= 0 ? lim == 1 : has_range;
+        if (limited && !(range[0] < range[1])) cfail("tendon '" + tname + "': limited tendon needs range[0] < range[1]");
+        M->v_tendon_adr.push_back(t.nwrap);
+        int num = 0;
+        double len0 = 0;
+        for (auto& w : e->children) {
+          if (w->name != "joint") pfail(*w, "a fixed tendon holds <joint> elements only");
+          check_attrs(*w, "tendon_joint");
+          const std::string* jn = w->attr("joint");
+          const std::string* cf = w->attr("coef");
+          if (!jn || !cf) pfail(*w, "tendon <joint> requires joint and coef");
+          const int j = find_name(nm[OX_OBJ_JOINT], *jn);
+          if (j < 0) cfail("tendon '" + tname + "': unknown joint '" + *jn + "'");
+          if (B.joints[j].type != OX_JNT_HINGE && B.joints[j].type != OX_JNT_SLIDE) cfail("tendon '" + tname + "': fixed tendons combine hinge / slide joints");
+          const double coef = std::stod(*cf);
+          M->v_wrap_objid.push_back(j); M->v_wrap_prm.push_back(coef);
+          len0 += coef * M->v_qpos0[M->v_jnt_qposadr[j]];
+          num++; t.nwrap++;
+        }
+        if (!num) cfail("tendon '" + tname + "': no joints");
+        M->v_tendon_num.push_back(num); M->v_tendon_limited.push_back(limited ? 1 : 0);
+        M->v_tendon_range.push_back(range[0]); M->v_tendon_range.push_back(range[1]);
+        M->v_tendon_margin.push_back(a.num("margin", 0));
+        for (double v : solref) M->v_tendon_solref_lim.push_back(v);
+        for (double v : solimp) M->v_tendon_solimp_lim.push_back(v);
+        M->v_tendon_stiffness.push_back(a.num("stiffness", 0)); M->v_tendon_damping.push_back(a.num("damping", 0));
+        if (a.num("damping", 0) != 0 && t.integrator == OX_INT_IMPLICITFAST)
+          cfail("tendon '" + tname + "': tendon damping with the implicitfast integrator (off-diagonal velocity derivative) is outside the supported subset");
+        // springlength -1 = "use the length at qpos0" (mj_setLengthRange convention of the compiler)
+        M->v_tendon_lengthspring.push_back(spring[0] < 0 && spring[1] < 0 ? len0 : spring[0]);
+        M->v_tendon_lengthspring.push_back(spring[0] < 0 && spring[1] < 0 ? len0 : spring[1]);
+        M->v_tendon_length0.push_back(len0); M->v_tendon_invweight0.push_back(0);
+        nm[OX_OBJ_TENDON].push_back(tname);
+        if (limited && !(t.disableflags & (OX_DSBL_LIMIT | OX_DSBL_CONSTRAINT))) t.nefcmax += 2;
+        t.ntendon++;
+      }
+  check_unique(OX_OBJ_TENDON, "tendon");
+
   // ---- sensors (N2 subset) ----
   {
     int adr = 0;
@@ -1120,6 +1185,7 @@ ox_model* compile_mjcf(const std::string& xml) {
               {"force", OX_SENS_FORCE, OX_OBJ_SITE, "site", 3}, {"torque", OX_SENS_TORQUE, OX_OBJ_SITE, "site", 3},
               {"framepos", OX_SENS_FRAMEPOS, -1, "objname", 3}, {"framequat", OX_SENS_FRAMEQUAT, -1, "objname", 4},
               {"framelinvel", OX_SENS_FRAMELINVEL, -1, "objname", 3}, {"frameangvel", OX_SENS_FRAMEANGVEL, -1, "objname", 3},
+              {"tendonpos", OX_SENS_TENDONPOS, OX_OBJ_TENDON, "tendon", 1}, {"tendonvel", OX_SENS_TENDONVEL, OX_OBJ_TENDON, "tendon", 1},
               {"clock", OX_SENS_CLOCK, OX_OBJ_UNKNOWN, nullptr, 1},
           };
           const Spec* sp = nullptr;
@@ -1274,6 +1340,15 @@ ox_model* compile_mjcf(const std::string& xml) {
         double a = (Minv[d * nv + d] + Minv[(d + 1) * nv + d + 1] + Minv[(d + 2) * nv + d + 2]) / 3;
         for (int k = 0; k < 3; k++) M->v_dof_invweight0[d + k] = a;
       } else M->v_dof_invweight0[d] = Minv[d * nv + d];
+    }
+    for (int i = 0; i < t.ntendon; i++) {   // tendon_invweight0 = J M^-1 J' with the (constant) tendon Jacobian
+      double w = 0;
+      for (int a = 0; a < M->v_tendon_num[i]; a++)
+        for (int c = 0; c < M->v_tendon_num[i]; c++) {
+          const int wa = M->v_tendon_adr[i] + a, wc = M->v_tendon_adr[i] + c;
+          w += M->v_wrap_prm[wa] * M->v_wrap_prm[wc] * Minv[jd[M->v_wrap_objid[wa]] * nv + jd[M->v_wrap_objid[wc]]];
+        }
+      M->v_tendon_invweight0[i] = w;
     }
     for (int b = 1; b < nbody; b++) {
       if (M->v_body_weldid[b] == 0) continue;  // static

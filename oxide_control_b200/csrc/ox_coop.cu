@@ -33,11 +33,11 @@ constexpr int CP_SROWS = 32;   // constraint rows of J staged in shared memory f
 // ---- per-group shared-memory layout: [DevBatch<T> view][int scalars + body levels][real fields][solver scratch]
 template <typename T>
 struct CoopSizes {
-  int nq, nv, nu, na, nb, nj, ng, ns, nM, ncm, nem, nsd, nmc, neq;
+  int nq, nv, nu, na, nb, nj, ng, ns, nM, ncm, nem, nsd, nmc, neq, nten;
   OX_HD static CoopSizes from(const BlobHeader& h) {
     CoopSizes s;
     s.nq = h.nq; s.nv = h.nv; s.nu = h.nu; s.na = h.na; s.nb = h.nbody; s.nj = h.njnt; s.ng = h.ngeom; s.ns = h.nsite; s.nM = h.nM;
-    s.ncm = h.nconmax > 1 ? h.nconmax : 1; s.nem = h.nefcmax > 1 ? h.nefcmax : 1; s.nsd = h.nsensordata; s.nmc = h.nmocap; s.neq = h.neq;
+    s.ncm = h.nconmax > 1 ? h.nconmax : 1; s.nem = h.nefcmax > 1 ? h.nefcmax : 1; s.nsd = h.nsensordata; s.nmc = h.nmocap; s.neq = h.neq; s.nten = h.ntendon;
     return s;
   }
 };
@@ -46,8 +46,8 @@ constexpr int COOP_NINT = 16;  // int scalars (ncon, nefc, ...) rounded up
 // words of T of shared memory one group needs (G enters through the solver scratch)
 template <typename T>
 OX_HD size_t coop_group_bytes(const CoopSizes<T>& z, int G) {
-  const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
-  (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq;
+  const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq, nten = z.nten;
+  (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq; (void)nten;
   size_t words = 0;
 #define OX_X(name, cnt) words += (size_t)((cnt) > 0 ? (cnt) : 1);
   OX_BATCH_REAL_FIELDS_SMALL(OX_X)
@@ -249,12 +249,17 @@ struct Coop {
       for (int k = 0; k < 6; k++) { b.cacc[k] = a0[k]; b.cfrc[k] = 0; }
     }
     each(h.nv, [&](int i) { b.qfrc_passive[i] = 0; });
+    each(h.ntendon, [&](int i) { env.tendon_length(i); });
     gsync();
     down(1, [&](int i) { env.vel_body(i); });
     if (!env.dis(OX_DSBL_PASSIVE)) {
       each(h.njnt, [&](int j) { env.passive_joint(j); });
       gsync();
       each(h.nv, [&](int i) { b.qfrc_passive[i] -= m.dof_damping(i) * b.qvel[i]; });
+      if (h.ntendon > 0) {   // a tendon touches several dofs: one lane applies them in order
+        gsync();
+        if (gl == 0) for (int i = 0; i < h.ntendon; i++) env.passive_tendon(i);
+      }
     }
     down(1, [&](int i) { env.rne_fwd_body(i); });
     gather_up<6>(b.cfrc, 1);
@@ -284,6 +289,13 @@ struct Coop {
           const int cnt = j < h.njnt ? env.limit_count(j) : 0;
           int r = base + gscan_excl(cnt);
           if (cnt) env.limit_rows(j, r);
+          base += gsumi(cnt);
+        }
+        for (int i0 = 0; i0 < h.ntendon; i0 += G) {
+          const int i = i0 + gl;
+          const int cnt = i < h.ntendon ? env.tendon_limit_count(i) : 0;
+          int r = base + gscan_excl(cnt);
+          if (cnt) env.tendon_limit_rows(i, r);
           base += gsumi(cnt);
         }
       }
@@ -635,8 +647,8 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   T* rb = reinterpret_cast<T*>(base + (sizeof(DevBatch<T>) + (COOP_NINT + (size_t)h.nbody) * sizeof(int32_t) + 15) / 16 * 16);
   const CoopSizes<T> z = CoopSizes<T>::from(h);
   if (gl == 0) {
-    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, ncm = z.ncm, nem = z.nem, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
-    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)ncm; (void)nem; (void)nsd; (void)nmc; (void)neq;
+    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, ncm = z.ncm, nem = z.nem, nsd = z.nsd, nmc = z.nmc, neq = z.neq, nten = z.nten;
+    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)ncm; (void)nem; (void)nsd; (void)nmc; (void)neq; (void)nten;
     lb->nenv = 1; lb->stride = 1; lb->lanes = 32;
     T* p = rb;
 #define OX_X(name, cnt) lb->name = p; p += ((cnt) > 0 ? (cnt) : 1);
@@ -655,8 +667,8 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
   __syncwarp(gmask);
   T* scratch = rb;
   {
-    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq;
-    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq;
+    const long nq = z.nq, nv = z.nv, nu = z.nu, na = z.na, nb = z.nb, nj = z.nj, ng = z.ng, ns = z.ns, nM = z.nM, nsd = z.nsd, nmc = z.nmc, neq = z.neq, nten = z.nten;
+    (void)nq; (void)nv; (void)nu; (void)na; (void)nb; (void)nj; (void)ng; (void)ns; (void)nM; (void)nsd; (void)nmc; (void)neq; (void)nten;
 #define OX_X(name, cnt) scratch += ((cnt) > 0 ? (cnt) : 1);
     OX_BATCH_REAL_FIELDS_SMALL(OX_X)
 #undef OX_X
@@ -732,7 +744,7 @@ template <typename T>
 static size_t coop_group_bytes_host(const ox_model_tables& t, int G) {
   CoopSizes<T> z;
   z.nq = t.nq; z.nv = t.nv; z.nu = t.nu; z.na = t.na; z.nb = t.nbody; z.nj = t.njnt; z.ng = t.ngeom; z.ns = t.nsite; z.nM = t.nM;
-  z.ncm = t.nconmax > 1 ? t.nconmax : 1; z.nem = t.nefcmax > 1 ? t.nefcmax : 1; z.nsd = t.nsensordata; z.nmc = t.nmocap; z.neq = t.neq;
+  z.ncm = t.nconmax > 1 ? t.nconmax : 1; z.nem = t.nefcmax > 1 ? t.nefcmax : 1; z.nsd = t.nsensordata; z.nmc = t.nmocap; z.neq = t.neq; z.nten = t.ntendon;
   return coop_group_bytes<T>(z, G);
 }
 size_t step_coop_smem(const ox_model_tables& t, int blob_bytes, bool f64) {

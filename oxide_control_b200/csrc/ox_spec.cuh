@@ -45,7 +45,7 @@ inline uint64_t model_hash(const ox_model_tables& t) {
     const unsigned char* c = static_cast<const unsigned char*>(p);
     for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
   };
-  const int32_t sizes[] = {t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
+  const int32_t sizes[] = {t.ntendon, t.nwrap, t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
                            t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags, t.noslip_iterations};
   mix(sizes, sizeof sizes);
   const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia, t.noslip_tolerance};
@@ -72,7 +72,7 @@ OX_HDN void spec_step_env(const DevBatch<T>& g, int e, const StepArgs& a, const 
   // struct): each array whose indices all fold to constants after unrolling is promoted to registers independently;
   // only the runtime-indexed ones (contact / constraint rows and what the contact Jacobian walk reads) stay in local memory.
   constexpr int nq = H::nq, nv = H::nv, nu = H::nu, na = H::na, nb = H::nbody, nj = H::njnt, ng = H::ngeom, ns = H::nsite, nM = H::nM,
-                ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata, nmc = H::nmocap, neq = H::neq;
+                ncm = AtLeast1<H::nconmax>::v, nem = AtLeast1<H::nefcmax>::v, nsd = H::nsensordata, nmc = H::nmocap, neq = H::neq, nten = H::ntendon;
 #define OX_X(name, cnt) T loc_##name[AtLeast1<(cnt)>::v];
   OX_BATCH_REAL_FIELDS(OX_X)
 #undef OX_X

@@ -631,16 +631,44 @@ struct Env {
   }
 
   // ============================================================ passive forces
+  // fixed tendons (mj_tendon): length = sum of coef * joint coordinate; the Jacobian is the constant coefficient vector
+  OX_HD void tendon_length(int i) const {
+    T L = 0;
+    OX_MLOOP
+    for (int w = 0; w < m.tendon_num(i); w++) L += m.wrap_prm(m.tendon_adr(i) + w) * at(b.qpos, m.jnt_qposadr(m.wrap_objid(m.tendon_adr(i) + w)));
+    at(b.ten_length, i) = L;
+  }
+  OX_HD T tendon_velocity(int i) const {
+    T v = 0;
+    OX_MLOOP
+    for (int w = 0; w < m.tendon_num(i); w++) v += m.wrap_prm(m.tendon_adr(i) + w) * at(b.qvel, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w)));
+    return v;
+  }
+  // spring with dead band [lengthspring0, lengthspring1] and damper, mapped to the joints through J'
+  OX_HD void passive_tendon(int i) const {
+    const T L = at(b.ten_length, i), lo = m.tendon_lengthspring(2 * i), hi = m.tendon_lengthspring(2 * i + 1);
+    T f = 0;
+    if (L > hi) f = m.tendon_stiffness(i) * (hi - L);
+    else if (L < lo) f = m.tendon_stiffness(i) * (lo - L);
+    f -= m.tendon_damping(i) * tendon_velocity(i);
+    if (f == 0) return;
+    OX_MLOOP
+    for (int w = 0; w < m.tendon_num(i); w++) at(b.qfrc_passive, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w))) += m.wrap_prm(m.tendon_adr(i) + w) * f;
+  }
   OX_HDN void passive() const {
     const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) = 0;
+    OX_MLOOP
+    for (int i = 0; i < h.ntendon; i++) tendon_length(i);
     if (dis(OX_DSBL_PASSIVE)) return;
     OX_MLOOP
     for (int j = 0; j < njnt; j++) passive_joint(j);
     OX_MLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping(i) * at(b.qvel, i);
+    OX_MLOOP
+    for (int i = 0; i < h.ntendon; i++) passive_tendon(i);
   }
   OX_HD void passive_joint(int j) const {  // joint spring: touches only this joint's dofs
     {
@@ -843,6 +871,73 @@ struct Env {
     c.pos[0] = pos1[0] + c.frame[0] * s; c.pos[1] = pos1[1] + c.frame[1] * s; c.pos[2] = pos1[2] + c.frame[2] * s;
     return 1;
   }
+  // sphere against a box (mjc_SphereBox): closest box point = the centre clamped to the box in the box frame; a centre inside the
+  // box leaves through the nearest face. Normal from the sphere (geom1) to the box (geom2).
+  static OX_HD int sphere_box(Con& c, T margin, const T* centre, T radius, const T* pos2, const T* mat2, const T* size2) {
+    const T tmp[3] = {centre[0] - pos2[0], centre[1] - pos2[1], centre[2] - pos2[2]};
+    T lc[3], clamped[3], dir[3], lpos[3], lnorm[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      lc[k] = mat2[k] * tmp[0] + mat2[3 + k] * tmp[1] + mat2[6 + k] * tmp[2];
+      clamped[k] = ox_clip(lc[k], -size2[k], size2[k]);
+      dir[k] = clamped[k] - lc[k];
+    }
+    const T dist = ox_sqrt(dot3(dir, dir));
+    if (dist - radius > margin) return 0;
+    if (dist <= (T)OX_MINVAL) {
+      T closest = 2 * ox_max(size2[0], ox_max(size2[1], size2[2]));
+      int face = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const T fd = ox_abs((i % 2 ? (T)1 : (T)-1) * size2[i / 2] - lc[i / 2]);
+        if (fd < closest) { closest = fd; face = i; }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) lnorm[k] = (k == face / 2) ? (face % 2 ? (T)-1 : (T)1) : (T)0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) lpos[k] = lc[k] + lnorm[k] * (radius - closest) / 2;
+      c.dist = -closest - radius;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) lnorm[k] = dir[k] / dist;
+#pragma unroll
+      for (int k = 0; k < 3; k++) lpos[k] = (T)0.5 * (clamped[k] + lc[k] + lnorm[k] * radius);
+      c.dist = dist - radius;
+    }
+    mat_vec3(c.frame, mat2, lnorm);
+    c.frame[3] = 0; c.frame[4] = 0; c.frame[5] = 0;
+    T w[3];
+    mat_vec3(w, mat2, lpos);
+    c.pos[0] = w[0] + pos2[0]; c.pos[1] = w[1] + pos2[1]; c.pos[2] = w[2] + pos2[2];
+    return 1;
+  }
+  // parameter t in [-1, 1] of the point of the segment lc + t la (box frame) closest to the box: zero crossing of the piecewise
+  // linear, non-decreasing derivative g(t) of half the squared distance (ORACLE_DECISIONS.md #12)
+  static OX_HD T segment_box_closest(const T* lc, const T* la, const T* size2) {
+    auto g = [&](T t) {
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { const T pk = lc[k] + t * la[k]; s += la[k] * (pk - ox_clip(pk, -size2[k], size2[k])); }
+      return s;
+    };
+    const T gm = g((T)-1), gp = g((T)1);
+    if (gm >= 0) return -1;
+    if (gp <= 0) return 1;
+    T ta = -1, ga = gm, tb = 1, gb = gp;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (!(ox_abs(la[k]) > (T)OX_MINVAL)) continue;
+#pragma unroll
+      for (int sg = -1; sg <= 1; sg += 2) {
+        const T t = ((T)sg * size2[k] - lc[k]) / la[k];
+        if (!(t > -1 && t < 1)) continue;
+        const T gi = g(t);
+        if (gi < 0) { if (t > ta) { ta = t; ga = gi; } }
+        else if (t < tb) { tb = t; gb = gi; }
+      }
+    }
+    return gb - ga > (T)OX_MINVAL ? ta - ga * (tb - ta) / (gb - ga) : ta;
+  }
   static OX_HD void make_frame(T* frame) {
     normalize3(frame);
     if (ox_sqrt(dot3(frame + 3, frame + 3)) < (T)0.5) {
@@ -900,7 +995,8 @@ struct Env {
           // produce a contact. Conservative (a hair of slack for round-off; the exact test follows when it does not fire),
           // so the contact set is unchanged - but the capsule-capsule narrowphase is ~1 k instructions per pair, and for a
           // humanoid's 20 self-collision pairs, almost always far apart, it was 43 % of the PRE kernel's instruction stream.
-          const T rb = size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0) + size2[0] + (t2 == OX_GEOM_CAPSULE ? size2[1] : (T)0) + margin;
+          const T rb2 = t2 == OX_GEOM_BOX ? ox_sqrt(dot3(size2, size2)) : size2[0] + (t2 == OX_GEOM_CAPSULE ? size2[1] : (T)0);
+          const T rb = size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0) + rb2 + margin;
           const T dx = pos2[0] - pos1[0], dy = pos2[1] - pos1[1], dz = pos2[2] - pos1[2];
           if (dx * dx + dy * dy + dz * dz > rb * rb * (T)1.0005 + (T)1e-9) return;
         }
@@ -957,6 +1053,36 @@ struct Env {
           vec[0] = pos2[0] + axis[0] * x; vec[1] = pos2[1] + axis[1] * x; vec[2] = pos2[2] + axis[2] * x;
           Con c;
           if (sphere_sphere(c, margin, pos1, size1[0], vec, size2[0])) emit(c, p, 0, ncon);
+        } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_BOX) {
+          T mat2[9];
+          ld<9>(mat2, b.geom_xmat, 9 * g2);
+          Con c;
+          if (sphere_box(c, margin, pos1, size1[0], pos2, mat2, size2)) emit(c, p, 0, ncon);
+        } else if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_BOX) {
+          T mat2[9];
+          ld<9>(mat2, b.geom_xmat, 9 * g2);
+          const T axis[3] = {at(b.geom_xmat, 9 * g1 + 2), at(b.geom_xmat, 9 * g1 + 5), at(b.geom_xmat, 9 * g1 + 8)};
+          const T hl = size1[1];
+          const T tmp[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+          T lc[3], la[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            lc[k] = mat2[k] * tmp[0] + mat2[3 + k] * tmp[1] + mat2[6 + k] * tmp[2];
+            la[k] = (mat2[k] * axis[0] + mat2[3 + k] * axis[1] + mat2[6 + k] * axis[2]) * hl;
+          }
+          const T tstar = segment_box_closest(lc, la, size2);
+          int n = 0;
+#pragma unroll
+          for (int which = 0; which < 2; which++) {   // the closest point of the axis, then the far end cap
+            const T t = which == 0 ? tstar : (tstar <= 0 ? (T)1 : (T)-1);
+            const T pt[3] = {pos1[0] + t * hl * axis[0], pos1[1] + t * hl * axis[1], pos1[2] + t * hl * axis[2]};
+            Con c;
+            if (sphere_box(c, margin, pt, size1[0], pos2, mat2, size2)) {
+              c.frame[3] = axis[0]; c.frame[4] = axis[1]; c.frame[5] = axis[2];
+              if (n == 0) emit(c, p, 0, ncon); else emit(c, p, 1, ncon);
+              n++;
+            }
+          }
         } else if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {
           T axis1[3] = {at(b.geom_xmat, 9 * g1 + 2) * size1[1], at(b.geom_xmat, 9 * g1 + 5) * size1[1], at(b.geom_xmat, 9 * g1 + 8) * size1[1]};
           T axis2[3] = {at(b.geom_xmat, 9 * g2 + 2) * size2[1], at(b.geom_xmat, 9 * g2 + 5) * size2[1], at(b.geom_xmat, 9 * g2 + 8) * size2[1]};
@@ -1153,6 +1279,10 @@ struct Env {
         OX_MLOOP
         for (int j = 0; j < njnt; j++) limit_rows(j, nefc);
       }
+      if (!dis(OX_DSBL_LIMIT)) {
+        OX_MLOOP
+        for (int i = 0; i < h.ntendon; i++) tendon_limit_rows(i, nefc);
+      }
       if (STATIC_CON) {  // static contact slots: every index below is a compile-time constant after unrolling
         OX_MLOOP
         for (int p = 0; p < h.npair; p++) {
@@ -1287,6 +1417,40 @@ struct Env {
               at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
             }
           }
+      }
+    }
+  }
+
+  // tendon limits: the joint-limit row with J = -side * (tendon coefficients), diagApprox = tendon_invweight0
+  OX_HD int tendon_limit_count(int i) const {
+    if (!m.tendon_limited(i)) return 0;
+    const T value = at(b.ten_length, i), margin = m.tendon_margin(i);
+    return (value - m.tendon_range(2 * i) < margin ? 1 : 0) + (m.tendon_range(2 * i + 1) - value < margin ? 1 : 0);
+  }
+  OX_HD void tendon_limit_rows(int i, int& nefc) const {
+    const int nv = m.h().nv;
+    if (!m.tendon_limited(i)) return;
+    const T value = at(b.ten_length, i), margin = m.tendon_margin(i);
+    OX_MLOOP
+    for (int side = -1; side <= 1; side += 2) {
+      const T dist = side * (m.tendon_range(2 * i + (side + 1) / 2) - value);
+      if (dist < margin) {
+        const int r = nefc++;
+        OX_MLOOP
+        for (int k = 0; k < nv; k++) at(b.efc_J, r * nv + k) = 0;
+        T vel = 0;
+        OX_MLOOP
+        for (int w = 0; w < m.tendon_num(i); w++) {
+          const int da = m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w));
+          const T c = (T)(-side) * m.wrap_prm(m.tendon_adr(i) + w);
+          at(b.efc_J, r * nv + da) += c;
+          vel += c * at(b.qvel, da);
+        }
+        T aref, sr[2], si[5];
+        OX_LDM(2, sr, tendon_solref_lim, 2 * i);
+        OX_LDM(5, si, tendon_solimp_lim, 5 * i);
+        const T R = row_params(sr, si, dist, margin, m.tendon_invweight0(i), vel, &aref);
+        at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
       }
     }
   }
@@ -1937,6 +2101,8 @@ struct Env {
         case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qpos, m.jnt_qposadr(m.actuator_trnid(id))); break;
         case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qvel, m.jnt_dofadr(m.actuator_trnid(id))); break;
         case OX_SENS_ACTUATORFRC: at(b.sensordata, adr) = at(b.actuator_force, id); break;
+        case OX_SENS_TENDONPOS: at(b.sensordata, adr) = at(b.ten_length, id); break;
+        case OX_SENS_TENDONVEL: at(b.sensordata, adr) = tendon_velocity(id); break;
         case OX_SENS_SUBTREECOM: for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_com, 3 * id + k); break;
         case OX_SENS_SUBTREELINVEL: {
           if (!have_slv) {

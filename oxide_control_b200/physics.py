@@ -75,7 +75,7 @@ class ObjectId:
 
 class obj:  # noqa: N801  (mirrors rusty_mujoco::obj)
     Body, Joint, Dof, Geom, Site = A.OBJ_BODY, A.OBJ_JOINT, A.OBJ_DOF, A.OBJ_GEOM, A.OBJ_SITE
-    Actuator, Sensor, Equality, Plugin = A.OBJ_ACTUATOR, A.OBJ_SENSOR, A.OBJ_EQUALITY, A.OBJ_PLUGIN
+    Actuator, Sensor, Equality, Plugin, Tendon = A.OBJ_ACTUATOR, A.OBJ_SENSOR, A.OBJ_EQUALITY, A.OBJ_PLUGIN, A.OBJ_TENDON
 
 
 class joint:  # noqa: N801  (mirrors rusty_mujoco::joint: Qpos / Qvel widths per joint type)

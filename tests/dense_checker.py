@@ -71,17 +71,18 @@ class DenseModel:
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
            "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
            "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id",
-           "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid"]
+           "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "wrap_objid"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
             "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
             "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
             "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
             "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange",
-            "eq_solref", "eq_solimp", "eq_data", "site_pos", "site_quat"]
+            "eq_solref", "eq_solimp", "eq_data", "site_pos", "site_quat", "wrap_prm", "tendon_range", "tendon_margin", "tendon_solref_lim",
+            "tendon_solimp_lim", "tendon_stiffness", "tendon_damping", "tendon_lengthspring", "tendon_invweight0"]
 
     def __init__(self, model):
         self.m = model
-        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq", "nsensor", "nsensordata"):
+        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq", "nsensor", "nsensordata", "ntendon"):
             setattr(self, k, int(getattr(model, k)))
         for k in ("timestep", "impratio"):
             setattr(self, k, float(getattr(model, k)))
@@ -228,7 +229,29 @@ def passive_force(dm, qpos, qvel):
             f[da:da + 3] -= k * sub_quat(q, dm.qpos_spring[qa:qa + 4])
         else:
             f[da] -= k * (qpos[qa] - dm.qpos_spring[qa])
-    return f - dm.dof_damping * qvel
+    f = f - dm.dof_damping * qvel
+    for i in range(dm.ntendon):                                          # tendon spring (dead band) and damper through the coefficient vector
+        Jt, L = tendon_jacobian(dm, i), tendon_jacobian(dm, i) @ tendon_coords(dm, qpos)
+        lo, hi = dm.tendon_lengthspring[2 * i:2 * i + 2]
+        frc = dm.tendon_stiffness[i] * ((hi - L) if L > hi else (lo - L) if L < lo else 0.0) - dm.tendon_damping[i] * (Jt @ qvel)
+        f = f + Jt * frc
+    return f
+
+
+def tendon_jacobian(dm, i):
+    Jt = np.zeros(dm.nv)
+    for w in range(int(dm.tendon_adr[i]), int(dm.tendon_adr[i] + dm.tendon_num[i])):
+        Jt[int(dm.jnt_dofadr[int(dm.wrap_objid[w])])] += dm.wrap_prm[w]
+    return Jt
+
+
+def tendon_coords(dm, qpos):
+    """joint coordinates laid out by dof address (scalar joints only carry a tendon)"""
+    x = np.zeros(dm.nv)
+    for j in range(dm.njnt):
+        if int(dm.jnt_type[j]) in (SLIDE, HINGE):
+            x[int(dm.jnt_dofadr[j])] = qpos[int(dm.jnt_qposadr[j])]
+    return x
 
 
 def actuator_force(dm, qpos, qvel, ctrl, act=None):
@@ -338,6 +361,49 @@ def segment_closest(p1, a1, p2, a2):
     return best[1], best[2]
 
 
+def sphere_box(centre, radius, bpos, bmat, bsize, margin):
+    """(dist, pos, normal) or None. World-frame statement: project the centre onto the box by clamping its box coordinates."""
+    lc = bmat.T @ (centre - bpos)
+    q = np.clip(lc, -bsize, bsize)
+    d = np.linalg.norm(q - lc)
+    if d - radius > margin:
+        return None
+    if d <= MINVAL:                                                      # centre inside: leave through the nearest face
+        gaps = np.concatenate([lc + bsize, bsize - lc])                  # distances to the -x,-y,-z,+x,+y,+z faces
+        order = [0, 3, 1, 4, 2, 5]                                       # the product scans -x,+x,-y,+y,-z,+z and keeps the first minimum
+        k = min(order, key=lambda i: (gaps[i], order.index(i)))
+        n = np.zeros(3)
+        n[k % 3] = 1.0 if k < 3 else -1.0
+        depth = gaps[k]
+        return -depth - radius, bpos + bmat @ (lc + n * (radius - depth) / 2), bmat @ n
+    n = (q - lc) / d
+    return d - radius, bpos + bmat @ (0.5 * (q + lc + n * radius)), bmat @ n
+
+
+def segment_box_closest(lc, la, bsize):
+    """argmin over t in [-1,1] of the distance from lc + t la to the box: the squared distance is quadratic between the breakpoints
+    where a coordinate crosses a face, so each interval is minimised in closed form (parabola through three samples)."""
+    f = lambda t: float(np.sum((lc + t * la - np.clip(lc + t * la, -bsize, bsize)) ** 2))
+    ts = [-1.0, 1.0]
+    for k in range(3):
+        if abs(la[k]) > MINVAL:
+            ts += [t for t in ((sg * bsize[k] - lc[k]) / la[k] for sg in (-1.0, 1.0)) if -1 < t < 1]
+    ts = sorted(ts)
+    best = (f(-1.0), -1.0)
+    for t0, t1 in zip(ts[:-1], ts[1:]):
+        if t1 - t0 < 1e-15:
+            continue
+        tm = 0.5 * (t0 + t1)
+        f0, fm, f1 = f(t0), f(tm), f(t1)
+        curv = 2 * (f0 - 2 * fm + f1) / (t1 - t0) ** 2                    # f'' on this piece
+        slope0 = (f1 - f0) / (t1 - t0) - 0.5 * curv * (t1 - t0)           # f' at t0
+        cands = [t0, t1] + ([float(np.clip(t0 - slope0 / curv, t0, t1))] if curv > 1e-300 else [])
+        for t in sorted(cands):
+            if f(t) < best[0] - 1e-18:
+                best = (f(t), t)
+    return best[1]
+
+
 def mix_params(dm, g1, g2):
     """mj_contactParam."""
     p1, p2 = dm.geom_priority[g1], dm.geom_priority[g2]
@@ -408,6 +474,16 @@ def collide(dm: DenseModel, kin: Kin):
             x = float(np.clip(ax @ (gpos[g1] - gpos[g2]), -s2[1], s2[1]))
             r = sphere_sphere(gpos[g1], s1[0], gpos[g2] + ax * x, s2[0], margin)
             if r: found.append((r, None))
+        elif t1 == SPHERE and t2 == BOX:
+            r = sphere_box(gpos[g1], s1[0], gpos[g2], gmat[g2], s2, margin)
+            if r: found.append((r, None))
+        elif t1 == CAPSULE and t2 == BOX:
+            ax = gmat[g1][:, 2]
+            lc, la = gmat[g2].T @ (gpos[g1] - gpos[g2]), gmat[g2].T @ ax * s1[1]
+            tstar = segment_box_closest(lc, la, s2)
+            for t in (tstar, 1.0 if tstar <= 0 else -1.0):               # closest point of the axis, then the far end cap
+                r = sphere_box(gpos[g1] + t * s1[1] * ax, s1[0], gpos[g2], gmat[g2], s2, margin)
+                if r: found.append((r, ax))
         elif t1 == CAPSULE and t2 == CAPSULE:
             a1, a2 = gmat[g1][:, 2] * s1[1], gmat[g2][:, 2] * s2[1]
             s, t = segment_closest(gpos[g1], a1, gpos[g2], a2)
@@ -506,6 +582,18 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                     row[da] = sign
                     a, R = row_params(dm, dm.jnt_solref[2 * j:2 * j + 2], dm.jnt_solimp[5 * j:5 * j + 5], dist, dm.jnt_margin[j],
                                       dm.dof_invweight0[da], row @ qvel)
+                    J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
+    if not dm.dis("limit"):
+        for i in range(dm.ntendon):
+            if not dm.tendon_limited[i]:
+                continue
+            Jt = tendon_jacobian(dm, i)
+            L = Jt @ tendon_coords(dm, qpos)
+            for sign, dist in ((1.0, L - dm.tendon_range[2 * i]), (-1.0, dm.tendon_range[2 * i + 1] - L)):
+                if dist < dm.tendon_margin[i]:
+                    row = sign * Jt
+                    a, R = row_params(dm, dm.tendon_solref_lim[2 * i:2 * i + 2], dm.tendon_solimp_lim[5 * i:5 * i + 5], dist, dm.tendon_margin[i],
+                                      dm.tendon_invweight0[i], row @ qvel)
                     J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
     for c in contacts:
         prm = c["prm"]

@@ -275,5 +275,41 @@ ZOO_F = """
 
 ZOO_G = HOPPER.replace('model="hopper_user"', 'model="zoo_g"').replace('<option timestep="0.004"/>', '<option timestep="0.004" noslip_iterations="3"/>')
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G}
+# N3: fixed tendons - a limited tendon coupling two hinges, a spring tendon with a dead band and damping over a hinge and a slide,
+# joint limits and contacts in the same problem, tendonpos / tendonvel sensors
+ZOO_H = """
+<mujoco model="zoo_h">
+  <compiler angle="radian"/>
+  <option timestep="0.004"/>
+  <default><joint damping="0.05" armature="0.005"/><tendon solreflimit="0.015 1"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <body name="base" pos="0 0 0.1">
+      <joint name="lift" type="slide" axis="0 0 1" range="-0.03 0.3" limited="true"/>
+      <geom name="base" type="sphere" size="0.06"/>
+      <body name="f1" pos="0 0 0">
+        <joint name="k1" type="hinge" axis="0 1 0" range="-1.5 1.5" limited="true"/>
+        <geom name="f1" type="capsule" fromto="0 0 0 0.25 0 0" size="0.025"/>
+        <body name="f2" pos="0.25 0 0">
+          <joint name="k2" type="hinge" axis="0 1 0"/>
+          <geom name="f2" type="capsule" fromto="0 0 0 0.2 0 0" size="0.02"/>
+          <body name="f3" pos="0.2 0 0">
+            <joint name="k3" type="hinge" axis="0 1 0"/>
+            <geom name="f3" type="capsule" fromto="0 0 0 0.15 0 0" size="0.018"/>
+          </body>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <tendon>
+    <fixed name="curl" limited="true" range="-0.6 0.9" margin="0.02"><joint joint="k2" coef="1"/><joint joint="k3" coef="-0.7"/></fixed>
+    <fixed name="spring" stiffness="12" damping="0.4" springlength="-0.1 0.15"><joint joint="k1" coef="0.5"/><joint joint="lift" coef="2"/></fixed>
+    <fixed name="soft" stiffness="3" range="-2 2"><joint joint="k1" coef="1"/><joint joint="k2" coef="1"/><joint joint="k3" coef="1"/></fixed>
+  </tendon>
+  <actuator><motor joint="k1" gear="2"/><motor joint="k3" gear="0.6"/></actuator>
+  <sensor><tendonpos tendon="curl"/><tendonvel tendon="spring"/><tendonpos tendon="soft"/><jointpos joint="k2"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H}
 NOCONTACT = {"zoo_d": ZOO_D}
