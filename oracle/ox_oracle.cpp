@@ -459,8 +459,20 @@ int capsuleBox(RawContact* con, double margin, const double* pos1, const double*
         double t = (sgn * size2[k] - c[k]) / a[k];
         if (t > -1 && t < 1) cand[nc++] = t;
       }
+  // the axis itself cuts through the box (deep penetration): every point of the cut is at distance zero, take its middle - the
+  // nearest-face rule of sphereBox needs a point well inside, not one on the surface
+  double tin = -1, tout = 1;
+  bool cut = true;
+  for (int k = 0; k < 3; k++) {
+    if (std::fabs(a[k]) > OX_MINVAL) {
+      double t1 = (-size2[k] - c[k]) / a[k], t2 = (size2[k] - c[k]) / a[k];
+      if (t1 > t2) std::swap(t1, t2);
+      tin = std::max(tin, t1); tout = std::min(tout, t2);
+    } else if (std::fabs(c[k]) > size2[k]) cut = false;
+  }
   double tstar;
-  if (g(-1) >= 0) tstar = -1;
+  if (cut && tin <= tout) tstar = 0.5 * (tin + tout);
+  else if (g(-1) >= 0) tstar = -1;
   else if (g(1) <= 0) tstar = 1;
   else {
     double ta = -1, ga = g(-1), tb = 1, gb = g(1);

@@ -920,6 +920,20 @@ struct Env {
       for (int k = 0; k < 3; k++) { const T pk = lc[k] + t * la[k]; s += la[k] * (pk - ox_clip(pk, -size2[k], size2[k])); }
       return s;
     };
+    {  // the axis itself cuts through the box (deep penetration): the middle of the cut, so that sphere_box's nearest-face rule
+       // sees a point well inside
+      T tin = -1, tout = 1;
+      bool cut = true;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (ox_abs(la[k]) > (T)OX_MINVAL) {
+          T t1 = (-size2[k] - lc[k]) / la[k], t2 = (size2[k] - lc[k]) / la[k];
+          if (t1 > t2) { const T sw = t1; t1 = t2; t2 = sw; }
+          tin = ox_max(tin, t1); tout = ox_min(tout, t2);
+        } else if (ox_abs(lc[k]) > size2[k]) cut = false;
+      }
+      if (cut && tin <= tout) return (T)0.5 * (tin + tout);
+    }
     const T gm = g((T)-1), gp = g((T)1);
     if (gm >= 0) return -1;
     if (gp <= 0) return 1;

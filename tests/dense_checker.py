@@ -381,27 +381,47 @@ def sphere_box(centre, radius, bpos, bmat, bsize, margin):
 
 
 def segment_box_closest(lc, la, bsize):
-    """argmin over t in [-1,1] of the distance from lc + t la to the box: the squared distance is quadratic between the breakpoints
-    where a coordinate crosses a face, so each interval is minimised in closed form (parabola through three samples)."""
-    f = lambda t: float(np.sum((lc + t * la - np.clip(lc + t * la, -bsize, bsize)) ** 2))
-    ts = [-1.0, 1.0]
+    """argmin over t in [-1,1] of the distance from lc + t la to the box, in EXACT rational arithmetic (the floats are taken as the
+    rationals they are): the squared distance is a quadratic between the breakpoints where a coordinate crosses a face, so every
+    piece is minimised in closed form and the pieces compared exactly; the leftmost minimiser wins ties. Near-parallel
+    configurations make this minimiser ill-conditioned in floating point, which is exactly where a checker must not be sloppy."""
+    from fractions import Fraction as Fr
+    c, a, sz = [Fr(float(v)) for v in lc], [Fr(float(v)) for v in la], [Fr(float(v)) for v in bsize]
+
+    def f(t):
+        tot = Fr(0)
+        for k in range(3):
+            p = c[k] + t * a[k]
+            e = p - max(-sz[k], min(sz[k], p))
+            tot += e * e
+        return tot
+
+    ts = {Fr(-1), Fr(1)}
     for k in range(3):
-        if abs(la[k]) > MINVAL:
-            ts += [t for t in ((sg * bsize[k] - lc[k]) / la[k] for sg in (-1.0, 1.0)) if -1 < t < 1]
+        if a[k] != 0:
+            for sg in (-1, 1):
+                t = (sg * sz[k] - c[k]) / a[k]
+                if -1 < t < 1:
+                    ts.add(t)
     ts = sorted(ts)
-    best = (f(-1.0), -1.0)
+    inside = [t for t in ts if f(t) == 0]                                 # the axis cuts through the box: the middle of the cut
+    if inside:                                                            # (entry and exit are breakpoints or segment ends)
+        return float((inside[0] + inside[-1]) / 2)
+    best_f, best_t = f(Fr(-1)), Fr(-1)
     for t0, t1 in zip(ts[:-1], ts[1:]):
-        if t1 - t0 < 1e-15:
-            continue
-        tm = 0.5 * (t0 + t1)
+        tm = (t0 + t1) / 2
         f0, fm, f1 = f(t0), f(tm), f(t1)
-        curv = 2 * (f0 - 2 * fm + f1) / (t1 - t0) ** 2                    # f'' on this piece
-        slope0 = (f1 - f0) / (t1 - t0) - 0.5 * curv * (t1 - t0)           # f' at t0
-        cands = [t0, t1] + ([float(np.clip(t0 - slope0 / curv, t0, t1))] if curv > 1e-300 else [])
+        h = t1 - t0
+        curv = 4 * (f0 - 2 * fm + f1) / (h * h)                          # exact f'' of this piece (second difference over (h/2)^2)
+        slope0 = (f1 - f0) / h - curv * h / 2                            # exact f'(t0+)
+        cands = [t0, t1]
+        if curv > 0:
+            cands.append(max(t0, min(t1, t0 - slope0 / curv)))
         for t in sorted(cands):
-            if f(t) < best[0] - 1e-18:
-                best = (f(t), t)
-    return best[1]
+            ft = f(t)
+            if ft < best_f:
+                best_f, best_t = ft, t
+    return float(best_t)
 
 
 def mix_params(dm, g1, g2):

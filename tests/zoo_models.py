@@ -311,5 +311,28 @@ ZOO_H = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H}
+# N3: box narrowphase beyond box-plane - spheres and capsules against free and static boxes (faces, edges, corners, corners), on top of the plane pairs; the box-box pair (slab / step) is masked out - that narrowphase is outside the supported set. zoo_f's crate / roller / marble exclusions are not needed any more.
+ZOO_I = """
+<mujoco model="zoo_i">
+  <compiler angle="radian"/>
+  <option timestep="0.003" tolerance="1e-13"/>
+  <default><geom friction="0.9 0.01 0.001"/><default class="mover"><geom contype="5"/></default></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <geom name="step" type="box" pos="0.5 0 0.1" size="0.25 0.3 0.1" euler="0 0 0.3" contype="2" conaffinity="4"/>
+    <body name="slab" pos="-0.4 0 0.08" euler="0.05 0.1 0.2">
+      <freejoint/>
+      <geom name="slab" type="box" size="0.3 0.25 0.06" density="300"/>
+    </body>
+    <body name="ball1" pos="-0.45 0.05 0.3"><freejoint/><geom name="ball1" class="mover" type="sphere" size="0.07"/></body>
+    <body name="ball2" pos="0.45 0.28 0.35"><freejoint/><geom name="ball2" class="mover" type="sphere" size="0.06" condim="1"/></body>
+    <body name="rod1" pos="-0.3 -0.1 0.35" euler="0.4 1.2 0"><freejoint/><geom name="rod1" class="mover" type="capsule" size="0.04 0.18"/></body>
+    <body name="rod2" pos="0.62 -0.05 0.32" euler="1.5707963 0.1 0.3"><freejoint/><geom name="rod2" class="mover" type="capsule" size="0.035 0.22"/></body>
+    <body name="rod3" pos="0.3 -0.32 0.42" euler="0.2 0.1 0"><freejoint/><geom name="rod3" class="mover" type="capsule" size="0.03 0.15"/></body>
+  </worldbody>
+  <sensor><framepos objtype="body" objname="ball1"/><framepos objtype="body" objname="rod2"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I}
 NOCONTACT = {"zoo_d": ZOO_D}
