@@ -124,8 +124,9 @@ __global__ void k_pack_record(TF* __restrict__ field, TU* __restrict__ user, int
 using namespace ox;
 
 namespace ox {
-cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax);
-cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int nefcmax);
+cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int resident_ctas, int* ctr);
+cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int resident_ctas, int* ctr);
+int solve_coop_resident_ctas(int blob_bytes, bool f64);
 cudaError_t solve_coop_prepare(int blob_bytes, bool f64);  // per-device opt-in to > 48 KB dynamic shared memory
 // cooperative whole-step kernel (ox_coop.cu)
 bool step_coop_eligible(const ox_model_tables& t);
@@ -146,8 +147,8 @@ template <> DevBatch<double>& dev<double>(ox_batch* b) { return b->bd; }
 template <typename T>
 cudaError_t launch_solve_coop(ox_batch* b) {
   b->launches++;
-  if (sizeof(T) == 8) return launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->model->t.nefcmax);
-  return launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->model->t.nefcmax);
+  if (sizeof(T) == 8) return launch_solve_coop_f64(b->stream, b->d_blob, b->blob_bytes, b->bd, b->coop_resident, b->d_coop_ctr);
+  return launch_solve_coop_f32(b->stream, b->d_blob, b->blob_bytes, b->bf, b->coop_resident, b->d_coop_ctr);
 }
 
 // launch one phase (0 = whole step, 1 = PRE, 2 = POST) of the batch's model-specialised kernel: a compiled-in launcher, or a
@@ -525,7 +526,12 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER || t.sensor_type[i] == OX_SENS_TOUCH || t.sensor_type[i] == OX_SENS_FORCE || t.sensor_type[i] == OX_SENS_TORQUE;
     b->split = b->spec && b->spec->has_phase(b->f64, 1) && b->spec->has_phase(b->f64, 2) && cfg->coop_solver != 0 && coop_ok && t.integrator == OX_INT_EULER && !acc_sensor;
   }
-  if (b->coop || b->split) CU_TRY(ox::solve_coop_prepare(b->blob_bytes, b->f64));
+  if (b->coop || b->split) {
+    CU_TRY(ox::solve_coop_prepare(b->blob_bytes, b->f64));
+    b->coop_resident = ox::solve_coop_resident_ctas(b->blob_bytes, b->f64);   // persistent grid of the ticket-drawing solver
+    CU_TRY(cudaMalloc(&b->d_coop_ctr, 2 * sizeof(int)));
+    CU_TRY(cudaMemset(b->d_coop_ctr, 0, 2 * sizeof(int)));
+  }
   CU_TRY(cudaMalloc(&b->d_step, sizeof(long long)));
   CU_TRY(cudaMemset(b->d_step, 0, sizeof(long long)));
   CU_TRY(cudaMalloc(&b->d_mask, b->stride));
@@ -554,7 +560,7 @@ void ox_batch_free(ox_batch* b) {
   cudaSetDevice(b->cfg.device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   drop_graph(b);
-  cudaFree(b->arena); cudaFree(b->d_blob); cudaFree(b->d_step); cudaFree(b->d_tmp); cudaFree(b->d_mask);
+  cudaFree(b->arena); cudaFree(b->d_blob); cudaFree(b->d_step); cudaFree(b->d_tmp); cudaFree(b->d_mask); cudaFree(b->d_coop_ctr);
   if (b->h_tmp) cudaFreeHost(b->h_tmp);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;

@@ -50,6 +50,8 @@ struct ox_batch {
   void* io_qpos = nullptr;
   void* io_qvel = nullptr;
   int io_f64 = 0;
+  int* d_coop_ctr = nullptr;   // {next env ticket, warps done} of the persistent cooperative solver
+  int coop_resident = 0;       // CTAs the device keeps resident for it (its grid size)
 };
 
 

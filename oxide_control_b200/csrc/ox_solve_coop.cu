@@ -15,6 +15,8 @@
 //     [element][env] (lane = env layout), which this kernel can only gather from.
 // Same algorithm, stopping rules and warm start as Env::fwd_constraint (ox_stages.cuh); only the summation order differs.
 // Eligibility (checked on the host): Newton solver, nv <= 32.
+#include <cstdlib>
+
 #include "ox_kernels.cuh"
 #include "ox_stages.cuh"
 
@@ -36,13 +38,9 @@ __device__ __forceinline__ double coop_rsqrt(double x) { return rsqrt(x); }
 // per-warp shared memory: five row arrays of RCAP, J staging (SROWS x 33), the Cholesky factor (32 x 33) for the back substitution
 __host__ __device__ inline size_t coop_warp_words() { return 5 * (size_t)COOP_RCAP + COOP_SROWS * 33 + 32 * 33; }
 
+// one environment's solve by one warp (the body of the kernel below)
 template <typename T>
-__global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b) {
-  DevModel<T> m{stage_model(gblob, bytes)};
-  extern __shared__ __align__(128) unsigned char ox_smem[];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * COOP_WARPS + wib;
-  if (env >= b.nenv) return;
+__device__ __forceinline__ void coop_solve_env(const DevModel<T>& m, const DevBatch<T>& b, unsigned char* ox_smem, int bytes, int env, int wib, int lane) {
   const BlobHeader& h = m.h();
   const int nv = h.nv;
   const bool me = lane < nv;
@@ -295,6 +293,35 @@ __global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned c
 #undef ROW
 }
 
+// PERSISTENT launch: the grid holds as many CTAs as the device keeps resident; every warp draws its next environment from a
+// global ticket counter. Solve times vary several-fold between envs (0 .. 8 Newton iterations, 0 .. 90 rows), and with the
+// static env -> warp map a CTA's slot stayed occupied until its slowest warp finished (ncu: 10 of 16 resident warps active,
+// 1.7 waves of CTAs); drawing tickets keeps every resident warp busy until the batch is done and stages the model tables once
+// per CTA instead of once per 8 envs. The last warp to leave resets both counters for the next launch (stream-ordered).
+template <typename T>
+__global__ void __launch_bounds__(32 * COOP_WARPS) k_solve_coop(const unsigned char* __restrict__ gblob, int bytes, DevBatch<T> b, int* __restrict__ ctr) {
+  DevModel<T> m{stage_model(gblob, bytes)};
+  extern __shared__ __align__(128) unsigned char ox_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!ctr) {   // static map (OX_B200_COOP_STATIC=1, kept for A/B measurements): warp w of CTA c solves env 8 c + w
+    const int env = blockIdx.x * COOP_WARPS + wib;
+    if (env < b.nenv) coop_solve_env<T>(m, b, ox_smem, bytes, env, wib, lane);
+    return;
+  }
+  for (;;) {
+    int env = 0;
+    if (lane == 0) env = atomicAdd(&ctr[0], 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= b.nenv) break;
+    coop_solve_env<T>(m, b, ox_smem, bytes, env, wib, lane);
+    __syncwarp();   // the warp's shared-memory scratch is reused by its next environment
+  }
+  if (lane == 0) {
+    const int done = atomicAdd(&ctr[1], 1);
+    if (done == (int)gridDim.x * COOP_WARPS - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+  }
+}
+
 constexpr size_t COOP_SMEM_LIMIT = 200 * 1024;  // opt-in dynamic shared memory per CTA this kernel asks for (the SM has 227 KB)
 
 size_t solve_coop_smem(int blob_bytes, bool f64) {
@@ -309,17 +336,30 @@ cudaError_t solve_coop_prepare(int blob_bytes, bool f64) {
              : cudaFuncSetAttribute(k_solve_coop<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM_LIMIT);
 }
 
+// CTAs the current device keeps resident for this kernel (0 on error): the size of the persistent grid
+int solve_coop_resident_ctas(int blob_bytes, bool f64) {
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  const size_t smem = solve_coop_smem(blob_bytes, f64);
+  const cudaError_t e = f64 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_coop<double>, 32 * COOP_WARPS, smem)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_coop<float>, 32 * COOP_WARPS, smem);
+  if (e != cudaSuccess || per_sm < 1) return 0;
+  return sms * per_sm;
+}
+
 template <typename T>
-static cudaError_t launch_coop(cudaStream_t stream, const unsigned char* blob, int bytes, const DevBatch<T>& b, int nefcmax) {
-  (void)nefcmax;
+static cudaError_t launch_coop(cudaStream_t stream, const unsigned char* blob, int bytes, const DevBatch<T>& b, int resident_ctas, int* ctr) {
   const size_t smem = solve_coop_smem(bytes, sizeof(T) == 8);
-  const int grid = (b.nenv + COOP_WARPS - 1) / COOP_WARPS;
-  k_solve_coop<T><<<grid, 32 * COOP_WARPS, smem, stream>>>(blob, bytes, b);
+  int grid = (b.nenv + COOP_WARPS - 1) / COOP_WARPS;
+  static const bool force_static = [] { const char* e = getenv("OX_B200_COOP_STATIC"); return e && *e == '1'; }();
+  if (force_static) ctr = nullptr;
+  else if (resident_ctas > 0 && grid > resident_ctas) grid = resident_ctas;
+  k_solve_coop<T><<<grid, 32 * COOP_WARPS, smem, stream>>>(blob, bytes, b, ctr);
   return cudaPeekAtLastError();  // the caller propagates it (CU_TRY); peek so that the sticky state is not silently cleared
 }
 
-cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int nefcmax) { return launch_coop<float>(s, blob, bytes, b, nefcmax); }
-cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int nefcmax) { return launch_coop<double>(s, blob, bytes, b, nefcmax); }
+cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int resident_ctas, int* ctr) { return launch_coop<float>(s, blob, bytes, b, resident_ctas, ctr); }
+cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int resident_ctas, int* ctr) { return launch_coop<double>(s, blob, bytes, b, resident_ctas, ctr); }
 bool solve_coop_eligible(const ox_model_tables& t) {
   return t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nv >= 1 && t.nv <= 32;
 }
