@@ -32,6 +32,7 @@
 #include "../include/ox_b200.h"
 
 typedef ox_model_tables Model;
+static const double OX_PI_D = 3.14159265358979323846;
 
 struct oxo_data {
   // state (mjData fields of the same names)
@@ -728,6 +729,23 @@ void makeConstraint(const Model* m, Data* d) {
     for (int j = 0; j < m->njnt; j++) {
       if (!m->jnt_limited[j]) continue;
       int jt = m->jnt_type[j];
+      if (jt == OX_JNT_BALL) {
+        // mj_instantiateLimit, ball: the rotation vector of the joint quaternion (mju_quat2Vel, dt = 1) gives angle and axis;
+        // dist = max(range) - angle, one row with J = -axis on the joint's dofs
+        double q[4], axis[3];
+        std::memcpy(q, &d->qpos[m->jnt_qposadr[j]], sizeof q);
+        normalize4(q);
+        double sn = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), ang = 2 * std::atan2(sn, q[0]);
+        if (ang > OX_PI_D) ang -= 2 * OX_PI_D;
+        for (int k = 0; k < 3; k++) axis[k] = sn > OX_MINVAL ? (ang < 0 ? -1.0 : 1.0) * q[1 + k] / sn : 0.0;
+        double dist = std::max(m->jnt_range[2 * j], m->jnt_range[2 * j + 1]) - std::fabs(ang), margin = m->jnt_margin[j];
+        if (dist < margin) {
+          std::fill(jrow.begin(), jrow.end(), 0.0);
+          for (int k = 0; k < 3; k++) jrow[m->jnt_dofadr[j] + k] = -axis[k];
+          addRow(m, d, jrow.data(), dist, margin, m->dof_invweight0[m->jnt_dofadr[j]], m->jnt_solref + 2 * j, m->jnt_solimp + 5 * j, 0, j);
+        }
+        continue;
+      }
       if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
       double value = d->qpos[m->jnt_qposadr[j]], margin = m->jnt_margin[j];
       for (int side = -1; side <= 1; side += 2) {

@@ -405,7 +405,6 @@ void parse_joint(Builder& B, const XmlElem& e, int body, const std::string& chil
     clamp_solimp(j.solimp);
     if (a.num("frictionloss", 0) != 0) cfail("joint '" + j.name + "': frictionloss is outside the supported subset");
     if (a.has("actuatorfrcrange")) cfail("joint '" + j.name + "': actuatorfrcrange is outside the supported subset");
-    if (j.type == OX_JNT_BALL && j.limited) cfail("joint '" + j.name + "': ball joint limits are outside the supported subset");
     if (j.type == OX_JNT_FREE || j.type == OX_JNT_BALL) { j.axis[0] = j.axis[1] = 0; j.axis[2] = 1; }
     else if (hm::normalize3(j.axis) < 1e-15) cfail("joint '" + j.name + "': zero axis");
   }

@@ -1284,6 +1284,7 @@ struct Env {
         for (int j = 0; j < njnt; j++) {
           if (!m.jnt_limited(j)) continue;
           const int jt = m.jnt_type(j);
+          if (jt == OX_JNT_BALL) { any_limit |= limit_count(j) > 0; continue; }
           if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) continue;
           const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
           any_limit |= (value - m.jnt_range(2 * j) < margin) | (m.jnt_range(2 * j + 1) - value < margin);
@@ -1398,9 +1399,27 @@ struct Env {
     }
   }
   // number of limit rows joint j contributes (0, 1 or 2) and the rows themselves
+  // ball joint: rotation angle and unit axis of the joint quaternion (mju_quat2Vel with dt = 1, then normalised); the limit is on
+  // the angle, range = (0, max angle)
+  OX_HD T ball_angle_axis(int j, T* axis) const {
+    T q[4];
+    ld<4>(q, b.qpos, m.jnt_qposadr(j));
+    normalize4(q);
+    const T sn = ox_sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    T ang = 2 * ox_atan2(sn, q[0]);
+    if (ang > (T)3.14159265358979323846) ang -= (T)(2 * 3.14159265358979323846);
+    const T inv = sn > (T)OX_MINVAL ? 1 / sn : (T)0;
+    const T sg = ang < 0 ? (T)-1 : (T)1;
+    axis[0] = sg * q[1] * inv; axis[1] = sg * q[2] * inv; axis[2] = sg * q[3] * inv;
+    return ox_abs(ang);
+  }
   OX_HD int limit_count(int j) const {
     if (!m.jnt_limited(j)) return 0;
     const int jt = m.jnt_type(j);
+    if (jt == OX_JNT_BALL) {
+      T axis[3];
+      return ox_max(m.jnt_range(2 * j), m.jnt_range(2 * j + 1)) - ball_angle_axis(j, axis) < m.jnt_margin(j) ? 1 : 0;
+    }
     if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) return 0;
     const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);
     return (value - m.jnt_range(2 * j) < margin ? 1 : 0) + (m.jnt_range(2 * j + 1) - value < margin ? 1 : 0);
@@ -1411,6 +1430,23 @@ struct Env {
       {
           if (!m.jnt_limited(j)) return;
           const int jt = m.jnt_type(j);
+          if (jt == OX_JNT_BALL) {   // one row: J = -axis on the joint's three dofs, pos = max angle - angle
+            T axis[3];
+            const T margin = m.jnt_margin(j), dist = ox_max(m.jnt_range(2 * j), m.jnt_range(2 * j + 1)) - ball_angle_axis(j, axis);
+            if (!(dist < margin)) return;
+            const int da = m.jnt_dofadr(j), r = nefc++;
+            OX_MLOOP
+            for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
+            T vel = 0;
+            OX_MLOOP
+            for (int k = 0; k < 3; k++) { at(b.efc_J, r * nv + da + k) = -axis[k]; vel -= axis[k] * at(b.qvel, da + k); }
+            T aref, sr[2], si[5];
+            OX_LDM(2, sr, jnt_solref, 2 * j);
+            OX_LDM(5, si, jnt_solimp, 5 * j);
+            const T R = row_params(sr, si, dist, margin, m.dof_invweight0(da), vel, &aref);
+            at(b.efc_pos, r) = dist; at(b.efc_margin, r) = margin; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref;
+            return;
+          }
           if (jt != OX_JNT_SLIDE && jt != OX_JNT_HINGE) return;
           const int da = m.jnt_dofadr(j);
           const T value = at(b.qpos, m.jnt_qposadr(j)), margin = m.jnt_margin(j);

@@ -593,6 +593,18 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     ne = len(J)
     if not dm.dis("limit"):
         for j in range(dm.njnt):
+            if dm.jnt_limited[j] and int(dm.jnt_type[j]) == BALL:            # limit on the rotation angle: J = -(unit rotation axis)
+                qa, da = int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j])
+                rv = sub_quat(qpos[qa:qa + 4] / np.linalg.norm(qpos[qa:qa + 4]), np.array([1.0, 0, 0, 0]))   # log of the joint rotation
+                ang = np.linalg.norm(rv)
+                dist = max(dm.jnt_range[2 * j], dm.jnt_range[2 * j + 1]) - ang
+                if dist < dm.jnt_margin[j]:
+                    row = np.zeros(dm.nv)
+                    row[da:da + 3] = -rv / ang if ang > MINVAL else 0.0
+                    a, R = row_params(dm, dm.jnt_solref[2 * j:2 * j + 2], dm.jnt_solimp[5 * j:5 * j + 5], dist, dm.jnt_margin[j],
+                                      dm.dof_invweight0[da], row @ qvel)
+                    J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
+                continue
             if not dm.jnt_limited[j] or int(dm.jnt_type[j]) not in (SLIDE, HINGE):
                 continue
             q, da = qpos[int(dm.jnt_qposadr[j])], int(dm.jnt_dofadr[j])

@@ -173,3 +173,30 @@ def test_act_accessors_mirror_the_reference():
     assert abs(p.act(hip_int) - (0.25 + 0.005)) < 1e-15                            # integrator: act += h ctrl
     p.reset()
     assert p.act(hip_int) == 0.0
+
+
+def test_ball_joint_limit_closed_form():
+    """A ball joint rotated by `ang` about a unit axis u, limit at 0.5 rad: one row, pos = 0.5 - ang, J = -u on the joint's dofs
+    (mj_instantiateLimit); inside the limit there is no row."""
+    xml = """<mujoco><compiler angle="radian"/><option gravity="0 0 0"/><worldbody><body pos="0 0 1">
+    <joint name="b" type="ball" range="0 0.5" margin="0.01"/><geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.03" contype="0" conaffinity="0"/>
+    </body></worldbody></mujoco>"""
+    m = ox.Model.from_xml_string(xml)
+    assert m.jnt_limited[0] == 1 and m.nefcmax >= 1
+    u = np.array([1.0, 2.0, -2.0]) / 3.0
+    for ang, rows in ((0.3, 0), (0.495, 1), (0.62, 1)):
+        od = OracleData(m)
+        od.field("qpos")[:] = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * u])
+        od.field("qvel")[:] = [0.1, -0.2, 0.3]
+        od.forward()
+        assert od.int("nefc") == rows, ang
+        if rows:
+            assert abs(od.field("efc_pos")[0] - (0.5 - ang)) < 1e-12 and np.allclose(od.field("efc_J")[:3], -u, atol=1e-12)
+            assert od.field("efc_force")[0] > 0 if ang > 0.5 else True
+    # the limit pushes back: released beyond the limit, the angle returns inside
+    od = OracleData(m)
+    od.field("qpos")[:] = np.concatenate([[np.cos(0.35)], np.sin(0.35) * u])      # 0.7 rad
+    for _ in range(400):
+        od.step()
+    q = od.field("qpos")
+    assert 2 * np.arctan2(np.linalg.norm(q[1:]), q[0]) < 0.52

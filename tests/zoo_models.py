@@ -16,7 +16,7 @@ ZOO_A = """
       <site name="top" pos="0 0 0.2" euler="0 0.3 0"/>
       <site name="box_sole" type="box" pos="0 0 -0.2" size="0.16 0.11 0.03"/>
       <body name="arm" pos="0.15 0 0.1">
-        <joint name="shoulder" type="ball" pos="0 0 0" stiffness="3" damping="0.4"/>
+        <joint name="shoulder" type="ball" pos="0 0 0" stiffness="3" damping="0.4" range="0 0.6" margin="0.02"/>
         <geom name="arm" type="capsule" fromto="0 0 0 0.3 0 0" size="0.04"/>
         <body name="hand" pos="0.3 0 0">
           <joint name="wrist" type="hinge" axis="0 1 0" range="-1 1" damping="0.05" armature="0.01" stiffness="1" springref="0.2"/>
