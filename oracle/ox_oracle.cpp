@@ -621,6 +621,15 @@ void addJacP(const Model* m, const Data* d, int body, const double* point, doubl
   }
 }
 
+// rotational Jacobian of `body` (mj_jac, jacr rows): the angular part of cdof along the body's dof chain
+void addJacR(const Model* m, const Data* d, int body, double sign, double* jacr /*3 x nv*/) {
+  int nv = m->nv;
+  while (body && m->body_dofnum[body] == 0) body = m->body_parentid[body];
+  if (!body) return;
+  for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i])
+    for (int k = 0; k < 3; k++) jacr[k * nv + i] += sign * d->cdof[6 * i + k];
+}
+
 void getImpedance(const double* solimp, double pos, double margin, double* imp) {
   double dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (dmin == dmax || width <= OX_MINVAL) { *imp = 0.5 * (dmin + dmax); return; }
@@ -785,7 +794,16 @@ void makeConstraint(const Model* m, Data* d) {
     for (int r = 0; r < 3; r++)
       for (int i = 0; i < nv; i++)
         jac[r * nv + i] = frame[3 * r] * jacp[i] + frame[3 * r + 1] * jacp[nv + i] + frame[3 * r + 2] * jacp[2 * nv + i];
-    double tran = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
+    double tran = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2], rot = m->body_invweight0[2 * b1 + 1] + m->body_invweight0[2 * b2 + 1];
+    if (m->pair_dim[p] > 3) {   // condim 4 / 6: rows 3..5 = relative angular velocity about the normal (torsion) and the tangents (rolling)
+      jac.resize(6 * nv);
+      std::vector<double> jacr(3 * nv, 0.0);
+      addJacR(m, d, b2, +1, jacr.data());
+      addJacR(m, d, b1, -1, jacr.data());
+      for (int r = 0; r < 3; r++)
+        for (int i = 0; i < nv; i++)
+          jac[(3 + r) * nv + i] = frame[3 * r] * jacr[i] + frame[3 * r + 1] * jacr[nv + i] + frame[3 * r + 2] * jacr[2 * nv + i];
+    }
     const double* fri = m->pair_friction + 5 * p;
     int dim = m->pair_dim[p];
     if (dim == 1) {
@@ -796,7 +814,7 @@ void makeConstraint(const Model* m, Data* d) {
         for (int s = 0; s < 2; s++) {
           double sg = s ? -1.0 : 1.0;
           for (int i = 0; i < nv; i++) jrow[i] = jac[i] + sg * fri[k - 1] * jac[k * nv + i];
-          addRow(m, d, jrow.data(), d->con_dist[c], includemargin, tran + fri[k - 1] * fri[k - 1] * tran, m->pair_solref + 2 * p,
+          addRow(m, d, jrow.data(), d->con_dist[c], includemargin, tran + fri[k - 1] * fri[k - 1] * (k < 3 ? tran : rot), m->pair_solref + 2 * p,
                  m->pair_solimp + 5 * p, 2, c);
         }
       // pyramidal regularisation: every edge gets R = 2 mu^2 R(first edge), mu = friction[0]/sqrt(impratio)
@@ -1429,7 +1447,7 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
     if (first < 0) continue;
     const int p = d->con_pair[c];
     const double* fri = m->pair_friction + 5 * p;
-    double lf[3] = {0, 0, 0};
+    double lf[6] = {0, 0, 0, 0, 0, 0};   // contact-frame force (normal, tangents) and torque (torsion, rolling)
     if (n == 1) lf[0] = d->efc_force[first];
     else
       for (int k = 0; k < n / 2; k++) {
@@ -1437,10 +1455,13 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
         lf[1 + k] = (d->efc_force[first + 2 * k] - d->efc_force[first + 2 * k + 1]) * fri[k];
       }
     const double* fr = &d->con_frame[9 * c];
-    double wf[3];
-    for (int k = 0; k < 3; k++) wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
-    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom1[p]], &d->con_pos[3 * c], wf, nullptr, -1.0);
-    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom2[p]], &d->con_pos[3 * c], wf, nullptr, +1.0);
+    double wf[3], wt[3];
+    for (int k = 0; k < 3; k++) {
+      wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
+      wt[k] = fr[k] * lf[3] + fr[3 + k] * lf[4] + fr[6 + k] * lf[5];
+    }
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom1[p]], &d->con_pos[3 * c], wf, n > 4 ? wt : nullptr, -1.0);
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom2[p]], &d->con_pos[3 * c], wf, n > 4 ? wt : nullptr, +1.0);
   }
   // connect equalities: the three row forces are a world-frame force on body1 at its anchor and the opposite on body2 at its own
   for (int r = 0; r + 2 < d->ne; r++) {

@@ -991,7 +991,7 @@ ox_model* compile_mjcf(const std::string& xml) {
               for (int k = 0; k < 5; k++) solimp[k] = mix * P.solimp[k] + (1 - mix) * Q.solimp[k];
               for (int k = 0; k < 3; k++) fri[k] = std::max(P.friction[k], Q.friction[k]);
             }
-            if (dim != 1 && dim != 3) cfail("contact dimension " + std::to_string(dim) + " (torsional/rolling friction) is outside the supported subset (condim 1 or 3)");
+            if (dim != 1 && dim != 3 && dim != 4 && dim != 6) cfail("contact dimension " + std::to_string(dim) + " is not a valid condim (1, 3, 4 or 6)");
             M->v_pair_geom1.push_back(ga); M->v_pair_geom2.push_back(gb);
             M->v_pair_dim.push_back(dim); M->v_pair_maxcon.push_back(maxcon); M->v_pair_conadr.push_back(nconmax);
             double f5[5] = {fri[0], fri[0], fri[1], fri[2], fri[2]};

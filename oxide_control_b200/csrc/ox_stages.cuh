@@ -1177,7 +1177,10 @@ struct Env {
     return ox_max((T)OX_MINVAL, (1 - imp) * diagApprox / imp);
   }
 
-  // rows of one contact (pyramidal cone or frictionless): Jacobian, impedance, reference acceleration
+  // rows of one contact (pyramidal cone or frictionless): Jacobian, impedance, reference acceleration. condim 3: normal + two
+  // tangents; condim 4 adds torsion about the normal, condim 6 rolling about the two tangents - those friction directions act
+  // on the RELATIVE ANGULAR velocity of the two bodies (rotational Jacobian), every direction k contributes the edge pair
+  // J_n +/- mu_k J_k.
   OX_HD void contact_rows(int c, int p, int& nefc) const {
     const auto& h = m.h();
     const int nv = h.nv;
@@ -1196,13 +1199,13 @@ struct Env {
       ld<3>(cpos, b.con_pos, 3 * c);
       ld<9>(frame, b.con_frame, 9 * c);
 #pragma unroll
-      for (int rr = 0; rr < 4; rr++) {
+      for (int rr = 0; rr < 10; rr++) {
         if (rr >= nrow) break;
         const int r = r0 + rr;
         OX_MLOOP
         for (int i = 0; i < nv; i++) at(b.efc_J, r * nv + i) = 0;
       }
-      T veln = 0, velt[2] = {0, 0};
+      T veln = 0, velt[5] = {0, 0, 0, 0, 0};
       const int bodies[2] = {m.geom_bodyid(m.pair_geom2(p)), m.geom_bodyid(m.pair_geom1(p))};
       OX_MLOOP
       for (int sidx = 0; sidx < 2; sidx++) {
@@ -1227,9 +1230,10 @@ struct Env {
             at(b.efc_J, r0 * nv + i) += jn;
           } else {
 #pragma unroll
-            for (int k = 1; k < 3; k++) {  // condim <= 3: static bound so that fri / velt stay in registers
+            for (int k = 1; k < 6; k++) {  // static bound so that fri / velt stay in registers; k >= 3: torsion / rolling (angular part of cdof)
               if (k >= dim) break;
-              const T jt = dot3(frame + 3 * k, jp) * fri[k - 1];
+              const T jr[3] = {sign * cd[0], sign * cd[1], sign * cd[2]};
+              const T jt = (k < 3 ? dot3(frame + 3 * k, jp) : dot3(frame + 3 * (k - 3), jr)) * fri[k - 1];
               velt[k - 1] += jt * qv;
               at(b.efc_J, (r0 + 2 * (k - 1)) * nv + i) += jn + jt;
               at(b.efc_J, (r0 + 2 * (k - 1) + 1) * nv + i) += jn - jt;
@@ -1246,20 +1250,21 @@ struct Env {
         const T R = row_params(solref, solimp, dist, includemargin, tran, veln, &aref);
         at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / R; at(b.efc_aref, r0) = aref;
       } else {
-        T arefs[4], Rfirst = 0;
+        T arefs[10], Rfirst = 0;
+        const T rot = dim > 3 ? m.body_invweight0(2 * bodies[1] + 1) + m.body_invweight0(2 * bodies[0] + 1) : (T)0;
 #pragma unroll
-        for (int k = 1; k < 3; k++)
+        for (int k = 1; k < 6; k++)
 #pragma unroll
           for (int s = 0; s < 2; s++) {
             if (k >= dim) continue;
             const T vel = veln + (s ? -velt[k - 1] : velt[k - 1]);
-            const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * tran, vel, &arefs[2 * (k - 1) + s]);
+            const T R = row_params(solref, solimp, dist, includemargin, tran + fri[k - 1] * fri[k - 1] * (k < 3 ? tran : rot), vel, &arefs[2 * (k - 1) + s]);
             if (k == 1 && s == 0) Rfirst = R;
           }
         const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
         const T D = 1 / (2 * mu * mu * Rfirst);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 10; r++) {
           if (r >= nrow) break;
           at(b.efc_pos, r0 + r) = dist; at(b.efc_margin, r0 + r) = includemargin; at(b.efc_D, r0 + r) = D;
           at(b.efc_aref, r0 + r) = arefs[r];
@@ -2072,24 +2077,27 @@ struct Env {
       const int ea = ati(b.con_efcadr, c);
       if (ea < 0) return;
       const int dim = m.pair_dim(p);
-      T lf[3] = {0, 0, 0};
+      T lf[6] = {0, 0, 0, 0, 0, 0};   // contact-frame force (normal, tangents) and torque (torsion, rolling)
       if (dim == 1) lf[0] = at(b.efc_force, ea);
       else {
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < 5; k++) {
           if (k >= dim - 1) break;
           const T fp = at(b.efc_force, ea + 2 * k), fm = at(b.efc_force, ea + 2 * k + 1);
           lf[0] += fp + fm;
           lf[1 + k] = (fp - fm) * m.pair_friction(5 * p + k);
         }
       }
-      T fr[9], cp[3], wf[3];
+      T fr[9], cp[3], wf[3], wt[3];
       ld<9>(fr, b.con_frame, 9 * c);
       ld<3>(cp, b.con_pos, 3 * c);
       OX_MLOOP
-      for (int k = 0; k < 3; k++) wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
-      sub_ext_force(m.geom_bodyid(m.pair_geom1(p)), cp, wf, nullptr, (T)-1);
-      sub_ext_force(m.geom_bodyid(m.pair_geom2(p)), cp, wf, nullptr, (T)1);
+      for (int k = 0; k < 3; k++) {
+        wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
+        wt[k] = fr[k] * lf[3] + fr[3 + k] * lf[4] + fr[6 + k] * lf[5];
+      }
+      sub_ext_force(m.geom_bodyid(m.pair_geom1(p)), cp, wf, dim > 3 ? wt : nullptr, (T)-1);
+      sub_ext_force(m.geom_bodyid(m.pair_geom2(p)), cp, wf, dim > 3 ? wt : nullptr, (T)1);
     };
     if (STATIC_CON || slots) {
       OX_MLOOP
@@ -2252,7 +2260,10 @@ struct Env {
             if (ea < 0) return;
             const int dim = m.pair_dim(p);
             T fn = at(b.efc_force, ea);                                   // frictionless: the row force; pyramid: sum over the edges
-            if (dim > 1) { fn += at(b.efc_force, ea + 1); fn += at(b.efc_force, ea + 2); fn += at(b.efc_force, ea + 3); }
+            if (dim > 1) {
+#pragma unroll
+              for (int r = 1; r < 10; r++) { if (r >= 2 * (dim - 1)) break; fn += at(b.efc_force, ea + r); }
+            }
             if (!(fn > 0)) return;
             T ray[3], cp[3];
             ld<3>(ray, b.con_frame, 9 * c);

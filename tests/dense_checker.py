@@ -639,16 +639,27 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
             a, R = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, Jd[0] @ qvel)
             J.append(Jd[0]); D.append(1 / R); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], c["frame"][0]))
         else:
-            assert prm["dim"] == 3, "condim 4/6 are outside the product's scope"
-            rows = [Jd[0] + s * prm["friction"][k] * Jd[1 + k] for k in range(2) for s in (1.0, -1.0)]
-            dirs = [c["frame"][0] + s * prm["friction"][k] * c["frame"][1 + k] for k in range(2) for s in (1.0, -1.0)]
+            dim = prm["dim"]
+            assert dim in (3, 4, 6)
+            # friction directions 1, 2: tangents (relative linear velocity of the contact point); 3: torsion about the normal,
+            # 4, 5: rolling about the tangents (relative ANGULAR velocity of the two bodies)
+            Jw = c["frame"] @ (kin.JW[b2] - kin.JW[b1])
+            Jk = [Jd[1], Jd[2], Jw[0], Jw[1], Jw[2]][:dim - 1]
+            zero = np.zeros(3)
+            rows, dirs = [], []
+            for k in range(dim - 1):
+                for s in (1.0, -1.0):
+                    rows.append(Jd[0] + s * prm["friction"][k] * Jk[k])
+                    lin = c["frame"][0] + (s * prm["friction"][k] * c["frame"][1 + k] if k < 2 else zero)
+                    tor = s * prm["friction"][k] * c["frame"][k - 2] if k >= 2 else zero
+                    dirs.append((lin, tor))
             _, R0 = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran + prm["friction"][0] ** 2 * tran, rows[0] @ qvel)
             mu = prm["friction"][0] * np.sqrt(1 / dm.impratio)
             Rpy = 2 * mu * mu * R0
-            dm._friction_pairs += [(len(J) + 2 * k, len(J) + 2 * k + 1) for k in range(2)]
-            for r, dr in zip(rows, dirs):
+            dm._friction_pairs += [(len(J) + 2 * k, len(J) + 2 * k + 1) for k in range(dim - 1)]
+            for r, (lin, tor) in zip(rows, dirs):
                 a, _ = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, r @ qvel)
-                J.append(r); D.append(1 / Rpy); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], dr))
+                J.append(r); D.append(1 / Rpy); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], lin, tor))
     if not J:
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
     return np.array(J), np.array(D), np.array(aref), ne
@@ -774,11 +785,12 @@ def force_torque_sensors(dm, kin, qacc, force, xfrc_applied):
         for r, info in enumerate(dm._row_cart):
             if info is None or force[r] == 0:
                 continue
-            bp, pp, bm, pm, dirv = info
+            bp, pp, bm, pm, dirv = info[:5]
+            tor = info[5] if len(info) > 5 else np.zeros(3)                # torsional / rolling friction: a pure torque pair
             if bp in sub:
-                F -= force[r] * dirv; Tq -= np.cross(pp - P, force[r] * dirv)
+                F -= force[r] * dirv; Tq -= np.cross(pp - P, force[r] * dirv) + force[r] * tor
             if bm in sub:
-                F += force[r] * dirv; Tq += np.cross(pm - P, force[r] * dirv)
+                F += force[r] * dirv; Tq += np.cross(pm - P, force[r] * dirv) + force[r] * tor
         out[int(dm.sensor_adr[s])] = Rs.T @ (F if ty == 4 else Tq)
     return out
 

@@ -334,5 +334,40 @@ ZOO_I = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I}
+# N3: condim 4 (torsional friction) and condim 6 (torsional + rolling): spinning / rolling bodies on the floor and on each other,
+# with touch / force / torque sensors reading the contact wrench (the torsional and rolling rows are pure torques)
+ZOO_J = """
+<mujoco model="zoo_j">
+  <compiler angle="radian"/>
+  <option timestep="0.003" tolerance="1e-13" impratio="3"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1" condim="3" friction="1 0.05 0.01"/>
+    <body name="top" pos="0 0 0.11">
+      <freejoint name="toproot"/>
+      <geom name="top" type="sphere" size="0.1" condim="4" friction="0.8 0.03 0.0001"/>
+      <site name="topsite" pos="0 0 -0.05"/>
+    </body>
+    <body name="wheel" pos="0.5 0 0.09">
+      <freejoint name="wheelroot"/>
+      <geom name="wheel" type="sphere" size="0.08" condim="6" friction="0.7 0.02 0.004"/>
+      <site name="wheelskin" type="sphere" size="0.1"/>
+    </body>
+    <body name="log" pos="-0.5 0 0.07" euler="1.5707963 0 0.4">
+      <freejoint name="logroot"/>
+      <geom name="log" type="capsule" size="0.06 0.2" condim="6" friction="0.6 0.01 0.002" priority="1"/>
+      <site name="logsite" pos="0 0 0.1"/>
+    </body>
+    <body name="rider" pos="-0.5 0 0.21">
+      <freejoint name="riderroot"/>
+      <geom name="rider" type="sphere" size="0.07" condim="4" friction="0.9 0.04 0.0001"/>
+    </body>
+  </worldbody>
+  <sensor>
+    <touch site="wheelskin"/><force site="topsite"/><torque site="topsite"/><torque site="logsite"/>
+    <frameangvel objtype="body" objname="top"/><frameangvel objtype="body" objname="wheel"/>
+  </sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J}
 NOCONTACT = {"zoo_d": ZOO_D}
