@@ -73,7 +73,7 @@ enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
 enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 << 4,
        OX_DSBL_PASSIVE = 1 << 5, OX_DSBL_GRAVITY = 1 << 6, OX_DSBL_CLAMPCTRL = 1 << 7,
        OX_DSBL_WARMSTART = 1 << 8, OX_DSBL_FILTERPARENT = 1 << 9, OX_DSBL_ACTUATION = 1 << 10,
-       OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13, OX_DSBL_EQUALITY = 1 << 1 };
+       OX_DSBL_REFSAFE = 1 << 11, OX_DSBL_EULERDAMP = 1 << 13, OX_DSBL_EQUALITY = 1 << 1, OX_DSBL_FRICTIONLOSS = 1 << 2 };
 /* mjtSensor subset */
 enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3, OX_SENS_FORCE = 4, OX_SENS_TORQUE = 5,
        OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_TENDONPOS = 11, OX_SENS_TENDONVEL = 12, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
@@ -115,6 +115,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(jnt_pos, njnt, 3) X(jnt_axis, njnt, 3) X(jnt_stiffness, njnt, 1) X(jnt_range, njnt, 2)         \
   X(jnt_margin, njnt, 1) X(jnt_solref, njnt, 2) X(jnt_solimp, njnt, 5)                             \
   X(dof_armature, nv, 1) X(dof_damping, nv, 1) X(dof_invweight0, nv, 1)                            \
+  X(dof_frictionloss, nv, 1) X(dof_solref_fri, nv, 2) X(dof_solimp_fri, nv, 5)                     \
   X(geom_size, ngeom, 3) X(geom_pos, ngeom, 3) X(geom_quat, ngeom, 4) X(geom_friction, ngeom, 3)   \
   X(geom_solmix, ngeom, 1) X(geom_solref, ngeom, 2) X(geom_solimp, ngeom, 5)                       \
   X(geom_margin, ngeom, 1) X(geom_gap, ngeom, 1)                                                    \
@@ -141,7 +142,8 @@ typedef struct ox_model_tables {
   int32_t ntendon, nwrap; /* fixed tendons (linear combinations of scalar joint coordinates) and their joint entries */
   /* mjOption subset */
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
-  int32_t noslip_iterations, padopt_;   /* noslip post-pass of the friction dimensions (0 = off, MuJoCo's default) */
+  int32_t noslip_iterations;   /* noslip post-pass of the friction dimensions (0 = off, MuJoCo's default) */
+  int32_t nfloss;              /* dofs with frictionloss > 0: one Huber-cost row each, after the equality rows */
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, noslip_tolerance;
   /* mjStatistic subset */
   double meaninertia;

@@ -48,8 +48,8 @@ struct oxo_data {
   std::vector<double> con_dist, con_pos, con_frame;
   std::vector<int> con_pair;
   // constraints
-  int nefc = 0, ne = 0;  // ne = number of equality rows (they come first and are two-sided)
-  std::vector<double> efc_J, efc_pos, efc_margin, efc_D, efc_R, efc_aref, efc_vel, efc_force, efc_diagApprox;
+  int nefc = 0, ne = 0, nf = 0;  // ne equality rows (first, two-sided quadratic), then nf dry-friction rows (Huber cost, |force| <= frictionloss)
+  std::vector<double> efc_J, efc_pos, efc_margin, efc_D, efc_R, efc_aref, efc_vel, efc_force, efc_diagApprox, efc_floss;
   std::vector<int> efc_type, efc_id;
   // solution
   std::vector<double> qacc, qfrc_constraint;
@@ -652,6 +652,7 @@ void addRow(const Model* m, Data* d, const double* jrow, double pos, double marg
   d->efc_margin[r] = margin;
   d->efc_type[r] = type;
   d->efc_id[r] = id;
+  d->efc_floss[r] = 0;
   d->efc_diagApprox[r] = diagApprox;
   double imp;
   getImpedance(solimp, pos, margin, &imp);
@@ -693,6 +694,7 @@ void makeConstraint(const Model* m, Data* d) {
   tendonLength(m, d);   // position-stage quantity (mj_tendon); idempotent, so passive() may have computed it already
   d->nefc = 0;
   d->ne = 0;
+  d->nf = 0;
   if (disabled(m, OX_DSBL_CONSTRAINT)) return;
   std::vector<double> jrow(nv), jacp(3 * nv), jac(3 * nv);
   // equality constraints first (mj_instantiateEquality): residual as pos, margin 0, always active in the solver
@@ -733,6 +735,16 @@ void makeConstraint(const Model* m, Data* d) {
       }
     }
   d->ne = d->nefc;
+  // dry joint friction (mj_instantiateFriction): one row per dof with frictionloss > 0, J = e_dof, pos = margin = 0
+  if (!disabled(m, OX_DSBL_FRICTIONLOSS))
+    for (int i = 0; i < nv; i++) {
+      if (!(m->dof_frictionloss[i] > 0)) continue;
+      std::fill(jrow.begin(), jrow.end(), 0.0);
+      jrow[i] = 1;
+      addRow(m, d, jrow.data(), 0.0, 0.0, m->dof_invweight0[i], m->dof_solref_fri + 2 * i, m->dof_solimp_fri + 5 * i, 5, i);
+      d->efc_floss[d->nefc - 1] = m->dof_frictionloss[i];
+    }
+  d->nf = d->nefc - d->ne;
   // joint limits
   if (!disabled(m, OX_DSBL_LIMIT))
     for (int j = 0; j < m->njnt; j++) {
@@ -994,7 +1006,13 @@ struct Solver {
   void updateConstraint() {
     double c = 0;
     for (int r = 0; r < nefc; r++) {
-      if (Jaref[r] < 0 || r < d->ne) {   // equality rows are quadratic on both sides
+      const double fl = d->efc_floss[r];
+      if (fl > 0 && std::fabs(Jaref[r]) >= fl / d->efc_D[r]) {   // dry friction, linear zone: |force| pinned at frictionloss
+        const double rf = fl / d->efc_D[r], sgn = Jaref[r] > 0 ? 1.0 : -1.0;
+        active[r] = 0;
+        d->efc_force[r] = -sgn * fl;
+        c += fl * (sgn * Jaref[r] - 0.5 * rf);
+      } else if (Jaref[r] < 0 || r < d->ne || fl > 0) {   // equality rows and the quadratic zone of friction rows: two-sided
         active[r] = 1;
         d->efc_force[r] = -d->efc_D[r] * Jaref[r];
         c += 0.5 * d->efc_D[r] * Jaref[r] * Jaref[r];
@@ -1067,7 +1085,13 @@ struct Solver {
     p.s0 = std::fabs(2 * a * quadGauss[2]) + std::fabs(quadGauss[1]);
     for (int r = 0; r < nefc; r++) {
       double x = Jaref[r] + a * Jv[r];
-      if (x < 0 || r < d->ne) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
+      const double fl = d->efc_floss[r];
+      if (fl > 0 && std::fabs(x) >= fl / d->efc_D[r]) {  // friction row in its linear zone: floss (|x| - R floss / 2)
+        const double sgn = x > 0 ? 1.0 : -1.0;
+        p.cost += fl * (sgn * x - 0.5 * fl / d->efc_D[r]);
+        p.d0 += sgn * fl * Jv[r];
+        p.s0 += std::fabs(fl * Jv[r]);
+      } else if (x < 0 || r < d->ne || fl > 0) {  // active at alpha: 1/2 D x^2 and its derivatives in alpha
         const double Dx = d->efc_D[r] * x, Dj = d->efc_D[r] * Jv[r];
         p.cost += 0.5 * Dx * x;
         p.d0 += Dx * Jv[r];
@@ -1165,7 +1189,9 @@ struct Solver {
     for (int r = 0; r < nefc; r++) {
       double v = -d->efc_aref[r];
       for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * qacc[i];
-      if (v < 0 || r < d->ne) c += 0.5 * d->efc_D[r] * v * v;
+      const double fl = d->efc_floss[r];
+      if (fl > 0 && std::fabs(v) >= fl / d->efc_D[r]) c += fl * (std::fabs(v) - 0.5 * fl / d->efc_D[r]);
+      else if (v < 0 || r < d->ne || fl > 0) c += 0.5 * d->efc_D[r] * v * v;
     }
     return c;
   }
@@ -1208,7 +1234,8 @@ struct DualSolver {
     if (!disabled(m, OX_DSBL_WARMSTART)) {
       for (int r = 0; r < nefc; r++) {
         double jar = rowDot(r, d->qacc_warmstart) - d->efc_aref[r];
-        d->efc_force[r] = (jar < 0 || r < d->ne) ? -d->efc_D[r] * jar : 0.0;
+        d->efc_force[r] = (jar < 0 || r < d->ne || d->efc_floss[r] > 0) ? -d->efc_D[r] * jar : 0.0;
+        if (d->efc_floss[r] > 0) d->efc_force[r] = clip(d->efc_force[r], -d->efc_floss[r], d->efc_floss[r]);
       }
       primalFromForces();
       double cost = 0;   // 1/2 f'(A + R) f + f'b  with  A f = J (w - qacc_smooth),  b = J qacc_smooth - aref
@@ -1231,7 +1258,8 @@ struct DualSolver {
         const double old = d->efc_force[r];
         const double res = rowDot(r, w) - d->efc_aref[r] + R * old;
         double f = old - res / ARrr;
-        if (r >= d->ne && f < 0) f = 0;             // limits and pyramidal contact edges push only; equalities pull both ways
+        if (d->efc_floss[r] > 0) f = clip(f, -d->efc_floss[r], d->efc_floss[r]);   // dry friction: a box
+        else if (r >= d->ne && f < 0) f = 0;        // limits and pyramidal contact edges push only; equalities pull both ways
         const double delta = f - old;
         if (delta != 0) {
           d->efc_force[r] = f;
@@ -1252,6 +1280,18 @@ struct DualSolver {
     primalFromForces();
     for (int iter = 0; iter < maxiter; iter++) {
       double improvement = 0;
+      for (int r = d->ne; r < d->ne + d->nf; r++) {   // dry-friction rows: the same update without the regulariser
+        minvJt(r);
+        const double Arr = rowDot(r, u);
+        if (Arr < OX_MINVAL) continue;
+        const double old = d->efc_force[r], res = rowDot(r, w) - d->efc_aref[r];
+        const double f = clip(old - res / Arr, -d->efc_floss[r], d->efc_floss[r]), delta = f - old;
+        if (delta != 0) {
+          d->efc_force[r] = f;
+          for (int i = 0; i < nv; i++) w[i] += delta * u[i];
+          improvement -= 0.5 * delta * delta * Arr + delta * res;
+        }
+      }
       for (int r = d->ne; r < nefc; r++) {
         if (d->efc_type[r] != 2) continue;
         const int c = d->efc_id[r];
@@ -1723,7 +1763,7 @@ void resetData(const Model* m, Data* d) {
   z(d->site_xpos); z(d->site_xmat); z(d->subtree_com); z(d->cinert); z(d->cdof); z(d->qM); z(d->qLD); z(d->qLDiagInv);
   z(d->cvel); z(d->cdof_dot); z(d->qfrc_bias); z(d->qfrc_passive); z(d->actuator_force); z(d->qfrc_actuator); z(d->qfrc_smooth);
   z(d->qacc_smooth); z(d->qfrc_constraint); z(d->sensordata); z(d->efc_force);
-  d->time = 0; d->ncon = 0; d->nefc = 0; d->ne = 0; d->solver_niter = 0;
+  d->time = 0; d->ncon = 0; d->nefc = 0; d->ne = 0; d->nf = 0; d->solver_niter = 0;
 }
 
 void step(const Model* m, Data* d) {
@@ -1786,7 +1826,7 @@ OXO_API oxo_data* oxo_make_data(const Model* m) {
   d->con_dist.resize(nc); d->con_pos.resize(3 * nc); d->con_frame.resize(9 * nc); d->con_pair.resize(nc);
   d->efc_J.resize((size_t)ne * std::max(1, nv)); d->efc_pos.resize(ne); d->efc_margin.resize(ne); d->efc_D.resize(ne);
   d->efc_R.resize(ne); d->efc_aref.resize(ne); d->efc_vel.resize(ne); d->efc_force.resize(ne); d->efc_diagApprox.resize(ne);
-  d->efc_type.resize(ne); d->efc_id.resize(ne);
+  d->efc_type.resize(ne); d->efc_id.resize(ne); d->efc_floss.resize(ne);
   d->qacc.resize(nv); d->qfrc_constraint.resize(nv); d->sensordata.resize(m->nsensordata);
   resetData(m, d);
   return d;
@@ -1826,7 +1866,7 @@ OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
   F(ten_length) F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
   F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
   F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
-  F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)
+  F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_floss) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)
   F(efc_diagApprox) F(qacc) F(qfrc_constraint) F(sensordata)
 #undef F
   if (s == "time") { *count = 1; return &d->time; }
@@ -1838,6 +1878,7 @@ OXO_API int32_t oxo_int(oxo_data* d, const char* name) {
   if (s == "ncon") return d->ncon;
   if (s == "nefc") return d->nefc;
   if (s == "ne") return d->ne;
+  if (s == "nf") return d->nf;
   if (s == "solver_niter") return d->solver_niter;
   if (s == "diverged") return d->diverged;
   return -1;

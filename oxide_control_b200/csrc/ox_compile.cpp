@@ -248,6 +248,7 @@ struct JointDef {
   int limited = 0;
   double damping = 0, stiffness = 0, springref = 0, armature = 0, ref = 0, margin = 0;
   double solref[2] = {0.02, 1}, solimp[5] = {0.9, 0.95, 0.001, 0.5, 2};
+  double frictionloss = 0, solref_fri[2] = {0.02, 1}, solimp_fri[5] = {0.9, 0.95, 0.001, 0.5, 2};
   int body = 0;
 };
 struct BodyDef {
@@ -403,7 +404,11 @@ void parse_joint(Builder& B, const XmlElem& e, int body, const std::string& chil
     a.vec("solreflimit", j.solref, 2, true);
     a.vec("solimplimit", j.solimp, 5, true);
     clamp_solimp(j.solimp);
-    if (a.num("frictionloss", 0) != 0) cfail("joint '" + j.name + "': frictionloss is outside the supported subset");
+    j.frictionloss = a.num("frictionloss", 0);
+    if (j.frictionloss < 0) cfail("joint '" + j.name + "': frictionloss must be >= 0");
+    a.vec("solreffriction", j.solref_fri, 2, true);
+    a.vec("solimpfriction", j.solimp_fri, 5, true);
+    clamp_solimp(j.solimp_fri);
     if (a.has("actuatorfrcrange")) cfail("joint '" + j.name + "': actuatorfrcrange is outside the supported subset");
     if (j.type == OX_JNT_FREE || j.type == OX_JNT_BALL) { j.axis[0] = j.axis[1] = 0; j.axis[2] = 1; }
     else if (hm::normalize3(j.axis) < 1e-15) cfail("joint '" + j.name + "': zero axis");
@@ -690,7 +695,7 @@ ox_model* compile_mjcf(const std::string& xml) {
         };
         dis("constraint", OX_DSBL_CONSTRAINT); dis("limit", OX_DSBL_LIMIT); dis("contact", OX_DSBL_CONTACT);
         dis("passive", OX_DSBL_PASSIVE); dis("gravity", OX_DSBL_GRAVITY); dis("clampctrl", OX_DSBL_CLAMPCTRL);
-        dis("warmstart", OX_DSBL_WARMSTART); dis("filterparent", OX_DSBL_FILTERPARENT); dis("equality", OX_DSBL_EQUALITY);
+        dis("warmstart", OX_DSBL_WARMSTART); dis("filterparent", OX_DSBL_FILTERPARENT); dis("equality", OX_DSBL_EQUALITY); dis("frictionloss", OX_DSBL_FRICTIONLOSS);
         dis("actuation", OX_DSBL_ACTUATION); dis("refsafe", OX_DSBL_REFSAFE); dis("eulerdamp", OX_DSBL_EULERDAMP);
         for (const char* k : {"energy", "fwdinv", "island", "multiccd", "override"})
           if (auto* s = f->attr(k))
@@ -810,6 +815,8 @@ ox_model* compile_mjcf(const std::string& xml) {
   M->v_qpos0.assign(nq, 0); M->v_qpos_spring.assign(nq, 0);
   M->v_dof_bodyid.resize(nv); M->v_dof_jntid.resize(nv); M->v_dof_parentid.resize(nv); M->v_dof_Madr.resize(nv); M->v_dof_depth.resize(nv);
   M->v_dof_armature.resize(nv); M->v_dof_damping.resize(nv); M->v_dof_invweight0.assign(nv, 0);
+  M->v_dof_frictionloss.assign(nv, 0); M->v_dof_solref_fri.assign(2 * nv, 0); M->v_dof_solimp_fri.assign(5 * nv, 0);
+  t.nfloss = 0;
   int nlimited = 0;
   for (int j = 0; j < njnt; j++) {
     const JointDef& jn = B.joints[j];
@@ -829,6 +836,10 @@ ox_model* compile_mjcf(const std::string& xml) {
       int d = jd[j] + k;
       M->v_dof_bodyid[d] = jn.body; M->v_dof_jntid[d] = j;
       M->v_dof_armature[d] = jn.armature; M->v_dof_damping[d] = jn.damping;
+      M->v_dof_frictionloss[d] = jn.frictionloss;   // dry friction acts on every dof of the joint
+      std::memcpy(&M->v_dof_solref_fri[2 * d], jn.solref_fri, 2 * sizeof(double));
+      std::memcpy(&M->v_dof_solimp_fri[5 * d], jn.solimp_fri, 5 * sizeof(double));
+      t.nfloss += jn.frictionloss > 0;
     }
     const BodyDef& b = B.bodies[jn.body];
     if (jn.type == OX_JNT_FREE) {
@@ -1008,7 +1019,7 @@ ox_model* compile_mjcf(const std::string& xml) {
     t.npair = (int)M->v_pair_geom1.size();
     t.nconmax = nconmax;
     bool limits_on = !(t.disableflags & (OX_DSBL_LIMIT | OX_DSBL_CONSTRAINT));
-    t.nefcmax = (limits_on ? 2 * nlimited : 0) + ncontact_rows;   // equality rows are added once they are compiled (below)
+    t.nefcmax = (limits_on ? 2 * nlimited : 0) + ncontact_rows + ((t.disableflags & OX_DSBL_CONSTRAINT) ? 0 : t.nfloss);   // equality rows are added once they are compiled (below)
   }
 
   // ---- actuators ----

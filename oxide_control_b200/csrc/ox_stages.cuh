@@ -1277,12 +1277,18 @@ struct Env {
     const int nv = h.nv, njnt = h.njnt;
     int nefc = 0;
     ati(b.ne, 0) = 0;
+    ati(b.nf, 0) = 0;
     if (!dis(OX_DSBL_CONSTRAINT)) {
       if (!dis(OX_DSBL_EQUALITY)) {   // equality rows come first (mj_makeConstraint order) and are always active in the solver
         OX_MLOOP
         for (int i = 0; i < h.neq; i++) equality_rows(i, nefc);
       }
       ati(b.ne, 0) = nefc;
+      if (h.nfloss > 0 && !dis(OX_DSBL_FRICTIONLOSS)) {   // dry joint friction: one row per dof with frictionloss > 0
+        OX_MLOOP
+        for (int i = 0; i < nv; i++) friction_row(i, nefc);
+      }
+      ati(b.nf, 0) = nefc - ati(b.ne, 0);
       bool any_limit = false;  // one test for "no joint is near a limit" (the common case), see fwd_acceleration
       if (!dis(OX_DSBL_LIMIT)) {
         OX_MLOOP
@@ -1403,6 +1409,20 @@ struct Env {
       eq_row_finish(i, r, pos, diag);
     }
   }
+  // dry friction of dof i (mj_instantiateFriction): J = e_i, pos = margin = 0, |force| <= frictionloss (efc_floss marks the row)
+  OX_HD void friction_row(int i, int& nefc) const {
+    const T fl = m.dof_frictionloss(i);
+    if (!(fl > 0)) return;
+    const int nv = m.h().nv, r = nefc++;
+    OX_MLOOP
+    for (int k = 0; k < nv; k++) at(b.efc_J, r * nv + k) = 0;
+    at(b.efc_J, r * nv + i) = 1;
+    T aref, sr[2], si[5];
+    OX_LDM(2, sr, dof_solref_fri, 2 * i);
+    OX_LDM(5, si, dof_solimp_fri, 5 * i);
+    const T R = row_params(sr, si, (T)0, (T)0, m.dof_invweight0(i), at(b.qvel, i), &aref);
+    at(b.efc_pos, r) = 0; at(b.efc_margin, r) = 0; at(b.efc_D, r) = 1 / R; at(b.efc_aref, r) = aref; at(b.efc_floss, r) = fl;
+  }
   // number of limit rows joint j contributes (0, 1 or 2) and the rows themselves
   // ball joint: rotation angle and unit axis of the joint quaternion (mju_quat2Vel with dt = 1, then normalised); the limit is on
   // the angle, range = (0, max angle)
@@ -1514,7 +1534,7 @@ struct Env {
   struct LsPt { T alpha, cost, d0, d1, s0; };  // s0 = sum of |terms| of d0: the resolution of the derivative
 
   OX_HD LsPt ls_eval(T a, int nefc, T qg0, T qg1, T qg2) const {
-    const int ne_ = ati(b.ne, 0);
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
     LsPt p;
     p.alpha = a;
     p.cost = a * a * qg2 + a * qg1 + qg0;
@@ -1525,7 +1545,17 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
-      if (x < 0 || r < ne_) {  // active at alpha (equality rows always): 1/2 D x^2 and its first / second derivative in alpha
+      if (r >= ne_ && r < nfe_) {  // dry friction: quadratic inside |x| < R floss, linear (force pinned at floss) outside
+        const T fl = at(b.efc_floss, r), D = at(b.efc_D, r);
+        if (ox_abs(x) * D >= fl) {
+          const T sg = x > 0 ? (T)1 : (T)-1;
+          p.cost += fl * (sg * x - (T)0.5 * fl / D);
+          p.d0 += sg * fl * jv;
+          p.s0 += ox_abs(fl * jv);
+          continue;
+        }
+      }
+      if (x < 0 || r < nfe_) {  // active at alpha (equality and quadratic-zone friction rows always): 1/2 D x^2 and its first / second derivative in alpha
         const T Dx = at(b.efc_D, r) * x, Dj = at(b.efc_D, r) * jv;
         p.cost += (T)0.5 * Dx * x;
         p.d0 += Dx * jv;
@@ -1539,7 +1569,7 @@ struct Env {
 
   // efc_force, qfrc_constraint and total cost at the current (qacc, Ma, Jaref); returns cost, gauss via pointer
   OX_HD T update_constraint(int nv, int nefc, T* gauss_out) const {
-    const int ne_ = ati(b.ne, 0);
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
     T c = 0;
     OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
@@ -1547,7 +1577,13 @@ struct Env {
     for (int r = 0; r < nefc; r++) {
       const T ja = at(b.s_Jaref, r);
       T f = 0;
-      if (ja < 0 || r < ne_) {
+      if (r >= ne_ && r < nfe_ && ox_abs(ja) * at(b.efc_D, r) >= at(b.efc_floss, r)) {   // dry friction, linear zone
+        const T fl = at(b.efc_floss, r), sg = ja > 0 ? (T)1 : (T)-1;
+        f = -sg * fl;
+        c += fl * (sg * ja - (T)0.5 * fl / at(b.efc_D, r));
+        OX_NVLOOP
+        for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, r * nv + i) * f;
+      } else if (ja < 0 || r < nfe_) {
         const T D = at(b.efc_D, r);
         f = -D * ja;
         c += (T)0.5 * D * ja * ja;
@@ -1579,7 +1615,7 @@ struct Env {
       return ox_sqrt(gn);
     }
     T* H = b.s_H;
-    const int ne_ = ati(b.ne, 0);
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
     OX_NVLOOP
     for (int i = 0; i < nv; i++) {
       OX_NVLOOP
@@ -1590,7 +1626,8 @@ struct Env {
     }
     OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
-      if (!(at(b.s_Jaref, r) < 0 || r < ne_)) continue;
+      if (r >= ne_ && r < nfe_) { if (ox_abs(at(b.s_Jaref, r)) * at(b.efc_D, r) >= at(b.efc_floss, r)) continue; }   // friction row in its linear zone: no curvature
+      else if (!(at(b.s_Jaref, r) < 0 || r < ne_)) continue;
       const T D = at(b.efc_D, r);
       if constexpr (UNROLL_NV) {  // the row once into registers, then the rank-1 update on register-resident H
         constexpr int NV = M::Hdr::nv;
@@ -1645,7 +1682,7 @@ struct Env {
   }
 
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
-    const int ne_ = ati(b.ne, 0);
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
     mul_m(b.s_Mv, qacc);
     T c = 0;
     OX_NVLOOP
@@ -1655,7 +1692,8 @@ struct Env {
       T v = -at(b.efc_aref, r);
       OX_NVLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(qacc, i);
-      if (v < 0 || r < ne_) c += (T)0.5 * at(b.efc_D, r) * v * v;
+      if (r >= ne_ && r < nfe_ && ox_abs(v) * at(b.efc_D, r) >= at(b.efc_floss, r)) c += at(b.efc_floss, r) * (ox_abs(v) - (T)0.5 * at(b.efc_floss, r) / at(b.efc_D, r));
+      else if (v < 0 || r < nfe_) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
     return c;
   }
@@ -1689,14 +1727,16 @@ struct Env {
   }
   OX_HD void dual_pgs(int nv, int nefc) const {
     const auto& h = m.h();
-    const int ne_ = ati(b.ne, 0);
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
     const T scale = 1 / ((T)h.meaninertia * (T)(nv > 1 ? nv : 1));
     bool warm = false;
     if (!dis(OX_DSBL_WARMSTART)) {  // forces implied by qacc_warmstart, kept only if their dual cost beats f = 0 (cost 0)
       OX_ROWLOOP
       for (int r = 0; r < nefc; r++) {
         const T jar = row_dot(r, b.qacc_warmstart, nv) - at(b.efc_aref, r);
-        at(b.efc_force, r) = (jar < 0 || r < ne_) ? -at(b.efc_D, r) * jar : (T)0;
+        T f = (jar < 0 || r < nfe_) ? -at(b.efc_D, r) * jar : (T)0;
+        if (r >= ne_ && r < nfe_) f = ox_clip(f, -at(b.efc_floss, r), at(b.efc_floss, r));
+        at(b.efc_force, r) = f;
       }
       dual_to_primal(nv, nefc);
       T cost = 0;
@@ -1728,7 +1768,8 @@ struct Env {
         const T old = at(b.efc_force, r);
         const T res = row_dot(r, b.s_Ma, nv) - at(b.efc_aref, r) + R * old;
         T f = old - res / ARrr;
-        if (r >= ne_ && f < 0) f = 0;   // limits and pyramidal contact edges push only; equalities pull both ways
+        if (r >= ne_ && r < nfe_) f = ox_clip(f, -at(b.efc_floss, r), at(b.efc_floss, r));   // dry friction: a box
+        else if (r >= ne_ && f < 0) f = 0;   // limits and pyramidal contact edges push only; equalities pull both ways
         const T delta = f - old;
         if (delta != 0) {
           at(b.efc_force, r) = f;
@@ -1773,8 +1814,26 @@ struct Env {
     const T scale = 1 / ((T)h.meaninertia * (T)(nv > 1 ? nv : 1));
     dual_to_primal(nv, nefc);
 #pragma unroll 1
+    const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
+#pragma unroll 1
     for (int iter = 0; iter < h.noslip_iterations; iter++) {
       T improvement = 0;
+#pragma unroll 1
+      for (int r = ne_; r < nfe_; r++) {   // dry-friction rows: the PGS update without the regulariser
+        OX_NVLOOP
+        for (int i = 0; i < nv; i++) at(b.s_Mv, i) = at(b.efc_J, r * nv + i);
+        solve_ld(b.s_Mv);
+        const T Arr = row_dot(r, b.s_Mv, nv);
+        if (Arr < (T)OX_MINVAL) continue;
+        const T old = at(b.efc_force, r), res = row_dot(r, b.s_Ma, nv) - at(b.efc_aref, r);
+        const T f = ox_clip(old - res / Arr, -at(b.efc_floss, r), at(b.efc_floss, r)), delta = f - old;
+        if (delta != 0) {
+          at(b.efc_force, r) = f;
+          OX_NVLOOP
+          for (int i = 0; i < nv; i++) at(b.s_Ma, i) += delta * at(b.s_Mv, i);
+          improvement -= (T)0.5 * delta * delta * Arr + delta * res;
+        }
+      }
       if (STATIC_CON || slots) {
 #pragma unroll 1
         for (int p = 0; p < h.npair; p++)

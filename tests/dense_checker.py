@@ -33,7 +33,7 @@ MINVAL, MINIMP, MAXIMP = 1e-15, 1e-4, 0.9999
 PLANE, SPHERE, CAPSULE, BOX = 0, 2, 3, 6
 FREE, BALL, SLIDE, HINGE = 0, 1, 2, 3
 DSBL = dict(constraint=1 << 0, limit=1 << 3, contact=1 << 4, passive=1 << 5, gravity=1 << 6, clampctrl=1 << 7,
-            filterparent=1 << 9, equality=1 << 1, warmstart=1 << 8, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
+            filterparent=1 << 9, equality=1 << 1, warmstart=1 << 8, frictionloss=1 << 2, actuation=1 << 10, refsafe=1 << 11, eulerdamp=1 << 13)
 
 
 def _T(a):
@@ -78,7 +78,8 @@ class DenseModel:
             "geom_margin", "geom_gap", "pair_friction", "pair_solref", "pair_solimp", "pair_margin", "pair_gap", "actuator_gear",
             "actuator_gainprm", "actuator_biasprm", "actuator_ctrlrange", "actuator_forcerange", "actuator_dynprm", "actuator_actrange",
             "eq_solref", "eq_solimp", "eq_data", "site_pos", "site_quat", "wrap_prm", "tendon_range", "tendon_margin", "tendon_solref_lim",
-            "tendon_solimp_lim", "tendon_stiffness", "tendon_damping", "tendon_lengthspring", "tendon_invweight0"]
+            "tendon_solimp_lim", "tendon_stiffness", "tendon_damping", "tendon_lengthspring", "tendon_invweight0",
+            "dof_frictionloss", "dof_solref_fri", "dof_solimp_fri"]
 
     def __init__(self, model):
         self.m = model
@@ -591,6 +592,14 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                 a, R = row_params(dm, sr, si, pos, 0.0, diag, row @ qvel)
                 J.append(row); D.append(1 / R); aref.append(a); cart.append(None)
     ne = len(J)
+    dm._floss = []                                                       # frictionloss of each dry-friction row (they follow the equality rows)
+    if not dm.dis("frictionloss"):
+        for i in range(dm.nv):
+            if dm.dof_frictionloss[i] > 0:
+                row = np.zeros(dm.nv)
+                row[i] = 1.0
+                a, R = row_params(dm, dm.dof_solref_fri[2 * i:2 * i + 2], dm.dof_solimp_fri[5 * i:5 * i + 5], 0.0, 0.0, dm.dof_invweight0[i], qvel[i])
+                J.append(row); D.append(1 / R); aref.append(a); cart.append(None); dm._floss.append(dm.dof_frictionloss[i])
     if not dm.dis("limit"):
         for j in range(dm.njnt):
             if dm.jnt_limited[j] and int(dm.jnt_type[j]) == BALL:            # limit on the rotation angle: J = -(unit rotation axis)
@@ -665,19 +674,32 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     return np.array(J), np.array(D), np.array(aref), ne
 
 
-def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0):
+def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0, floss=()):
     """argmin_a 1/2 (a-a0)' M (a-a0) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2 by damped Newton with backtracking."""
     a0 = np.linalg.solve(M, qfrc_smooth)
     if J.shape[0] == 0:
         return a0, np.zeros(0)
-    two_sided = np.arange(J.shape[0]) < ne                              # equality rows: 1/2 D x^2 for either sign of x
-    pen = lambda x: np.where(two_sided, x, np.minimum(0.0, x))
-    cost = lambda a: 0.5 * (a - a0) @ M @ (a - a0) + 0.5 * np.sum(D * pen(J @ a - aref) ** 2)
+    n, nf = J.shape[0], len(floss)
+    two_sided = np.arange(n) < ne + nf                                   # equality rows (and friction rows inside their band): 1/2 D x^2 for either sign
+    fl = np.zeros(n)
+    fl[ne:ne + nf] = floss
+    band = np.where(fl > 0, fl / D, np.inf)                              # dry friction: Huber cost, quadratic for |x| < R floss, slope floss beyond
+
+    def pen_cost(x):
+        quad = np.where(two_sided, x, np.minimum(0.0, x))
+        lin = np.abs(x) >= band
+        return np.sum(np.where(lin, fl * (np.abs(x) - 0.5 * fl / D), 0.5 * D * quad ** 2))
+
+    def pen_force(x):
+        lin = np.abs(x) >= band
+        return np.where(lin, -np.sign(x) * fl, np.where((x < 0) | two_sided, -D * x, 0.0))
+
+    cost = lambda a: 0.5 * (a - a0) @ M @ (a - a0) + pen_cost(J @ a - aref)
     a = a0.copy()
     for _ in range(500):
         jar = J @ a - aref
-        act = (jar < 0) | two_sided
-        g = M @ (a - a0) + J.T @ (D * jar * act)
+        act = ((jar < 0) | two_sided) & (np.abs(jar) < band)
+        g = M @ (a - a0) - J.T @ pen_force(jar)
         if np.linalg.norm(g) <= 1e-13 * max(1.0, np.linalg.norm(M @ a0)):
             break
         H = M + (J[act].T * D[act]) @ J[act]
@@ -689,7 +711,7 @@ def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0):
             break
         a = a + t * step
     jar = J @ a - aref
-    return a, np.where((jar < 0) | two_sided, -D * jar, 0.0)
+    return a, pen_force(jar)
 
 
 def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
@@ -705,12 +727,16 @@ def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
     bvec = J @ a0 - aref
     scale = 1 / (float(dm.m.meaninertia) * max(1, nv))
     two_sided = np.arange(n) < ne
+    nf = len(dm._floss)
+    fl = np.zeros(n)
+    fl[ne:ne + nf] = dm._floss
     niter = 0
     if pgs:
         f = np.zeros(n)
         if not dm.dis("warmstart"):
             jar = J @ warmstart - aref
-            fw = np.where((jar < 0) | two_sided, -D * jar, 0.0)
+            fw = np.where((jar < 0) | two_sided | (fl > 0), -D * jar, 0.0)
+            fw = np.where(fl > 0, np.clip(fw, -fl, fl), fw)
             if 0.5 * fw @ (A @ fw + R * fw) + fw @ bvec < 0:
                 f = fw
         AR = A + np.diag(R)
@@ -719,7 +745,9 @@ def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
             for r in range(n):
                 res = AR[r] @ f + bvec[r]
                 new = f[r] - res / AR[r, r]
-                if not two_sided[r]:
+                if fl[r] > 0:
+                    new = min(fl[r], max(-fl[r], new))
+                elif not two_sided[r]:
                     new = max(0.0, new)
                 delta = new - f[r]
                 f[r] = new
@@ -730,6 +758,14 @@ def solve_dual(dm, M, qfrc_smooth, J, D, aref, ne, warmstart, pgs):
         f = warmstart                                                   # the primal solver's forces
     for _ in range(int(dm.m.noslip_iterations)):
         improvement = 0.0
+        for r in range(ne, ne + nf):                                      # dry-friction rows, unregularised
+            if A[r, r] < MINVAL:
+                continue
+            res = A[r] @ f + bvec[r]
+            new = min(fl[r], max(-fl[r], f[r] - res / A[r, r]))
+            delta = new - f[r]
+            f[r] = new
+            improvement -= 0.5 * delta * delta * A[r, r] + delta * res
         for ra, rb in dm._friction_pairs:
             K = A[ra, ra] + A[rb, rb] - 2 * A[ra, rb]
             if K < MINVAL:
@@ -817,7 +853,7 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     if solver == 0:                                                      # PGS (+ noslip)
         qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, np.zeros(dm.nv) if warmstart is None else np.asarray(warmstart, float), True)
     else:
-        qacc, force = solve_qacc(M, f, J, D, aref, ne)
+        qacc, force = solve_qacc(M, f, J, D, aref, ne, dm._floss)
         if noslip and len(force):
             qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, force.copy(), False)
     ft = force_torque_sensors(dm, kin, qacc, force, xfrc_applied) if dm.nsensor else {}

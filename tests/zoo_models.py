@@ -369,5 +369,39 @@ ZOO_J = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J}
+# N3: dry joint friction (frictionloss): Huber-cost rows on hinges, a slide and a ball joint, Newton here and PGS + noslip in
+# zoo_l, together with limits and a contact
+ZOO_K = """
+<mujoco model="zoo_k">
+  <compiler angle="radian"/>
+  <option timestep="0.004" tolerance="1e-13"/>
+  <default><joint damping="0.02" armature="0.002"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <body name="cart" pos="0 0 0.5">
+      <joint name="rail" type="slide" axis="1 0 0" frictionloss="1.5" range="-1 1" limited="true"/>
+      <geom name="cart" type="box" size="0.1 0.08 0.05" density="600" contype="0" conaffinity="0"/>
+      <body name="arm1" pos="0 0 -0.05">
+        <joint name="a1" type="hinge" axis="0 1 0" frictionloss="0.15" solreffriction="0.01 1" solimpfriction="0.8 0.9 0.001 0.5 2"/>
+        <geom name="arm1" type="capsule" fromto="0 0 0 0 0 -0.25" size="0.02"/>
+        <body name="arm2" pos="0 0 -0.25">
+          <joint name="a2" type="ball" frictionloss="0.05"/>
+          <geom name="arm2" type="capsule" fromto="0 0 0 0 0 -0.2" size="0.018"/>
+          <geom name="bob" type="sphere" pos="0 0 -0.2" size="0.04"/>
+        </body>
+      </body>
+    </body>
+    <body name="free" pos="0.4 0.1 0.3"><freejoint/><geom name="free" type="sphere" size="0.06"/>
+      <body name="flap" pos="0 0 0.06"><joint name="fl" type="hinge" axis="1 0 0" frictionloss="0.02" range="-1 1" limited="true"/>
+        <geom name="flap" type="capsule" fromto="0 0 0 0 0.12 0" size="0.012"/></body></body>
+  </worldbody>
+  <actuator><motor joint="rail" gear="4"/><motor joint="a1" gear="0.5"/><motor joint="fl" gear="0.05"/></actuator>
+  <sensor><jointpos joint="rail"/><jointvel joint="a1"/><jointpos joint="fl"/></sensor>
+</mujoco>
+"""
+
+ZOO_L = ZOO_K.replace('model="zoo_k"', 'model="zoo_l"').replace('<option timestep="0.004" tolerance="1e-13"/>',
+                                                              '<option timestep="0.004" solver="PGS" iterations="80" tolerance="1e-12" noslip_iterations="3" noslip_tolerance="1e-9"/>')
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L}
 NOCONTACT = {"zoo_d": ZOO_D}
