@@ -820,6 +820,17 @@ void makeConstraint(const Model* m, Data* d) {
     int dim = m->pair_dim[p];
     if (dim == 1) {
       addRow(m, d, jac.data(), d->con_dist[c], includemargin, tran, m->pair_solref + 2 * p, m->pair_solimp + 5 * p, 1, c);
+    } else if (m->cone == OX_CONE_ELLIPTIC) {
+      // elliptic cone: rows = normal, then one row per friction direction (tangents; torsion / rolling for condim 4 / 6). Only the
+      // normal row has a position term; the friction rows get R_j = R_n mu^2 / friction_j^2 with the regularised friction
+      // mu = friction_1 / sqrt(impratio), which makes the cone circular in the scaled coordinates of the cost (ellipticCost).
+      const int first = d->nefc;
+      addRow(m, d, jac.data(), d->con_dist[c], includemargin, tran, m->pair_solref + 2 * p, m->pair_solimp + 5 * p, 6, c);
+      const double mu = fri[0] * std::sqrt(1 / m->impratio);
+      for (int k = 1; k < dim; k++) {
+        addRow(m, d, &jac[(size_t)k * nv], 0.0, 0.0, tran, m->pair_solref + 2 * p, m->pair_solimp + 5 * p, 6, c);
+        d->efc_R[d->nefc - 1] = d->efc_R[first] * mu * mu / (fri[k - 1] * fri[k - 1]);
+      }
     } else {
       int first = d->nefc;
       for (int k = 1; k < dim; k++)
@@ -988,6 +999,56 @@ void fwdAcceleration(const Model* m, Data* d) {
   solveLD(m, d->qLD.data(), d->qLDiagInv.data(), d->qacc_smooth.data());
 }
 
+// ---------------------------------------------------------------- elliptic cone (mj_constraintUpdate, mjCNSTR_CONTACT_ELLIPTIC)
+// Cost of one elliptic contact as a function of x = J a - aref of its rows (normal first). In the scaled coordinates
+// N = mu x_0, T = |(friction_j x_j)| the regularised cone is circular and the cost has three zones:
+//   top    (N >= mu T)     : the constraint is satisfied, cost 0
+//   bottom (mu N + T <= 0) : every row is an ordinary quadratic row, cost 1/2 sum D_r x_r^2
+//   middle (the cone)      : cost 1/2 Dm (N - mu T)^2 with Dm = D_n / (mu^2 (1 + mu^2))
+// force = -d cost / d x;  Hc = d^2 cost / d x^2 (dim x dim, only in the middle zone; bottom = diag(D), top = 0).
+// Returns the zone (0 top, 1 bottom, 2 middle).
+struct EllipticContact { int row, dim; double mu, fri[5]; };
+int ellipticCost(const EllipticContact& c, const double* D, const double* x, double* cost, double* force, double* Hc) {
+  const int dim = c.dim;
+  double U[6] = {0, 0, 0, 0, 0, 0}, scl[6];
+  scl[0] = c.mu;
+  for (int j = 1; j < dim; j++) scl[j] = c.fri[j - 1];
+  for (int j = 0; j < dim; j++) U[j] = x[j] * scl[j];
+  double T2 = 0;
+  for (int j = 1; j < dim; j++) T2 += U[j] * U[j];
+  const double N = U[0], T = std::sqrt(T2), mu = c.mu;
+  if (force) std::fill(force, force + dim, 0.0);
+  if (Hc) std::fill(Hc, Hc + dim * dim, 0.0);
+  *cost = 0;
+  if (N >= mu * T || (T <= 0 && N >= 0)) return 0;
+  if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+    for (int j = 0; j < dim; j++) {
+      *cost += 0.5 * D[j] * x[j] * x[j];
+      if (force) force[j] = -D[j] * x[j];
+      if (Hc) Hc[j * dim + j] = D[j];
+    }
+    return 1;
+  }
+  const double Dm = D[0] / (mu * mu * (1 + mu * mu)), NT = N - mu * T;
+  *cost = 0.5 * Dm * NT * NT;
+  // gradient in U: g_0 = Dm NT, g_j = -Dm NT mu U_j / T
+  if (force) {
+    force[0] = -Dm * NT * scl[0];
+    for (int j = 1; j < dim; j++) force[j] = Dm * NT * mu * U[j] / T * scl[j];
+  }
+  if (Hc) {
+    double HU[36];
+    HU[0] = Dm;
+    for (int j = 1; j < dim; j++) HU[j] = HU[j * dim] = -Dm * mu * U[j] / T;
+    for (int j = 1; j < dim; j++)
+      for (int k = 1; k < dim; k++)
+        HU[j * dim + k] = Dm * mu * mu * U[j] * U[k] / T2 - Dm * NT * mu * ((j == k ? 1.0 : 0.0) / T - U[j] * U[k] / (T2 * T));
+    for (int j = 0; j < dim; j++)
+      for (int k = 0; k < dim; k++) Hc[j * dim + k] = HU[j * dim + k] * scl[j] * scl[k];
+  }
+  return 2;
+}
+
 // ---------------------------------------------------------------- A.11 constraint solver (primal: Newton / CG)
 struct Solver {
   const Model* m;
@@ -995,17 +1056,39 @@ struct Solver {
   int nv, nefc;
   std::vector<double> Ma, Jaref, grad, Mgrad, search, Mv, Jv, H, gradold, Mgradold;
   std::vector<char> active;
+  std::vector<EllipticContact> ell;   // elliptic contacts (their rows are skipped by the row loops and handled per contact)
+  std::vector<char> isell;
+  std::vector<double> ellH;           // per contact: 36 entries of the cone Hessian at the current point
+  std::vector<int> ellZone;
   double cost = 0, gauss = 0;
   double quadGauss[3];
 
   Solver(const Model* m_, Data* d_) : m(m_), d(d_), nv(m_->nv), nefc(d_->nefc) {
     Ma.resize(nv); Jaref.resize(nefc); grad.resize(nv); Mgrad.resize(nv); search.resize(nv); Mv.resize(nv); Jv.resize(nefc);
     H.resize((size_t)nv * nv); gradold.resize(nv); Mgradold.resize(nv); active.resize(nefc);
+    isell.assign(nefc, 0);
+    for (int r = 0; r < nefc; r++)
+      if (d->efc_type[r] == 6 && (r == 0 || d->efc_type[r - 1] != 6 || d->efc_id[r - 1] != d->efc_id[r])) {
+        const int p = d->con_pair[d->efc_id[r]];
+        EllipticContact c;
+        c.row = r; c.dim = m->pair_dim[p]; c.mu = m->pair_friction[5 * p] * std::sqrt(1 / m->impratio);
+        for (int k = 0; k < 5; k++) c.fri[k] = m->pair_friction[5 * p + k];
+        ell.push_back(c);
+        for (int k = 0; k < c.dim; k++) isell[r + k] = 1;
+      }
+    ellH.assign(36 * ell.size(), 0.0); ellZone.assign(ell.size(), 0);
   }
   // efc_force, active set, cost, qfrc_constraint at the current Jaref / Ma / qacc
   void updateConstraint() {
     double c = 0;
+    for (size_t k = 0; k < ell.size(); k++) {
+      double ck;
+      ellZone[k] = ellipticCost(ell[k], &d->efc_D[ell[k].row], &Jaref[ell[k].row], &ck, &d->efc_force[ell[k].row], &ellH[36 * k]);
+      c += ck;
+      for (int j = 0; j < ell[k].dim; j++) active[ell[k].row + j] = 0;   // their curvature enters through ellH
+    }
     for (int r = 0; r < nefc; r++) {
+      if (isell[r]) continue;
       const double fl = d->efc_floss[r];
       if (fl > 0 && std::fabs(Jaref[r]) >= fl / d->efc_D[r]) {   // dry friction, linear zone: |force| pinned at frictionloss
         const double rf = fl / d->efc_D[r], sgn = Jaref[r] > 0 ? 1.0 : -1.0;
@@ -1053,6 +1136,21 @@ struct Solver {
         for (int j = 0; j <= i; j++) H[(size_t)i * nv + j] += s * J[j];
       }
     }
+    for (size_t k = 0; k < ell.size(); k++) {   // J_c' Hc J_c of every elliptic contact that is not in the top zone
+      if (ellZone[k] == 0) continue;
+      const int dim = ell[k].dim, r0 = ell[k].row;
+      for (int a = 0; a < dim; a++)
+        for (int b = 0; b < dim; b++) {
+          const double h = ellH[36 * k + a * dim + b];
+          if (h == 0) continue;
+          const double *Ja = &d->efc_J[(size_t)(r0 + a) * nv], *Jb = &d->efc_J[(size_t)(r0 + b) * nv];
+          for (int i = 0; i < nv; i++) {
+            if (Ja[i] == 0) continue;
+            const double sa = h * Ja[i];
+            for (int j = 0; j <= i; j++) H[(size_t)i * nv + j] += sa * Jb[j];
+          }
+        }
+    }
     for (int j = 0; j < nv; j++) {
       double s = H[(size_t)j * nv + j];
       for (int k = 0; k < j; k++) s -= H[(size_t)j * nv + k] * H[(size_t)j * nv + k];
@@ -1083,7 +1181,20 @@ struct Solver {
     p.d0 = 2 * a * quadGauss[2] + quadGauss[1];
     p.d1 = 2 * quadGauss[2];
     p.s0 = std::fabs(2 * a * quadGauss[2]) + std::fabs(quadGauss[1]);
+    for (size_t k = 0; k < ell.size(); k++) {   // elliptic contacts: exact cost, slope and curvature along the search direction
+      const int dim = ell[k].dim, r0 = ell[k].row;
+      double x[6], f[6], Hc[36], ck;
+      for (int j = 0; j < dim; j++) x[j] = Jaref[r0 + j] + a * Jv[r0 + j];
+      ellipticCost(ell[k], &d->efc_D[r0], x, &ck, f, Hc);
+      p.cost += ck;
+      for (int j = 0; j < dim; j++) {
+        p.d0 -= f[j] * Jv[r0 + j];
+        p.s0 += std::fabs(f[j] * Jv[r0 + j]);
+        for (int l = 0; l < dim; l++) p.d1 += Jv[r0 + j] * Hc[j * dim + l] * Jv[r0 + l];
+      }
+    }
     for (int r = 0; r < nefc; r++) {
+      if (isell[r]) continue;
       double x = Jaref[r] + a * Jv[r];
       const double fl = d->efc_floss[r];
       if (fl > 0 && std::fabs(x) >= fl / d->efc_D[r]) {  // friction row in its linear zone: floss (|x| - R floss / 2)
@@ -1186,9 +1297,20 @@ struct Solver {
     mulM(m, d->qM.data(), ma.data(), qacc);
     double c = 0;
     for (int i = 0; i < nv; i++) c += 0.5 * (ma[i] - d->qfrc_smooth[i]) * (qacc[i] - d->qacc_smooth[i]);
+    std::vector<double> jar(nefc);
     for (int r = 0; r < nefc; r++) {
       double v = -d->efc_aref[r];
       for (int i = 0; i < nv; i++) v += d->efc_J[(size_t)r * nv + i] * qacc[i];
+      jar[r] = v;
+    }
+    for (size_t k = 0; k < ell.size(); k++) {
+      double ck;
+      ellipticCost(ell[k], &d->efc_D[ell[k].row], &jar[ell[k].row], &ck, nullptr, nullptr);
+      c += ck;
+    }
+    for (int r = 0; r < nefc; r++) {
+      if (isell[r]) continue;
+      double v = jar[r];
       const double fl = d->efc_floss[r];
       if (fl > 0 && std::fabs(v) >= fl / d->efc_D[r]) c += fl * (std::fabs(v) - 0.5 * fl / d->efc_D[r]);
       else if (v < 0 || r < d->ne || fl > 0) c += 0.5 * d->efc_D[r] * v * v;
@@ -1483,12 +1605,15 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
   for (int c = 0; c < d->ncon; c++) {
     int first = -1, n = 0;
     for (int r = 0; r < d->nefc; r++)
-      if ((d->efc_type[r] == 1 || d->efc_type[r] == 2) && d->efc_id[r] == c) { if (first < 0) first = r; n++; }
+      if ((d->efc_type[r] == 1 || d->efc_type[r] == 2 || d->efc_type[r] == 6) && d->efc_id[r] == c) { if (first < 0) first = r; n++; }
     if (first < 0) continue;
     const int p = d->con_pair[c];
     const double* fri = m->pair_friction + 5 * p;
     double lf[6] = {0, 0, 0, 0, 0, 0};   // contact-frame force (normal, tangents) and torque (torsion, rolling)
+    const bool elliptic = d->efc_type[first] == 6;
     if (n == 1) lf[0] = d->efc_force[first];
+    else if (elliptic)
+      for (int k = 0; k < n; k++) lf[k] = d->efc_force[first + k];   // rows are the contact-frame components themselves
     else
       for (int k = 0; k < n / 2; k++) {
         lf[0] += d->efc_force[first + 2 * k] + d->efc_force[first + 2 * k + 1];
@@ -1500,8 +1625,9 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
       wf[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2];
       wt[k] = fr[k] * lf[3] + fr[3 + k] * lf[4] + fr[6 + k] * lf[5];
     }
-    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom1[p]], &d->con_pos[3 * c], wf, n > 4 ? wt : nullptr, -1.0);
-    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom2[p]], &d->con_pos[3 * c], wf, n > 4 ? wt : nullptr, +1.0);
+    const bool has_torque = elliptic ? n > 3 : n > 4;
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom1[p]], &d->con_pos[3 * c], wf, has_torque ? wt : nullptr, -1.0);
+    addExtForce(m, d, ext, m->geom_bodyid[m->pair_geom2[p]], &d->con_pos[3 * c], wf, has_torque ? wt : nullptr, +1.0);
   }
   // connect equalities: the three row forces are a world-frame force on body1 at its anchor and the opposite on body2 at its own
   for (int r = 0; r + 2 < d->ne; r++) {
@@ -1556,6 +1682,7 @@ void sensors(const Model* m, Data* d) {
           bool has_rows = false;
           for (int r = 0; r < d->nefc; r++)
             if ((d->efc_type[r] == 1 || d->efc_type[r] == 2) && d->efc_id[r] == c) { fn += d->efc_force[r]; has_rows = true; }
+            else if (d->efc_type[r] == 6 && d->efc_id[r] == c) { if (!has_rows) fn = d->efc_force[r]; has_rows = true; }   // elliptic: the first row IS the normal force
           if (!has_rows || fn <= 0) continue;
           double ray[3] = {d->con_frame[9 * c], d->con_frame[9 * c + 1], d->con_frame[9 * c + 2]};
           if (sbody == b2) for (double& v : ray) v = -v;

@@ -679,9 +679,11 @@ ox_model* compile_mjcf(const std::string& xml) {
       }
       if (a.has("cone")) {
         const std::string& s = a.str("cone");
-        if (s == "elliptic") cfail("cone elliptic is outside the supported subset (pyramidal)");
+        if (s == "elliptic") t.cone = OX_CONE_ELLIPTIC;
         else if (s != "pyramidal") pfail(*ch, "unknown cone '" + s + "'");
       }
+      if (t.cone == OX_CONE_ELLIPTIC && (t.solver == OX_SOL_PGS || t.noslip_iterations > 0))
+        cfail("cone elliptic with the PGS solver or the noslip pass is outside the supported subset (Newton, CG)");
       if (!(t.timestep > 0)) cfail("timestep must be positive");
       if (t.impratio <= 0) cfail("impratio must be positive");
       for (auto& f : ch->children) {

@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
 template <typename T> static int coop_group_size(const ox_model_tables& t) { return t.nv <= 16 ? 16 : 32; }
 
 bool step_coop_eligible(const ox_model_tables& t) {
-  return t.nv >= 1 && t.nv <= 32 && t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nfloss == 0 && (t.integrator == OX_INT_EULER || t.integrator == OX_INT_IMPLICITFAST);
+  return t.nv >= 1 && t.nv <= 32 && t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nfloss == 0 && t.cone == OX_CONE_PYRAMIDAL && (t.integrator == OX_INT_EULER || t.integrator == OX_INT_IMPLICITFAST);
 }
 template <typename T>
 static size_t coop_group_bytes_host(const ox_model_tables& t, int G) {

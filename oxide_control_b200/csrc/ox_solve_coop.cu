@@ -361,7 +361,7 @@ static cudaError_t launch_coop(cudaStream_t stream, const unsigned char* blob, i
 cudaError_t launch_solve_coop_f32(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<float>& b, int resident_ctas, int* ctr) { return launch_coop<float>(s, blob, bytes, b, resident_ctas, ctr); }
 cudaError_t launch_solve_coop_f64(cudaStream_t s, const unsigned char* blob, int bytes, const DevBatch<double>& b, int resident_ctas, int* ctr) { return launch_coop<double>(s, blob, bytes, b, resident_ctas, ctr); }
 bool solve_coop_eligible(const ox_model_tables& t) {
-  return t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nfloss == 0 && t.nv >= 1 && t.nv <= 32;
+  return t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nfloss == 0 && t.cone == OX_CONE_PYRAMIDAL && t.nv >= 1 && t.nv <= 32;
 }
 
 }  // namespace ox

@@ -1272,6 +1272,155 @@ struct Env {
       }
   }
 
+  // rows of one contact under the ELLIPTIC cone: normal row, then one row per friction direction (tangents; torsion / rolling
+  // for condim 4 / 6) - the contact-frame components themselves, not pyramid edges. Only the normal row has a position term;
+  // friction row k gets D_k = D_n friction_k^2 / mu^2 with the regularised friction mu = friction_1 / sqrt(impratio), which makes
+  // the cone circular in the scaled coordinates of elliptic_cost().
+  OX_HD void contact_rows_elliptic(int c, int p, int& nefc) const {
+    const auto& h = m.h();
+    const int nv = h.nv;
+    const T includemargin = m.pair_margin(p) - m.pair_gap(p);
+    const T dist = at(b.con_dist, c);
+    ati(b.con_efcadr, c) = -1;
+    if (dist >= includemargin) return;
+    const int dim = m.pair_dim(p);
+    const int r0 = nefc;
+    ati(b.con_efcadr, c) = r0;
+    nefc += dim;
+    T fri[5], cpos[3], frame[9], vel[6] = {0, 0, 0, 0, 0, 0};
+    OX_LDM(5, fri, pair_friction, 5 * p);
+    ld<3>(cpos, b.con_pos, 3 * c);
+    ld<9>(frame, b.con_frame, 9 * c);
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) {
+      if (rr >= dim) break;
+      OX_MLOOP
+      for (int i = 0; i < nv; i++) at(b.efc_J, (r0 + rr) * nv + i) = 0;
+    }
+    const int bodies[2] = {m.geom_bodyid(m.pair_geom2(p)), m.geom_bodyid(m.pair_geom1(p))};
+    OX_MLOOP
+    for (int sidx = 0; sidx < 2; sidx++) {
+      const T sign = sidx == 0 ? (T)1 : (T)-1;
+      int body = bodies[sidx];
+      T sc[3], offset[3];
+      ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));
+      offset[0] = cpos[0] - sc[0]; offset[1] = cpos[1] - sc[1]; offset[2] = cpos[2] - sc[2];
+      body = m.body_weldid(body);
+      if (!body) continue;
+      const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+      OX_MLOOP
+      for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
+        T cd[6], jp[3];
+        ld<6>(cd, b.cdof, 6 * i);
+        cross3(jp, cd, offset);
+        jp[0] = sign * (jp[0] + cd[3]); jp[1] = sign * (jp[1] + cd[4]); jp[2] = sign * (jp[2] + cd[5]);
+        const T jr[3] = {sign * cd[0], sign * cd[1], sign * cd[2]};
+        const T qv = at(b.qvel, i);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          if (k >= dim) break;
+          const T j = k < 3 ? dot3(frame + 3 * k, jp) : dot3(frame + 3 * (k - 3), jr);
+          at(b.efc_J, (r0 + k) * nv + i) += j;
+          vel[k] += j * qv;
+        }
+      }
+    }
+    const T tran = m.body_invweight0(2 * bodies[1]) + m.body_invweight0(2 * bodies[0]);
+    T solref[2], solimp[5], aref;
+    OX_LDM(2, solref, pair_solref, 2 * p);
+    OX_LDM(5, solimp, pair_solimp, 5 * p);
+    const T Rn = row_params(solref, solimp, dist, includemargin, tran, vel[0], &aref);
+    at(b.efc_pos, r0) = dist; at(b.efc_margin, r0) = includemargin; at(b.efc_D, r0) = 1 / Rn; at(b.efc_aref, r0) = aref;
+    const T mu = fri[0] * ox_sqrt(1 / (T)h.impratio);
+#pragma unroll
+    for (int k = 1; k < 6; k++) {
+      if (k >= dim) break;
+      (void)row_params(solref, solimp, (T)0, (T)0, tran, vel[k], &aref);   // no position term: aref = -B vel
+      at(b.efc_pos, r0 + k) = 0; at(b.efc_margin, r0 + k) = 0; at(b.efc_aref, r0 + k) = aref;
+      at(b.efc_D, r0 + k) = fri[k - 1] * fri[k - 1] / (Rn * mu * mu);
+    }
+  }
+  OX_HD void contact_rows_any(int c, int p, int& nefc) const {
+    if (m.h().cone == OX_CONE_ELLIPTIC && m.pair_dim(p) > 1) contact_rows_elliptic(c, p, nefc);
+    else contact_rows(c, p, nefc);
+  }
+  // visit every contact that has constraint rows: f(contact slot, pair, first row, dim)
+  template <typename F>
+  OX_HD void for_each_contact(F&& f) const {
+    const auto& h = m.h();
+    if (STATIC_CON || slots) {
+      OX_MLOOP
+      for (int p = 0; p < h.npair; p++) {
+        OX_MLOOP
+        for (int k = 0; k < m.pair_maxcon(p); k++) {
+          const int c = m.pair_conadr(p) + k;
+          if (ati(b.con_active, c) && ati(b.con_efcadr, c) >= 0) f(c, p, ati(b.con_efcadr, c), m.pair_dim(p));
+        }
+      }
+    } else {
+      const int ncon = ati(b.ncon, 0);
+      for (int c = 0; c < ncon; c++) {
+        const int p = ati(b.con_pair, c);
+        if (ati(b.con_efcadr, c) >= 0) f(c, p, ati(b.con_efcadr, c), m.pair_dim(p));
+      }
+    }
+  }
+  // Cost of one elliptic contact as a function of x = J a - aref of its rows (mj_constraintUpdate, elliptic). In the scaled
+  // coordinates N = mu x_0, T = |(friction_j x_j)|: top zone (N >= mu T) cost 0; bottom zone (mu N + T <= 0) every row an ordinary
+  // quadratic row; middle zone 1/2 Dm (N - mu T)^2, Dm = D_n / (mu^2 (1 + mu^2)). force = -d cost/dx (may be null), Hc = d2 cost/dx2
+  // (dim x dim, may be null). Returns the zone (0 top, 1 bottom, 2 middle).
+  OX_HD int elliptic_cost(int p, int dim, const T* D, const T* x, T* cost, T* force, T* Hc) const {
+    T U[6] = {0, 0, 0, 0, 0, 0}, scl[6] = {0, 0, 0, 0, 0, 0};
+    const T mu = m.pair_friction(5 * p) * ox_sqrt(1 / (T)m.h().impratio);
+    scl[0] = mu;
+#pragma unroll
+    for (int j = 1; j < 6; j++) { if (j >= dim) break; scl[j] = m.pair_friction(5 * p + j - 1); }
+    T T2 = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) { if (j >= dim) break; U[j] = x[j] * scl[j]; if (j) T2 += U[j] * U[j]; }
+    const T N = U[0], Tn = ox_sqrt(T2);
+    *cost = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) { if (j >= dim) break; if (force) force[j] = 0; }
+    if (Hc) {
+#pragma unroll
+      for (int j = 0; j < 36; j++) { if (j >= dim * dim) break; Hc[j] = 0; }
+    }
+    if (N >= mu * Tn || (Tn <= 0 && N >= 0)) return 0;
+    if (mu * N + Tn <= 0 || (Tn <= 0 && N < 0)) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        if (j >= dim) break;
+        *cost += (T)0.5 * D[j] * x[j] * x[j];
+        if (force) force[j] = -D[j] * x[j];
+        if (Hc) Hc[j * dim + j] = D[j];
+      }
+      return 1;
+    }
+    const T Dm = D[0] / (mu * mu * (1 + mu * mu)), NT = N - mu * Tn;
+    *cost = (T)0.5 * Dm * NT * NT;
+    if (force) {
+      force[0] = -Dm * NT * scl[0];
+#pragma unroll
+      for (int j = 1; j < 6; j++) { if (j >= dim) break; force[j] = Dm * NT * mu * U[j] / Tn * scl[j]; }
+    }
+    if (Hc) {
+      Hc[0] = Dm * scl[0] * scl[0];
+#pragma unroll
+      for (int j = 1; j < 6; j++) {
+        if (j >= dim) break;
+        const T h0 = -Dm * mu * U[j] / Tn * scl[0] * scl[j];
+        Hc[j] = h0; Hc[j * dim] = h0;
+#pragma unroll
+        for (int k = 1; k < 6; k++) {
+          if (k >= dim) break;
+          Hc[j * dim + k] = (Dm * mu * mu * U[j] * U[k] / T2 - Dm * NT * mu * ((j == k ? (T)1 : (T)0) / Tn - U[j] * U[k] / (T2 * Tn))) * scl[j] * scl[k];
+        }
+      }
+    }
+    return 2;
+  }
+
   OX_HDN void make_constraint() const {
     const auto& h = m.h();
     const int nv = h.nv, njnt = h.njnt;
@@ -1319,15 +1468,23 @@ struct Env {
           OX_MLOOP
           for (int k = 0; k < m.pair_maxcon(p); k++) {
             const int c = m.pair_conadr(p) + k;
-            if (ati(b.con_active, c)) contact_rows(c, p, nefc);
+            if (ati(b.con_active, c)) contact_rows_any(c, p, nefc);
           }
         }
       } else {
         const int ncon = ati(b.ncon, 0);
-        for (int c = 0; c < ncon; c++) contact_rows(c, ati(b.con_pair, c), nefc);
+        for (int c = 0; c < ncon; c++) contact_rows_any(c, ati(b.con_pair, c), nefc);
       }
     }
     ati(b.nefc, 0) = nefc;
+    if (h.cone == OX_CONE_ELLIPTIC && nefc > 0) {   // mark the rows of elliptic contacts (efc_floss < 0): the solver's row loops skip them
+      OX_ROWLOOP
+      for (int r = ati(b.ne, 0) + ati(b.nf, 0); r < nefc; r++) at(b.efc_floss, r) = 0;
+      for_each_contact([&](int, int, int ea, int dim) {
+        if (dim > 1)
+          for (int j = 0; j < dim; j++) at(b.efc_floss, ea + j) = -1;
+      });
+    }
   }
   // rows of equality constraint i (mj_instantiateEquality): connect = the two anchors coincide (3 rows), joint = q1 tracks a
   // quartic polynomial of q2 (1 row). pos = residual, margin = 0.
@@ -1542,7 +1699,26 @@ struct Env {
     p.d1 = 2 * qg2;
     p.s0 = ox_abs(2 * a * qg2) + ox_abs(qg1);
     OX_ROWLOOP
+    const bool ell_ = m.h().cone == OX_CONE_ELLIPTIC;
+    if (ell_)   // elliptic contacts: exact cost, slope and curvature of the three-zone function along the search direction
+      for_each_contact([&](int, int pp, int ea, int dim) {
+        if (dim == 1) return;
+        T x[6], D[6], jvv[6], f[6], Hc[36], ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { if (j >= dim) break; jvv[j] = at(b.s_Jv, ea + j); x[j] = at(b.s_Jaref, ea + j) + a * jvv[j]; D[j] = at(b.efc_D, ea + j); }
+        elliptic_cost(pp, dim, D, x, &ck, f, Hc);
+        p.cost += ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          if (j >= dim) break;
+          p.d0 -= f[j] * jvv[j];
+          p.s0 += ox_abs(f[j] * jvv[j]);
+#pragma unroll
+          for (int l = 0; l < 6; l++) { if (l >= dim) break; p.d1 += jvv[j] * Hc[j * dim + l] * jvv[l]; }
+        }
+      });
     for (int r = 0; r < nefc; r++) {
+      if (ell_ && r >= nfe_ && at(b.efc_floss, r) < 0) continue;
       const T ja = at(b.s_Jaref, r), jv = at(b.s_Jv, r);
       const T x = ja + a * jv;
       if (r >= ne_ && r < nfe_) {  // dry friction: quadratic inside |x| < R floss, linear (force pinned at floss) outside
@@ -1573,8 +1749,28 @@ struct Env {
     T c = 0;
     OX_NVLOOP
     for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) = 0;
+    const bool ell_ = m.h().cone == OX_CONE_ELLIPTIC;
+    if (ell_)
+      for_each_contact([&](int, int pp, int ea, int dim) {
+        if (dim == 1) return;
+        T x[6], D[6], f[6], ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { if (j >= dim) break; x[j] = at(b.s_Jaref, ea + j); D[j] = at(b.efc_D, ea + j); }
+        elliptic_cost(pp, dim, D, x, &ck, f, (T*)nullptr);
+        c += ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          if (j >= dim) break;
+          at(b.efc_force, ea + j) = f[j];
+          if (f[j] != 0) {
+            OX_NVLOOP
+            for (int i = 0; i < nv; i++) at(b.qfrc_constraint, i) += at(b.efc_J, (ea + j) * nv + i) * f[j];
+          }
+        }
+      });
     OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
+      if (ell_ && r >= nfe_ && at(b.efc_floss, r) < 0) continue;
       const T ja = at(b.s_Jaref, r);
       T f = 0;
       if (r >= ne_ && r < nfe_ && ox_abs(ja) * at(b.efc_D, r) >= at(b.efc_floss, r)) {   // dry friction, linear zone
@@ -1627,6 +1823,7 @@ struct Env {
     OX_ROWLOOP
     for (int r = 0; r < nefc; r++) {
       if (r >= ne_ && r < nfe_) { if (ox_abs(at(b.s_Jaref, r)) * at(b.efc_D, r) >= at(b.efc_floss, r)) continue; }   // friction row in its linear zone: no curvature
+      else if (m.h().cone == OX_CONE_ELLIPTIC && r >= nfe_ && at(b.efc_floss, r) < 0) continue;   // rows of elliptic contacts: their block follows
       else if (!(at(b.s_Jaref, r) < 0 || r < ne_)) continue;
       const T D = at(b.efc_D, r);
       if constexpr (UNROLL_NV) {  // the row once into registers, then the rank-1 update on register-resident H
@@ -1649,6 +1846,24 @@ struct Env {
         }
       }
     }
+    if (m.h().cone == OX_CONE_ELLIPTIC)   // J_c' Hc J_c of every elliptic contact outside the top zone (bottom: diag(D); middle: the cone Hessian)
+      for_each_contact([&](int, int pp, int ea, int dim) {
+        if (dim == 1) return;
+        T x[6], D[6], Hc[36], ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { if (j >= dim) break; x[j] = at(b.s_Jaref, ea + j); D[j] = at(b.efc_D, ea + j); }
+        if (elliptic_cost(pp, dim, D, x, &ck, (T*)nullptr, Hc) == 0) return;
+        for (int a = 0; a < dim; a++)
+          for (int c2 = 0; c2 < dim; c2++) {
+            const T hh = Hc[a * dim + c2];
+            if (hh == 0) continue;
+            for (int i = 0; i < nv; i++) {
+              const T sa = hh * at(b.efc_J, (ea + a) * nv + i);
+              if (sa == 0) continue;
+              for (int j = 0; j <= i; j++) at(H, i * nv + j) += sa * at(b.efc_J, (ea + c2) * nv + j);
+            }
+          }
+      });
     OX_NVLOOP
     for (int j = 0; j < nv; j++) {  // Cholesky, lower
       T s = at(H, j * nv + j);
@@ -1683,6 +1898,7 @@ struct Env {
 
   OX_HD T cost_at(const T* qacc, int nv, int nefc) const {  // warm-start selection; uses s_Mv as scratch
     const int ne_ = ati(b.ne, 0), nfe_ = ne_ + ati(b.nf, 0);
+    const bool ell_ = m.h().cone == OX_CONE_ELLIPTIC;
     mul_m(b.s_Mv, qacc);
     T c = 0;
     OX_NVLOOP
@@ -1692,9 +1908,20 @@ struct Env {
       T v = -at(b.efc_aref, r);
       OX_NVLOOP
       for (int i = 0; i < nv; i++) v += at(b.efc_J, r * nv + i) * at(qacc, i);
+      if (ell_) at(b.s_Jv, r) = v;   // elliptic contacts need all their rows at once (s_Jv is free before the first line search)
+      if (ell_ && r >= nfe_ && at(b.efc_floss, r) < 0) continue;
       if (r >= ne_ && r < nfe_ && ox_abs(v) * at(b.efc_D, r) >= at(b.efc_floss, r)) c += at(b.efc_floss, r) * (ox_abs(v) - (T)0.5 * at(b.efc_floss, r) / at(b.efc_D, r));
       else if (v < 0 || r < nfe_) c += (T)0.5 * at(b.efc_D, r) * v * v;
     }
+    if (ell_)
+      for_each_contact([&](int, int pp, int ea, int dim) {
+        if (dim == 1) return;
+        T x[6], D[6], ck;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { if (j >= dim) break; x[j] = at(b.s_Jv, ea + j); D[j] = at(b.efc_D, ea + j); }
+        elliptic_cost(pp, dim, D, x, &ck, (T*)nullptr, (T*)nullptr);
+        c += ck;
+      });
     return c;
   }
 
@@ -2138,7 +2365,10 @@ struct Env {
       const int dim = m.pair_dim(p);
       T lf[6] = {0, 0, 0, 0, 0, 0};   // contact-frame force (normal, tangents) and torque (torsion, rolling)
       if (dim == 1) lf[0] = at(b.efc_force, ea);
-      else {
+      else if (h.cone == OX_CONE_ELLIPTIC) {   // the rows ARE the contact-frame components
+#pragma unroll
+        for (int k = 0; k < 6; k++) { if (k >= dim) break; lf[k] = at(b.efc_force, ea + k); }
+      } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) {
           if (k >= dim - 1) break;
@@ -2318,8 +2548,8 @@ struct Env {
             const int ea = ati(b.con_efcadr, c);
             if (ea < 0) return;
             const int dim = m.pair_dim(p);
-            T fn = at(b.efc_force, ea);                                   // frictionless: the row force; pyramid: sum over the edges
-            if (dim > 1) {
+            T fn = at(b.efc_force, ea);                                   // frictionless / elliptic: the (first) row force; pyramid: sum over the edges
+            if (dim > 1 && h.cone != OX_CONE_ELLIPTIC) {
 #pragma unroll
               for (int r = 1; r < 10; r++) { if (r >= 2 * (dim - 1)) break; fn += at(b.efc_force, ea + r); }
             }

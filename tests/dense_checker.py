@@ -83,7 +83,7 @@ class DenseModel:
 
     def __init__(self, model):
         self.m = model
-        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "nmocap", "neq", "nsensor", "nsensordata", "ntendon"):
+        for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "cone", "nmocap", "neq", "nsensor", "nsensordata", "ntendon"):
             setattr(self, k, int(getattr(model, k)))
         for k in ("timestep", "impratio"):
             setattr(self, k, float(getattr(model, k)))
@@ -559,6 +559,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     """Rows (J, D, aref) and ne = number of leading equality rows (quadratic on both sides)."""
     J, D, aref = [], [], []
     dm._friction_pairs = []                                              # (row of edge +, row of edge -) of every pyramidal friction direction
+    dm._ell = []                                                         # elliptic contacts: (first row, dim, mu, friction[:dim-1])
     cart = dm._row_cart = []                                             # per row: (body+, point+, body-, point-, direction) of the Cartesian force it is, or None
     if dm.dis("constraint"):
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
@@ -647,6 +648,23 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
         if prm["dim"] == 1:
             a, R = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, Jd[0] @ qvel)
             J.append(Jd[0]); D.append(1 / R); aref.append(a); cart.append((b2, c["pos"], b1, c["pos"], c["frame"][0]))
+        elif dm.cone == 1:                                               # elliptic cone: rows are the contact-frame components themselves
+            dim = prm["dim"]
+            Jw = c["frame"] @ (kin.JW[b2] - kin.JW[b1])
+            comp = [Jd[0], Jd[1], Jd[2], Jw[0], Jw[1], Jw[2]][:dim]
+            mu = prm["friction"][0] * np.sqrt(1 / dm.impratio)
+            a0_, Rn = row_params(dm, prm["solref"], prm["solimp"], c["dist"], incl, tran, comp[0] @ qvel)
+            dm._ell.append((len(J), dim, mu, np.array(prm["friction"][:dim - 1])))
+            zero = np.zeros(3)
+            for k in range(dim):
+                if k == 0:
+                    a_k, D_k = a0_, 1 / Rn
+                else:                                                    # friction rows: no position term, D_k = D_n f_k^2 / mu^2
+                    a_k, _ = row_params(dm, prm["solref"], prm["solimp"], 0.0, 0.0, tran, comp[k] @ qvel)
+                    D_k = prm["friction"][k - 1] ** 2 / (Rn * mu * mu)
+                lin = c["frame"][k] if k < 3 else zero
+                tor = c["frame"][k - 3] if k >= 3 else zero
+                J.append(comp[k]); D.append(D_k); aref.append(a_k); cart.append((b2, c["pos"], b1, c["pos"], lin, tor))
         else:
             dim = prm["dim"]
             assert dim in (3, 4, 6)
@@ -672,6 +690,88 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
     if not J:
         return np.zeros((0, dm.nv)), np.zeros(0), np.zeros(0), 0
     return np.array(J), np.array(D), np.array(aref), ne
+
+
+def solve_qacc_autodiff(M, qfrc_smooth, J, D, aref, ne, floss, ell):
+    """Elliptic cones: the objective is written down once (quadratic gauss term + row penalties + the three-zone cone cost of
+    every elliptic contact) and torch differentiates it - gradient and Hessian by autograd, damped Newton on top. The product and
+    the oracle use hand-derived cone Hessians; nothing of that derivation is shared here."""
+    n, nf = J.shape[0], len(floss)
+    Mt, Jt, Dt, at_ = _T(M), _T(J), _T(D), _T(aref)
+    a0 = np.linalg.solve(M, qfrc_smooth)
+    a0t = _T(a0)
+    inell = np.zeros(n, bool)
+    for r0, dim, _, _ in ell:
+        inell[r0:r0 + dim] = True
+    two_sided = _T((np.arange(n) < ne + nf).astype(float))
+    fl = np.zeros(n)
+    fl[ne:ne + nf] = floss
+    plain = _T((~inell).astype(float))
+
+    def objective(a):
+        x = Jt @ a - at_
+        c = 0.5 * (a - a0t) @ Mt @ (a - a0t)
+        quad = torch.where(two_sided > 0, x, torch.clamp(x, max=0.0))
+        rowc = 0.5 * Dt * quad ** 2
+        if nf:
+            flt, band = _T(fl), _T(np.where(fl > 0, fl / D, np.inf))
+            rowc = torch.where(torch.abs(x) >= band, flt * (torch.abs(x) - 0.5 * flt / Dt), rowc)
+        c = c + torch.sum(rowc * plain)
+        for r0, dim, mu, fri in ell:
+            xc = x[r0:r0 + dim]
+            N = xc[0] * mu
+            U = xc[1:] * _T(fri)
+            Tn = torch.sqrt(torch.sum(U * U))
+            if N >= mu * Tn:
+                continue
+            if mu * N + Tn <= 0:
+                c = c + 0.5 * torch.sum(Dt[r0:r0 + dim] * xc ** 2)
+            else:
+                c = c + 0.5 * Dt[r0] / (mu * mu * (1 + mu * mu)) * (N - mu * Tn) ** 2
+        return c
+
+    a = _T(a0.copy())
+    for _ in range(200):
+        a = a.detach().requires_grad_(True)
+        c = objective(a)
+        g, = torch.autograd.grad(c, a, create_graph=True)
+        if float(torch.linalg.norm(g)) <= 1e-13 * max(1.0, float(np.linalg.norm(M @ a0))):
+            break
+        H = torch.stack([torch.autograd.grad(g[i], a, retain_graph=True)[0] for i in range(len(a))])
+        step = -torch.linalg.solve(H.detach() + 1e-300 * torch.eye(len(a)), g.detach())
+        c0, t, gs = float(c), 1.0, float(g.detach() @ step)
+        while float(objective((a + t * step).detach())) > c0 + 1e-4 * t * gs and t > 1e-12:
+            t *= 0.5
+        if t <= 1e-12:
+            break
+        a = (a + t * step).detach()
+    # per-row forces = -d(penalty)/dx at the solution, again by autograd
+    aa = a.detach().numpy()
+    xv = (J @ aa - aref)
+    xt = _T(xv).requires_grad_(True)
+    quad = torch.where(two_sided > 0, xt, torch.clamp(xt, max=0.0))
+    rowc = 0.5 * Dt * quad ** 2
+    if nf:
+        flt, band = _T(fl), _T(np.where(fl > 0, fl / D, np.inf))
+        rowc = torch.where(torch.abs(xt) >= band, flt * (torch.abs(xt) - 0.5 * flt / Dt), rowc)
+    pc = torch.sum(rowc * plain)
+    for r0, dim, mu, fri in ell:
+        xc = xt[r0:r0 + dim]
+        N = xc[0] * mu
+        U = xc[1:] * _T(fri)
+        Tn = torch.sqrt(torch.sum(U * U))
+        if N >= mu * Tn:
+            continue
+        if mu * N + Tn <= 0:
+            pc = pc + 0.5 * torch.sum(Dt[r0:r0 + dim] * xc ** 2)
+        else:
+            pc = pc + 0.5 * Dt[r0] / (mu * mu * (1 + mu * mu)) * (N - mu * Tn) ** 2
+    force = np.zeros(n)
+    if pc.requires_grad:
+        gx, = torch.autograd.grad(pc, xt, allow_unused=True)
+        if gx is not None:
+            force = -gx.numpy()
+    return aa, force
 
 
 def solve_qacc(M, qfrc_smooth, J, D, aref, ne=0, floss=()):
@@ -853,7 +953,10 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     if solver == 0:                                                      # PGS (+ noslip)
         qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, np.zeros(dm.nv) if warmstart is None else np.asarray(warmstart, float), True)
     else:
-        qacc, force = solve_qacc(M, f, J, D, aref, ne, dm._floss)
+        if dm._ell:
+            qacc, force = solve_qacc_autodiff(M, f, J, D, aref, ne, dm._floss, dm._ell)
+        else:
+            qacc, force = solve_qacc(M, f, J, D, aref, ne, dm._floss)
         if noslip and len(force):
             qacc, force, _ = solve_dual(dm, M, f, J, D, aref, ne, force.copy(), False)
     ft = force_torque_sensors(dm, kin, qacc, force, xfrc_applied) if dm.nsensor else {}

@@ -123,7 +123,7 @@ def test_error_convention():
         ox.Model.from_xml_string('<mujoco><worldbody><body><geom size="0.1" bogus="1"/></body></worldbody></mujoco>')
     with pytest.raises(ox.MujocoError):
         ox.Model.from_xml("/nonexistent/model.xml")
-    for bad in ['<mujoco><option cone="elliptic"/><worldbody/></mujoco>',
+    for bad in ['<mujoco><option cone="elliptic" solver="PGS"/><worldbody/></mujoco>',
                 '<mujoco><worldbody><body><joint range="1 -1"/><geom size="0.1"/></body></worldbody></mujoco>',
                 '<mujoco><worldbody><body><joint/></body></worldbody></mujoco>',                       # massless moving body
                 '<mujoco><worldbody><body><freejoint/><geom type="box" size=".1 .1 .1"/></body><body><freejoint/>'

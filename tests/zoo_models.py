@@ -403,5 +403,12 @@ ZOO_K = """
 ZOO_L = ZOO_K.replace('model="zoo_k"', 'model="zoo_l"').replace('<option timestep="0.004" tolerance="1e-13"/>',
                                                               '<option timestep="0.004" solver="PGS" iterations="80" tolerance="1e-12" noslip_iterations="3" noslip_tolerance="1e-9"/>')
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L}
+# N3: elliptic friction cones (Newton here, CG in zoo_n): condim 3, 4 and 6 contacts in the same problem, sliding, sticking and
+# spinning bodies, force / torque / touch sensors reading the cone's force directly
+ZOO_M = ZOO_J.replace('model="zoo_j"', 'model="zoo_m"').replace('<option timestep="0.003" tolerance="1e-13" impratio="3"/>',
+                                                              '<option timestep="0.003" tolerance="1e-13" impratio="3" cone="elliptic"/>')
+ZOO_N = HOPPER.replace('model="hopper_user"', 'model="zoo_n"').replace('<option timestep="0.004"/>',
+                                                                     '<option timestep="0.004" cone="elliptic" solver="CG" tolerance="1e-12" iterations="300"/>')
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N}
 NOCONTACT = {"zoo_d": ZOO_D}
