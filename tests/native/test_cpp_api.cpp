@@ -17,7 +17,7 @@ int main() {
   if (!m.object_id<OX_OBJ_JOINT>("hinge") || m.object_id<OX_OBJ_JOINT>("nope")) return 2;
   if (m.object_name(obj::Actuator{0}) != "torque") return 3;
   try { Model::from_xml_string("<mujoco><worldbody>"); return 4; } catch (const Error& e) { if (e.kind != Error::Kind::Mujoco) return 5; }
-  try { Model::from_xml_string("<mujoco><option cone=\"elliptic\"/></mujoco>"); return 6; } catch (const Error& e) { if (e.kind != Error::Kind::Mjs) return 7; }
+  try { Model::from_xml_string("<mujoco><option integrator=\"implicit\"/></mujoco>"); return 6; } catch (const Error& e) { if (e.kind != Error::Kind::Mjs) return 7; }
   try {
     Physics p = Physics::from_xml_string(kPendulum);
     auto hinge = *p.object_id<OX_OBJ_JOINT>("hinge");
