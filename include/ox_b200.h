@@ -65,7 +65,7 @@ enum { OX_INT_EULER = 0, OX_INT_RK4 = 1, OX_INT_IMPLICIT = 2 /* refused by the c
 /* mjtDyn subset: activation dynamics of stateful actuators (act, src/physics.rs:96-102) */
 enum { OX_DYN_NONE = 0, OX_DYN_INTEGRATOR = 1, OX_DYN_FILTER = 2, OX_DYN_FILTEREXACT = 3 };
 /* mjtEq subset: equality constraints */
-enum { OX_EQ_CONNECT = 0, OX_EQ_WELD = 1 /* refused */, OX_EQ_JOINT = 2 };
+enum { OX_EQ_CONNECT = 0, OX_EQ_WELD = 1, OX_EQ_JOINT = 2 };
 enum { OX_SOL_PGS = 0, OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
 enum { OX_CONE_PYRAMIDAL = 0, OX_CONE_ELLIPTIC = 1 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };

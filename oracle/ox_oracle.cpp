@@ -606,6 +606,21 @@ void collision(const Model* m, Data* d) {
 }
 
 // ---------------------------------------------------------------- A.6 constraint assembly
+// weld orientation rows: residual[3] = ts * imag(conj(q2) q1 qrel) and the 3x3 map G with d residual / dt = G (w1 - w2):
+// column c of G = ts/2 * imag(conj(q2) [0, e_c] q1 qrel)
+void weldRotMap(const double* q1, const double* q2, const double* qrel, double ts, double* G, double* residual) {
+  double quat[4], q2c[4] = {q2[0], -q2[1], -q2[2], -q2[3]}, e[4], t1[4], t2[4];
+  mulQuat(quat, q1, qrel);
+  mulQuat(e, q2c, quat);
+  for (int k = 0; k < 3; k++) residual[k] = ts * e[1 + k];
+  for (int c = 0; c < 3; c++) {
+    double ax[4] = {0, 0, 0, 0};
+    ax[1 + c] = 1;
+    mulQuat(t1, q2c, ax);
+    mulQuat(t2, t1, quat);
+    for (int k = 0; k < 3; k++) G[3 * k + c] = 0.5 * ts * t2[1 + k];
+  }
+}
 // translational Jacobian of a world point attached to `body` (mj_jac, jacp rows only), accumulated with sign
 void addJacP(const Model* m, const Data* d, int body, const double* point, double sign, double* jacp /*3 x nv*/) {
   int nv = m->nv;
@@ -702,7 +717,7 @@ void makeConstraint(const Model* m, Data* d) {
     for (int i = 0; i < m->neq; i++) {
       if (d->eq_active[i] == 0) continue;
       const double* data = m->eq_data + 11 * i;
-      if (m->eq_type[i] == OX_EQ_CONNECT) {
+      if (m->eq_type[i] == OX_EQ_CONNECT || m->eq_type[i] == OX_EQ_WELD) {
         // anchors of the two bodies in world coordinates must coincide: residual p1 - p2, Jacobian Jp(b1, p1) - Jp(b2, p2)
         int b1 = m->eq_obj1id[i], b2 = m->eq_obj2id[i];
         double p1[3], p2[3], w[3];
@@ -716,6 +731,21 @@ void makeConstraint(const Model* m, Data* d) {
         double diag = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
         for (int k = 0; k < 3; k++)
           addRow(m, d, &jacp[(size_t)k * nv], p1[k] - p2[k], 0.0, diag, m->eq_solref + 2 * i, m->eq_solimp + 5 * i, 3, i);
+        if (m->eq_type[i] == OX_EQ_WELD) {
+          // orientation: e = conj(q2) (q1 q_rel) is the identity when body2 sits at its welded orientation; residual =
+          // torquescale * imag(e); d/dt imag(e) = 1/2 imag(conj(q2) [0, w1 - w2] q1 q_rel), linear in the relative angular velocity
+          double G[9];
+          weldRotMap(&d->xquat[4 * b1], &d->xquat[4 * b2], data + 6, data[10], G, jrow.data() /*scratch: residual in [0..2]*/);
+          const double res[3] = {jrow[0], jrow[1], jrow[2]};
+          std::vector<double> jacr(3 * nv, 0.0);
+          addJacR(m, d, b1, +1, jacr.data());
+          addJacR(m, d, b2, -1, jacr.data());
+          const double rdiag = m->body_invweight0[2 * b1 + 1] + m->body_invweight0[2 * b2 + 1];
+          for (int k = 0; k < 3; k++) {
+            for (int c = 0; c < nv; c++) jrow[c] = G[3 * k] * jacr[c] + G[3 * k + 1] * jacr[nv + c] + G[3 * k + 2] * jacr[2 * nv + c];
+            addRow(m, d, jrow.data(), res[k], 0.0, rdiag, m->eq_solref + 2 * i, m->eq_solimp + 5 * i, 3, i);
+          }
+        }
       } else {
         // joint coupling: q1 - q1_0 = c0 + c1 dq2 + ... + c4 dq2^4 with dq2 = q2 - q2_0 (only c0 without a second joint)
         int j1 = m->eq_obj1id[i], j2 = m->eq_obj2id[i];
@@ -1631,7 +1661,7 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
   }
   // connect equalities: the three row forces are a world-frame force on body1 at its anchor and the opposite on body2 at its own
   for (int r = 0; r + 2 < d->ne; r++) {
-    if (d->efc_type[r] != 3 || m->eq_type[d->efc_id[r]] != OX_EQ_CONNECT) continue;
+    if (d->efc_type[r] != 3 || m->eq_type[d->efc_id[r]] == OX_EQ_JOINT) continue;
     const int i = d->efc_id[r], b1 = m->eq_obj1id[i], b2 = m->eq_obj2id[i];
     const double* data = m->eq_data + 11 * i;
     double p1[3], p2[3], w[3];
@@ -1642,6 +1672,14 @@ void rnePostConstraint(const Model* m, const Data* d, const std::vector<double>&
     addExtForce(m, d, ext, b1, p1, &d->efc_force[r], nullptr, +1.0);
     addExtForce(m, d, ext, b2, p2, &d->efc_force[r], nullptr, -1.0);
     r += 2;
+    if (m->eq_type[i] == OX_EQ_WELD) {   // the three orientation rows are a torque pair: tau = G' f on body1, -tau on body2
+      double G[9], res[3], tau[3], zero[3] = {0, 0, 0};
+      weldRotMap(&d->xquat[4 * b1], &d->xquat[4 * b2], data + 6, data[10], G, res);
+      for (int c = 0; c < 3; c++) tau[c] = G[c] * d->efc_force[r + 1] + G[3 + c] * d->efc_force[r + 2] + G[6 + c] * d->efc_force[r + 3];
+      addExtForce(m, d, ext, b1, p1, zero, tau, +1.0);
+      addExtForce(m, d, ext, b2, p2, zero, tau, -1.0);
+      r += 3;
+    }
   }
   cfrc_int.assign(6 * nb, 0.0);
   for (int b = 1; b < nb; b++) {

@@ -76,7 +76,7 @@ const std::map<std::string, std::set<std::string>>& schema() {
       {"tendon_fixed", {"name", "class", "group", "limited", "range", "solreflimit", "solimplimit", "solreffriction", "solimpfriction", "margin",
                         "frictionloss", "springlength", "stiffness", "damping", "user", "width", "material", "rgba"}},
       {"tendon_joint", {"joint", "coef"}},
-      {"equality_common", {"name", "class", "active", "solref", "solimp", "body1", "body2", "anchor", "joint1", "joint2", "polycoef"}},
+      {"equality_common", {"name", "class", "active", "solref", "solimp", "body1", "body2", "anchor", "joint1", "joint2", "polycoef", "relpose", "torquescale"}},
       {"sensor_common", {"name", "joint", "actuator", "site", "body", "tendon", "objtype", "objname", "reftype", "refname", "cutoff",
                          "noise", "user"}},
   };
@@ -1406,7 +1406,7 @@ ox_model* compile_mjcf(const std::string& xml) {
     for (auto& ch : root->children)
       if (ch->name == "equality")
         for (auto& e : ch->children) {
-          if (e->name != "connect" && e->name != "joint") cfail("equality <" + e->name + "> is outside the supported subset (connect, joint)");
+          if (e->name != "connect" && e->name != "joint" && e->name != "weld") cfail("equality <" + e->name + "> is outside the supported subset (connect, weld, joint)");
           check_attrs(*e, "equality_common");
           Attrs a = merged(B.c, *e, "equality", "");
           const std::string ename = a.str_or("name", "");
@@ -1428,6 +1428,35 @@ ox_model* compile_mjcf(const std::string& xml) {
             for (int k = 0; k < 3; k++) d2[k] = xpos[3 * o1 + k] + w[k] - xpos[3 * o2 + k];
             hm::rotvec(data + 3, d2, q2c);
             eq_rows += 3;
+          } else if (e->name == "weld") {
+            // weld: body2 keeps a fixed pose relative to body1. data = [weld point in body1's frame, the same point in body2's frame
+            // (MJCF anchor), relative orientation q_rel (target q2 = q1 * q_rel), torquescale]. relpose all zero / absent = the pose at qpos0.
+            type = OX_EQ_WELD;
+            if (!a.has("body1")) pfail(*e, "weld requires body1");
+            o1 = find_name(nm[OX_OBJ_BODY], a.str("body1"));
+            if (o1 < 0) cfail("equality '" + ename + "': unknown body '" + a.str("body1") + "'");
+            o2 = 0;
+            if (a.has("body2")) { o2 = find_name(nm[OX_OBJ_BODY], a.str("body2")); if (o2 < 0) cfail("equality '" + ename + "': unknown body '" + a.str("body2") + "'"); }
+            double relpose[7] = {0, 0, 0, 0, 0, 0, 0}, anchor2[3] = {0, 0, 0}, qrel[4], rpos[3];
+            a.vec("relpose", relpose, 7);
+            a.vec("anchor", anchor2, 3);
+            const double* q1 = &xquat[4 * o1];
+            const double q1c[4] = {q1[0], -q1[1], -q1[2], -q1[3]};
+            if (relpose[3] == 0 && relpose[4] == 0 && relpose[5] == 0 && relpose[6] == 0) {
+              hm::mulquat(qrel, q1c, &xquat[4 * o2]);
+              double dpos[3] = {xpos[3 * o2] - xpos[3 * o1], xpos[3 * o2 + 1] - xpos[3 * o1 + 1], xpos[3 * o2 + 2] - xpos[3 * o1 + 2]};
+              hm::rotvec(rpos, dpos, q1c);
+            } else {
+              for (int k = 0; k < 4; k++) qrel[k] = relpose[3 + k];
+              for (int k = 0; k < 3; k++) rpos[k] = relpose[k];
+            }
+            hm::normalize4(qrel);
+            double w[3];
+            hm::rotvec(w, anchor2, qrel);
+            for (int k = 0; k < 3; k++) { data[k] = rpos[k] + w[k]; data[3 + k] = anchor2[k]; }
+            for (int k = 0; k < 4; k++) data[6 + k] = qrel[k];
+            data[10] = a.num("torquescale", 1.0);
+            eq_rows += 6;
           } else {
             type = OX_EQ_JOINT;
             if (!a.has("joint1")) pfail(*e, "joint equality requires joint1");

@@ -1490,7 +1490,27 @@ struct Env {
   // quartic polynomial of q2 (1 row). pos = residual, margin = 0.
   OX_HD int equality_count(int i) const {
     if (!(at(b.eq_active, i) != 0)) return 0;
-    return m.eq_type(i) == OX_EQ_CONNECT ? 3 : 1;
+    return m.eq_type(i) == OX_EQ_CONNECT ? 3 : (m.eq_type(i) == OX_EQ_WELD ? 6 : 1);
+  }
+  // weld orientation rows: residual = ts * imag(conj(q2) q1 qrel); G (3x3, row-major) maps the relative angular velocity w1 - w2 to
+  // its time derivative: column c = ts/2 * imag(conj(q2) [0, e_c] q1 qrel)
+  OX_HD void weld_rot_map(int i, int b1, int b2, T* G, T* residual) const {
+    T q1[4], q2[4], qrel[4], quat[4], e[4], t1[4], t2[4];
+    ld<4>(q1, b.xquat, 4 * b1);
+    ld<4>(q2, b.xquat, 4 * b2);
+    OX_LDM(4, qrel, eq_data, 11 * i + 6);
+    const T ts = m.eq_data(11 * i + 10);
+    const T q2c[4] = {q2[0], -q2[1], -q2[2], -q2[3]};
+    mul_quat(quat, q1, qrel);
+    mul_quat(e, q2c, quat);
+    residual[0] = ts * e[1]; residual[1] = ts * e[2]; residual[2] = ts * e[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const T ax[4] = {0, c == 0 ? (T)1 : (T)0, c == 1 ? (T)1 : (T)0, c == 2 ? (T)1 : (T)0};
+      mul_quat(t1, q2c, ax);
+      mul_quat(t2, t1, quat);
+      G[c] = (T)0.5 * ts * t2[1]; G[3 + c] = (T)0.5 * ts * t2[2]; G[6 + c] = (T)0.5 * ts * t2[3];
+    }
   }
   OX_HD void eq_row_finish(int i, int r, T pos, T diag) const {
     const int nv = m.h().nv;
@@ -1506,7 +1526,7 @@ struct Env {
   OX_HD void equality_rows(int i, int& nefc) const {
     const int nv = m.h().nv;
     if (!(at(b.eq_active, i) != 0)) return;
-    if (m.eq_type(i) == OX_EQ_CONNECT) {
+    if (m.eq_type(i) == OX_EQ_CONNECT || m.eq_type(i) == OX_EQ_WELD) {
       const int b1 = m.eq_obj1id(i), b2 = m.eq_obj2id(i);
       T p[2][3];
       const int bodies[2] = {b1, b2};
@@ -1544,6 +1564,31 @@ struct Env {
       const T diag = m.body_invweight0(2 * b1) + m.body_invweight0(2 * b2);
       OX_MLOOP
       for (int k = 0; k < 3; k++) eq_row_finish(i, r0 + k, p[0][k] - p[1][k], diag);
+      if (m.eq_type(i) == OX_EQ_WELD) {   // three orientation rows: J = G (jacr(body1) - jacr(body2))
+        T G[9], res[3];
+        weld_rot_map(i, b1, b2, G, res);
+        const int q0 = nefc;
+        nefc += 3;
+        OX_MLOOP
+        for (int k = 0; k < 3 * nv; k++) at(b.efc_J, q0 * nv + k) = 0;
+        OX_MLOOP
+        for (int s = 0; s < 2; s++) {
+          const T sign = s == 0 ? (T)1 : (T)-1;
+          const int body = m.body_weldid(bodies[s]);
+          if (!body) continue;
+          const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+          OX_MLOOP
+          for (int d_ = 0, dof = last_; d_ < m.dof_depth(last_); d_++, dof = m.dof_parentid(dof)) {
+            T cd[6];
+            ld<6>(cd, b.cdof, 6 * dof);
+            OX_MLOOP
+            for (int k = 0; k < 3; k++) at(b.efc_J, (q0 + k) * nv + dof) += sign * (G[3 * k] * cd[0] + G[3 * k + 1] * cd[1] + G[3 * k + 2] * cd[2]);
+          }
+        }
+        const T rdiag = m.body_invweight0(2 * b1 + 1) + m.body_invweight0(2 * b2 + 1);
+        OX_MLOOP
+        for (int k = 0; k < 3; k++) eq_row_finish(i, q0 + k, res[k], rdiag);
+      }
     } else {
       const int j1 = m.eq_obj1id(i), j2 = m.eq_obj2id(i);
       const int d1 = m.jnt_dofadr(j1), q1 = m.jnt_qposadr(j1);
@@ -2407,7 +2452,7 @@ struct Env {
       OX_MLOOP
       for (int i = 0; i < h.neq; i++) {
         if (!(at(b.eq_active, i) != 0)) continue;
-        if (m.eq_type(i) != OX_EQ_CONNECT) { r += 1; continue; }
+        if (m.eq_type(i) == OX_EQ_JOINT) { r += 1; continue; }
         T f[3] = {at(b.efc_force, r), at(b.efc_force, r + 1), at(b.efc_force, r + 2)};
         r += 3;
         const int bodies[2] = {m.eq_obj1id(i), m.eq_obj2id(i)};
@@ -2420,6 +2465,20 @@ struct Env {
           mat_vec3(w, mat, a);
           pt[0] = xp[0] + w[0]; pt[1] = xp[1] + w[1]; pt[2] = xp[2] + w[2];
           sub_ext_force(bodies[s], pt, f, nullptr, s == 0 ? (T)1 : (T)-1);
+        }
+        if (m.eq_type(i) == OX_EQ_WELD) {   // the three orientation rows are a torque pair: tau = G' f on body1, -tau on body2
+          T G[9], res[3], tau[3], xp[3];
+          weld_rot_map(i, bodies[0], bodies[1], G, res);
+          const T fr[3] = {at(b.efc_force, r), at(b.efc_force, r + 1), at(b.efc_force, r + 2)};
+          r += 3;
+          const T zero[3] = {0, 0, 0};
+          OX_MLOOP
+          for (int c = 0; c < 3; c++) tau[c] = G[c] * fr[0] + G[3 + c] * fr[1] + G[6 + c] * fr[2];
+          OX_MLOOP
+          for (int s = 0; s < 2; s++) {
+            ld<3>(xp, b.xpos, 3 * bodies[s]);
+            sub_ext_force(bodies[s], xp, zero, tau, s == 0 ? (T)1 : (T)-1);
+          }
         }
       }
     }

@@ -65,6 +65,25 @@ def quat2mat(q):
     return quat2mat_t(_T(q)).numpy()
 
 
+def mat2quat_pos(R):
+    """unit quaternion (w, x, y, z) of a rotation matrix, w >= 0 branch; the largest diagonal term picks the pivot"""
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        s = 2 * np.sqrt(tr + 1.0)
+        q = np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    elif R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]:
+        s = 2 * np.sqrt(1.0 + R[0, 0] - R[1, 1] - R[2, 2])
+        q = np.array([(R[2, 1] - R[1, 2]) / s, 0.25 * s, (R[0, 1] + R[1, 0]) / s, (R[0, 2] + R[2, 0]) / s])
+    elif R[1, 1] > R[2, 2]:
+        s = 2 * np.sqrt(1.0 + R[1, 1] - R[0, 0] - R[2, 2])
+        q = np.array([(R[0, 2] - R[2, 0]) / s, (R[0, 1] + R[1, 0]) / s, 0.25 * s, (R[1, 2] + R[2, 1]) / s])
+    else:
+        s = 2 * np.sqrt(1.0 + R[2, 2] - R[0, 0] - R[1, 1])
+        q = np.array([(R[1, 0] - R[0, 1]) / s, (R[0, 2] + R[2, 0]) / s, (R[1, 2] + R[2, 1]) / s, 0.25 * s])
+    q = q / np.linalg.norm(q)
+    return q if q[0] >= 0 else -q
+
+
 class DenseModel:
     """numpy copies of the compiled tables (read through the Python Model mirror)."""
     INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
@@ -568,7 +587,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
             if eq_active is not None and not eq_active[i]:
                 continue
             data, sr, si = dm.eq_data[11 * i:11 * i + 11], dm.eq_solref[2 * i:2 * i + 2], dm.eq_solimp[5 * i:5 * i + 5]
-            if int(dm.eq_type[i]) == 0:                                  # connect: the two anchors coincide
+            if int(dm.eq_type[i]) in (0, 1):                             # connect / weld: the two anchors coincide
                 b1, b2 = int(dm.eq_obj1id[i]), int(dm.eq_obj2id[i])
                 p1, p2 = kin.P[b1] + kin.R[b1] @ data[0:3], kin.P[b2] + kin.R[b2] @ data[3:6]
                 Jd = kin.point_jac(b1, p1) - kin.point_jac(b2, p2)
@@ -576,6 +595,22 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
                 for k in range(3):
                     a, R = row_params(dm, sr, si, p1[k] - p2[k], 0.0, diag, Jd[k] @ qvel)
                     J.append(Jd[k]); D.append(1 / R); aref.append(a); cart.append((b1, p1, b2, p2, np.eye(3)[k]))
+                if int(dm.eq_type[i]) == 1:                              # weld: orientation error e = R2' R1 Rrel, residual = ts * imag(quat(e))
+                    Rrel, ts = quat2mat(data[6:10]), data[10]
+                    qerr = lambda R1, R2: mat2quat_pos(R2.T @ R1 @ Rrel)[1:] * ts
+                    res = qerr(kin.R[b1], kin.R[b2])
+                    # d residual / dt for a relative angular velocity w (world frame): rotate body 1 by a small w dt and difference it
+                    # numerically? no - exact: e' = R2' hat(w1 - w2) R1 Rrel; imag(quat)' = 1/2 (E_w + trace-part) ... use the quaternion form
+                    q1, q2 = mat2quat_pos(kin.R[b1]), mat2quat_pos(kin.R[b2])
+                    quat = quat_mul(q1, mat2quat_pos(Rrel))
+                    if quat_mul(np.array([q2[0], -q2[1], -q2[2], -q2[3]]), quat)[0] < 0:
+                        quat = -quat                                       # same branch as the residual (w >= 0)
+                    G = np.stack([0.5 * ts * quat_mul(quat_mul(np.array([q2[0], -q2[1], -q2[2], -q2[3]]), np.r_[0.0, np.eye(3)[c]]), quat)[1:] for c in range(3)], axis=1)
+                    Jr = G @ (kin.JW[b1] - kin.JW[b2])
+                    rdiag = dm.body_invweight0[2 * b1 + 1] + dm.body_invweight0[2 * b2 + 1]
+                    for k in range(3):
+                        a, R = row_params(dm, sr, si, res[k], 0.0, rdiag, Jr[k] @ qvel)
+                        J.append(Jr[k]); D.append(1 / R); aref.append(a); cart.append((b1, p1, b2, p2, np.zeros(3), G[k]))
             else:                                                        # joint: q1 follows a quartic polynomial of q2
                 j1, j2 = int(dm.eq_obj1id[i]), int(dm.eq_obj2id[i])
                 q1, d1 = int(dm.jnt_qposadr[j1]), int(dm.jnt_dofadr[j1])

@@ -147,8 +147,8 @@ def test_compiler_tables_and_refusals():
                   [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
     assert np.allclose(R @ np.asarray(m.eq_data[3:6]) + np.asarray(m.body_pos[3 * hand:3 * hand + 3]), [0.7, 0, 1.0], atol=1e-12)
     base = "<mujoco><worldbody><body name='a'><joint name='j' type='hinge'/><geom size='0.1'/><body name='b' pos='0 0 1'><joint name='k' type='ball'/><geom size='0.1'/></body></body></worldbody>{}</mujoco>"
-    with pytest.raises(ox.MjsError, match="weld"):
-        ox.Model.from_xml_string(base.format("<equality><weld body1='a'/></equality>"))
+    with pytest.raises(ox.MjsError, match="flex"):
+        ox.Model.from_xml_string(base.format("<equality><flex flex='f'/></equality>"))
     with pytest.raises(ox.MjsError, match="hinge / slide"):
         ox.Model.from_xml_string(base.format("<equality><joint joint1='k'/></equality>"))
     with pytest.raises(ox.MjsError, match="unknown body"):
@@ -234,3 +234,78 @@ def test_physics_accessors_and_snapshot():
     b.set_state(snap); b.set_step_counter(counter)
     b.step(20); b.sync()
     assert np.array_equal(b.get("qpos"), ref)
+
+
+# ---------------------------------------------------------------------------------------------------- weld
+WELDED = """<mujoco><compiler angle="radian"/><option timestep="0.002" gravity="0 0 0"/><worldbody>
+<body name="target" mocap="true" pos="0 0 1" quat="{q}"/>
+<body name="b" pos="0 0 1"><freejoint/><geom type="box" size="0.1 0.2 0.3" contype="0" conaffinity="0"/></body></worldbody>
+<equality><weld name="w" body1="b" body2="target" torquescale="{ts}"/></equality></mujoco>"""
+
+
+def test_weld_rows_closed_form_and_tracking():
+    """Free box welded to a mocap body. Rows 0-2 are the connect rows; rows 3-5 carry residual = torquescale * imag(conj(q2) q1 qrel)
+    and J = G on the free joint's angular dofs (body axes for a free joint), so at small angles residual ~ torquescale * angle / 2."""
+    ang = 0.2
+    q = f"{np.cos(ang / 2)} 0 {np.sin(ang / 2)} 0"            # target rotated about y; qrel = that relative pose at qpos0
+    m = ox.Model.from_xml_string(WELDED.format(q=q, ts=0.7))
+    assert list(m.eq_type) == [1] and m.nefcmax == 6
+    od = OracleData(m)
+    od.forward()
+    assert od.int("nefc") == 6 and od.int("ne") == 6 and np.allclose(od.field("efc_pos")[:6], 0, atol=1e-15)     # welded at qpos0
+    od.field("mocap_quat")[:] = [1, 0, 0, 0]                  # move the target: the box must now turn by -ang about y
+    od.forward()
+    res = od.field("efc_pos")[3:6]
+    # e = conj(q2) q1 qrel with q1 = q2 = identity: e = qrel, residual = ts * imag(qrel)
+    assert np.allclose(res, 0.7 * np.array([0, np.sin(ang / 2), 0]), atol=1e-14)
+    for _ in range(1500):
+        od.step()
+    qb = od.field("qpos")[3:7]
+    assert np.allclose(qb * np.sign(qb[0]), [np.cos(ang / 2), 0, -np.sin(ang / 2), 0], atol=2e-3)   # orientation follows the mocap body
+    assert np.abs(od.field("qpos")[:3] - [0, 0, 1]).max() < 1e-4
+
+
+def test_weld_host_instantiation_and_refusals():
+    m = ox.Model.from_xml_string(ZOO["zoo_o"])
+    assert list(m.eq_type) == [1, 1, 1] and list(m.eq_active0) == [1, 1, 0]
+    nenv, nsteps = 5, 150
+    qpos, qvel = random_state(m, nenv, seed=89)
+    hb = HostBatch(m, nenv, "f64")
+    hb.set("qpos", qpos); hb.set("qvel", qvel)
+    hb.step(nsteps, True, SEED, 0, 0)
+    for e in range(nenv):
+        od = OracleData(m)
+        od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]
+        for s in range(nsteps):
+            od.fill_ctrl_philox(e, s); od.step()
+        assert od.int("ne") == 12
+        for f in ("qpos", "qvel", "qacc", "sensordata"):
+            assert rel_err(hb.get(f)[e], od.field(f)) <= 1e-8, (f, e)
+    with pytest.raises(ox.MjsError, match="tendon"):
+        ox.Model.from_xml_string("<mujoco><worldbody><body name='a'><joint/><geom size='0.1'/></body></worldbody><equality><tendon tendon1='t'/></equality></mujoco>")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,specialize", [("fused", 0), ("staged", 0), ("coop", 0), ("fused", 2)])
+def test_weld_gpu_vs_oracle(mode, specialize):
+    m = ox.Model.from_xml_string(ZOO["zoo_o"])
+    nenv, nsteps = 64, 100
+    rng = np.random.default_rng(97)
+    qpos, qvel = random_state(m, nenv, seed=97)
+    od0 = OracleData(m)
+    mpos = np.tile(od0.field("mocap_pos"), (nenv, 1)) + rng.uniform(-0.03, 0.03, (nenv, 3))
+    mquat = np.tile(od0.field("mocap_quat"), (nenv, 1)) + rng.normal(0, 0.05, (nenv, 4))
+    b = ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
+    b.set("qpos", qpos); b.set("qvel", qvel); b.set("mocap_pos", mpos); b.set("mocap_quat", mquat); b.ctrl_philox(True, SEED)
+    b.step(nsteps); b.sync()
+    ref = {f: [] for f in ("qpos", "qacc", "sensordata")}
+    for e in range(nenv):
+        od = OracleData(m)
+        od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]; od.field("mocap_pos")[:] = mpos[e]; od.field("mocap_quat")[:] = mquat[e]
+        for s in range(nsteps):
+            od.fill_ctrl_philox(e, s); od.step()
+        for f in ref:
+            ref[f].append(od.field(f).copy())
+    for f in ref:
+        assert rel_err(b.get(f), np.stack(ref[f])) <= 1e-6, f
+    assert int(b.diverged().sum()) == 0

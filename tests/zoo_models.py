@@ -410,5 +410,43 @@ ZOO_M = ZOO_J.replace('model="zoo_j"', 'model="zoo_m"').replace('<option timeste
 ZOO_N = HOPPER.replace('model="hopper_user"', 'model="zoo_n"').replace('<option timestep="0.004"/>',
                                                                      '<option timestep="0.004" cone="elliptic" solver="CG" tolerance="1e-12" iterations="300"/>')
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N}
+# N3: weld equality - a free body welded to a mocap body (the standard mocap drive: position AND orientation), a weld between two
+# moving bodies with an explicit relpose and torquescale, one weld inactive in the model; force / torque sensors read the weld wrench
+ZOO_O = """
+<mujoco model="zoo_o">
+  <compiler angle="radian"/>
+  <option timestep="0.004" tolerance="1e-13"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <body name="hand" mocap="true" pos="0.3 0.1 0.6" quat="0.95 0.1 0.25 0.05"/>
+    <body name="tool" pos="0.3 0.1 0.6" quat="0.95 0.1 0.25 0.05">
+      <freejoint name="toolroot"/>
+      <geom name="tool" type="capsule" fromto="0 0 0 0.25 0 0" size="0.03"/>
+      <site name="grip" pos="0.05 0 0"/>
+      <body name="tip" pos="0.25 0 0">
+        <joint name="wrist" type="hinge" axis="0 0 1" damping="0.05"/>
+        <geom name="tip" type="capsule" fromto="0 0 0 0.12 0 0" size="0.02"/>
+      </body>
+    </body>
+    <body name="base" pos="-0.4 0 0.4">
+      <joint name="b1" type="hinge" axis="0 1 0" damping="0.1"/>
+      <geom name="base" type="capsule" fromto="0 0 0 0 0 -0.3" size="0.03"/>
+      <site name="basesite" pos="0 0 -0.1"/>
+    </body>
+    <body name="rider" pos="-0.4 0.1 0.15">
+      <freejoint name="riderroot"/>
+      <geom name="rider" type="box" size="0.06 0.04 0.03" density="400"/>
+    </body>
+  </worldbody>
+  <equality>
+    <weld name="grasp" body1="tool" body2="hand" solref="0.01 1"/>
+    <weld name="saddle" body1="rider" body2="base" relpose="0 0.1 -0.25 0.98 0 0.2 0" anchor="0 0 -0.25" torquescale="0.5"/>
+    <weld name="spare" body1="tip" active="false"/>
+  </equality>
+  <actuator><motor joint="wrist" gear="0.3"/><motor joint="b1" gear="1.5"/></actuator>
+  <sensor><force site="grip"/><torque site="grip"/><torque site="basesite"/><framequat objtype="body" objname="tool"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O}
 NOCONTACT = {"zoo_d": ZOO_D}
