@@ -42,7 +42,7 @@ def test_oracle_matches_dense_checker_fixtures(name):
     g = load(name)
     m = ox.Model.from_xml_string(XML[name])
     assert (g["nq"], g["nv"]) == (m.nq, m.nv) and len(g["cases"]) >= (64 if m.npair else 16)
-    if m.npair and name != "zoo_o":              # (zoo_o's constrained path is its three welds: every state has 12 equality rows)
+    if m.npair:
         assert g["states_in_contact"] >= 30      # the fixtures really exercise the constrained path
     worst = dict(qpos=0.0, qvel=0.0, qacc=0.0, act=0.0)
     for case in g["cases"]:

@@ -437,6 +437,7 @@ ZOO_O = """
       <freejoint name="riderroot"/>
       <geom name="rider" type="box" size="0.06 0.04 0.03" density="400"/>
     </body>
+    <body name="pebble" pos="0.8 0 0.0495"><freejoint name="pebbleroot"/><geom name="pebble" type="sphere" size="0.05"/></body>
   </worldbody>
   <equality>
     <weld name="grasp" body1="tool" body2="hand" solref="0.01 1"/>
