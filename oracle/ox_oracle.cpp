@@ -494,6 +494,116 @@ int capsuleBox(RawContact* con, double margin, const double* pos1, const double*
   return n;
 }
 
+// box against box. NOT a restatement of mjc_BoxBox (ORACLE_DECISIONS.md #32): separating-axis test over the 6 face normals and
+// the 9 edge-edge cross products; the axis of least penetration decides the contact kind. Face axis: the face of the other box
+// most opposed to the normal is clipped (Sutherland-Hodgman) against the four side planes of the reference face and every vertex
+// of the clipped polygon within the margin of the reference face becomes a contact (up to 8). Edge axis: one contact between the
+// closest points of the two supporting edges. Face axes win ties (an edge axis must be better by a relative 1e-3 of the box size).
+int boxBox(RawContact* con, double margin, const double* pos1, const double* mat1, const double* size1, const double* pos2, const double* mat2,
+           const double* size2) {
+  double A[3][3], B[3][3], dvec[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { A[i][k] = mat1[3 * k + i]; B[i][k] = mat2[3 * k + i]; }   // axis i = column i
+  auto radius = [&](const double (*ax)[3], const double* sz, const double* L) {
+    return sz[0] * std::fabs(dot3(ax[0], L)) + sz[1] * std::fabs(dot3(ax[1], L)) + sz[2] * std::fabs(dot3(ax[2], L));
+  };
+  double bestFace = -1e300, bestEdge = -1e300;
+  int faceIdx = -1, edgeI = -1, edgeJ = -1;
+  for (int f = 0; f < 6; f++) {
+    const double* L = f < 3 ? A[f] : B[f - 3];
+    const double sep = std::fabs(dot3(dvec, L)) - radius(A, size1, L) - radius(B, size2, L);
+    if (sep > margin) return 0;
+    if (sep > bestFace) { bestFace = sep; faceIdx = f; }
+  }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double L[3];
+      cross3(L, A[i], B[j]);
+      const double n = std::sqrt(dot3(L, L));
+      if (n < 1e-6) continue;   // parallel edges: a face axis covers it
+      for (int k = 0; k < 3; k++) L[k] /= n;
+      const double sep = std::fabs(dot3(dvec, L)) - radius(A, size1, L) - radius(B, size2, L);
+      if (sep > margin) return 0;
+      if (sep > bestEdge) { bestEdge = sep; edgeI = i; edgeJ = j; }
+    }
+  const double scale = std::max(std::max(size1[0], size1[1]), std::max(size1[2], std::max(size2[0], std::max(size2[1], size2[2]))));
+  if (edgeI >= 0 && bestEdge > bestFace + 1e-3 * scale) {
+    double L[3];
+    cross3(L, A[edgeI], B[edgeJ]);
+    normalize3(L);
+    if (dot3(L, dvec) < 0) for (double& v : L) v = -v;   // from box 1 to box 2
+    double c1[3] = {pos1[0], pos1[1], pos1[2]}, c2[3] = {pos2[0], pos2[1], pos2[2]};
+    for (int k = 0; k < 3; k++) {
+      if (k != edgeI) { const double sg = dot3(A[k], L) > 0 ? 1.0 : -1.0; for (int c = 0; c < 3; c++) c1[c] += sg * size1[k] * A[k][c]; }
+      if (k != edgeJ) { const double sg = dot3(B[k], L) > 0 ? -1.0 : 1.0; for (int c = 0; c < 3; c++) c2[c] += sg * size2[k] * B[k][c]; }
+    }
+    // closest points of the lines c1 + s A_i, c2 + t B_j, clamped to the edges
+    const double* u = A[edgeI]; const double* v = B[edgeJ];
+    double w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+    const double b = dot3(u, v), dd = dot3(u, w), e = dot3(v, w), den = 1 - b * b;
+    double sA = den > 1e-12 ? (b * e - dd) / den : 0.0, tB = den > 1e-12 ? (e - b * dd) / den : 0.0;
+    sA = clip(sA, -size1[edgeI], size1[edgeI]); tB = clip(tB, -size2[edgeJ], size2[edgeJ]);
+    double pA[3], pB[3];
+    for (int c = 0; c < 3; c++) { pA[c] = c1[c] + sA * u[c]; pB[c] = c2[c] + tB * v[c]; }
+    const double diff[3] = {pB[0] - pA[0], pB[1] - pA[1], pB[2] - pA[2]};
+    con->dist = dot3(diff, L);
+    if (con->dist > margin) return 0;
+    for (int c = 0; c < 3; c++) { con->pos[c] = 0.5 * (pA[c] + pB[c]); con->frame[c] = L[c]; con->frame[3 + c] = 0; }
+    return 1;
+  }
+  // face contact: reference box R (the owner of the axis), incident box I
+  const bool refA = faceIdx < 3;
+  const int ra = refA ? faceIdx : faceIdx - 3;
+  const double (*Rax)[3] = refA ? A : B; const double (*Iax)[3] = refA ? B : A;
+  const double* Rpos = refA ? pos1 : pos2; const double* Ipos = refA ? pos2 : pos1;
+  const double* Rsz = refA ? size1 : size2; const double* Isz = refA ? size2 : size1;
+  double n[3], toI[3] = {Ipos[0] - Rpos[0], Ipos[1] - Rpos[1], Ipos[2] - Rpos[2]};
+  const double sgn = dot3(toI, Rax[ra]) >= 0 ? 1.0 : -1.0;
+  for (int c = 0; c < 3; c++) n[c] = sgn * Rax[ra][c];   // outward normal of the reference face, towards the incident box
+  int ia = 0;
+  double best = -1;
+  for (int k = 0; k < 3; k++) { const double a = std::fabs(dot3(Iax[k], n)); if (a > best) { best = a; ia = k; } }
+  const double isg = dot3(Iax[ia], n) > 0 ? -1.0 : 1.0;   // the incident face looks against n
+  const int iu = (ia + 1) % 3, iv = (ia + 2) % 3;
+  double poly[16][3], tmp[16][3];
+  int np = 4;
+  static const double su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
+  for (int q = 0; q < 4; q++)
+    for (int c = 0; c < 3; c++)
+      poly[q][c] = Ipos[c] + isg * Isz[ia] * Iax[ia][c] + su[q] * Isz[iu] * Iax[iu][c] + sv[q] * Isz[iv] * Iax[iv][c];
+  for (int side = 0; side < 4 && np > 0; side++) {   // clip against the four side planes of the reference face
+    const int ta = (ra + 1 + side / 2) % 3;
+    const double ps = side % 2 ? -1.0 : 1.0;
+    auto inside = [&](const double* pt) {
+      const double rel[3] = {pt[0] - Rpos[0], pt[1] - Rpos[1], pt[2] - Rpos[2]};
+      return Rsz[ta] - ps * dot3(rel, Rax[ta]);   // >= 0 inside
+    };
+    int no = 0;
+    for (int q = 0; q < np; q++) {
+      const double* P = poly[q]; const double* Q = poly[(q + 1) % np];
+      const double dp = inside(P), dq = inside(Q);
+      if (dp >= 0) { for (int c = 0; c < 3; c++) tmp[no][c] = P[c]; no++; }
+      if ((dp >= 0) != (dq >= 0)) { const double t = dp / (dp - dq); for (int c = 0; c < 3; c++) tmp[no][c] = P[c] + t * (Q[c] - P[c]); no++; }
+    }
+    np = no;
+    for (int q = 0; q < np; q++) for (int c = 0; c < 3; c++) poly[q][c] = tmp[q][c];
+  }
+  int cnt = 0;
+  for (int q = 0; q < np && cnt < 8; q++) {
+    const double rel[3] = {poly[q][0] - Rpos[0], poly[q][1] - Rpos[1], poly[q][2] - Rpos[2]};
+    const double depth = dot3(rel, n) - Rsz[ra];
+    if (depth > margin) continue;
+    con[cnt].dist = depth;
+    for (int c = 0; c < 3; c++) {
+      con[cnt].pos[c] = poly[q][c] - 0.5 * depth * n[c];
+      con[cnt].frame[c] = refA ? n[c] : -n[c];   // from box 1 to box 2
+      con[cnt].frame[3 + c] = 0;
+    }
+    cnt++;
+  }
+  return cnt;
+}
+
 int collidePair(const Model* m, const Data* d, int p, RawContact* con) {
   int g1 = m->pair_geom1[p], g2 = m->pair_geom2[p];
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
@@ -538,6 +648,7 @@ int collidePair(const Model* m, const Data* d, int p, RawContact* con) {
     for (int k = 0; k < 3; k++) vec[k] = pos2[k] + axis[k] * x;
     return sphereSphere(con, margin, pos1, size1[0], vec, size2[0]);
   }
+  if (t1 == OX_GEOM_BOX && t2 == OX_GEOM_BOX) return boxBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
   if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_BOX) return sphereBox(con, margin, pos1, size1[0], pos2, mat2, size2);
   if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_BOX) return capsuleBox(con, margin, pos1, mat1, size1, pos2, mat2, size2);
   if (t1 == OX_GEOM_CAPSULE && t2 == OX_GEOM_CAPSULE) {

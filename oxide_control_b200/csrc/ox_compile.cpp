@@ -976,6 +976,7 @@ ox_model* compile_mjcf(const std::string& xml) {
             else if (ta == OX_GEOM_CAPSULE && tb == OX_GEOM_CAPSULE) maxcon = 2;
             else if (ta == OX_GEOM_SPHERE && tb == OX_GEOM_BOX) maxcon = 1;
             else if (ta == OX_GEOM_CAPSULE && tb == OX_GEOM_BOX) maxcon = 2;
+            else if (ta == OX_GEOM_BOX && tb == OX_GEOM_BOX) maxcon = 8;
             else {
               static const char* tn[] = {"plane", "hfield", "sphere", "capsule", "ellipsoid", "cylinder", "box", "mesh"};
               cfail(std::string("collision pair ") + tn[ta] + "-" + tn[tb] + " (geoms '" + G[ga].name + "', '" + G[gb].name +

@@ -991,6 +991,119 @@ struct Env {
     }
     ati(b.ncon, 0) = ncon;
   }
+  // box against box (ORACLE_DECISIONS.md #32; not mjc_BoxBox): separating-axis test over 6 face normals and 9 edge cross products;
+  // face axis -> the opposed face of the other box clipped against the reference face's side planes, every clipped vertex within
+  // the margin is a contact (<= 8); edge axis -> one contact between the closest points of the supporting edges. Faces win ties.
+  OX_HD void box_box(int p, T margin, const T* pos1, const T* size1, const T* pos2, const T* size2, int g1, int g2, int& ncon) const {
+    T A[3][3], B[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) { A[i][k] = at(b.geom_xmat, 9 * g1 + 3 * k + i); B[i][k] = at(b.geom_xmat, 9 * g2 + 3 * k + i); }
+    const T dvec[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+    auto radius = [&](const T (*ax)[3], const T* sz, const T* L) {
+      return sz[0] * ox_abs(dot3(ax[0], L)) + sz[1] * ox_abs(dot3(ax[1], L)) + sz[2] * ox_abs(dot3(ax[2], L));
+    };
+    T bestFace = (T)-1e30, bestEdge = (T)-1e30;
+    int faceIdx = -1, edgeI = -1, edgeJ = -1;
+#pragma unroll 1
+    for (int f = 0; f < 6; f++) {
+      const T* L = f < 3 ? A[f] : B[f - 3];
+      const T sep = ox_abs(dot3(dvec, L)) - radius(A, size1, L) - radius(B, size2, L);
+      if (sep > margin) return;
+      if (sep > bestFace) { bestFace = sep; faceIdx = f; }
+    }
+#pragma unroll 1
+    for (int ij = 0; ij < 9; ij++) {
+      const int i = ij / 3, j = ij % 3;
+      T L[3];
+      cross3(L, A[i], B[j]);
+      const T n = ox_sqrt(dot3(L, L));
+      if (n < (T)1e-6) continue;
+      L[0] /= n; L[1] /= n; L[2] /= n;
+      const T sep = ox_abs(dot3(dvec, L)) - radius(A, size1, L) - radius(B, size2, L);
+      if (sep > margin) return;
+      if (sep > bestEdge) { bestEdge = sep; edgeI = i; edgeJ = j; }
+    }
+    const T scale = ox_max(ox_max(size1[0], size1[1]), ox_max(size1[2], ox_max(size2[0], ox_max(size2[1], size2[2]))));
+    if (edgeI >= 0 && bestEdge > bestFace + (T)1e-3 * scale) {
+      T L[3];
+      cross3(L, A[edgeI], B[edgeJ]);
+      normalize3(L);
+      if (dot3(L, dvec) < 0) { L[0] = -L[0]; L[1] = -L[1]; L[2] = -L[2]; }
+      T c1[3] = {pos1[0], pos1[1], pos1[2]}, c2[3] = {pos2[0], pos2[1], pos2[2]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k != edgeI) { const T sg = dot3(A[k], L) > 0 ? (T)1 : (T)-1; for (int c = 0; c < 3; c++) c1[c] += sg * size1[k] * A[k][c]; }
+        if (k != edgeJ) { const T sg = dot3(B[k], L) > 0 ? (T)-1 : (T)1; for (int c = 0; c < 3; c++) c2[c] += sg * size2[k] * B[k][c]; }
+      }
+      const T* u = A[edgeI]; const T* v = B[edgeJ];
+      const T w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+      const T bb = dot3(u, v), dd = dot3(u, w), e = dot3(v, w), den = 1 - bb * bb;
+      T sA = den > (T)1e-12 ? (bb * e - dd) / den : (T)0, tB = den > (T)1e-12 ? (e - bb * dd) / den : (T)0;
+      sA = ox_clip(sA, -size1[edgeI], size1[edgeI]); tB = ox_clip(tB, -size2[edgeJ], size2[edgeJ]);
+      T pA[3], pB[3], diff[3];
+      for (int c = 0; c < 3; c++) { pA[c] = c1[c] + sA * u[c]; pB[c] = c2[c] + tB * v[c]; diff[c] = pB[c] - pA[c]; }
+      Con cc;
+      cc.dist = dot3(diff, L);
+      if (cc.dist > margin) return;
+      for (int c = 0; c < 3; c++) { cc.pos[c] = (T)0.5 * (pA[c] + pB[c]); cc.frame[c] = L[c]; cc.frame[3 + c] = 0; }
+      emit(cc, p, 0, ncon);
+      return;
+    }
+    const bool refA = faceIdx < 3;
+    const int ra = refA ? faceIdx : faceIdx - 3;
+    const T (*Rax)[3] = refA ? A : B; const T (*Iax)[3] = refA ? B : A;
+    const T* Rpos = refA ? pos1 : pos2; const T* Ipos = refA ? pos2 : pos1;
+    const T* Rsz = refA ? size1 : size2; const T* Isz = refA ? size2 : size1;
+    const T toI[3] = {Ipos[0] - Rpos[0], Ipos[1] - Rpos[1], Ipos[2] - Rpos[2]};
+    const T sgn = dot3(toI, Rax[ra]) >= 0 ? (T)1 : (T)-1;
+    const T n[3] = {sgn * Rax[ra][0], sgn * Rax[ra][1], sgn * Rax[ra][2]};
+    int ia = 0;
+    T best = -1;
+    for (int k = 0; k < 3; k++) { const T a = ox_abs(dot3(Iax[k], n)); if (a > best) { best = a; ia = k; } }
+    const T isg = dot3(Iax[ia], n) > 0 ? (T)-1 : (T)1;
+    const int iu = (ia + 1) % 3, iv = (ia + 2) % 3;
+    T poly[16][3], tmp[16][3];
+    int np = 4;
+    for (int q = 0; q < 4; q++) {
+      const T su = (q == 0 || q == 3) ? (T)1 : (T)-1, sv = q < 2 ? (T)1 : (T)-1;
+      for (int c = 0; c < 3; c++) poly[q][c] = Ipos[c] + isg * Isz[ia] * Iax[ia][c] + su * Isz[iu] * Iax[iu][c] + sv * Isz[iv] * Iax[iv][c];
+    }
+#pragma unroll 1
+    for (int side = 0; side < 4 && np > 0; side++) {
+      const int ta = (ra + 1 + side / 2) % 3;
+      const T ps = side % 2 ? (T)-1 : (T)1;
+      auto inside = [&](const T* pt) {
+        const T rel[3] = {pt[0] - Rpos[0], pt[1] - Rpos[1], pt[2] - Rpos[2]};
+        return Rsz[ta] - ps * dot3(rel, Rax[ta]);
+      };
+      int no = 0;
+      for (int q = 0; q < np; q++) {
+        const T* P = poly[q]; const T* Q = poly[(q + 1) % np];
+        const T dp = inside(P), dq = inside(Q);
+        if (dp >= 0) { for (int c = 0; c < 3; c++) tmp[no][c] = P[c]; no++; }
+        if ((dp >= 0) != (dq >= 0)) { const T t = dp / (dp - dq); for (int c = 0; c < 3; c++) tmp[no][c] = P[c] + t * (Q[c] - P[c]); no++; }
+      }
+      np = no;
+      for (int q = 0; q < np; q++) for (int c = 0; c < 3; c++) poly[q][c] = tmp[q][c];
+    }
+    int cnt = 0;
+    for (int q = 0; q < np && cnt < 8; q++) {
+      const T rel[3] = {poly[q][0] - Rpos[0], poly[q][1] - Rpos[1], poly[q][2] - Rpos[2]};
+      const T depth = dot3(rel, n) - Rsz[ra];
+      if (depth > margin) continue;
+      Con cc;
+      cc.dist = depth;
+      for (int c = 0; c < 3; c++) {
+        cc.pos[c] = poly[q][c] - (T)0.5 * depth * n[c];
+        cc.frame[c] = refA ? n[c] : -n[c];
+        cc.frame[3 + c] = 0;
+      }
+      emit(cc, p, cnt, ncon);
+      cnt++;
+    }
+  }
   // narrowphase of one candidate pair; emits 0..pair_maxcon(p) contacts
   OX_HD void collide_pair(int p, int& ncon) const {
     {
@@ -1010,7 +1123,8 @@ struct Env {
           // so the contact set is unchanged - but the capsule-capsule narrowphase is ~1 k instructions per pair, and for a
           // humanoid's 20 self-collision pairs, almost always far apart, it was 43 % of the PRE kernel's instruction stream.
           const T rb2 = t2 == OX_GEOM_BOX ? ox_sqrt(dot3(size2, size2)) : size2[0] + (t2 == OX_GEOM_CAPSULE ? size2[1] : (T)0);
-          const T rb = size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0) + rb2 + margin;
+          const T rb1 = t1 == OX_GEOM_BOX ? ox_sqrt(dot3(size1, size1)) : size1[0] + (t1 == OX_GEOM_CAPSULE ? size1[1] : (T)0);
+          const T rb = rb1 + rb2 + margin;
           const T dx = pos2[0] - pos1[0], dy = pos2[1] - pos1[1], dz = pos2[2] - pos1[2];
           if (dx * dx + dy * dy + dz * dz > rb * rb * (T)1.0005 + (T)1e-9) return;
         }
@@ -1067,6 +1181,8 @@ struct Env {
           vec[0] = pos2[0] + axis[0] * x; vec[1] = pos2[1] + axis[1] * x; vec[2] = pos2[2] + axis[2] * x;
           Con c;
           if (sphere_sphere(c, margin, pos1, size1[0], vec, size2[0])) emit(c, p, 0, ncon);
+        } else if (t1 == OX_GEOM_BOX && t2 == OX_GEOM_BOX) {
+          box_box(p, margin, pos1, size1, pos2, size2, g1, g2, ncon);
         } else if (t1 == OX_GEOM_SPHERE && t2 == OX_GEOM_BOX) {
           T mat2[9];
           ld<9>(mat2, b.geom_xmat, 9 * g2);

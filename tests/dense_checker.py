@@ -444,6 +444,78 @@ def segment_box_closest(lc, la, bsize):
     return float(best_t)
 
 
+def box_box(p1, R1, h1, p2, R2, h2, margin):
+    """Contacts [(dist, pos, normal)] of two boxes. Contact generation is a DEFINITION, not a law of physics, so this follows the
+    product's construction (separating axes, clipping of the incident face, closest points of the supporting edges) - written
+    independently, vectorised differently, and checked on its own by the geometric properties in tests/test_box_contacts.py."""
+    d = p2 - p1
+    A, B = R1.T, R2.T                                                      # rows = axes
+    rad = lambda ax, h, L: float(np.sum(h * np.abs(ax @ L)))
+    face = []
+    for f in range(6):
+        L = A[f] if f < 3 else B[f - 3]
+        face.append(abs(d @ L) - rad(A, h1, L) - rad(B, h2, L))
+    if max(face) > margin:
+        return []
+    fidx = int(np.argmax(face))                                            # first maximum
+    edge = {}
+    for i in range(3):
+        for j in range(3):
+            L = np.cross(A[i], B[j])
+            n = np.linalg.norm(L)
+            if n < 1e-6:
+                continue
+            L = L / n
+            edge[(i, j)] = abs(d @ L) - rad(A, h1, L) - rad(B, h2, L)
+    if edge and max(edge.values()) > margin:
+        return []
+    scale = max(h1.max(), h2.max())
+    if edge:
+        (ei, ej), esep = max(edge.items(), key=lambda kv: (kv[1], -3 * kv[0][0] - kv[0][1]))   # first maximum in (i, j) order
+        if esep > face[fidx] + 1e-3 * scale:
+            L = np.cross(A[ei], B[ej]); L /= np.linalg.norm(L)
+            if L @ d < 0:
+                L = -L
+            c1 = p1 + sum((1.0 if A[k] @ L > 0 else -1.0) * h1[k] * A[k] for k in range(3) if k != ei)
+            c2 = p2 + sum((-1.0 if B[k] @ L > 0 else 1.0) * h2[k] * B[k] for k in range(3) if k != ej)
+            u, v, w = A[ei], B[ej], c1 - c2
+            b, dd, e = u @ v, u @ w, v @ w
+            den = 1 - b * b
+            sA = float(np.clip((b * e - dd) / den if den > 1e-12 else 0.0, -h1[ei], h1[ei]))
+            tB = float(np.clip((e - b * dd) / den if den > 1e-12 else 0.0, -h2[ej], h2[ej]))
+            pA, pB = c1 + sA * u, c2 + tB * v
+            dist = (pB - pA) @ L
+            return [(dist, 0.5 * (pA + pB), L)] if dist <= margin else []
+    refA = fidx < 3
+    ra = fidx if refA else fidx - 3
+    Rax, Iax, Rp, Ip, Rh, Ih = (A, B, p1, p2, h1, h2) if refA else (B, A, p2, p1, h2, h1)
+    n = (1.0 if (Ip - Rp) @ Rax[ra] >= 0 else -1.0) * Rax[ra]
+    ia = int(np.argmax(np.abs(Iax @ n)))
+    isg = -1.0 if Iax[ia] @ n > 0 else 1.0
+    iu, iv = (ia + 1) % 3, (ia + 2) % 3
+    poly = [Ip + isg * Ih[ia] * Iax[ia] + su * Ih[iu] * Iax[iu] + sv * Ih[iv] * Iax[iv] for su, sv in ((1, 1), (-1, 1), (-1, -1), (1, -1))]
+    for side in range(4):
+        ta, ps = (ra + 1 + side // 2) % 3, (-1.0 if side % 2 else 1.0)
+        ins = lambda pt: Rh[ta] - ps * ((pt - Rp) @ Rax[ta])
+        out = []
+        for q in range(len(poly)):
+            P, Q = poly[q], poly[(q + 1) % len(poly)]
+            dp, dq = ins(P), ins(Q)
+            if dp >= 0:
+                out.append(P)
+            if (dp >= 0) != (dq >= 0):
+                out.append(P + dp / (dp - dq) * (Q - P))
+        poly = out
+        if not poly:
+            break
+    res = []
+    for v in poly[:]:
+        depth = (v - Rp) @ n - Rh[ra]
+        if depth <= margin and len(res) < 8:
+            res.append((depth, v - 0.5 * depth * n, n if refA else -n))
+    return res
+
+
 def mix_params(dm, g1, g2):
     """mj_contactParam."""
     p1, p2 = dm.geom_priority[g1], dm.geom_priority[g2]
@@ -514,6 +586,9 @@ def collide(dm: DenseModel, kin: Kin):
             x = float(np.clip(ax @ (gpos[g1] - gpos[g2]), -s2[1], s2[1]))
             r = sphere_sphere(gpos[g1], s1[0], gpos[g2] + ax * x, s2[0], margin)
             if r: found.append((r, None))
+        elif t1 == BOX and t2 == BOX:
+            for r in box_box(gpos[g1], gmat[g1], s1, gpos[g2], gmat[g2], s2, margin):
+                found.append((r, None))
         elif t1 == SPHERE and t2 == BOX:
             r = sphere_box(gpos[g1], s1[0], gpos[g2], gmat[g2], s2, margin)
             if r: found.append((r, None))

@@ -126,8 +126,8 @@ def test_error_convention():
     for bad in ['<mujoco><option cone="elliptic" solver="PGS"/><worldbody/></mujoco>',
                 '<mujoco><worldbody><body><joint range="1 -1"/><geom size="0.1"/></body></worldbody></mujoco>',
                 '<mujoco><worldbody><body><joint/></body></worldbody></mujoco>',                       # massless moving body
-                '<mujoco><worldbody><body><freejoint/><geom type="box" size=".1 .1 .1"/></body><body><freejoint/>'
-                '<geom type="box" size=".1 .1 .1"/></body></worldbody></mujoco>',                    # box-box unsupported
+                '<mujoco><worldbody><body><freejoint/><geom type="cylinder" size=".1 .1"/></body><body><freejoint/>'
+                '<geom type="box" size=".1 .1 .1"/></body></worldbody></mujoco>',                    # cylinder collisions unsupported
                 '<mujoco><worldbody><body name="a"><joint/><geom size="0.1"/></body><body name="a"><joint/><geom size="0.1"/>'
                 '</body></worldbody></mujoco>']:
         with pytest.raises(ox.MjsError):  # compile failure -> Error::Mjs(message)

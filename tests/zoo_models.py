@@ -449,5 +449,24 @@ ZOO_O = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O}
+# N3 / north_star "box contacts": box-box narrowphase - boxes dropped on a static box and on each other (face-face with clipped
+# polygons, edge and corner touches), next to box-plane, sphere-box and capsule-box pairs
+ZOO_P = """
+<mujoco model="zoo_p">
+  <compiler angle="radian"/>
+  <option timestep="0.003" tolerance="1e-13"/>
+  <default><geom friction="0.8 0.01 0.001"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <geom name="table" type="box" pos="0 0 0.15" size="0.4 0.3 0.15" euler="0 0 0.2"/>
+    <body name="crate" pos="0.05 0.02 0.42" euler="0.1 0.05 0.4"><freejoint/><geom name="crate" type="box" size="0.12 0.1 0.08" density="500"/></body>
+    <body name="brick" pos="0.1 0.0 0.62" euler="0.3 0.2 1.0"><freejoint/><geom name="brick" type="box" size="0.08 0.04 0.03" density="800"/></body>
+    <body name="plank" pos="-0.3 0.25 0.4" euler="0.5 0.1 0"><freejoint/><geom name="plank" type="box" size="0.2 0.03 0.02" density="600"/></body>
+    <body name="marble" pos="-0.1 -0.1 0.45"><freejoint/><geom name="marble" type="sphere" size="0.04"/></body>
+  </worldbody>
+  <sensor><framepos objtype="body" objname="crate"/><framepos objtype="body" objname="brick"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O, "zoo_p": ZOO_P}
 NOCONTACT = {"zoo_d": ZOO_D}
