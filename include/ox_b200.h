@@ -69,6 +69,8 @@ enum { OX_EQ_CONNECT = 0, OX_EQ_WELD = 1, OX_EQ_JOINT = 2 };
 enum { OX_SOL_PGS = 0, OX_SOL_CG = 1, OX_SOL_NEWTON = 2 };
 enum { OX_CONE_PYRAMIDAL = 0, OX_CONE_ELLIPTIC = 1 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
+/* mjtTrn subset: what an actuator pulls on (actuator_trnid is a joint id or a tendon id) */
+enum { OX_TRN_JOINT = 0, OX_TRN_TENDON = 3 };
 enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
 /* mjtDisableBit subset */
 enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 << 4,
@@ -102,7 +104,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(geom_conaffinity, ngeom, 1) X(geom_condim, ngeom, 1) X(geom_priority, ngeom, 1)                \
   X(site_bodyid, nsite, 1) X(site_type, nsite, 1)                                                   \
   X(pair_geom1, npair, 1) X(pair_geom2, npair, 1) X(pair_dim, npair, 1) X(pair_maxcon, npair, 1) X(pair_conadr, npair, 1)   \
-  X(actuator_trnid, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
+  X(actuator_trnid, nu, 1) X(actuator_trntype, nu, 1) X(actuator_gaintype, nu, 1) X(actuator_biastype, nu, 1)                 \
   X(actuator_ctrllimited, nu, 1) X(actuator_forcelimited, nu, 1)                                    \
   X(actuator_dyntype, nu, 1) X(actuator_actadr, nu, 1) X(actuator_actlimited, nu, 1)                \
   X(sensor_type, nsensor, 1) X(sensor_objtype, nsensor, 1) X(sensor_objid, nsensor, 1)             \

@@ -1088,9 +1088,12 @@ void actuation(const Model* m, Data* d) {
   std::fill(d->actuator_force.begin(), d->actuator_force.end(), 0.0);
   if (disabled(m, OX_DSBL_ACTUATION)) return;
   for (int i = 0; i < m->nu; i++) {
-    int j = m->actuator_trnid[i], qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+    // mj_transmission: joint coordinate, or the length of a fixed tendon (moment = gear * tendon Jacobian)
+    const bool ten = m->actuator_trntype[i] == OX_TRN_TENDON;
+    const int j = m->actuator_trnid[i];
     double gear = m->actuator_gear[i];
-    double length = gear * d->qpos[qa], velocity = gear * d->qvel[da];
+    double length = gear * (ten ? d->ten_length[j] : d->qpos[m->jnt_qposadr[j]]);
+    double velocity = gear * (ten ? tendonVelocity(m, d, j) : d->qvel[m->jnt_dofadr[j]]);
     double ctrl = d->ctrl[i];
     if (m->actuator_ctrllimited[i] && !disabled(m, OX_DSBL_CLAMPCTRL))
       ctrl = clip(ctrl, m->actuator_ctrlrange[2 * i], m->actuator_ctrlrange[2 * i + 1]);
@@ -1110,7 +1113,9 @@ void actuation(const Model* m, Data* d) {
     double force = gain * ctrl + bias;
     if (m->actuator_forcelimited[i]) force = clip(force, m->actuator_forcerange[2 * i], m->actuator_forcerange[2 * i + 1]);
     d->actuator_force[i] = force;
-    d->qfrc_actuator[da] += gear * force;
+    if (ten)
+      for (int w = m->tendon_adr[j]; w < m->tendon_adr[j] + m->tendon_num[j]; w++) d->qfrc_actuator[m->jnt_dofadr[m->wrap_objid[w]]] += gear * force * m->wrap_prm[w];
+    else d->qfrc_actuator[m->jnt_dofadr[j]] += gear * force;
   }
 }
 
@@ -1814,8 +1819,12 @@ void sensors(const Model* m, Data* d) {
     switch (m->sensor_type[s]) {
       case OX_SENS_JOINTPOS: out[0] = d->qpos[m->jnt_qposadr[id]]; break;
       case OX_SENS_JOINTVEL: out[0] = d->qvel[m->jnt_dofadr[id]]; break;
-      case OX_SENS_ACTUATORPOS: out[0] = m->actuator_gear[id] * d->qpos[m->jnt_qposadr[m->actuator_trnid[id]]]; break;
-      case OX_SENS_ACTUATORVEL: out[0] = m->actuator_gear[id] * d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]; break;
+      case OX_SENS_ACTUATORPOS:
+        out[0] = m->actuator_gear[id] * (m->actuator_trntype[id] == OX_TRN_TENDON ? d->ten_length[m->actuator_trnid[id]] : d->qpos[m->jnt_qposadr[m->actuator_trnid[id]]]);
+        break;
+      case OX_SENS_ACTUATORVEL:
+        out[0] = m->actuator_gear[id] * (m->actuator_trntype[id] == OX_TRN_TENDON ? tendonVelocity(m, d, m->actuator_trnid[id]) : d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]);
+        break;
       case OX_SENS_ACTUATORFRC: out[0] = d->actuator_force[id]; break;
       case OX_SENS_TENDONPOS: out[0] = d->ten_length[id]; break;
       case OX_SENS_TENDONVEL: out[0] = tendonVelocity(m, d, id); break;

@@ -498,7 +498,7 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     return OX_ERR_INVALID;
   }
   if (cfg->mode == OX_MODE_COOP) {
-    if (!ox::step_coop_eligible(t)) { ox::set_error("ox_batch_create: mode = coop needs nv <= 32, the Newton solver with the pyramidal cone, without noslip or frictionloss, and the Euler or implicitfast integrator"); return OX_ERR_INVALID; }
+    if (!ox::step_coop_eligible(t)) { ox::set_error("ox_batch_create: mode = coop needs nv <= 32, the Newton solver with the pyramidal cone, joint transmissions only, no noslip or frictionloss, and the Euler or implicitfast integrator"); return OX_ERR_INVALID; }
     if (ox::step_coop_smem(t, b->blob_bytes, b->f64) > 227 * 1024) { ox::set_error("ox_batch_create: mode = coop: model tables + per-env intermediates exceed shared memory"); return OX_ERR_INVALID; }
     CU_TRY(ox::step_coop_prepare(t, b->blob_bytes, b->f64));
   }

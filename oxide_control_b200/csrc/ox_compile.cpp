@@ -569,7 +569,7 @@ void body_inertia_from_geoms(Builder& B, BodyDef& b) {
 
 struct ActDef {
   std::string name;
-  int joint = -1;
+  int joint = -1, tendon = -1;
   double gear = 1;
   int gaintype = OX_GAIN_FIXED, biastype = OX_BIAS_NONE;
   double gainprm[3] = {1, 0, 0}, biasprm[3] = {0, 0, 0};
@@ -1025,102 +1025,6 @@ ox_model* compile_mjcf(const std::string& xml) {
     t.nefcmax = (limits_on ? 2 * nlimited : 0) + ncontact_rows + ((t.disableflags & OX_DSBL_CONSTRAINT) ? 0 : t.nfloss);   // equality rows are added once they are compiled (below)
   }
 
-  // ---- actuators ----
-  std::vector<ActDef> acts;
-  for (auto& ch : root->children)
-    if (ch->name == "actuator")
-      for (auto& e : ch->children) {
-        if (!is_actuator_tag(e->name)) cfail("actuator <" + e->name + "> is outside the supported subset (motor, position, velocity, general)");
-        check_attrs(*e, "actuator_common");
-        Attrs a = merged(B.c, *e, "actuator", "");
-        ActDef ad;
-        ad.name = a.str_or("name", "");
-        for (const char* k : {"tendon", "site", "body", "jointinparent", "slidersite", "cranksite"})
-          if (a.has(k)) cfail("actuator '" + ad.name + "': transmission '" + k + "' is outside the supported subset (joint)");
-        if (!a.has("joint")) pfail(*e, "actuator requires a joint transmission");
-        ad.joint = find_name(nm[OX_OBJ_JOINT], a.str("joint"));
-        if (ad.joint < 0) cfail("actuator '" + ad.name + "': unknown joint '" + a.str("joint") + "'");
-        int jt = B.joints[ad.joint].type;
-        if (jt != OX_JNT_HINGE && jt != OX_JNT_SLIDE) cfail("actuator '" + ad.name + "': only hinge/slide joint transmissions are supported");
-        if (a.has("gear")) ad.gear = a.nums("gear").at(0);
-        if (a.has("dyntype")) {
-          const std::string& s = a.str("dyntype");
-          if (e->name != "general" && s != "none") cfail("actuator '" + ad.name + "': dyntype is an attribute of <general>");
-          if (s == "none") ad.dyntype = OX_DYN_NONE;
-          else if (s == "integrator") ad.dyntype = OX_DYN_INTEGRATOR;
-          else if (s == "filter") ad.dyntype = OX_DYN_FILTER;
-          else if (s == "filterexact") ad.dyntype = OX_DYN_FILTEREXACT;
-          else cfail("actuator '" + ad.name + "': dyntype '" + s + "' is outside the supported subset (none, integrator, filter, filterexact)");
-        }
-        if (a.has("actdim") || a.has("actearly")) cfail("actuator '" + ad.name + "': actdim / actearly are outside the supported subset");
-        a.vec("dynprm", ad.dynprm, 3, true);
-        {
-          const bool has_ar = a.has("actrange");
-          if (has_ar) a.vec("actrange", ad.actrange, 2);
-          const int al = a.boolean("actlimited");
-          ad.actlimited = al >= 0 ? al : (has_ar && B.c.autolimits);
-          if (ad.actlimited && ad.dyntype == OX_DYN_NONE) cfail("actuator '" + ad.name + "': actlimited needs a stateful actuator (dyntype)");
-          if (ad.actlimited && !(ad.actrange[0] < ad.actrange[1])) cfail("actuator '" + ad.name + "': invalid actrange");
-        }
-        if (e->name == "position") {
-          double kp = a.num("kp", 1), kv = a.num("kv", 0);
-          if (a.has("dampratio") || a.has("timeconst")) cfail("actuator '" + ad.name + "': dampratio/timeconst are outside the supported subset");
-          ad.gainprm[0] = kp; ad.biastype = OX_BIAS_AFFINE; ad.biasprm[1] = -kp; ad.biasprm[2] = -kv;
-        } else if (e->name == "velocity") {
-          double kv = a.num("kv", 1);
-          ad.gainprm[0] = kv; ad.biastype = OX_BIAS_AFFINE; ad.biasprm[2] = -kv;
-        } else if (e->name == "general") {
-          if (a.has("gaintype")) {
-            const std::string& s = a.str("gaintype");
-            if (s == "fixed") ad.gaintype = OX_GAIN_FIXED;
-            else if (s == "affine") ad.gaintype = OX_GAIN_AFFINE;
-            else cfail("actuator '" + ad.name + "': gaintype '" + s + "' unsupported");
-          }
-          if (a.has("biastype")) {
-            const std::string& s = a.str("biastype");
-            if (s == "none") ad.biastype = OX_BIAS_NONE;
-            else if (s == "affine") ad.biastype = OX_BIAS_AFFINE;
-            else cfail("actuator '" + ad.name + "': biastype '" + s + "' unsupported");
-          }
-          a.vec("gainprm", ad.gainprm, 3, true);
-          a.vec("biasprm", ad.biasprm, 3, true);
-        }
-        bool has_cr = a.has("ctrlrange"), has_fr = a.has("forcerange");
-        if (has_cr) a.vec("ctrlrange", ad.ctrlrange, 2);
-        if (has_fr) a.vec("forcerange", ad.forcerange, 2);
-        int cl = a.boolean("ctrllimited"), fl = a.boolean("forcelimited");
-        ad.ctrllimited = cl >= 0 ? cl : (has_cr && B.c.autolimits);
-        ad.forcelimited = fl >= 0 ? fl : (has_fr && B.c.autolimits);
-        if (ad.ctrllimited && !(ad.ctrlrange[0] < ad.ctrlrange[1])) cfail("actuator '" + ad.name + "': invalid ctrlrange");
-        if (ad.forcelimited && !(ad.forcerange[0] < ad.forcerange[1])) cfail("actuator '" + ad.name + "': invalid forcerange");
-        acts.push_back(ad);
-      }
-  const int nu = (int)acts.size();
-  t.nu = nu;
-  M->v_actuator_trnid.resize(nu); M->v_actuator_gaintype.resize(nu); M->v_actuator_biastype.resize(nu);
-  M->v_actuator_ctrllimited.resize(nu); M->v_actuator_forcelimited.resize(nu);
-  M->v_actuator_gear.resize(nu); M->v_actuator_gainprm.resize(3 * nu); M->v_actuator_biasprm.resize(3 * nu);
-  M->v_actuator_ctrlrange.resize(2 * nu); M->v_actuator_forcerange.resize(2 * nu);
-  M->v_actuator_dyntype.resize(nu); M->v_actuator_actadr.resize(nu); M->v_actuator_actlimited.resize(nu);
-  M->v_actuator_dynprm.resize(3 * nu); M->v_actuator_actrange.resize(2 * nu);
-  nm[OX_OBJ_ACTUATOR].resize(nu);
-  int na = 0;
-  for (int i = 0; i < nu; i++) {
-    const ActDef& a = acts[i];
-    nm[OX_OBJ_ACTUATOR][i] = a.name;
-    M->v_actuator_trnid[i] = a.joint; M->v_actuator_gaintype[i] = a.gaintype; M->v_actuator_biastype[i] = a.biastype;
-    M->v_actuator_ctrllimited[i] = a.ctrllimited; M->v_actuator_forcelimited[i] = a.forcelimited;
-    M->v_actuator_gear[i] = a.gear;
-    for (int k = 0; k < 3; k++) { M->v_actuator_gainprm[3 * i + k] = a.gainprm[k]; M->v_actuator_biasprm[3 * i + k] = a.biasprm[k]; }
-    for (int k = 0; k < 2; k++) { M->v_actuator_ctrlrange[2 * i + k] = a.ctrlrange[k]; M->v_actuator_forcerange[2 * i + k] = a.forcerange[k]; }
-    M->v_actuator_dyntype[i] = a.dyntype; M->v_actuator_actlimited[i] = a.actlimited;
-    M->v_actuator_actadr[i] = a.dyntype != OX_DYN_NONE ? na++ : -1;   // one activation variable per stateful actuator (actdim 1)
-    for (int k = 0; k < 3; k++) M->v_actuator_dynprm[3 * i + k] = a.dynprm[k];
-    for (int k = 0; k < 2; k++) M->v_actuator_actrange[2 * i + k] = a.actrange[k];
-  }
-  t.na = na;
-  check_unique(OX_OBJ_ACTUATOR, "actuator");
-
   // ---- fixed tendons: length = sum_i coef_i * q_i over hinge / slide joints; limits, spring (with dead band) and damper.
   // Spatial tendons (site / geom wrapping), tendon friction loss and tendon transmissions are outside the supported subset.
   t.ntendon = 0; t.nwrap = 0;
@@ -1177,6 +1081,109 @@ ox_model* compile_mjcf(const std::string& xml) {
         t.ntendon++;
       }
   check_unique(OX_OBJ_TENDON, "tendon");
+
+  // ---- actuators ----
+  std::vector<ActDef> acts;
+  for (auto& ch : root->children)
+    if (ch->name == "actuator")
+      for (auto& e : ch->children) {
+        if (!is_actuator_tag(e->name)) cfail("actuator <" + e->name + "> is outside the supported subset (motor, position, velocity, general)");
+        check_attrs(*e, "actuator_common");
+        Attrs a = merged(B.c, *e, "actuator", "");
+        ActDef ad;
+        ad.name = a.str_or("name", "");
+        for (const char* k : {"site", "body", "jointinparent", "slidersite", "cranksite"})
+          if (a.has(k)) cfail("actuator '" + ad.name + "': transmission '" + k + "' is outside the supported subset (joint, tendon)");
+        if (a.has("joint") == a.has("tendon")) pfail(*e, "actuator requires exactly one of joint / tendon");
+        if (a.has("tendon")) {   // fixed-tendon transmission: length = gear * tendon length, moment = gear * tendon Jacobian
+          ad.tendon = find_name(nm[OX_OBJ_TENDON], a.str("tendon"));
+          if (ad.tendon < 0) cfail("actuator '" + ad.name + "': unknown tendon '" + a.str("tendon") + "'");
+          if (t.integrator == OX_INT_IMPLICITFAST) cfail("actuator '" + ad.name + "': tendon transmissions with the implicitfast integrator (off-diagonal velocity derivative) are outside the supported subset");
+        } else {
+          ad.joint = find_name(nm[OX_OBJ_JOINT], a.str("joint"));
+          if (ad.joint < 0) cfail("actuator '" + ad.name + "': unknown joint '" + a.str("joint") + "'");
+          int jt = B.joints[ad.joint].type;
+          if (jt != OX_JNT_HINGE && jt != OX_JNT_SLIDE) cfail("actuator '" + ad.name + "': only hinge/slide joint transmissions are supported");
+        }
+        if (a.has("gear")) ad.gear = a.nums("gear").at(0);
+        if (a.has("dyntype")) {
+          const std::string& s = a.str("dyntype");
+          if (e->name != "general" && s != "none") cfail("actuator '" + ad.name + "': dyntype is an attribute of <general>");
+          if (s == "none") ad.dyntype = OX_DYN_NONE;
+          else if (s == "integrator") ad.dyntype = OX_DYN_INTEGRATOR;
+          else if (s == "filter") ad.dyntype = OX_DYN_FILTER;
+          else if (s == "filterexact") ad.dyntype = OX_DYN_FILTEREXACT;
+          else cfail("actuator '" + ad.name + "': dyntype '" + s + "' is outside the supported subset (none, integrator, filter, filterexact)");
+        }
+        if (a.has("actdim") || a.has("actearly")) cfail("actuator '" + ad.name + "': actdim / actearly are outside the supported subset");
+        a.vec("dynprm", ad.dynprm, 3, true);
+        {
+          const bool has_ar = a.has("actrange");
+          if (has_ar) a.vec("actrange", ad.actrange, 2);
+          const int al = a.boolean("actlimited");
+          ad.actlimited = al >= 0 ? al : (has_ar && B.c.autolimits);
+          if (ad.actlimited && ad.dyntype == OX_DYN_NONE) cfail("actuator '" + ad.name + "': actlimited needs a stateful actuator (dyntype)");
+          if (ad.actlimited && !(ad.actrange[0] < ad.actrange[1])) cfail("actuator '" + ad.name + "': invalid actrange");
+        }
+        if (e->name == "position") {
+          double kp = a.num("kp", 1), kv = a.num("kv", 0);
+          if (a.has("dampratio") || a.has("timeconst")) cfail("actuator '" + ad.name + "': dampratio/timeconst are outside the supported subset");
+          ad.gainprm[0] = kp; ad.biastype = OX_BIAS_AFFINE; ad.biasprm[1] = -kp; ad.biasprm[2] = -kv;
+        } else if (e->name == "velocity") {
+          double kv = a.num("kv", 1);
+          ad.gainprm[0] = kv; ad.biastype = OX_BIAS_AFFINE; ad.biasprm[2] = -kv;
+        } else if (e->name == "general") {
+          if (a.has("gaintype")) {
+            const std::string& s = a.str("gaintype");
+            if (s == "fixed") ad.gaintype = OX_GAIN_FIXED;
+            else if (s == "affine") ad.gaintype = OX_GAIN_AFFINE;
+            else cfail("actuator '" + ad.name + "': gaintype '" + s + "' unsupported");
+          }
+          if (a.has("biastype")) {
+            const std::string& s = a.str("biastype");
+            if (s == "none") ad.biastype = OX_BIAS_NONE;
+            else if (s == "affine") ad.biastype = OX_BIAS_AFFINE;
+            else cfail("actuator '" + ad.name + "': biastype '" + s + "' unsupported");
+          }
+          a.vec("gainprm", ad.gainprm, 3, true);
+          a.vec("biasprm", ad.biasprm, 3, true);
+        }
+        bool has_cr = a.has("ctrlrange"), has_fr = a.has("forcerange");
+        if (has_cr) a.vec("ctrlrange", ad.ctrlrange, 2);
+        if (has_fr) a.vec("forcerange", ad.forcerange, 2);
+        int cl = a.boolean("ctrllimited"), fl = a.boolean("forcelimited");
+        ad.ctrllimited = cl >= 0 ? cl : (has_cr && B.c.autolimits);
+        ad.forcelimited = fl >= 0 ? fl : (has_fr && B.c.autolimits);
+        if (ad.ctrllimited && !(ad.ctrlrange[0] < ad.ctrlrange[1])) cfail("actuator '" + ad.name + "': invalid ctrlrange");
+        if (ad.forcelimited && !(ad.forcerange[0] < ad.forcerange[1])) cfail("actuator '" + ad.name + "': invalid forcerange");
+        acts.push_back(ad);
+      }
+  const int nu = (int)acts.size();
+  t.nu = nu;
+  M->v_actuator_trnid.resize(nu); M->v_actuator_trntype.resize(nu); M->v_actuator_gaintype.resize(nu); M->v_actuator_biastype.resize(nu);
+  M->v_actuator_ctrllimited.resize(nu); M->v_actuator_forcelimited.resize(nu);
+  M->v_actuator_gear.resize(nu); M->v_actuator_gainprm.resize(3 * nu); M->v_actuator_biasprm.resize(3 * nu);
+  M->v_actuator_ctrlrange.resize(2 * nu); M->v_actuator_forcerange.resize(2 * nu);
+  M->v_actuator_dyntype.resize(nu); M->v_actuator_actadr.resize(nu); M->v_actuator_actlimited.resize(nu);
+  M->v_actuator_dynprm.resize(3 * nu); M->v_actuator_actrange.resize(2 * nu);
+  nm[OX_OBJ_ACTUATOR].resize(nu);
+  int na = 0;
+  for (int i = 0; i < nu; i++) {
+    const ActDef& a = acts[i];
+    nm[OX_OBJ_ACTUATOR][i] = a.name;
+    M->v_actuator_trnid[i] = a.tendon >= 0 ? a.tendon : a.joint; M->v_actuator_trntype[i] = a.tendon >= 0 ? OX_TRN_TENDON : OX_TRN_JOINT;
+    M->v_actuator_gaintype[i] = a.gaintype; M->v_actuator_biastype[i] = a.biastype;
+    M->v_actuator_ctrllimited[i] = a.ctrllimited; M->v_actuator_forcelimited[i] = a.forcelimited;
+    M->v_actuator_gear[i] = a.gear;
+    for (int k = 0; k < 3; k++) { M->v_actuator_gainprm[3 * i + k] = a.gainprm[k]; M->v_actuator_biasprm[3 * i + k] = a.biasprm[k]; }
+    for (int k = 0; k < 2; k++) { M->v_actuator_ctrlrange[2 * i + k] = a.ctrlrange[k]; M->v_actuator_forcerange[2 * i + k] = a.forcerange[k]; }
+    M->v_actuator_dyntype[i] = a.dyntype; M->v_actuator_actlimited[i] = a.actlimited;
+    M->v_actuator_actadr[i] = a.dyntype != OX_DYN_NONE ? na++ : -1;   // one activation variable per stateful actuator (actdim 1)
+    for (int k = 0; k < 3; k++) M->v_actuator_dynprm[3 * i + k] = a.dynprm[k];
+    for (int k = 0; k < 2; k++) M->v_actuator_actrange[2 * i + k] = a.actrange[k];
+  }
+  t.na = na;
+  check_unique(OX_OBJ_ACTUATOR, "actuator");
 
   // ---- sensors (N2 subset) ----
   {

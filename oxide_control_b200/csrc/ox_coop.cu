@@ -738,6 +738,8 @@ __global__ void __launch_bounds__(COOP_THREADS, COOP_THREADS >= 256 ? 1 : 2) k_s
 template <typename T> static int coop_group_size(const ox_model_tables& t) { return t.nv <= 16 ? 16 : 32; }
 
 bool step_coop_eligible(const ox_model_tables& t) {
+  for (int i = 0; i < t.nu; i++)
+    if (t.actuator_trntype[i] != OX_TRN_JOINT) return false;   // the lane = dof gather of the actuator forces knows joint transmissions only
   return t.nv >= 1 && t.nv <= 32 && t.solver == OX_SOL_NEWTON && t.noslip_iterations == 0 && t.nfloss == 0 && t.cone == OX_CONE_PYRAMIDAL && (t.integrator == OX_INT_EULER || t.integrator == OX_INT_IMPLICITFAST);
 }
 template <typename T>

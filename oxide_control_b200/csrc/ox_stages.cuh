@@ -762,8 +762,23 @@ struct Env {
     OX_MLOOP
     for (int i = 0; i < nu; i++) {
       const T gf = actuator_one(i);   // gear * force (0 when actuation is disabled)
-      at(b.qfrc_actuator, m.jnt_dofadr(m.actuator_trnid(i))) += gf;
+      if (m.actuator_trntype(i) == OX_TRN_TENDON) {   // moment = gear * tendon Jacobian (the coefficient vector)
+        const int tn = m.actuator_trnid(i);
+        OX_MLOOP
+        for (int w = 0; w < m.tendon_num(tn); w++) at(b.qfrc_actuator, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(tn) + w))) += gf * m.wrap_prm(m.tendon_adr(tn) + w);
+      } else {
+        at(b.qfrc_actuator, m.jnt_dofadr(m.actuator_trnid(i))) += gf;
+      }
     }
+  }
+  // transmission length / velocity of actuator i without the gear (joint coordinate, or fixed-tendon length)
+  OX_HD T act_length(int i) const {
+    if (m.actuator_trntype(i) == OX_TRN_TENDON) return at(b.ten_length, m.actuator_trnid(i));
+    return at(b.qpos, m.jnt_qposadr(m.actuator_trnid(i)));
+  }
+  OX_HD T act_velocity(int i) const {
+    if (m.actuator_trntype(i) == OX_TRN_TENDON) return tendon_velocity(m.actuator_trnid(i));
+    return at(b.qvel, m.jnt_dofadr(m.actuator_trnid(i)));
   }
   // force of one actuator -> actuator_force[i] (and act_dot for stateful ones); returns its generalised force gear * force
   OX_HD T actuator_one(int i) const {
@@ -771,9 +786,8 @@ struct Env {
     const bool clamp = !dis(OX_DSBL_CLAMPCTRL);
     {
       if (off) { at(b.actuator_force, i) = 0; return (T)0; }
-      const int j = m.actuator_trnid(i), qa = m.jnt_qposadr(j), da = m.jnt_dofadr(j);
       const T gear = m.actuator_gear(i);
-      const T length = gear * at(b.qpos, qa), velocity = gear * at(b.qvel, da);
+      const T length = gear * act_length(i), velocity = gear * act_velocity(i);
       T ctrl = at(b.ctrl, i);
       if (m.actuator_ctrllimited(i) && clamp) ctrl = ox_clip(ctrl, m.actuator_ctrlrange(2 * i), m.actuator_ctrlrange(2 * i + 1));
       // stateful actuators (mjtDyn integrator / filter / filterexact): the force is driven by the activation state, and the
@@ -2620,8 +2634,8 @@ struct Env {
       switch (ty) {
         case OX_SENS_JOINTPOS: at(b.sensordata, adr) = at(b.qpos, m.jnt_qposadr(id)); break;
         case OX_SENS_JOINTVEL: at(b.sensordata, adr) = at(b.qvel, m.jnt_dofadr(id)); break;
-        case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qpos, m.jnt_qposadr(m.actuator_trnid(id))); break;
-        case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear(id) * at(b.qvel, m.jnt_dofadr(m.actuator_trnid(id))); break;
+        case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear(id) * act_length(id); break;
+        case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear(id) * act_velocity(id); break;
         case OX_SENS_ACTUATORFRC: at(b.sensordata, adr) = at(b.actuator_force, id); break;
         case OX_SENS_TENDONPOS: at(b.sensordata, adr) = at(b.ten_length, id); break;
         case OX_SENS_TENDONVEL: at(b.sensordata, adr) = tendon_velocity(id); break;

@@ -88,7 +88,7 @@ class DenseModel:
     """numpy copies of the compiled tables (read through the Python Model mirror)."""
     INT = ["body_parentid", "body_jntadr", "body_jntnum", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited",
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
-           "actuator_trnid", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
+           "actuator_trnid", "actuator_trntype", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
            "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id",
            "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "wrap_objid"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
@@ -281,9 +281,15 @@ def actuator_force(dm, qpos, qvel, ctrl, act=None):
     if dm.dis("actuation"):
         return f, frc, act_dot, dfdv
     for i in range(dm.nu):
-        j = int(dm.actuator_trnid[i])
-        qa, da, gear = int(dm.jnt_qposadr[j]), int(dm.jnt_dofadr[j]), dm.actuator_gear[i]
-        length, vel = gear * qpos[qa], gear * qvel[da]
+        j, gear = int(dm.actuator_trnid[i]), dm.actuator_gear[i]
+        if int(dm.actuator_trntype[i]) == 3:                     # tendon transmission: moment arm = gear * (tendon coefficient vector)
+            moment = gear * tendon_jacobian(dm, j)
+            da = None
+        else:
+            moment = np.zeros(dm.nv)
+            da = int(dm.jnt_dofadr[j])
+            moment[da] = gear
+        length, vel = moment @ tendon_coords(dm, qpos), moment @ qvel
         u = ctrl[i]
         if dm.actuator_ctrllimited[i] and not dm.dis("clampctrl"):
             u = min(max(u, dm.actuator_ctrlrange[2 * i]), dm.actuator_ctrlrange[2 * i + 1])
@@ -303,8 +309,8 @@ def actuator_force(dm, qpos, qvel, ctrl, act=None):
             clamped = force <= lo or force >= hi
             force = min(max(force, lo), hi)
         frc[i] = force
-        f[da] += gear * force
-        if not clamped:
+        f += moment * force
+        if not clamped and da is not None:
             dfdv[da] += gear * gear * ((gp[2] * u if gaff else 0.0) + (bp[2] if baff else 0.0))
     return f, frc, act_dot, dfdv
 

@@ -53,6 +53,29 @@ def test_limit_row_closed_form():
     assert od.int("nefc") == 0
 
 
+def test_tendon_transmission_closed_form():
+    """A motor on the tendon L = q1 - 2 q2 with gear 3: generalised force = gear * u * (1, -2); a position servo on it reads the
+    tendon length through the gear (actuatorpos / actuatorvel sensors)."""
+    xml = TWO.format(attrs="").replace("</tendon>", "</tendon><actuator><motor name='m' tendon='t' gear='3'/>"
+                                      "<position name='p' tendon='t' kp='5' kv='0.5' gear='2'/></actuator>")
+    xml = xml.replace("<sensor>", "<sensor><actuatorpos actuator='p'/><actuatorvel actuator='p'/>")
+    m = ox.Model.from_xml_string(xml)
+    assert list(m.actuator_trntype) == [3, 3] and list(m.actuator_trnid) == [0, 0]
+    od = OracleData(m)
+    q1, q2, v1, v2, u = 0.3, -0.1, 0.2, 0.4, 0.6
+    od.field("qpos")[:] = [q1, q2]; od.field("qvel")[:] = [v1, v2]; od.field("ctrl")[:] = [u, 0.25]
+    od.forward()
+    L, Ld = q1 - 2 * q2, v1 - 2 * v2
+    fp = 5 * 0.25 - 5 * (2 * L) - 0.5 * (2 * Ld)              # position servo: kp (ctrl - length) - kv velocity, length = gear * L
+    assert np.allclose(od.field("actuator_force"), [u, fp], atol=1e-14)
+    gen = 3 * u + 2 * fp
+    assert np.allclose(od.field("qfrc_actuator"), [gen, -2 * gen], atol=1e-13)
+    assert np.allclose(od.field("sensordata")[:2], [2 * L, 2 * Ld], atol=1e-14)
+    assert np.allclose(od.field("qacc"), [gen / 2, -2 * gen / 3], atol=1e-12)
+    with pytest.raises(ox.MjsError, match="implicitfast"):
+        ox.Model.from_xml_string(xml.replace('timestep="0.002"', 'timestep="0.002" integrator="implicitfast"'))
+
+
 def test_compiler_refusals():
     body = "<worldbody><body><joint name='j' type='hinge'/><geom size='0.1'/><site name='s'/><body pos='0 0 1'><joint name='b' type='ball'/><geom size='0.1'/></body></body></worldbody>"
     for tendon, msg in (("<spatial><site site='s'/></spatial>", "spatial"), ("<fixed><joint joint='b' coef='1'/></fixed>", "hinge / slide"),
@@ -91,6 +114,10 @@ def test_gpu_vs_oracle(mode, specialize):
     nenv, nsteps = 64, 150
     qpos, qvel = random_state(m, nenv, seed=47)
     qvel *= 10
+    if mode == "coop":   # the lane = dof kernel gathers actuator forces per joint: tendon transmissions are not offered there
+        with pytest.raises(ox.Error, match="coop"):
+            ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
+        return
     b = ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
     b.set("qpos", qpos); b.set("qvel", qvel); b.ctrl_philox(True, SEED)
     b.step(nsteps); b.sync()

@@ -306,8 +306,10 @@ ZOO_H = """
     <fixed name="spring" stiffness="12" damping="0.4" springlength="-0.1 0.15"><joint joint="k1" coef="0.5"/><joint joint="lift" coef="2"/></fixed>
     <fixed name="soft" stiffness="3" range="-2 2"><joint joint="k1" coef="1"/><joint joint="k2" coef="1"/><joint joint="k3" coef="1"/></fixed>
   </tendon>
-  <actuator><motor joint="k1" gear="2"/><motor joint="k3" gear="0.6"/></actuator>
-  <sensor><tendonpos tendon="curl"/><tendonvel tendon="spring"/><tendonpos tendon="soft"/><jointpos joint="k2"/></sensor>
+  <actuator><motor joint="k1" gear="2"/><motor joint="k3" gear="0.6"/>
+    <motor name="pull" tendon="curl" gear="0.4"/><position name="servo" tendon="soft" kp="3" kv="0.2" gear="1.5" forcerange="-2 2"/></actuator>
+  <sensor><tendonpos tendon="curl"/><tendonvel tendon="spring"/><tendonpos tendon="soft"/><jointpos joint="k2"/>
+    <actuatorpos actuator="servo"/><actuatorvel actuator="servo"/><actuatorfrc actuator="pull"/></sensor>
 </mujoco>
 """
 
