@@ -71,6 +71,9 @@ enum { OX_CONE_PYRAMIDAL = 0, OX_CONE_ELLIPTIC = 1 };
 enum { OX_GAIN_FIXED = 0, OX_GAIN_AFFINE = 1 };
 /* mjtTrn subset: what an actuator pulls on (actuator_trnid is a joint id or a tendon id) */
 enum { OX_TRN_JOINT = 0, OX_TRN_TENDON = 3 };
+/* tendon kinds: fixed = linear combination of joint coordinates (wrap_objid = joints, wrap_prm = coefficients);
+ * spatial = straight segments through sites (wrap_objid = sites; wrapping geoms and pulleys are refused) */
+enum { OX_TEN_FIXED = 0, OX_TEN_SPATIAL = 1 };
 enum { OX_BIAS_NONE = 0, OX_BIAS_AFFINE = 1 };
 /* mjtDisableBit subset */
 enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 << 4,
@@ -96,7 +99,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(body_jntadr, nbody, 1) X(body_jntnum, nbody, 1) X(body_dofadr, nbody, 1) X(body_dofnum, nbody, 1) \
   X(body_mocapid, nbody, 1)                                                                         \
   X(eq_type, neq, 1) X(eq_obj1id, neq, 1) X(eq_obj2id, neq, 1) X(eq_active0, neq, 1)                \
-  X(tendon_adr, ntendon, 1) X(tendon_num, ntendon, 1) X(tendon_limited, ntendon, 1) X(wrap_objid, nwrap, 1) \
+  X(tendon_adr, ntendon, 1) X(tendon_num, ntendon, 1) X(tendon_limited, ntendon, 1) X(tendon_type, ntendon, 1) X(wrap_objid, nwrap, 1) \
   X(jnt_type, njnt, 1) X(jnt_qposadr, njnt, 1) X(jnt_dofadr, njnt, 1) X(jnt_bodyid, njnt, 1)       \
   X(jnt_limited, njnt, 1)                                                                           \
   X(dof_bodyid, nv, 1) X(dof_jntid, nv, 1) X(dof_parentid, nv, 1) X(dof_Madr, nv, 1) X(dof_depth, nv, 1) X(dof_Mdense, nvv, 1)               \
@@ -252,7 +255,7 @@ enum {
   OX_F_QFRC_SMOOTH, OX_F_QACC_SMOOTH, OX_F_QFRC_CONSTRAINT,
   OX_F_CON_DIST, OX_F_CON_POS, OX_F_CON_FRAME,
   OX_F_EFC_J, OX_F_EFC_POS, OX_F_EFC_MARGIN, OX_F_EFC_D, OX_F_EFC_AREF, OX_F_EFC_FORCE,
-  OX_F_ACT_DOT, OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE, OX_F_TEN_LENGTH,
+  OX_F_ACT_DOT, OX_F_MOCAP_POS, OX_F_MOCAP_QUAT, OX_F_EQ_ACTIVE, OX_F_TEN_LENGTH, OX_F_TEN_J,
   OX_F_COUNT_REAL,
   /* int32 fields */
   OX_F_NCON = 100, OX_F_NEFC, OX_F_SOLVER_NITER, OX_F_DIVERGED, OX_F_CON_PAIR

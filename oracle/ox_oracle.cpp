@@ -36,7 +36,7 @@ static const double OX_PI_D = 3.14159265358979323846;
 
 struct oxo_data {
   // state (mjData fields of the same names)
-  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot, mocap_pos, mocap_quat, eq_active, ten_length;
+  std::vector<double> qpos, qvel, ctrl, qfrc_applied, xfrc_applied, qacc_warmstart, act, act_dot, mocap_pos, mocap_quat, eq_active, ten_length, ten_J;
   double time = 0;
   // position stage
   std::vector<double> xpos, xquat, xmat, xipos, ximat, xanchor, xaxis, geom_xpos, geom_xmat, site_xpos, site_xmat;
@@ -801,17 +801,43 @@ void addRow(const Model* m, Data* d, const double* jrow, double pos, double marg
   d->efc_aref[r] = -Bd * vel - K * imp * (pos - margin);
 }
 
-// fixed tendons (mj_tendon): length = sum of coef * joint coordinate; the Jacobian is the (constant) coefficient vector
+// mj_tendon: length and Jacobian row of every tendon. Fixed: length = sum of coef * joint coordinate, J = the coefficients.
+// Spatial (sites only): length = sum of segment lengths, J = sum dir' (Jp(site k+1) - Jp(site k)).
+void addJacP(const Model* m, const Data* d, int body, const double* point, double sign, double* jacp);
 void tendonLength(const Model* m, Data* d) {
+  const int nv = m->nv;
+  std::fill(d->ten_J.begin(), d->ten_J.end(), 0.0);
+  std::vector<double> jacp(3 * nv);
   for (int i = 0; i < m->ntendon; i++) {
     double L = 0;
-    for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) L += m->wrap_prm[w] * d->qpos[m->jnt_qposadr[m->wrap_objid[w]]];
+    double* J = &d->ten_J[(size_t)i * nv];
+    const int adr = m->tendon_adr[i], num = m->tendon_num[i];
+    if (m->tendon_type[i] == OX_TEN_FIXED) {
+      for (int w = adr; w < adr + num; w++) {
+        L += m->wrap_prm[w] * d->qpos[m->jnt_qposadr[m->wrap_objid[w]]];
+        J[m->jnt_dofadr[m->wrap_objid[w]]] += m->wrap_prm[w];
+      }
+    } else {
+      for (int w = adr; w + 1 < adr + num; w++) {
+        const int sa = m->wrap_objid[w], sb = m->wrap_objid[w + 1];
+        const double *pa = &d->site_xpos[3 * sa], *pb = &d->site_xpos[3 * sb];
+        double dir[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        const double len = std::sqrt(dot3(dir, dir));
+        L += len;
+        if (len < OX_MINVAL) continue;
+        for (double& v : dir) v /= len;
+        std::fill(jacp.begin(), jacp.end(), 0.0);
+        addJacP(m, d, m->site_bodyid[sb], pb, +1, jacp.data());
+        addJacP(m, d, m->site_bodyid[sa], pa, -1, jacp.data());
+        for (int k = 0; k < nv; k++) J[k] += dir[0] * jacp[k] + dir[1] * jacp[nv + k] + dir[2] * jacp[2 * nv + k];
+      }
+    }
     d->ten_length[i] = L;
   }
 }
 double tendonVelocity(const Model* m, const Data* d, int i) {
   double v = 0;
-  for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) v += m->wrap_prm[w] * d->qvel[m->jnt_dofadr[m->wrap_objid[w]]];
+  for (int k = 0; k < m->nv; k++) v += d->ten_J[(size_t)i * m->nv + k] * d->qvel[k];
   return v;
 }
 
@@ -929,7 +955,7 @@ void makeConstraint(const Model* m, Data* d) {
         double dist = side * (m->tendon_range[2 * i + (side + 1) / 2] - value);
         if (dist < margin) {
           std::fill(jrow.begin(), jrow.end(), 0.0);
-          for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) jrow[m->jnt_dofadr[m->wrap_objid[w]]] += -side * m->wrap_prm[w];
+          for (int k = 0; k < nv; k++) jrow[k] = -side * d->ten_J[(size_t)i * nv + k];
           addRow(m, d, jrow.data(), dist, margin, m->tendon_invweight0[i], m->tendon_solref_lim + 2 * i, m->tendon_solimp_lim + 5 * i, 4, i);
         }
       }
@@ -1055,7 +1081,7 @@ void passive(const Model* m, Data* d) {
     else if (L < lo) f = m->tendon_stiffness[i] * (lo - L);
     f -= m->tendon_damping[i] * tendonVelocity(m, d, i);
     if (f != 0)
-      for (int w = m->tendon_adr[i]; w < m->tendon_adr[i] + m->tendon_num[i]; w++) d->qfrc_passive[m->jnt_dofadr[m->wrap_objid[w]]] += m->wrap_prm[w] * f;
+      for (int k = 0; k < m->nv; k++) d->qfrc_passive[k] += d->ten_J[(size_t)i * m->nv + k] * f;
   }
 }
 
@@ -1114,7 +1140,7 @@ void actuation(const Model* m, Data* d) {
     if (m->actuator_forcelimited[i]) force = clip(force, m->actuator_forcerange[2 * i], m->actuator_forcerange[2 * i + 1]);
     d->actuator_force[i] = force;
     if (ten)
-      for (int w = m->tendon_adr[j]; w < m->tendon_adr[j] + m->tendon_num[j]; w++) d->qfrc_actuator[m->jnt_dofadr[m->wrap_objid[w]]] += gear * force * m->wrap_prm[w];
+      for (int k = 0; k < m->nv; k++) d->qfrc_actuator[k] += gear * force * d->ten_J[(size_t)j * m->nv + k];
     else d->qfrc_actuator[m->jnt_dofadr[j]] += gear * force;
   }
 }
@@ -2099,7 +2125,7 @@ OXO_API oxo_data* oxo_make_data(const Model* m) {
   int nb = m->nbody, nv = m->nv;
   d->qpos.resize(m->nq); d->qvel.resize(nv); d->ctrl.resize(m->nu); d->qfrc_applied.resize(nv); d->xfrc_applied.resize(6 * nb);
   d->qacc_warmstart.resize(nv); d->act.resize(m->na); d->act_dot.resize(m->na);
-  d->mocap_pos.resize(3 * m->nmocap); d->mocap_quat.resize(4 * m->nmocap); d->eq_active.resize(m->neq); d->ten_length.resize(m->ntendon);
+  d->mocap_pos.resize(3 * m->nmocap); d->mocap_quat.resize(4 * m->nmocap); d->eq_active.resize(m->neq); d->ten_length.resize(m->ntendon); d->ten_J.resize((size_t)m->ntendon * m->nv);
   d->xpos.resize(3 * nb); d->xquat.resize(4 * nb); d->xmat.resize(9 * nb); d->xipos.resize(3 * nb); d->ximat.resize(9 * nb);
   d->xanchor.resize(3 * m->njnt); d->xaxis.resize(3 * m->njnt); d->geom_xpos.resize(3 * m->ngeom); d->geom_xmat.resize(9 * m->ngeom);
   d->site_xpos.resize(3 * m->nsite); d->site_xmat.resize(9 * m->nsite);
@@ -2148,7 +2174,7 @@ OXO_API void oxo_stage(const Model* m, oxo_data* d, const char* name) {
 OXO_API double* oxo_field(oxo_data* d, const char* name, int32_t* count) {
   std::string s(name);
 #define F(f) if (s == #f) { *count = (int32_t)d->f.size(); return d->f.data(); }
-  F(ten_length) F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
+  F(ten_length) F(ten_J) F(mocap_pos) F(mocap_quat) F(eq_active) F(act) F(act_dot) F(qpos) F(qvel) F(ctrl) F(qfrc_applied) F(xfrc_applied) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat)
   F(xanchor) F(xaxis) F(geom_xpos) F(geom_xmat) F(site_xpos) F(site_xmat) F(subtree_com) F(cinert) F(cdof) F(qM) F(qLD)
   F(qLDiagInv) F(cvel) F(cdof_dot) F(qfrc_bias) F(qfrc_passive) F(actuator_force) F(qfrc_actuator) F(qfrc_smooth) F(qacc_smooth)
   F(con_dist) F(con_pos) F(con_frame) F(efc_J) F(efc_pos) F(efc_margin) F(efc_D) F(efc_floss) F(efc_R) F(efc_aref) F(efc_vel) F(efc_force)

@@ -54,7 +54,7 @@ size_t layout_arena(const ox_model_tables& t, int stride, unsigned char* base, D
     R(OX_F_CON_FRAME, con_frame, 9 * ncm) R(OX_F_EFC_J, efc_J, nem * nv) R(OX_F_EFC_POS, efc_pos, nem)
     R(OX_F_EFC_MARGIN, efc_margin, nem) R(OX_F_EFC_D, efc_D, nem) R(OX_F_EFC_AREF, efc_aref, nem) R(OX_F_EFC_FORCE, efc_force, nem)
     R(OX_F_ACT, act, na) R(OX_F_ACT_DOT, act_dot, na) R(OX_F_MOCAP_POS, mocap_pos, 3 * nmc) R(OX_F_MOCAP_QUAT, mocap_quat, 4 * nmc)
-    R(OX_F_EQ_ACTIVE, eq_active, neq) R(OX_F_TEN_LENGTH, ten_length, nten)
+    R(OX_F_EQ_ACTIVE, eq_active, neq) R(OX_F_TEN_LENGTH, ten_length, nten) R(OX_F_TEN_J, ten_J, nten * nv)
 #undef R
 #define I(id, name, cnt) f[id] = FieldInfo{out->name, (int)(cnt), true};
     I(OX_F_NCON, ncon, 1) I(OX_F_NEFC, nefc, 1) I(OX_F_SOLVER_NITER, solver_niter, 1) I(OX_F_DIVERGED, diverged, 1)

@@ -111,7 +111,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
 #define OX_BATCH_REAL_FIELDS_SMALL(X)                                                                  \
   /* state */                                                                                          \
   X(qpos, nq) X(qvel, nv) X(ctrl, nu) X(qfrc_applied, nv) X(xfrc_applied, 6 * nb) X(qacc_warmstart, nv) \
-  X(time, 1) X(act, na) X(act_dot, na) X(mocap_pos, 3 * nmc) X(mocap_quat, 4 * nmc) X(eq_active, neq) X(ten_length, nten)  \
+  X(time, 1) X(act, na) X(act_dot, na) X(mocap_pos, 3 * nmc) X(mocap_quat, 4 * nmc) X(eq_active, neq) X(ten_length, nten) X(ten_J, nten * nv)  \
   /* position stage */                                                                                 \
   X(xpos, 3 * nb) X(xquat, 4 * nb) X(xmat, 9 * nb) X(xipos, 3 * nb) X(ximat, 9 * nb)                   \
   X(xanchor, 3 * nj) X(xaxis, 3 * nj) X(geom_xpos, 3 * ng) X(geom_xmat, 9 * ng)                        \

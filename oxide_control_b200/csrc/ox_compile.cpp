@@ -76,6 +76,7 @@ const std::map<std::string, std::set<std::string>>& schema() {
       {"tendon_fixed", {"name", "class", "group", "limited", "range", "solreflimit", "solimplimit", "solreffriction", "solimpfriction", "margin",
                         "frictionloss", "springlength", "stiffness", "damping", "user", "width", "material", "rgba"}},
       {"tendon_joint", {"joint", "coef"}},
+      {"tendon_site", {"site"}},
       {"equality_common", {"name", "class", "active", "solref", "solimp", "body1", "body2", "anchor", "joint1", "joint2", "polycoef", "relpose", "torquescale"}},
       {"sensor_common", {"name", "joint", "actuator", "site", "body", "tendon", "objtype", "objname", "reftype", "refname", "cutoff",
                          "noise", "user"}},
@@ -1028,10 +1029,12 @@ ox_model* compile_mjcf(const std::string& xml) {
   // ---- fixed tendons: length = sum_i coef_i * q_i over hinge / slide joints; limits, spring (with dead band) and damper.
   // Spatial tendons (site / geom wrapping), tendon friction loss and tendon transmissions are outside the supported subset.
   t.ntendon = 0; t.nwrap = 0;
+  std::vector<char> spring_default;   // springlength unspecified: the length at qpos0 (known for spatial tendons only after the qpos0 pass)
   for (auto& ch : root->children)
     if (ch->name == "tendon")
       for (auto& e : ch->children) {
-        if (e->name != "fixed") cfail("tendon <" + e->name + "> is outside the supported subset (fixed)");
+        if (e->name != "fixed" && e->name != "spatial") cfail("tendon <" + e->name + "> is outside the supported subset (fixed, spatial)");
+        const bool spatial = e->name == "spatial";
         check_attrs(*e, "tendon_fixed");
         Attrs a = merged(B.c, *e, "tendon", "");
         const std::string tname = a.str_or("name", "");
@@ -1050,6 +1053,17 @@ ox_model* compile_mjcf(const std::string& xml) {
         int num = 0;
         double len0 = 0;
         for (auto& w : e->children) {
+          if (spatial) {   // straight segments through sites; wrapping geoms and pulleys are outside the supported subset
+            if (w->name != "site") cfail("tendon '" + tname + "': <" + w->name + "> in a spatial tendon is outside the supported subset (site)");
+            check_attrs(*w, "tendon_site");
+            const std::string* sn = w->attr("site");
+            if (!sn) pfail(*w, "tendon <site> requires site");
+            const int sid = find_name(nm[OX_OBJ_SITE], *sn);
+            if (sid < 0) cfail("tendon '" + tname + "': unknown site '" + *sn + "'");
+            M->v_wrap_objid.push_back(sid); M->v_wrap_prm.push_back(0);
+            num++; t.nwrap++;
+            continue;
+          }
           if (w->name != "joint") pfail(*w, "a fixed tendon holds <joint> elements only");
           check_attrs(*w, "tendon_joint");
           const std::string* jn = w->attr("joint");
@@ -1064,6 +1078,9 @@ ox_model* compile_mjcf(const std::string& xml) {
           num++; t.nwrap++;
         }
         if (!num) cfail("tendon '" + tname + "': no joints");
+        if (spatial && num < 2) cfail("tendon '" + tname + "': a spatial tendon needs at least two sites");
+        M->v_tendon_type.push_back(spatial ? OX_TEN_SPATIAL : OX_TEN_FIXED);
+        spring_default.push_back(spring[0] < 0 && spring[1] < 0);
         M->v_tendon_num.push_back(num); M->v_tendon_limited.push_back(limited ? 1 : 0);
         M->v_tendon_range.push_back(range[0]); M->v_tendon_range.push_back(range[1]);
         M->v_tendon_margin.push_back(a.num("margin", 0));
@@ -1361,13 +1378,39 @@ ox_model* compile_mjcf(const std::string& xml) {
         for (int k = 0; k < 3; k++) M->v_dof_invweight0[d + k] = a;
       } else M->v_dof_invweight0[d] = Minv[d * nv + d];
     }
-    for (int i = 0; i < t.ntendon; i++) {   // tendon_invweight0 = J M^-1 J' with the (constant) tendon Jacobian
-      double w = 0;
-      for (int a = 0; a < M->v_tendon_num[i]; a++)
-        for (int c = 0; c < M->v_tendon_num[i]; c++) {
-          const int wa = M->v_tendon_adr[i] + a, wc = M->v_tendon_adr[i] + c;
-          w += M->v_wrap_prm[wa] * M->v_wrap_prm[wc] * Minv[jd[M->v_wrap_objid[wa]] * nv + jd[M->v_wrap_objid[wc]]];
+    for (int i = 0; i < t.ntendon; i++) {   // tendon_invweight0 = J M^-1 J' with the tendon Jacobian at qpos0 (constant for fixed tendons)
+      std::vector<double> J0(nv, 0.0);
+      const int adr = M->v_tendon_adr[i], num = M->v_tendon_num[i];
+      if (M->v_tendon_type[i] == OX_TEN_FIXED) {
+        for (int a = 0; a < num; a++) J0[jd[M->v_wrap_objid[adr + a]]] += M->v_wrap_prm[adr + a];
+      } else {
+        double L0 = 0;
+        std::vector<double> ja, jb, jr_;
+        for (int a = 0; a + 1 < num; a++) {
+          double p[2][3];
+          int bodies[2];
+          for (int s2 = 0; s2 < 2; s2++) {
+            const int sid = M->v_wrap_objid[adr + a + s2];
+            bodies[s2] = M->v_site_bodyid[sid];
+            double r3[3];
+            hm::rotvec(r3, &M->v_site_pos[3 * sid], &xquat[4 * bodies[s2]]);
+            for (int c = 0; c < 3; c++) p[s2][c] = xpos[3 * bodies[s2] + c] + r3[c];
+          }
+          double dvec[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]};
+          const double len = std::sqrt(dvec[0] * dvec[0] + dvec[1] * dvec[1] + dvec[2] * dvec[2]);
+          L0 += len;
+          if (len < OX_MINVAL) continue;
+          jac(bodies[0], p[0], ja, jr_);
+          jac(bodies[1], p[1], jb, jr_);
+          for (int k = 0; k < nv; k++)
+            for (int c = 0; c < 3; c++) J0[k] += dvec[c] / len * (jb[c * nv + k] - ja[c * nv + k]);
         }
+        M->v_tendon_length0[i] = L0;
+        if (spring_default[i]) { M->v_tendon_lengthspring[2 * i] = L0; M->v_tendon_lengthspring[2 * i + 1] = L0; }
+      }
+      double w = 0;
+      for (int a = 0; a < nv; a++)
+        for (int c = 0; c < nv; c++) w += J0[a] * Minv[a * nv + c] * J0[c];
       M->v_tendon_invweight0[i] = w;
     }
     for (int b = 1; b < nbody; b++) {

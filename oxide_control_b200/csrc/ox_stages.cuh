@@ -631,17 +631,61 @@ struct Env {
   }
 
   // ============================================================ passive forces
-  // fixed tendons (mj_tendon): length = sum of coef * joint coordinate; the Jacobian is the constant coefficient vector
+  // mj_tendon: length and Jacobian row (ten_J) of tendon i. Fixed: length = sum of coef * joint coordinate, J = the coefficients.
+  // Spatial: straight segments through sites, length = sum |p_{k+1} - p_k|, J = sum dir_k' (Jp(site_{k+1}) - Jp(site_k)).
   OX_HD void tendon_length(int i) const {
+    const int nv = m.h().nv, adr = m.tendon_adr(i);
     T L = 0;
     OX_MLOOP
-    for (int w = 0; w < m.tendon_num(i); w++) L += m.wrap_prm(m.tendon_adr(i) + w) * at(b.qpos, m.jnt_qposadr(m.wrap_objid(m.tendon_adr(i) + w)));
+    for (int k = 0; k < nv; k++) at(b.ten_J, i * nv + k) = 0;
+    if (m.tendon_type(i) == OX_TEN_FIXED) {
+      OX_MLOOP
+      for (int w = 0; w < m.tendon_num(i); w++) {
+        const int j = m.wrap_objid(adr + w);
+        L += m.wrap_prm(adr + w) * at(b.qpos, m.jnt_qposadr(j));
+        at(b.ten_J, i * nv + m.jnt_dofadr(j)) += m.wrap_prm(adr + w);
+      }
+    } else {
+      OX_MLOOP
+      for (int w = 0; w + 1 < m.tendon_num(i); w++) {
+        const int sites[2] = {m.wrap_objid(adr + w), m.wrap_objid(adr + w + 1)};
+        T pa[3], pb[3], dir[3];
+        ld<3>(pa, b.site_xpos, 3 * sites[0]);
+        ld<3>(pb, b.site_xpos, 3 * sites[1]);
+        dir[0] = pb[0] - pa[0]; dir[1] = pb[1] - pa[1]; dir[2] = pb[2] - pa[2];
+        const T len = ox_sqrt(dot3(dir, dir));
+        L += len;
+        if (len < (T)OX_MINVAL) continue;
+        dir[0] /= len; dir[1] /= len; dir[2] /= len;
+        OX_MLOOP
+        for (int s = 0; s < 2; s++) {   // + Jp(site b) - Jp(site a), projected on the segment direction
+          const T sign = s == 0 ? (T)-1 : (T)1;
+          const T* pt = s == 0 ? pa : pb;
+          const int sb = m.site_bodyid(sites[s]);
+          const int body = m.body_weldid(sb);
+          if (!body) continue;
+          T sc[3], offset[3];
+          ld<3>(sc, b.subtree_com, 3 * m.body_rootid(sb));
+          offset[0] = pt[0] - sc[0]; offset[1] = pt[1] - sc[1]; offset[2] = pt[2] - sc[2];
+          const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+          OX_MLOOP
+          for (int d_ = 0, dof = last_; d_ < m.dof_depth(last_); d_++, dof = m.dof_parentid(dof)) {
+            T cd[6], jp[3];
+            ld<6>(cd, b.cdof, 6 * dof);
+            cross3(jp, cd, offset);
+            jp[0] += cd[3]; jp[1] += cd[4]; jp[2] += cd[5];
+            at(b.ten_J, i * nv + dof) += sign * dot3(dir, jp);
+          }
+        }
+      }
+    }
     at(b.ten_length, i) = L;
   }
   OX_HD T tendon_velocity(int i) const {
+    const int nv = m.h().nv;
     T v = 0;
     OX_MLOOP
-    for (int w = 0; w < m.tendon_num(i); w++) v += m.wrap_prm(m.tendon_adr(i) + w) * at(b.qvel, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w)));
+    for (int k = 0; k < nv; k++) v += at(b.ten_J, i * nv + k) * at(b.qvel, k);
     return v;
   }
   // spring with dead band [lengthspring0, lengthspring1] and damper, mapped to the joints through J'
@@ -652,8 +696,9 @@ struct Env {
     else if (L < lo) f = m.tendon_stiffness(i) * (lo - L);
     f -= m.tendon_damping(i) * tendon_velocity(i);
     if (f == 0) return;
+    const int nv = m.h().nv;
     OX_MLOOP
-    for (int w = 0; w < m.tendon_num(i); w++) at(b.qfrc_passive, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w))) += m.wrap_prm(m.tendon_adr(i) + w) * f;
+    for (int k = 0; k < nv; k++) at(b.qfrc_passive, k) += at(b.ten_J, i * nv + k) * f;
   }
   OX_HDN void passive() const {
     const auto& h = m.h();
@@ -765,7 +810,7 @@ struct Env {
       if (m.actuator_trntype(i) == OX_TRN_TENDON) {   // moment = gear * tendon Jacobian (the coefficient vector)
         const int tn = m.actuator_trnid(i);
         OX_MLOOP
-        for (int w = 0; w < m.tendon_num(tn); w++) at(b.qfrc_actuator, m.jnt_dofadr(m.wrap_objid(m.tendon_adr(tn) + w))) += gf * m.wrap_prm(m.tendon_adr(tn) + w);
+        for (int k = 0; k < nv; k++) at(b.qfrc_actuator, k) += gf * at(b.ten_J, tn * nv + k);
       } else {
         at(b.qfrc_actuator, m.jnt_dofadr(m.actuator_trnid(i))) += gf;
       }
@@ -1847,11 +1892,10 @@ struct Env {
         for (int k = 0; k < nv; k++) at(b.efc_J, r * nv + k) = 0;
         T vel = 0;
         OX_MLOOP
-        for (int w = 0; w < m.tendon_num(i); w++) {
-          const int da = m.jnt_dofadr(m.wrap_objid(m.tendon_adr(i) + w));
-          const T c = (T)(-side) * m.wrap_prm(m.tendon_adr(i) + w);
-          at(b.efc_J, r * nv + da) += c;
-          vel += c * at(b.qvel, da);
+        for (int k = 0; k < nv; k++) {
+          const T c = (T)(-side) * at(b.ten_J, i * nv + k);
+          at(b.efc_J, r * nv + k) = c;
+          vel += c * at(b.qvel, k);
         }
         T aref, sr[2], si[5];
         OX_LDM(2, sr, tendon_solref_lim, 2 * i);

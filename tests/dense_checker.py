@@ -90,7 +90,7 @@ class DenseModel:
            "dof_bodyid", "geom_type", "geom_bodyid", "geom_condim", "geom_priority", "pair_geom1", "pair_geom2", "pair_dim",
            "actuator_trnid", "actuator_trntype", "actuator_gaintype", "actuator_biastype", "actuator_ctrllimited", "actuator_forcelimited",
            "actuator_dyntype", "actuator_actadr", "actuator_actlimited", "body_mocapid", "eq_type", "eq_obj1id", "eq_obj2id",
-           "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "wrap_objid"]
+           "sensor_type", "sensor_objid", "sensor_adr", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "tendon_type", "wrap_objid"]
     REAL = ["qpos0", "qpos_spring", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_invweight0",
             "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin", "jnt_solref", "jnt_solimp", "dof_armature", "dof_damping",
             "dof_invweight0", "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_solmix", "geom_solref", "geom_solimp",
@@ -251,7 +251,7 @@ def passive_force(dm, qpos, qvel):
             f[da] -= k * (qpos[qa] - dm.qpos_spring[qa])
     f = f - dm.dof_damping * qvel
     for i in range(dm.ntendon):                                          # tendon spring (dead band) and damper through the coefficient vector
-        Jt, L = tendon_jacobian(dm, i), tendon_jacobian(dm, i) @ tendon_coords(dm, qpos)
+        Jt, L = dm._tenJ[i], dm._tenL[i]
         lo, hi = dm.tendon_lengthspring[2 * i:2 * i + 2]
         frc = dm.tendon_stiffness[i] * ((hi - L) if L > hi else (lo - L) if L < lo else 0.0) - dm.tendon_damping[i] * (Jt @ qvel)
         f = f + Jt * frc
@@ -259,10 +259,31 @@ def passive_force(dm, qpos, qvel):
 
 
 def tendon_jacobian(dm, i):
-    Jt = np.zeros(dm.nv)
-    for w in range(int(dm.tendon_adr[i]), int(dm.tendon_adr[i] + dm.tendon_num[i])):
-        Jt[int(dm.jnt_dofadr[int(dm.wrap_objid[w])])] += dm.wrap_prm[w]
-    return Jt
+    return dm._tenJ[i]
+
+
+def tendons(dm, kin, qpos):
+    """lengths and Jacobian rows of all tendons -> dm._tenL, dm._tenJ. Fixed: the coefficient vector; spatial: the path through the
+    sites, differentiated through the autodiff point Jacobians of the bodies that carry them."""
+    dm._tenJ, dm._tenL = np.zeros((dm.ntendon, dm.nv)), np.zeros(dm.ntendon)
+    x = tendon_coords(dm, qpos)
+    for i in range(dm.ntendon):
+        ws = range(int(dm.tendon_adr[i]), int(dm.tendon_adr[i] + dm.tendon_num[i]))
+        if int(dm.tendon_type[i]) == 0:
+            for w in ws:
+                dm._tenJ[i, int(dm.jnt_dofadr[int(dm.wrap_objid[w])])] += dm.wrap_prm[w]
+            dm._tenL[i] = dm._tenJ[i] @ x
+        else:
+            pts = []
+            for w in ws:
+                sid = int(dm.wrap_objid[w]); bd = int(dm.site_bodyid[sid])
+                pts.append((bd, kin.P[bd] + kin.R[bd] @ dm.site_pos[3 * sid:3 * sid + 3]))
+            for (ba, pa), (bb, pb) in zip(pts[:-1], pts[1:]):
+                seg = pb - pa
+                ln = np.linalg.norm(seg)
+                dm._tenL[i] += ln
+                if ln > MINVAL:
+                    dm._tenJ[i] += seg / ln @ (kin.point_jac(bb, pb) - kin.point_jac(ba, pa))
 
 
 def tendon_coords(dm, qpos):
@@ -283,13 +304,14 @@ def actuator_force(dm, qpos, qvel, ctrl, act=None):
     for i in range(dm.nu):
         j, gear = int(dm.actuator_trnid[i]), dm.actuator_gear[i]
         if int(dm.actuator_trntype[i]) == 3:                     # tendon transmission: moment arm = gear * (tendon coefficient vector)
-            moment = gear * tendon_jacobian(dm, j)
+            moment = gear * dm._tenJ[j]
             da = None
+            tlen = gear * dm._tenL[j]
         else:
             moment = np.zeros(dm.nv)
             da = int(dm.jnt_dofadr[j])
             moment[da] = gear
-        length, vel = moment @ tendon_coords(dm, qpos), moment @ qvel
+        length, vel = (tlen if da is None else moment @ tendon_coords(dm, qpos)), moment @ qvel
         u = ctrl[i]
         if dm.actuator_ctrllimited[i] and not dm.dis("clampctrl"):
             u = min(max(u, dm.actuator_ctrlrange[2 * i]), dm.actuator_ctrlrange[2 * i + 1])
@@ -745,8 +767,7 @@ def constraints(dm: DenseModel, kin: Kin, qpos, qvel, contacts, eq_active=None):
         for i in range(dm.ntendon):
             if not dm.tendon_limited[i]:
                 continue
-            Jt = tendon_jacobian(dm, i)
-            L = Jt @ tendon_coords(dm, qpos)
+            Jt, L = dm._tenJ[i], dm._tenL[i]
             for sign, dist in ((1.0, L - dm.tendon_range[2 * i]), (-1.0, dm.tendon_range[2 * i + 1] - L)):
                 if dist < dm.tendon_margin[i]:
                     row = sign * Jt
@@ -1052,6 +1073,7 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     qpos, qvel = np.asarray(qpos, float), np.asarray(qvel, float)
     act = np.zeros(dm.na) if act is None else np.asarray(act, float)
     kin = Kin(dm, qpos, qvel, mocap)
+    tendons(dm, kin, qpos)
     M, c = mass_matrix_and_bias(dm, kin)
     fa, frc, act_dot, dfdv = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float), act)
     f = passive_force(dm, qpos, qvel) - c + fa

@@ -78,7 +78,7 @@ def test_tendon_transmission_closed_form():
 
 def test_compiler_refusals():
     body = "<worldbody><body><joint name='j' type='hinge'/><geom size='0.1'/><site name='s'/><body pos='0 0 1'><joint name='b' type='ball'/><geom size='0.1'/></body></body></worldbody>"
-    for tendon, msg in (("<spatial><site site='s'/></spatial>", "spatial"), ("<fixed><joint joint='b' coef='1'/></fixed>", "hinge / slide"),
+    for tendon, msg in (("<spatial><site site='s'/></spatial>", "two sites"), ("<spatial><site site='s'/><geom geom='g'/></spatial>", "outside the supported subset"), ("<fixed><joint joint='b' coef='1'/></fixed>", "hinge / slide"),
                         ("<fixed><joint joint='zz' coef='1'/></fixed>", "unknown joint"), ("<fixed frictionloss='1'><joint joint='j' coef='1'/></fixed>", "frictionloss"),
                         ("<fixed/>", "no joints")):
         with pytest.raises(ox.MjsError, match=msg):
@@ -118,6 +118,75 @@ def test_gpu_vs_oracle(mode, specialize):
         with pytest.raises(ox.Error, match="coop"):
             ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
         return
+    b = ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
+    b.set("qpos", qpos); b.set("qvel", qvel); b.ctrl_philox(True, SEED)
+    b.step(nsteps); b.sync()
+    ref = {f: [] for f in ("qpos", "qacc", "sensordata")}
+    for e in range(nenv):
+        od = OracleData(m)
+        od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]
+        for s in range(nsteps):
+            od.fill_ctrl_philox(e, s); od.step()
+        for f in ref:
+            ref[f].append(od.field(f).copy())
+    for f in ref:
+        assert rel_err(b.get(f), np.stack(ref[f])) <= 1e-6, f
+    assert int(b.diverged().sum()) == 0
+
+
+SPATIAL = """<mujoco><compiler angle="radian"/><option timestep="0.002" gravity="0 0 0"/><worldbody>
+<site name="o" pos="0 0 0"/>
+<body name="a" pos="0.3 0 0.4"><freejoint/><geom type="sphere" size="0.05" mass="2" contype="0" conaffinity="0"/><site name="sa" pos="0 0 0"/></body>
+</worldbody><tendon><spatial name="t" {attrs}><site site="o"/><site site="sa"/></spatial></tendon>
+<sensor><tendonpos tendon="t"/><tendonvel tendon="t"/></sensor></mujoco>"""
+
+
+def test_spatial_tendon_closed_forms():
+    """A point mass on a string from the origin: L = |p|, Ldot = p.v / |p|, the spring pulls along -p / |p| with k (L - L0), and the
+    limit row is the unit radial direction (J = -side * p / |p| on the translational dofs)."""
+    m = ox.Model.from_xml_string(SPATIAL.format(attrs='stiffness="30" damping="2" springlength="0.2"'))
+    assert list(m.tendon_type) == [1] and abs(m.tendon_length0[0] - 0.5) < 1e-15
+    assert abs(m.tendon_invweight0[0] - 0.5) < 1e-12                      # J M^-1 J' = 1/m for a unit radial Jacobian
+    od = OracleData(m)
+    p, v = np.array([0.2, -0.1, 0.3]), np.array([0.4, 0.2, -0.5])
+    od.field("qpos")[:3] = p; od.field("qvel")[:3] = v
+    od.forward()
+    L, u = np.linalg.norm(p), p / np.linalg.norm(p)
+    assert np.allclose(od.field("sensordata"), [L, u @ v], atol=1e-14) and np.allclose(od.field("ten_J")[:3], u, atol=1e-14)
+    f = -30 * (L - 0.2) - 2 * (u @ v)
+    assert np.allclose(od.field("qfrc_passive")[:3], f * u, atol=1e-13) and np.allclose(od.field("qacc")[:3], f * u / 2, atol=1e-12)
+    lim = ox.Model.from_xml_string(SPATIAL.format(attrs='limited="true" range="0 0.45"'))
+    od = OracleData(lim)
+    od.forward()                                                          # L0 = 0.5 > 0.45: the upper limit is violated by 0.05
+    assert od.int("nefc") == 1 and abs(od.field("efc_pos")[0] + 0.05) < 1e-15
+    assert np.allclose(od.field("efc_J")[:3], -np.array([0.3, 0, 0.4]) / 0.5, atol=1e-14) and od.field("efc_force")[0] > 0
+    for _ in range(2000):
+        od.step()
+    assert np.linalg.norm(od.field("qpos")[:3]) < 0.452                   # pulled back inside the limit
+
+
+def test_spatial_tendon_host_instantiation():
+    m = ox.Model.from_xml_string(ZOO["zoo_q"])
+    nenv, nsteps = 5, 250
+    qpos, qvel = random_state(m, nenv, seed=103)
+    hb = HostBatch(m, nenv, "f64")
+    hb.set("qpos", qpos); hb.set("qvel", qvel)
+    hb.step(nsteps, True, SEED, 0, 0)
+    for e in range(nenv):
+        od = OracleData(m)
+        od.field("qpos")[:] = qpos[e]; od.field("qvel")[:] = qvel[e]
+        for s in range(nsteps):
+            od.fill_ctrl_philox(e, s); od.step()
+        for f in ("qpos", "qvel", "qacc", "sensordata", "ten_length", "ten_J"):
+            assert rel_err(hb.get(f)[e], od.field(f)) <= 1e-8, (f, e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,specialize", [("fused", 0), ("staged", 0), ("fused", 2)])
+def test_spatial_tendon_gpu_vs_oracle(mode, specialize):
+    m = ox.Model.from_xml_string(ZOO["zoo_q"])
+    nenv, nsteps = 64, 150
+    qpos, qvel = random_state(m, nenv, seed=107)
     b = ox.BatchedPhysics(m, nenv, precision="f64", mode=mode, specialize=specialize)
     b.set("qpos", qpos); b.set("qvel", qvel); b.ctrl_philox(True, SEED)
     b.step(nsteps); b.sync()

@@ -470,5 +470,39 @@ ZOO_P = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O, "zoo_p": ZOO_P}
+# N3: spatial tendons (straight segments through sites): a limited tendon from the world to a swinging arm's tip through an
+# intermediate site, a spring-damper tendon between two free bodies, an actuator pulling on a spatial tendon
+ZOO_Q = """
+<mujoco model="zoo_q">
+  <compiler angle="radian"/>
+  <option timestep="0.004" tolerance="1e-13"/>
+  <default><joint damping="0.05" armature="0.003"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <site name="anchor" pos="0.1 0 1.1"/>
+    <body name="arm" pos="0 0 1">
+      <joint name="sh" type="hinge" axis="0 1 0"/>
+      <geom name="arm" type="capsule" fromto="0 0 0 0.4 0 0" size="0.03"/>
+      <site name="mid" pos="0.2 0 0.05"/>
+      <body name="fore" pos="0.4 0 0">
+        <joint name="el" type="hinge" axis="0 1 0" range="-2.2 2.2" limited="true"/>
+        <joint name="tw" type="hinge" axis="1 0 0"/>
+        <geom name="fore" type="capsule" fromto="0 0 0 0.3 0 0" size="0.025"/>
+        <site name="tip" pos="0.3 0 0.03"/>
+      </body>
+    </body>
+    <body name="puck" pos="0.5 0.2 0.4"><freejoint/><geom name="puck" type="sphere" size="0.05"/><site name="puck_c" pos="0 0 0.05"/></body>
+    <body name="bob" pos="0.6 -0.1 0.25"><freejoint/><geom name="bob" type="sphere" size="0.04"/><site name="bob_c" pos="0.01 0 0"/></body>
+  </worldbody>
+  <tendon>
+    <spatial name="leash" limited="true" range="0 0.62" solreflimit="0.015 1"><site site="anchor"/><site site="mid"/><site site="tip"/></spatial>
+    <spatial name="bungee" stiffness="40" damping="0.8" springlength="0.25"><site site="tip"/><site site="puck_c"/></spatial>
+    <spatial name="cord" stiffness="25" range="0.05 0.5"><site site="puck_c"/><site site="bob_c"/></spatial>
+  </tendon>
+  <actuator><motor name="winch" tendon="leash" gear="-3"/><motor joint="tw" gear="0.2"/></actuator>
+  <sensor><tendonpos tendon="leash"/><tendonvel tendon="bungee"/><tendonpos tendon="cord"/><actuatorpos actuator="winch"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O, "zoo_p": ZOO_P, "zoo_q": ZOO_Q}
 NOCONTACT = {"zoo_d": ZOO_D}
