@@ -493,6 +493,7 @@ ZOO_Q = """
     </body>
     <body name="puck" pos="0.5 0.2 0.4"><freejoint/><geom name="puck" type="sphere" size="0.05"/><site name="puck_c" pos="0 0 0.05"/></body>
     <body name="bob" pos="0.6 -0.1 0.25"><freejoint/><geom name="bob" type="sphere" size="0.04"/><site name="bob_c" pos="0.01 0 0"/></body>
+    <body name="pebble" pos="-0.6 0.3 0.0495"><freejoint name="pebbleroot"/><geom name="pebble" type="sphere" size="0.05"/></body>
   </worldbody>
   <tendon>
     <spatial name="leash" limited="true" range="0 0.62" solreflimit="0.015 1"><site site="anchor"/><site site="mid"/><site site="tip"/></spatial>
