@@ -117,7 +117,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(qpos0, nq, 1) X(qpos_spring, nq, 1)                                                             \
   X(body_pos, nbody, 3) X(body_quat, nbody, 4) X(body_ipos, nbody, 3) X(body_iquat, nbody, 4)      \
   X(body_mass, nbody, 1) X(body_inertia, nbody, 3) X(body_subtreemass, nbody, 1)                   \
-  X(body_invweight0, nbody, 2)                                                                      \
+  X(body_invweight0, nbody, 2) X(body_fluid, nfluid, 11)                                            \
   X(jnt_pos, njnt, 3) X(jnt_axis, njnt, 3) X(jnt_stiffness, njnt, 1) X(jnt_range, njnt, 2)         \
   X(jnt_margin, njnt, 1) X(jnt_solref, njnt, 2) X(jnt_solimp, njnt, 5)                             \
   X(dof_armature, nv, 1) X(dof_damping, nv, 1) X(dof_invweight0, nv, 1)                            \
@@ -151,6 +151,11 @@ typedef struct ox_model_tables {
   int32_t noslip_iterations;   /* noslip post-pass of the friction dimensions (0 = off, MuJoCo's default) */
   int32_t nfloss;              /* dofs with frictionloss > 0: one Huber-cost row each, after the equality rows */
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, noslip_tolerance;
+  /* medium (mjOption density / viscosity / wind): inertia-box fluid forces of mj_passive. nfluid = nbody when density or
+   * viscosity is positive, else 0; body_fluid[11] per body = viscous torque and force coefficients (pi d^3 mu, 3 pi d mu),
+   * quadratic drag coefficients of the three box faces (force, then torque), and the wind velocity */
+  int32_t nfluid;
+  double density, viscosity, wind[3];
   /* mjStatistic subset */
   double meaninertia;
 #define OX_X(name, n, w) const int32_t* name;

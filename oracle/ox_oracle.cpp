@@ -1083,6 +1083,55 @@ void passive(const Model* m, Data* d) {
     if (f != 0)
       for (int k = 0; k < m->nv; k++) d->qfrc_passive[k] += d->ten_J[(size_t)i * m->nv + k] * f;
   }
+  // mj_inertiaBoxFluidModel (engine_passive.c): viscous and quadratic drag on the equivalent inertia box of every body. Done from
+  // mjOption density / viscosity / wind and body_inertia as MuJoCo does at run time (the product uses a table compiled from them).
+  if (m->viscosity > 0 || m->density > 0)
+    for (int b = 1; b < m->nbody; b++) {
+      const double mass = m->body_mass[b], *I = &m->body_inertia[3 * b];
+      if (mass < OX_MINVAL) continue;
+      const double* R = &d->ximat[9 * b];
+      double offset[3], vel[3], lvel[6], lfrc[6] = {0, 0, 0, 0, 0, 0}, box[3];
+      for (int k = 0; k < 3; k++) offset[k] = d->xipos[3 * b + k] - d->subtree_com[3 * m->body_rootid[b] + k];
+      // mj_objectVelocity(mjOBJ_BODY, flg_local = 1): velocity at xipos, rotated into the inertial frame; minus the wind
+      cross3(vel, &d->cvel[6 * b], offset);
+      for (int k = 0; k < 3; k++) vel[k] += d->cvel[6 * b + 3 + k] - m->wind[k];
+      for (int k = 0; k < 3; k++) {
+        lvel[k] = R[k] * d->cvel[6 * b] + R[3 + k] * d->cvel[6 * b + 1] + R[6 + k] * d->cvel[6 * b + 2];
+        lvel[3 + k] = R[k] * vel[0] + R[3 + k] * vel[1] + R[6 + k] * vel[2];
+      }
+      box[0] = std::sqrt(std::max(OX_MINVAL, I[1] + I[2] - I[0]) / mass * 6.0);
+      box[1] = std::sqrt(std::max(OX_MINVAL, I[0] + I[2] - I[1]) / mass * 6.0);
+      box[2] = std::sqrt(std::max(OX_MINVAL, I[0] + I[1] - I[2]) / mass * 6.0);
+      if (m->viscosity > 0) {
+        const double diam = (box[0] + box[1] + box[2]) / 3.0;
+        for (int k = 0; k < 3; k++) lfrc[k] = -OX_PI_D * diam * diam * diam * m->viscosity * lvel[k];
+        for (int k = 0; k < 3; k++) lfrc[3 + k] = -3.0 * OX_PI_D * diam * m->viscosity * lvel[3 + k];
+      }
+      if (m->density > 0) {
+        lfrc[3] -= 0.5 * m->density * box[1] * box[2] * std::fabs(lvel[3]) * lvel[3];
+        lfrc[4] -= 0.5 * m->density * box[0] * box[2] * std::fabs(lvel[4]) * lvel[4];
+        lfrc[5] -= 0.5 * m->density * box[0] * box[1] * std::fabs(lvel[5]) * lvel[5];
+        lfrc[0] -= m->density * box[0] * (std::pow(box[1], 4) + std::pow(box[2], 4)) * std::fabs(lvel[0]) * lvel[0] / 64.0;
+        lfrc[1] -= m->density * box[1] * (std::pow(box[0], 4) + std::pow(box[2], 4)) * std::fabs(lvel[1]) * lvel[1] / 64.0;
+        lfrc[2] -= m->density * box[2] * (std::pow(box[0], 4) + std::pow(box[1], 4)) * std::fabs(lvel[2]) * lvel[2] / 64.0;
+      }
+      double trq[3], frc[3];
+      for (int k = 0; k < 3; k++) {
+        trq[k] = R[3 * k] * lfrc[0] + R[3 * k + 1] * lfrc[1] + R[3 * k + 2] * lfrc[2];
+        frc[k] = R[3 * k] * lfrc[3] + R[3 * k + 1] * lfrc[4] + R[3 * k + 2] * lfrc[5];
+      }
+      // mj_applyFT at xipos
+      int body = b;
+      while (body && m->body_dofnum[body] == 0) body = m->body_parentid[body];
+      if (!body) continue;
+      for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i]) {
+        const double* cd = &d->cdof[6 * i];
+        double jp[3];
+        cross3(jp, cd, offset);
+        for (int k = 0; k < 3; k++) jp[k] += cd[3 + k];
+        d->qfrc_passive[i] += dot3(jp, frc) + dot3(cd, trq);
+      }
+    }
 }
 
 // ---------------------------------------------------------------- A.8 bias forces (RNE, flg_acc = 0)

@@ -228,6 +228,9 @@ ox_status ox_model_real_table(const ox_model* m, const char* name, const double*
   if (!std::strcmp(name, "impratio")) { *ptr = &m->t.impratio; *count = 1; return OX_OK; }
   if (!std::strcmp(name, "noslip_tolerance")) { *ptr = &m->t.noslip_tolerance; *count = 1; return OX_OK; }
   if (!std::strcmp(name, "meaninertia")) { *ptr = &m->t.meaninertia; *count = 1; return OX_OK; }
+  if (!std::strcmp(name, "density")) { *ptr = &m->t.density; *count = 1; return OX_OK; }
+  if (!std::strcmp(name, "viscosity")) { *ptr = &m->t.viscosity; *count = 1; return OX_OK; }
+  if (!std::strcmp(name, "wind")) { *ptr = m->t.wind; *count = 3; return OX_OK; }
   ox::set_error(std::string("unknown real table '") + name + "'");
   return OX_ERR_INVALID;
 }
@@ -237,7 +240,7 @@ int32_t ox_model_size(const ox_model* m, const char* name) {
   const ox_model_tables& t = m->t;
 #define S(f) if (!std::strcmp(name, #f)) return t.f;
   S(nq) S(nv) S(nu) S(na) S(nbody) S(njnt) S(ngeom) S(nsite) S(nM) S(npair) S(nsensor) S(nsensordata) S(nconmax) S(nefcmax) S(nvv) S(nmocap) S(neq) S(ntendon) S(nwrap)
-  S(integrator) S(solver) S(cone) S(iterations) S(ls_iterations) S(disableflags) S(noslip_iterations) S(nfloss)
+  S(integrator) S(solver) S(cone) S(iterations) S(ls_iterations) S(disableflags) S(noslip_iterations) S(nfloss) S(nfluid)
 #undef S
   return -1;
 }

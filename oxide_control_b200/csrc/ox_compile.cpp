@@ -314,6 +314,8 @@ void parse_geom(Builder& B, const XmlElem& e, int body, const std::string& child
   }
   g.density = a.num("density", g.density);
   g.mass = a.num("mass", -1);
+  if (a.has("fluidshape") && a.str("fluidshape") != "none")
+    cfail("geom '" + g.name + "': fluidshape='" + a.str("fluidshape") + "' (ellipsoid fluid model) is outside the supported subset (inertia-box model)");
   a.vec("friction", g.friction, 3, true);
   g.condim = (int)a.num("condim", g.condim);
   g.contype = (int)a.num("contype", g.contype);
@@ -620,6 +622,7 @@ ox_model* compile_mjcf(const std::string& xml) {
   t.disableflags = 0;
   t.noslip_iterations = 0;
   t.noslip_tolerance = 1e-6;
+  t.density = 0; t.viscosity = 0; t.wind[0] = t.wind[1] = t.wind[2] = 0;
 
   // pass 1: compiler, option, defaults (must precede use regardless of document order)
   for (auto& ch : root->children) {
@@ -663,6 +666,10 @@ ox_model* compile_mjcf(const std::string& xml) {
       t.noslip_iterations = (int)a.num("noslip_iterations", t.noslip_iterations);
       t.noslip_tolerance = a.num("noslip_tolerance", t.noslip_tolerance);
       if (t.noslip_iterations < 0) cfail("noslip_iterations must be >= 0");
+      t.density = a.num("density", t.density);
+      t.viscosity = a.num("viscosity", t.viscosity);
+      a.vec("wind", t.wind, 3);
+      if (t.density < 0 || t.viscosity < 0) cfail("option density / viscosity must be >= 0");
       if (a.has("integrator")) {
         const std::string& s = a.str("integrator");
         if (s == "Euler") t.integrator = OX_INT_EULER;
@@ -685,6 +692,8 @@ ox_model* compile_mjcf(const std::string& xml) {
       }
       if (t.cone == OX_CONE_ELLIPTIC && (t.solver == OX_SOL_PGS || t.noslip_iterations > 0))
         cfail("cone elliptic with the PGS solver or the noslip pass is outside the supported subset (Newton, CG)");
+      if ((t.density > 0 || t.viscosity > 0) && t.integrator == OX_INT_IMPLICITFAST)
+        cfail("fluid forces (option density / viscosity) with the implicitfast integrator (their velocity derivative is not built) are outside the supported subset");
       if (!(t.timestep > 0)) cfail("timestep must be positive");
       if (t.impratio <= 0) cfail("impratio must be positive");
       for (auto& f : ch->children) {
@@ -798,6 +807,26 @@ ox_model* compile_mjcf(const std::string& xml) {
       }
       M->v_body_dofnum[i] = nd;
     }
+  }
+  // inertia-box fluid model (mj_passive -> mj_inertiaBoxFluidModel): every body is replaced by the box with the same mass and
+  // principal inertia; the coefficients of its viscous (Stokes, equivalent sphere) and quadratic (face-by-face) drag are constants
+  t.nfluid = (t.density > 0 || t.viscosity > 0) ? nbody : 0;
+  M->v_body_fluid.assign((size_t)11 * t.nfluid, 0);
+  for (int i = 1; i < t.nfluid; i++) {
+    const double mass = M->v_body_mass[i], *I = &M->v_body_inertia[3 * i];
+    if (mass < OX_MINVAL) continue;   // massless bodies feel no medium
+    double bx[3];
+    for (int k = 0; k < 3; k++) bx[k] = std::sqrt(std::max(OX_MINVAL, I[(k + 1) % 3] + I[(k + 2) % 3] - I[k]) / mass * 6.0);
+    double* f = &M->v_body_fluid[11 * i];
+    const double diam = (bx[0] + bx[1] + bx[2]) / 3, pi = 3.14159265358979323846;
+    f[0] = pi * diam * diam * diam * t.viscosity;   // torque = -f0 * angular velocity
+    f[1] = 3 * pi * diam * t.viscosity;              // force  = -f1 * linear velocity
+    for (int k = 0; k < 3; k++) {
+      const double a = bx[k], b = bx[(k + 1) % 3], c = bx[(k + 2) % 3];
+      f[2 + k] = 0.5 * t.density * b * c;                                   // force_k  -= f * |v_k| v_k
+      f[5 + k] = t.density * a * (b * b * b * b + c * c * c * c) / 64;      // torque_k -= f * |w_k| w_k
+    }
+    for (int k = 0; k < 3; k++) f[8 + k] = t.wind[k];
   }
   nm[OX_OBJ_BODY][0] = "world";
   for (int i = nbody - 1; i >= 0; i--) {

@@ -260,6 +260,10 @@ struct Coop {
         gsync();
         if (gl == 0) for (int i = 0; i < h.ntendon; i++) env.passive_tendon(i);
       }
+      if (h.nfluid > 0) {    // fluid drag: a body's wrench touches its whole dof chain, same rule
+        gsync();
+        if (gl == 0) for (int bd = 1; bd < h.nfluid; bd++) env.passive_fluid(bd);
+      }
     }
     down(1, [&](int i) { env.rne_fwd_body(i); });
     gather_up<6>(b.cfrc, 1);

@@ -714,6 +714,49 @@ struct Env {
     for (int i = 0; i < nv; i++) at(b.qfrc_passive, i) -= m.dof_damping(i) * at(b.qvel, i);
     OX_MLOOP
     for (int i = 0; i < h.ntendon; i++) passive_tendon(i);
+    OX_MLOOP
+    for (int bd = 1; bd < h.nfluid; bd++) passive_fluid(bd);
+  }
+  // mj_inertiaBoxFluidModel: drag of the medium on the equivalent inertia box of body bd. The body's velocity at its com in
+  // the inertial frame (ximat), minus the wind; a viscous term linear in it (equivalent sphere) and a quadratic term face by
+  // face (coefficients: body_fluid, compiled from density / viscosity / the box sizes); the wrench is applied at xipos
+  OX_HD void passive_fluid(int bd) const {
+    if (m.body_mass(bd) < (T)OX_MINVAL) return;
+    const int body = m.body_weldid(bd);
+    if (!body) return;
+    T cv[6], xi[3], sc[3], offset[3], R[9], vel[3], lw[3], lv[3], lt[3], lf[3], f[6];
+    ld<6>(cv, b.cvel, 6 * bd);
+    ld<3>(xi, b.xipos, 3 * bd);
+    ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bd));
+    ld<9>(R, b.ximat, 9 * bd);
+    offset[0] = xi[0] - sc[0]; offset[1] = xi[1] - sc[1]; offset[2] = xi[2] - sc[2];
+    cross3(vel, cv, offset);   // cvel is expressed at the subtree com: v(xipos) = v + w x offset
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) vel[k] += cv[3 + k] - m.body_fluid(11 * bd + 8 + k);
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) {   // into the inertial frame: R' w, R' v
+      lw[k] = R[k] * cv[0] + R[3 + k] * cv[1] + R[6 + k] * cv[2];
+      lv[k] = R[k] * vel[0] + R[3 + k] * vel[1] + R[6 + k] * vel[2];
+    }
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) {
+      lt[k] = -m.body_fluid(11 * bd) * lw[k] - m.body_fluid(11 * bd + 5 + k) * ox_abs(lw[k]) * lw[k];
+      lf[k] = -m.body_fluid(11 * bd + 1) * lv[k] - m.body_fluid(11 * bd + 2 + k) * ox_abs(lv[k]) * lv[k];
+    }
+    OX_MLOOP
+    for (int k = 0; k < 3; k++) {   // back to the world frame: (force, torque)
+      f[k] = R[3 * k] * lf[0] + R[3 * k + 1] * lf[1] + R[3 * k + 2] * lf[2];
+      f[3 + k] = R[3 * k] * lt[0] + R[3 * k + 1] * lt[1] + R[3 * k + 2] * lt[2];
+    }
+    const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+    OX_MLOOP
+    for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
+      T cd[6], jp[3];
+      ld<6>(cd, b.cdof, 6 * i);
+      cross3(jp, cd, offset);
+      jp[0] += cd[3]; jp[1] += cd[4]; jp[2] += cd[5];
+      at(b.qfrc_passive, i) += dot3(jp, f) + dot3(cd, f + 3);
+    }
   }
   OX_HD void passive_joint(int j) const {  // joint spring: touches only this joint's dofs
     {

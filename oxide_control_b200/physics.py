@@ -167,7 +167,7 @@ class Model:
         dp = C.POINTER(C.c_double)()
         if L.ox_model_real_table(self._h, name.encode(), C.byref(dp), C.byref(cnt)) == A.OX_OK:
             arr = np.ctypeslib.as_array(dp, shape=(cnt.value,)).copy() if cnt.value else np.zeros(0)
-            if name in ("timestep", "tolerance", "ls_tolerance", "impratio", "meaninertia", "noslip_tolerance"):
+            if name in ("timestep", "tolerance", "ls_tolerance", "impratio", "meaninertia", "noslip_tolerance", "density", "viscosity"):
                 arr = float(arr[0])
             self._cache[name] = arr
             return arr

@@ -104,9 +104,10 @@ class DenseModel:
         self.m = model
         for k in ("nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "npair", "integrator", "disableflags", "cone", "nmocap", "neq", "nsensor", "nsensordata", "ntendon"):
             setattr(self, k, int(getattr(model, k)))
-        for k in ("timestep", "impratio"):
+        for k in ("timestep", "impratio", "density", "viscosity"):
             setattr(self, k, float(getattr(model, k)))
         self.gravity = np.asarray(model.gravity, dtype=np.float64)
+        self.wind = np.asarray(model.wind, dtype=np.float64)
         for k in self.INT:
             setattr(self, k, np.asarray(getattr(model, k), dtype=np.int64))
         for k in self.REAL:
@@ -231,6 +232,38 @@ def sub_quat(qa, qb):
     if ang > np.pi:
         ang -= 2 * np.pi
     return d[1:] / s * ang
+
+
+def fluid_force(dm, kin):
+    """Drag of the medium (MuJoCo's inertia-box model, computation documentation 'Passive forces'): each body is the box of equal
+    mass and principal inertia, moving with the velocity of its centre of mass relative to the wind; Stokes drag of the equivalent
+    sphere plus quadratic drag face by face, in the inertial frame; mapped to the joints by the exact (autodiff) Jacobians."""
+    f = np.zeros(dm.nv)
+    rho, mu = dm.density, dm.viscosity
+    if rho <= 0 and mu <= 0:
+        return f
+    for b in range(1, dm.nbody):
+        mass, I = dm.body_mass[b], dm.body_inertia[3 * b:3 * b + 3]
+        if mass < MINVAL:
+            continue
+        ipos = dm.body_ipos[3 * b:3 * b + 3]
+        Ri = kin.R[b] @ quat2mat(dm.body_iquat[4 * b:4 * b + 4])
+        com = kin.P[b] + kin.R[b] @ ipos
+        v = Ri.T @ (kin.vP[b] + kin.vR[b] @ ipos - dm.wind)               # d/dt of the com, in the inertial frame
+        w = Ri.T @ kin.w[b]
+        box = np.sqrt(np.maximum(MINVAL, I.sum() - 2 * I) / mass * 6.0)  # I_y + I_z - I_x = m/6 * (2 a)^2 / ... -> full side length
+        frc, trq = np.zeros(3), np.zeros(3)
+        if mu > 0:
+            d = box.mean()
+            trq -= np.pi * d ** 3 * mu * w
+            frc -= 3 * np.pi * d * mu * v
+        if rho > 0:
+            area = np.array([box[1] * box[2], box[0] * box[2], box[0] * box[1]])
+            frc -= 0.5 * rho * area * np.abs(v) * v
+            quart = np.array([box[1] ** 4 + box[2] ** 4, box[0] ** 4 + box[2] ** 4, box[0] ** 4 + box[1] ** 4])
+            trq -= rho * box * quart * np.abs(w) * w / 64.0
+        f += kin.point_jac(b, com).T @ (Ri @ frc) + kin.JW[b].T @ (Ri @ trq)
+    return f
 
 
 def passive_force(dm, qpos, qvel):
@@ -1077,6 +1110,8 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     M, c = mass_matrix_and_bias(dm, kin)
     fa, frc, act_dot, dfdv = actuator_force(dm, qpos, qvel, np.asarray(ctrl, float), act)
     f = passive_force(dm, qpos, qvel) - c + fa
+    if not dm.dis("passive"):
+        f = f + fluid_force(dm, kin)
     if qfrc_applied is not None:
         f = f + qfrc_applied
     if xfrc_applied is not None:

@@ -505,5 +505,38 @@ ZOO_Q = """
 </mujoco>
 """
 
-ZOO = {"zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O, "zoo_p": ZOO_P, "zoo_q": ZOO_Q}
+# mj_passive fluid forces (inertia-box model): a three-link swimmer on planar root joints (dm_control swimmer's structure) in a
+# dense, viscous medium with wind, next to a tumbling free plate that falls to the floor and a resting pebble
+ZOO_R = """
+<mujoco model="zoo_r">
+  <compiler angle="radian"/>
+  <option timestep="0.003" tolerance="1e-13" density="900" viscosity="0.2" wind="0.3 -0.1 0.05"/>
+  <default><joint damping="0.02" armature="0.002"/></default>
+  <worldbody>
+    <geom name="floor" type="plane" size="3 3 0.1"/>
+    <body name="head" pos="0 0 0.6">
+      <joint name="rootx" type="slide" axis="1 0 0"/>
+      <joint name="rooty" type="slide" axis="0 1 0"/>
+      <joint name="rootz" type="hinge" axis="0 0 1"/>
+      <geom name="head" type="capsule" fromto="0 0 0 -0.2 0 0" size="0.03" density="1000"/>
+      <body name="seg1" pos="-0.2 0 0">
+        <joint name="j1" type="hinge" axis="0 0 1" range="-1.6 1.6" limited="true"/>
+        <geom name="seg1" type="box" pos="-0.1 0 0" size="0.1 0.015 0.04" density="1000"/>
+        <body name="seg2" pos="-0.2 0 0">
+          <joint name="j2" type="hinge" axis="0 0 1" range="-1.6 1.6" limited="true"/>
+          <geom name="seg2" type="capsule" fromto="0 0 0 -0.2 0 0" size="0.025" density="1000"/>
+          <site name="tail" pos="-0.2 0 0"/>
+        </body>
+      </body>
+    </body>
+    <body name="plate" pos="0.7 0.3 0.35" euler="0.4 0.2 0.1"><freejoint/><geom name="plate" type="box" size="0.15 0.1 0.01" density="1500"/></body>
+    <body name="float" pos="-0.5 -0.6 0.5"><freejoint/><geom name="float" type="sphere" size="0.06" density="300"/></body>
+    <body name="pebble" pos="0.8 -0.7 0.0495"><freejoint name="pebbleroot"/><geom name="pebble" type="sphere" size="0.05" density="9000"/></body>
+  </worldbody>
+  <actuator><motor joint="j1" gear="0.8"/><motor joint="j2" gear="0.8"/></actuator>
+  <sensor><framepos objtype="site" objname="tail"/><framelinvel objtype="body" objname="plate"/><gyro site="tail"/></sensor>
+</mujoco>
+"""
+
+ZOO = {"zoo_r": ZOO_R, "zoo_a": ZOO_A, "zoo_b": ZOO_B, "zoo_c": ZOO_C, "zoo_e": ZOO_E, "zoo_f": ZOO_F, "zoo_g": ZOO_G, "zoo_h": ZOO_H, "zoo_i": ZOO_I, "zoo_j": ZOO_J, "zoo_k": ZOO_K, "zoo_l": ZOO_L, "zoo_m": ZOO_M, "zoo_n": ZOO_N, "zoo_o": ZOO_O, "zoo_p": ZOO_P, "zoo_q": ZOO_Q}
 NOCONTACT = {"zoo_d": ZOO_D}

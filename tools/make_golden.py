@@ -35,7 +35,7 @@ MODELS = {  # name -> (xml, number of states, apply external forces)
     "zoo_j": (ZOO["zoo_j"], 64, True), "zoo_k": (ZOO["zoo_k"], 64, True), "zoo_l": (ZOO["zoo_l"], 64, True),
     "zoo_m": (ZOO["zoo_m"], 64, True), "zoo_n": (ZOO["zoo_n"], 64, True),
     "zoo_o": (ZOO["zoo_o"], 64, True), "zoo_p": (ZOO["zoo_p"], 64, True),
-    "zoo_q": (ZOO["zoo_q"], 64, True),
+    "zoo_q": (ZOO["zoo_q"], 64, True), "zoo_r": (ZOO["zoo_r"], 64, True),
 }
 OUT_KEYS = ("qpos", "qvel", "act", "qacc", "qfrc_bias", "qfrc_smooth", "qfrc_constraint", "actuator_force")
 
