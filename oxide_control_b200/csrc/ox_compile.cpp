@@ -97,6 +97,7 @@ struct Ctx {
   int inertiafromgeom = 2;  // 0 false, 1 true, 2 auto
   std::string eulerseq = "xyz";
   double boundmass = 0, boundinertia = 0;
+  double settotalmass = -1;   // > 0: rescale every body's mass and inertia so that the model weighs this much
   // defaults: class -> element tag -> attrs
   std::map<std::string, std::map<std::string, AttrMap>> defaults;
 };
@@ -643,7 +644,10 @@ ox_model* compile_mjcf(const std::string& xml) {
           if (std::string("xyzXYZ").find(cc) == std::string::npos) pfail(*ch, "eulerseq must use xyzXYZ");
         B.c.eulerseq = *s;
       }
-      if (ch->attr("settotalmass")) cfail("compiler settotalmass is outside the supported subset");
+      if (auto* s = ch->attr("settotalmass")) B.c.settotalmass = std::stod(*s);
+      if (auto* s = ch->attr("boundmass")) B.c.boundmass = std::stod(*s);
+      if (auto* s = ch->attr("boundinertia")) B.c.boundinertia = std::stod(*s);
+      if (B.c.boundmass < 0 || B.c.boundinertia < 0) cfail("compiler boundmass / boundinertia must be >= 0");
     }
   }
   for (auto& ch : root->children)
@@ -739,6 +743,17 @@ ox_model* compile_mjcf(const std::string& xml) {
     bool use_geoms = B.c.inertiafromgeom == 1 || (B.c.inertiafromgeom == 2 && !b.has_inertial);
     if (use_geoms) body_inertia_from_geoms(B, b);
     else if (!b.has_inertial) { b.mass = 0; }
+    b.mass = std::max(b.mass, B.c.boundmass);   // compiler boundmass / boundinertia: lower bounds for every body but the world
+    for (int k = 0; k < 3; k++) b.inertia[k] = std::max(b.inertia[k], B.c.boundinertia);
+  }
+  if (B.c.settotalmass > 0) {   // mjCModel::SetTotalMass: one scale for all masses and inertias (densities scale, shapes do not)
+    double total = 0;
+    for (int i = 1; i < nbody; i++) total += B.bodies[i].mass;
+    if (total > OX_MINVAL)
+      for (int i = 1; i < nbody; i++) {
+        B.bodies[i].mass *= B.c.settotalmass / total;
+        for (int k = 0; k < 3; k++) B.bodies[i].inertia[k] *= B.c.settotalmass / total;
+      }
   }
 
   // ---- sizes, joint/dof addressing ----

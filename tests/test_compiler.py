@@ -68,6 +68,23 @@ def test_inertial_element_overrides_geoms():
     assert m.body_mass[1] == 2 and np.allclose(m.body_inertia[3:6], [0.3, 0.2, 0.1]) and np.allclose(m.body_ipos[3:6], [0, 0, 0.1])
 
 
+def test_settotalmass_boundmass_boundinertia():
+    """<compiler settotalmass> rescales every mass and inertia by one factor (dm_control's cheetah.xml sets 14 kg this way);
+    boundmass / boundinertia are lower bounds applied to every body first."""
+    body = ('<worldbody><body><joint/><geom type="sphere" size="0.1" density="1000"/><body pos="0 0 0.3"><joint/>'
+            '<geom type="box" size="0.1 0.2 0.05" density="300"/></body></body></worldbody>')
+    m0 = ox.Model.from_xml_string(f"<mujoco>{body}</mujoco>")
+    m1 = ox.Model.from_xml_string(f'<mujoco><compiler settotalmass="14"/>{body}</mujoco>')
+    k = 14 / m0.body_mass.sum()
+    assert abs(m1.body_mass.sum() - 14) < 1e-12 and np.allclose(m1.body_mass, k * m0.body_mass, rtol=1e-13)
+    assert np.allclose(m1.body_inertia, k * m0.body_inertia, rtol=1e-13) and np.allclose(m1.body_subtreemass[1], 14)
+    assert np.allclose(m1.dof_invweight0, m0.dof_invweight0 / k, rtol=1e-12)             # everything downstream sees the new masses
+    m2 = ox.Model.from_xml_string(f'<mujoco><compiler boundmass="5" boundinertia="0.02"/>{body}</mujoco>')
+    assert np.allclose(m2.body_mass[1:], np.maximum(m0.body_mass[1:], 5)) and np.allclose(m2.body_inertia[3:], np.maximum(m0.body_inertia[3:], 0.02))
+    m3 = ox.Model.from_xml_string(f'<mujoco><compiler boundmass="5" settotalmass="1"/>{body}</mujoco>')   # bounds first, then the scale
+    assert np.allclose(m3.body_mass[1:], [0.5, 0.5])
+
+
 def test_topology_tables_of_the_benchmark_models():
     m = ox.Model.from_xml_string(ox.models.CHEETAH)
     assert (m.nq, m.nv, m.nu, m.nbody, m.ngeom, m.nM) == (9, 9, 6, 8, 9, 36)
