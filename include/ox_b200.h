@@ -83,7 +83,8 @@ enum { OX_DSBL_CONSTRAINT = 1 << 0, OX_DSBL_LIMIT = 1 << 3, OX_DSBL_CONTACT = 1 
 /* mjtSensor subset */
 enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX_SENS_GYRO = 3, OX_SENS_FORCE = 4, OX_SENS_TORQUE = 5,
        OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_TENDONPOS = 11, OX_SENS_TENDONVEL = 12, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
-       OX_SENS_ACTUATORFRC = 15, OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26,
+       OX_SENS_ACTUATORFRC = 15, OX_SENS_JOINTACTFRC = 16, OX_SENS_BALLQUAT = 17, OX_SENS_BALLANGVEL = 18,
+       OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26, OX_SENS_FRAMEXAXIS = 27, OX_SENS_FRAMEYAXIS = 28, OX_SENS_FRAMEZAXIS = 29,
        OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_SUBTREECOM = 34,
        OX_SENS_SUBTREELINVEL = 35, OX_SENS_CLOCK = 45 };
 

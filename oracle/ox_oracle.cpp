@@ -1901,6 +1901,15 @@ void sensors(const Model* m, Data* d) {
         out[0] = m->actuator_gear[id] * (m->actuator_trntype[id] == OX_TRN_TENDON ? tendonVelocity(m, d, m->actuator_trnid[id]) : d->qvel[m->jnt_dofadr[m->actuator_trnid[id]]]);
         break;
       case OX_SENS_ACTUATORFRC: out[0] = d->actuator_force[id]; break;
+      case OX_SENS_JOINTACTFRC: out[0] = d->qfrc_actuator[m->jnt_dofadr[id]]; break;   // mjSENS_JOINTACTFRC: net actuator force on the joint
+      case OX_SENS_BALLQUAT: {                                                          // mjSENS_BALLQUAT: copy, then mju_normalize4
+        const double* q = &d->qpos[m->jnt_qposadr[id]];
+        const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        if (n < OX_MINVAL) { out[0] = 1; out[1] = out[2] = out[3] = 0; }
+        else for (int k = 0; k < 4; k++) out[k] = q[k] / n;
+        break;
+      }
+      case OX_SENS_BALLANGVEL: std::memcpy(out, &d->qvel[m->jnt_dofadr[id]], 3 * sizeof(double)); break;
       case OX_SENS_TENDONPOS: out[0] = d->ten_length[id]; break;
       case OX_SENS_TENDONVEL: out[0] = tendonVelocity(m, d, id); break;
       case OX_SENS_TOUCH: {
@@ -1930,6 +1939,12 @@ void sensors(const Model* m, Data* d) {
         break;
       case OX_SENS_FRAMEPOS: objFrame(m, d, ot, id, &pos, &mat, &body); std::memcpy(out, pos, 3 * sizeof(double)); break;
       case OX_SENS_FRAMEQUAT: objFrame(m, d, ot, id, &pos, &mat, &body); mat2Quat(out, mat); break;
+      case OX_SENS_FRAMEXAXIS: case OX_SENS_FRAMEYAXIS: case OX_SENS_FRAMEZAXIS: {     // column of xmat (mjSENS_FRAME[XYZ]AXIS)
+        objFrame(m, d, ot, id, &pos, &mat, &body);
+        const int c = m->sensor_type[s] - OX_SENS_FRAMEXAXIS;
+        for (int k = 0; k < 3; k++) out[k] = mat[3 * k + c];
+        break;
+      }
       case OX_SENS_FRAMELINVEL: case OX_SENS_FRAMEANGVEL: case OX_SENS_VELOCIMETER: case OX_SENS_GYRO: {
         // object velocity (mj_objectVelocity): cvel transported from the com frame origin to the object position
         objFrame(m, d, ot, id, &pos, &mat, &body);

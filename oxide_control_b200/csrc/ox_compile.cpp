@@ -1267,6 +1267,10 @@ ox_model* compile_mjcf(const std::string& xml) {
               {"framepos", OX_SENS_FRAMEPOS, -1, "objname", 3}, {"framequat", OX_SENS_FRAMEQUAT, -1, "objname", 4},
               {"framelinvel", OX_SENS_FRAMELINVEL, -1, "objname", 3}, {"frameangvel", OX_SENS_FRAMEANGVEL, -1, "objname", 3},
               {"tendonpos", OX_SENS_TENDONPOS, OX_OBJ_TENDON, "tendon", 1}, {"tendonvel", OX_SENS_TENDONVEL, OX_OBJ_TENDON, "tendon", 1},
+              {"framexaxis", OX_SENS_FRAMEXAXIS, -1, "objname", 3}, {"frameyaxis", OX_SENS_FRAMEYAXIS, -1, "objname", 3},
+              {"framezaxis", OX_SENS_FRAMEZAXIS, -1, "objname", 3},
+              {"ballquat", OX_SENS_BALLQUAT, OX_OBJ_JOINT, "joint", 4}, {"ballangvel", OX_SENS_BALLANGVEL, OX_OBJ_JOINT, "joint", 3},
+              {"jointactuatorfrc", OX_SENS_JOINTACTFRC, OX_OBJ_JOINT, "joint", 1},
               {"clock", OX_SENS_CLOCK, OX_OBJ_UNKNOWN, nullptr, 1},
           };
           const Spec* sp = nullptr;
@@ -1293,6 +1297,10 @@ ox_model* compile_mjcf(const std::string& xml) {
             if ((sp->type == OX_SENS_JOINTPOS || sp->type == OX_SENS_JOINTVEL) &&
                 B.joints[objid].type != OX_JNT_HINGE && B.joints[objid].type != OX_JNT_SLIDE)
               cfail("jointpos/jointvel sensors require a hinge or slide joint");
+            if (sp->type == OX_SENS_JOINTACTFRC && B.joints[objid].type != OX_JNT_HINGE && B.joints[objid].type != OX_JNT_SLIDE)
+              cfail("jointactuatorfrc sensors require a hinge or slide joint");
+            if ((sp->type == OX_SENS_BALLQUAT || sp->type == OX_SENS_BALLANGVEL) && B.joints[objid].type != OX_JNT_BALL)
+              cfail("ballquat/ballangvel sensors require a ball joint");
             if (sp->type == OX_SENS_TOUCH) {
               const int st = M->v_site_type[objid];
               if (st != OX_GEOM_SPHERE && st != OX_GEOM_CAPSULE && st != OX_GEOM_BOX)

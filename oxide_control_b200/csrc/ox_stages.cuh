@@ -2724,6 +2724,15 @@ struct Env {
         case OX_SENS_ACTUATORPOS: at(b.sensordata, adr) = m.actuator_gear(id) * act_length(id); break;
         case OX_SENS_ACTUATORVEL: at(b.sensordata, adr) = m.actuator_gear(id) * act_velocity(id); break;
         case OX_SENS_ACTUATORFRC: at(b.sensordata, adr) = at(b.actuator_force, id); break;
+        case OX_SENS_JOINTACTFRC: at(b.sensordata, adr) = at(b.qfrc_actuator, m.jnt_dofadr(id)); break;
+        case OX_SENS_BALLQUAT: {   // a normalised copy of the joint's quaternion
+          T q[4];
+          ld<4>(q, b.qpos, m.jnt_qposadr(id));
+          normalize4(q);
+          st<4>(b.sensordata, adr, q);
+          break;
+        }
+        case OX_SENS_BALLANGVEL: for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.qvel, m.jnt_dofadr(id) + k); break;
         case OX_SENS_TENDONPOS: at(b.sensordata, adr) = at(b.ten_length, id); break;
         case OX_SENS_TENDONVEL: at(b.sensordata, adr) = tendon_velocity(id); break;
         case OX_SENS_SUBTREECOM: for (int k = 0; k < 3; k++) at(b.sensordata, adr + k) = at(b.subtree_com, 3 * id + k); break;
@@ -2763,12 +2772,19 @@ struct Env {
           break;
         }
         case OX_SENS_FRAMEPOS: case OX_SENS_FRAMEQUAT: case OX_SENS_FRAMELINVEL: case OX_SENS_FRAMEANGVEL:
+        case OX_SENS_FRAMEXAXIS: case OX_SENS_FRAMEYAXIS: case OX_SENS_FRAMEZAXIS:
         case OX_SENS_VELOCIMETER: case OX_SENS_GYRO: {
           T pos[3], mat[9];
           int body;
           obj_frame(ot, id, pos, mat, &body);
           if (ty == OX_SENS_FRAMEPOS) { st<3>(b.sensordata, adr, pos); break; }
           if (ty == OX_SENS_FRAMEQUAT) { T q[4]; mat2quat(q, mat); st<4>(b.sensordata, adr, q); break; }
+          if (ty >= OX_SENS_FRAMEXAXIS && ty <= OX_SENS_FRAMEZAXIS) {   // a column of the frame's rotation matrix
+            const int c = ty - OX_SENS_FRAMEXAXIS;
+            T ax[3] = {mat[c], mat[3 + c], mat[6 + c]};
+            st<3>(b.sensordata, adr, ax);
+            break;
+          }
           T cv[6], sc[3], dif[3], tmp[3], lin[3], out[3];
           ld<6>(cv, b.cvel, 6 * body);
           ld<3>(sc, b.subtree_com, 3 * m.body_rootid(body));

@@ -55,6 +55,8 @@ ZOO_A = """
     <subtreecom body="boxy"/> <subtreelinvel body="boxy"/> <subtreelinvel body="arm"/> <clock/>
     <touch site="ball_skin"/> <touch site="rod_skin"/> <touch site="rod_tip"/> <touch site="box_sole"/> <touch site="tip"/>
     <force site="tip"/> <torque site="tip"/> <force site="top"/> <torque site="top"/> <force site="ball_skin"/> <torque site="rod_tip"/>
+    <framexaxis objtype="site" objname="tip"/> <frameyaxis objtype="body" objname="hand"/> <framezaxis objtype="geom" objname="arm"/>
+    <ballquat joint="shoulder"/> <ballangvel joint="shoulder"/> <jointactuatorfrc joint="wrist"/> <jointactuatorfrc joint="extend"/>
   </sensor>
 </mujoco>
 """
