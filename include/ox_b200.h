@@ -85,7 +85,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
        OX_SENS_JOINTPOS = 8, OX_SENS_JOINTVEL = 9, OX_SENS_TENDONPOS = 11, OX_SENS_TENDONVEL = 12, OX_SENS_ACTUATORPOS = 13, OX_SENS_ACTUATORVEL = 14,
        OX_SENS_ACTUATORFRC = 15, OX_SENS_JOINTACTFRC = 16, OX_SENS_BALLQUAT = 17, OX_SENS_BALLANGVEL = 18,
        OX_SENS_FRAMEPOS = 25, OX_SENS_FRAMEQUAT = 26, OX_SENS_FRAMEXAXIS = 27, OX_SENS_FRAMEYAXIS = 28, OX_SENS_FRAMEZAXIS = 29,
-       OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_SUBTREECOM = 34,
+       OX_SENS_FRAMELINVEL = 30, OX_SENS_FRAMEANGVEL = 31, OX_SENS_FRAMELINACC = 32, OX_SENS_FRAMEANGACC = 33, OX_SENS_SUBTREECOM = 34,
        OX_SENS_SUBTREELINVEL = 35, OX_SENS_CLOCK = 45 };
 
 #define OX_MAXVAL 1e10  /* mjMAXVAL re-exported at src/physics.rs:2 */

@@ -1960,11 +1960,12 @@ void sensors(const Model* m, Data* d) {
         } else std::memcpy(out, src, 3 * sizeof(double));
         break;
       }
-      case OX_SENS_ACCELEROMETER: {
+      case OX_SENS_FRAMELINACC: case OX_SENS_FRAMEANGACC: case OX_SENS_ACCELEROMETER: {
         // mj_objectAcceleration(local): cacc and cvel transported to the site, plus omega x v, in the site frame.
         // At rest this reads -gravity (an accelerometer measures proper acceleration).
+        // mjSENS_FRAMELINACC / FRAMEANGACC: mj_objectAcceleration(flg_local = 0) of any frame object - world axes.
         if (cacc.empty()) bodyAcc(m, d, cacc);
-        objFrame(m, d, OX_OBJ_SITE, id, &pos, &mat, &body);
+        objFrame(m, d, m->sensor_type[s] == OX_SENS_ACCELEROMETER ? (int)OX_OBJ_SITE : ot, id, &pos, &mat, &body);
         const double *cv = &d->cvel[6 * body], *ca = &cacc[6 * body];
         double dif[3], lv[3], la[3], t1[3], t2[3], t3[3];
         for (int k = 0; k < 3; k++) dif[k] = pos[k] - d->subtree_com[3 * m->body_rootid[body] + k];
@@ -1973,6 +1974,8 @@ void sensors(const Model* m, Data* d) {
         for (int k = 0; k < 3; k++) { lv[k] = cv[3 + k] + t1[k]; la[k] = ca[3 + k] + t2[k]; }
         cross3(t3, cv, lv);
         for (int k = 0; k < 3; k++) la[k] += t3[k];
+        if (m->sensor_type[s] == OX_SENS_FRAMELINACC) { std::memcpy(out, la, sizeof la); break; }
+        if (m->sensor_type[s] == OX_SENS_FRAMEANGACC) { std::memcpy(out, ca, 3 * sizeof(double)); break; }
         for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
         break;
       }

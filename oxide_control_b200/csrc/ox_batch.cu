@@ -523,7 +523,7 @@ ox_status ox_batch_create(const ox_model* m, const ox_batch_config* cfg, ox_batc
     b->spec_rt.ls_iterations = cfg->ls_iterations > 0 ? cfg->ls_iterations : t.ls_iterations;
     b->spec_rt.tolerance = b->f64 ? effective_tolerance<double>(t, cfg->tolerance) : effective_tolerance<float>(t, cfg->tolerance);
     bool acc_sensor = false;  // acceleration-stage sensors read the solved qacc: the PRE phase of the split pipeline runs too early for them
-    for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER || t.sensor_type[i] == OX_SENS_TOUCH || t.sensor_type[i] == OX_SENS_FORCE || t.sensor_type[i] == OX_SENS_TORQUE;
+    for (int i = 0; i < t.nsensor; i++) acc_sensor |= t.sensor_type[i] == OX_SENS_ACCELEROMETER || t.sensor_type[i] == OX_SENS_TOUCH || t.sensor_type[i] == OX_SENS_FORCE || t.sensor_type[i] == OX_SENS_TORQUE || t.sensor_type[i] == OX_SENS_FRAMELINACC || t.sensor_type[i] == OX_SENS_FRAMEANGACC;
     b->split = b->spec && b->spec->has_phase(b->f64, 1) && b->spec->has_phase(b->f64, 2) && cfg->coop_solver != 0 && coop_ok && t.integrator == OX_INT_EULER && !acc_sensor;
   }
   if (b->coop || b->split) {

@@ -1269,6 +1269,7 @@ ox_model* compile_mjcf(const std::string& xml) {
               {"tendonpos", OX_SENS_TENDONPOS, OX_OBJ_TENDON, "tendon", 1}, {"tendonvel", OX_SENS_TENDONVEL, OX_OBJ_TENDON, "tendon", 1},
               {"framexaxis", OX_SENS_FRAMEXAXIS, -1, "objname", 3}, {"frameyaxis", OX_SENS_FRAMEYAXIS, -1, "objname", 3},
               {"framezaxis", OX_SENS_FRAMEZAXIS, -1, "objname", 3},
+              {"framelinacc", OX_SENS_FRAMELINACC, -1, "objname", 3}, {"frameangacc", OX_SENS_FRAMEANGACC, -1, "objname", 3},
               {"ballquat", OX_SENS_BALLQUAT, OX_OBJ_JOINT, "joint", 4}, {"ballangvel", OX_SENS_BALLANGVEL, OX_OBJ_JOINT, "joint", 3},
               {"jointactuatorfrc", OX_SENS_JOINTACTFRC, OX_OBJ_JOINT, "joint", 1},
               {"clock", OX_SENS_CLOCK, OX_OBJ_UNKNOWN, nullptr, 1},

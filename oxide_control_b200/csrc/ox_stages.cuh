@@ -2799,13 +2799,14 @@ struct Env {
           st<3>(b.sensordata, adr, out);
           break;
         }
-        case OX_SENS_ACCELEROMETER: {
+        case OX_SENS_FRAMELINACC: case OX_SENS_FRAMEANGACC: case OX_SENS_ACCELEROMETER: {
+          // framelinacc / frameangacc: the same object acceleration, of any frame object, left in world axes
           // mj_objectAcceleration(local) on top of mj_rnePostConstraint's forward pass: cacc[0] = (0, -gravity),
           // cacc[b] = cacc[parent] + sum over the body's dofs of cdof_dot*qvel + cdof*qacc (b.cacc is free after rne())
           if (!have_cacc) { body_acc(); have_cacc = true; }
           T pos[3], mat[9];
           int body;
-          obj_frame(OX_OBJ_SITE, id, pos, mat, &body);
+          obj_frame(ty == OX_SENS_ACCELEROMETER ? (int)OX_OBJ_SITE : ot, id, pos, mat, &body);
           T cv[6], ca[6], sc[3], dif[3], lv[3], la[3], t1[3], t2[3], t3[3];
           ld<6>(cv, b.cvel, 6 * body);
           ld<6>(ca, b.cacc, 6 * body);
@@ -2819,6 +2820,8 @@ struct Env {
           T out[3];
           OX_MLOOP
           for (int k = 0; k < 3; k++) la[k] += t3[k];
+          if (ty == OX_SENS_FRAMELINACC) { st<3>(b.sensordata, adr, la); break; }
+          if (ty == OX_SENS_FRAMEANGACC) { st<3>(b.sensordata, adr, ca); break; }
           OX_MLOOP
           for (int k = 0; k < 3; k++) out[k] = mat[k] * la[0] + mat[3 + k] * la[1] + mat[6 + k] * la[2];
           st<3>(b.sensordata, adr, out);

@@ -57,6 +57,7 @@ ZOO_A = """
     <force site="tip"/> <torque site="tip"/> <force site="top"/> <torque site="top"/> <force site="ball_skin"/> <torque site="rod_tip"/>
     <framexaxis objtype="site" objname="tip"/> <frameyaxis objtype="body" objname="hand"/> <framezaxis objtype="geom" objname="arm"/>
     <ballquat joint="shoulder"/> <ballangvel joint="shoulder"/> <jointactuatorfrc joint="wrist"/> <jointactuatorfrc joint="extend"/>
+    <framelinacc objtype="site" objname="tip"/> <frameangacc objtype="body" objname="hand"/> <framelinacc objtype="geom" objname="ball"/>
   </sensor>
 </mujoco>
 """
