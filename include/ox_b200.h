@@ -118,7 +118,7 @@ enum { OX_SENS_TOUCH = 0, OX_SENS_ACCELEROMETER = 1, OX_SENS_VELOCIMETER = 2, OX
   X(qpos0, nq, 1) X(qpos_spring, nq, 1)                                                             \
   X(body_pos, nbody, 3) X(body_quat, nbody, 4) X(body_ipos, nbody, 3) X(body_iquat, nbody, 4)      \
   X(body_mass, nbody, 1) X(body_inertia, nbody, 3) X(body_subtreemass, nbody, 1)                   \
-  X(body_invweight0, nbody, 2) X(body_fluid, nfluid, 11)                                            \
+  X(body_invweight0, nbody, 2) X(body_fluid, nfluid, 11) X(body_gravcomp, ngravcomp, 1)                                          \
   X(jnt_pos, njnt, 3) X(jnt_axis, njnt, 3) X(jnt_stiffness, njnt, 1) X(jnt_range, njnt, 2)         \
   X(jnt_margin, njnt, 1) X(jnt_solref, njnt, 2) X(jnt_solimp, njnt, 5)                             \
   X(dof_armature, nv, 1) X(dof_damping, nv, 1) X(dof_invweight0, nv, 1)                            \
@@ -156,6 +156,7 @@ typedef struct ox_model_tables {
    * viscosity is positive, else 0; body_fluid[11] per body = viscous torque and force coefficients (pi d^3 mu, 3 pi d mu),
    * quadratic drag coefficients of the three box faces (force, then torque), and the wind velocity */
   int32_t nfluid;
+  int32_t ngravcomp;           /* nbody when any body has gravcomp != 0 (mj_passive adds -gravity * mass * gravcomp at its com), else 0 */
   double density, viscosity, wind[3];
   /* mjStatistic subset */
   double meaninertia;

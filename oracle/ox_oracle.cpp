@@ -1083,6 +1083,24 @@ void passive(const Model* m, Data* d) {
     if (f != 0)
       for (int k = 0; k < m->nv; k++) d->qfrc_passive[k] += d->ten_J[(size_t)i * m->nv + k] * f;
   }
+  // body gravcomp (mj_passive, qfrc_gravcomp): -gravity * mass * gravcomp applied at xipos
+  if (m->ngravcomp && !disabled(m, OX_DSBL_GRAVITY))
+    for (int b = 1; b < m->nbody; b++) {
+      if (m->body_gravcomp[b] == 0) continue;
+      double offset[3], frc[3];
+      for (int k = 0; k < 3; k++) offset[k] = d->xipos[3 * b + k] - d->subtree_com[3 * m->body_rootid[b] + k];
+      for (int k = 0; k < 3; k++) frc[k] = -m->gravity[k] * m->body_mass[b] * m->body_gravcomp[b];
+      int body = b;
+      while (body && m->body_dofnum[body] == 0) body = m->body_parentid[body];
+      if (!body) continue;
+      for (int i = m->body_dofadr[body] + m->body_dofnum[body] - 1; i >= 0; i = m->dof_parentid[i]) {
+        const double* cd = &d->cdof[6 * i];
+        double jp[3];
+        cross3(jp, cd, offset);
+        for (int k = 0; k < 3; k++) jp[k] += cd[3 + k];
+        d->qfrc_passive[i] += dot3(jp, frc);
+      }
+    }
   // mj_inertiaBoxFluidModel (engine_passive.c): viscous and quadratic drag on the equivalent inertia box of every body. Done from
   // mjOption density / viscosity / wind and body_inertia as MuJoCo does at run time (the product uses a table compiled from them).
   if (m->viscosity > 0 || m->density > 0)

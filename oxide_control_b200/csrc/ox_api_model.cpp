@@ -240,7 +240,7 @@ int32_t ox_model_size(const ox_model* m, const char* name) {
   const ox_model_tables& t = m->t;
 #define S(f) if (!std::strcmp(name, #f)) return t.f;
   S(nq) S(nv) S(nu) S(na) S(nbody) S(njnt) S(ngeom) S(nsite) S(nM) S(npair) S(nsensor) S(nsensordata) S(nconmax) S(nefcmax) S(nvv) S(nmocap) S(neq) S(ntendon) S(nwrap)
-  S(integrator) S(solver) S(cone) S(iterations) S(ls_iterations) S(disableflags) S(noslip_iterations) S(nfloss) S(nfluid)
+  S(integrator) S(solver) S(cone) S(iterations) S(ls_iterations) S(disableflags) S(noslip_iterations) S(nfloss) S(nfluid) S(ngravcomp)
 #undef S
   return -1;
 }

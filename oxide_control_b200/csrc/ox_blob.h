@@ -24,7 +24,7 @@
 namespace ox {
 
 struct BlobHeader {
-  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata, nconmax, nefcmax, nvv, nmocap, neq, noslip_iterations, ntendon, nwrap, nfloss, nfluid, padn_[2];
+  int32_t nq, nv, nu, na, nbody, njnt, ngeom, nsite, nM, npair, nsensor, nsensordata, nconmax, nefcmax, nvv, nmocap, neq, noslip_iterations, ntendon, nwrap, nfloss, nfluid, ngravcomp, padn_[1];
   int32_t integrator, solver, cone, iterations, ls_iterations, disableflags;
   int32_t total_bytes, any_damping;
   double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia, noslip_tolerance;
@@ -66,7 +66,7 @@ inline std::vector<unsigned char> build_blob(const ox_model_tables& t, int itera
   BlobHeader h;
   std::memset(&h, 0, sizeof h);
   h.nq = t.nq; h.nv = t.nv; h.nu = t.nu; h.na = t.na; h.nbody = t.nbody; h.njnt = t.njnt; h.ngeom = t.ngeom; h.nsite = t.nsite;
-  h.nM = t.nM; h.npair = t.npair; h.nsensor = t.nsensor; h.nsensordata = t.nsensordata; h.nconmax = t.nconmax; h.nefcmax = t.nefcmax; h.nvv = t.nvv; h.nmocap = t.nmocap; h.neq = t.neq; h.ntendon = t.ntendon; h.nwrap = t.nwrap; h.nfloss = t.nfloss; h.nfluid = t.nfluid; h.noslip_iterations = t.noslip_iterations; h.noslip_tolerance = t.noslip_tolerance;
+  h.nM = t.nM; h.npair = t.npair; h.nsensor = t.nsensor; h.nsensordata = t.nsensordata; h.nconmax = t.nconmax; h.nefcmax = t.nefcmax; h.nvv = t.nvv; h.nmocap = t.nmocap; h.neq = t.neq; h.ntendon = t.ntendon; h.nwrap = t.nwrap; h.nfloss = t.nfloss; h.nfluid = t.nfluid; h.ngravcomp = t.ngravcomp; h.noslip_iterations = t.noslip_iterations; h.noslip_tolerance = t.noslip_tolerance;
   h.integrator = t.integrator; h.solver = t.solver; h.cone = t.cone;
   h.iterations = iterations > 0 ? iterations : t.iterations;
   h.ls_iterations = ls_iterations > 0 ? ls_iterations : t.ls_iterations;

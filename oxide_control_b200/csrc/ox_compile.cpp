@@ -259,6 +259,7 @@ struct BodyDef {
   double pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0};
   bool has_inertial = false, mocap = false;
   double ipos[3] = {0, 0, 0}, iquat[4] = {1, 0, 0, 0}, mass = 0, inertia[3] = {0, 0, 0};
+  double gravcomp = 0;   // fraction of the body's weight cancelled by a passive force at its com
   std::vector<int> joints, geoms;
 };
 
@@ -315,6 +316,7 @@ void parse_geom(Builder& B, const XmlElem& e, int body, const std::string& child
   }
   g.density = a.num("density", g.density);
   g.mass = a.num("mass", -1);
+  if (a.has("shellinertia") && a.str("shellinertia") == "true") cfail("geom '" + g.name + "': shellinertia is outside the supported subset");
   if (a.has("fluidshape") && a.str("fluidshape") != "none")
     cfail("geom '" + g.name + "': fluidshape='" + a.str("fluidshape") + "' (ellipsoid fluid model) is outside the supported subset (inertia-box model)");
   a.vec("friction", g.friction, 3, true);
@@ -414,6 +416,13 @@ void parse_joint(Builder& B, const XmlElem& e, int body, const std::string& chil
     a.vec("solimpfriction", j.solimp_fri, 5, true);
     clamp_solimp(j.solimp_fri);
     if (a.has("actuatorfrcrange")) cfail("joint '" + j.name + "': actuatorfrcrange is outside the supported subset");
+    if (a.has("actuatorfrclimited") && a.str("actuatorfrclimited") == "true") cfail("joint '" + j.name + "': actuatorfrclimited is outside the supported subset");
+    if (a.has("actuatorgravcomp") && a.str("actuatorgravcomp") == "true") cfail("joint '" + j.name + "': actuatorgravcomp is outside the supported subset");
+    if (a.has("springdamper")) {
+      double sd[2] = {0, 0};
+      a.vec("springdamper", sd, 2);
+      if (sd[0] != 0 || sd[1] != 0) cfail("joint '" + j.name + "': springdamper is outside the supported subset (give stiffness and damping)");
+    }
     if (j.type == OX_JNT_FREE || j.type == OX_JNT_BALL) { j.axis[0] = j.axis[1] = 0; j.axis[2] = 1; }
     else if (hm::normalize3(j.axis) < 1e-15) cfail("joint '" + j.name + "': zero axis");
   }
@@ -433,6 +442,7 @@ void parse_body(Builder& B, const XmlElem& e, int parent, std::string childclass
     b.name = a.str_or("name", "");
     a.vec("pos", b.pos, 3);
     orientation(B.c, a, b.quat);
+    b.gravcomp = a.num("gravcomp", 0);
     if (a.has("mocap") && a.str("mocap") == "true") {
       if (parent != 0) cfail("body '" + b.name + "': a mocap body must be a child of the world");
       b.mocap = true;
@@ -645,6 +655,8 @@ ox_model* compile_mjcf(const std::string& xml) {
         B.c.eulerseq = *s;
       }
       if (auto* s = ch->attr("settotalmass")) B.c.settotalmass = std::stod(*s);
+      if (ch->attr("inertiagrouprange")) cfail("compiler inertiagrouprange is outside the supported subset");
+      if (auto* s = ch->attr("balanceinertia")) if (*s == "true") cfail("compiler balanceinertia is outside the supported subset");
       if (auto* s = ch->attr("boundmass")) B.c.boundmass = std::stod(*s);
       if (auto* s = ch->attr("boundinertia")) B.c.boundinertia = std::stod(*s);
       if (B.c.boundmass < 0 || B.c.boundinertia < 0) cfail("compiler boundmass / boundinertia must be >= 0");
@@ -674,6 +686,8 @@ ox_model* compile_mjcf(const std::string& xml) {
       t.viscosity = a.num("viscosity", t.viscosity);
       a.vec("wind", t.wind, 3);
       if (t.density < 0 || t.viscosity < 0) cfail("option density / viscosity must be >= 0");
+      if (a.has("actuatorgroupdisable") && a.str("actuatorgroupdisable").find_first_not_of(" \t\n") != std::string::npos)
+        cfail("option actuatorgroupdisable is outside the supported subset");
       if (a.has("integrator")) {
         const std::string& s = a.str("integrator");
         if (s == "Euler") t.integrator = OX_INT_EULER;
@@ -713,7 +727,10 @@ ox_model* compile_mjcf(const std::string& xml) {
         dis("passive", OX_DSBL_PASSIVE); dis("gravity", OX_DSBL_GRAVITY); dis("clampctrl", OX_DSBL_CLAMPCTRL);
         dis("warmstart", OX_DSBL_WARMSTART); dis("filterparent", OX_DSBL_FILTERPARENT); dis("equality", OX_DSBL_EQUALITY); dis("frictionloss", OX_DSBL_FRICTIONLOSS);
         dis("actuation", OX_DSBL_ACTUATION); dis("refsafe", OX_DSBL_REFSAFE); dis("eulerdamp", OX_DSBL_EULERDAMP);
-        for (const char* k : {"energy", "fwdinv", "island", "multiccd", "override"})
+        for (const char* k : {"sensor", "autoreset", "spring", "damper"})   // disable flags the step does not implement: refuse, do not ignore
+          if (auto* s = f->attr(k))
+            if (*s == "disable") cfail(std::string("flag ") + k + "=disable is outside the supported subset");
+        for (const char* k : {"energy", "fwdinv", "island", "multiccd", "override", "invdiscrete"})
           if (auto* s = f->attr(k))
             if (*s == "enable") cfail(std::string("flag ") + k + "=enable is outside the supported subset");
       }
@@ -722,6 +739,7 @@ ox_model* compile_mjcf(const std::string& xml) {
     } else if (n == "compiler" || n == "default" || n == "size" || n == "visual" || n == "statistic" || n == "custom" ||
                n == "keyframe" || n == "actuator" || n == "sensor" || n == "contact") {
       // handled elsewhere / no effect on the step
+      if (n == "statistic" && ch->attr("meaninertia")) cfail("statistic meaninertia (an override of the solver's scale) is outside the supported subset");
     } else if (n == "asset") {
       for (auto& as : ch->children)
         if (as->name == "mesh" || as->name == "hfield") cfail("asset <" + as->name + "> is outside the supported subset");
@@ -843,6 +861,10 @@ ox_model* compile_mjcf(const std::string& xml) {
     }
     for (int k = 0; k < 3; k++) f[8 + k] = t.wind[k];
   }
+  t.ngravcomp = 0;
+  for (int i = 1; i < nbody; i++) if (B.bodies[i].gravcomp != 0) t.ngravcomp = nbody;
+  M->v_body_gravcomp.assign(t.ngravcomp, 0);
+  for (int i = 1; i < t.ngravcomp; i++) M->v_body_gravcomp[i] = B.bodies[i].gravcomp;
   nm[OX_OBJ_BODY][0] = "world";
   for (int i = nbody - 1; i >= 0; i--) {
     M->v_body_subtreemass[i] += M->v_body_mass[i];
@@ -1176,6 +1198,7 @@ ox_model* compile_mjcf(const std::string& xml) {
           else if (s == "filterexact") ad.dyntype = OX_DYN_FILTEREXACT;
           else cfail("actuator '" + ad.name + "': dyntype '" + s + "' is outside the supported subset (none, integrator, filter, filterexact)");
         }
+        if (a.has("inheritrange") && a.num("inheritrange", 0) != 0) cfail("actuator '" + ad.name + "': inheritrange is outside the supported subset (give ctrlrange)");
         if (a.has("actdim") || a.has("actearly")) cfail("actuator '" + ad.name + "': actdim / actearly are outside the supported subset");
         a.vec("dynprm", ad.dynprm, 3, true);
         {
@@ -1279,6 +1302,7 @@ ox_model* compile_mjcf(const std::string& xml) {
             if (e->name == s.tag) sp = &s;
           if (!sp) cfail("sensor <" + e->name + "> is outside the supported subset");
           if (e->attr("reftype") || e->attr("refname")) cfail("sensor reference frames (reftype/refname) are outside the supported subset");
+          if (auto* c = e->attr("cutoff")) if (std::stod(*c) > 0) cfail("sensor cutoff is outside the supported subset");
           int objtype = sp->objtype, objid = -1;
           if (sp->attr) {
             const std::string* on = e->attr(sp->attr);

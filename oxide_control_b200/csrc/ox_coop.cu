@@ -264,6 +264,10 @@ struct Coop {
         gsync();
         if (gl == 0) for (int bd = 1; bd < h.nfluid; bd++) env.passive_fluid(bd);
       }
+      if (h.ngravcomp > 0 && !env.dis(OX_DSBL_GRAVITY)) {
+        gsync();
+        if (gl == 0) for (int bd = 1; bd < h.ngravcomp; bd++) env.passive_gravcomp(bd);
+      }
     }
     down(1, [&](int i) { env.rne_fwd_body(i); });
     gather_up<6>(b.cfrc, 1);

@@ -45,7 +45,7 @@ inline uint64_t model_hash(const ox_model_tables& t) {
     const unsigned char* c = static_cast<const unsigned char*>(p);
     for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
   };
-  const int32_t sizes[] = {t.nfluid, t.nfloss, t.ntendon, t.nwrap, t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
+  const int32_t sizes[] = {t.ngravcomp, t.nfluid, t.nfloss, t.ntendon, t.nwrap, t.nmocap, t.neq, t.nq, t.nv, t.nu, t.na, t.nbody, t.njnt, t.ngeom, t.nsite, t.nM, t.npair, t.nsensor, t.nsensordata,
                            t.nconmax, t.nefcmax, t.integrator, t.solver, t.cone, t.disableflags, t.noslip_iterations};
   mix(sizes, sizeof sizes);
   const double opts[] = {t.timestep, t.gravity[0], t.gravity[1], t.gravity[2], t.ls_tolerance, t.impratio, t.meaninertia, t.noslip_tolerance};

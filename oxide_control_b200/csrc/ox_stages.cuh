@@ -716,6 +716,30 @@ struct Env {
     for (int i = 0; i < h.ntendon; i++) passive_tendon(i);
     OX_MLOOP
     for (int bd = 1; bd < h.nfluid; bd++) passive_fluid(bd);
+    if (!dis(OX_DSBL_GRAVITY)) {
+      OX_MLOOP
+      for (int bd = 1; bd < h.ngravcomp; bd++) passive_gravcomp(bd);
+    }
+  }
+  // body gravcomp: the force -gravity * mass * gravcomp at the body's com, mapped to the joints (mj_passive, qfrc_gravcomp)
+  OX_HD void passive_gravcomp(int bd) const {
+    const T gc = m.body_gravcomp(bd) * m.body_mass(bd);
+    const int body = m.body_weldid(bd);
+    if (gc == 0 || !body) return;
+    const auto& h = m.h();
+    T xi[3], sc[3], offset[3], f[3] = {-(T)h.grav(0) * gc, -(T)h.grav(1) * gc, -(T)h.grav(2) * gc};
+    ld<3>(xi, b.xipos, 3 * bd);
+    ld<3>(sc, b.subtree_com, 3 * m.body_rootid(bd));
+    offset[0] = xi[0] - sc[0]; offset[1] = xi[1] - sc[1]; offset[2] = xi[2] - sc[2];
+    const int last_ = m.body_dofadr(body) + m.body_dofnum(body) - 1;
+    OX_MLOOP
+    for (int d_ = 0, i = last_; d_ < m.dof_depth(last_); d_++, i = m.dof_parentid(i)) {
+      T cd[6], jp[3];
+      ld<6>(cd, b.cdof, 6 * i);
+      cross3(jp, cd, offset);
+      jp[0] += cd[3]; jp[1] += cd[4]; jp[2] += cd[5];
+      at(b.qfrc_passive, i) += dot3(jp, f);
+    }
   }
   // mj_inertiaBoxFluidModel: drag of the medium on the equivalent inertia box of body bd. The body's velocity at its com in
   // the inertial frame (ximat), minus the wind; a viscous term linear in it (equivalent sphere) and a quadratic term face by

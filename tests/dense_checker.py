@@ -1112,6 +1112,12 @@ def forward(dm: DenseModel, qpos, qvel, ctrl, qfrc_applied=None, xfrc_applied=No
     f = passive_force(dm, qpos, qvel) - c + fa
     if not dm.dis("passive"):
         f = f + fluid_force(dm, kin)
+        if dm.m.ngravcomp and not dm.dis("gravity"):                      # gravity compensation: a counter-weight force at each body's com
+            gc = np.asarray(dm.m.body_gravcomp, float)
+            for b in range(1, dm.nbody):
+                if gc[b]:
+                    com = kin.P[b] + kin.R[b] @ dm.body_ipos[3 * b:3 * b + 3]
+                    f = f + kin.point_jac(b, com).T @ (-dm.gravity * dm.body_mass[b] * gc[b])
     if qfrc_applied is not None:
         f = f + qfrc_applied
     if xfrc_applied is not None:

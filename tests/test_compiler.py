@@ -85,6 +85,26 @@ def test_settotalmass_boundmass_boundinertia():
     assert np.allclose(m3.body_mass[1:], [0.5, 0.5])
 
 
+def test_attributes_with_an_effect_are_never_silently_ignored():
+    """Everything the schema accepts either acts on the step or is refused with Error::Mjs."""
+    one = '<mujoco>{top}<worldbody><body {b}><joint name="j" {j}/><geom size="0.1" {g}/></body></worldbody>{tail}</mujoco>'
+    cases = [dict(top='<option><flag sensor="disable"/></option>'), dict(top='<option><flag autoreset="disable"/></option>'),
+             dict(top='<option><flag spring="disable"/></option>'), dict(top='<option><flag damper="disable"/></option>'),
+             dict(top='<option><flag invdiscrete="enable"/></option>'), dict(top='<option actuatorgroupdisable="1"/>'),
+             dict(top='<compiler inertiagrouprange="0 1"/>'), dict(top='<compiler balanceinertia="true"/>'),
+             dict(top='<statistic meaninertia="2"/>'), dict(j='springdamper="0.1 1"'), dict(j='actuatorfrclimited="true"'),
+             dict(j='actuatorgravcomp="true"'), dict(g='shellinertia="true"'),
+             dict(j='range="-1 1"', tail='<actuator><position joint="j" inheritrange="1"/></actuator>'),
+             dict(tail='<sensor><jointpos joint="j" cutoff="0.5"/></sensor>')]
+    for c in cases:
+        xml = one.format(top=c.get("top", ""), b=c.get("b", ""), j=c.get("j", ""), g=c.get("g", ""), tail=c.get("tail", ""))
+        with pytest.raises(ox.MjsError, match="outside the supported subset"):
+            ox.Model.from_xml_string(xml)
+    ok = one.format(top='<option><flag midphase="disable" nativeccd="disable"/></option><statistic extent="2"/>', b="", j='springdamper="0 0"',
+                    g='shellinertia="false"', tail='<sensor><jointpos joint="j" cutoff="0" noise="0.1"/></sensor>')
+    assert ox.Model.from_xml_string(ok).nsensor == 1                                # no effect on the step in the subset: accepted
+
+
 def test_topology_tables_of_the_benchmark_models():
     m = ox.Model.from_xml_string(ox.models.CHEETAH)
     assert (m.nq, m.nv, m.nu, m.nbody, m.ngeom, m.nM) == (9, 9, 6, 8, 9, 36)

@@ -1,4 +1,4 @@
-"""Fluid forces of mj_passive (mjOption density / viscosity / wind, MuJoCo's inertia-box model) on the path of
+"""Fluid forces of mj_passive (mjOption density / viscosity / wind, MuJoCo's inertia-box model) and body gravcomp on the path of
 Physics::step (reference src/physics.rs:44-46): compiler table, closed forms for the oracle, refusals, and - with zoo_r -
 the host instantiation of the stage templates and (GPU) every kernel family against the oracle. tests/test_golden.py pins
 the oracle on zoo_r against the dense checker, which derives the same forces from body velocities and exact Jacobians."""
@@ -84,6 +84,32 @@ def test_flag_and_refusals():
         ox.Model.from_xml_string(BOX.format(rho=5, mu=0, wind="0 0 0", g=0).replace('density="500"', 'density="500" fluidshape="ellipsoid"'))
     with pytest.raises(ox.Error, match="density"):
         ox.Model.from_xml_string(BOX.format(rho=-1, mu=0, wind="0 0 0", g=0))
+
+
+def test_gravcomp_closed_forms():
+    """body gravcomp = c adds -c * m * gravity at the body's com (mj_passive): c = 1 hovers, 0.5 halves the fall, 2 rises; a chain
+    whose bodies are all fully compensated is in equilibrium in every pose; the gravity and passive flags switch it off."""
+    free = '<mujoco><option {o}/><worldbody><body pos="0 0 1" gravcomp="{c}"><freejoint/><geom type="box" size="0.1 0.2 0.3"/></body></worldbody></mujoco>'
+    for c, az in ((1, 0.0), (0.5, -4.905), (2, 9.81), (0, -9.81)):
+        m = ox.Model.from_xml_string(free.format(o='gravity="0 0 -9.81"', c=c))
+        assert m.ngravcomp == (m.nbody if c else 0)
+        od = OracleData(m); od.forward()
+        assert np.allclose(od.field("qacc"), [0, 0, az, 0, 0, 0], atol=1e-12)
+    m = ox.Model.from_xml_string(free.format(o='gravity="1 2 -9.81"', c=1).replace("/><worldbody>", '><flag passive="disable"/></option><worldbody>'))
+    od = OracleData(m); od.forward()
+    assert np.allclose(od.field("qacc")[:3], [1, 2, -9.81], atol=1e-12)
+    chain = """<mujoco><worldbody><body pos="0 0 1" gravcomp="1"><joint axis="0 1 0"/><geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.03"/>
+    <body pos="0.4 0 0" gravcomp="1"><joint type="ball"/><geom type="capsule" fromto="0 0 0 0.2 0.1 0.1" size="0.02"/>
+    <body pos="0.2 0.1 0.1" gravcomp="{c}"><joint type="slide" axis="1 1 0"/><geom size="0.05"/></body></body></body></worldbody></mujoco>"""
+    m = ox.Model.from_xml_string(chain.format(c=1))
+    qpos, _ = random_state(m, 3, seed=5)
+    for e in range(3):
+        od = OracleData(m); od.field("qpos")[:] = qpos[e]; od.forward()
+        assert np.abs(od.field("qacc")).max() < 1e-10 and np.abs(od.field("qfrc_bias")).max() > 0.1
+        assert np.allclose(od.field("qfrc_passive"), od.field("qfrc_bias"), atol=1e-12)
+    m = ox.Model.from_xml_string(chain.format(c=0))                                 # the last body uncompensated: it alone pulls
+    od = OracleData(m); od.field("qpos")[:] = qpos[0]; od.forward()
+    assert np.abs(od.field("qacc")).max() > 0.1
 
 
 def test_swimmer_is_propelled_by_the_medium():

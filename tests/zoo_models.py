@@ -509,7 +509,8 @@ ZOO_Q = """
 """
 
 # mj_passive fluid forces (inertia-box model): a three-link swimmer on planar root joints (dm_control swimmer's structure) in a
-# dense, viscous medium with wind, next to a tumbling free plate that falls to the floor and a resting pebble
+# dense, viscous medium with wind, next to a tumbling free plate that falls to the floor and a resting pebble; body gravcomp: a
+# neutrally buoyant float and a half-compensated tail segment (its hinge is tilted so that gravity has a moment about it)
 ZOO_R = """
 <mujoco model="zoo_r">
   <compiler angle="radian"/>
@@ -525,15 +526,15 @@ ZOO_R = """
       <body name="seg1" pos="-0.2 0 0">
         <joint name="j1" type="hinge" axis="0 0 1" range="-1.6 1.6" limited="true"/>
         <geom name="seg1" type="box" pos="-0.1 0 0" size="0.1 0.015 0.04" density="1000"/>
-        <body name="seg2" pos="-0.2 0 0">
-          <joint name="j2" type="hinge" axis="0 0 1" range="-1.6 1.6" limited="true"/>
+        <body name="seg2" pos="-0.2 0 0" gravcomp="0.5">
+          <joint name="j2" type="hinge" axis="0.1 0 1" range="-1.6 1.6" limited="true"/>
           <geom name="seg2" type="capsule" fromto="0 0 0 -0.2 0 0" size="0.025" density="1000"/>
           <site name="tail" pos="-0.2 0 0"/>
         </body>
       </body>
     </body>
     <body name="plate" pos="0.7 0.3 0.35" euler="0.4 0.2 0.1"><freejoint/><geom name="plate" type="box" size="0.15 0.1 0.01" density="1500"/></body>
-    <body name="float" pos="-0.5 -0.6 0.5"><freejoint/><geom name="float" type="sphere" size="0.06" density="300"/></body>
+    <body name="float" pos="-0.5 -0.6 0.5" gravcomp="1"><freejoint/><geom name="float" type="sphere" size="0.06" density="300"/></body>
     <body name="pebble" pos="0.8 -0.7 0.0495"><freejoint name="pebbleroot"/><geom name="pebble" type="sphere" size="0.05" density="9000"/></body>
   </worldbody>
   <actuator><motor joint="j1" gear="0.8"/><motor joint="j2" gear="0.8"/></actuator>
