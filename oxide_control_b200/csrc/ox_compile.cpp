@@ -1201,6 +1201,10 @@ ox_model* compile_mjcf(const std::string& xml) {
         if (a.has("inheritrange") && a.num("inheritrange", 0) != 0) cfail("actuator '" + ad.name + "': inheritrange is outside the supported subset (give ctrlrange)");
         if (a.has("actdim") || a.has("actearly")) cfail("actuator '" + ad.name + "': actdim / actearly are outside the supported subset");
         a.vec("dynprm", ad.dynprm, 3, true);
+        if (e->name == "position" && a.num("timeconst", 0) > 0) {   // <position timeconst>: first-order filter on the target, exact integration
+          ad.dyntype = OX_DYN_FILTEREXACT;
+          ad.dynprm[0] = a.num("timeconst", 0);
+        }
         {
           const bool has_ar = a.has("actrange");
           if (has_ar) a.vec("actrange", ad.actrange, 2);
@@ -1211,7 +1215,8 @@ ox_model* compile_mjcf(const std::string& xml) {
         }
         if (e->name == "position") {
           double kp = a.num("kp", 1), kv = a.num("kv", 0);
-          if (a.has("dampratio") || a.has("timeconst")) cfail("actuator '" + ad.name + "': dampratio/timeconst are outside the supported subset");
+          if (a.num("timeconst", 0) < 0) cfail("actuator '" + ad.name + "': timeconst must be >= 0");
+          if (a.has("dampratio")) cfail("actuator '" + ad.name + "': dampratio is outside the supported subset (give kv)");
           ad.gainprm[0] = kp; ad.biastype = OX_BIAS_AFFINE; ad.biasprm[1] = -kp; ad.biasprm[2] = -kv;
         } else if (e->name == "velocity") {
           double kv = a.num("kv", 1);

@@ -200,3 +200,25 @@ def test_ball_joint_limit_closed_form():
         od.step()
     q = od.field("qpos")
     assert 2 * np.arctan2(np.linalg.norm(q[1:]), q[0]) < 0.52
+
+
+def test_position_timeconst_is_a_filterexact_activation():
+    """<position timeconst="T">: the target passes a first-order filter integrated exactly (dyntype filterexact, dynprm[0] = T);
+    the force is kp (act - q) - kv v with the filtered target act."""
+    xml = """<mujoco><option timestep="0.001" gravity="0 0 0"/><worldbody><body><joint name="j" type="slide" axis="1 0 0"/>
+    <geom size="0.1" mass="1"/></body></worldbody><actuator><position joint="j" kp="10" kv="0.5" timeconst="0.05"/></actuator></mujoco>"""
+    m = ox.Model.from_xml_string(xml)
+    assert m.na == 1 and int(m.actuator_dyntype[0]) == 3 and m.actuator_dynprm[0] == 0.05
+    od = OracleData(m)
+    od.field("ctrl")[:] = 1.0
+    od.field("qpos")[:] = 0.2; od.field("qvel")[:] = 0.3
+    od.forward()
+    assert abs(od.field("actuator_force")[0] - (10 * (0.0 - 0.2) - 0.5 * 0.3)) < 1e-14        # act = 0 at the start
+    for _ in range(100):
+        od.step()
+    assert abs(od.field("act")[0] - (1 - np.exp(-0.1 / 0.05))) < 1e-12                         # exact, not Euler
+    od.forward()
+    q, v, act = od.field("qpos")[0], od.field("qvel")[0], od.field("act")[0]
+    assert abs(od.field("actuator_force")[0] - (10 * (act - q) - 0.5 * v)) < 1e-13
+    with pytest.raises(ox.MjsError, match="dampratio"):
+        ox.Model.from_xml_string(xml.replace('timeconst="0.05"', 'dampratio="1"').replace('kv="0.5"', ""))
